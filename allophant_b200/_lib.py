@@ -1,0 +1,94 @@
+"""ctypes binding of ``liballophant_b200.so`` (the C ABI in ``include/allophant_b200.h``).
+
+The shared library is the product: there is no Python/torch fallback for any
+entry point.  Importing this module on a machine without the built library
+raises immediately; calling a compute entry point without a GPU fails inside
+CUDA and is reported as ``RuntimeError`` with the library's own message.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liballophant_b200.so")
+
+APH_OK = 0
+APH_ERR_INVALID = -1
+APH_ERR_CUDA = -2
+APH_ERR_UNSUPPORTED = -3
+
+APH_GEMM_ROWS = 0
+APH_GEMM_TAPS = 1
+APH_EPI_STORE = 0
+APH_EPI_QKV = 1
+
+
+class GemmArgs(Structure):
+    """Mirror of ``aph_gemm_args``."""
+
+    _fields_ = [
+        ("a", c_void_p),
+        ("a_row_stride", c_int64),
+        ("a_batch_stride", c_int64),
+        ("a_rows", c_int32),
+        ("a_inner", c_int32),
+        ("batch", c_int32),
+        ("mode", c_int32),
+        ("tap_pad", c_int32),
+        ("b", c_void_p),
+        ("n", c_int32),
+        ("k", c_int32),
+        ("epilogue", c_int32),
+        ("gelu", c_int32),
+        ("scale", c_float),
+        ("bias", c_void_p),
+        ("resid", c_void_p),
+        ("ld_resid", c_int64),
+        ("out_f32", c_void_p),
+        ("ld_f32", c_int64),
+        ("out_bf16", c_void_p),
+        ("ld_bf16", c_int64),
+        ("out_batch_rows", c_int64),
+        ("lengths", c_void_p),
+        ("len_period", c_int32),
+        ("q", c_void_p),
+        ("kmat", c_void_p),
+        ("vt", c_void_p),
+        ("heads", c_int32),
+        ("t_v", c_int32),
+        ("q_scale", c_float),
+    ]
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make -C allophant_b200/csrc` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "allophant_b200 has no CPU or PyTorch fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.aph_abi_version.restype = c_int
+    lib.aph_last_error.restype = c_char_p
+    lib.aph_launch_count.restype = c_int64
+    lib.aph_reset_launch_count.restype = None
+    lib.aph_gemm_bf16.argtypes = [POINTER(GemmArgs), c_void_p]
+    lib.aph_gemm_bf16.restype = c_int
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int, what: str) -> None:
+    """Turns a negative APH_ERR_* code into the exception type the reference raises."""
+    if rc == APH_OK:
+        return
+    message = f"{what}: {lib.aph_last_error().decode(errors='replace')} (code {rc})"
+    if rc == APH_ERR_INVALID:
+        raise ValueError(message)
+    if rc == APH_ERR_UNSUPPORTED:
+        raise NotImplementedError(message)
+    raise RuntimeError(message)

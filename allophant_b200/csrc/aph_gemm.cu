@@ -1,0 +1,420 @@
+// allophant_b200 — persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+// D[m, n] = sum_k A[m, k] * B[n, k]  (A, B bf16 K-major; fp32 accumulators in TMEM)
+//
+// Roles inside one 192-thread CTA (one CTA per SM, persistent over output tiles):
+//   warp 0      TMA producer: A tile 128x64 + B tile BNx64 per stage, 128B swizzle
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16)
+//   warps 2..5  epilogue: tcgen05.ld the accumulator (one TMEM lane quadrant each),
+//               bias / GELU / residual / padding mask, vectorised global stores
+// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM double buffer tfull/tempty
+// (MMA <-> epilogue) so the epilogue of tile i overlaps the mainloop of tile i+1.
+//
+// The A operand is always fetched through a rank-3 tensor map
+// [batch][rows][inner] whose row stride is free, which gives three uses:
+//   plain Linear            row stride = K
+//   strided Conv1d (HF:281) channels-last input, row stride = conv_stride*C and
+//                           inner = kernel*C: output position t reads the
+//                           contiguous window starting at sample t*stride — the
+//                           rows overlap, no im2col buffer exists
+//   grouped pos-conv (HF:326) "taps" mode: k-block j reads rows t - pad + j of
+//                           channel group n/64 (zero-filled outside [0, rows))
+#include "aph_common.cuh"
+
+namespace aph {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kGemmThreads = 192;
+constexpr int kSmemBudget = 200 * 1024;
+
+struct GemmParams {
+  int m_tiles_per_batch;
+  int batch;
+  int n_tiles;
+  int k_blocks;
+  int a_rows;
+  int mode;
+  int tap_pad;
+  int n;
+  int gelu;
+  float scale;
+  const float* bias;
+  const float* resid;
+  long long ld_resid;
+  float* out_f32;
+  long long ld_f32;
+  __nv_bfloat16* out_bf16;
+  long long ld_bf16;
+  long long out_batch_rows;
+  const int* lengths;
+  int len_period;
+  __nv_bfloat16* q;
+  __nv_bfloat16* kmat;
+  __nv_bfloat16* vt;
+  int heads;
+  int t_v;
+  float q_scale;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
+  static constexpr int kTmemCols = 2 * BN;  // double-buffered accumulator
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+    gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                     const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_m = p.m_tiles_per_batch * p.batch;
+  const int total_tiles = tiles_m * p.n_tiles;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.n_tiles;
+        const int mt = tile / p.n_tiles;
+        const int b = mt / p.m_tiles_per_batch;
+        const int t0 = (mt % p.m_tiles_per_batch) * kBM;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (p.mode == APH_GEMM_TAPS) {
+            tma_load_3d(sa, &tm_a, &full_bar[stage], n_blk * kBK, t0 - p.tap_pad + kb, b);
+          } else {
+            tma_load_3d(sa, &tm_a, &full_bar[stage], kb * kBK, t0, b);
+          }
+          tma_load_2d(sb, &tm_b, &full_bar[stage], kb * kBK, n_blk * BN);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t da = umma_desc_sw128(sa);
+          const uint64_t db = umma_desc_sw128(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // +32 bytes along K inside the 128B swizzle atom = +2 in the encoded address
+            umma_bf16(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
+                      idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps, 128 rows) =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int r = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.n_tiles;
+      const int mt = tile / p.n_tiles;
+      const int b = mt / p.m_tiles_per_batch;
+      const int t = (mt % p.m_tiles_per_batch) * kBM + r;
+      const bool row_ok = t < p.a_rows;
+      const long long grow = static_cast<long long>(b) * p.out_batch_rows + t;
+      bool masked = false;
+      int utt = 0, tt = 0;
+      if (p.len_period > 0) {
+        utt = static_cast<int>(grow / p.len_period);
+        tt = static_cast<int>(grow - static_cast<long long>(utt) * p.len_period);
+        if (p.lengths != nullptr && row_ok) masked = tt >= p.lengths[utt];
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr0 =
+          tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int col = n_blk * BN + c0;
+        if (col >= p.n) break;  // warp-uniform
+        float v[32];
+        tmem_ld32(taddr0 + static_cast<uint32_t>(c0), v);
+        tmem_ld_wait();
+        if (EPI == APH_EPI_QKV) {
+          const int hidden = p.heads * 64;
+          const int which = col / hidden;
+          const int hc = col - which * hidden;
+          const int h = hc >> 6;
+          const int d0 = hc & 63;
+          const float sc = which == 0 ? p.q_scale : 1.0f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = (v[j] + __ldg(p.bias + col + j)) * sc;
+          if (row_ok) {
+            const long long bh = static_cast<long long>(utt) * p.heads + h;
+            if (which < 2) {
+              __nv_bfloat16* dst = (which == 0 ? p.q : p.kmat) + (bh * p.len_period + tt) * 64 + d0;
+              uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 o;
+                o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                d4[j] = o;
+              }
+            } else {
+              __nv_bfloat16* dst = p.vt + (bh * 64 + d0) * p.t_v + tt;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.t_v] = __float2bfloat16(v[j]);
+            }
+          }
+        } else {
+          const bool full_chunk = col + 32 <= p.n;
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = fmaf(v[j], p.scale, (full_chunk || col + j < p.n) ? __ldg(p.bias + col + j) : 0.f);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= p.scale;
+          }
+          if (p.gelu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          }
+          if (row_ok) {
+            if (p.resid != nullptr) {
+              const float4* rs = reinterpret_cast<const float4*>(p.resid + grow * p.ld_resid + col);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (full_chunk || col + 4 * j + 4 <= p.n) {
+                  const float4 rv = rs[j];
+                  v[4 * j + 0] += rv.x;
+                  v[4 * j + 1] += rv.y;
+                  v[4 * j + 2] += rv.z;
+                  v[4 * j + 3] += rv.w;
+                }
+              }
+            }
+            if (masked) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+            if (p.out_f32 != nullptr) {
+              float4* d4 = reinterpret_cast<float4*>(p.out_f32 + grow * p.ld_f32 + col);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (full_chunk || col + 4 * j + 4 <= p.n)
+                  d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              }
+            }
+            if (p.out_bf16 != nullptr) {
+              uint4* d4 = reinterpret_cast<uint4*>(p.out_bf16 + grow * p.ld_bf16 + col);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (full_chunk || col + 8 * j + 8 <= p.n) {
+                  uint4 o;
+                  o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                  o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                  o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                  o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                  d4[j] = o;
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN, int EPI>
+static int launch_gemm(const aph_gemm_args* a, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap tm_a, tm_b;
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(a->a_inner), static_cast<uint64_t>(a->a_rows),
+                              static_cast<uint64_t>(a->batch)};
+    uint64_t batch_stride = static_cast<uint64_t>(a->a_batch_stride) * 2;
+    if (a->batch == 1 && batch_stride == 0) batch_stride = static_cast<uint64_t>(a->a_row_stride) * 2;
+    const uint64_t strides[2] = {static_cast<uint64_t>(a->a_row_stride) * 2, batch_stride};
+    const uint32_t box[3] = {kBK, kBM, 1};
+    int rc = encode_tmap(&tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->a, dims, strides, box,
+                         CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != APH_OK) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(a->k), static_cast<uint64_t>(a->n)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(a->k) * 2};
+    const uint32_t box[2] = {kBK, static_cast<uint32_t>(BN)};
+    int rc = encode_tmap(&tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->b, dims, strides, box,
+                         CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != APH_OK) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    APH_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int total_tiles = p.m_tiles_per_batch * p.batch * p.n_tiles;
+  const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
+  gemm_bf16_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, p);
+  APH_POST_LAUNCH(1);
+  return APH_OK;
+}
+
+}  // namespace aph
+
+extern "C" int aph_gemm_bf16(const aph_gemm_args* a, void* stream_) {
+  using namespace aph;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  APH_REQUIRE(a != nullptr, "null args");
+  APH_REQUIRE(a->a != nullptr && a->b != nullptr, "null operand");
+  APH_REQUIRE(a->k > 0 && a->k % kBK == 0, "k must be a positive multiple of 64");
+  APH_REQUIRE(a->n > 0 && a->n % 8 == 0, "n must be a positive multiple of 8");
+  APH_REQUIRE(a->a_rows > 0 && a->batch > 0, "empty A");
+  APH_REQUIRE(a->a_row_stride % 8 == 0 && a->a_batch_stride % 8 == 0, "A strides must be multiples of 8 elements");
+  APH_REQUIRE((reinterpret_cast<uintptr_t>(a->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->b) & 15) == 0,
+              "operands must be 16-byte aligned");
+  APH_REQUIRE(a->mode == APH_GEMM_ROWS || a->mode == APH_GEMM_TAPS, "bad mode");
+
+  GemmParams p;
+  p.m_tiles_per_batch = ceil_div(a->a_rows, kBM);
+  p.batch = a->batch;
+  p.k_blocks = a->k / kBK;
+  p.a_rows = a->a_rows;
+  p.mode = a->mode;
+  p.tap_pad = a->tap_pad;
+  p.n = a->n;
+  p.gelu = a->gelu;
+  p.scale = a->scale;
+  p.bias = a->bias;
+  p.resid = a->resid;
+  p.ld_resid = a->ld_resid;
+  p.out_f32 = a->out_f32;
+  p.ld_f32 = a->ld_f32;
+  p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16);
+  p.ld_bf16 = a->ld_bf16;
+  p.out_batch_rows = a->out_batch_rows;
+  p.lengths = a->lengths;
+  p.len_period = a->len_period;
+  p.q = static_cast<__nv_bfloat16*>(a->q);
+  p.kmat = static_cast<__nv_bfloat16*>(a->kmat);
+  p.vt = static_cast<__nv_bfloat16*>(a->vt);
+  p.heads = a->heads;
+  p.t_v = a->t_v;
+  p.q_scale = a->q_scale;
+
+  if (a->mode == APH_GEMM_TAPS) {
+    // one 64-channel group per N tile; k-block j is tap j of that group
+    APH_REQUIRE(a->n % 64 == 0 && a->a_inner == a->n, "taps mode: n == channels, multiple of 64");
+    APH_REQUIRE(a->epilogue == APH_EPI_STORE, "taps mode supports the store epilogue only");
+    p.n_tiles = a->n / 64;
+    return launch_gemm<64, APH_EPI_STORE>(a, p, stream);
+  }
+  APH_REQUIRE(a->a_inner >= a->k, "A rows shorter than k");
+
+  if (a->epilogue == APH_EPI_QKV) {
+    APH_REQUIRE(a->q && a->kmat && a->vt && a->bias, "qkv epilogue needs q/k/vt/bias");
+    APH_REQUIRE(a->heads > 0 && a->n == 3 * a->heads * 64, "qkv epilogue: n == 3*heads*64");
+    APH_REQUIRE(a->len_period > 0 && a->t_v % 8 == 0 && a->t_v >= a->len_period, "qkv epilogue: bad lengths");
+    APH_REQUIRE((a->heads * 64) % 256 == 0, "qkv epilogue: hidden must be a multiple of 256");
+    p.n_tiles = ceil_div(a->n, 256);
+    return launch_gemm<256, APH_EPI_QKV>(a, p, stream);
+  }
+  APH_REQUIRE(a->epilogue == APH_EPI_STORE, "bad epilogue");
+  APH_REQUIRE(a->out_f32 || a->out_bf16, "no output");
+  APH_REQUIRE(!a->out_f32 || (a->ld_f32 % 4 == 0 && (reinterpret_cast<uintptr_t>(a->out_f32) & 15) == 0),
+              "fp32 output must be 16-byte aligned with ld % 4 == 0");
+  APH_REQUIRE(!a->out_bf16 || (a->ld_bf16 % 8 == 0 && (reinterpret_cast<uintptr_t>(a->out_bf16) & 15) == 0),
+              "bf16 output must be 16-byte aligned with ld % 8 == 0");
+  APH_REQUIRE(!a->resid || (a->ld_resid % 4 == 0 && (reinterpret_cast<uintptr_t>(a->resid) & 15) == 0),
+              "residual must be 16-byte aligned with ld % 4 == 0");
+  APH_REQUIRE(!a->lengths || a->len_period > 0, "lengths need len_period");
+  if (a->n > 128) {
+    p.n_tiles = ceil_div(a->n, 256);
+    return launch_gemm<256, APH_EPI_STORE>(a, p, stream);
+  } else if (a->n > 64) {
+    p.n_tiles = 1;
+    return launch_gemm<128, APH_EPI_STORE>(a, p, stream);
+  }
+  p.n_tiles = 1;
+  return launch_gemm<64, APH_EPI_STORE>(a, p, stream);
+}
