@@ -76,6 +76,9 @@ def _load() -> ctypes.CDLL:
     lib.aph_reset_launch_count.restype = None
     lib.aph_gemm_bf16.argtypes = [POINTER(GemmArgs), c_void_p]
     lib.aph_gemm_bf16.restype = c_int
+    lib.aph_attention_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_int32, c_int32, c_int32, c_int32, c_void_p]
+    lib.aph_attention_bf16.restype = c_int
     return lib
 
 

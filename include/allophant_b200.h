@@ -96,6 +96,18 @@ typedef struct aph_gemm_args {
 
 int aph_gemm_bf16(const aph_gemm_args* args, void* stream);
 
+/* ---- variable-length self-attention (tcgen05, flash-style online softmax) --- */
+/* Replaces the SDPA call of Wav2Vec2Attention (HF:466-549) and the dense
+ * additive mask of HF:758-762: keys t >= lengths[b] get probability 0.
+ *   q, k : bf16 [n_utt*heads][T][64]   (q already scaled by head_dim^-0.5)
+ *   vt   : bf16 [n_utt*heads][64][t_v] (V transposed, keys contiguous, t_v % 8 == 0,
+ *          columns [T, t_v) must be finite)
+ *   ctx  : bf16 [n_utt*T][heads*64]    rows of padded query tiles are left untouched
+ */
+int aph_attention_bf16(const void* q, const void* k, const void* vt, void* ctx,
+                       const int32_t* lengths, int32_t n_utt, int32_t heads, int32_t T,
+                       int32_t t_v, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
