@@ -62,6 +62,58 @@ class GemmArgs(Structure):
     ]
 
 
+class CtcHead(Structure):
+    """Mirror of ``aph_ctc_head``."""
+
+    _fields_ = [
+        ("log_probs", c_void_p),
+        ("grad", c_void_p),
+        ("stride_t", c_int64),
+        ("stride_n", c_int64),
+        ("n_classes", c_int32),
+        ("s_pad", c_int32),
+        ("labels", c_void_p),
+        ("label_stride", c_int64),
+        ("label_lengths", c_void_p),
+        ("alpha_offset", c_int64),
+    ]
+
+
+_P = c_void_p
+_I32 = c_int32
+_I64 = c_int64
+_F = c_float
+
+# name -> argtypes; every function returns int (APH_OK or a negative APH_ERR_* code)
+_SIGNATURES = {
+    "aph_gemm_bf16": [POINTER(GemmArgs), _P],
+    "aph_attention_bf16": [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
+    "aph_wave_stats": [_P, _P, _I32, _I32, _P, _P, _P],
+    "aph_wave_norm": [_P, _P, _P, _I32, _I32, _P, _P],
+    "aph_frame_lengths": [_P, _I32, _P, _P, _I32, _P, _P, _P],
+    "aph_conv0_ln_gelu": [_P, _P, _P, _I32, _I32, _P, _P, _P, _P, _F, _I32, _P, _P],
+    "aph_conv0_gn_gelu": [_P, _P, _P, _I32, _I32, _P, _P, _P, _P, _F, _P, _P, _P, _P],
+    "aph_layernorm_rows": [_P, _I32, _I64, _I64, _I32, _P, _P, _F, _I32, _P, _I64, _P, _I64, _P],
+    "aph_compose_embeddings": [_P, _I32, _I32, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P],
+    "aph_log_softmax_heads": [_P, _I64, _I64, _I32, _I32, _P, _P, _P, _I32, _P, _P, _P, _P],
+    "aph_log_softmax_wide": [_P, _I64, _I64, _I32, _P, _I64, _P, _P, _P],
+    "aph_dependency_softmax": [_P, _I64, _I64, _P, _P, _P, _I32, _I32, _P, _I64, _P],
+    "aph_argmax_rows": [_P, _I64, _I64, _I32, _P, _P, _P],
+    "aph_ctc_greedy_collapse": [_P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
+    "aph_cast_bf16": [_P, _P, _I64, _P],
+    "aph_cast_bf16_2d": [_P, _I64, _P, _I64, _I64, _I32, _P],
+    "aph_pack_conv_weight": [_P, _P, _I32, _I32, _I32, _P],
+    "aph_pack_posconv_weight": [_P, _P, _P, _P, _I32, _I32, _I32, _P],
+    "aph_ctc_states_pad": [_I32],
+    "aph_ctc_forward": [_P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
+    "aph_ctc_backward": [_P, POINTER(CtcHead), _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
+}
+
+EXPORTED_SYMBOLS = sorted(
+    list(_SIGNATURES) + ["aph_abi_version", "aph_last_error", "aph_launch_count", "aph_reset_launch_count"]
+)
+
+
 def _load() -> ctypes.CDLL:
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -74,11 +126,10 @@ def _load() -> ctypes.CDLL:
     lib.aph_last_error.restype = c_char_p
     lib.aph_launch_count.restype = c_int64
     lib.aph_reset_launch_count.restype = None
-    lib.aph_gemm_bf16.argtypes = [POINTER(GemmArgs), c_void_p]
-    lib.aph_gemm_bf16.restype = c_int
-    lib.aph_attention_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                       c_int32, c_int32, c_int32, c_int32, c_void_p]
-    lib.aph_attention_bf16.restype = c_int
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int
     return lib
 
 

@@ -1,0 +1,453 @@
+// allophant_b200 — multi-head CTC loss (forward alpha recursion, backward beta
+// recursion fused with the gradient w.r.t. the LOGITS).
+//
+// Replaces, for ALL classifier heads of a step in one launch each way,
+//   CTCWrapper.forward = nn.CTCLoss(reduction="sum", zero_infinity=True)(log_softmax(logits), ...)
+//   (loss_functions.py:19-27, called per head at estimator.py:721-734 / 645-650)
+// and its autograd backward (estimator.py:738).
+//
+// One warp owns one (utterance, head) pair and walks time sequentially in log
+// space.  The 2S+1 CTC states are distributed over the lanes in contiguous
+// chunks of K states (K = 2..32 by template), so only two values cross lanes
+// per frame (warp shuffles).  Log-probs of narrow heads (<= 32 classes) are
+// staged through shared memory 32 frames at a time with coalesced loads; wide
+// heads gather only the label columns they need.  The blank index is 0
+// (config.py:555 BLANK_OFFSET) and labels are the padded int64 [N, S_max]
+// matrices of LabeledBatch (dataset_processing.py:132-162).
+#include "aph_common.cuh"
+
+namespace aph {
+
+constexpr int kCtcWarps = 4;
+constexpr int kCtcChunk = 32;    // frames staged per shared-memory refill
+constexpr int kCtcSmallC = 32;   // heads up to this many classes use the staged path
+
+__device__ __forceinline__ float lse2(float a, float b) {
+  const float m = fmaxf(a, b);
+  if (m == -INFINITY) return -INFINITY;
+  return m + logf(expf(a - m) + expf(b - m));
+}
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+  const float m = fmaxf(a, fmaxf(b, c));
+  if (m == -INFINITY) return -INFINITY;
+  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+}
+
+struct PairInfo {
+  const float* lp;      // log-probs of this utterance: element (t, k) at lp[t*stride_t + k]
+  float* grad;          // same addressing, or NULL
+  long long stride_t;
+  int c;
+  int T_in;             // valid frames
+  int S;                // label length
+  const int64_t* labels;
+  float* alpha;         // [T][s_pad] workspace for this pair or NULL
+  int s_pad;
+};
+
+__device__ __forceinline__ bool load_pair(const aph_ctc_head* heads, int h, int n, int n_utt, int T,
+                                          const long long* input_lengths, float* alpha_ws, PairInfo& p) {
+  const aph_ctc_head& hd = heads[h];
+  p.lp = hd.log_probs + static_cast<long long>(n) * hd.stride_n;
+  p.grad = hd.grad ? hd.grad + static_cast<long long>(n) * hd.stride_n : nullptr;
+  p.stride_t = hd.stride_t;
+  p.c = hd.n_classes;
+  long long tl = input_lengths[n];
+  p.T_in = static_cast<int>(tl < 0 ? 0 : (tl > T ? T : tl));
+  long long sl = hd.label_lengths[n];
+  p.S = static_cast<int>(sl < 0 ? 0 : sl);
+  p.labels = hd.labels + static_cast<long long>(n) * hd.label_stride;
+  p.s_pad = hd.s_pad;
+  p.alpha = alpha_ws ? alpha_ws + hd.alpha_offset + static_cast<long long>(n) * T * hd.s_pad : nullptr;
+  return true;
+}
+
+// ---------------------------------------------------------------------------
+// forward: alpha recursion, per-pair negative log-likelihood
+// ---------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(kCtcWarps * 32) ctc_alpha_kernel(const aph_ctc_head* __restrict__ heads, int n_heads,
+                                                                   int n_utt, int T,
+                                                                   const long long* __restrict__ input_lengths,
+                                                                   float* __restrict__ alpha_ws,
+                                                                   float* __restrict__ nll_out /*[H][N]*/) {
+  __shared__ float stage[kCtcWarps][kCtcChunk * kCtcSmallC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.x * kCtcWarps + warp;
+  if (pair >= n_heads * n_utt) return;
+  const int h = pair / n_utt, n = pair - h * n_utt;
+  PairInfo p;
+  load_pair(heads, h, n, n_utt, T, input_lengths, alpha_ws, p);
+  const int S2 = 2 * p.S + 1;
+  float* out = nll_out + static_cast<long long>(h) * n_utt + n;
+  if (S2 > 32 * K || p.S > heads[h].label_stride) {  // host guarantees this never happens
+    if (lane == 0) *out = NAN;
+    return;
+  }
+  if (p.T_in == 0) {
+    if (lane == 0) *out = p.S == 0 ? 0.f : INFINITY;
+    return;
+  }
+  // per-lane state metadata
+  int lab[K];
+  bool skip[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    const int s = lane * K + i;
+    int l = 0;
+    bool sk = false;
+    if (s < S2 && (s & 1)) {
+      l = static_cast<int>(p.labels[s >> 1]);
+      if (s >= 3) sk = l != static_cast<int>(p.labels[(s >> 1) - 1]);
+    }
+    lab[i] = l;
+    skip[i] = sk;
+  }
+  const bool small_c = p.c <= kCtcSmallC;
+  float* st = stage[warp];
+  float a[K];
+  float nll = 0.f;
+
+  for (int t0 = 0; t0 < p.T_in; t0 += kCtcChunk) {
+    const int nt = min(kCtcChunk, p.T_in - t0);
+    if (small_c) {
+      __syncwarp();
+      const int total = nt * p.c;
+      if (p.stride_t == p.c) {
+        const float* src = p.lp + static_cast<long long>(t0) * p.stride_t;
+        for (int i = lane; i < total; i += 32) st[i] = __ldg(src + i);
+      } else {
+        for (int i = lane; i < total; i += 32) {
+          const int tt = i / p.c, k = i - tt * p.c;
+          st[i] = __ldg(p.lp + static_cast<long long>(t0 + tt) * p.stride_t + k);
+        }
+      }
+      __syncwarp();
+    }
+    for (int tt = 0; tt < nt; ++tt) {
+      const int t = t0 + tt;
+      float e[K];
+      if (small_c) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) e[i] = st[tt * p.c + lab[i]];
+      } else {
+        const float* row = p.lp + static_cast<long long>(t) * p.stride_t;
+        const float eb = __ldg(row);
+#pragma unroll
+        for (int i = 0; i < K; ++i) e[i] = ((lane * K + i) & 1) ? __ldg(row + lab[i]) : eb;
+      }
+      if (t == 0) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          const int s = lane * K + i;
+          a[i] = (s < 2 && s < S2) ? e[i] : -INFINITY;
+        }
+      } else {
+        const float left1 = __shfl_up_sync(0xffffffffu, a[K - 1], 1);
+        const float left2 = __shfl_up_sync(0xffffffffu, a[K - 2], 1);
+        float prev1 = lane == 0 ? -INFINITY : left1;
+        float prev2 = lane == 0 ? -INFINITY : left2;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          const float cur = a[i];
+          const float v = lse3(cur, prev1, skip[i] ? prev2 : -INFINITY) + e[i];
+          prev2 = prev1;
+          prev1 = cur;
+          a[i] = (lane * K + i) < S2 ? v : -INFINITY;
+        }
+      }
+      if (p.alpha) {
+        float* dst = p.alpha + static_cast<long long>(t) * p.s_pad + lane * K;
+        if (lane * K < p.s_pad) {
+#pragma unroll
+          for (int i = 0; i < K; ++i) dst[i] = a[i];
+        }
+      }
+    }
+  }
+  // nll = -logsumexp(alpha_T-1(S2-1), alpha_T-1(S2-2))
+  float last1 = -INFINITY, last2 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    const int s = lane * K + i;
+    if (s == S2 - 1) last1 = a[i];
+    if (s == S2 - 2) last2 = a[i];
+  }
+  last1 = warp_max(last1);
+  last2 = warp_max(last2);
+  nll = -lse2(last1, last2);
+  if (lane == 0) *out = nll;
+}
+
+// ---------------------------------------------------------------------------
+// backward: beta recursion fused with d(sum of losses)/d(logits)
+//   grad[t][k] = g * ( exp(lp[t][k]) - sum_{s: l'_s = k} exp(alpha_t(s) + beta_t(s) - lp[t][l'_s] + nll) )
+// for t < T_in and finite nll; 0 otherwise (zero_infinity=True).
+// Narrow heads: the class sums are accumulated in shared memory and the whole
+// gradient row is written here.  Wide heads: the row exp(lp)*g was written by
+// ctc_grad_init_kernel and the (few) label columns are corrected with atomics.
+// ---------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(kCtcWarps * 32) ctc_beta_kernel(const aph_ctc_head* __restrict__ heads, int n_heads, int n_utt,
+                                                                  int T, const long long* __restrict__ input_lengths,
+                                                                  const float* __restrict__ alpha_ws,
+                                                                  const float* __restrict__ nll_in /*[H][N]*/,
+                                                                  const float* __restrict__ grad_scale /*[H]*/) {
+  __shared__ float stage[kCtcWarps][kCtcChunk * kCtcSmallC];
+  __shared__ float csum[kCtcWarps][kCtcSmallC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.x * kCtcWarps + warp;
+  if (pair >= n_heads * n_utt) return;
+  const int h = pair / n_utt, n = pair - h * n_utt;
+  PairInfo p;
+  load_pair(heads, h, n, n_utt, T, input_lengths, const_cast<float*>(alpha_ws), p);
+  if (p.grad == nullptr) return;
+  const int S2 = 2 * p.S + 1;
+  const float nll = nll_in[static_cast<long long>(h) * n_utt + n];
+  const float g = grad_scale ? grad_scale[h] : 1.f;
+  const bool small_c = p.c <= kCtcSmallC;
+  const bool dead = !(nll < INFINITY) || S2 > 32 * K;  // inf / nan loss -> zero gradient
+  // frames past the utterance's length (and every frame of a zeroed loss) get zero gradient
+  if (small_c) {
+    const int t_zero_from = dead ? 0 : p.T_in;
+    for (int t = t_zero_from; t < T; ++t)
+      for (int k = lane; k < p.c; k += 32) p.grad[static_cast<long long>(t) * p.stride_t + k] = 0.f;
+  }
+  if (dead || p.T_in == 0) return;
+
+  int lab[K];
+  bool skip[K];  // transition s -> s+2 allowed
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    const int s = lane * K + i;
+    int l = 0;
+    bool sk = false;
+    if (s < S2 && (s & 1)) {
+      l = static_cast<int>(p.labels[s >> 1]);
+      if (s + 2 < S2) sk = l != static_cast<int>(p.labels[(s >> 1) + 1]);
+    }
+    lab[i] = l;
+    skip[i] = sk;
+  }
+  float* st = stage[warp];
+  float* cs = csum[warp];
+  float b[K];
+
+  const int n_chunks = (p.T_in + kCtcChunk - 1) / kCtcChunk;
+  for (int ch = n_chunks - 1; ch >= 0; --ch) {
+    const int t0 = ch * kCtcChunk;
+    const int nt = min(kCtcChunk, p.T_in - t0);
+    if (small_c) {
+      __syncwarp();
+      const int total = nt * p.c;
+      if (p.stride_t == p.c) {
+        const float* src = p.lp + static_cast<long long>(t0) * p.stride_t;
+        for (int i = lane; i < total; i += 32) st[i] = __ldg(src + i);
+      } else {
+        for (int i = lane; i < total; i += 32) {
+          const int tt = i / p.c, k = i - tt * p.c;
+          st[i] = __ldg(p.lp + static_cast<long long>(t0 + tt) * p.stride_t + k);
+        }
+      }
+      __syncwarp();
+    }
+    for (int tt = nt - 1; tt >= 0; --tt) {
+      const int t = t0 + tt;
+      float e[K];
+      if (small_c) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) e[i] = st[tt * p.c + lab[i]];
+      } else {
+        const float* row = p.lp + static_cast<long long>(t) * p.stride_t;
+        const float eb = __ldg(row);
+#pragma unroll
+        for (int i = 0; i < K; ++i) e[i] = ((lane * K + i) & 1) ? __ldg(row + lab[i]) : eb;
+      }
+      if (t == p.T_in - 1) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          const int s = lane * K + i;
+          b[i] = (s < S2 && s >= S2 - 2) ? e[i] : -INFINITY;
+        }
+      } else {
+        const float right1 = __shfl_down_sync(0xffffffffu, b[0], 1);
+        const float right2 = __shfl_down_sync(0xffffffffu, b[1], 1);
+        float next1 = lane == 31 ? -INFINITY : right1;
+        float next2 = lane == 31 ? -INFINITY : right2;
+#pragma unroll
+        for (int i = K - 1; i >= 0; --i) {
+          const float cur = b[i];
+          const float v = lse3(cur, next1, skip[i] ? next2 : -INFINITY) + e[i];
+          next2 = next1;
+          next1 = cur;
+          b[i] = (lane * K + i) < S2 ? v : -INFINITY;
+        }
+      }
+      // occupation probabilities gamma_t(s)
+      const float* arow = p.alpha + static_cast<long long>(t) * p.s_pad + lane * K;
+      float gam[K];
+      float blank_sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        const int s = lane * K + i;
+        float gm = 0.f;
+        if (s < S2) {
+          const float x = arow[i] + b[i] - e[i] + nll;
+          gm = x > -80.f ? expf(x) : 0.f;
+        }
+        gam[i] = gm;
+        if (!(s & 1)) blank_sum += gm;
+      }
+      blank_sum = warp_sum(blank_sum);
+      if (small_c) {
+        if (lane < p.c) cs[lane] = 0.f;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          const int s = lane * K + i;
+          if ((s & 1) && s < S2 && gam[i] != 0.f) atomicAdd(&cs[lab[i]], gam[i]);
+        }
+        __syncwarp();
+        if (lane < p.c) {
+          const float occ = cs[lane] + (lane == 0 ? blank_sum : 0.f);
+          p.grad[static_cast<long long>(t) * p.stride_t + lane] = g * (expf(st[tt * p.c + lane]) - occ);
+        }
+        __syncwarp();
+      } else {
+        float* grow = p.grad + static_cast<long long>(t) * p.stride_t;
+        if (lane == 0) atomicAdd(grow, -g * blank_sum);
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          const int s = lane * K + i;
+          if ((s & 1) && s < S2 && gam[i] != 0.f) atomicAdd(grow + lab[i], -g * gam[i]);
+        }
+      }
+    }
+  }
+}
+
+// wide heads: grad[t][k] = g * exp(lp[t][k]) for valid frames of finite-loss pairs, else 0
+__global__ void __launch_bounds__(256) ctc_grad_init_kernel(const aph_ctc_head* __restrict__ heads, int h, int n_utt, int T,
+                                                            const long long* __restrict__ input_lengths,
+                                                            const float* __restrict__ nll_in,
+                                                            const float* __restrict__ grad_scale) {
+  const aph_ctc_head hd = heads[h];
+  const int n = blockIdx.y;
+  const float nll = nll_in[static_cast<long long>(h) * n_utt + n];
+  const float g = grad_scale ? grad_scale[h] : 1.f;
+  long long tl = input_lengths[n];
+  const int t_in = (nll < INFINITY) ? static_cast<int>(tl < 0 ? 0 : (tl > T ? T : tl)) : 0;
+  const long long total = static_cast<long long>(T) * hd.n_classes;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(i / hd.n_classes);
+    const int k = static_cast<int>(i - static_cast<long long>(t) * hd.n_classes);
+    const long long off = static_cast<long long>(n) * hd.stride_n + static_cast<long long>(t) * hd.stride_t + k;
+    hd.grad[off] = t < t_in ? g * expf(hd.log_probs[off]) : 0.f;
+  }
+}
+
+// per-head sum over the batch with zero_infinity (fixed order -> deterministic)
+__global__ void ctc_reduce_kernel(const float* __restrict__ nll, int n_heads, int n_utt, float* __restrict__ loss_out) {
+  const int h = blockIdx.x;
+  const int lane = threadIdx.x;
+  float s = 0.f;
+  for (int n = lane; n < n_utt; n += 32) {
+    const float v = nll[static_cast<long long>(h) * n_utt + n];
+    if (v < INFINITY) s += v;
+  }
+  s = warp_sum(s);
+  if (lane == 0) loss_out[h] = s;
+}
+
+template <int K>
+static int launch_alpha(const aph_ctc_head* heads, int n_heads, int n_utt, int T, const int64_t* input_lengths, float* alpha_ws,
+                        float* nll, cudaStream_t stream) {
+  const int pairs = n_heads * n_utt;
+  ctc_alpha_kernel<K><<<ceil_div(pairs, kCtcWarps), kCtcWarps * 32, 0, stream>>>(
+      heads, n_heads, n_utt, T, reinterpret_cast<const long long*>(input_lengths), alpha_ws, nll);
+  return APH_OK;
+}
+template <int K>
+static int launch_beta(const aph_ctc_head* heads, int n_heads, int n_utt, int T, const int64_t* input_lengths,
+                       const float* alpha_ws, const float* nll, const float* grad_scale, cudaStream_t stream) {
+  const int pairs = n_heads * n_utt;
+  ctc_beta_kernel<K><<<ceil_div(pairs, kCtcWarps), kCtcWarps * 32, 0, stream>>>(
+      heads, n_heads, n_utt, T, reinterpret_cast<const long long*>(input_lengths), alpha_ws, nll, grad_scale);
+  return APH_OK;
+}
+
+static int pick_k(int max_label_len) {
+  const int states = 2 * max_label_len + 1;
+  for (int k = 2; k <= 32; k *= 2)
+    if (states <= 32 * k) return k;
+  return 0;
+}
+
+}  // namespace aph
+
+using namespace aph;
+
+extern "C" int aph_ctc_states_pad(int32_t max_label_len) {
+  const int k = pick_k(max_label_len);
+  return k == 0 ? APH_ERR_UNSUPPORTED : 32 * k;
+}
+
+extern "C" int aph_ctc_forward(const aph_ctc_head* heads_dev, int32_t n_heads, int32_t n_utt, int32_t T,
+                               int32_t max_label_len, const int64_t* input_lengths, float* alpha_ws, float* nll_out,
+                               float* loss_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  APH_REQUIRE(heads_dev && input_lengths && nll_out, "null pointer");
+  APH_REQUIRE(n_heads > 0 && n_utt > 0 && T > 0, "empty problem");
+  const int k = pick_k(max_label_len);
+  if (k == 0) {
+    set_last_error("aph_ctc_forward", "label sequences longer than 511 are not supported", __FILE__, __LINE__);
+    return APH_ERR_UNSUPPORTED;
+  }
+  switch (k) {
+    case 2: launch_alpha<2>(heads_dev, n_heads, n_utt, T, input_lengths, alpha_ws, nll_out, stream); break;
+    case 4: launch_alpha<4>(heads_dev, n_heads, n_utt, T, input_lengths, alpha_ws, nll_out, stream); break;
+    case 8: launch_alpha<8>(heads_dev, n_heads, n_utt, T, input_lengths, alpha_ws, nll_out, stream); break;
+    case 16: launch_alpha<16>(heads_dev, n_heads, n_utt, T, input_lengths, alpha_ws, nll_out, stream); break;
+    default: launch_alpha<32>(heads_dev, n_heads, n_utt, T, input_lengths, alpha_ws, nll_out, stream); break;
+  }
+  int launched = 1;
+  if (loss_out) {
+    ctc_reduce_kernel<<<n_heads, 32, 0, stream>>>(nll_out, n_heads, n_utt, loss_out);
+    ++launched;
+  }
+  APH_POST_LAUNCH(launched);
+  return APH_OK;
+}
+
+extern "C" int aph_ctc_backward(const aph_ctc_head* heads_dev, const aph_ctc_head* heads_host, int32_t n_heads, int32_t n_utt,
+                                int32_t T, int32_t max_label_len, const int64_t* input_lengths, const float* alpha_ws,
+                                const float* nll, const float* grad_scale, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  APH_REQUIRE(heads_dev && heads_host && input_lengths && alpha_ws && nll, "null pointer");
+  APH_REQUIRE(n_heads > 0 && n_utt > 0 && T > 0, "empty problem");
+  const int k = pick_k(max_label_len);
+  if (k == 0) {
+    set_last_error("aph_ctc_backward", "label sequences longer than 511 are not supported", __FILE__, __LINE__);
+    return APH_ERR_UNSUPPORTED;
+  }
+  int launched = 0;
+  for (int h = 0; h < n_heads; ++h) {
+    if (heads_host[h].n_classes > kCtcSmallC && heads_host[h].grad != nullptr) {
+      long long blocks = (static_cast<long long>(T) * heads_host[h].n_classes + 255) / 256;
+      if (blocks > 64) blocks = 64;
+      ctc_grad_init_kernel<<<dim3(static_cast<unsigned>(blocks), n_utt), 256, 0, stream>>>(
+          heads_dev, h, n_utt, T, reinterpret_cast<const long long*>(input_lengths), nll, grad_scale);
+      ++launched;
+    }
+  }
+  switch (k) {
+    case 2: launch_beta<2>(heads_dev, n_heads, n_utt, T, input_lengths, alpha_ws, nll, grad_scale, stream); break;
+    case 4: launch_beta<4>(heads_dev, n_heads, n_utt, T, input_lengths, alpha_ws, nll, grad_scale, stream); break;
+    case 8: launch_beta<8>(heads_dev, n_heads, n_utt, T, input_lengths, alpha_ws, nll, grad_scale, stream); break;
+    case 16: launch_beta<16>(heads_dev, n_heads, n_utt, T, input_lengths, alpha_ws, nll, grad_scale, stream); break;
+    default: launch_beta<32>(heads_dev, n_heads, n_utt, T, input_lengths, alpha_ws, nll, grad_scale, stream); break;
+  }
+  APH_POST_LAUNCH(launched + 1);
+  return APH_OK;
+}

@@ -1,0 +1,120 @@
+"""``Estimator`` facade (drop-in for the inference surface of ``allophant/estimator.py:931-1126``).
+
+``from_config`` / ``restore`` / ``predict`` / ``save`` keep the reference's signatures and the
+checkpoint dictionary layout (``estimator.py:199-249``) so a checkpoint written by either side
+loads on the other, as far as the pieces in scope go.  The training loop,
+optimizer wrappers and dataset management are the reference's control plane and are not rebuilt.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Tuple, Type, TypeVar, Union
+
+import torch
+from torch import Tensor
+
+from . import __version__
+from .attribute_graph import AttributeGraph, AttributeNode
+from .config import Config, ProjectionEntryConfig
+from .dataset_processing import Batch
+from .loss_functions import LossWrapper
+from .network.acoustic_model import Allophant, Predictions
+from .phonetic_features import PhoneticAttributeIndexer
+from .utils import evaluation
+
+EstimatorCls = TypeVar("EstimatorCls", bound="Estimator")
+
+
+def attribute_graph_from_config(config: Config, attribute_indexer: Any) -> AttributeGraph:
+    """One node per configured classifier, sized by its number of categories (``run.py:212-226``)."""
+    return AttributeGraph(
+        AttributeNode(entry.name, attribute_indexer.size(entry.name), entry.time_layer, list(entry.dependencies))
+        for entry in config.nn.projection.classes
+    )
+
+
+@dataclass
+class Estimator:
+    config: Config
+    feature_size: int
+    sample_rate: int
+    attribute_graph: AttributeGraph
+    model: Allophant
+    loss_functions: Dict[str, LossWrapper]
+    history: List[Any] = field(default_factory=list)
+    epoch: Dict[str, int] = field(default_factory=lambda: {"epoch": 0, "global_step": 0, "step": 0})
+    dataset_meta_data: List[Any] = field(default_factory=list)
+
+    @classmethod
+    def from_config(
+        cls: Type[EstimatorCls],
+        config: Config,
+        feature_size: int,
+        sample_rate: int,
+        attribute_graph: AttributeGraph,
+        attribute_indexer: Optional[PhoneticAttributeIndexer] = None,
+        device: "torch.device | str" = "cuda",
+        load_pretrained_weights: bool = True,
+    ) -> EstimatorCls:
+        model = Allophant.from_config(config.nn, feature_size, sample_rate, attribute_graph, attribute_indexer, load_pretrained_weights)
+        model = model.to(device)
+        return cls(config, feature_size, sample_rate, attribute_graph, model, config.nn.projection.loss_functions())
+
+    @torch.inference_mode()
+    def predict(self, batch: Batch, target_feature_indices: Optional[Tensor] = None, log_probabilities: bool = True) -> Predictions:
+        with evaluation(self.model):
+            if log_probabilities:
+                return self.model.predict_log_probabilities(batch, target_feature_indices)
+            return self.model(batch, target_feature_indices, predict=True)
+
+    def map_allophones(self, phone_logits: Tensor, language_ids: Tensor) -> Tensor:
+        return self.model.map_allophones(phone_logits, language_ids)
+
+    # -- checkpoints --------------------------------------------------------------------------
+    def checkpoint(self, attribute_indexer: Optional[PhoneticAttributeIndexer] = None) -> Dict[str, Any]:
+        return {
+            "config": self.config.dump(),
+            "allophant_version": __version__,
+            "feature_size": self.feature_size,
+            "sample_rate": self.sample_rate,
+            "attribute_graph": self.attribute_graph.state(),
+            "epoch": dict(self.epoch),
+            "phonetic_indexer_state": None if attribute_indexer is None else attribute_indexer.state(),
+            "dataset_meta_data": list(self.dataset_meta_data),
+            "model_state": self.model.state_dict(),
+            "additional": {},
+            "history": list(self.history),
+            "optimization_states": None,
+        }
+
+    def save(self, file: Any, attribute_indexer: Optional[PhoneticAttributeIndexer] = None) -> None:
+        torch.save(self.checkpoint(attribute_indexer), file)
+
+    @classmethod
+    def restore(
+        cls: Type[EstimatorCls],
+        checkpoint: Union[Dict[str, Any], Any],
+        device: "torch.device | str" = "cuda",
+        attribute_indexer: Optional[PhoneticAttributeIndexer] = None,
+        **kwargs: Any,
+    ) -> Tuple[EstimatorCls, PhoneticAttributeIndexer]:
+        """Restores an estimator from a checkpoint dict, a local path or a file object.
+
+        The reference also accepts a Hugging Face model id (``estimator.py:229-249``); there is no
+        network here, so ids are treated as local paths."""
+        if not isinstance(checkpoint, dict):
+            checkpoint = torch.load(checkpoint, map_location=device, weights_only=True)
+        config = Config.load(checkpoint["config"])
+        composition_features = [
+            entry.name for entry in config.nn.projection.classes if entry.name != ProjectionEntryConfig.PHONEME_LAYER
+        ]
+        if attribute_indexer is None:
+            attribute_indexer = PhoneticAttributeIndexer.from_state(checkpoint["phonetic_indexer_state"], composition_features)
+        graph = AttributeGraph.from_state(checkpoint["attribute_graph"])
+        estimator = cls.from_config(
+            config, checkpoint["feature_size"], checkpoint["sample_rate"], graph, attribute_indexer, device, load_pretrained_weights=False
+        )
+        estimator.model.load_state_dict(checkpoint["model_state"])
+        estimator.epoch = dict(checkpoint.get("epoch") or estimator.epoch)
+        estimator.history = list(checkpoint.get("history") or [])
+        return estimator, attribute_indexer

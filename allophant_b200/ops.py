@@ -1,0 +1,517 @@
+"""Tensor-level wrappers over the C ABI (``include/allophant_b200.h``).
+
+Every function takes CUDA tensors, launches on ``torch.cuda.current_stream()`` and
+returns without synchronising.  torch is used for device memory and streams only;
+the arithmetic happens in ``liballophant_b200.so``.  Non-CUDA tensors are rejected:
+there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import CtcHead, GemmArgs, check, lib
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*tensors: Optional[Tensor]) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "allophant_b200 kernels run on CUDA tensors only (no CPU fallback exists); "
+                f"got a tensor on {t.device}"
+            )
+
+
+def launch_count() -> int:
+    return int(lib.aph_launch_count())
+
+
+def reset_launch_count() -> None:
+    lib.aph_reset_launch_count()
+
+
+# --------------------------------------------------------------------------------------
+# GEMM
+# --------------------------------------------------------------------------------------
+def make_gemm_args(
+    a: Tensor,
+    w: Tensor,
+    *,
+    a_rows: int,
+    a_inner: int,
+    a_row_stride: int,
+    batch: int = 1,
+    a_batch_stride: int = 0,
+    k: Optional[int] = None,
+    n: Optional[int] = None,
+    mode: int = _lib.APH_GEMM_ROWS,
+    tap_pad: int = 0,
+    bias: Optional[Tensor] = None,
+    gelu: bool = False,
+    scale: float = 1.0,
+    resid: Optional[Tensor] = None,
+    ld_resid: int = 0,
+    out_f32: Optional[Tensor] = None,
+    ld_f32: int = 0,
+    out_bf16: Optional[Tensor] = None,
+    ld_bf16: int = 0,
+    out_batch_rows: int = 0,
+    lengths: Optional[Tensor] = None,
+    len_period: int = 0,
+) -> GemmArgs:
+    """Builds an ``aph_gemm_args`` (store epilogue).  The caller keeps the tensors alive."""
+    _require_cuda(a, w, bias, resid, out_f32, out_bf16, lengths)
+    g = GemmArgs()
+    g.a = a.data_ptr()
+    g.a_row_stride, g.a_batch_stride = a_row_stride, a_batch_stride
+    g.a_rows, g.a_inner, g.batch = a_rows, a_inner, batch
+    g.mode, g.tap_pad = mode, tap_pad
+    g.b = w.data_ptr()
+    g.n = w.shape[0] if n is None else n
+    g.k = w.shape[1] if k is None else k
+    g.epilogue = _lib.APH_EPI_STORE
+    g.gelu = int(gelu)
+    g.scale = scale
+    g.bias = _ptr(bias)
+    g.resid, g.ld_resid = _ptr(resid), ld_resid
+    g.out_f32, g.ld_f32 = _ptr(out_f32), ld_f32
+    g.out_bf16, g.ld_bf16 = _ptr(out_bf16), ld_bf16
+    g.out_batch_rows = out_batch_rows
+    g.lengths, g.len_period = _ptr(lengths), len_period
+    return g
+
+
+def make_qkv_args(
+    a: Tensor, w_qkv: Tensor, bias_qkv: Tensor, q: Tensor, k: Tensor, vt: Tensor, *, rows: int, seq: int, heads: int, t_v: int
+) -> GemmArgs:
+    _require_cuda(a, w_qkv, bias_qkv, q, k, vt)
+    hidden = heads * 64
+    g = GemmArgs()
+    g.a = a.data_ptr()
+    g.a_row_stride, g.a_batch_stride = a.stride(0), 0
+    g.a_rows, g.a_inner, g.batch = rows, hidden, 1
+    g.mode = _lib.APH_GEMM_ROWS
+    g.b, g.n, g.k = w_qkv.data_ptr(), 3 * hidden, hidden
+    g.epilogue = _lib.APH_EPI_QKV
+    g.scale = 1.0
+    g.bias = bias_qkv.data_ptr()
+    g.len_period = seq
+    g.q, g.kmat, g.vt = q.data_ptr(), k.data_ptr(), vt.data_ptr()
+    g.heads, g.t_v, g.q_scale = heads, t_v, 0.125
+    return g
+
+
+def run_gemm(args: GemmArgs) -> None:
+    check(lib.aph_gemm_bf16(ctypes.byref(args), _stream()), "aph_gemm_bf16")
+
+
+def linear_bf16(
+    x: Tensor,
+    w: Tensor,
+    bias: Optional[Tensor] = None,
+    *,
+    gelu: bool = False,
+    scale: float = 1.0,
+    resid: Optional[Tensor] = None,
+    out_dtype: torch.dtype = torch.bfloat16,
+) -> Tensor:
+    """``act(x @ w.T * scale + bias) (+ resid)`` for 2-D bf16 ``x`` [M, K] and ``w`` [N, K]."""
+    assert x.dim() == 2 and w.dim() == 2 and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    m, k = x.shape
+    n = w.shape[0]
+    out = torch.empty(m, n, device=x.device, dtype=out_dtype)
+    g = make_gemm_args(
+        x,
+        w,
+        a_rows=m,
+        a_inner=k,
+        a_row_stride=x.stride(0),
+        bias=bias,
+        gelu=gelu,
+        scale=scale,
+        resid=resid,
+        ld_resid=resid.stride(0) if resid is not None else 0,
+        out_f32=out if out_dtype == torch.float32 else None,
+        ld_f32=n,
+        out_bf16=out if out_dtype == torch.bfloat16 else None,
+        ld_bf16=n,
+    )
+    run_gemm(g)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# attention
+# --------------------------------------------------------------------------------------
+def attention(q: Tensor, k: Tensor, vt: Tensor, ctx: Tensor, frame_lengths: Tensor, n_utt: int, heads: int, seq: int, t_v: int) -> None:
+    _require_cuda(q, k, vt, ctx, frame_lengths)
+    check(
+        lib.aph_attention_bf16(
+            q.data_ptr(), k.data_ptr(), vt.data_ptr(), ctx.data_ptr(), frame_lengths.data_ptr(), n_utt, heads, seq, t_v, _stream()
+        ),
+        "aph_attention_bf16",
+    )
+
+
+# --------------------------------------------------------------------------------------
+# front end
+# --------------------------------------------------------------------------------------
+def wave_stats(x: Tensor, lengths: Tensor, stats_scratch: Tensor, mean_rstd: Tensor) -> None:
+    _require_cuda(x, lengths, stats_scratch, mean_rstd)
+    n, t = x.shape
+    check(
+        lib.aph_wave_stats(x.data_ptr(), lengths.data_ptr(), n, t, stats_scratch.data_ptr(), mean_rstd.data_ptr(), _stream()),
+        "aph_wave_stats",
+    )
+
+
+def zero_mean_unit_var_norm(features: Tensor, lengths: Tensor) -> Tensor:
+    """``acoustic_model.py:762-767`` on the GPU (materialised; the fused encoder folds this into conv 0)."""
+    _require_cuda(features, lengths)
+    features = features.contiguous().float()
+    lengths = lengths.to(torch.int64).contiguous()
+    n, t = features.shape
+    stats = torch.empty(n, 3, device=features.device, dtype=torch.float64)
+    mean_rstd = torch.empty(n, 2, device=features.device, dtype=torch.float32)
+    wave_stats(features, lengths, stats, mean_rstd)
+    out = torch.empty_like(features)
+    check(
+        lib.aph_wave_norm(features.data_ptr(), lengths.data_ptr(), mean_rstd.data_ptr(), n, t, out.data_ptr(), _stream()),
+        "aph_wave_norm",
+    )
+    return out
+
+
+def frame_lengths(lengths: Tensor, kernels: Tensor, strides: Tensor, frames32: Optional[Tensor], frames64: Optional[Tensor]) -> None:
+    _require_cuda(lengths, kernels, strides, frames32, frames64)
+    check(
+        lib.aph_frame_lengths(
+            lengths.data_ptr(), lengths.numel(), kernels.data_ptr(), strides.data_ptr(), kernels.numel(), _ptr(frames32), _ptr(frames64), _stream()
+        ),
+        "aph_frame_lengths",
+    )
+
+
+def conv0_ln_gelu(
+    x: Tensor,
+    lengths: Optional[Tensor],
+    mean_rstd: Optional[Tensor],
+    w: Tensor,
+    bias: Optional[Tensor],
+    gamma: Tensor,
+    beta: Tensor,
+    eps: float,
+    out: Tensor,
+    skip_padded_frames: bool = True,
+) -> None:
+    _require_cuda(x, lengths, mean_rstd, w, bias, gamma, beta, out)
+    n, t = x.shape
+    check(
+        lib.aph_conv0_ln_gelu(
+            x.data_ptr(), _ptr(lengths), _ptr(mean_rstd), n, t, w.data_ptr(), _ptr(bias), gamma.data_ptr(), beta.data_ptr(), eps, int(skip_padded_frames), out.data_ptr(), _stream()
+        ),
+        "aph_conv0_ln_gelu",
+    )
+
+
+def conv0_gn_gelu(
+    x: Tensor,
+    lengths: Optional[Tensor],
+    mean_rstd: Optional[Tensor],
+    w: Tensor,
+    bias: Optional[Tensor],
+    gamma: Tensor,
+    beta: Tensor,
+    eps: float,
+    raw_scratch: Tensor,
+    stats_scratch: Tensor,
+    out: Tensor,
+) -> None:
+    _require_cuda(x, lengths, mean_rstd, w, bias, gamma, beta, raw_scratch, stats_scratch, out)
+    n, t = x.shape
+    check(
+        lib.aph_conv0_gn_gelu(
+            x.data_ptr(),
+            _ptr(lengths),
+            _ptr(mean_rstd),
+            n,
+            t,
+            w.data_ptr(),
+            _ptr(bias),
+            gamma.data_ptr(),
+            beta.data_ptr(),
+            eps,
+            raw_scratch.data_ptr(),
+            stats_scratch.data_ptr(),
+            out.data_ptr(),
+            _stream(),
+        ),
+        "aph_conv0_gn_gelu",
+    )
+
+
+def layernorm_rows(
+    x: Tensor,
+    rows: int,
+    cols: int,
+    ld_in: int,
+    gamma: Tensor,
+    beta: Tensor,
+    eps: float,
+    *,
+    gelu: bool = False,
+    out_bf16: Optional[Tensor] = None,
+    ld_bf16: int = 0,
+    out_f32: Optional[Tensor] = None,
+    ld_f32: int = 0,
+) -> None:
+    _require_cuda(x, gamma, beta, out_bf16, out_f32)
+    check(
+        lib.aph_layernorm_rows(
+            x.data_ptr(),
+            int(x.dtype == torch.float32),
+            ld_in,
+            rows,
+            cols,
+            gamma.data_ptr(),
+            beta.data_ptr(),
+            eps,
+            int(gelu),
+            _ptr(out_bf16),
+            ld_bf16,
+            _ptr(out_f32),
+            ld_f32,
+            _stream(),
+        ),
+        "aph_layernorm_rows",
+    )
+
+
+# --------------------------------------------------------------------------------------
+# heads
+# --------------------------------------------------------------------------------------
+def compose_embeddings(
+    weight: Tensor, tfi: Tensor, category_offsets: Optional[Tensor], rows_out: int, err_flag: Tensor, *, out_bf16: Optional[Tensor] = None, out_f32: Optional[Tensor] = None
+) -> None:
+    _require_cuda(weight, tfi, category_offsets, err_flag, out_bf16, out_f32)
+    v, f = tfi.shape
+    check(
+        lib.aph_compose_embeddings(
+            weight.data_ptr(), weight.shape[0], weight.shape[1], tfi.data_ptr(), _ptr(category_offsets), v, f, rows_out, _ptr(out_bf16), _ptr(out_f32), err_flag.data_ptr(), _stream()
+        ),
+        "aph_compose_embeddings",
+    )
+
+
+def log_softmax_heads(
+    logits: Tensor,
+    ld: int,
+    rows: int,
+    col_lo: int,
+    col_span: int,
+    col_off: Tensor,
+    width: Tensor,
+    out_off: Tensor,
+    n_heads: int,
+    out: Tensor,
+    argmax_out: Optional[Tensor],
+    maxlp_out: Optional[Tensor],
+) -> None:
+    _require_cuda(logits, col_off, width, out_off, out, argmax_out, maxlp_out)
+    check(
+        lib.aph_log_softmax_heads(
+            logits.data_ptr(), ld, rows, col_lo, col_span, col_off.data_ptr(), width.data_ptr(), out_off.data_ptr(), n_heads, out.data_ptr(), _ptr(argmax_out), _ptr(maxlp_out), _stream()
+        ),
+        "aph_log_softmax_heads",
+    )
+
+
+def log_softmax_wide(logits: Tensor, ld: int, rows: int, width: int, out: Tensor, ld_out: int, argmax_out: Optional[Tensor], maxlp_out: Optional[Tensor]) -> None:
+    _require_cuda(logits, out, argmax_out, maxlp_out)
+    check(
+        lib.aph_log_softmax_wide(logits.data_ptr(), ld, rows, width, out.data_ptr(), ld_out, _ptr(argmax_out), _ptr(maxlp_out), _stream()),
+        "aph_log_softmax_wide",
+    )
+
+
+def log_softmax(x: Tensor) -> Tensor:
+    """``functional.log_softmax(x, -1)`` for an fp32 CUDA tensor of any shape (``acoustic_model.py:1051-1052``)."""
+    _require_cuda(x)
+    width = x.shape[-1]
+    flat = x.float().reshape(-1, width)
+    if flat.stride(-1) != 1 or flat.stride(0) != width:
+        flat = flat.contiguous()
+    out = torch.empty_like(flat)
+    log_softmax_wide(flat, width, flat.shape[0], width, out, width, None, None)
+    return out.view(x.shape)
+
+
+def dependency_softmax(logits: Tensor, ld: int, rows: int, col_off: Tensor, width: Tensor, dst_col: Tensor, n_deps: int, skip: int, dst: Tensor, ld_dst: int) -> None:
+    _require_cuda(logits, col_off, width, dst_col, dst)
+    check(
+        lib.aph_dependency_softmax(logits.data_ptr(), ld, rows, col_off.data_ptr(), width.data_ptr(), dst_col.data_ptr(), n_deps, skip, dst.data_ptr(), ld_dst, _stream()),
+        "aph_dependency_softmax",
+    )
+
+
+def argmax_rows(x: Tensor, ld: int, rows: int, width: int, argmax_out: Tensor, max_out: Tensor) -> None:
+    _require_cuda(x, argmax_out, max_out)
+    check(lib.aph_argmax_rows(x.data_ptr(), ld, rows, width, argmax_out.data_ptr(), max_out.data_ptr(), _stream()), "aph_argmax_rows")
+
+
+def ctc_greedy_collapse(
+    argmax_in: Tensor, maxlp_in: Tensor, frame_lengths32: Tensor, n_utt: int, seq: int, n_seq: int, blank: int
+) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Returns (tokens int32 [n_seq, T], timesteps int32 [n_seq, T], counts int32 [n_seq], scores fp32 [n_seq])."""
+    _require_cuda(argmax_in, maxlp_in, frame_lengths32)
+    dev = argmax_in.device
+    tokens = torch.empty(n_seq, seq, device=dev, dtype=torch.int32)
+    timesteps = torch.empty(n_seq, seq, device=dev, dtype=torch.int32)
+    counts = torch.empty(n_seq, device=dev, dtype=torch.int32)
+    scores = torch.empty(n_seq, device=dev, dtype=torch.float32)
+    check(
+        lib.aph_ctc_greedy_collapse(
+            argmax_in.data_ptr(), maxlp_in.data_ptr(), frame_lengths32.data_ptr(), n_utt, seq, n_seq, blank, tokens.data_ptr(), timesteps.data_ptr(), counts.data_ptr(), scores.data_ptr(), _stream()
+        ),
+        "aph_ctc_greedy_collapse",
+    )
+    return tokens, timesteps, counts, scores
+
+
+# --------------------------------------------------------------------------------------
+# weight packing
+# --------------------------------------------------------------------------------------
+def cast_bf16(src: Tensor, dst: Optional[Tensor] = None) -> Tensor:
+    _require_cuda(src, dst)
+    src = src.detach()
+    if src.dtype != torch.float32 or not src.is_contiguous():
+        src = src.float().contiguous()
+    if dst is None:
+        dst = torch.empty(src.shape, device=src.device, dtype=torch.bfloat16)
+    check(lib.aph_cast_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "aph_cast_bf16")
+    return dst
+
+
+def cast_bf16_2d(src: Tensor, ld_src: int, dst: Tensor, ld_dst: int, rows: int, cols: int) -> None:
+    _require_cuda(src, dst)
+    check(lib.aph_cast_bf16_2d(src.data_ptr(), ld_src, dst.data_ptr(), ld_dst, rows, cols, _stream()), "aph_cast_bf16_2d")
+
+
+def pack_conv_weight(weight: Tensor) -> Tensor:
+    """Conv1d weight [O, C, k] fp32 -> bf16 [O, k*C]."""
+    _require_cuda(weight)
+    w = weight.detach().float().contiguous()
+    o, c, k = w.shape
+    dst = torch.empty(o, k * c, device=w.device, dtype=torch.bfloat16)
+    check(lib.aph_pack_conv_weight(w.data_ptr(), dst.data_ptr(), o, c, k, _stream()), "aph_pack_conv_weight")
+    return dst
+
+
+def pack_posconv_weight(weight_g: Tensor, weight_v: Tensor) -> Tensor:
+    """weight-normed grouped conv weight -> bf16 [O, k*Cg] (tap-major)."""
+    _require_cuda(weight_g, weight_v)
+    g = weight_g.detach().float().contiguous()
+    v = weight_v.detach().float().contiguous()
+    o, cg, k = v.shape
+    dst = torch.empty(o, k * cg, device=v.device, dtype=torch.bfloat16)
+    scratch = torch.empty(k, device=v.device, dtype=torch.float32)
+    check(lib.aph_pack_posconv_weight(g.data_ptr(), v.data_ptr(), dst.data_ptr(), scratch.data_ptr(), o, cg, k, _stream()), "aph_pack_posconv_weight")
+    return dst
+
+
+# --------------------------------------------------------------------------------------
+# CTC
+# --------------------------------------------------------------------------------------
+class CtcProblem:
+    """Device + host copies of the per-head descriptors of one multi-head CTC evaluation."""
+
+    def __init__(
+        self,
+        log_probs: Sequence[Tensor],
+        labels: Sequence[Tensor],
+        label_lengths: Sequence[Tensor],
+        input_lengths: Tensor,
+        batch_first: bool,
+        need_grad: bool,
+    ) -> None:
+        _require_cuda(input_lengths, *log_probs, *labels, *label_lengths)
+        self.n_heads = len(log_probs)
+        first = log_probs[0]
+        self.n_utt = first.shape[0] if batch_first else first.shape[1]
+        self.seq = first.shape[1] if batch_first else first.shape[0]
+        dev = first.device
+        self.input_lengths = input_lengths.to(device=dev, dtype=torch.int64).contiguous()
+        self.max_label_len = max(int(l.shape[1]) if l.dim() == 2 else 0 for l in labels)
+        s_pad = int(lib.aph_ctc_states_pad(self.max_label_len))
+        if s_pad < 0:
+            raise NotImplementedError(f"CTC label sequences longer than 511 are not supported (got {self.max_label_len})")
+        self.s_pad = s_pad
+        self.keep: List[Tensor] = []
+        self.grads: List[Optional[Tensor]] = []
+        heads = (CtcHead * self.n_heads)()
+        alpha_total = 0
+        for h, (lp, lab, lab_len) in enumerate(zip(log_probs, labels, label_lengths)):
+            if lp.dtype != torch.float32 or lp.stride(-1) != 1:
+                raise ValueError("CTC log-probabilities must be fp32 with a contiguous class axis")
+            lab = lab.to(device=dev, dtype=torch.int64)
+            if lab.dim() != 2:
+                raise ValueError("CTC labels must be a padded [N, S_max] matrix")
+            if lab.shape[1] == 0:
+                lab = torch.zeros(self.n_utt, 1, device=dev, dtype=torch.int64)
+            lab = lab.contiguous()
+            lab_len = lab_len.to(device=dev, dtype=torch.int64).contiguous()
+            grad = torch.empty_like(lp, memory_format=torch.preserve_format) if need_grad else None
+            if grad is not None and grad.stride() != lp.stride():
+                grad = torch.empty_strided(lp.shape, lp.stride(), device=dev, dtype=lp.dtype)
+            self.keep += [lp, lab, lab_len]
+            self.grads.append(grad)
+            hd = heads[h]
+            hd.log_probs = lp.data_ptr()
+            hd.grad = _ptr(grad)
+            hd.stride_n, hd.stride_t = (lp.stride(0), lp.stride(1)) if batch_first else (lp.stride(1), lp.stride(0))
+            hd.n_classes = lp.shape[2]
+            hd.s_pad = s_pad
+            hd.labels = lab.data_ptr()
+            hd.label_stride = lab.stride(0)
+            hd.label_lengths = lab_len.data_ptr()
+            hd.alpha_offset = alpha_total
+            alpha_total += self.n_utt * self.seq * s_pad
+        self.heads_host = heads
+        raw = torch.frombuffer(bytearray(bytes(heads)), dtype=torch.uint8)
+        self.heads_dev = raw.to(dev)
+        self.alpha = torch.empty(alpha_total, device=dev, dtype=torch.float32) if need_grad else None
+        self.nll = torch.empty(self.n_heads, self.n_utt, device=dev, dtype=torch.float32)
+        self.loss = torch.empty(self.n_heads, device=dev, dtype=torch.float32)
+
+    def forward(self) -> Tensor:
+        check(
+            lib.aph_ctc_forward(
+                self.heads_dev.data_ptr(), self.n_heads, self.n_utt, self.seq, self.max_label_len, self.input_lengths.data_ptr(), _ptr(self.alpha), self.nll.data_ptr(), self.loss.data_ptr(), _stream()
+            ),
+            "aph_ctc_forward",
+        )
+        return self.loss
+
+    def backward(self, grad_scale: Tensor) -> List[Optional[Tensor]]:
+        if self.alpha is None:
+            raise RuntimeError("CtcProblem was built without need_grad")
+        grad_scale = grad_scale.to(dtype=torch.float32).contiguous()
+        check(
+            lib.aph_ctc_backward(
+                self.heads_dev.data_ptr(), self.heads_host, self.n_heads, self.n_utt, self.seq, self.max_label_len, self.input_lengths.data_ptr(), self.alpha.data_ptr(), self.nll.data_ptr(), grad_scale.data_ptr(), _stream()
+            ),
+            "aph_ctc_backward",
+        )
+        return self.grads

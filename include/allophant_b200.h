@@ -108,6 +108,140 @@ int aph_attention_bf16(const void* q, const void* k, const void* vt, void* ctx,
                        const int32_t* lengths, int32_t n_utt, int32_t heads, int32_t T,
                        int32_t t_v, void* stream);
 
+/* ---- waveform normalisation and frame bookkeeping ------------------------- */
+/* zero_mean_unit_var_norm, acoustic_model.py:762-767:
+ *   mean = sum_all(x) / len; var = sum_valid((x-mean)^2) / len;
+ *   out  = (x - mean) / sqrt(var + 1e-7) on valid samples, 0 on padding.
+ * aph_wave_stats writes mean_rstd[n_utt][2] (fp32) using stats_scratch[n_utt*3] (fp64);
+ * aph_wave_norm materialises the normalised waveform (the fused encoder never does:
+ * aph_conv0_* apply mean/rstd while loading). lengths are int64 like Batch.lengths. */
+int aph_wave_stats(const float* x, const int64_t* lengths, int32_t n_utt, int32_t T,
+                   double* stats_scratch, float* mean_rstd, void* stream);
+int aph_wave_norm(const float* x, const int64_t* lengths, const float* mean_rstd, int32_t n_utt,
+                  int32_t T, float* out, void* stream);
+/* Wav2Vec2AcousticModel.downsampled_lengths, acoustic_model.py:832-835 with
+ * conv_length(use_padding=False), frontend.py:192-203: L <- floor((L - k)/s) + 1 per layer.
+ * kernels/strides are device int32[n_layers]; either output may be NULL. */
+int aph_frame_lengths(const int64_t* lengths, int32_t n_utt, const int32_t* kernels,
+                      const int32_t* strides, int32_t n_layers, int32_t* frames32,
+                      int64_t* frames64, void* stream);
+
+/* ---- feature-extractor layer 0 and row LayerNorm --------------------------- */
+/* Conv1d(1,512,k=10,s=5,bias) + LayerNorm(512) + GELU (HF:275-299, layer 0), reading the RAW
+ * waveform and applying mean_rstd on the fly (NULL = no normalisation). Output bf16
+ * channels-last [n_utt][L0][512], L0 = (T-10)/5+1; with skip_padded_frames != 0 frames that
+ * would read padding are not computed (their rows keep stale, finite data).
+ * w is the Conv1d weight [512][1][10] (fp32), gamma/beta the LayerNorm affine. */
+int aph_conv0_ln_gelu(const float* x, const int64_t* lengths, const float* mean_rstd,
+                      int32_t n_utt, int32_t T, const float* w, const float* bias,
+                      const float* gamma, const float* beta, float eps,
+                      int32_t skip_padded_frames, void* out_bf16, void* stream);
+/* feat_extract_norm="group" variant (HF:302-323): conv (bias may be NULL) + GroupNorm(512,512)
+ * whose statistics run over the whole padded time axis + GELU.
+ * raw_scratch: fp32 [n_utt][L0][512]; stats_scratch: fp64 [n_utt][512][2]. */
+int aph_conv0_gn_gelu(const float* x, const int64_t* lengths, const float* mean_rstd,
+                      int32_t n_utt, int32_t T, const float* w, const float* bias,
+                      const float* gamma, const float* beta, float eps, float* raw_scratch,
+                      double* stats_scratch, void* out_bf16, void* stream);
+/* nn.LayerNorm over the last axis (+ optional GELU), one warp per row; cols in {512, 1024}.
+ * Call sites: conv layers 1-6 (HF:290-299), feature projection (HF:429-431), encoder layers
+ * (HF:766-767 ×2 per layer), final encoder norm (HF:792). in: bf16 or fp32. */
+int aph_layernorm_rows(const void* in, int32_t in_is_f32, int64_t ld_in, int64_t rows,
+                       int32_t cols, const float* gamma, const float* beta, float eps,
+                       int32_t gelu, void* out_bf16, int64_t ld_bf16, float* out_f32,
+                       int64_t ld_f32, void* stream);
+
+/* ---- classifier heads -------------------------------------------------------- */
+/* EmbeddingCompositionLayer.forward, acoustic_model.py:219-232: row 0 = blank embedding
+ * weight[0]; row 1+v = sum_f weight[tfi[v][f] + category_offsets[f]] (EmbeddingBag "sum").
+ * category_offsets NULL = tfi already offset (the training table). Rows up to rows_out are
+ * zero-filled (GEMM padding). err_flag is set to 1 on an out-of-range category. */
+int aph_compose_embeddings(const float* weight, int32_t n_categories, int32_t embedding_size,
+                           const int64_t* tfi, const int64_t* category_offsets,
+                           int32_t n_phonemes, int32_t n_features, int32_t rows_out,
+                           void* out_bf16, float* out_f32, int32_t* err_flag, void* stream);
+/* log_softmax(logits, -1) for many narrow heads in one launch (acoustic_model.py:1051-1052
+ * via estimator.py:1041-1045; loss_functions.py:27). logits fp32 [rows][ld]; head h reads
+ * columns [col_off[h], col_off[h]+width[h]) (all inside [col_lo, col_lo+col_span)) and writes a
+ * contiguous fp32 [rows][width[h]] block at out + out_off[h]. Optional per-frame argmax
+ * (lowest index on ties) and max log-prob, laid out [n_heads][rows], feed greedy decoding. */
+int aph_log_softmax_heads(const float* logits, int64_t ld, int64_t rows, int32_t col_lo,
+                          int32_t col_span, const int32_t* col_off, const int32_t* width,
+                          const int64_t* out_off, int32_t n_heads, float* out,
+                          int32_t* argmax_out, float* maxlp_out, void* stream);
+/* Same for one wide head (large inventories): one warp per frame, row staged in smem. */
+int aph_log_softmax_wide(const float* logits, int64_t ld, int64_t rows, int32_t width,
+                         float* out, int64_t ld_out, int32_t* argmax_out, float* maxlp_out,
+                         void* stream);
+/* HierarchicalProjection.forward dependency inputs, acoustic_model.py:497-514:
+ * softmax(logits[..., skip:]) of each dependency written as bf16 into columns
+ * [dst_col[d], ...) of the next classifier's input matrix. */
+int aph_dependency_softmax(const float* logits, int64_t ld, int64_t rows, const int32_t* col_off,
+                           const int32_t* width, const int32_t* dst_col, int32_t n_deps,
+                           int32_t skip, void* dst_bf16, int64_t ld_dst, void* stream);
+
+/* ---- greedy CTC decoding ------------------------------------------------------ */
+/* torch.max(log_emissions, -1), predictions.py:195. x fp32 [rows][ld]. */
+int aph_argmax_rows(const float* x, int64_t ld, int64_t rows, int32_t width, int32_t* argmax_out,
+                    float* max_out, void* stream);
+/* GreedyCTCDecoder.__call__, predictions.py:196-206, for n_seq = heads*n_utt sequences of T
+ * frames (sequence s belongs to utterance s % n_utt): collapse repeats, drop `blank`,
+ * 1-based run-start timesteps, score = sum of max log-probs over valid frames.
+ * tokens/timesteps: int32 [n_seq][T] (first counts[s] entries valid). */
+int aph_ctc_greedy_collapse(const int32_t* argmax_in, const float* maxlp_in,
+                            const int32_t* lengths, int32_t n_utt, int32_t T, int32_t n_seq,
+                            int32_t blank, int32_t* tokens, int32_t* timesteps, int32_t* counts,
+                            float* scores, void* stream);
+
+/* ---- weight packing (once per weight version) ---------------------------------- */
+/* fp32 -> bf16 (nn.Linear weights are already the K-major B operand). */
+int aph_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+/* Same for a row-strided matrix (keeps a hidden state as a bf16 classifier input block). */
+int aph_cast_bf16_2d(const float* src, int64_t ld_src, void* dst_bf16, int64_t ld_dst,
+                     int64_t rows, int32_t cols, void* stream);
+/* Conv1d weight [O][C][k] (HF:281-287) -> bf16 [O][k][C] for the channels-last implicit GEMM. */
+int aph_pack_conv_weight(const float* src, void* dst_bf16, int32_t out_channels,
+                         int32_t in_channels, int32_t kernel, void* stream);
+/* weight_norm(dim=2) of the positional conv (HF:326-350): w = g[j] * v / ||v[:,:,j]||, packed
+ * to bf16 [O][k][Cg]. weight_g: parametrizations.weight.original0 [1][1][k]; weight_v:
+ * original1 [O][Cg][k]; tap_scale_scratch: fp32 [k]. */
+int aph_pack_posconv_weight(const float* weight_g, const float* weight_v, void* dst_bf16,
+                            float* tap_scale_scratch, int32_t out_channels,
+                            int32_t group_channels, int32_t kernel, void* stream);
+
+/* ---- multi-head CTC loss -------------------------------------------------------- */
+/* CTCWrapper (loss_functions.py:19-27): nn.CTCLoss(reduction="sum", zero_infinity=True) on
+ * log_softmax(logits); blank = 0; called once per classifier head (estimator.py:721-734).
+ * Here ONE launch covers every (head, utterance) pair. A head is described by: */
+typedef struct aph_ctc_head {
+  const float* log_probs;       /* element (n, t, k) at log_probs[n*stride_n + t*stride_t + k]   */
+  float* grad;                  /* d loss / d LOGITS, same addressing; NULL = no gradient        */
+  int64_t stride_t;
+  int64_t stride_n;
+  int32_t n_classes;
+  int32_t s_pad;                /* aph_ctc_states_pad(max label length over all heads)           */
+  const int64_t* labels;        /* int64 [n_utt][label_stride], zero padded, values >= 1          */
+  int64_t label_stride;
+  const int64_t* label_lengths; /* int64 [n_utt]                                                  */
+  int64_t alpha_offset;         /* float offset of this head's [n_utt][T][s_pad] block in alpha_ws */
+} aph_ctc_head;
+
+/* Padded number of CTC states per frame used for the alpha workspace (negative = unsupported). */
+int aph_ctc_states_pad(int32_t max_label_len);
+/* Forward: nll_out[h][n] = -log p(labels | log_probs) (inf when infeasible); loss_out[h] =
+ * sum_n nll with infinities zeroed (may be NULL). alpha_ws (may be NULL when no gradient is
+ * needed) receives the forward variables for aph_ctc_backward. heads_dev is a DEVICE array. */
+int aph_ctc_forward(const aph_ctc_head* heads_dev, int32_t n_heads, int32_t n_utt, int32_t T,
+                    int32_t max_label_len, const int64_t* input_lengths, float* alpha_ws,
+                    float* nll_out, float* loss_out, void* stream);
+/* Backward: writes grad (w.r.t. the logits that produced log_probs) for every head with a
+ * non-NULL grad pointer: grad_scale[h] * (softmax - state occupancies), zero for padded
+ * frames and for pairs whose loss was infinite. heads_host is the same array in HOST memory. */
+int aph_ctc_backward(const aph_ctc_head* heads_dev, const aph_ctc_head* heads_host,
+                     int32_t n_heads, int32_t n_utt, int32_t T, int32_t max_label_len,
+                     const int64_t* input_lengths, const float* alpha_ws, const float* nll,
+                     const float* grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
