@@ -48,7 +48,14 @@ class PackedEncoder:
         self.device: Optional[torch.device] = None
 
     def _current_version(self) -> Tuple[int, ...]:
-        return tuple(p._version for p in self.weights.parameters()) + tuple(p.data_ptr() for p in self.weights.parameters())
+        def version(p: Tensor) -> int:
+            try:
+                return p._version
+            except RuntimeError:  # inference tensors do not track a version counter
+                return -1
+
+        params = list(self.weights.parameters())
+        return tuple(version(p) for p in params) + tuple(p.data_ptr() for p in params)
 
     def ensure(self) -> None:
         version = self._current_version()

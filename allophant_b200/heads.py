@@ -30,6 +30,14 @@ _OUTPUT = ProjectionEntryConfig.OUTPUT_DEPENDENCY
 _PATTERN = ProjectionEntryConfig.OUTPUT_PATTERN
 
 
+def _version(tensor: Tensor) -> int:
+    """Version counter, or -1 for inference tensors (which do not track one)."""
+    try:
+        return tensor._version
+    except RuntimeError:
+        return -1
+
+
 def _round_up(value: int, multiple: int) -> int:
     return (value + multiple - 1) // multiple * multiple
 
@@ -107,7 +115,7 @@ class HeadsRuntime:
     # ------------------------------------------------------------------ weights
     def _params_version(self) -> Tuple[int, ...]:
         params = list(self.model._projection.parameters())
-        return tuple(p._version for p in params) + tuple(p.data_ptr() for p in params)
+        return tuple(_version(p) for p in params) + tuple(p.data_ptr() for p in params)
 
     @torch.no_grad()
     def _ensure_weights(self, device: torch.device) -> None:
@@ -149,7 +157,7 @@ class HeadsRuntime:
             indices, offsets = layer._dense_feature_table, None
         else:
             indices, offsets = target_feature_indices, layer._category_offsets
-        key = (name, indices.data_ptr(), indices._version, tuple(indices.shape), offsets is None, weight._version, weight.data_ptr())
+        key = (name, indices.data_ptr(), _version(indices), tuple(indices.shape), offsets is None, _version(weight), weight.data_ptr())
         cached = self._composed_cache.get(key)
         if cached is not None:
             return cached
@@ -202,6 +210,7 @@ class HeadsRuntime:
         # (name, logits buffer, leading dim, first column, width) in topological order
         heads: List[Tuple[str, Tensor, int, int, int]] = []
         level_logits: List[Tensor] = []
+        produced_all: Dict[str, Tuple[Tensor, int, int, int]] = {}
         for level_index, layout in enumerate(self.levels):
             logits = torch.empty(rows, layout.n_pad, device=device, dtype=torch.float32)
             logits_bf16 = torch.empty(rows, layout.n_pad, device=device, dtype=torch.bfloat16) if layout.has_composition else None
@@ -243,30 +252,42 @@ class HeadsRuntime:
                     produced[spec.name] = (composed, table.shape[0], 0, classes)
                 else:
                     produced[spec.name] = (logits, layout.n_pad, offset, spec.out_features)
-            # dependency probabilities for later levels
+            # dependency probabilities for later levels: one launch per source buffer
+            by_buffer: Dict[int, List[str]] = {}
             for name in layout.feeds_later:
-                buffer, ld, column, width = produced[name]
-                target_column, expected = self.dep_cols[name]
-                if width - skip != expected:
-                    raise ValueError(
-                        f"classifier {name!r} produces {width - skip} dependency features but its dependents expect {expected}"
-                    )
-                col_off = self._int_tensor(("dep_col", name, column), [column], device, torch.int32)
-                widths = self._int_tensor(("dep_w", name, width), [width], device, torch.int32)
-                dst_col = self._int_tensor(("dep_dst", name, target_column), [target_column], device, torch.int32)
-                ops.dependency_softmax(buffer, ld, rows, col_off, widths, dst_col, 1, skip, plan.x, self.ldx)
-            for spec in layout.specs:
-                classifier = projection._layers[spec.name]
-                buffer, ld, column, width = produced[spec.name]
-                if classifier._allophone_layer is not None:
-                    if not predict:
-                        raise NotImplementedError(
-                            "allophant_b200: the allophone layer's training forward (map_allophones) is not available in this build"
+                by_buffer.setdefault(id(produced[name][0]), []).append(name)
+            for names in by_buffer.values():
+                buffer, ld = produced[names[0]][0], produced[names[0]][1]
+                columns, widths_list, targets = [], [], []
+                for name in names:
+                    _, _, column, width = produced[name]
+                    target_column, expected = self.dep_cols[name]
+                    if width - skip != expected:
+                        raise ValueError(
+                            f"classifier {name!r} produces {width - skip} dependency features but its dependents expect {expected}"
                         )
-                    heads.append((ProjectionEntryConfig.PHONE, buffer, ld, column, width))
-                    heads.append((ProjectionEntryConfig.PHONEME_LAYER, buffer, ld, column, width))
-                else:
-                    heads.append((spec.name, buffer, ld, column, width))
+                    columns.append(column)
+                    widths_list.append(width)
+                    targets.append(target_column)
+                col_off = self._int_tensor(("dep_col", tuple(columns)), columns, device, torch.int32)
+                widths = self._int_tensor(("dep_w", tuple(widths_list)), widths_list, device, torch.int32)
+                dst_col = self._int_tensor(("dep_dst", tuple(targets)), targets, device, torch.int32)
+                ops.dependency_softmax(buffer, ld, rows, col_off, widths, dst_col, len(names), skip, plan.x, self.ldx)
+            produced_all.update(produced)
+
+        # outputs in the reference's (topological) order, independent of the column layout
+        for spec in projection._specs:
+            classifier = projection._layers[spec.name]
+            buffer, ld, column, width = produced_all[spec.name]
+            if classifier._allophone_layer is not None:
+                if not predict:
+                    raise NotImplementedError(
+                        "allophant_b200: the allophone layer's training forward (map_allophones) is not available in this build"
+                    )
+                heads.append((ProjectionEntryConfig.PHONE, buffer, ld, column, width))
+                heads.append((ProjectionEntryConfig.PHONEME_LAYER, buffer, ld, column, width))
+            else:
+                heads.append((spec.name, buffer, ld, column, width))
 
         if not log_probabilities:
             outputs = {

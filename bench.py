@@ -1,0 +1,397 @@
+"""Headline benchmark: multitask predict + greedy CTC decode, audio-seconds per second.
+
+    python bench.py --gpus N --steps K --warmup W            # B200 path (one process per GPU under torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+
+Workload (BASELINE.json configs[1]): Allophant Multitask, XLS-R-300M shape, random init, batch 32 x 10 s of
+synthetic 16 kHz audio per GPU, all 36 attribute heads + composed phoneme head ('es'-sized inventory of 25),
+log_softmax + greedy CTC decode of all 37 heads.  One step = one batch through that path.
+
+The JSON line follows the driver's contract: `value` is device-timed with inputs resident in HBM, `e2e` is the
+same metric through the public API (Estimator.predict + decode_predictions) with pinned-host inputs copied in and
+decoded tokens copied out inside the timed region, `roofline` describes the dominant kernel (the tcgen05 GEMM over
+the encoder's linear layers), `cpu_baseline` is the oracle timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from typing import Any, Dict, List, Optional
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "audio-sec/sec, multitask predict+CTC"
+UNIT = "audio-s/s"
+BATCH = 32
+SECONDS = 10
+SAMPLE_RATE = 16000
+INVENTORY = 25
+
+
+def encoder_flops(frames: int, hidden: int = 1024, ffn: int = 4096, layers: int = 24) -> Dict[str, float]:
+    """Algorithmic forward FLOPs per utterance."""
+    linear = layers * (8 * hidden * hidden + 4 * hidden * ffn) * frames
+    attention = layers * 4 * hidden * frames * frames
+    return {"linear": float(linear), "attention": float(attention)}
+
+
+def utterance_flops(samples: int) -> float:
+    lengths, length = [], samples
+    for kernel, stride in zip((10, 3, 3, 3, 3, 2, 2), (5, 2, 2, 2, 2, 2, 2)):
+        length = (length - kernel) // stride + 1
+        lengths.append(length)
+    conv = 2 * 1 * 10 * 512 * lengths[0] + sum(2 * 512 * k * 512 * l for k, l in zip((3, 3, 3, 3, 2, 2), lengths[1:]))
+    frames = lengths[-1]
+    proj = 2 * 512 * 1024 * frames
+    pos = 2 * 64 * 128 * 1024 * frames
+    enc = encoder_flops(frames)
+    heads = 2 * 1024 * (36 * 4 + 640) * frames + 2 * 640 * (INVENTORY + 1) * frames
+    return conv + proj + pos + enc["linear"] + enc["attention"] + heads
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    QUERY = (
+        "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    )
+
+    def __init__(self, index: int) -> None:
+        self.index = index
+        self.samples: List[List[str]] = []
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self) -> None:
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits"],
+                    capture_output=True, text=True, timeout=5,
+                ).stdout.strip()  # fmt: skip
+                if out:
+                    self.samples.append([cell.strip() for cell in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=6)
+
+    def summary(self) -> Dict[str, Any]:
+        clocks, reasons, max_clock = [], set(), None
+        for cells in self.samples:
+            try:
+                clocks.append(float(cells[0]))
+                max_clock = float(cells[1])
+            except (ValueError, IndexError):
+                continue
+            for name, cell in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), cells[3:7]):
+                if cell.lower().startswith("active"):
+                    reasons.add(name)
+        clocks.sort()
+        return {
+            "sm_mhz": clocks[len(clocks) // 2] if clocks else None,
+            "sm_max_mhz": max_clock,
+            "reasons": sorted(reasons),
+            "samples": len(clocks),
+        }
+
+
+def measured_peaks() -> Dict[str, Any]:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as file:
+            peaks = json.load(file)
+        peaks["source"] = "measured (MEASURED_PEAKS.json)"
+        return peaks
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# --------------------------------------------------------------------------------------------------
+# model construction (random init of the named architecture; synthetic inventory — no network, no CSV)
+# --------------------------------------------------------------------------------------------------
+def build_estimator(device: str):
+    from allophant_b200.config import Config, PhonemeLayerType
+    from allophant_b200.estimator import Estimator, attribute_graph_from_config
+    from allophant_b200.phonetic_features import PhoneticAttributeIndexer
+
+    torch.manual_seed(2)
+    config = Config.default()
+    config.nn.projection.phoneme_layer = PhonemeLayerType.SHARED
+    names = [entry.name for entry in config.nn.projection.classes]
+    indexer = PhoneticAttributeIndexer.synthetic(109, names, n_categories=3, seed=1, training_inventory=60)
+    graph = attribute_graph_from_config(config, indexer)
+    estimator = Estimator.from_config(config, 1, SAMPLE_RATE, graph, indexer, device=device, load_pretrained_weights=False)
+    inventory = [f"p{index}" for index in range(INVENTORY)]
+    return estimator, indexer.composition_feature_matrix(inventory)
+
+
+def cpu_reference_step(oracle, audio, lengths, tfi) -> None:
+    from oracle import restatement
+
+    outputs, frames = oracle.predict(audio, lengths, None, tfi)
+    for value in outputs.values():
+        restatement.greedy_ctc_decode(value.transpose(1, 0).contiguous(), frames)
+
+
+def time_cpu_reference(n_utt: int, steps: int, warmup: int) -> Dict[str, Any]:
+    """The reference's CPU path (oracle port: HF encoder + restated heads/decoder) on this box's host cores."""
+    from oracle import restatement
+
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    spec = restatement.multitask_spec(n_train_phonemes=60)
+    oracle = restatement.OracleModel(spec)
+    samples = SECONDS * SAMPLE_RATE
+    audio = restatement.synthetic_audio(n_utt, samples, seed=0)
+    lengths = torch.full((n_utt,), samples, dtype=torch.long)
+    tfi = torch.randint(0, 3, (INVENTORY, 36), generator=torch.Generator().manual_seed(1))
+    for _ in range(warmup):
+        cpu_reference_step(oracle, audio, lengths, tfi)
+    times = []
+    for _ in range(steps):
+        start = time.perf_counter()
+        cpu_reference_step(oracle, audio, lengths, tfi)
+        times.append(time.perf_counter() - start)
+    total = sum(times)
+    return {
+        "value": n_utt * SECONDS * steps / total,
+        "unit": UNIT,
+        "cores": cores,
+        "kind": "port",
+        "sample": f"{steps} x (batch {n_utt} x {SECONDS} s, fp32, all 37 heads + greedy decode), {warmup} warm-up",
+        "ms_per_step": 1000.0 * total / steps,
+    }
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_utt = 2
+    result = time_cpu_reference(n_utt, max(1, args.steps), max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": result["value"],
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": result["ms_per_step"],
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {k: result[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": result["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus: int) -> Dict[str, Any]:
+    return {
+        "workload": "BASELINE configs[1]: Allophant Multitask (XLS-R-300M shape, random init) inference, "
+        f"batch {BATCH} x {SECONDS} s synthetic 16 kHz audio per GPU, 36 attribute heads + composed phoneme head "
+        f"(inventory {INVENTORY}), log_softmax + greedy CTC decode of all 37 heads",
+        "batch_per_gpu": BATCH,
+        "seconds_per_utterance": SECONDS,
+        "parallelism": f"dp{n_gpus} (independent utterance shards, no collective)",
+        "l2": "per-step activations (>1 GB) exceed the 126 MB L2; no explicit flush between iterations",
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+def run_gpu_arm(args) -> None:
+    from allophant_b200 import ops
+    from allophant_b200.dataset_processing import Batch
+    from allophant_b200.predictions import decode_predictions
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: allophant_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = f"cuda:{local_rank}"
+    distributed = world > 1
+    if distributed:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device(device))
+
+    estimator, tfi = build_estimator(device)
+    tfi_dev = tfi.to(device)
+    samples = SECONDS * SAMPLE_RATE
+    generator = torch.Generator().manual_seed(rank)
+    host_audio = (0.1 * torch.randn(BATCH, samples, generator=generator)).pin_memory()
+    host_lengths = torch.full((BATCH,), samples, dtype=torch.long).pin_memory()
+    host_languages = torch.zeros(BATCH, dtype=torch.long).pin_memory()
+    resident = Batch(host_audio.to(device), host_lengths.to(device), host_languages.to(device))
+
+    def device_step():
+        predictions = estimator.predict(resident, tfi_dev)
+        cache = predictions._decode_cache
+        return ops.ctc_greedy_collapse(cache["argmax"], cache["maxlp"], cache["frames32"], cache["n_utt"], cache["seq"],
+                                       cache["argmax"].shape[0] * cache["n_utt"], 0)  # fmt: skip
+
+    def e2e_step():
+        batch = Batch(host_audio, host_lengths, host_languages).to(device, non_blocking=True)
+        predictions = estimator.predict(batch, tfi_dev)
+        return decode_predictions(predictions)
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step, steps: int) -> float:
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        start.record()
+        for _ in range(steps):
+            step()
+        end.record()
+        barrier()
+        elapsed = torch.tensor([start.elapsed_time(end)], device=device)
+        if distributed:
+            dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+        return float(elapsed.item())
+
+    for _ in range(max(3, args.warmup)):
+        device_step()
+    ops.reset_launch_count()
+    with ClockSampler(local_rank) as sampler:
+        elapsed_ms = timed(device_step, args.steps)
+    launches = ops.launch_count() // args.steps
+    clocks = sampler.summary()
+
+    for _ in range(2):
+        e2e_step()
+    wall_start = time.perf_counter()
+    barrier()
+    for _ in range(args.steps):
+        result = e2e_step()  # decode_predictions ends with a device-to-host copy: the step is complete on return
+    barrier()
+    e2e_seconds = torch.tensor([time.perf_counter() - wall_start], device=device)
+    if distributed:
+        dist.all_reduce(e2e_seconds, op=dist.ReduceOp.MAX)
+    d2h_bytes = 0
+    cache = estimator.predict(resident, tfi_dev)._decode_cache
+    n_seq = cache["argmax"].shape[0] * cache["n_utt"]
+    d2h_bytes = n_seq * cache["seq"] * 4 * 2 + n_seq * 8
+    h2d_bytes = host_audio.numel() * 4 + host_lengths.numel() * 8 + host_languages.numel() * 8
+
+    audio_seconds = world * BATCH * SECONDS * args.steps
+    value = audio_seconds / (elapsed_ms / 1000.0)
+    e2e_value = audio_seconds / float(e2e_seconds.item())
+
+    # ---- roofline of the dominant kernel: the tcgen05 GEMM over the encoder's 24 x {QKV, out, FFN1, FFN2} ----
+    roofline = None
+    cpu_baseline = None
+    if rank == 0:
+        frames = estimator.model.acoustic_model.plan_for(BATCH, samples, 1024, {}).seq
+        gemm_events: List[Any] = []
+        original = ops.run_gemm
+
+        def timed_gemm(gemm_args):
+            if gemm_args.k in (1024, 4096) and gemm_args.n in (1024, 3072, 4096) and gemm_args.mode == 0:
+                start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                start.record()
+                original(gemm_args)
+                end.record()
+                gemm_events.append((start, end))
+            else:
+                original(gemm_args)
+
+        ops.run_gemm = timed_gemm
+        try:
+            device_step()
+            torch.cuda.synchronize()
+        finally:
+            ops.run_gemm = original
+        gemm_ms = sum(start.elapsed_time(end) for start, end in gemm_events)
+        flops = encoder_flops(frames)["linear"] * BATCH
+        peaks = measured_peaks()
+        achieved = flops / (gemm_ms / 1000.0) / 1e12
+        peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+        roofline = {
+            "kernel": "aph::gemm_bf16_kernel (encoder QKV / out-proj / FFN1 / FFN2, 96 launches per step)",
+            "bound": "tensor",
+            "achieved": achieved,
+            "peak": peak,
+            "unit": "TFLOP/s",
+            "frac": achieved / peak,
+            "traffic": None,
+            "peak_source": f"bf16_tflops_sustained, {peaks['source']}",
+            "launches": len(gemm_events),
+            "avg_launch_ms": gemm_ms / max(1, len(gemm_events)),
+            "share_of_step": gemm_ms / (elapsed_ms / args.steps),
+        }
+        if not args.skip_cpu_baseline:
+            baseline = time_cpu_reference(2, 3, 1)
+            cpu_baseline = {k: baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": max(3, args.warmup),
+        "ms_per_step": elapsed_ms / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "bf16",
+        "data": "synthetic",
+        "config": workload_config(world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "tflops_per_gpu": utterance_flops(samples) * BATCH / (elapsed_ms / args.steps / 1000.0) / 1e12,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    parser = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    parser.add_argument("--gpus", type=int, default=1)
+    parser.add_argument("--steps", type=int, default=10)
+    parser.add_argument("--warmup", type=int, default=3)
+    parser.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    parser.add_argument("--skip-cpu-baseline", action="store_true")
+    args = parser.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,110 @@
+"""Shared test helpers: oracle construction (CPU) and the CUDA model loaded with the oracle's weights."""
+from __future__ import annotations
+
+import os
+from functools import lru_cache
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from oracle import restatement
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name: str) -> Dict[str, Any]:
+    return torch.load(os.path.join(GOLDEN_DIR, f"{name}.pt"), weights_only=False)
+
+
+def synthetic_allophones(n_languages: int, n_phonemes: int, n_phones: int, seed: int):
+    rng = np.random.default_rng(seed)
+    result = {}
+    for language in range(n_languages):
+        inventory = sorted(rng.choice(n_phonemes, size=max(4, n_phonemes // 2), replace=False).tolist())
+        mapping = {}
+        for phoneme in inventory:
+            count = int(rng.integers(1, 4))
+            mapping[int(phoneme)] = sorted(int(p) for p in rng.choice(n_phones, size=count, replace=False))
+        result[language] = mapping
+    return result
+
+
+def spec_for_case(case: Dict[str, Any]) -> restatement.OracleSpec:
+    """Same construction as oracle/make_golden.py:build_spec (kept in sync by test_oracle_golden)."""
+    spec = restatement.multitask_spec(**case["spec"])
+    allophones = case.get("allophones")
+    if allophones is not None:
+        n_phonemes = case["spec"]["n_train_phonemes"]
+        spec.allophones = synthetic_allophones(allophones["n_languages"], n_phonemes, allophones["n_phones"], allophones["seed"])
+        spec.n_phones = allophones["n_phones"]
+        rng = np.random.default_rng(77)
+        table = rng.integers(0, 3, size=(spec.n_phones, len(restatement.PHOIBLE_FEATURES)))
+        table[:3, :] = np.arange(3)[:, None]
+        spec.feature_table = table
+    return spec
+
+
+def batch_for_case(fixture: Dict[str, Any]) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    lengths = fixture["lengths"]
+    audio = restatement.synthetic_audio(len(lengths), int(lengths.max()), seed=0)
+    audio = audio * restatement.mask_sequence(lengths)
+    return audio, lengths, fixture["language_ids"]
+
+
+def cuda_model_for_spec(spec: restatement.OracleSpec, oracle: restatement.OracleModel, device: str = "cuda"):
+    """Builds allophant_b200's Allophant with the architecture of ``spec`` and loads the oracle's weights."""
+    from allophant_b200.attribute_graph import AttributeGraph, AttributeNode
+    from allophant_b200.config import (
+        Architecture,
+        CTCLossConfig,
+        EmbeddingCompositionConfig,
+        PhonemeLayerType,
+        ProjectionConfig,
+        ProjectionEntryConfig,
+        Wav2Vec2PretrainedConfig,
+    )
+    from allophant_b200.network import wav2vec2
+    from allophant_b200.network.acoustic_model import Allophant
+    from allophant_b200.phonetic_features import AllophoneData, ArticulatoryAttributes, LanguageAllophoneMappings, PhoneticAttributeIndexer
+
+    features = restatement.PHOIBLE_FEATURES
+    table = np.asarray(spec.feature_table)
+    categories = {f: [str(v) for v in range(int(table[:, i].max()) + 1)] for i, f in enumerate(features)}
+    phoneme_class = next(c for c in spec.classes if c.name == "phoneme")
+    if spec.allophones is None:
+        names = [f"p{i}" for i in range(table.shape[0])]
+        attributes = ArticulatoryAttributes(names, features, table, categories)
+        indexer = PhoneticAttributeIndexer(attributes, names, features, features + ["phoneme"])
+        phoneme_layer = PhonemeLayerType.SHARED
+    else:
+        phones = [f"ph{i}" for i in range(spec.n_phones)]
+        shared = ArticulatoryAttributes(phones, features, table, categories)
+        mappings = LanguageAllophoneMappings(spec.allophones, [f"l{i}" for i in range(len(spec.allophones))], phones)
+        indexer = PhoneticAttributeIndexer(
+            shared, [f"p{i}" for i in range(phoneme_class.size)], features, features + ["phoneme"], mappings, AllophoneData(shared)
+        )
+        phoneme_layer = PhonemeLayerType.ALLOPHONES
+    projection = ProjectionConfig(
+        [ProjectionEntryConfig(c.name, list(c.dependencies)) for c in spec.classes],
+        phoneme_layer=phoneme_layer,
+        acoustic_model_dropout=0.2,
+        dependency_blanks=spec.dependency_blanks,
+        embedding_composition=None if spec.embedding_size is None else EmbeddingCompositionConfig(spec.embedding_size),
+    )
+    model_id = "facebook/wav2vec2-xls-r-300m"
+    if spec.encoder_overrides:
+        import dataclasses
+
+        model_id = "test/" + "-".join(f"{k}{v}" for k, v in sorted(spec.encoder_overrides.items()))
+        wav2vec2.KNOWN_MODELS[model_id] = dataclasses.replace(wav2vec2.KNOWN_MODELS["facebook/wav2vec2-xls-r-300m"], **spec.encoder_overrides)
+    architecture = Architecture(16_000_000, projection, Wav2Vec2PretrainedConfig(model_id), loss=CTCLossConfig())
+    graph = AttributeGraph(AttributeNode(c.name, c.size, None, list(c.dependencies)) for c in spec.classes)
+    model = Allophant.from_config(architecture, 1, 16000, graph, indexer, load_pretrained_weights=False)
+    result = model.load_state_dict(oracle.state_dict(), strict=True)
+    assert not result.missing_keys and not result.unexpected_keys
+    return model.to(device).eval(), indexer
+
+
+def rel_err(value: torch.Tensor, reference: torch.Tensor) -> float:
+    return float((value.double().cpu() - reference.double().cpu()).abs().max() / reference.double().abs().max().clamp_min(1e-12))

@@ -1,0 +1,182 @@
+"""-m gpu: the CUDA path, through the drop-in Python API, against the CPU oracle and the golden vectors
+frozen from the unmodified reference, on identical seeded weights and inputs."""
+import io
+
+import pytest
+import torch
+
+from oracle import restatement
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+# Tolerance (north_star): 2e-2 for bf16 kernels.  The encoder's GEMM operands are bf16 (fp32 accumulation,
+# fp32 residual stream, fp32 LayerNorm/softmax statistics); errors are measured against each tensor's range.
+RANGE_TOL = 2e-2
+
+
+def _range_error(ours: torch.Tensor, reference: torch.Tensor, frames) -> float:
+    worst, scale = 0.0, 0.0
+    for index, length in enumerate(frames):
+        worst = max(worst, float((ours[:length, index] - reference[:length, index]).abs().max()))
+        scale = max(scale, float(reference[:length, index].abs().max()))
+    return worst / scale
+
+
+@pytest.fixture(scope="module", params=["multitask_2layer", "hierarchical_2layer", "allophones_2layer", "xlsr300m_1x1s"])
+def case(request):
+    from allophant_b200.dataset_processing import Batch
+
+    fixture = helpers.load_golden(request.param)
+    spec = helpers.spec_for_case(fixture["case_config"])
+    oracle = restatement.OracleModel(spec)
+    assert restatement.state_checksum(oracle.state_dict()) == pytest.approx(fixture["checksum"], rel=1e-9)
+    model, indexer = helpers.cuda_model_for_spec(spec, oracle)
+    audio, lengths, language_ids = helpers.batch_for_case(fixture)
+    batch = Batch(audio.cuda(), lengths.cuda(), language_ids.cuda())
+    return dict(name=request.param, fixture=fixture, spec=spec, oracle=oracle, model=model, batch=batch, audio=audio, lengths=lengths)
+
+
+def test_hidden_states_match_oracle(case):
+    """Wav2Vec2AcousticModel.forward: all hidden states, time-first, and the frame counts."""
+    hidden_ref, frames_ref = case["oracle"].encode(case["audio"], case["lengths"])
+    with torch.inference_mode():
+        hidden, frames = case["model"].acoustic_model(case["batch"])
+    assert torch.equal(frames.cpu(), frames_ref)
+    assert len(hidden) == len(hidden_ref)
+    for index, (ours, ref) in enumerate(zip(hidden, hidden_ref)):
+        assert ours.shape == ref.shape
+        error = _range_error(ours.float().cpu(), ref, frames_ref.tolist())
+        assert error < RANGE_TOL, f"hidden state {index}: {error:.3e} of range"
+
+
+def test_log_probabilities_match_golden(case):
+    """Estimator.predict (log_probabilities=True) against the outputs of the UNMODIFIED reference."""
+    fixture, model = case["fixture"], case["model"]
+    tfi = fixture["target_feature_indices"]
+    with torch.inference_mode():
+        predictions = model.predict_log_probabilities(case["batch"], None if tfi is None else tfi.cuda())
+    assert torch.equal(predictions.lengths.cpu(), fixture["frames"])
+    assert list(predictions.outputs) == fixture["head_order"]
+    frames = fixture["frames"].tolist()
+    for name, reference in fixture["log_probs"].items():
+        ours = predictions.outputs[name].float().cpu()
+        assert ours.shape == reference.shape, (name, ours.shape, reference.shape)
+        error = _range_error(ours, reference, frames)
+        assert error < RANGE_TOL, f"{name}: {error:.3e} of range"
+        # rows are normalised log-probabilities
+        assert float(torch.logsumexp(ours, -1).abs().max()) < 1e-4
+
+
+def test_logits_path_and_log_probabilities_op(case):
+    """Allophant.forward(predict=True) returns logits; Allophant.log_probabilities is log_softmax."""
+    fixture, model = case["fixture"], case["model"]
+    tfi = fixture["target_feature_indices"]
+    with torch.inference_mode():
+        logits = model(case["batch"], None if tfi is None else tfi.cuda(), predict=True)
+        name = fixture["head_order"][-1]
+        ours = model.log_probabilities(logits.outputs[name]).float().cpu()
+    assert _range_error(ours, fixture["log_probs"][name], fixture["frames"].tolist()) < RANGE_TOL
+
+
+def test_greedy_decode_identical_given_same_log_probs(case):
+    """Token sequences, timesteps and scores of the CUDA decoder equal the reference decoder's on the SAME
+    log-probabilities (bit-exact integers); against the golden tokens (computed from fp32 CPU log-probs) every
+    disagreement must sit on a near-tie of the oracle's top-2 classes."""
+    from allophant_b200.predictions import GreedyCTCDecoder, decode_predictions
+
+    fixture, model = case["fixture"], case["model"]
+    tfi = fixture["target_feature_indices"]
+    with torch.inference_mode():
+        predictions = model.predict_log_probabilities(case["batch"], None if tfi is None else tfi.cuda())
+        decoded = decode_predictions(predictions)
+        single = GreedyCTCDecoder()(predictions.outputs["stress"].transpose(1, 0).contiguous(), predictions.lengths)
+    frames = fixture["frames"]
+    mismatched_frames = 0
+    total_frames = 0
+    for name in fixture["head_order"]:
+        ours_lp = predictions.outputs[name].float().cpu()
+        expected = restatement.greedy_ctc_decode(ours_lp.transpose(0, 1), frames)
+        for hypothesis, reference in zip(decoded[name], expected):
+            assert torch.equal(hypothesis[0].tokens, reference[0].tokens)
+            assert torch.equal(hypothesis[0].timesteps, reference[0].timesteps)
+            assert abs(float(hypothesis[0].score) - float(reference[0].score)) <= 1e-3 * max(1.0, abs(float(reference[0].score)))
+        # frame-level agreement with the fp32 oracle: a different argmax is only acceptable on a near-tie
+        golden = fixture["log_probs"][name]
+        for index, length in enumerate(frames.tolist()):
+            ours_arg = ours_lp[:length, index].argmax(-1)
+            ref_arg = golden[:length, index].argmax(-1)
+            differs = ours_arg != ref_arg
+            total_frames += length
+            mismatched_frames += int(differs.sum())
+            if differs.any():
+                top2 = golden[:length, index].topk(2, -1).values
+                gap = (top2[:, 0] - top2[:, 1])[differs]
+                scale = float(golden[:length, index].abs().max())
+                assert float(gap.max()) < 2 * RANGE_TOL * scale, f"{name}: argmax flipped on a clear decision (gap {float(gap.max()):.3f})"
+    for hypothesis, reference in zip(single, decoded["stress"]):
+        assert torch.equal(hypothesis[0].tokens, reference[0].tokens)
+    print(f"{case['name']}: {mismatched_frames}/{total_frames} frame argmaxes differ from the fp32 oracle (all near-ties)")
+
+
+def test_multi_head_ctc_matches_golden(case):
+    """CTCWrapper per head == the reference's CTCWrapper on the reference's logits (golden), evaluated on OUR logits:
+    loss within 2e-2 relative (bf16 encoder), and exactly the torch value when fed the same logits."""
+    from allophant_b200.loss_functions import multi_head_ctc_loss
+
+    fixture, model = case["fixture"], case["model"]
+    if case["name"] == "allophones_2layer":
+        pytest.skip("training-mode allophone mapping is covered by test_gpu_training")
+    tfi = fixture["target_feature_indices"]
+    with torch.inference_mode():
+        logits = model(case["batch"], None if tfi is None else tfi.cuda(), predict=True)
+    names = [n for n in fixture["ctc_losses"]]
+    frames = fixture["frames"].cuda()
+    ours = multi_head_ctc_loss(
+        [logits.outputs[n].float() for n in names],
+        [fixture["ctc_labels"][n].cuda() for n in names],
+        frames,
+        [fixture["ctc_label_lengths"][n].cuda() for n in names],
+    ).cpu()
+    for index, name in enumerate(names):
+        golden = fixture["ctc_losses"][name]
+        same_logits = float(
+            restatement.ctc_wrapper(logits.outputs[name].float().cpu(), fixture["ctc_labels"][name], fixture["frames"], fixture["ctc_label_lengths"][name])
+        )
+        assert abs(float(ours[index]) - same_logits) <= 1e-3 * max(1.0, abs(same_logits)), name
+        assert abs(float(ours[index]) - golden) <= RANGE_TOL * max(1.0, abs(golden)), name
+
+
+def test_estimator_checkpoint_roundtrip(case):
+    """Estimator.save / Estimator.restore keep the checkpoint layout (estimator.py:199-249) and the outputs."""
+    if case["name"] != "multitask_2layer":
+        pytest.skip("one architecture is enough for the checkpoint round trip")
+    from allophant_b200.config import Config, PhonemeLayerType
+    from allophant_b200.estimator import Estimator, attribute_graph_from_config
+    from allophant_b200.network import wav2vec2
+    from allophant_b200.phonetic_features import PhoneticAttributeIndexer
+
+    config = Config.default()
+    config.nn.projection.phoneme_layer = PhonemeLayerType.SHARED
+    model_id = next(k for k in wav2vec2.KNOWN_MODELS if k.startswith("test/") and "num_hidden_layers2" in k)
+    config.nn.acoustic_model.model_id = model_id
+    names = [entry.name for entry in config.nn.projection.classes]
+    indexer = PhoneticAttributeIndexer.synthetic(80, names, training_inventory=50)
+    graph = attribute_graph_from_config(config, indexer)
+    estimator = Estimator.from_config(config, 1, 16000, graph, indexer, "cuda", load_pretrained_weights=False)
+    tfi = indexer.composition_feature_matrix(["p3", "p7", "p11", "p60"]).cuda()
+    first = estimator.predict(case["batch"], tfi)
+    buffer = io.BytesIO()
+    estimator.save(buffer, indexer)
+    buffer.seek(0)
+    checkpoint = torch.load(buffer, weights_only=True)
+    assert {"config", "allophant_version", "feature_size", "sample_rate", "attribute_graph", "epoch", "phonetic_indexer_state",
+            "dataset_meta_data", "model_state", "additional", "history", "optimization_states"} <= set(checkpoint)  # fmt: skip
+    assert len(checkpoint["model_state"]) == len(estimator.model.state_dict())
+    buffer.seek(0)
+    restored, restored_indexer = Estimator.restore(buffer, "cuda")
+    second = restored.predict(case["batch"], restored_indexer.composition_feature_matrix(["p3", "p7", "p11", "p60"]).cuda())
+    assert list(first.outputs) == list(second.outputs)
+    for name in first.outputs:
+        assert torch.equal(first.outputs[name], second.outputs[name]), name
+    assert second.outputs["phoneme"].shape[-1] == 5

@@ -1,0 +1,403 @@
+"""-m gpu: every C-ABI kernel against the CPU oracle / torch's own CPU ops on seeded inputs.
+
+Tolerances: integer / index results bit-exact; fp32 kernels 1e-3 relative (north_star) — in practice
+they sit at 1e-6; kernels with bf16 operands 2e-2 of the tensor's range.
+"""
+import math
+
+import pytest
+import torch
+from torch.nn import functional as F
+
+from oracle import restatement
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    from allophant_b200 import ops
+
+    return ops
+
+
+def range_err(value, reference):
+    reference = reference.double().cpu()
+    return float((value.double().cpu() - reference).abs().max() / reference.abs().max().clamp_min(1e-12))
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (1000, 1024, 1024), (333, 784, 1024), (77, 32, 640), (4096, 4096, 1024)])
+def test_gemm_plain(m, n, k):
+    ops = _ops()
+    torch.manual_seed(m + n + k)
+    a = (torch.randn(m, k, device=DEV) * 0.5).bfloat16()
+    w = (torch.randn(n, k, device=DEV) * 0.05).bfloat16()
+    bias = torch.randn(n, device=DEV)
+    out = ops.linear_bf16(a, w, bias, out_dtype=torch.float32)
+    reference = a.float() @ w.float().T + bias
+    assert range_err(out, reference) < 1e-4  # same bf16 inputs, fp32 accumulate: only summation order differs
+    out16 = ops.linear_bf16(a, w, bias, gelu=True)
+    assert range_err(out16, F.gelu(reference)) < 1e-2
+
+
+def test_gemm_residual_mask_and_scale():
+    ops = _ops()
+    torch.manual_seed(1)
+    m, n, k, period = 998, 1024, 512, 499
+    a = (torch.randn(m, k, device=DEV) * 0.5).bfloat16()
+    w = (torch.randn(n, k, device=DEV) * 0.05).bfloat16()
+    bias = torch.randn(n, device=DEV)
+    resid = torch.randn(m, n, device=DEV)
+    lengths = torch.tensor([300, 1], device=DEV, dtype=torch.int32)
+    out = resid.clone()
+    args = ops.make_gemm_args(
+        a, w, a_rows=m, a_inner=k, a_row_stride=k, bias=bias, scale=0.5, resid=out, ld_resid=n, out_f32=out, ld_f32=n, lengths=lengths, len_period=period
+    )
+    ops.run_gemm(args)
+    reference = (a.float() @ w.float().T) * 0.5 + bias + resid
+    rows = torch.arange(m, device=DEV)
+    reference[(rows % period) >= lengths[rows // period]] = 0
+    assert range_err(out, reference) < 1e-4
+
+
+@pytest.mark.parametrize("length_in,kernel,stride", [(1001, 3, 2), (3999, 3, 2), (999, 2, 2)])
+def test_gemm_strided_conv(length_in, kernel, stride):
+    """Implicit-GEMM Conv1d over a channels-last activation through an overlapping-row TMA view (HF:281-299)."""
+    ops = _ops()
+    torch.manual_seed(length_in)
+    n, c = 2, 512
+    x = (torch.randn(n, length_in, c, device=DEV) * 0.5).bfloat16()
+    weight = (torch.randn(c, c, kernel, device=DEV) * 0.03).bfloat16()
+    bias = torch.randn(c, device=DEV)
+    length_out = (length_in - kernel) // stride + 1
+    packed = ops.pack_conv_weight(weight.float())
+    out = torch.zeros(n, length_out, c, device=DEV, dtype=torch.bfloat16)
+    args = ops.make_gemm_args(
+        x, packed, a_rows=length_out, a_inner=kernel * c, a_row_stride=stride * c, batch=n, a_batch_stride=length_in * c, bias=bias,
+        out_bf16=out, ld_bf16=c, out_batch_rows=length_out,
+    )  # fmt: skip
+    ops.run_gemm(args)
+    reference = F.conv1d(x.float().cpu().transpose(1, 2), weight.float().cpu(), bias.cpu(), stride=stride).transpose(1, 2)
+    assert range_err(out, reference) < 1e-2
+
+
+@pytest.mark.parametrize("frames", [499, 130, 17])
+def test_gemm_positional_conv(frames):
+    """Grouped 128-tap positional conv + GELU + residual (HF:326-368, 764-765) incl. weight_norm packing."""
+    ops = _ops()
+    torch.manual_seed(frames)
+    n, c, groups, taps = 2, 1024, 16, 128
+    x = (torch.randn(n, frames, c, device=DEV) * 0.5).bfloat16()
+    v = torch.randn(c, c // groups, taps, device=DEV) * 0.02
+    g = torch.rand(1, 1, taps, device=DEV) + 0.5
+    bias = torch.randn(c, device=DEV)
+    packed = ops.pack_posconv_weight(g, v)
+    weight = (g * v / v.pow(2).sum(dim=(0, 1), keepdim=True).sqrt()).cpu()  # weight_norm(dim=2)
+    assert range_err(packed.float().view(c, taps, c // groups).permute(0, 2, 1), weight) < 1e-2
+    hidden = x.float().contiguous()
+    args = ops.make_gemm_args(
+        x, packed, a_rows=frames, a_inner=c, a_row_stride=c, batch=n, a_batch_stride=frames * c, mode=1, tap_pad=taps // 2, n=c,
+        k=taps * (c // groups), bias=bias, gelu=True, resid=hidden, ld_resid=c, out_f32=hidden, ld_f32=c, out_batch_rows=frames,
+    )  # fmt: skip
+    ops.run_gemm(args)
+    conv = F.conv1d(x.float().cpu().transpose(1, 2), packed.float().cpu().view(c, taps, c // groups).permute(0, 2, 1).contiguous(),
+                    bias.cpu(), padding=taps // 2, groups=groups)[:, :, :-1].transpose(1, 2)  # fmt: skip
+    reference = x.float().cpu() + F.gelu(conv)
+    assert range_err(hidden, reference) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("n,heads,frames,lengths", [(1, 1, 128, [128]), (2, 16, 499, [499, 300]), (3, 4, 749, [749, 1, 130]), (1, 2, 1499, [1000])])
+def test_attention(n, heads, frames, lengths):
+    ops = _ops()
+    torch.manual_seed(frames)
+    t_v = (frames + 7) // 8 * 8
+    q = torch.randn(n, heads, frames, 64, device=DEV).bfloat16()
+    k = torch.randn(n, heads, frames, 64, device=DEV).bfloat16()
+    v = torch.randn(n, heads, frames, 64, device=DEV).bfloat16()
+    vt = torch.zeros(n, heads, 64, t_v, device=DEV, dtype=torch.bfloat16)
+    vt[..., :frames] = v.transpose(2, 3)
+    q_scaled = (q.float() * 0.125).bfloat16()
+    ctx = torch.zeros(n * frames, heads * 64, device=DEV, dtype=torch.bfloat16)
+    frame_lengths = torch.tensor(lengths, device=DEV, dtype=torch.int32)
+    ops.attention(q_scaled, k, vt, ctx, frame_lengths, n, heads, frames, t_v)
+    mask = torch.arange(frames)[None, :] < torch.tensor(lengths)[:, None]
+    scores = (q_scaled.float().cpu() @ k.float().cpu().transpose(2, 3)).masked_fill(~mask[:, None, None, :], float("-inf"))
+    reference = (torch.softmax(scores, -1) @ v.float().cpu()).permute(0, 2, 1, 3).reshape(n, frames, heads * 64)
+    ours = ctx.float().cpu().view(n, frames, heads * 64)
+    for index, length in enumerate(lengths):
+        assert range_err(ours[index, :length], reference[index, :length]) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------ front end
+def test_wave_norm_and_frame_lengths():
+    ops = _ops()
+    lengths = torch.tensor([16000, 12345, 400, 10])
+    audio = restatement.synthetic_audio(4, 16000, seed=3) + 0.05
+    audio = audio * restatement.mask_sequence(lengths)
+    reference = restatement.zero_mean_unit_var_norm(audio, lengths, restatement.mask_sequence(lengths))
+    ours = ops.zero_mean_unit_var_norm(audio.cuda(), lengths.cuda())
+    assert range_err(ours, reference) < 1e-5
+    assert torch.equal(ours.cpu()[1, 12345:], torch.zeros(16000 - 12345))
+    kernels = torch.tensor(restatement.XLSR_300M["conv_kernel"], dtype=torch.int32, device=DEV)
+    strides = torch.tensor(restatement.XLSR_300M["conv_stride"], dtype=torch.int32, device=DEV)
+    many = torch.tensor([16000, 12345, 400, 10, 480000, 399, 401, 80000, 160000, 240000, 5, 0])
+    frames32 = torch.empty(len(many), dtype=torch.int32, device=DEV)
+    frames64 = torch.empty(len(many), dtype=torch.int64, device=DEV)
+    ops.frame_lengths(many.cuda(), kernels, strides, frames32, frames64)
+    expected = restatement.conv_lengths(many, restatement.XLSR_300M["conv_kernel"], restatement.XLSR_300M["conv_stride"])
+    assert torch.equal(frames64.cpu(), expected)
+    assert torch.equal(frames32.cpu().long(), expected)
+
+
+def test_conv0_layernorm_gelu():
+    ops = _ops()
+    torch.manual_seed(5)
+    lengths = torch.tensor([8000, 5003])
+    audio = restatement.synthetic_audio(2, 8000, seed=4) * restatement.mask_sequence(lengths)
+    weight = torch.randn(512, 1, 10) * 0.3
+    bias, gamma, beta = torch.randn(512) * 0.1, torch.rand(512) + 0.5, torch.randn(512) * 0.1
+    normalised = restatement.zero_mean_unit_var_norm(audio, lengths, restatement.mask_sequence(lengths))
+    conv = F.conv1d(normalised[:, None], weight, bias, stride=5).transpose(1, 2)
+    reference = F.gelu(F.layer_norm(conv, (512,), gamma, beta, 1e-5))
+    frames0 = (8000 - 10) // 5 + 1
+    stats = torch.empty(2, 3, dtype=torch.float64, device=DEV)
+    mean_rstd = torch.empty(2, 2, device=DEV)
+    ops.wave_stats(audio.cuda(), lengths.cuda(), stats, mean_rstd)
+    out = torch.zeros(2, frames0, 512, device=DEV, dtype=torch.bfloat16)
+    ops.conv0_ln_gelu(audio.cuda(), lengths.cuda(), mean_rstd, weight.view(512, 10).cuda(), bias.cuda(), gamma.cuda(), beta.cuda(), 1e-5, out)
+    valid = [(int(l) - 10) // 5 + 1 for l in lengths]
+    for index, frames in enumerate(valid):
+        assert range_err(out[index, :frames], reference[index, :frames]) < 1e-2
+    # frames that would read padding are skipped (buffer stays zero; a warp finishes its group of 4 frames) ...
+    assert float(out[1, (valid[1] + 3) // 4 * 4 :].float().abs().max()) == 0.0
+    # ... unless asked not to
+    ops.conv0_ln_gelu(audio.cuda(), lengths.cuda(), mean_rstd, weight.view(512, 10).cuda(), bias.cuda(), gamma.cuda(), beta.cuda(), 1e-5, out, False)
+    assert range_err(out, reference) < 1e-2
+
+
+def test_conv0_groupnorm_gelu():
+    """feat_extract_norm="group" (wav2vec2-base style, HF:302-323): per-channel statistics over the padded time axis."""
+    ops = _ops()
+    torch.manual_seed(6)
+    lengths = torch.tensor([6000, 4000])
+    audio = restatement.synthetic_audio(2, 6000, seed=7) * restatement.mask_sequence(lengths)
+    weight = torch.randn(512, 1, 10) * 0.3
+    gamma, beta = torch.rand(512) + 0.5, torch.randn(512) * 0.1
+    normalised = restatement.zero_mean_unit_var_norm(audio, lengths, restatement.mask_sequence(lengths))
+    conv = F.conv1d(normalised[:, None], weight, None, stride=5)
+    reference = F.gelu(F.group_norm(conv, 512, gamma, beta, 1e-5)).transpose(1, 2)
+    frames0 = conv.shape[-1]
+    stats = torch.empty(2, 3, dtype=torch.float64, device=DEV)
+    mean_rstd = torch.empty(2, 2, device=DEV)
+    ops.wave_stats(audio.cuda(), lengths.cuda(), stats, mean_rstd)
+    raw = torch.empty(2, frames0, 512, device=DEV)
+    gn_stats = torch.empty(2, 512, 2, dtype=torch.float64, device=DEV)
+    out = torch.zeros(2, frames0, 512, device=DEV, dtype=torch.bfloat16)
+    ops.conv0_gn_gelu(audio.cuda(), lengths.cuda(), mean_rstd, weight.view(512, 10).cuda(), None, gamma.cuda(), beta.cuda(), 1e-5, raw, gn_stats, out)
+    assert range_err(out, reference) < 1e-2
+
+
+@pytest.mark.parametrize("cols,dtype", [(512, torch.bfloat16), (1024, torch.float32), (1024, torch.bfloat16), (512, torch.float32)])
+def test_layernorm_rows(cols, dtype):
+    ops = _ops()
+    torch.manual_seed(cols)
+    rows = 1003
+    x = (torch.randn(rows, cols) * 2 + 0.3).to(dtype)
+    gamma, beta = torch.rand(cols) + 0.5, torch.randn(cols) * 0.1
+    reference = F.layer_norm(x.float(), (cols,), gamma, beta, 1e-5)
+    out32 = torch.empty(rows, cols, device=DEV)
+    out16 = torch.empty(rows, cols + 64, device=DEV, dtype=torch.bfloat16)
+    ops.layernorm_rows(x.cuda(), rows, cols, cols, gamma.cuda(), beta.cuda(), 1e-5, out_bf16=out16, ld_bf16=cols + 64, out_f32=out32, ld_f32=cols)
+    assert range_err(out32, reference) < 1e-5
+    assert range_err(out16[:, :cols], reference) < 1e-2
+    ops.layernorm_rows(x.cuda(), rows, cols, cols, gamma.cuda(), beta.cuda(), 1e-5, gelu=True, out_f32=out32, ld_f32=cols)
+    assert range_err(out32, F.gelu(reference)) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ heads
+def test_compose_embeddings_matches_embedding_bag():
+    ops = _ops()
+    torch.manual_seed(8)
+    spec = restatement.multitask_spec(n_train_phonemes=40)
+    oracle_table = torch.from_numpy(spec.feature_table).long()
+    num_categories = torch.cat((torch.LongTensor([0]), oracle_table.max(0).values)) + 1
+    offsets = num_categories.cumsum(0)[:-1]
+    bag = torch.nn.EmbeddingBag(int(num_categories.sum()), 640, mode="sum")
+    tfi = torch.randint(0, 3, (25, 36))
+    reference = torch.cat((bag(torch.zeros(1, 1, dtype=torch.long)), bag(tfi + offsets))).detach()
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    out32 = torch.empty(32, 640, device=DEV)
+    out16 = torch.empty(32, 640, device=DEV, dtype=torch.bfloat16)
+    ops.compose_embeddings(bag.weight.detach().cuda(), tfi.cuda(), offsets.cuda(), 32, err, out_bf16=out16, out_f32=out32)
+    assert int(err.item()) == 0
+    assert range_err(out32[:26], reference) < 1e-6
+    assert float(out32[26:].abs().max()) == 0.0
+    assert range_err(out16[:26], reference) < 1e-2
+    ops.compose_embeddings(bag.weight.detach().cuda(), (tfi + 5).cuda(), offsets.cuda(), 32, err, out_f32=out32)
+    assert int(err.item()) == 1  # out-of-range category is flagged, not read
+
+
+def test_log_softmax_heads_and_wide():
+    ops = _ops()
+    torch.manual_seed(9)
+    rows = 1000
+    widths = [4, 4, 3, 7, 26, 2, 64]
+    columns, position = [], 8
+    for width in widths:
+        columns.append(position)
+        position += width
+    ld = (position + 3) // 4 * 4
+    logits = torch.randn(rows, ld) * 3
+    logits[5, columns[0] : columns[0] + 4] = 1.25  # exact tie -> lowest index wins
+    out_offsets, total = [], 0
+    for width in widths:
+        out_offsets.append(total)
+        total += rows * width
+    out = torch.empty(total, device=DEV)
+    argmax = torch.empty(len(widths), rows, dtype=torch.int32, device=DEV)
+    maxlp = torch.empty(len(widths), rows, device=DEV)
+    ops.log_softmax_heads(
+        logits.cuda(), ld, rows, 8, ld - 8,
+        torch.tensor(columns, dtype=torch.int32, device=DEV), torch.tensor(widths, dtype=torch.int32, device=DEV),
+        torch.tensor(out_offsets, dtype=torch.int64, device=DEV), len(widths), out, argmax, maxlp,
+    )  # fmt: skip
+    for head, (column, width) in enumerate(zip(columns, widths)):
+        reference = F.log_softmax(logits[:, column : column + width], -1)
+        ours = out[out_offsets[head] : out_offsets[head] + rows * width].view(rows, width).cpu()
+        assert float((ours - reference).abs().max()) < 1e-5
+        values, indices = reference.max(-1)
+        assert torch.equal(argmax[head].cpu().long(), indices)
+        assert float((maxlp[head].cpu() - values).abs().max()) < 1e-5
+    assert int(argmax[0, 5]) == 0
+    # wide head
+    wide = torch.randn(300, 3184) * 4
+    out_wide = torch.empty(300, 3184, device=DEV)
+    arg_wide = torch.empty(300, dtype=torch.int32, device=DEV)
+    max_wide = torch.empty(300, device=DEV)
+    ops.log_softmax_wide(wide.cuda(), 3184, 300, 3184, out_wide, 3184, arg_wide, max_wide)
+    reference = F.log_softmax(wide, -1)
+    assert float((out_wide.cpu() - reference).abs().max()) < 1e-4
+    assert torch.equal(arg_wide.cpu().long(), reference.argmax(-1))
+    assert float(torch.logsumexp(out_wide, -1).abs().max()) < 1e-4  # rows are normalised
+    assert float((ops.log_softmax(wide.cuda().view(3, 100, 3184)).cpu() - reference.view(3, 100, 3184)).abs().max()) < 1e-4
+
+
+def test_dependency_softmax():
+    ops = _ops()
+    torch.manual_seed(10)
+    rows, ld = 500, 160
+    logits = torch.randn(rows, ld) * 2
+    columns, widths, targets = [0, 4, 100], [4, 4, 27], [1024, 1028, 1040]
+    for skip in (0, 1):
+        dst = torch.zeros(rows, 1088, dtype=torch.bfloat16, device=DEV)
+        ops.dependency_softmax(
+            logits.cuda(), ld, rows, torch.tensor(columns, dtype=torch.int32, device=DEV), torch.tensor(widths, dtype=torch.int32, device=DEV),
+            torch.tensor(targets, dtype=torch.int32, device=DEV), 3, skip, dst, 1088,
+        )  # fmt: skip
+        for column, width, target in zip(columns, widths, targets):
+            reference = torch.softmax(logits[:, column + skip : column + width], -1)
+            assert range_err(dst[:, target : target + width - skip], reference) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------ greedy decoding
+def test_greedy_decode_matches_oracle_exactly():
+    from allophant_b200.predictions import GreedyCTCDecoder
+
+    torch.manual_seed(11)
+    n, frames, classes = 6, 211, 5
+    emissions = F.log_softmax(torch.randn(n, frames, classes) * 2, -1)
+    emissions[0, :, 1:] -= 50  # all blank
+    emissions[1, :, 0] -= 50  # never blank
+    emissions[2, 10:40] = emissions[2, 10]  # one long run
+    lengths = torch.tensor([211, 200, 150, 1, 0, 33])
+    reference = restatement.greedy_ctc_decode(emissions, lengths)
+    ours = GreedyCTCDecoder()(emissions.cuda(), lengths.cuda())
+    for hypothesis, expected in zip(ours, reference):
+        assert torch.equal(hypothesis[0].tokens, expected[0].tokens)
+        assert torch.equal(hypothesis[0].timesteps, expected[0].timesteps)
+        assert abs(float(hypothesis[0].score) - float(expected[0].score)) < 1e-3 * max(1.0, abs(float(expected[0].score)))
+        assert hypothesis[0].words == []
+    # wide emissions use the warp-per-frame argmax
+    wide = F.log_softmax(torch.randn(2, 90, 300), -1)
+    lengths = torch.tensor([90, 45])
+    for hypothesis, expected in zip(GreedyCTCDecoder()(wide.cuda(), lengths.cuda()), restatement.greedy_ctc_decode(wide, lengths)):
+        assert torch.equal(hypothesis[0].tokens, expected[0].tokens)
+        assert torch.equal(hypothesis[0].timesteps, expected[0].timesteps)
+
+
+# ------------------------------------------------------------------------------------------ CTC
+def _ctc_case(seed, n, frames, class_counts, label_fraction, time_first=True):
+    generator = torch.Generator().manual_seed(seed)
+    input_lengths = torch.randint(frames // 2, frames + 1, (n,), generator=generator)
+    input_lengths[0] = frames
+    logits, labels, label_lengths = [], [], []
+    for head, classes in enumerate(class_counts):
+        shape = (frames, n, classes) if time_first else (n, frames, classes)
+        logits.append(torch.randn(*shape, generator=generator) * 2)
+        head_labels, head_lengths = restatement.synthetic_labels(input_lengths, classes, seed=seed * 31 + head, fraction=label_fraction)
+        labels.append(head_labels)
+        label_lengths.append(head_lengths)
+    return logits, labels, input_lengths, label_lengths
+
+
+@pytest.mark.parametrize("class_counts,fraction", [([4, 4, 3, 26], 0.25), ([4], 0.5), ([61, 500], 0.3), ([4, 40], 0.02)])
+def test_ctc_loss_and_gradient_match_torch(class_counts, fraction):
+    from allophant_b200.loss_functions import CTCWrapper, multi_head_ctc_loss
+
+    logits, labels, input_lengths, label_lengths = _ctc_case(len(class_counts), 5, 120, class_counts, fraction)
+    # make one utterance infeasible (labels longer than frames): zero_infinity must zero loss AND gradient
+    label_lengths[0][1] = min(int(labels[0].shape[1]), int(input_lengths[1]) + 5)
+    if label_lengths[0][1] <= input_lengths[1]:
+        input_lengths[1] = max(1, int(label_lengths[0][1]) - 1)
+    # repeated labels need an extra blank between them
+    labels[0][2, : max(1, int(label_lengths[0][2]))] = 1
+    reference_losses, reference_grads = [], []
+    for head_logits, head_labels, head_lengths in zip(logits, labels, label_lengths):
+        leaf = head_logits.clone().requires_grad_(True)
+        loss = restatement.ctc_wrapper(leaf, head_labels, input_lengths, head_lengths)
+        loss.backward()
+        reference_losses.append(float(loss))
+        reference_grads.append(leaf.grad)
+    leaves = [t.cuda().requires_grad_(True) for t in logits]
+    losses = multi_head_ctc_loss(leaves, [l.cuda() for l in labels], input_lengths.cuda(), [l.cuda() for l in label_lengths])
+    weights = torch.arange(1, len(class_counts) + 1, device=DEV, dtype=torch.float32)
+    (losses * weights).sum().backward()
+    for head in range(len(class_counts)):
+        assert abs(float(losses[head]) - reference_losses[head]) <= 1e-3 * max(1.0, abs(reference_losses[head]))
+        ours = leaves[head].grad.cpu() / float(weights[head])
+        scale = float(reference_grads[head].abs().max().clamp_min(1e-6))
+        assert float((ours - reference_grads[head]).abs().max()) <= 1e-3 * scale + 1e-5
+    # the drop-in single-head wrapper
+    single = CTCWrapper()(logits[0].cuda(), labels[0].cuda(), input_lengths.cuda(), label_lengths[0].cuda())
+    assert abs(float(single) - reference_losses[0]) <= 1e-3 * max(1.0, abs(reference_losses[0]))
+
+
+def test_ctc_long_labels_and_empty_targets():
+    from allophant_b200.loss_functions import multi_head_ctc_loss
+
+    logits, labels, input_lengths, label_lengths = _ctc_case(21, 3, 700, [4, 30], 0.45)
+    label_lengths[1][2] = 0  # empty target
+    leaves = [t.cuda().requires_grad_(True) for t in logits]
+    losses = multi_head_ctc_loss(leaves, [l.cuda() for l in labels], input_lengths.cuda(), [l.cuda() for l in label_lengths])
+    losses.sum().backward()
+    for head in range(2):
+        leaf = logits[head].clone().requires_grad_(True)
+        reference = restatement.ctc_wrapper(leaf, labels[head], input_lengths, label_lengths[head])
+        reference.backward()
+        # 700-frame log-space recursions in fp32 accumulate rounding (alpha ~ -1e3): judge both fp32
+        # implementations against the same recursion in fp64
+        leaf64 = logits[head].double().requires_grad_(True)
+        exact = restatement.ctc_wrapper(leaf64, labels[head], input_lengths, label_lengths[head])
+        exact.backward()
+        assert abs(float(losses[head]) - float(exact)) <= 1e-3 * abs(float(exact))
+        scale = float(leaf64.grad.abs().max())
+        ours_error = float((leaves[head].grad.cpu().double() - leaf64.grad).abs().max())
+        torch_error = float((leaf.grad.double() - leaf64.grad).abs().max())
+        print(f"ctc long head {head}: ours vs fp64 {ours_error:.2e}, torch fp32 vs fp64 {torch_error:.2e}")
+        assert ours_error <= max(3 * torch_error, 1e-3 * scale)
+        # size-independent property: on valid frames the gradient rows of a finite loss sum to zero
+        row_sums = leaves[head].grad.sum(-1).cpu()
+        assert float(row_sums.abs().max()) < 2e-3
