@@ -1,0 +1,97 @@
+"""Data-parallel plumbing: one process per GPU, utterances sharded across ranks.
+
+The reference has no distributed code.  The hot path shards by utterance (no
+cross-utterance op exists), so inference needs NO collective on the data path: every rank runs
+``Estimator.predict`` on its own shard and only the decoded hypotheses (host objects) are gathered.
+Training adds the two real exchange steps of §8e: a sum all-reduce of the gradient buckets and of
+the scalar loss normaliser (``estimator.py:737`` divides by the label count of the WHOLE batch).
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from .dataset_processing import Batch
+
+
+def shard_indices(lengths: Sequence[int], world_size: int) -> List[List[int]]:
+    """Length-balanced assignment: utterances sorted by length (longest first), dealt round-robin in
+    serpentine order so every rank gets a similar number of samples and padding stays small."""
+    order = sorted(range(len(lengths)), key=lambda index: (-int(lengths[index]), index))
+    shards: List[List[int]] = [[] for _ in range(world_size)]
+    for position, index in enumerate(order):
+        round_index, slot = divmod(position, world_size)
+        rank = slot if round_index % 2 == 0 else world_size - 1 - slot
+        shards[rank].append(index)
+    return shards
+
+
+def shard_batch(batch: Batch, rank: int, world_size: int) -> Tuple[Batch, List[int]]:
+    """The sub-batch of ``rank`` (re-padded to its own longest utterance) and the original indices."""
+    lengths = batch.lengths.tolist()
+    indices = shard_indices(lengths, world_size)[rank]
+    if not indices:
+        return Batch(batch.audio_features[:0], batch.lengths[:0], batch.language_ids[:0]), indices
+    select = torch.tensor(indices, device=batch.lengths.device)
+    longest = max(lengths[i] for i in indices)
+    return (
+        Batch(
+            batch.audio_features.index_select(0, select)[:, :longest].contiguous(),
+            batch.lengths.index_select(0, select),
+            batch.language_ids.index_select(0, select),
+        ),
+        indices,
+    )
+
+
+def gather_by_index(local: Dict[int, Any], group: Optional[dist.ProcessGroup] = None) -> Dict[int, Any]:
+    """Gathers per-utterance host results (e.g. decoded hypotheses) from every rank, keyed by original index."""
+    if not dist.is_available() or not dist.is_initialized():
+        return dict(local)
+    gathered: List[Optional[Dict[int, Any]]] = [None] * dist.get_world_size(group)
+    dist.all_gather_object(gathered, local, group=group)
+    merged: Dict[int, Any] = {}
+    for part in gathered:
+        merged.update(part or {})
+    return merged
+
+
+def allreduce_gradients(parameters: Iterable[Tensor], bucket_bytes: int = 48 << 20, group: Optional[dist.ProcessGroup] = None) -> int:
+    """Sum all-reduce of ``.grad`` in flat buckets (≈48 MB: a few launches, each far above NCCL's latency floor).
+    Returns the number of collectives issued."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    grads = [p.grad for p in parameters if p.grad is not None]
+    issued, bucket, size = 0, [], 0
+
+    def flush() -> None:
+        nonlocal issued, bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([g.reshape(-1) for g in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        offset = 0
+        for g in bucket:
+            g.copy_(flat[offset : offset + g.numel()].view_as(g))
+            offset += g.numel()
+        issued += 1
+        bucket, size = [], 0
+
+    for grad in grads:
+        bucket.append(grad)
+        size += grad.numel() * grad.element_size()
+        if size >= bucket_bytes:
+            flush()
+    flush()
+    return issued
+
+
+def global_label_count(local_label_lengths: Sequence[Tensor], group: Optional[dist.ProcessGroup] = None) -> Tensor:
+    """Σ label lengths over all heads and all ranks — the divisor of the step loss (``estimator.py:737``)."""
+    total = torch.stack([lengths.sum() for lengths in local_label_lengths]).sum().to(torch.float64)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    return total

@@ -1,0 +1,135 @@
+"""CPU: host-side mirror of the reference interface (graph order, config schema, batch containers, layouts)."""
+import random
+
+import pytest
+import torch
+
+from oracle import restatement
+from tests import helpers
+
+
+def test_attribute_graph_order_matches_reference_order():
+    from allophant_b200.attribute_graph import AttributeGraph, AttributeNode, DependencyCycleError
+
+    # golden head orders come from the reference's own AttributeGraph.sort()
+    for case in ("multitask_2layer", "hierarchical_2layer"):
+        fixture = helpers.load_golden(case)
+        spec = helpers.spec_for_case(fixture["case_config"])
+        graph = AttributeGraph(AttributeNode(c.name, c.size, None, list(c.dependencies)) for c in spec.classes)
+        assert [node.name for node in graph.sort()] == fixture["head_order"]
+    # random DAGs: same order as the restated Tarjan post-order
+    generator = random.Random(3)
+    for _ in range(50):
+        count = generator.randint(1, 12)
+        classes = []
+        for index in range(count):
+            dependencies = ["OUTPUT"] + [f"n{j}" for j in range(index + 1, count) if generator.random() < 0.3]
+            generator.shuffle(dependencies)
+            classes.append(restatement.ClassSpec(f"n{index}", generator.randint(1, 5), dependencies))
+        graph = AttributeGraph(AttributeNode(c.name, c.size, None, list(c.dependencies)) for c in classes)
+        assert [n.name for n in graph.sort()] == [c.name for c in restatement.topological_order(classes)]
+        restored = AttributeGraph.from_state(graph.state())
+        assert [n.name for n in restored.sort()] == [n.name for n in graph.sort()]
+    with pytest.raises(DependencyCycleError):
+        list(AttributeGraph([AttributeNode("a", 1, None, ["b"]), AttributeNode("b", 1, None, ["a"])]).sort())
+
+
+def test_config_schema_roundtrip_and_defaults():
+    from allophant_b200.config import Config, PhonemeLayerType, ProjectionEntryConfig
+
+    config = Config.default()
+    assert len(config.nn.projection.classes) == 37
+    assert config.nn.projection.classes[-1].name == ProjectionEntryConfig.PHONEME_LAYER
+    assert config.nn.projection.embedding_composition.embedding_size == 640
+    assert config.nn.projection.phoneme_layer == PhonemeLayerType.ALLOPHONES
+    assert config.nn.projection.acoustic_model_dropout == 0.2
+    assert config.nn.acoustic_model.model_id == "facebook/wav2vec2-xls-r-300m" and config.nn.acoustic_model.freeze_feature_encoder
+    assert config.nn.loss.BLANK_OFFSET == 1
+    dumped = config.dump()
+    assert Config.load(dumped).dump() == dumped
+    assert dumped["nn"]["acoustic_model"]["type"] == "wav2vec2-pretrained" and dumped["nn"]["loss"]["type"] == "CTC"
+    minimal = {"nn": {"batch_size": 8, "projection": {"classes": [{"name": "phoneme"}]},
+                      "acoustic_model": {"type": "wav2vec2-pretrained", "model_id": "facebook/wav2vec2-xls-r-300m"}}}  # fmt: skip
+    loaded = Config.load(minimal)
+    assert loaded.nn.projection.classes[0].dependencies == ["OUTPUT"] and loaded.nn.projection.dependency_blanks
+    assert ProjectionEntryConfig.OUTPUT_PATTERN.match("OUTPUT_12").group(1) == "12"
+
+
+def test_batch_containers_and_length_helpers():
+    from allophant_b200.dataset_processing import Batch, LabeledBatch
+    from allophant_b200.network.frontend import conv_length
+    from allophant_b200.utils import mask_sequence
+
+    lengths = torch.tensor([5, 3, 0])
+    assert torch.equal(mask_sequence(lengths), restatement.mask_sequence(lengths))
+    assert torch.equal(mask_sequence(lengths, inverse=True), restatement.mask_sequence(lengths, inverse=True))
+    assert mask_sequence(lengths, 7, batch_first=False).shape == (7, 3)
+    samples = torch.tensor([16000, 400, 399, 160000, 10])
+    folded = samples
+    for kernel, stride in zip(restatement.XLSR_300M["conv_kernel"], restatement.XLSR_300M["conv_stride"]):
+        folded = conv_length(kernel, stride, use_padding=False)(folded)
+    assert torch.equal(folded, restatement.conv_lengths(samples, restatement.XLSR_300M["conv_kernel"], restatement.XLSR_300M["conv_stride"]))
+    batch = Batch(torch.zeros(2, 8), torch.tensor([8, 4]), torch.zeros(2, dtype=torch.long))
+    assert len(batch) == 2 and batch.size() == 2 and "Features" in repr(batch)
+    moved = batch.to("cpu", copy=True)
+    assert isinstance(moved, Batch) and moved.audio_features.data_ptr() != batch.audio_features.data_ptr()
+    labeled = LabeledBatch(batch.audio_features, batch.lengths, batch.language_ids, [{"phoneme": torch.ones(2, 3, dtype=torch.long)}],
+                           [torch.tensor([[3, 2]])], {"phoneme": 0})  # fmt: skip
+    moved = labeled.to("cpu")
+    assert isinstance(moved, LabeledBatch) and moved.label_length_indices == {"phoneme": 0}
+    assert [f.name for f in __import__("dataclasses").fields(LabeledBatch)] == [
+        "audio_features", "lengths", "language_ids", "attribute_indices", "label_lengths", "label_length_indices"]  # fmt: skip
+
+
+@pytest.mark.parametrize("case", ["multitask_2layer", "hierarchical_2layer", "allophones_2layer"])
+def test_state_dict_layout_is_the_reference_layout(case):
+    fixture = helpers.load_golden(case)
+    spec = helpers.spec_for_case(fixture["case_config"])
+    oracle = restatement.OracleModel(spec)
+    model, _ = helpers.cuda_model_for_spec(spec, oracle, device="cpu")  # construction + load_state_dict only
+    ours = model.state_dict()
+    reference = oracle.state_dict()
+    assert sorted(ours) == sorted(reference)
+    for key, value in reference.items():
+        assert ours[key].shape == value.shape, key
+        assert torch.equal(ours[key], value), key
+    assert model.classes == [c.name for c in spec.classes]
+    assert model.d_model == 1024 and model.feature_size == 1 and model.upscale_factor == 1
+    assert model.l2_penalty() is None
+    assert torch.equal(model.downsampled_lengths(torch.tensor([16000, 8000])), torch.tensor([49, 24]))
+    # frozen feature encoder (default) and trainable rest
+    assert not any(p.requires_grad for p in model.acoustic_model.model.feature_extractor.parameters())
+    assert all(p.requires_grad for p in model.acoustic_model.model.encoder.parameters())
+    # the forward path refuses to run off-GPU instead of falling back
+    from allophant_b200.dataset_processing import Batch
+
+    with pytest.raises(RuntimeError, match="CUDA"), torch.inference_mode():
+        model(Batch(torch.zeros(1, 4000), torch.tensor([4000]), torch.zeros(1, dtype=torch.long)), predict=True)
+
+
+def test_heads_layout_for_dependency_graph():
+    fixture = helpers.load_golden("hierarchical_2layer")
+    spec = helpers.spec_for_case(fixture["case_config"])
+    oracle = restatement.OracleModel(spec)
+    model, _ = helpers.cuda_model_for_spec(spec, oracle, device="cpu")
+    runtime = model._heads
+    runtime._build_layout()
+    # X = [OUTPUT(1024) | 36 x softmax(4) | pad] -> 1168 columns rounded up to a multiple of 64
+    assert runtime.ldx == 1216 and len(runtime.levels) == 2
+    assert runtime.dep_cols["stress"] == (1024, 4) and len(runtime.dep_cols) == 36
+    assert [s.name for s in runtime.levels[1].specs] == ["phoneme"] and runtime.levels[0].n_pad == 144
+    assert runtime.levels[0].feeds_later == [s.name for s in runtime.levels[0].specs]
+
+
+def test_error_behaviour_mirrors_reference():
+    from allophant_b200.attribute_graph import AttributeGraph, AttributeNode
+    from allophant_b200.config import EmbeddingCompositionConfig
+    from allophant_b200.network.acoustic_model import HierarchicalProjection
+
+    with pytest.raises(ValueError, match="reserved keyword"):
+        HierarchicalProjection(1024, AttributeGraph([AttributeNode("OUTPUT", 3, None, ["OUTPUT"])]), 1)
+    with pytest.raises(ValueError, match="requires a dependency"):
+        HierarchicalProjection(1024, AttributeGraph([AttributeNode("a", 3, None, [])]), 1)
+    with pytest.raises(ValueError, match="requires an attribute indexer"):
+        HierarchicalProjection(1024, AttributeGraph([AttributeNode("phoneme", 3, None, ["OUTPUT"])]), 1,
+                               embedding_composition_config=EmbeddingCompositionConfig(64))  # fmt: skip

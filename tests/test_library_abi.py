@@ -1,0 +1,69 @@
+"""CPU: the C-ABI library loads without a GPU and exports every symbol include/allophant_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "allophant_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(aph_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_entry_points():
+    symbols = declared_symbols()
+    for required in ("aph_gemm_bf16", "aph_attention_bf16", "aph_ctc_forward", "aph_ctc_backward", "aph_ctc_greedy_collapse",
+                     "aph_log_softmax_heads", "aph_conv0_ln_gelu", "aph_wave_stats", "aph_compose_embeddings"):  # fmt: skip
+        assert required in symbols
+
+
+def test_library_exports_every_declared_symbol():
+    from allophant_b200 import _lib
+
+    assert os.path.exists(_lib.LIB_PATH)
+    for symbol in declared_symbols():
+        assert hasattr(_lib.lib, symbol), f"{symbol} is declared in the header but not exported"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared_symbols(), "ctypes signatures and header disagree"
+    assert _lib.lib.aph_abi_version() == 1
+
+
+def test_argument_validation_needs_no_gpu():
+    """Launchers validate before touching CUDA and report through aph_last_error()."""
+    from allophant_b200 import _lib
+
+    args = _lib.GemmArgs()
+    rc = _lib.lib.aph_gemm_bf16(ctypes.byref(args), None)
+    assert rc == _lib.APH_ERR_INVALID
+    assert b"null operand" in _lib.lib.aph_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(rc, "aph_gemm_bf16")
+    assert _lib.lib.aph_ctc_states_pad(100) == 256
+    assert _lib.lib.aph_ctc_states_pad(511) == 1024
+    assert _lib.lib.aph_ctc_states_pad(512) == _lib.APH_ERR_UNSUPPORTED
+
+
+def test_no_cpu_fallback():
+    """The product path fails loudly off-GPU instead of silently computing on the CPU."""
+    import torch
+
+    from allophant_b200 import ops
+    from allophant_b200.predictions import GreedyCTCDecoder
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.log_softmax(torch.zeros(4, 4))
+    with pytest.raises(RuntimeError, match="GPU"):
+        GreedyCTCDecoder()(torch.zeros(1, 4, 4), torch.tensor([4]))
+
+
+def test_product_never_imports_the_oracle():
+    package = os.path.join(ROOT, "allophant_b200")
+    for directory, _, files in os.walk(package):
+        for name in files:
+            if name.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(directory, name), errors="replace").read()
+                assert "import oracle" not in text and "from oracle" not in text, f"{name} imports the oracle"
