@@ -22,8 +22,10 @@ constexpr int kAttQ = 128;    // query rows per CTA
 constexpr int kAttKV = 128;   // keys per block
 constexpr int kAttD = 64;     // head dim
 constexpr int kAttTileBytes = 128 * 64 * 2;  // 16 KB
+// 7 tiles + barriers = 114,944 B: two CTAs fit one SM (2 x (114,944 + 1,024 reserved) <= 233,472), so the
+// tensor core works on one CTA's MMAs while the other CTA's warps are in the softmax.
 constexpr int kAttSmemBytes = kAttTileBytes /*Q*/ + 2 * kAttTileBytes /*K*/ + 2 * kAttTileBytes /*Vt*/ +
-                              2 * kAttTileBytes /*P*/ + 1024 /*align*/ + 256 /*barriers*/;
+                              2 * kAttTileBytes /*P*/ + 256 /*barriers*/;
 constexpr uint32_t kAttTmemCols = 256;  // S: [0,128)  PV: [128,192)
 
 struct AttParams {
@@ -33,7 +35,7 @@ struct AttParams {
   int heads;
 };
 
-__global__ void __launch_bounds__(kAttThreads, 1)
+__global__ void __launch_bounds__(kAttThreads, 2)
     attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                      const __grid_constant__ CUtensorMap tm_v, const AttParams p) {
   const int bh = blockIdx.y;
@@ -45,9 +47,11 @@ __global__ void __launch_bounds__(kAttThreads, 1)
   if (q0 >= len) return;  // whole tile is padding (uniform per CTA, before any barrier/TMEM use)
   const int n_kv = (len + kAttKV - 1) / kAttKV;
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) {  // 128B-swizzled tiles need 1024-byte alignment
+    if (threadIdx.x == 0) printf("aph: attention shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   uint8_t* s_q = smem;
   uint8_t* s_k = s_q + kAttTileBytes;       // 2 stages
   uint8_t* s_v = s_k + 2 * kAttTileBytes;   // 2 stages, each two 8 KB halves (keys 0-63 / 64-127)
@@ -142,7 +146,6 @@ __global__ void __launch_bounds__(kAttThreads, 1)
     // ===================== softmax / output (one query row per thread) =====================
     const int r = warp * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-    constexpr float kLog2e = 1.4426950408889634f;
     float m_run = -INFINITY;
     float l_run = 0.f;
     float o[kAttD];
@@ -155,34 +158,43 @@ __global__ void __launch_bounds__(kAttThreads, 1)
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int key0 = j * kAttKV;
-      // pass 1: row max
-      float m_blk = -INFINITY;
+      const bool full_block = key0 + kAttKV <= len;  // no padded keys in this block (CTA-uniform)
+      // pass 1: row max (scores are already in the log2 domain: q carries head_dim^-0.5 * log2(e))
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
       for (int c0 = 0; c0 < kAttKV; c0 += 32) {
         float v[32];
         tmem_ld32(tmem_s + lane_off + static_cast<uint32_t>(c0), v);
         tmem_ld_wait();
+        if (full_block) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = (key0 + c0 + i < len) ? v[i] : -INFINITY;
-          m_blk = fmaxf(m_blk, s);
+          for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], v[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], (key0 + c0 + i < len) ? v[i] : -INFINITY);
         }
       }
-      const float m_new = fmaxf(m_run, m_blk);
-      const float alpha = exp2f((m_run - m_new) * kLog2e);
-      const float m_scaled = m_new * kLog2e;
+      const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])));
+      const float alpha = exp2f(m_run - m_new);
       // pass 2: probabilities -> smem (bf16, swizzled K-major), row sum
-      float l_blk = 0.f;
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int c0 = 0; c0 < kAttKV; c0 += 32) {
         float v[32];
         tmem_ld32(tmem_s + lane_off + static_cast<uint32_t>(c0), v);
         tmem_ld_wait();
+        if (full_block) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = (key0 + c0 + i < len) ? exp2f(fmaf(v[i], kLog2e, -m_scaled)) : 0.f;
-          v[i] = e;
-          l_blk += e;
+          for (int i = 0; i < 32; ++i) {
+            v[i] = exp2f(v[i] - m_new);
+            ls[i & 3] += v[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v[i] = (key0 + c0 + i < len) ? exp2f(v[i] - m_new) : 0.f;
+            ls[i & 3] += v[i];
+          }
         }
         uint8_t* dst_half = p_row + (c0 >> 6) * kAttTileBytes;
         const int chunk0 = (c0 & 63) >> 3;
@@ -196,7 +208,7 @@ __global__ void __launch_bounds__(kAttThreads, 1)
           *reinterpret_cast<uint4*>(dst_half + (((chunk0 + i) ^ sw) << 4)) = o4;
         }
       }
-      l_run = l_run * alpha + l_blk;
+      l_run = l_run * alpha + ((ls[0] + ls[1]) + (ls[2] + ls[3]));
       m_run = m_new;
       fence_proxy_async_smem();  // P visible to the tensor core's smem reads
       tc_fence_before();         // our TMEM reads of S are ordered before the next S = Q K^T

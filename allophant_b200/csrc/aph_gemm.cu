@@ -5,8 +5,9 @@
 // Roles inside one 192-thread CTA (one CTA per SM, persistent over output tiles):
 //   warp 0      TMA producer: A tile 128x64 + B tile BNx64 per stage, 128B swizzle
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16)
-//   warps 2..5  epilogue: tcgen05.ld the accumulator (one TMEM lane quadrant each),
-//               bias / GELU / residual / padding mask, vectorised global stores
+//   warps 2..9  epilogue: tcgen05.ld the accumulator (TMEM lane quadrant = warp % 4, two warps
+//               per quadrant split the tile's columns), bias / GELU / residual / padding
+//               mask, vectorised global stores
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM double buffer tfull/tempty
 // (MMA <-> epilogue) so the epilogue of tile i overlaps the mainloop of tile i+1.
 //
@@ -25,7 +26,7 @@ namespace aph {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kSmemBudget = 200 * 1024;
 
 struct GemmParams {
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 128);
+      mbar_init(&tempty_bar[s], 256);
     }
     fence_mbar_init();
   }
@@ -172,8 +173,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       }
     }
   } else {
-    // ===================== epilogue (4 warps, 128 rows) =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===================== epilogue (8 warps: 128 rows x 2 column halves) =====================
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;    // which half of the tile's columns this warp drains
     const int r = quad * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       const uint32_t taddr0 =
           tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
         const int col = n_blk * BN + c0;
         if (col >= p.n) break;  // warp-uniform
         float v[32];

@@ -109,7 +109,7 @@ def make_qkv_args(
     g.bias = bias_qkv.data_ptr()
     g.len_period = seq
     g.q, g.kmat, g.vt = q.data_ptr(), k.data_ptr(), vt.data_ptr()
-    g.heads, g.t_v, g.q_scale = heads, t_v, 0.125
+    g.heads, g.t_v, g.q_scale = heads, t_v, 0.125 * 1.4426950408889634  # head_dim^-0.5 * log2(e)
     return g
 
 

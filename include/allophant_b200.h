@@ -99,7 +99,8 @@ int aph_gemm_bf16(const aph_gemm_args* args, void* stream);
 /* ---- variable-length self-attention (tcgen05, flash-style online softmax) --- */
 /* Replaces the SDPA call of Wav2Vec2Attention (HF:466-549) and the dense
  * additive mask of HF:758-762: keys t >= lengths[b] get probability 0.
- *   q, k : bf16 [n_utt*heads][T][64]   (q already scaled by head_dim^-0.5)
+ *   q, k : bf16 [n_utt*heads][T][64]   (q already scaled by head_dim^-0.5 * log2(e): the kernel
+ *          exponentiates with exp2)
  *   vt   : bf16 [n_utt*heads][64][t_v] (V transposed, keys contiguous, t_v % 8 == 0,
  *          columns [T, t_v) must be finite)
  *   ctx  : bf16 [n_utt*T][heads*64]    rows of padded query tiles are left untouched

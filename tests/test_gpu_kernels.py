@@ -119,12 +119,12 @@ def test_attention(n, heads, frames, lengths):
     v = torch.randn(n, heads, frames, 64, device=DEV).bfloat16()
     vt = torch.zeros(n, heads, 64, t_v, device=DEV, dtype=torch.bfloat16)
     vt[..., :frames] = v.transpose(2, 3)
-    q_scaled = (q.float() * 0.125).bfloat16()
+    q_scaled = (q.float() * 0.125 * math.log2(math.e)).bfloat16()  # the kernel works in the log2 domain
     ctx = torch.zeros(n * frames, heads * 64, device=DEV, dtype=torch.bfloat16)
     frame_lengths = torch.tensor(lengths, device=DEV, dtype=torch.int32)
     ops.attention(q_scaled, k, vt, ctx, frame_lengths, n, heads, frames, t_v)
     mask = torch.arange(frames)[None, :] < torch.tensor(lengths)[:, None]
-    scores = (q_scaled.float().cpu() @ k.float().cpu().transpose(2, 3)).masked_fill(~mask[:, None, None, :], float("-inf"))
+    scores = (q_scaled.float().cpu() / math.log2(math.e) @ k.float().cpu().transpose(2, 3)).masked_fill(~mask[:, None, None, :], float("-inf"))
     reference = (torch.softmax(scores, -1) @ v.float().cpu()).permute(0, 2, 1, 3).reshape(n, frames, heads * 64)
     ours = ctx.float().cpu().view(n, frames, heads * 64)
     for index, length in enumerate(lengths):

@@ -22,7 +22,7 @@ def case(N, H, T, lengths, iters=0):
     v = (torch.randn(N, H, T, 64, device=dev)).bfloat16()
     vt = torch.zeros(N, H, 64, tv, device=dev).bfloat16()
     vt[..., :T] = v.transpose(2, 3)
-    qs = (q.float() * 0.125).bfloat16()
+    qs = (q.float() * 0.125 * 1.4426950408889634).bfloat16()
     ctx = torch.zeros(N * T, H * 64, device=dev).bfloat16()
     len_t = torch.tensor(lengths, device=dev, dtype=torch.int32)
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -30,7 +30,7 @@ def case(N, H, T, lengths, iters=0):
     L.check(rc, "aph_attention_bf16")
     torch.cuda.synchronize()
     mask = torch.arange(T, device=dev)[None, :] < len_t[:, None]  # [N, T]
-    s = (qs.float() @ k.float().transpose(2, 3))
+    s = (qs.float() / 1.4426950408889634 @ k.float().transpose(2, 3))
     s = s.masked_fill(~mask[:, None, None, :], float("-inf"))
     ref = torch.softmax(s, -1) @ v.float()  # [N,H,T,64]
     ref = ref.permute(0, 2, 1, 3).reshape(N, T, H * 64)
