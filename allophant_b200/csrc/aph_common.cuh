@@ -148,6 +148,27 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// ---- thread-block clusters -------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// One CTA of the cluster fetches the box once from L2; the hardware writes it to the same smem
+// offset of every CTA in `cta_mask` and completes tx bytes on each of their mbarriers.
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
+                                                      int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+
 // ---- tcgen05 / TMEM --------------------------------------------------------
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {
@@ -186,6 +207,14 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
                : "memory");
+}
+// Same, arriving on the barrier at this smem offset in every CTA of `cta_mask`.
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -233,8 +262,26 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
 }
 
 // ---- math ------------------------------------------------------------------
+// Exact-form GELU 0.5 x (1 + erf(x / sqrt 2)) (torch's default, HF "gelu").  erf is evaluated with
+// Abramowitz-Stegun 7.1.28, erf(u) = 1 - (1 + a1 u + ... + a6 u^6)^-16 (|error| <= 3e-7, i.e. fp32
+// round-off of the GELU): 15 FMA-pipe instructions and ONE MUFU op per element.  erff() costs ~25
+// instructions and two MUFU ops, which made the FFN1 epilogue longer than its mainloop.
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  const float u = fabsf(x) * 0.70710678118654752440f;
+  float d = fmaf(0.0000430638f, u, 0.0002765672f);
+  d = fmaf(d, u, 0.0001520143f);
+  d = fmaf(d, u, 0.0092705272f);
+  d = fmaf(d, u, 0.0422820123f);
+  d = fmaf(d, u, 0.0705230784f);
+  d = fmaf(d, u, 1.0f);
+  d *= d;
+  d *= d;
+  d *= d;
+  d *= d;  // ^16 (overflows to +inf for |x| > ~25, where the reciprocal below is exactly 0)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), 1.0f - r, hx);  // 0.5 x + 0.5 |x| erf(|x|/sqrt2) = 0.5 x (1 + erf(x/sqrt2))
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
