@@ -104,13 +104,15 @@ _SIGNATURES = {
     "aph_cast_bf16_2d": [_P, _I64, _P, _I64, _I64, _I32, _P],
     "aph_pack_conv_weight": [_P, _P, _I32, _I32, _I32, _P],
     "aph_pack_posconv_weight": [_P, _P, _P, _P, _I32, _I32, _I32, _P],
+    "aph_edit_statistics_batch": [_P, _P, _P, _P, _I64, _P, _P, _I32],
     "aph_ctc_states_pad": [_I32],
     "aph_ctc_forward": [_P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
     "aph_ctc_backward": [_P, POINTER(CtcHead), _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
 }
 
 EXPORTED_SYMBOLS = sorted(
-    list(_SIGNATURES) + ["aph_abi_version", "aph_last_error", "aph_launch_count", "aph_reset_launch_count"]
+    list(_SIGNATURES)
+    + ["aph_abi_version", "aph_last_error", "aph_launch_count", "aph_reset_launch_count", "aph_word_error_rate"]
 )
 
 
@@ -126,6 +128,8 @@ def _load() -> ctypes.CDLL:
     lib.aph_last_error.restype = c_char_p
     lib.aph_launch_count.restype = c_int64
     lib.aph_reset_launch_count.restype = None
+    lib.aph_word_error_rate.argtypes = [ctypes.c_uint64] * 4
+    lib.aph_word_error_rate.restype = c_float
     for name, argtypes in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

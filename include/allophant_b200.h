@@ -243,6 +243,21 @@ int aph_ctc_backward(const aph_ctc_head* heads_dev, const aph_ctc_head* heads_ho
                      const int64_t* input_lengths, const float* alpha_ws, const float* nll,
                      const float* grad_scale, void* stream);
 
+/* ---- edit distance (host) --------------------------------------------------------- */
+/* Batched replacement of the Rust extension `allophant.phonemes` (src/edit_distance.rs):
+ * levensthein (70-96) and levensthein_statistics (601-608 -> 372-481, uniform costs 483-496)
+ * over int64 symbol ids. Pair p compares expected[expected_offsets[p]:expected_offsets[p+1]]
+ * with actual[actual_offsets[p]:actual_offsets[p+1]]; statistics rows are
+ * {insertions, deletions, substitutions, correct}. ALL POINTERS ARE HOST POINTERS; the work is
+ * spread over n_threads host threads (<= 0: all cores). Either output may be NULL. */
+int aph_edit_statistics_batch(const int64_t* expected_host, const int64_t* expected_offsets_host,
+                              const int64_t* actual_host, const int64_t* actual_offsets_host,
+                              int64_t n_pairs, uint64_t* statistics_host,
+                              uint64_t* distances_host, int32_t n_threads);
+/* EditStatistics.word_error_rate (src/edit_distance.rs:311-317): (S+D+I)/(S+D+C) in f32. */
+float aph_word_error_rate(uint64_t insertions, uint64_t deletions, uint64_t substitutions,
+                          uint64_t correct);
+
 #ifdef __cplusplus
 }
 #endif
