@@ -147,6 +147,97 @@ __global__ void __launch_bounds__(256) log_softmax_wide_kernel(const float* __re
   }
 }
 
+// Same contract, rows moved by the TMA engine: every warp double-buffers whole rows in shared memory
+// (cp.async.bulk global->smem signalled on an mbarrier), makes one online max/sum pass and one
+// in-place normalisation pass over smem with 16-byte accesses, and writes the row back with a bulk
+// smem->global store.  HBM sees each element once in and once out; no register staging, the loads
+// of row i+1 and the store of row i-1 overlap the arithmetic of row i.  Needs 16-byte aligned rows.
+constexpr int kLsmBulkWarps = 4;
+
+__global__ void __launch_bounds__(kLsmBulkWarps * 32) log_softmax_wide_bulk_kernel(const float* __restrict__ logits, long long ld,
+                                                                                   long long rows, int width,
+                                                                                   float* __restrict__ out, long long ld_out,
+                                                                                   int* __restrict__ argmax_out,
+                                                                                   float* __restrict__ maxlp_out) {
+  extern __shared__ __align__(16) uint8_t lsm_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t row_bytes = static_cast<uint32_t>(width) * 4u;
+  const uint32_t buf_bytes = (row_bytes + 127u) & ~127u;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lsm_smem);  // [warps][2]
+  float* bufs = reinterpret_cast<float*>(lsm_smem + 128);
+  float* buf0 = bufs + static_cast<size_t>(warp) * 2 * (buf_bytes / 4);
+  uint64_t* bar = bars + warp * 2;
+  if (lane == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  const long long first = static_cast<long long>(blockIdx.x) * kLsmBulkWarps + warp;
+  const long long step = static_cast<long long>(gridDim.x) * kLsmBulkWarps;
+  if (first >= rows) return;
+  if (lane == 0) {
+    mbar_arrive_expect_tx(&bar[0], row_bytes);
+    bulk_load_1d(buf0, logits + first * ld, row_bytes, &bar[0]);
+  }
+  const int n_vec = width >> 2;
+  int it = 0;
+  for (long long row = first; row < rows; row += step, ++it) {
+    const int cur = it & 1;
+    float* buf = buf0 + cur * (buf_bytes / 4);
+    const long long next = row + step;
+    if (next < rows && lane == 0) {
+      bulk_store_wait_read<0>();  // the store that last read the other buffer has drained it
+      mbar_arrive_expect_tx(&bar[cur ^ 1], row_bytes);
+      bulk_load_1d(buf0 + (cur ^ 1) * (buf_bytes / 4), logits + next * ld, row_bytes, &bar[cur ^ 1]);
+    }
+    mbar_wait(&bar[cur], (it >> 1) & 1);
+    // pass 1: online max / sum (4 independent chains per lane), argmax with lowest-index tie-break
+    float m = -INFINITY, s = 0.f;
+    int am = 0;
+    const float4* v4 = reinterpret_cast<const float4*>(buf);
+    for (int i = lane; i < n_vec; i += 32) {
+      const float4 v = v4[i];
+      const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+      if (m4 > m) {
+        s *= __expf(m - m4);
+        m = m4;
+        am = 4 * i + (v.x == m4 ? 0 : (v.y == m4 ? 1 : (v.z == m4 ? 2 : 3)));
+      }
+      s += (__expf(v.x - m) + __expf(v.y - m)) + (__expf(v.z - m) + __expf(v.w - m));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float mo = __shfl_xor_sync(0xffffffffu, m, o);
+      const float so = __shfl_xor_sync(0xffffffffu, s, o);
+      const int ao = __shfl_xor_sync(0xffffffffu, am, o);
+      const float mn = fmaxf(m, mo);
+      s = (m == -INFINITY ? 0.f : s * __expf(m - mn)) + (mo == -INFINITY ? 0.f : so * __expf(mo - mn));
+      if (mo > m || (mo == m && ao < am)) am = ao;
+      m = mn;
+    }
+    const float ls = logf(s);
+    // pass 2: normalise in place
+    float4* w4 = reinterpret_cast<float4*>(buf);
+    for (int i = lane; i < n_vec; i += 32) {
+      float4 v = w4[i];
+      v.x = (v.x - m) - ls;
+      v.y = (v.y - m) - ls;
+      v.z = (v.z - m) - ls;
+      v.w = (v.w - m) - ls;
+      w4[i] = v;
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      bulk_store_1d(out + row * ld_out, buf, row_bytes);
+      if (argmax_out) argmax_out[row] = am;
+      if (maxlp_out) maxlp_out[row] = -ls;
+    }
+  }
+  if (lane == 0) bulk_store_wait_read<0>();
+}
+
 // ---------------------------------------------------------------------------
 // softmax(dependency logits[..., skip:]) -> bf16 columns of the next classifier's input
 // ---------------------------------------------------------------------------
@@ -317,6 +408,23 @@ extern "C" int aph_log_softmax_wide(const float* logits, int64_t ld, int64_t row
   APH_REQUIRE(logits && out, "null pointer");
   APH_REQUIRE(width > 0, "bad width");
   if (rows <= 0) return APH_OK;
+  const bool aligned = width % 4 == 0 && ld % 4 == 0 && ld_out % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  const size_t bulk_smem = 128 + static_cast<size_t>(kLsmBulkWarps) * 2 * ((static_cast<size_t>(width) * 4 + 127) & ~static_cast<size_t>(127));
+  if (aligned && width >= 256 && bulk_smem <= 110 * 1024) {
+    static bool bulk_attr_set = false;
+    if (!bulk_attr_set) {
+      APH_CUDA_CHECK(cudaFuncSetAttribute(log_softmax_wide_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+      bulk_attr_set = true;
+    }
+    long long blocks = (rows + kLsmBulkWarps - 1) / kLsmBulkWarps;
+    const long long cap = 2LL * sm_count();
+    if (blocks > cap) blocks = cap;
+    log_softmax_wide_bulk_kernel<<<static_cast<unsigned>(blocks), kLsmBulkWarps * 32, bulk_smem, stream>>>(
+        logits, ld, rows, width, out, ld_out, argmax_out, maxlp_out);
+    APH_POST_LAUNCH(1);
+    return APH_OK;
+  }
   int warps = static_cast<int>((100 * 1024) / (sizeof(float) * width));
   APH_REQUIRE(warps >= 1, "row too wide for the shared-memory staged log_softmax");
   if (warps > 8) warps = 8;
