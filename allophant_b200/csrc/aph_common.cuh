@@ -162,6 +162,14 @@ __device__ __forceinline__ void bulk_store_1d(void* gmem_dst, const void* smem_s
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// tensor-map (tiled) store smem -> global: rows/columns outside the tensor are clipped by the hardware
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 // waits until at most `kPending` of this thread's bulk stores still READ their shared-memory source
 template <int kPending>
 __device__ __forceinline__ void bulk_store_wait_read() {

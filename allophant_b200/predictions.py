@@ -25,22 +25,24 @@ class CTCHypothesis(NamedTuple):
 
 
 def _hypotheses(tokens: Tensor, timesteps: Tensor, counts: Tensor, scores: Tensor, n_utt: int) -> List[List[List[CTCHypothesis]]]:
-    """Splits the padded device results into per-(head, utterance) hypotheses on the host."""
-    tokens_h = tokens.cpu()
-    timesteps_h = timesteps.cpu()
-    counts_h = counts.cpu().tolist()
-    scores_h = scores.cpu()
-    n_heads = len(counts_h) // n_utt
+    """Splits the padded device results into per-(head, utterance) hypotheses on the host.
+
+    One device-to-host copy per array, then a single masked compaction and ``Tensor.split`` (C++ loops):
+    the per-hypothesis Python work is only the NamedTuple construction."""
+    counts_h = counts.cpu()
+    lengths = counts_h.tolist()
+    frames = tokens.shape[1]
+    keep = torch.arange(frames).unsqueeze(0) < counts_h.unsqueeze(1)
+    token_parts = tokens.cpu()[keep].long().split(lengths)
+    timestep_parts = timesteps.cpu()[keep].long().split(lengths)
+    score_parts = scores.cpu().unbind(0)
+    n_heads = len(lengths) // n_utt
     result = []
     for head in range(n_heads):
-        per_head = []
-        for utt in range(n_utt):
-            seq = head * n_utt + utt
-            count = counts_h[seq]
-            per_head.append(
-                [CTCHypothesis(tokens_h[seq, :count].long(), [], scores_h[seq], timesteps_h[seq, :count].long())]
-            )
-        result.append(per_head)
+        base = head * n_utt
+        result.append(
+            [[CTCHypothesis(token_parts[base + utt], [], score_parts[base + utt], timestep_parts[base + utt])] for utt in range(n_utt)]
+        )
     return result
 
 
