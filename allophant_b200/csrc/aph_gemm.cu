@@ -3,11 +3,13 @@
 // D[m, n] = sum_k A[m, k] * B[n, k]  (A, B bf16 K-major; fp32 accumulators in TMEM)
 //
 // Roles inside one 320-thread CTA (one CTA per SM, persistent over output tiles):
-//   warp 8      TMA producer: A tile 128x64 + B tile BNx64 per stage, 128B swizzle.  CTAs run as
-//               clusters of 2 that work on vertically adjacent M tiles of the same N tile: each
-//               fetches HALF of the shared B tile and multicasts it into both CTAs' smem, which
-//               cuts the L2->SM operand traffic per tile from 48 KB to 32 KB per k-block (the
-//               un-clustered kernel sat on the L2 bandwidth cap at ~1.0 PFLOP/s)
+//   warp 8      TMA producer: A tile 128x64 + HALF of the B tile (BN/2 x 64) per stage, 128B swizzle.
+//               CTAs run as PAIRS (cluster of 2, tcgen05 cta_group::2) on a 256 x BN output tile:
+//               each CTA owns 128 rows of A and of the accumulator, the B tile is split between
+//               the two SMs and read by the pair's single UMMA (M = 256).  Per SM this halves the
+//               B bytes held, fetched and read from shared memory per k-block (32 KB instead of
+//               48 KB per stage -> 6 stages; operand reads 64 instead of 96 B/clk of the 128 B/clk
+//               smem port, which the epilogue's staging traffic otherwise saturates)
 //   warp 9      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16).  The two
 //               single-thread roles sit on the HIGHEST warp ids: the SMSP arbiter favours high warp
 //               ids, so the epilogue's ALU work never delays a TMA or MMA issue
@@ -70,10 +72,10 @@ struct GemmParams {
 template <int BN>
 struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kBBytes = (BN / 2) * kBK * 2;  // this CTA's half of the pair's B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
-  static constexpr int kTmemCols = 2 * BN;  // double-buffered accumulator
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // double-buffered accumulator (128 lanes x BN columns per CTA)
   static constexpr int kEpiBytes = 8 * 4096;  // one 32-row x 128-byte staging tile per epilogue warp
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
@@ -103,16 +105,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     tma_prefetch_desc(&tm_b);
     if (p.staged) tma_prefetch_desc(&tm_out);
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 2);  // released by the MMA threads of BOTH CTAs of the cluster
+      mbar_init(&full_bar[s], 2);   // leader's copy is the one in use: one arrive.expect_tx per CTA of the pair
+      mbar_init(&empty_bar[s], 1);  // released in both CTAs by the leader's tcgen05.commit multicast
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 256);
+      mbar_init(&tempty_bar[s], 16);  // leader's copy: one arrival per epilogue warp of both CTAs
     }
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 9) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
   tc_fence_before();
   cluster_sync_all();  // barrier inits visible cluster-wide before any multicast / remote arrive
   tc_fence_after();
@@ -141,15 +143,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          if (p.mode == APH_GEMM_TAPS) {
-            tma_load_3d(sa, &tm_a, &full_bar[stage], n_blk * kBK, t0 - p.tap_pad + kb, b);
+          // both CTAs' bytes are accounted on the LEADER's full barrier (the leader issues the pair's MMA)
+          if (cta_rank == 0) {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           } else {
-            tma_load_3d(sa, &tm_a, &full_bar[stage], kb * kBK, t0, b);
+            mbar_arrive_expect_tx_remote(&full_bar[stage], 0, Cfg::kStageBytes);
           }
-          // my half of the B tile goes to both CTAs; the peer delivers the other half
-          tma_load_2d_multicast(sb + cta_rank * (Cfg::kBBytes / 2), &tm_b, &full_bar[stage], kb * kBK,
-                                n_blk * BN + cta_rank * (BN / 2), static_cast<uint16_t>(3));
+          if (p.mode == APH_GEMM_TAPS) {
+            tma_load_3d_pair(sa, &tm_a, &full_bar[stage], n_blk * kBK, t0 - p.tap_pad + kb, b);
+          } else {
+            tma_load_3d_pair(sa, &tm_a, &full_bar[stage], kb * kBK, t0, b);
+          }
+          tma_load_2d_pair(sb, &tm_b, &full_bar[stage], kb * kBK, n_blk * BN + cta_rank * (BN / 2));
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -159,8 +164,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     }
   } else if (warp == 9) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * kBM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -178,16 +183,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // +32 bytes along K inside the 128B swizzle atom = +2 in the encoded address
-            umma_bf16(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
-                      idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_pair(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
+                           idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit_multicast(&empty_bar[stage], static_cast<uint16_t>(3));  // frees the stage in both CTAs
+          umma_commit_pair(&empty_bar[stage], static_cast<uint16_t>(3));  // frees the stage in both CTAs
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[acc]);
+        umma_commit_pair(&tfull_bar[acc], static_cast<uint16_t>(3));  // accumulator ready in both CTAs
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -374,7 +379,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
+      __syncwarp();
+      if (lane == 0) {  // the accumulator of BOTH CTAs must be drained before the leader overwrites it
+        if (cta_rank == 0) {
+          mbar_arrive(&tempty_bar[acc]);
+        } else {
+          mbar_arrive_remote(&tempty_bar[acc], 0);
+        }
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -386,7 +398,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
   if (warp == 9) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
   }
 }
 
