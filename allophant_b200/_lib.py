@@ -21,6 +21,7 @@ APH_ERR_UNSUPPORTED = -3
 
 APH_GEMM_ROWS = 0
 APH_GEMM_TAPS = 1
+APH_GEMM_DIAG_TAPS = 2
 APH_EPI_STORE = 0
 APH_EPI_QKV = 1
 
@@ -59,6 +60,19 @@ class GemmArgs(Structure):
         ("heads", c_int32),
         ("t_v", c_int32),
         ("q_scale", c_float),
+        ("a_mn_major", c_int32),
+        ("b_mn_major", c_int32),
+        ("b_row_stride", c_int64),
+        ("b_seg_stride", c_int64),
+        ("k_seq", c_int32),
+        ("k_batch", c_int32),
+        ("b_k_shift", c_int32),
+        ("n_taps", c_int32),
+        ("aux_bf16", c_void_p),
+        ("ld_aux", c_int64),
+        ("gelu_bwd", c_void_p),
+        ("ld_gelu_bwd", c_int64),
+        ("vmat", c_void_p),
     ]
 
 
@@ -88,6 +102,8 @@ _F = c_float
 _SIGNATURES = {
     "aph_gemm_bf16": [POINTER(GemmArgs), _P],
     "aph_attention_bf16": [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
+    "aph_attention_bf16_lse": [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
+    "aph_attention_backward_bf16": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P],
     "aph_wave_stats": [_P, _P, _I32, _I32, _P, _P, _P],
     "aph_wave_norm": [_P, _P, _P, _I32, _I32, _P, _P],
     "aph_frame_lengths": [_P, _I32, _P, _P, _I32, _P, _P, _P],
@@ -104,6 +120,19 @@ _SIGNATURES = {
     "aph_cast_bf16_2d": [_P, _I64, _P, _I64, _I64, _I32, _P],
     "aph_pack_conv_weight": [_P, _P, _I32, _I32, _I32, _P],
     "aph_pack_posconv_weight": [_P, _P, _P, _P, _I32, _I32, _I32, _P],
+    "aph_allophone_forward": [_P, _I64, _I64, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P],
+    "aph_allophone_backward": [_P, _P, _P, _I64, _I64, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
+    "aph_transpose_cast_bf16": [_P, _I32, _I64, _I64, _I32, _P, _I64, _I64, _P],
+    "aph_colsum_f32": [_P, _I64, _I64, _I32, _P, _P],
+    "aph_colsum_bf16": [_P, _I64, _I64, _I32, _P, _P],
+    "aph_layernorm_backward": [_P, _I32, _I64, _P, _I32, _I64, _I64, _I32, _P, _F, _P, _I64, _P, _I64, _P, _P, _P],
+    "aph_mask_rows_f32": [_P, _I64, _I64, _I32, _P, _I32, _P],
+    "aph_add_f32_2d": [_P, _I64, _P, _I64, _I64, _I32, _P],
+    "aph_gelu_backward_bf16": [_P, _I64, _P, _I64, _I64, _I32, _P, _I64, _P],
+    "aph_pack_posconv_weight_dgrad": [_P, _P, _P, _P, _I32, _I32, _I32, _P],
+    "aph_posconv_weight_backward": [_P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P],
+    "aph_embedding_bag_backward": [_P, _I64, _I32, _I32, _I32, _P, _P, _P, _P],
+    "aph_softmax_backward_cols": [_P, _I64, _P, _I64, _I64, _P, _P, _P, _I32, _I32, _P, _I64, _P],
     "aph_edit_statistics_batch": [_P, _P, _P, _P, _I64, _P, _P, _I32],
     "aph_ctc_states_pad": [_I32],
     "aph_ctc_forward": [_P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],

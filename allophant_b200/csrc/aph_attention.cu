@@ -33,6 +33,7 @@ struct AttParams {
   const int* lengths;  // [N]
   int T;
   int heads;
+  float* lse2;         // [N*heads, T] log2-domain log-sum-exp of every query row (training) or nullptr
 };
 
 __global__ void __launch_bounds__(kAttThreads, 2)
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(kAttThreads, 2)
     }
 
     if (q0 + r < p.T) {
+      if (p.lse2 != nullptr) p.lse2[static_cast<long long>(bh) * p.T + q0 + r] = m_run + log2f(l_run);
       const float inv = 1.0f / l_run;
       __nv_bfloat16* dst = p.ctx + (static_cast<long long>(b) * p.T + q0 + r) * (p.heads * kAttD) + h * kAttD;
       uint4* d4 = reinterpret_cast<uint4*>(dst);
@@ -257,6 +259,12 @@ __global__ void __launch_bounds__(kAttThreads, 2)
 extern "C" int aph_attention_bf16(const void* q, const void* k, const void* vt, void* ctx,
                                   const int32_t* lengths, int32_t n_utt, int32_t heads, int32_t T,
                                   int32_t t_v, void* stream_) {
+  return aph_attention_bf16_lse(q, k, vt, ctx, nullptr, lengths, n_utt, heads, T, t_v, stream_);
+}
+
+extern "C" int aph_attention_bf16_lse(const void* q, const void* k, const void* vt, void* ctx, float* lse2,
+                                      const int32_t* lengths, int32_t n_utt, int32_t heads, int32_t T,
+                                      int32_t t_v, void* stream_) {
   using namespace aph;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   APH_REQUIRE(q && k && vt && ctx && lengths, "null pointer");
@@ -290,6 +298,7 @@ extern "C" int aph_attention_bf16(const void* q, const void* k, const void* vt, 
   p.lengths = lengths;
   p.T = T;
   p.heads = heads;
+  p.lse2 = lse2;
   dim3 grid(ceil_div(T, kAttQ), static_cast<unsigned>(nh));
   attention_kernel<<<grid, kAttThreads, kAttSmemBytes, stream>>>(tm_q, tm_k, tm_v, p);
   APH_POST_LAUNCH(1);

@@ -170,6 +170,14 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// same, but the tile is ADDED to global memory (element type from the tensor map): split-K partial tiles
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 // waits until at most `kPending` of this thread's bulk stores still READ their shared-memory source
 template <int kPending>
 __device__ __forceinline__ void bulk_store_wait_read() {
@@ -351,6 +359,22 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// MN-major, 128-byte-swizzled operand (cute::UMMA::make_umma_desc<Major::MN>, canonical layout
+// Swizzle<3,4,3> o ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): a tile is stored as 64-element
+// (128-byte) wide chunks along M/N, each chunk [k rows][128 B]; LBO = bytes between chunks,
+// SBO = 1024 B between 8-row groups along K.  One UMMA_K = 16 step advances the start address by 16 rows
+// = 2048 B (128 in the encoded address).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t chunk_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((chunk_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+constexpr uint32_t kIdescAMnMajor = 1u << 15;  // cute::UMMA::InstrDescriptor::a_major_
+constexpr uint32_t kIdescBMnMajor = 1u << 16;  // cute::UMMA::InstrDescriptor::b_major_
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, both operands K-major
 // (cute::UMMA::InstrDescriptor): c_format(F32)=1 @4, a_format(BF16)=1 @7,
 // b_format(BF16)=1 @10, N>>3 @17, M>>4 @24.
@@ -380,6 +404,29 @@ __device__ __forceinline__ float gelu_erf(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
   const float hx = 0.5f * x;
   return fmaf(fabsf(hx), 1.0f - r, hx);  // 0.5 x + 0.5 |x| erf(|x|/sqrt2) = 0.5 x (1 + erf(x/sqrt2))
+}
+// d/dx of the GELU above: Phi(x) + x phi(x), Phi from the same erf approximation
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float u = fabsf(x) * 0.70710678118654752440f;
+  float d = fmaf(0.0000430638f, u, 0.0002765672f);
+  d = fmaf(d, u, 0.0001520143f);
+  d = fmaf(d, u, 0.0092705272f);
+  d = fmaf(d, u, 0.0422820123f);
+  d = fmaf(d, u, 0.0705230784f);
+  d = fmaf(d, u, 1.0f);
+  d *= d;
+  d *= d;
+  d *= d;
+  d *= d;
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  const float erf_abs = 1.0f - r;                                  // erf(|x| / sqrt 2)
+  const float cdf = 0.5f + copysignf(0.5f * erf_abs, x);           // Phi(x)
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);   // phi(x)
+  return fmaf(x, pdf, cdf);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

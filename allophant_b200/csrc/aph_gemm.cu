@@ -28,6 +28,15 @@
 //                           rows overlap, no im2col buffer exists
 //   grouped pos-conv (HF:326) "taps" mode: k-block j reads rows t - pad + j of
 //                           channel group n/64 (zero-filled outside [0, rows))
+//
+// Training (autograd of the same call sites) reuses the kernel with MN-major operands, so that
+// activations, output gradients and weights are read in the layout the forward pass left them in:
+//   dgrad  dX = dY W      A = dY K-major, B = W stored [k = out][n = in] (MN-major B)
+//   wgrad  dW = dY^T X    A = dY stored [k = frame][m = out], B = X stored [k = frame][n = in]
+// An MN-major tile is fetched as 64-column x 64-row boxes (128B swizzle) = the canonical UMMA
+// MN-major SW128 layout (LBO = 8 KB between 64-wide chunks, SBO = 1 KB between 8-row groups).
+// Frames past the end of a segment are zero-filled by TMA, so K needs no padding.  Split-K work
+// items add their partial tile with TMA reduce stores (cp.reduce.async.bulk.tensor ... .add).
 #include <string.h>
 
 #include "aph_common.cuh"
@@ -67,7 +76,55 @@ struct GemmParams {
   int t_v;
   float q_scale;
   int staged;  // 0 = direct stores, 1 = fp32 output through TMA store, 2 = bf16 output through TMA store
+  // ---- MN-major operands / training epilogues
+  int a_mn;            // A stored [k][m]
+  int b_mn;            // B stored [k][n]
+  int k_seq_blocks;    // MN-major: 64-row blocks per segment (k_blocks = segments * k_seq_blocks)
+  int b_k_shift;       // MN-major B: row shift inside the segment
+  int diag_taps;       // APH_GEMM_DIAG_TAPS: number of taps (0 = off)
+  int split_k;         // >= 1; > 1: partial tiles are reduce-added into the (pre-initialised) fp32 output
+  int kb_per_split;
+  uint32_t idesc;
+  __nv_bfloat16* aux_bf16;
+  long long ld_aux;
+  const __nv_bfloat16* gelu_bwd;
+  long long ld_gelu_bwd;
+  __nv_bfloat16* vmat;
 };
+
+// Work item -> (n block, m pair, output batch, k-block range, B row shift)
+struct WorkItem {
+  int n_blk;
+  int m_pair;
+  int kb_lo;
+  int kb_hi;
+  int shift;
+  int out_batch;  // DIAG_TAPS: tap index (output batch); otherwise -1
+};
+
+__device__ __forceinline__ WorkItem decode_work(const GemmParams& p, int work, int m_pairs) {
+  WorkItem w;
+  if (p.diag_taps > 0) {
+    const int tap = work / m_pairs;
+    w.m_pair = work - tap * m_pairs;
+    w.n_blk = w.m_pair;
+    w.kb_lo = 0;
+    w.kb_hi = p.k_blocks;
+    w.shift = p.b_k_shift + tap - p.tap_pad;
+    w.out_batch = tap;
+    return w;
+  }
+  const int per_split = m_pairs * p.n_tiles;
+  const int split = work / per_split;
+  const int rest = work - split * per_split;
+  w.n_blk = rest % p.n_tiles;
+  w.m_pair = rest / p.n_tiles;
+  w.kb_lo = split * p.kb_per_split;
+  w.kb_hi = w.kb_lo + p.kb_per_split < p.k_blocks ? w.kb_lo + p.kb_per_split : p.k_blocks;
+  w.shift = p.b_k_shift;
+  w.out_batch = -1;
+  return w;
+}
 
 template <int BN>
 struct GemmCfg {
@@ -126,7 +183,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
   const int n_clusters = gridDim.x >> 1;
   const int tiles_m = p.m_tiles_per_batch * p.batch;
   const int m_pairs = (tiles_m + 1) >> 1;
-  const int total_work = m_pairs * p.n_tiles;
+  const int total_work = p.diag_taps > 0 ? m_pairs * p.diag_taps : m_pairs * p.n_tiles * p.split_k;
 
   if (warp == 8) {
     // ===================== TMA producer =====================
@@ -134,12 +191,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
       int stage = 0;
       uint32_t phase = 0;
       for (int work = cluster_id; work < total_work; work += n_clusters) {
-        const int n_blk = work % p.n_tiles;
-        int mt = 2 * (work / p.n_tiles) + cta_rank;
+        const WorkItem w = decode_work(p, work, m_pairs);
+        const int n_blk = w.n_blk;
+        int mt = 2 * w.m_pair + cta_rank;
         if (mt >= tiles_m) mt = tiles_m - 1;  // odd tile count: the idle CTA still feeds the shared B half
         const int b = mt / p.m_tiles_per_batch;
         const int t0 = (mt % p.m_tiles_per_batch) * kBM;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        for (int kb = w.kb_lo; kb < w.kb_hi; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
@@ -149,12 +207,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           } else {
             mbar_arrive_expect_tx_remote(&full_bar[stage], 0, Cfg::kStageBytes);
           }
-          if (p.mode == APH_GEMM_TAPS) {
+          int seg = 0, r0 = kb * kBK;
+          if (p.a_mn | p.b_mn) {
+            seg = kb / p.k_seq_blocks;
+            r0 = (kb - seg * p.k_seq_blocks) * kBK;
+          }
+          if (p.a_mn) {
+            // [64 frames][64 output channels] boxes: two 64-wide chunks cover this CTA's 128 rows of D
+            tma_load_3d_pair(sa, &tm_a, &full_bar[stage], mt * kBM, r0, seg);
+            tma_load_3d_pair(sa + Cfg::kABytes / 2, &tm_a, &full_bar[stage], mt * kBM + 64, r0, seg);
+          } else if (p.mode == APH_GEMM_TAPS) {
             tma_load_3d_pair(sa, &tm_a, &full_bar[stage], n_blk * kBK, t0 - p.tap_pad + kb, b);
           } else {
             tma_load_3d_pair(sa, &tm_a, &full_bar[stage], kb * kBK, t0, b);
           }
-          tma_load_2d_pair(sb, &tm_b, &full_bar[stage], kb * kBK, n_blk * BN + cta_rank * (BN / 2));
+          if (p.b_mn) {
+            const int n0 = n_blk * BN + cta_rank * (BN / 2);
+#pragma unroll
+            for (int c = 0; c < (BN / 2) / 64; ++c)
+              tma_load_3d_pair(sb + c * (64 * kBK * 2), &tm_b, &full_bar[stage], n0 + 64 * c, r0 + w.shift, seg);
+          } else {
+            tma_load_2d_pair(sb, &tm_b, &full_bar[stage], kb * kBK, n_blk * BN + cta_rank * (BN / 2));
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -165,26 +239,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
   } else if (warp == 9) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0 && cta_rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * kBM, BN);
+      const uint32_t idesc = p.idesc;
+      // descriptor advance per UMMA_K = 16: 32 bytes along K inside the swizzle atom (K-major) or 16 rows of
+      // 128 bytes (MN-major), in 16-byte units
+      const uint64_t a_step = p.a_mn ? 128u : 2u;
+      const uint64_t b_step = p.b_mn ? 128u : 2u;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int work = cluster_id; work < total_work; work += n_clusters) {
+        const WorkItem w = decode_work(p, work, m_pairs);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        for (int kb = w.kb_lo; kb < w.kb_hi; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint64_t da = umma_desc_sw128(sa);
-          const uint64_t db = umma_desc_sw128(sa + Cfg::kABytes);
+          const uint64_t da = p.a_mn ? umma_desc_mn_sw128(sa, 64 * kBK * 2) : umma_desc_sw128(sa);
+          const uint64_t db = p.b_mn ? umma_desc_mn_sw128(sa + Cfg::kABytes, 64 * kBK * 2) : umma_desc_sw128(sa + Cfg::kABytes);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
-            // +32 bytes along K inside the 128B swizzle atom = +2 in the encoded address
-            umma_bf16_pair(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
-                           idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_pair(tmem_d, da + static_cast<uint64_t>(k) * a_step, db + static_cast<uint64_t>(k) * b_step, idesc,
+                           (kb != w.kb_lo || k != 0) ? 1u : 0u);
           }
           umma_commit_pair(&empty_bar[stage], static_cast<uint16_t>(3));  // frees the stage in both CTAs
           if (++stage == kStages) {
@@ -213,10 +291,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int work = cluster_id; work < total_work; work += n_clusters) {
-      const int n_blk = work % p.n_tiles;
-      const int mt = 2 * (work / p.n_tiles) + cta_rank;
-      const int b = mt / p.m_tiles_per_batch;
+      const WorkItem w = decode_work(p, work, m_pairs);
+      const int n_blk = w.n_blk;
+      const int mt = 2 * w.m_pair + cta_rank;
+      const int b = w.out_batch >= 0 ? w.out_batch : mt / p.m_tiles_per_batch;
       const int t = (mt % p.m_tiles_per_batch) * kBM + r;
+      const int col_base = w.out_batch >= 0 ? 0 : n_blk * BN;  // DIAG_TAPS: the 256 columns of the diagonal block
       const bool row_ok = mt < tiles_m && t < p.a_rows;
       const long long grow = static_cast<long long>(b) * p.out_batch_rows + t;
       bool masked = false;
@@ -232,7 +312,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
       for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
-        const int col = n_blk * BN + c0;
+        const int col = col_base + c0;
         if (col >= p.n) break;  // warp-uniform
         float v[32];
         tmem_ld32(taddr0 + static_cast<uint32_t>(c0), v);
@@ -264,6 +344,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
               __nv_bfloat16* dst = p.vt + (bh * 64 + d0) * p.t_v + tt;
 #pragma unroll
               for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.t_v] = __float2bfloat16(v[j]);
+              if (p.vmat != nullptr) {  // training: V also row-major for the attention backward
+                uint4* d4 = reinterpret_cast<uint4*>(p.vmat + (bh * p.len_period + tt) * 64 + d0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint4 o;
+                  o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                  o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                  o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                  o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                  d4[j] = o;
+                }
+              }
             }
           }
         } else {
@@ -287,9 +379,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= p.scale;
           }
+          if (p.aux_bf16 != nullptr && row_ok) {  // training forward: keep the pre-activation for the backward pass
+            uint4* d4 = reinterpret_cast<uint4*>(p.aux_bf16 + grow * p.ld_aux + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (full_chunk || col + 8 * j + 8 <= p.n) {
+                uint4 o;
+                o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                d4[j] = o;
+              }
+            }
+          }
           if (p.gelu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          }
+          if (p.gelu_bwd != nullptr && row_ok) {  // backward of GELU: dL/d(pre) = dL/d(act) * gelu'(pre)
+            const uint4* s4 = reinterpret_cast<const uint4*>(p.gelu_bwd + grow * p.ld_gelu_bwd + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (full_chunk || col + 8 * j + 8 <= p.n) {
+                const uint4 raw = s4[j];
+                const uint32_t wds[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 pre = unpack_bf16x2(wds[e]);
+                  v[8 * j + 2 * e + 0] *= gelu_erf_grad(pre.x);
+                  v[8 * j + 2 * e + 1] *= gelu_erf_grad(pre.y);
+                }
+              }
+            }
           }
           if (row_ok) {
             if (p.resid != nullptr) {
@@ -349,7 +471,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
                 *reinterpret_cast<float4*>(stage_row + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
               fence_proxy_async_smem();
               __syncwarp();
-              if (lane == 0) tma_store_3d(&tm_out, stage_buf, col, t_row0, b);
+              if (lane == 0) {
+                if (p.split_k > 1) {
+                  tma_reduce_add_3d(&tm_out, stage_buf, col, t_row0, b);
+                } else {
+                  tma_store_3d(&tm_out, stage_buf, col, t_row0, b);
+                }
+              }
               store_pending = true;
             } else {
               // bf16: two consecutive 32-column chunks fill the 128-byte rows (64 columns per store)
@@ -406,9 +534,21 @@ template <int BN, int EPI>
 static int launch_gemm(const aph_gemm_args* a, GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap tm_a, tm_b;
-  {
-    const uint64_t dims[3] = {static_cast<uint64_t>(a->a_inner), static_cast<uint64_t>(a->a_rows),
-                              static_cast<uint64_t>(a->batch)};
+  const int k_seq = a->k_seq;
+  const int k_batch = a->k_batch > 0 ? a->k_batch : 1;
+  if (a->a_mn_major) {
+    // stored [segment][frame][output channel]: 64 x 64 boxes, frames past the segment read as zero
+    const uint64_t dims[3] = {static_cast<uint64_t>(a->a_rows), static_cast<uint64_t>(k_seq), static_cast<uint64_t>(k_batch)};
+    uint64_t seg_stride = static_cast<uint64_t>(a->a_batch_stride) * 2;
+    if (k_batch == 1 || seg_stride == 0) seg_stride = static_cast<uint64_t>(a->a_row_stride) * 2 * static_cast<uint64_t>(k_seq);
+    const uint64_t strides[2] = {static_cast<uint64_t>(a->a_row_stride) * 2, seg_stride};
+    const uint32_t box[3] = {64, kBK, 1};
+    int rc = encode_tmap(&tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->a, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != APH_OK) return rc;
+  } else {
+    // a K-major A paired with an MN-major B contracts over k_seq columns only: clip the map so the tail reads zero
+    const uint64_t inner = a->b_mn_major && k_seq < a->a_inner ? k_seq : a->a_inner;
+    const uint64_t dims[3] = {inner, static_cast<uint64_t>(a->a_rows), static_cast<uint64_t>(a->batch)};
     uint64_t batch_stride = static_cast<uint64_t>(a->a_batch_stride) * 2;
     if (a->batch == 1 && batch_stride == 0) batch_stride = static_cast<uint64_t>(a->a_row_stride) * 2;
     const uint64_t strides[2] = {static_cast<uint64_t>(a->a_row_stride) * 2, batch_stride};
@@ -417,9 +557,19 @@ static int launch_gemm(const aph_gemm_args* a, GemmParams& p, cudaStream_t strea
                          CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != APH_OK) return rc;
   }
-  {
+  if (a->b_mn_major) {
+    const uint64_t row_stride = static_cast<uint64_t>(a->b_row_stride > 0 ? a->b_row_stride : a->n) * 2;
+    const uint64_t dims[3] = {static_cast<uint64_t>(a->n), static_cast<uint64_t>(k_seq), static_cast<uint64_t>(k_batch)};
+    uint64_t seg_stride = static_cast<uint64_t>(a->b_seg_stride) * 2;
+    if (k_batch == 1 || seg_stride == 0) seg_stride = row_stride * static_cast<uint64_t>(k_seq);
+    const uint64_t strides[2] = {row_stride, seg_stride};
+    const uint32_t box[3] = {64, kBK, 1};
+    int rc = encode_tmap(&tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->b, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != APH_OK) return rc;
+  } else {
+    const uint64_t row_stride = static_cast<uint64_t>(a->b_row_stride > 0 ? a->b_row_stride : a->k) * 2;
     const uint64_t dims[2] = {static_cast<uint64_t>(a->k), static_cast<uint64_t>(a->n)};
-    const uint64_t strides[1] = {static_cast<uint64_t>(a->k) * 2};
+    const uint64_t strides[1] = {row_stride};
     const uint32_t box[2] = {kBK, static_cast<uint32_t>(BN / 2)};  // each CTA of a cluster fetches half the B tile
     int rc = encode_tmap(&tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->b, dims, strides, box,
                          CU_TENSOR_MAP_SWIZZLE_128B);
@@ -431,9 +581,10 @@ static int launch_gemm(const aph_gemm_args* a, GemmParams& p, cudaStream_t strea
     const bool f32 = p.staged == 1;
     const uint64_t es = f32 ? 4 : 2;
     const uint64_t ld = static_cast<uint64_t>(f32 ? a->ld_f32 : a->ld_bf16);
-    const uint64_t dims[3] = {static_cast<uint64_t>(a->n), static_cast<uint64_t>(a->a_rows), static_cast<uint64_t>(a->batch)};
+    const uint64_t out_batches = p.diag_taps > 0 ? static_cast<uint64_t>(p.diag_taps) : static_cast<uint64_t>(a->batch);
+    const uint64_t dims[3] = {static_cast<uint64_t>(p.n), static_cast<uint64_t>(a->a_rows), out_batches};
     uint64_t batch_stride = static_cast<uint64_t>(a->out_batch_rows) * ld * es;
-    if (a->batch == 1 || batch_stride == 0) batch_stride = static_cast<uint64_t>(a->a_rows) * ld * es;
+    if (out_batches == 1 || batch_stride == 0) batch_stride = static_cast<uint64_t>(a->a_rows) * ld * es;
     const uint64_t strides[2] = {ld * es, batch_stride};
     const uint32_t box[3] = {f32 ? 32u : 64u, 32u, 1u};
     int rc = encode_tmap(&tm_out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
@@ -446,8 +597,30 @@ static int launch_gemm(const aph_gemm_args* a, GemmParams& p, cudaStream_t strea
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int total_work = ((p.m_tiles_per_batch * p.batch + 1) / 2) * p.n_tiles;
+  p.idesc = umma_idesc_bf16(2 * kBM, BN) | (p.a_mn ? kIdescAMnMajor : 0u) | (p.b_mn ? kIdescBMnMajor : 0u);
+  const int m_pairs = (p.m_tiles_per_batch * p.batch + 1) / 2;
   const int max_clusters = sm_count() / 2;
+  // split K when the output has too few tiles to fill the machine (weight gradients: K = frames is the long axis)
+  p.split_k = 1;
+  p.kb_per_split = p.k_blocks;
+  if (a->a_mn_major && p.diag_taps == 0 && p.staged == 1 && a->bias == nullptr && a->resid == nullptr && !a->gelu &&
+      a->aux_bf16 == nullptr && a->gelu_bwd == nullptr && a->out_bf16 == nullptr) {
+    const int tiles = m_pairs * p.n_tiles;
+    int want = max_clusters / tiles;                  // splits that still fit one wave
+    const int max_by_k = p.k_blocks / 8;              // keep >= 8 k-blocks (512 frames) per split
+    if (want > max_by_k) want = max_by_k;
+    if (want > 1) {
+      p.kb_per_split = ceil_div(p.k_blocks, want);
+      p.split_k = ceil_div(p.k_blocks, p.kb_per_split);
+      // partial tiles are reduce-added: start from zero
+      if (a->ld_f32 == a->n) {
+        APH_CUDA_CHECK(cudaMemsetAsync(a->out_f32, 0, sizeof(float) * static_cast<size_t>(a->a_rows) * a->n, stream));
+      } else {
+        APH_CUDA_CHECK(cudaMemset2DAsync(a->out_f32, sizeof(float) * a->ld_f32, 0, sizeof(float) * a->n, a->a_rows, stream));
+      }
+    }
+  }
+  const int total_work = p.diag_taps > 0 ? m_pairs * p.diag_taps : m_pairs * p.n_tiles * p.split_k;
   const int grid = 2 * (total_work < max_clusters ? total_work : max_clusters);
   gemm_bf16_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, tm_out, p);
   APH_POST_LAUNCH(1);
@@ -461,18 +634,39 @@ extern "C" int aph_gemm_bf16(const aph_gemm_args* a, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   APH_REQUIRE(a != nullptr, "null args");
   APH_REQUIRE(a->a != nullptr && a->b != nullptr, "null operand");
-  APH_REQUIRE(a->k > 0 && a->k % kBK == 0, "k must be a positive multiple of 64");
+  const bool mn = a->a_mn_major || a->b_mn_major;
+  APH_REQUIRE(mn || (a->k > 0 && a->k % kBK == 0), "k must be a positive multiple of 64");
   APH_REQUIRE(a->n > 0 && a->n % 8 == 0, "n must be a positive multiple of 8");
   APH_REQUIRE(a->a_rows > 0 && a->batch > 0, "empty A");
   APH_REQUIRE(a->a_row_stride % 8 == 0 && a->a_batch_stride % 8 == 0, "A strides must be multiples of 8 elements");
+  APH_REQUIRE(a->b_row_stride % 8 == 0 && a->b_seg_stride % 8 == 0, "B strides must be multiples of 8 elements");
   APH_REQUIRE((reinterpret_cast<uintptr_t>(a->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->b) & 15) == 0,
               "operands must be 16-byte aligned");
-  APH_REQUIRE(a->mode == APH_GEMM_ROWS || a->mode == APH_GEMM_TAPS, "bad mode");
+  APH_REQUIRE(a->mode == APH_GEMM_ROWS || a->mode == APH_GEMM_TAPS || a->mode == APH_GEMM_DIAG_TAPS, "bad mode");
+  APH_REQUIRE(!a->a_mn_major || a->b_mn_major, "an MN-major A needs an MN-major B (weight-gradient form)");
+  APH_REQUIRE(!mn || (a->k_seq > 0 && a->k_batch >= 0), "MN-major operands need k_seq");
+  APH_REQUIRE(!mn || a->mode != APH_GEMM_TAPS, "taps mode takes K-major operands");
+  APH_REQUIRE(!a->a_mn_major || (a->batch == 1 && a->a_rows % 8 == 0), "MN-major A: batch 1, a_rows % 8 == 0");
+  APH_REQUIRE(!(a->b_mn_major && !a->a_mn_major) || a->k_batch <= 1, "K-major A with MN-major B: one segment");
+  APH_REQUIRE(!a->aux_bf16 || (a->ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux_bf16) & 15) == 0),
+              "aux output must be 16-byte aligned with ld % 8 == 0");
+  APH_REQUIRE(!a->gelu_bwd || (a->ld_gelu_bwd % 8 == 0 && (reinterpret_cast<uintptr_t>(a->gelu_bwd) & 15) == 0),
+              "gelu_bwd source must be 16-byte aligned with ld % 8 == 0");
 
   GemmParams p;
+  memset(&p, 0, sizeof(p));
   p.m_tiles_per_batch = ceil_div(a->a_rows, kBM);
   p.batch = a->batch;
-  p.k_blocks = a->k / kBK;
+  if (mn) {
+    p.k_seq_blocks = ceil_div(a->k_seq, kBK);
+    p.k_blocks = p.k_seq_blocks * (a->k_batch > 0 ? a->k_batch : 1);
+  } else {
+    p.k_seq_blocks = 1;
+    p.k_blocks = a->k / kBK;
+  }
+  p.a_mn = a->a_mn_major ? 1 : 0;
+  p.b_mn = a->b_mn_major ? 1 : 0;
+  p.b_k_shift = a->b_k_shift;
   p.a_rows = a->a_rows;
   p.mode = a->mode;
   p.tap_pad = a->tap_pad;
@@ -492,11 +686,31 @@ extern "C" int aph_gemm_bf16(const aph_gemm_args* a, void* stream_) {
   p.q = static_cast<__nv_bfloat16*>(a->q);
   p.kmat = static_cast<__nv_bfloat16*>(a->kmat);
   p.vt = static_cast<__nv_bfloat16*>(a->vt);
+  p.vmat = static_cast<__nv_bfloat16*>(a->vmat);
   p.heads = a->heads;
   p.t_v = a->t_v;
   p.q_scale = a->q_scale;
+  p.aux_bf16 = static_cast<__nv_bfloat16*>(a->aux_bf16);
+  p.ld_aux = a->ld_aux;
+  p.gelu_bwd = static_cast<const __nv_bfloat16*>(a->gelu_bwd);
+  p.ld_gelu_bwd = a->ld_gelu_bwd;
   p.staged = 0;
+  p.split_k = 1;
+  p.kb_per_split = p.k_blocks;
 
+  if (a->mode == APH_GEMM_DIAG_TAPS) {
+    // dW of the grouped positional conv: for tap j and 256-channel block q,
+    //   out[j][q*256 + m][c] = sum_frames A[frame][q*256 + m] * B[frame + j - tap_pad][q*256 + c]
+    APH_REQUIRE(a->a_mn_major && a->b_mn_major, "diag-taps mode takes MN-major operands");
+    APH_REQUIRE(a->epilogue == APH_EPI_STORE && a->out_f32 && !a->out_bf16 && !a->bias && !a->resid, "diag-taps: fp32 output only");
+    APH_REQUIRE(a->n_taps > 0 && a->a_rows % 256 == 0 && a->n == a->a_rows, "diag-taps: square, channels % 256 == 0");
+    APH_REQUIRE(a->ld_f32 == 256 && a->out_batch_rows == a->a_rows, "diag-taps: output [n_taps][channels][256]");
+    p.diag_taps = a->n_taps;
+    p.n_tiles = a->a_rows / 256;
+    p.n = 256;
+    p.staged = 1;
+    return launch_gemm<256, APH_EPI_STORE>(a, p, stream);
+  }
   if (a->mode == APH_GEMM_TAPS) {
     // one 64-channel group per N tile; k-block j is tap j of that group
     APH_REQUIRE(a->n % 64 == 0 && a->a_inner == a->n, "taps mode: n == channels, multiple of 64");
@@ -505,9 +719,10 @@ extern "C" int aph_gemm_bf16(const aph_gemm_args* a, void* stream_) {
     p.staged = a->out_f32 ? 1 : 0;  // 64-column tiles: only the fp32 staging granularity (32 columns) fits
     return launch_gemm<64, APH_EPI_STORE>(a, p, stream);
   }
-  APH_REQUIRE(a->a_inner >= a->k, "A rows shorter than k");
+  APH_REQUIRE(mn || a->a_inner >= a->k, "A rows shorter than k");
 
   if (a->epilogue == APH_EPI_QKV) {
+    APH_REQUIRE(!mn, "qkv epilogue takes K-major operands");
     APH_REQUIRE(a->q && a->kmat && a->vt && a->bias, "qkv epilogue needs q/k/vt/bias");
     APH_REQUIRE(a->heads > 0 && a->n == 3 * a->heads * 64, "qkv epilogue: n == 3*heads*64");
     APH_REQUIRE(a->len_period > 0 && a->t_v % 8 == 0 && a->t_v >= a->len_period, "qkv epilogue: bad lengths");
@@ -529,7 +744,7 @@ extern "C" int aph_gemm_bf16(const aph_gemm_args* a, void* stream_) {
   if (a->n > 128) {
     p.n_tiles = ceil_div(a->n, 256);
     return launch_gemm<256, APH_EPI_STORE>(a, p, stream);
-  } else if (a->n > 64) {
+  } else if (a->n > 64 || a->b_mn_major) {  // an MN-major B tile needs at least one 64-column chunk per CTA
     p.n_tiles = 1;
     return launch_gemm<128, APH_EPI_STORE>(a, p, stream);
   }

@@ -111,6 +111,15 @@ class PackedEncoder:
                 )
             )
         self.final_ln = (f32(w.encoder.layer_norm.weight), f32(w.encoder.layer_norm.bias))
+        self._pos_w_dgrad: Optional[Tensor] = None
+
+    @property
+    def pos_w_dgrad(self) -> Tensor:
+        """B operand of the positional conv's data-gradient GEMM, packed on first use (training only)."""
+        if self._pos_w_dgrad is None:
+            pc = self.weights.encoder.pos_conv_embed.conv
+            self._pos_w_dgrad = ops.pack_posconv_weight_dgrad(pc.parametrizations.weight.original0, pc.parametrizations.weight.original1)
+        return self._pos_w_dgrad
 
 
 Step = Callable[[], None]
@@ -128,8 +137,11 @@ class EncoderPlan:
         hidden_blocks: Dict[int, int],
         normalize: bool = True,
         use_lengths: bool = True,
+        training: bool = False,
     ) -> None:
         cfg = packed.cfg
+        self.training = training
+        self.generation = 0  # bumped by every run(): a backward pass checks that its activations are still there
         dev = packed.device
         assert dev is not None
         self.packed = packed
@@ -178,8 +190,42 @@ class EncoderPlan:
         self.ffn = z(M, cfg.intermediate_size)
         self.x = z(M, ldx)  # classifier feature matrix: [final LN | kept hidden states | dependency probabilities | 0]
         self.captured: Optional[List[Tensor]] = None
+        if training:
+            # Everything the backward pass reads is kept per layer (sized for 180 GB of HBM: nothing is recomputed
+            # except the attention probabilities).  hs[i] = input of layer i (hs[L] = input of the final LayerNorm),
+            # mids[i] = residual stream after the attention block of layer i.
+            n_layers = len(packed.layers)
+            FF = cfg.intermediate_size
+            self.hs = [self.hidden] + [z(M, H, dtype=f32) for _ in range(n_layers)]
+            self.mids = [z(M, H, dtype=f32) for _ in range(n_layers)]
+            self.hidden_fp = z(M, H, dtype=f32)  # feature projection output (input of the positional conv)
+            self.pos_pre = z(M, H)               # positional conv + bias, before the GELU
+            self.saved = [
+                dict(
+                    ln1=z(M, H), q=z(n_utt * heads * self.seq * 64), k=z(n_utt * heads * self.seq * 64), v=z(n_utt * heads * self.seq * 64),
+                    vt=z(n_utt * heads * 64 * self.t_v), lse=z(n_utt * heads * self.seq, dtype=f32), ctx=z(M, H), ln2=z(M, H),
+                    pre=z(M, FF), act=z(M, FF),
+                )
+                for _ in range(n_layers)
+            ]  # fmt: skip
+            # backward workspaces
+            self.dh = z(M, H, dtype=f32)
+            self.dh_bf16 = z(M, H)
+            self.d_ff = z(M, FF)
+            self.d_ln = z(M, H, dtype=f32)
+            self.d_ctx = z(M, H)
+            self.dqkv = z(M, 3 * H)
+            self.delta = z(n_utt * heads * self.seq, dtype=f32)
+            self.d_fp_in = z(M, 512, dtype=f32)
 
         self._steps: List[Step] = []
+        self._build()
+
+    def rebind(self, packed: PackedEncoder) -> None:
+        """New packed weights (after an optimizer step) for the same shape: the workspaces stay, the launch
+        list (whose GEMM descriptors point at the packed operands) is rebuilt."""
+        self.packed = packed
+        self._steps = []
         self._build()
 
     # ------------------------------------------------------------------
@@ -221,6 +267,7 @@ class EncoderPlan:
                 )
             src, dst = dst, src
         conv_out = src  # [N, T', 512]
+        self.conv_out = conv_out
 
         # feature projection: LN -> Linear, padded frames zeroed (HF:753-756), fp32 residual stream + bf16 copy
         g, b = p.fp_ln
@@ -234,7 +281,7 @@ class EncoderPlan:
                     a_inner=512,
                     a_row_stride=512,
                     bias=p.fp_b,
-                    out_f32=self.hidden,
+                    out_f32=self.hidden_fp if self.training else self.hidden,
                     ld_f32=H,
                     out_bf16=self.hidden_bf16,
                     ld_bf16=H,
@@ -263,11 +310,13 @@ class EncoderPlan:
                     k=taps * 64,
                     bias=p.pos_b,
                     gelu=True,
-                    resid=self.hidden,
+                    resid=self.hidden_fp if self.training else self.hidden,
                     ld_resid=H,
                     out_f32=self.hidden,
                     ld_f32=H,
                     out_batch_rows=self.seq,
+                    aux_bf16=self.pos_pre if self.training else None,
+                    ld_aux=H,
                 )
             )
         )
@@ -275,64 +324,63 @@ class EncoderPlan:
             raise NotImplementedError("post-LN wav2vec2 encoders (do_stable_layer_norm=False) are not implemented yet")
 
         heads = cfg.num_attention_heads
+        FF = cfg.intermediate_size
         for index, lw in enumerate(p.layers):
-            steps.append(lambda index=index: self._keep_hidden(index))
+            if self.training:
+                sv = self.saved[index]
+                h_in, h_mid, h_out = self.hs[index], self.mids[index], self.hs[index + 1]
+                ln1, ln2, q, k, vt, ctx, ffn = sv["ln1"], sv["ln2"], sv["q"], sv["k"], sv["vt"], sv["ctx"], sv["act"]
+                vmat, lse, pre = sv["v"], sv["lse"], sv["pre"]
+            else:
+                h_in = h_mid = h_out = self.hidden
+                ln1 = ln2 = self.ln_out
+                q, k, vt, ctx, ffn = self.q, self.k, self.vt, self.ctx, self.ffn
+                vmat = lse = pre = None
+            steps.append(lambda index=index, h_in=h_in: self._keep_hidden(index, h_in))
             g1, b1 = lw["ln1"]
-            steps.append(lambda g1=g1, b1=b1: ops.layernorm_rows(self.hidden, M, H, H, g1, b1, eps, out_bf16=self.ln_out, ld_bf16=H))
+            steps.append(lambda g1=g1, b1=b1, h_in=h_in, ln1=ln1: ops.layernorm_rows(h_in, M, H, H, g1, b1, eps, out_bf16=ln1, ld_bf16=H))
             steps.append(
-                self._gemm(
-                    ops.make_qkv_args(self.ln_out, lw["wqkv"], lw["bqkv"], self.q, self.k, self.vt, rows=M, seq=self.seq, heads=heads, t_v=self.t_v)
-                )
+                self._gemm(ops.make_qkv_args(ln1, lw["wqkv"], lw["bqkv"], q, k, vt, rows=M, seq=self.seq, heads=heads, t_v=self.t_v, vmat=vmat))
             )
-            steps.append(lambda: ops.attention(self.q, self.k, self.vt, self.ctx, self.att_lengths, N, heads, self.seq, self.t_v))
+            steps.append(
+                lambda q=q, k=k, vt=vt, ctx=ctx, lse=lse: ops.attention(q, k, vt, ctx, self.att_lengths, N, heads, self.seq, self.t_v, lse)
+            )
             steps.append(
                 self._gemm(
-                    ops.make_gemm_args(
-                        self.ctx, lw["wo"], a_rows=M, a_inner=H, a_row_stride=H, bias=lw["bo"], resid=self.hidden, ld_resid=H, out_f32=self.hidden, ld_f32=H
-                    )
+                    ops.make_gemm_args(ctx, lw["wo"], a_rows=M, a_inner=H, a_row_stride=H, bias=lw["bo"], resid=h_in, ld_resid=H, out_f32=h_mid, ld_f32=H)
                 )
             )
             g2, b2 = lw["ln2"]
-            steps.append(lambda g2=g2, b2=b2: ops.layernorm_rows(self.hidden, M, H, H, g2, b2, eps, out_bf16=self.ln_out, ld_bf16=H))
+            steps.append(lambda g2=g2, b2=b2, h_mid=h_mid, ln2=ln2: ops.layernorm_rows(h_mid, M, H, H, g2, b2, eps, out_bf16=ln2, ld_bf16=H))
             steps.append(
                 self._gemm(
                     ops.make_gemm_args(
-                        self.ln_out, lw["w1"], a_rows=M, a_inner=H, a_row_stride=H, bias=lw["b1"], gelu=True, out_bf16=self.ffn, ld_bf16=cfg.intermediate_size
+                        ln2, lw["w1"], a_rows=M, a_inner=H, a_row_stride=H, bias=lw["b1"], gelu=True, out_bf16=ffn, ld_bf16=FF, aux_bf16=pre, ld_aux=FF
                     )
                 )
             )
             steps.append(
                 self._gemm(
-                    ops.make_gemm_args(
-                        self.ffn,
-                        lw["w2"],
-                        a_rows=M,
-                        a_inner=cfg.intermediate_size,
-                        a_row_stride=cfg.intermediate_size,
-                        bias=lw["b2"],
-                        resid=self.hidden,
-                        ld_resid=H,
-                        out_f32=self.hidden,
-                        ld_f32=H,
-                    )
+                    ops.make_gemm_args(ffn, lw["w2"], a_rows=M, a_inner=FF, a_row_stride=FF, bias=lw["b2"], resid=h_mid, ld_resid=H, out_f32=h_out, ld_f32=H)
                 )
             )
+        self.h_last = self.hs[len(p.layers)] if self.training else self.hidden
         gf, bf = p.final_ln
-        steps.append(lambda: ops.layernorm_rows(self.hidden, M, H, H, gf, bf, eps, out_bf16=self.x, ld_bf16=self.ldx))
-        steps.append(lambda: self._keep_hidden(len(p.layers)))
+        steps.append(lambda: ops.layernorm_rows(self.h_last, M, H, H, gf, bf, eps, out_bf16=self.x, ld_bf16=self.ldx))
+        steps.append(lambda: self._keep_hidden(len(p.layers), self.h_last))
 
-    def _keep_hidden(self, index: int) -> None:
-        """Hidden state ``index`` of HF's ``hidden_states`` tuple is live in ``self.hidden`` right now
+    def _keep_hidden(self, index: int, hidden: Tensor) -> None:
+        """Hidden state ``index`` of HF's ``hidden_states`` tuple is live in ``hidden`` right now
         (for the last index: the final LayerNorm output, already in X)."""
         last = len(self.packed.layers)
         if self.captured is not None:
             if index < last:
-                self.captured.append(self.hidden.clone())
+                self.captured.append(hidden.clone())
             else:
                 self.captured.append(self.x[:, : self.cfg.hidden_size].float())
         column = self.hidden_blocks.get(index)
         if column is not None and index < last:
-            ops.cast_bf16_2d(self.hidden, self.cfg.hidden_size, self.x[:, column:], self.ldx, self.rows, self.cfg.hidden_size)
+            ops.cast_bf16_2d(hidden, self.cfg.hidden_size, self.x[:, column:], self.ldx, self.rows, self.cfg.hidden_size)
 
     # ------------------------------------------------------------------
     def run(self, audio: Tensor, lengths: Tensor, frames64: Tensor, capture: bool = False) -> None:
@@ -341,6 +389,7 @@ class EncoderPlan:
         p, cfg = self.packed, self.cfg
         N = self.n_utt
         self.captured = [] if capture else None
+        self.generation += 1
         ops.frame_lengths(lengths, self.kernels_dev, self.strides_dev, self.frames32, frames64)
         if self.use_lengths:
             self.att_lengths = self.frames32
@@ -358,3 +407,122 @@ class EncoderPlan:
             ops.conv0_gn_gelu(audio, lengths, mean_rstd, p.conv0_w, p.conv_bias[0], g, b, 1e-5, self.gn_raw, self.gn_stats, self.buf_a)
         for step in self._steps:
             step()
+
+    # ------------------------------------------------------------------ backward (training plans only)
+    @torch.no_grad()
+    def backward(self, d_x: Tensor, need_encoder: bool, need_projection: bool) -> Dict[str, Tensor]:
+        """Backward pass of everything ``run`` enqueued, from the gradient of the classifier feature matrix.
+
+        ``d_x`` fp32 ``[M, ldx]`` is dL/dX (X = ``[final LayerNorm | kept hidden states | ...]``).  Returns
+        fp32 gradients keyed by the Hugging Face parameter names of ``Wav2Vec2Weights`` for the transformer
+        (``need_encoder``) and the feature projection (``need_projection``).  The convolutional feature
+        extractor is frozen in the reference's configurations (``default_config.toml:40``,
+        ``acoustic_model.py:806-807``); its backward is not part of this build.
+
+        Every Linear contributes two tcgen05 GEMMs that read the forward pass's own buffers:
+        ``dX = dY W`` (W as an MN-major B operand) and ``dW = dY^T X`` (both operands MN-major, split-K
+        with TMA reduce-add stores); GELU' is fused into the FFN2 data-gradient epilogue and residual
+        accumulation into the LayerNorm backward kernel."""
+        if not self.training:
+            raise RuntimeError("this EncoderPlan was built for inference: no activations were kept")
+        p, cfg = self.packed, self.cfg
+        w = p.weights
+        N, M, H, FF = self.n_utt, self.rows, cfg.hidden_size, cfg.intermediate_size
+        heads, eps, seq = cfg.num_attention_heads, cfg.layer_norm_eps, self.seq
+        dev = d_x.device
+        grads: Dict[str, Tensor] = {}
+        new = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)  # noqa: E731
+        n_layers = len(p.layers)
+        dh, dh16 = self.dh, self.dh_bf16
+
+        def wgrad(dy: Tensor, ld_dy: int, m: int, x: Tensor, ld_x: int, n: int) -> Tensor:
+            out = new(m, n)
+            ops.run_gemm(ops.make_wgrad_args(dy, x, out, rows=M, m=m, ld_dy=ld_dy, n=n, ld_x=ld_x, ld_out=n))
+            return out
+
+        # final LayerNorm (HF:792): X[:, :H] = LN(hs[L])
+        gf, _ = p.final_ln
+        dg, db = (new(H), new(H)) if need_encoder else (None, None)
+        ops.layernorm_backward(self.hs[n_layers], H, d_x, self.ldx, M, H, gf, eps, None, 0, dh, H, dg, db)
+        if need_encoder:
+            grads["encoder.layer_norm.weight"], grads["encoder.layer_norm.bias"] = dg, db
+
+        for index in reversed(range(n_layers)):
+            lw, sv = p.layers[index], self.saved[index]
+            prefix = f"encoder.layers.{index}."
+            column = self.hidden_blocks.get(index + 1)
+            if column is not None and index + 1 < n_layers:  # hidden state index+1 is also a classifier input (OUTPUT_i)
+                ops.add_2d(dh, H, d_x[:, column:], self.ldx, M, H)
+            # ---- feed forward: h_out = h_mid + W2 gelu(W1 LN2(h_mid) + b1) + b2
+            ops.cast_bf16_2d(dh, H, dh16, H, M, H)
+            ops.run_gemm(ops.make_dgrad_args(dh16, lw["w2"], rows=M, ld_dy=H, k=H, n=FF, ld_w=FF, gelu_bwd=sv["pre"], ld_gelu_bwd=FF,
+                                             out_bf16=self.d_ff, ld_bf16=FF))  # fmt: skip
+            if need_encoder:
+                grads[prefix + "feed_forward.output_dense.weight"] = wgrad(dh16, H, H, sv["act"], FF, FF)
+                grads[prefix + "feed_forward.output_dense.bias"] = ops.colsum_f32(dh, M, H, H)
+                grads[prefix + "feed_forward.intermediate_dense.weight"] = wgrad(self.d_ff, FF, FF, sv["ln2"], H, H)
+                grads[prefix + "feed_forward.intermediate_dense.bias"] = ops.colsum_bf16(self.d_ff, M, FF, FF)
+            ops.run_gemm(ops.make_dgrad_args(self.d_ff, lw["w1"], rows=M, ld_dy=FF, k=FF, n=H, ld_w=H, out_f32=self.d_ln, ld_f32=H))
+            g2, _ = lw["ln2"]
+            dg, db = (new(H), new(H)) if need_encoder else (None, None)
+            ops.layernorm_backward(self.mids[index], H, self.d_ln, H, M, H, g2, eps, dh, H, dh, H, dg, db)
+            if need_encoder:
+                grads[prefix + "final_layer_norm.weight"], grads[prefix + "final_layer_norm.bias"] = dg, db
+            # ---- attention block: h_mid = h_in + Wo attention(Wqkv LN1(h_in)) + bo
+            ops.cast_bf16_2d(dh, H, dh16, H, M, H)
+            ops.run_gemm(ops.make_dgrad_args(dh16, lw["wo"], rows=M, ld_dy=H, k=H, n=H, ld_w=H, out_bf16=self.d_ctx, ld_bf16=H))
+            if need_encoder:
+                grads[prefix + "attention.out_proj.weight"] = wgrad(dh16, H, H, sv["ctx"], H, H)
+                grads[prefix + "attention.out_proj.bias"] = ops.colsum_f32(dh, M, H, H)
+            ops.attention_backward(sv["q"], sv["k"], sv["v"], sv["ctx"], self.d_ctx, sv["lse"], self.delta, self.dqkv, self.att_lengths, N, heads, seq)
+            if need_encoder:
+                grad_wqkv = wgrad(self.dqkv, 3 * H, 3 * H, sv["ln1"], H, H)
+                grad_bqkv = ops.colsum_bf16(self.dqkv, M, 3 * H, 3 * H)
+                for part, name in enumerate(("q_proj", "k_proj", "v_proj")):
+                    grads[prefix + f"attention.{name}.weight"] = grad_wqkv[part * H : (part + 1) * H]
+                    grads[prefix + f"attention.{name}.bias"] = grad_bqkv[part * H : (part + 1) * H]
+            ops.run_gemm(ops.make_dgrad_args(self.dqkv, lw["wqkv"], rows=M, ld_dy=3 * H, k=3 * H, n=H, ld_w=H, out_f32=self.d_ln, ld_f32=H))
+            g1, _ = lw["ln1"]
+            dg, db = (new(H), new(H)) if need_encoder else (None, None)
+            ops.layernorm_backward(self.hs[index], H, self.d_ln, H, M, H, g1, eps, dh, H, dh, H, dg, db)
+            if need_encoder:
+                grads[prefix + "layer_norm.weight"], grads[prefix + "layer_norm.bias"] = dg, db
+
+        column = self.hidden_blocks.get(0)
+        if column is not None and n_layers > 0:
+            ops.add_2d(dh, H, d_x[:, column:], self.ldx, M, H)
+        # ---- positional conv embedding (HF:764-765, 353-368): hs[0] = h_fp + gelu(conv(h_fp) + b)
+        taps = cfg.num_conv_pos_embeddings
+        pc = w.encoder.pos_conv_embed.conv
+        ops.gelu_backward_bf16(dh, H, self.pos_pre, H, M, H, dh16, H)  # dh16 = d(conv output)
+        if need_encoder:
+            grads["encoder.pos_conv_embed.conv.bias"] = ops.colsum_bf16(dh16, M, H, H)
+            raw = new(taps, H, 256)
+            args = ops.make_wgrad_args(dh16, self.hidden_bf16, raw, rows=seq, m=H, ld_dy=H, n=H, ld_x=H, ld_out=256)
+            args.mode, args.n_taps, args.tap_pad = _lib.APH_GEMM_DIAG_TAPS, taps, taps // 2
+            args.k_batch, args.a_batch_stride, args.b_seg_stride = N, seq * H, seq * H
+            args.out_batch_rows = H
+            ops.run_gemm(args)
+            grad_g, grad_v = ops.posconv_weight_backward(raw, pc.parametrizations.weight.original0, pc.parametrizations.weight.original1)
+            grads["encoder.pos_conv_embed.conv.parametrizations.weight.original0"] = grad_g
+            grads["encoder.pos_conv_embed.conv.parametrizations.weight.original1"] = grad_v
+        if need_projection:
+            # data gradient of the grouped conv: the same sliding-tap GEMM with flipped taps, accumulated onto dh
+            ops.run_gemm(
+                ops.make_gemm_args(
+                    dh16, p.pos_w_dgrad, a_rows=seq, a_inner=H, a_row_stride=H, batch=N, a_batch_stride=seq * H, mode=_lib.APH_GEMM_TAPS,
+                    tap_pad=taps // 2 - 1, n=H, k=taps * 64, resid=dh, ld_resid=H, out_f32=dh, ld_f32=H, out_batch_rows=seq,
+                )
+            )  # fmt: skip
+            # ---- feature projection (HF:422-434) behind the padded-frame zeroing (HF:753-756)
+            if self.use_lengths:
+                ops.mask_rows(dh, H, M, H, self.frames32, seq)
+            ops.cast_bf16_2d(dh, H, dh16, H, M, H)
+            grads["feature_projection.projection.weight"] = wgrad(dh16, H, H, self.fp_in, 512, 512)
+            grads["feature_projection.projection.bias"] = ops.colsum_f32(dh, M, H, H)
+            ops.run_gemm(ops.make_dgrad_args(dh16, p.fp_w, rows=M, ld_dy=H, k=H, n=512, ld_w=512, out_f32=self.d_fp_in, ld_f32=512))
+            gp, _ = p.fp_ln
+            dg, db = new(512), new(512)
+            ops.layernorm_backward(self.conv_out, 512, self.d_fp_in, 512, M, 512, gp, eps, None, 0, self.d_fp_in, 512, dg, db)
+            grads["feature_projection.layer_norm.weight"], grads["feature_projection.layer_norm.bias"] = dg, db
+        return grads

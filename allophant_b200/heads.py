@@ -51,6 +51,22 @@ class _LevelLayout:
     feeds_later: List[str] = field(default_factory=list)  # classifiers of this level used as dependencies
 
 
+class _ProjectionFunction(torch.autograd.Function):
+    """All classifier heads as one autograd node: forward and backward run in ``liballophant_b200.so``."""
+
+    @staticmethod
+    def forward(ctx, runtime, state, *parameters):
+        ctx.runtime = runtime
+        ctx.state = state
+        outputs = runtime._differentiable_forward_impl(state)
+        return outputs
+
+    @staticmethod
+    def backward(ctx, *grads):
+        parameter_grads = ctx.runtime._differentiable_backward_impl(ctx.state, grads)
+        return (None, None, *parameter_grads)
+
+
 class HeadsRuntime:
     def __init__(self, model: Any) -> None:
         self.model = model
@@ -187,29 +203,19 @@ class HeadsRuntime:
             cache["v"] = tensor
         return tensor
 
-    # ------------------------------------------------------------------ forward
-    def forward(self, batch: Batch, target_feature_indices: Optional[Tensor], predict: bool, log_probabilities: bool):
-        from .network.acoustic_model import Predictions
-
-        model = self.model
-        projection = model._projection
-        if not self._layout_ready:
-            self._build_layout()
-        if torch.is_grad_enabled() and model.training and any(p.requires_grad for p in model.parameters()):
-            raise NotImplementedError(
-                "allophant_b200: the differentiable training forward is not available in this build; "
-                "wrap inference in torch.inference_mode()/no_grad() or call model.eval()"
-            )
-        acoustic = model._acoustic_model
-        plan, frames = acoustic.encode(batch, self.ldx, self.hidden_blocks)
+    # ------------------------------------------------------------------ level GEMMs
+    def _run_levels(self, plan, batch: Batch, target_feature_indices: Optional[Tensor], predict: bool, keep: Optional[Dict[str, Any]]):
+        """Evaluates every classifier level.  Returns the heads list [(name, buffer, ld, column, width)] in the
+        reference's output order; with ``keep`` (a dict) also records what the backward pass needs."""
+        projection = self.model._projection
         device = plan.x.device
-        self._ensure_weights(device)
         rows, n_utt, seq = plan.rows, plan.n_utt, plan.seq
         skip = 0 if projection._dependency_blanks else projection._blank_offset
-
         # (name, logits buffer, leading dim, first column, width) in topological order
         heads: List[Tuple[str, Tensor, int, int, int]] = []
         level_logits: List[Tensor] = []
+        level_bf16: List[Optional[Tensor]] = []
+        composed_info: Dict[str, Dict[str, Any]] = {}
         produced_all: Dict[str, Tuple[Tensor, int, int, int]] = {}
         for level_index, layout in enumerate(self.levels):
             logits = torch.empty(rows, layout.n_pad, device=device, dtype=torch.float32)
@@ -228,6 +234,7 @@ class HeadsRuntime:
             )
             ops.run_gemm(args)
             level_logits.append(logits)
+            level_bf16.append(logits_bf16)
             produced: Dict[str, Tuple[Tensor, int, int, int]] = {}
             for spec in layout.specs:
                 classifier = projection._layers[spec.name]
@@ -248,7 +255,7 @@ class HeadsRuntime:
                         ld_f32=table.shape[0],
                     )
                     ops.run_gemm(comp_args)
-                    level_logits.append(composed)
+                    composed_info[spec.name] = dict(table=table, classes=classes, logits=composed, level=level_index, offset=offset)
                     produced[spec.name] = (composed, table.shape[0], 0, classes)
                 else:
                     produced[spec.name] = (logits, layout.n_pad, offset, spec.out_features)
@@ -280,14 +287,48 @@ class HeadsRuntime:
             classifier = projection._layers[spec.name]
             buffer, ld, column, width = produced_all[spec.name]
             if classifier._allophone_layer is not None:
-                if not predict:
-                    raise NotImplementedError(
-                        "allophant_b200: the allophone layer's training forward (map_allophones) is not available in this build"
-                    )
-                heads.append((ProjectionEntryConfig.PHONE, buffer, ld, column, width))
-                heads.append((ProjectionEntryConfig.PHONEME_LAYER, buffer, ld, column, width))
+                if predict:
+                    # acoustic_model.py:164-166: phone logits under both names
+                    heads.append((ProjectionEntryConfig.PHONE, buffer, ld, column, width))
+                    heads.append((ProjectionEntryConfig.PHONEME_LAYER, buffer, ld, column, width))
+                else:
+                    mapped, argmax = self._map_allophones(buffer[:, column : column + width].view(n_utt, seq, width), batch.language_ids)
+                    if keep is not None:
+                        keep["allophone"] = dict(argmax=argmax, source=(buffer, ld, column, width), name=spec.name)
+                    heads.append((ProjectionEntryConfig.PHONEME_LAYER, mapped.view(rows, -1), mapped.shape[-1], 0, mapped.shape[-1]))
             else:
                 heads.append((spec.name, buffer, ld, column, width))
+
+        if keep is not None:
+            keep.update(level_logits=level_logits, level_bf16=level_bf16, produced=produced_all, composed=composed_info)
+        return heads, produced_all
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, batch: Batch, target_feature_indices: Optional[Tensor], predict: bool, log_probabilities: bool):
+        from .network.acoustic_model import Predictions
+
+        model = self.model
+        projection = model._projection
+        if not self._layout_ready:
+            self._build_layout()
+        acoustic = model._acoustic_model
+        if torch.is_grad_enabled() and not log_probabilities:
+            weights = acoustic._model
+            if any(p.requires_grad for p in weights.feature_extractor.parameters()):
+                raise NotImplementedError(
+                    "allophant_b200: the backward pass of the convolutional feature extractor is not part of this build; keep "
+                    "nn.acoustic_model.freeze_feature_encoder = true (the reference's default, default_config.toml:40) or run "
+                    "under torch.no_grad()/inference_mode()"
+                )
+            need_encoder = any(p.requires_grad for p in weights.encoder.parameters())
+            need_feature_projection = any(p.requires_grad for p in weights.feature_projection.parameters())
+            if need_encoder or need_feature_projection or any(p.requires_grad for p in projection.parameters()):
+                return self._forward_differentiable(batch, target_feature_indices, predict, need_encoder, need_feature_projection)
+        plan, frames = acoustic.encode(batch, self.ldx, self.hidden_blocks)
+        device = plan.x.device
+        self._ensure_weights(device)
+        rows, n_utt, seq = plan.rows, plan.n_utt, plan.seq
+        heads, _ = self._run_levels(plan, batch, target_feature_indices, predict, keep=None)
 
         if not log_probabilities:
             outputs = {
@@ -355,8 +396,219 @@ class HeadsRuntime:
         )
         return predictions
 
-    def map_allophones(self, phone_logits: Tensor, language_ids: Tensor) -> Tensor:
+    # ------------------------------------------------------------------ differentiable path (training)
+    def _forward_differentiable(self, batch: Batch, target_feature_indices: Optional[Tensor], predict: bool, need_encoder: bool, need_feature_projection: bool):
+        """Training / validation forward with autograd: the whole model is ONE ``torch.autograd.Function``.
+
+        torch only carries the graph edge from the returned logits back to the parameters; forward and
+        backward run in ``liballophant_b200.so`` (``EncoderPlan.run`` / ``EncoderPlan.backward`` for the
+        wav2vec2 encoder, the level GEMMs and the small kernels of ``aph_train.cu`` for the heads).
+        Stochastic regularisation (HF dropout / LayerDrop / SpecAugment, the dropout on the acoustic-model
+        outputs, ``acoustic_model.py:486-488``) is not applied: the arithmetic is the ``eval()``-mode
+        arithmetic, which is what the parity tests pin against the reference."""
+        from .network.acoustic_model import Predictions
+
+        acoustic = self.model._acoustic_model
+        through_encoder = need_encoder or need_feature_projection
+        with torch.no_grad():
+            plan, frames = acoustic.encode(batch, self.ldx, self.hidden_blocks, training=through_encoder)
+            self._ensure_weights(plan.x.device)
+        named = [(f"_projection.{name}", parameter) for name, parameter in self.model._projection.named_parameters()]
+        if through_encoder:
+            named += [(f"_acoustic_model._model.{name}", parameter) for name, parameter in acoustic._model.named_parameters() if parameter.requires_grad]
+        state: Dict[str, Any] = dict(
+            batch=batch, tfi=target_feature_indices, predict=predict, plan=plan, names=[n for n, _ in named], generation=None,
+            need_encoder=need_encoder, need_feature_projection=need_feature_projection,
+        )  # fmt: skip
+        outputs = _ProjectionFunction.apply(self, state, *[p for _, p in named])
+        names = state["head_names"]
+        return Predictions({name: tensor.transpose(0, 1) for name, tensor in zip(names, outputs)}, frames)
+
+    @torch.no_grad()
+    def _differentiable_forward_impl(self, state: Dict[str, Any]) -> Tuple[Tensor, ...]:
+        plan = state["plan"]
+        keep: Dict[str, Any] = {}
+        heads, _ = self._run_levels(plan, state["batch"], state["tfi"], state["predict"], keep)
+        rows, n_utt, seq = plan.rows, plan.n_utt, plan.seq
+        state.update(keep)
+        state["generation"] = plan.generation  # the plan's buffers (X, kept activations) are overwritten by its next run
+        state["heads"] = heads
+        state["head_names"] = [name for name, *_ in heads]
+        state["dims"] = (rows, n_utt, seq)
+        return tuple(buffer[:, column : column + width].reshape(n_utt, seq, width).contiguous() for _, buffer, _, column, width in heads)
+
+    @torch.no_grad()
+    def _differentiable_backward_impl(self, state: Dict[str, Any], grads: Tuple[Optional[Tensor], ...]) -> List[Optional[Tensor]]:
+        projection = self.model._projection
+        plan = state["plan"]
+        if plan.generation != state["generation"]:
+            raise RuntimeError(
+                "allophant_b200: the activations of this forward pass were overwritten by a later forward pass of the same "
+                "batch shape; call backward() before running the next training forward"
+            )
+        rows, n_utt, seq = state["dims"]
+        x = plan.x
+        device = x.device
+        skip = 0 if projection._dependency_blanks else projection._blank_offset
+        param_grads: Dict[str, Tensor] = {}
+        through_encoder = state["need_encoder"] or state["need_feature_projection"]
+        need_dx = through_encoder or any(layout.feeds_later for layout in self.levels)
+
+        # gradient of every classifier's final logits, keyed by classifier name, fp32 [rows, width]
+        head_grads: Dict[str, Tensor] = {}
+        for (name, _, _, _, width), grad in zip(state["heads"], grads):
+            if grad is None:
+                continue
+            flat = grad.float().reshape(rows, width)
+            head_grads[name] = head_grads[name] + flat if name in head_grads else flat
+        # allophone layer: "phoneme" (mapped) -> gradient w.r.t. the phone logits and the matrices
+        allophone = state.get("allophone")
+        if allophone is not None and ProjectionEntryConfig.PHONEME_LAYER in head_grads:
+            buffer, ld, column, width = allophone["source"]
+            layer = projection._layers[allophone["name"]]._allophone_layer
+            languages = state["batch"].language_ids.to(device=device, dtype=torch.int64).contiguous()
+            grad_mapped = head_grads.pop(ProjectionEntryConfig.PHONEME_LAYER).contiguous()
+            grad_phone, grad_matrices = ops.allophone_backward(
+                grad_mapped.view(n_utt, seq, -1), allophone["argmax"], buffer[:, column : column + width].view(n_utt, seq, width),
+                layer._allophone_matrices.detach().float().contiguous(), languages, True, True,
+            )  # fmt: skip
+            param_grads[f"_projection._layers.{allophone['name']}._allophone_layer._allophone_matrices"] = grad_matrices
+            head_grads["__phone__" + allophone["name"]] = grad_phone.view(rows, width)
+        elif state["predict"]:
+            # predict=True returns the phone logits under both names: both gradients flow into the same logits
+            phone = head_grads.pop(ProjectionEntryConfig.PHONE, None)
+            if phone is not None:
+                key = ProjectionEntryConfig.PHONEME_LAYER
+                head_grads[key] = head_grads[key] + phone if key in head_grads else phone
+
+        d_x: Optional[Tensor] = None  # dL/dX fp32 [rows, ldx], accumulated over the levels (highest level first)
+        for level_index in reversed(range(len(self.levels))):
+            layout = self.levels[level_index]
+            n_pad = layout.n_pad
+            grad_level = torch.zeros(rows, n_pad, device=device, dtype=torch.float32)
+            # gradients arriving through the dependency probabilities of later levels (all processed already)
+            feeders = [name for name in layout.feeds_later]
+            if feeders and d_x is not None:
+                for name in feeders:
+                    if projection._layers[name]._composition_layer is not None or projection._layers[name]._allophone_layer is not None:
+                        raise NotImplementedError("gradients through a composed/allophone phoneme layer used as a dependency are not implemented")
+                x_col = self._int_tensor(("bwd_xcol", level_index), [self.dep_cols[name][0] for name in feeders], device, torch.int32)
+                widths = self._int_tensor(("bwd_w", level_index, skip), [self.dep_cols[name][1] + skip for name in feeders], device, torch.int32)
+                dst_col = self._int_tensor(("bwd_dst", level_index), [layout.offsets[name] for name in feeders], device, torch.int32)
+                ops.softmax_backward_cols(d_x, self.ldx, x, self.ldx, rows, x_col, widths, dst_col, len(feeders), skip, grad_level, n_pad)
+            for spec in layout.specs:
+                classifier = projection._layers[spec.name]
+                offset = layout.offsets[spec.name]
+                grad = head_grads.get(spec.name)
+                if grad is None:
+                    grad = head_grads.get("__phone__" + spec.name)
+                if grad is None:
+                    continue
+                if classifier._composition_layer is None:
+                    grad_level[:, offset : offset + spec.out_features] += grad
+                    continue
+                # composed phoneme logits = (projection @ table^T) / sqrt(E)   (acoustic_model.py:219-234)
+                info = state["composed"][spec.name]
+                table, classes = info["table"], info["classes"]
+                embedding = classifier._composition_layer.embedding_size
+                v_pad = table.shape[0]
+                grad_logits = torch.zeros(rows, v_pad, device=device, dtype=torch.bfloat16)
+                grad_logits[:, :classes] = grad
+                scale = 1.0 / math.sqrt(embedding)
+                # d projection [rows, E] = d logits @ table * scale, accumulated into this level's logits gradient
+                grad_projection = torch.empty(rows, embedding, device=device, dtype=torch.float32)
+                ops.run_gemm(ops.make_dgrad_args(grad_logits, table, rows=rows, ld_dy=v_pad, k=v_pad, n=embedding, ld_w=embedding, scale=scale,
+                                                 out_f32=grad_projection, ld_f32=embedding))  # fmt: skip
+                grad_level[:, offset : offset + embedding] += grad_projection
+                # d table [v_pad, E] = d logits^T @ projection * scale -> EmbeddingBag backward
+                projection_bf16 = state["level_bf16"][level_index]
+                grad_table = torch.empty(v_pad, embedding, device=device, dtype=torch.float32)
+                ops.run_gemm(ops.make_wgrad_args(grad_logits, projection_bf16[:, offset:], grad_table, rows=rows, m=v_pad, ld_dy=v_pad,
+                                                 n=embedding, ld_x=n_pad, ld_out=embedding, scale=scale))  # fmt: skip
+                layer = classifier._composition_layer
+                weight = layer._attribute_embeddings.weight
+                grad_weight = torch.zeros(weight.shape, device=device, dtype=torch.float32)
+                if state["tfi"] is None:
+                    indices, offsets = layer._dense_feature_table, None
+                else:
+                    indices, offsets = state["tfi"], layer._category_offsets
+                indices = indices.to(device=device, dtype=torch.int64).contiguous()
+                offsets = None if offsets is None else offsets.to(device=device, dtype=torch.int64).contiguous().view(-1)
+                ops.embedding_bag_backward(grad_table, embedding, indices, offsets, grad_weight)
+                param_grads[f"_projection._layers.{spec.name}._composition_layer._attribute_embeddings.weight"] = grad_weight
+            # weight / bias gradients of the level: dW = dY^T X, db = colsum(dY)
+            grad_level_bf16 = ops.cast_bf16(grad_level)
+            grad_weight_level = torch.empty(n_pad, self.ldx, device=device, dtype=torch.float32)
+            ops.run_gemm(ops.make_wgrad_args(grad_level_bf16, x, grad_weight_level, rows=rows, m=n_pad, ld_dy=n_pad, n=self.ldx, ld_x=self.ldx,
+                                             ld_out=self.ldx))  # fmt: skip
+            grad_bias_level = ops.colsum_f32(grad_level, rows, n_pad, n_pad)
+            for spec in layout.specs:
+                linear = projection._layers[spec.name]._time_distributed_layer
+                row = layout.offsets[spec.name]
+                grad_w = torch.empty(linear.weight.shape, device=device, dtype=torch.float32)
+                source_column = 0
+                for dependency in spec.dependencies:
+                    if _PATTERN.match(dependency.name):
+                        target = self.x_cols[dependency.name]
+                    else:
+                        target = self.dep_cols[dependency.name][0]
+                    grad_w[:, source_column : source_column + dependency.size] = grad_weight_level[row : row + spec.out_features, target : target + dependency.size]
+                    source_column += dependency.size
+                param_grads[f"_projection._layers.{spec.name}._time_distributed_layer.weight"] = grad_w
+                param_grads[f"_projection._layers.{spec.name}._time_distributed_layer.bias"] = grad_bias_level[row : row + spec.out_features].clone()
+            # data gradient dX += dY @ W_level (W read in its forward layout as an MN-major operand)
+            if need_dx and (through_encoder or level_index > 0):
+                if d_x is None:
+                    d_x = torch.empty(rows, self.ldx, device=device, dtype=torch.float32)
+                    resid = None
+                else:
+                    resid = d_x
+                ops.run_gemm(ops.make_dgrad_args(grad_level_bf16, self.level_w[level_index], rows=rows, ld_dy=n_pad, k=n_pad, n=self.ldx, ld_w=self.ldx,
+                                                 resid=resid, ld_resid=self.ldx, out_f32=d_x, ld_f32=self.ldx))  # fmt: skip
+
+        if through_encoder:
+            assert d_x is not None
+            encoder_grads = plan.backward(d_x, state["need_encoder"], state["need_feature_projection"])
+            for name, value in encoder_grads.items():
+                param_grads[f"_acoustic_model._model.{name}"] = value
+        return [param_grads.get(name) for name in state["names"]]
+
+    # ------------------------------------------------------------------ allophone layer
+    def _allophone_csr(self, layer: Any, device: torch.device) -> Tuple[Tensor, Tensor]:
+        """CSR list of the allowed (phone, phoneme) pairs per language; the mask is fixed at construction
+        (``acoustic_model.py:134-136``), only the matrix values train."""
+        cached = getattr(self, "_csr_cache", None)
+        if cached is not None and cached[0] == (layer._allophone_mask.data_ptr(), str(device)):
+            return cached[1], cached[2]
+        allowed = ~layer._allophone_mask.cpu()  # [L, P+1, Q+1]
+        offsets, phones = [0], []
+        for language in range(allowed.shape[0]):
+            for phoneme in range(allowed.shape[2]):
+                listed = torch.nonzero(allowed[language, :, phoneme]).flatten().tolist()
+                phones.extend(listed)
+                offsets.append(len(phones))
+        csr_off = torch.tensor(offsets, dtype=torch.int32, device=device)
+        csr_p = torch.tensor(phones if phones else [0], dtype=torch.int32, device=device)
+        self._csr_cache = ((layer._allophone_mask.data_ptr(), str(device)), csr_off, csr_p)
+        return csr_off, csr_p
+
+    def _map_allophones(self, phone_logits: Tensor, language_ids: Tensor) -> Tuple[Tensor, Tensor]:
+        """``phone_logits`` fp32 [N, T', P+1] (batch-first view) -> ([N, T', Q+1], argmax)."""
         layer = self.model._projection._layers[ProjectionEntryConfig.PHONEME_LAYER]._allophone_layer
         if layer is None:
             raise ValueError("Can't map phones to allophones with a model without an allophone layer")
-        raise NotImplementedError("allophant_b200: map_allophones is not available in this build")
+        device = phone_logits.device
+        csr_off, csr_p = self._allophone_csr(layer, device)
+        languages = language_ids.to(device=device, dtype=torch.int64).contiguous()
+        matrices = layer._allophone_matrices.detach().float().contiguous()
+        return ops.allophone_forward(phone_logits, matrices, csr_off, csr_p, languages)
+
+    def map_allophones(self, phone_logits: Tensor, language_ids: Tensor) -> Tensor:
+        """``Allophant.map_allophones`` (``acoustic_model.py:1040-1041``): time-first ``[T', N, P+1]`` in and out."""
+        if not phone_logits.is_cuda:
+            raise RuntimeError("allophant_b200 runs on CUDA only")
+        batch_first = phone_logits.float().transpose(0, 1)
+        if batch_first.stride(-1) != 1:
+            batch_first = batch_first.contiguous()
+        mapped, _ = self._map_allophones(batch_first, language_ids)
+        return mapped.transpose(0, 1)

@@ -349,19 +349,25 @@ class Wav2Vec2AcousticModel(AcousticModel):
         return lengths
 
     # -- engine access ---------------------------------------------------------------------
-    def plan_for(self, n_utt: int, samples: int, ldx: int, hidden_blocks: Dict[int, int]) -> EncoderPlan:
+    def plan_for(self, n_utt: int, samples: int, ldx: int, hidden_blocks: Dict[int, int], training: bool = False) -> EncoderPlan:
         self._packed.ensure()
-        key = (n_utt, samples, ldx, tuple(sorted(hidden_blocks.items())))
+        key = (n_utt, samples, ldx, tuple(sorted(hidden_blocks.items())), training)
         plan = self._plans.get(key)
         if plan is None or plan.packed_version != self._packed._version:
-            if len(self._plans) >= 4:  # workspaces are large: keep a handful of shapes
+            if plan is None and len(self._plans) >= 4:  # workspaces are large: keep a handful of shapes
                 self._plans.pop(next(iter(self._plans)))
-            plan = EncoderPlan(self._packed, n_utt, samples, ldx, hidden_blocks, self._normalize, self._use_attention_mask)
+            if plan is not None and plan.packed_version != self._packed._version:
+                # same shape, new weights (an optimizer step): keep the workspaces, rebuild the launch list only
+                plan.rebind(self._packed)
+            else:
+                plan = EncoderPlan(self._packed, n_utt, samples, ldx, hidden_blocks, self._normalize, self._use_attention_mask, training)
             plan.packed_version = self._packed._version
             self._plans[key] = plan
         return plan
 
-    def encode(self, batch: Batch, ldx: int, hidden_blocks: Dict[int, int], capture: bool = False) -> Tuple[EncoderPlan, Tensor]:
+    def encode(
+        self, batch: Batch, ldx: int, hidden_blocks: Dict[int, int], capture: bool = False, training: bool = False
+    ) -> Tuple[EncoderPlan, Tensor]:
         audio = batch.audio_features
         if not audio.is_cuda:
             raise RuntimeError("allophant_b200 runs on CUDA only: move the batch to the GPU (`batch.to('cuda')`)")
@@ -371,7 +377,7 @@ class Wav2Vec2AcousticModel(AcousticModel):
             raise ValueError(f"expected raw audio of shape [batch, samples], got {tuple(audio.shape)}")
         audio = audio.float().contiguous()
         lengths = batch.lengths.to(device=audio.device, dtype=torch.int64).contiguous()
-        plan = self.plan_for(audio.shape[0], audio.shape[1], ldx, hidden_blocks)
+        plan = self.plan_for(audio.shape[0], audio.shape[1], ldx, hidden_blocks, training)
         frames = torch.empty(audio.shape[0], device=audio.device, dtype=torch.int64)
         plan.run(audio, lengths, frames, capture)
         return plan, frames

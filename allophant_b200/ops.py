@@ -70,9 +70,13 @@ def make_gemm_args(
     out_batch_rows: int = 0,
     lengths: Optional[Tensor] = None,
     len_period: int = 0,
+    aux_bf16: Optional[Tensor] = None,
+    ld_aux: int = 0,
+    gelu_bwd: Optional[Tensor] = None,
+    ld_gelu_bwd: int = 0,
 ) -> GemmArgs:
     """Builds an ``aph_gemm_args`` (store epilogue).  The caller keeps the tensors alive."""
-    _require_cuda(a, w, bias, resid, out_f32, out_bf16, lengths)
+    _require_cuda(a, w, bias, resid, out_f32, out_bf16, lengths, aux_bf16, gelu_bwd)
     g = GemmArgs()
     g.a = a.data_ptr()
     g.a_row_stride, g.a_batch_stride = a_row_stride, a_batch_stride
@@ -90,13 +94,83 @@ def make_gemm_args(
     g.out_bf16, g.ld_bf16 = _ptr(out_bf16), ld_bf16
     g.out_batch_rows = out_batch_rows
     g.lengths, g.len_period = _ptr(lengths), len_period
+    g.aux_bf16, g.ld_aux = _ptr(aux_bf16), ld_aux
+    g.gelu_bwd, g.ld_gelu_bwd = _ptr(gelu_bwd), ld_gelu_bwd
+    return g
+
+
+def make_dgrad_args(
+    dy: Tensor,
+    w: Tensor,
+    *,
+    rows: int,
+    ld_dy: int,
+    k: int,
+    n: int,
+    ld_w: int,
+    scale: float = 1.0,
+    gelu_bwd: Optional[Tensor] = None,
+    ld_gelu_bwd: int = 0,
+    resid: Optional[Tensor] = None,
+    ld_resid: int = 0,
+    out_f32: Optional[Tensor] = None,
+    ld_f32: int = 0,
+    out_bf16: Optional[Tensor] = None,
+    ld_bf16: int = 0,
+) -> GemmArgs:
+    """Data gradient of ``y = x @ w.T``: ``dx[rows, n] = dy[rows, k] @ w[k, n]`` with ``w`` read in its
+    forward layout ``[out = k][in = n]`` as an MN-major B operand (no transposed copy)."""
+    _require_cuda(dy, w, gelu_bwd, resid, out_f32, out_bf16)
+    g = GemmArgs()
+    g.a = dy.data_ptr()
+    g.a_row_stride, g.a_batch_stride = ld_dy, 0
+    g.a_rows, g.a_inner, g.batch = rows, k, 1
+    g.mode = _lib.APH_GEMM_ROWS
+    g.b, g.n, g.k = w.data_ptr(), n, k
+    g.b_mn_major, g.b_row_stride, g.k_seq, g.k_batch = 1, ld_w, k, 1
+    g.epilogue = _lib.APH_EPI_STORE
+    g.scale = scale
+    g.gelu_bwd, g.ld_gelu_bwd = _ptr(gelu_bwd), ld_gelu_bwd
+    g.resid, g.ld_resid = _ptr(resid), ld_resid
+    g.out_f32, g.ld_f32 = _ptr(out_f32), ld_f32
+    g.out_bf16, g.ld_bf16 = _ptr(out_bf16), ld_bf16
+    return g
+
+
+def make_wgrad_args(
+    dy: Tensor,
+    x: Tensor,
+    out_f32: Tensor,
+    *,
+    rows: int,
+    m: int,
+    ld_dy: int,
+    n: int,
+    ld_x: int,
+    ld_out: int,
+    scale: float = 1.0,
+) -> GemmArgs:
+    """Weight gradient of ``y = x @ w.T``: ``dw[m, n] = sum_r dy[r, m] * x[r, n]`` with both operands read
+    frame-major as they were produced (MN-major A and B); the frame axis may have any length."""
+    _require_cuda(dy, x, out_f32)
+    g = GemmArgs()
+    g.a = dy.data_ptr()
+    g.a_row_stride, g.a_batch_stride = ld_dy, 0
+    g.a_rows, g.a_inner, g.batch = m, m, 1
+    g.mode = _lib.APH_GEMM_ROWS
+    g.b, g.n, g.k = x.data_ptr(), n, 0
+    g.a_mn_major, g.b_mn_major, g.b_row_stride, g.k_seq, g.k_batch = 1, 1, ld_x, rows, 1
+    g.epilogue = _lib.APH_EPI_STORE
+    g.scale = scale
+    g.out_f32, g.ld_f32 = out_f32.data_ptr(), ld_out
     return g
 
 
 def make_qkv_args(
-    a: Tensor, w_qkv: Tensor, bias_qkv: Tensor, q: Tensor, k: Tensor, vt: Tensor, *, rows: int, seq: int, heads: int, t_v: int
+    a: Tensor, w_qkv: Tensor, bias_qkv: Tensor, q: Tensor, k: Tensor, vt: Tensor, *, rows: int, seq: int, heads: int, t_v: int,
+    vmat: Optional[Tensor] = None,
 ) -> GemmArgs:
-    _require_cuda(a, w_qkv, bias_qkv, q, k, vt)
+    _require_cuda(a, w_qkv, bias_qkv, q, k, vt, vmat)
     hidden = heads * 64
     g = GemmArgs()
     g.a = a.data_ptr()
@@ -110,6 +184,7 @@ def make_qkv_args(
     g.len_period = seq
     g.q, g.kmat, g.vt = q.data_ptr(), k.data_ptr(), vt.data_ptr()
     g.heads, g.t_v, g.q_scale = heads, t_v, 0.125 * 1.4426950408889634  # head_dim^-0.5 * log2(e)
+    g.vmat = _ptr(vmat)
     return g
 
 
@@ -155,13 +230,30 @@ def linear_bf16(
 # --------------------------------------------------------------------------------------
 # attention
 # --------------------------------------------------------------------------------------
-def attention(q: Tensor, k: Tensor, vt: Tensor, ctx: Tensor, frame_lengths: Tensor, n_utt: int, heads: int, seq: int, t_v: int) -> None:
-    _require_cuda(q, k, vt, ctx, frame_lengths)
+def attention(
+    q: Tensor, k: Tensor, vt: Tensor, ctx: Tensor, frame_lengths: Tensor, n_utt: int, heads: int, seq: int, t_v: int, lse2: Optional[Tensor] = None
+) -> None:
+    _require_cuda(q, k, vt, ctx, frame_lengths, lse2)
     check(
-        lib.aph_attention_bf16(
-            q.data_ptr(), k.data_ptr(), vt.data_ptr(), ctx.data_ptr(), frame_lengths.data_ptr(), n_utt, heads, seq, t_v, _stream()
+        lib.aph_attention_bf16_lse(
+            q.data_ptr(), k.data_ptr(), vt.data_ptr(), ctx.data_ptr(), _ptr(lse2), frame_lengths.data_ptr(), n_utt, heads, seq, t_v, _stream()
         ),
-        "aph_attention_bf16",
+        "aph_attention_bf16_lse",
+    )
+
+
+def attention_backward(
+    q: Tensor, k: Tensor, v: Tensor, ctx: Tensor, d_ctx: Tensor, lse2: Tensor, delta_scratch: Tensor, dqkv: Tensor,
+    frame_lengths: Tensor, n_utt: int, heads: int, seq: int,
+) -> None:  # fmt: skip
+    """(dQ | dK | dV) bf16 ``[n_utt*seq, 3*heads*64]`` from the forward's q/k/v/ctx/lse2 and ``d_ctx``."""
+    _require_cuda(q, k, v, ctx, d_ctx, lse2, delta_scratch, dqkv, frame_lengths)
+    check(
+        lib.aph_attention_backward_bf16(
+            q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), d_ctx.data_ptr(), lse2.data_ptr(), delta_scratch.data_ptr(),
+            dqkv.data_ptr(), frame_lengths.data_ptr(), n_utt, heads, seq, _stream(),
+        ),  # fmt: skip
+        "aph_attention_backward_bf16",
     )
 
 
@@ -429,6 +521,130 @@ def pack_posconv_weight(weight_g: Tensor, weight_v: Tensor) -> Tensor:
     scratch = torch.empty(k, device=v.device, dtype=torch.float32)
     check(lib.aph_pack_posconv_weight(g.data_ptr(), v.data_ptr(), dst.data_ptr(), scratch.data_ptr(), o, cg, k, _stream()), "aph_pack_posconv_weight")
     return dst
+
+
+# --------------------------------------------------------------------------------------
+# training-side kernels of the classifier heads
+# --------------------------------------------------------------------------------------
+def allophone_forward(logits: Tensor, matrices: Tensor, csr_offsets: Tensor, csr_phones: Tensor, language_ids: Tensor) -> Tuple[Tensor, Tensor]:
+    """``logits`` fp32 [N, T, P+1] (any N/T strides) -> (mapped [N, T, Q+1] fp32, argmax int32)."""
+    _require_cuda(logits, matrices, csr_offsets, csr_phones, language_ids)
+    n, t, p1 = logits.shape
+    q1 = matrices.shape[2]
+    out = torch.empty(n, t, q1, device=logits.device, dtype=torch.float32)
+    arg = torch.empty(n, t, q1, device=logits.device, dtype=torch.int32)
+    check(
+        lib.aph_allophone_forward(
+            logits.data_ptr(), logits.stride(0), logits.stride(1), n, t, p1, q1, matrices.data_ptr(), csr_offsets.data_ptr(), csr_phones.data_ptr(), language_ids.data_ptr(), out.data_ptr(), arg.data_ptr(), _stream()
+        ),
+        "aph_allophone_forward",
+    )
+    return out, arg
+
+
+def allophone_backward(grad_out: Tensor, arg: Tensor, logits: Tensor, matrices: Tensor, language_ids: Tensor, need_logits_grad: bool, need_matrix_grad: bool):
+    _require_cuda(grad_out, arg, logits, matrices, language_ids)
+    n, t, p1 = logits.shape
+    q1 = matrices.shape[2]
+    grad_logits = torch.zeros(n, t, p1, device=logits.device, dtype=torch.float32) if need_logits_grad else None
+    grad_matrices = torch.zeros_like(matrices, dtype=torch.float32) if need_matrix_grad else None
+    check(
+        lib.aph_allophone_backward(
+            grad_out.data_ptr(), arg.data_ptr(), logits.data_ptr(), logits.stride(0), logits.stride(1), n, t, p1, q1, matrices.data_ptr(), language_ids.data_ptr(), _ptr(grad_logits), _ptr(grad_matrices), _stream()
+        ),
+        "aph_allophone_backward",
+    )
+    return grad_logits, grad_matrices
+
+
+def transpose_cast_bf16(x: Tensor, rows: int, cols: int, ld_in: int, rows_padded: int) -> Tensor:
+    """[rows, cols] (fp32/bf16, row stride ``ld_in``) -> bf16 [cols, rows_padded], zero padded."""
+    _require_cuda(x)
+    out = torch.empty(cols, rows_padded, device=x.device, dtype=torch.bfloat16)
+    check(lib.aph_transpose_cast_bf16(x.data_ptr(), int(x.dtype == torch.float32), ld_in, rows, cols, out.data_ptr(), rows_padded, rows_padded, _stream()), "aph_transpose_cast_bf16")
+    return out
+
+
+def colsum_f32(x: Tensor, rows: int, cols: int, ld: int) -> Tensor:
+    _require_cuda(x)
+    out = torch.empty(cols, device=x.device, dtype=torch.float32)
+    check(lib.aph_colsum_f32(x.data_ptr(), ld, rows, cols, out.data_ptr(), _stream()), "aph_colsum_f32")
+    return out
+
+
+def colsum_bf16(x: Tensor, rows: int, cols: int, ld: int) -> Tensor:
+    _require_cuda(x)
+    out = torch.empty(cols, device=x.device, dtype=torch.float32)
+    check(lib.aph_colsum_bf16(x.data_ptr(), ld, rows, cols, out.data_ptr(), _stream()), "aph_colsum_bf16")
+    return out
+
+
+def layernorm_backward(
+    x: Tensor, ld_x: int, dy: Tensor, ld_dy: int, rows: int, cols: int, gamma: Tensor, eps: float,
+    dx_resid: Optional[Tensor], ld_resid: int, dx: Tensor, ld_dx: int, dgamma: Optional[Tensor], dbeta: Optional[Tensor],
+) -> None:  # fmt: skip
+    _require_cuda(x, dy, gamma, dx_resid, dx, dgamma, dbeta)
+    check(
+        lib.aph_layernorm_backward(
+            x.data_ptr(), int(x.dtype == torch.float32), ld_x, dy.data_ptr(), int(dy.dtype == torch.float32), ld_dy, rows, cols,
+            gamma.data_ptr(), eps, _ptr(dx_resid), ld_resid, dx.data_ptr(), ld_dx, _ptr(dgamma), _ptr(dbeta), _stream(),
+        ),  # fmt: skip
+        "aph_layernorm_backward",
+    )
+
+
+def mask_rows(x: Tensor, ld: int, rows: int, cols: int, frame_lengths32: Tensor, period: int) -> None:
+    _require_cuda(x, frame_lengths32)
+    check(lib.aph_mask_rows_f32(x.data_ptr(), ld, rows, cols, frame_lengths32.data_ptr(), period, _stream()), "aph_mask_rows_f32")
+
+
+def add_2d(dst: Tensor, ld_dst: int, src: Tensor, ld_src: int, rows: int, cols: int) -> None:
+    _require_cuda(dst, src)
+    check(lib.aph_add_f32_2d(dst.data_ptr(), ld_dst, src.data_ptr(), ld_src, rows, cols, _stream()), "aph_add_f32_2d")
+
+
+def gelu_backward_bf16(dy: Tensor, ld_dy: int, pre: Tensor, ld_pre: int, rows: int, cols: int, out: Tensor, ld_out: int) -> None:
+    _require_cuda(dy, pre, out)
+    check(lib.aph_gelu_backward_bf16(dy.data_ptr(), ld_dy, pre.data_ptr(), ld_pre, rows, cols, out.data_ptr(), ld_out, _stream()), "aph_gelu_backward_bf16")
+
+
+def pack_posconv_weight_dgrad(weight_g: Tensor, weight_v: Tensor) -> Tensor:
+    """B operand of the positional conv's data-gradient GEMM (taps flipped, in/out channels swapped)."""
+    _require_cuda(weight_g, weight_v)
+    g = weight_g.detach().float().contiguous()
+    v = weight_v.detach().float().contiguous()
+    o, cg, k = v.shape
+    dst = torch.empty(o, k * cg, device=v.device, dtype=torch.bfloat16)
+    scratch = torch.empty(2 * k, device=v.device, dtype=torch.float32)
+    check(lib.aph_pack_posconv_weight_dgrad(g.data_ptr(), v.data_ptr(), dst.data_ptr(), scratch.data_ptr(), o, cg, k, _stream()), "aph_pack_posconv_weight_dgrad")
+    return dst
+
+
+def posconv_weight_backward(raw: Tensor, weight_g: Tensor, weight_v: Tensor) -> Tuple[Tensor, Tensor]:
+    """``raw`` fp32 [k, O, 256] from the DIAG_TAPS GEMM -> (grad of original0 [1,1,k], grad of original1 [O,Cg,k])."""
+    _require_cuda(raw, weight_g, weight_v)
+    g = weight_g.detach().float().contiguous()
+    v = weight_v.detach().float().contiguous()
+    o, cg, k = v.shape
+    grad_g = torch.empty(g.shape, device=v.device, dtype=torch.float32)
+    grad_v = torch.empty(v.shape, device=v.device, dtype=torch.float32)
+    scratch = torch.empty(3 * k, device=v.device, dtype=torch.float32)
+    check(lib.aph_posconv_weight_backward(raw.data_ptr(), g.data_ptr(), v.data_ptr(), scratch.data_ptr(), o, cg, k, grad_g.data_ptr(), grad_v.data_ptr(), _stream()), "aph_posconv_weight_backward")
+    return grad_g, grad_v
+
+
+def embedding_bag_backward(grad_rows: Tensor, ld: int, tfi: Tensor, category_offsets: Optional[Tensor], grad_weight: Tensor) -> None:
+    _require_cuda(grad_rows, tfi, category_offsets, grad_weight)
+    v, f = tfi.shape
+    check(lib.aph_embedding_bag_backward(grad_rows.data_ptr(), ld, v, f, grad_weight.shape[1], tfi.data_ptr(), _ptr(category_offsets), grad_weight.data_ptr(), _stream()), "aph_embedding_bag_backward")
+
+
+def softmax_backward_cols(grad_x: Tensor, ld_gx: int, x: Tensor, ld_x: int, rows: int, x_col: Tensor, width: Tensor, dst_col: Tensor, n_deps: int, skip: int, grad_logits: Tensor, ld_gl: int) -> None:
+    _require_cuda(grad_x, x, x_col, width, dst_col, grad_logits)
+    check(
+        lib.aph_softmax_backward_cols(grad_x.data_ptr(), ld_gx, x.data_ptr(), ld_x, rows, x_col.data_ptr(), width.data_ptr(), dst_col.data_ptr(), n_deps, skip, grad_logits.data_ptr(), ld_gl, _stream()),
+        "aph_softmax_backward_cols",
+    )
 
 
 # --------------------------------------------------------------------------------------

@@ -29,7 +29,7 @@ extern "C" {
 #define APH_ERR_CUDA (-2)        /* CUDA runtime / driver error                    */
 #define APH_ERR_UNSUPPORTED (-3) /* valid request outside the implemented envelope */
 
-#define APH_ABI_VERSION 1
+#define APH_ABI_VERSION 2
 
 /* ---- library ------------------------------------------------------------ */
 int aph_abi_version(void);
@@ -54,6 +54,8 @@ void aph_reset_launch_count(void);
  */
 #define APH_GEMM_ROWS 0    /* A rows addressed as base + row*a_row_stride (plain & strided conv) */
 #define APH_GEMM_TAPS 1    /* sliding taps: k-block j reads rows t - pad + j of channel group n/64 */
+#define APH_GEMM_DIAG_TAPS 2 /* weight gradient of the grouped positional conv (both operands MN-major):
+                              * work item (tap j, 256-channel block q): D_j[q] = A[:, q]^T . shift_j(B[:, q]) */
 #define APH_EPI_STORE 0    /* generic epilogue described above                                   */
 #define APH_EPI_QKV 1      /* scatter bf16 into Q[b,h,t,64] (pre-scaled), K[b,h,t,64], Vt[b,h,64,t_v] */
 
@@ -92,6 +94,27 @@ typedef struct aph_gemm_args {
   int32_t heads;
   int32_t t_v;            /* padded key length of Vt (multiple of 8) */
   float q_scale;
+  /* ---- ABI 2: operand majors and training epilogues (all zero = ABI 1 behaviour) ---------------
+   * MN-major operands let the backward GEMMs of nn.Linear read activations and weights in the
+   * layout the forward pass left them in (no transposed copies):
+   *   dgrad  dX[m,i] = sum_o dY[m,o] W[o,i]   A = dY (K-major),  B = W  [k=o][n=i]  (b_mn_major)
+   *   wgrad  dW[o,i] = sum_m dY[m,o] X[m,i]   A = dY [k=m][m=o]  (a_mn_major), B = X [k=m][n=i]
+   * An MN-major operand is addressed as [k_batch][k_seq][cols]: element (segment s, row r, col c) at
+   * base + s*seg_stride + r*row_stride + c; the contraction runs over all (s, r); rows outside
+   * [0, k_seq) read as zero (TMA fill).  k = k_batch * k_seq is implied, args.k is ignored. */
+  int32_t a_mn_major;     /* A stored [k rows][a_rows cols], row stride a_row_stride, segment stride a_batch_stride */
+  int32_t b_mn_major;     /* B stored [k rows][n cols] */
+  int64_t b_row_stride;   /* elements between stored rows of B (0: k for K-major, n for MN-major) */
+  int64_t b_seg_stride;   /* MN-major B: elements between segments */
+  int32_t k_seq;          /* MN-major: stored rows per segment */
+  int32_t k_batch;        /* MN-major: number of segments (0 = 1) */
+  int32_t b_k_shift;      /* MN-major B: row offset added inside the segment (DIAG_TAPS: tap - tap_pad is added on top) */
+  int32_t n_taps;         /* DIAG_TAPS: number of taps; output [n_taps][a_rows][256] fp32 */
+  void* aux_bf16;         /* store epilogue: value BEFORE gelu (after scale/bias), bf16 [rows][ld_aux] or NULL */
+  int64_t ld_aux;
+  const void* gelu_bwd;   /* store epilogue: v *= gelu'(pre[row][col]) with pre bf16 [rows][ld_gelu_bwd] or NULL */
+  int64_t ld_gelu_bwd;
+  void* vmat;             /* APH_EPI_QKV: additionally V row-major [b,h,t,64] (attention backward) or NULL */
 } aph_gemm_args;
 
 int aph_gemm_bf16(const aph_gemm_args* args, void* stream);
@@ -108,6 +131,22 @@ int aph_gemm_bf16(const aph_gemm_args* args, void* stream);
 int aph_attention_bf16(const void* q, const void* k, const void* vt, void* ctx,
                        const int32_t* lengths, int32_t n_utt, int32_t heads, int32_t T,
                        int32_t t_v, void* stream);
+
+/* Training variant: additionally writes lse2[n_utt*heads][T] = log2-domain log-sum-exp of every
+ * query row of a non-skipped tile (NULL = same as aph_attention_bf16). */
+int aph_attention_bf16_lse(const void* q, const void* k, const void* vt, void* ctx, float* lse2,
+                           const int32_t* lengths, int32_t n_utt, int32_t heads, int32_t T,
+                           int32_t t_v, void* stream);
+/* Backward of the same call (autograd of HF:466-549, reached from loss.backward(), estimator.py:738).
+ *   q, k, v : bf16 [n_utt*heads][T][64] as written by the QKV epilogue (q pre-scaled; v row-major = args.vmat)
+ *   ctx, d_ctx : bf16 [n_utt*T][heads*64] forward output and its gradient (rows of padded frames must be 0 in d_ctx)
+ *   lse2 : from aph_attention_bf16_lse; delta_scratch : fp32 [n_utt*heads][T]
+ *   dqkv : bf16 [n_utt*T][3*heads*64] = (dQ | dK | dV), dQ w.r.t. the UNSCALED query projection;
+ *          rows of padded frames are written as zeros. */
+int aph_attention_backward_bf16(const void* q, const void* k, const void* v, const void* ctx,
+                                const void* d_ctx, const float* lse2, float* delta_scratch,
+                                void* dqkv, const int32_t* lengths, int32_t n_utt, int32_t heads,
+                                int32_t T, void* stream);
 
 /* ---- waveform normalisation and frame bookkeeping ------------------------- */
 /* zero_mean_unit_var_norm, acoustic_model.py:762-767:
@@ -242,6 +281,71 @@ int aph_ctc_backward(const aph_ctc_head* heads_dev, const aph_ctc_head* heads_ho
                      int32_t n_heads, int32_t n_utt, int32_t T, int32_t max_label_len,
                      const int64_t* input_lengths, const float* alpha_ws, const float* nll,
                      const float* grad_scale, void* stream);
+
+/* ---- training-side kernels of the classifier heads ------------------------------------ */
+/* AllophoneMapping.map_allophones + _multiply_allophone_matrix (acoustic_model.py:75-87, 142-159):
+ * out[n][t][q] = max_p (mask[lang][p][q] ? finfo(float32).min : logits[n][t][p] * matrices[lang][p][q]).
+ * The allowed (p, q) pairs of every language are given as a CSR list over q
+ * (csr_offsets[lang*n_phonemes + q] .. [+1] indexes csr_phones). logits element (n,t,p) is at
+ * logits[n*stride_n + t*stride_t + p]; out/argmax are contiguous [n_utt][T][n_phonemes]. */
+int aph_allophone_forward(const float* logits, int64_t stride_n, int64_t stride_t, int32_t n_utt,
+                          int32_t T, int32_t n_phones, int32_t n_phonemes, const float* matrices,
+                          const int32_t* csr_offsets, const int32_t* csr_phones,
+                          const int64_t* language_ids, float* out, int32_t* argmax_out, void* stream);
+/* Its backward: grad_logits (contiguous [n_utt][T][n_phones], pre-zeroed) and grad_matrices
+ * (same shape as matrices, accumulated) receive the gradient of the winning phone. */
+int aph_allophone_backward(const float* grad_out, const int32_t* argmax_in, const float* logits,
+                           int64_t stride_n, int64_t stride_t, int32_t n_utt, int32_t T,
+                           int32_t n_phones, int32_t n_phonemes, const float* matrices,
+                           const int64_t* language_ids, float* grad_logits, float* grad_matrices,
+                           void* stream);
+/* [rows][cols] (fp32 or bf16) -> bf16 [cols][rows_padded] (zero padded): turns the frame axis into
+ * the contiguous K axis of the weight-gradient GEMMs dW = dY^T X (autograd of nn.Linear). */
+int aph_transpose_cast_bf16(const void* in, int32_t in_is_f32, int64_t ld_in, int64_t rows,
+                            int32_t cols, void* out_bf16, int64_t ld_out, int64_t rows_padded,
+                            void* stream);
+/* out[c] = sum_r in[r][c] (bias gradients). */
+int aph_colsum_f32(const float* in, int64_t ld, int64_t rows, int32_t cols, float* out, void* stream);
+int aph_colsum_bf16(const void* in_bf16, int64_t ld, int64_t rows, int32_t cols, float* out, void* stream);
+/* Backward of nn.LayerNorm over the last axis (cols in {512, 1024}); statistics are recomputed from x.
+ *   dx[r] = (dx_resid ? dx_resid[r] : 0) + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
+ *   dgamma[c] = sum_r dy * xhat, dbeta[c] = sum_r dy (either may be NULL).  x, dy: fp32 or bf16. dx may alias dx_resid. */
+int aph_layernorm_backward(const void* x, int32_t x_is_f32, int64_t ld_x, const void* dy,
+                           int32_t dy_is_f32, int64_t ld_dy, int64_t rows, int32_t cols,
+                           const float* gamma, float eps, const float* dx_resid, int64_t ld_resid,
+                           float* dx, int64_t ld_dx, float* dgamma, float* dbeta, void* stream);
+/* Backward of `hidden_states[~mask] = 0` (HF:753-756): zero the rows t >= lengths[row / len_period]. */
+int aph_mask_rows_f32(float* x, int64_t ld, int64_t rows, int32_t cols, const int32_t* lengths,
+                      int32_t len_period, void* stream);
+/* dst[r][c] += src[r][c] (gradient of a hidden state that is also a classifier input, OUTPUT_i). */
+int aph_add_f32_2d(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, int64_t rows,
+                   int32_t cols, void* stream);
+/* out = bf16(dy * gelu'(pre)): backward of the GELU after the positional conv (HF:353-368). */
+int aph_gelu_backward_bf16(const float* dy, int64_t ld_dy, const void* pre_bf16, int64_t ld_pre,
+                           int64_t rows, int32_t cols, void* out_bf16, int64_t ld_out, void* stream);
+/* Positional conv backward (weight_norm(dim=2) grouped Conv1d, HF:326-350).
+ * aph_pack_posconv_weight_dgrad: B operand of the data-gradient sliding-tap GEMM (tap_pad = k/2 - 1),
+ *   dst[g*Cg + ci][j*Cg + co] = w[g*Cg + co][ci][k-1-j]; tap_scratch: fp32 [2*k].
+ * aph_posconv_weight_backward: raw = output of the APH_GEMM_DIAG_TAPS GEMM, fp32 [k][O][256] -> gradients of
+ *   weight_g [1][1][k] and weight_v [O][Cg][k]; tap_scratch: fp32 [3*k]. */
+int aph_pack_posconv_weight_dgrad(const float* weight_g, const float* weight_v, void* dst_bf16,
+                                  float* tap_scratch, int32_t out_channels, int32_t group_channels,
+                                  int32_t kernel, void* stream);
+int aph_posconv_weight_backward(const float* raw, const float* weight_g, const float* weight_v,
+                                float* tap_scratch, int32_t out_channels, int32_t group_channels,
+                                int32_t kernel, float* grad_g, float* grad_v, void* stream);
+/* Backward of EmbeddingCompositionLayer's EmbeddingBag("sum") (acoustic_model.py:208, 225-232):
+ * grad_rows[0] -> category 0 (blank), grad_rows[1+v] -> every category tfi[v][f] + offsets[f]. */
+int aph_embedding_bag_backward(const float* grad_rows, int64_t ld, int32_t n_phonemes,
+                               int32_t n_features, int32_t embedding_size, const int64_t* tfi,
+                               const int64_t* category_offsets, float* grad_weight, void* stream);
+/* Backward of the dependency softmax (acoustic_model.py:497-514): for dependency d,
+ * grad_logits[:, dst_col[d]+skip : ...] += p * (dp - sum(p*dp)) with p the bf16 probabilities stored
+ * in x[:, x_col[d] : ...] and dp = grad_x[:, x_col[d] : ...]. */
+int aph_softmax_backward_cols(const float* grad_x, int64_t ld_gx, const void* x_bf16, int64_t ld_x,
+                              int64_t rows, const int32_t* x_col, const int32_t* width,
+                              const int32_t* dst_col, int32_t n_deps, int32_t skip,
+                              float* grad_logits, int64_t ld_gl, void* stream);
 
 /* ---- edit distance (host) --------------------------------------------------------- */
 /* Batched replacement of the Rust extension `allophant.phonemes` (src/edit_distance.rs):

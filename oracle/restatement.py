@@ -14,7 +14,7 @@ What is restated (plain torch, fp32, CPU) and from where:
   * ``Estimator.predict``                  allophant/estimator.py:1035-1046
   * ``CTCWrapper``                         allophant/loss_functions.py:19-27
   * ``GreedyCTCDecoder``                   allophant/predictions.py:189-207
-  * step loss arithmetic                   allophant/estimator.py:710-738
+  * step loss arithmetic + backward        allophant/estimator.py:708-738 (``OracleModel.training_step``)
 
 The encoder arithmetic itself lives in a third-party dependency of the reference,
 ``transformers`` (pinned 4.41.2 in the reference's pyproject.toml:23; 5.5.0 is what this image
@@ -279,6 +279,23 @@ class OracleModel:
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def encode(self, audio: Tensor, lengths: Tensor) -> Tuple[List[Tensor], Tensor]:
+        return self._encode(audio, lengths)
+
+    @torch.no_grad()
+    def compose(self, inputs: Tensor, target_feature_indices: Optional[Tensor]) -> Tensor:
+        return self._compose(inputs, target_feature_indices)
+
+    @torch.no_grad()
+    def project(
+        self,
+        hidden_states: List[Tensor],
+        language_ids: Optional[Tensor] = None,
+        target_feature_indices: Optional[Tensor] = None,
+        predict: bool = True,
+    ) -> Dict[str, Tensor]:
+        return self._project(hidden_states, language_ids, target_feature_indices, predict)
+
+    def _encode(self, audio: Tensor, lengths: Tensor) -> Tuple[List[Tensor], Tensor]:
         """Wav2Vec2AcousticModel.forward, acoustic_model.py:837-853 (do_normalize / return_attention_mask = True)."""
         mask = mask_sequence(lengths)
         hidden_states = self.encoder(
@@ -287,8 +304,7 @@ class OracleModel:
         frames = conv_lengths(lengths, self.config.conv_kernel, self.config.conv_stride)
         return [h.transpose(0, 1) for h in hidden_states], frames
 
-    @torch.no_grad()
-    def compose(self, inputs: Tensor, target_feature_indices: Optional[Tensor]) -> Tensor:
+    def _compose(self, inputs: Tensor, target_feature_indices: Optional[Tensor]) -> Tensor:
         """EmbeddingCompositionLayer.forward, acoustic_model.py:219-234."""
         assert self.composition is not None
         if target_feature_indices is None:
@@ -298,8 +314,7 @@ class OracleModel:
         composed = torch.cat((self.composition(torch.zeros(1, 1, dtype=indices.dtype)), self.composition(indices))).T
         return (inputs @ composed) / self.scale_factor
 
-    @torch.no_grad()
-    def project(
+    def _project(
         self,
         hidden_states: List[Tensor],
         language_ids: Optional[Tensor] = None,
@@ -324,17 +339,19 @@ class OracleModel:
                 )
             out = self.linears[node.name](inputs)
             if node.name == "phoneme" and self.composition is not None:
-                out = self.compose(out, target_feature_indices)
+                out = self._compose(out, target_feature_indices)
             if node.name == "phoneme" and self.allophone_matrices is not None:
                 if predict:
                     produced = {"phone": out, "phoneme": out}  # acoustic_model.py:164-166
                 else:
-                    mapped = torch.empty(*out.shape[:2], self.allophone_matrices.shape[2])
+                    columns = []
                     for index, language_id in enumerate(map(int, language_ids)):  # acoustic_model.py:142-159
-                        mapped[:, index] = multiply_allophone_matrix(
-                            out[:, index].unsqueeze(-1), self.allophone_matrices[language_id], self.allophone_mask[language_id]
+                        columns.append(
+                            multiply_allophone_matrix(
+                                out[:, index].unsqueeze(-1), self.allophone_matrices[language_id], self.allophone_mask[language_id]
+                            )
                         )
-                    produced = {"phoneme": mapped}
+                    produced = {"phoneme": torch.stack(columns, 1)}
                 results.update(produced)
                 outputs.update(produced)
             else:
@@ -357,6 +374,59 @@ class OracleModel:
         if log_probabilities:
             return {name: functional.log_softmax(value, -1) for name, value in logits.items()}, frames
         return logits, frames
+
+
+    # ------------------------------------------------------------------ training step
+    def trainable_parameters(self, freeze_feature_encoder: bool = True) -> Dict[str, Tensor]:
+        """Leaf tensors under their ``Allophant.state_dict()`` names; the convolutional feature extractor is frozen
+        like the reference's default (``default_config.toml:40``, ``acoustic_model.py:806-807``)."""
+        named: Dict[str, Tensor] = {}
+        for key, parameter in self.encoder.named_parameters():
+            frozen = freeze_feature_encoder and key.startswith("feature_extractor.")
+            parameter.requires_grad_(not frozen)
+            if not frozen:
+                named[f"_acoustic_model._model.{key}"] = parameter
+        for name, linear in self.linears.items():
+            named[f"_projection._layers.{name}._time_distributed_layer.weight"] = linear.weight
+            named[f"_projection._layers.{name}._time_distributed_layer.bias"] = linear.bias
+        if self.composition is not None:
+            named["_projection._layers.phoneme._composition_layer._attribute_embeddings.weight"] = self.composition.weight
+        if self.allophone_matrices is not None:
+            self.allophone_matrices.requires_grad_(True)
+            named["_projection._layers.phoneme._allophone_layer._allophone_matrices"] = self.allophone_matrices
+        return named
+
+    def training_step(
+        self,
+        audio: Tensor,
+        lengths: Tensor,
+        labels: Dict[str, Tensor],
+        label_lengths: Dict[str, Tensor],
+        language_ids: Optional[Tensor] = None,
+        target_feature_indices: Optional[Tensor] = None,
+    ) -> Tuple[Tensor, Dict[str, float], Dict[str, Tensor]]:
+        """``estimator.py:708-738`` in eval()-mode arithmetic: ``model(batch)`` (predict=False), per-head
+        ``CTCWrapper``, ``loss = sum_heads ctc / sum_heads sum_utt label_length``, ``backward()``.
+        Returns (loss, per-head CTC sums, gradients by state_dict name)."""
+        named = self.trainable_parameters()
+        for parameter in named.values():
+            parameter.grad = None
+        with torch.enable_grad():
+            hidden_states, frames = self._encode(audio, lengths)
+            outputs = self._project(hidden_states, language_ids, target_feature_indices, predict=False)
+            outputs.pop("phone", None)  # estimator.py:717-718
+            total = torch.tensor(0, dtype=torch.float32)
+            per_head: Dict[str, float] = {}
+            normaliser = 0
+            for name, output in outputs.items():
+                head_loss = ctc_wrapper(output, labels[name], frames, label_lengths[name])
+                per_head[name] = float(head_loss)
+                normaliser += int(label_lengths[name].sum())
+                total = total + head_loss
+            loss = total / normaliser
+            loss.backward()
+        gradients = {name: parameter.grad.detach().clone() for name, parameter in named.items() if parameter.grad is not None}
+        return loss.detach(), per_head, gradients
 
 
 def state_checksum(state: Dict[str, Tensor]) -> Dict[str, float]:
@@ -385,3 +455,34 @@ def synthetic_labels(frames: Tensor, n_classes: int, seed: int, fraction: float 
     for index, length in enumerate(lengths.tolist()):
         labels[index, :length] = torch.randint(1, n_classes, (length,), generator=generator)
     return labels, lengths
+
+
+def training_labels(
+    spec: OracleSpec, head_classes: Dict[str, int], frames: Tensor, language_ids: Optional[Tensor], seed: int = 100
+) -> Tuple[Dict[str, Tensor], Dict[str, Tensor]]:
+    """Per-head CTC labels for a training step: random sequences of length
+    ``floor(0.25 * frames)``.  With an allophone layer the phoneme labels of an utterance are drawn from its own
+    language's inventory: absent phonemes are fully masked (``acoustic_model.py:72, 81-84``), which makes the CTC
+    loss infinite and ``zero_infinity`` would silently zero the whole utterance."""
+    labels: Dict[str, Tensor] = {}
+    lengths: Dict[str, Tensor] = {}
+    for index, (name, classes) in enumerate(head_classes.items()):
+        head_labels, head_lengths = synthetic_labels(frames, classes, seed=seed + index)
+        if name == "phoneme" and spec.allophones is not None:
+            assert language_ids is not None
+            generator = torch.Generator().manual_seed(seed + 1000)
+            languages = list(spec.allophones)
+            for row, language in enumerate(language_ids.tolist()):
+                inventory = torch.tensor(sorted(spec.allophones[languages[language]]), dtype=torch.long) + BLANK_OFFSET
+                length = int(head_lengths[row])
+                picks = torch.randint(0, len(inventory), (length,), generator=generator)
+                head_labels[row, :length] = inventory[picks]
+        labels[name], lengths[name] = head_labels, head_lengths
+    return labels, lengths
+
+
+def gradient_summary(gradient: Tensor, samples: int = 32) -> Dict[str, object]:
+    """Compact fingerprint of one gradient tensor for the golden fixtures: norm, sum and evenly spaced samples."""
+    flat = gradient.detach().double().flatten()
+    index = torch.linspace(0, flat.numel() - 1, min(samples, flat.numel())).long()
+    return dict(norm=float(flat.norm()), sum=float(flat.sum()), index=index, values=flat[index].float(), shape=tuple(gradient.shape))
