@@ -104,6 +104,7 @@ _SIGNATURES = {
     "aph_attention_bf16": [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
     "aph_attention_bf16_lse": [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
     "aph_attention_backward_bf16": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P],
+    "aph_debug_set_progress": [_P],
     "aph_wave_stats": [_P, _P, _I32, _I32, _P, _P, _P],
     "aph_wave_norm": [_P, _P, _P, _I32, _I32, _P, _P],
     "aph_frame_lengths": [_P, _I32, _P, _P, _I32, _P, _P, _P],

@@ -17,6 +17,8 @@
 //                             (K tile re-read as an MN-major B operand).
 // Outputs go straight into the bf16 [rows][3*hidden] matrix (dQ | dK | dV) that the QKV
 // dgrad / wgrad GEMMs read.  Rows of padded frames are written as zeros.
+#include <stdlib.h>
+
 #include "aph_common.cuh"
 
 namespace aph {
@@ -34,6 +36,24 @@ struct AttBwdParams {
   int T;
   int heads;
 };
+
+// Debug progress markers (host-mapped memory set through aph_debug_set_progress; NULL in production)
+__device__ int* g_progress = nullptr;
+#define APH_MARK(slot, value)                                              \
+  do {                                                                     \
+    if (g_progress != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {     \
+      g_progress[slot] = (value);                                          \
+      __threadfence_system();                                              \
+    }                                                                      \
+  } while (0)
+
+#define APH_COUNT(slot)                                                    \
+  do {                                                                     \
+    if (g_progress != nullptr) {                                           \
+      atomicAdd_system(g_progress + (slot), 1);                            \
+      __threadfence_system();                                              \
+    }                                                                      \
+  } while (0)
 
 constexpr uint32_t kIdescS = umma_idesc_bf16(128, 128);                       // both K-major
 constexpr uint32_t kIdescAcc = umma_idesc_bf16(128, 64) | kIdescBMnMajor;     // B read MN-major ([k rows][64 d])
@@ -284,7 +304,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    if (k0 + r < p.T) {
+    {
+      // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only rows inside the utterance store
+      const bool row_in = k0 + r < p.T;
       __nv_bfloat16* row = p.dqkv + (static_cast<long long>(b) * p.T + k0 + r) * hidden3 + h * kBwdD;
       uint4* dk4 = reinterpret_cast<uint4*>(row + p.heads * kBwdD);
       uint4* dv4 = reinterpret_cast<uint4*>(row + 2 * p.heads * kBwdD);
@@ -295,23 +317,23 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
         tmem_ld32(tmem_dv + lane_off + static_cast<uint32_t>(c0), g);
         tmem_ld_wait();
         constexpr float kLn2 = 0.6931471805599453f;
+        if (row_in) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 o4;
-          o4.x = pack_bf16x2(a[8 * j + 0] * kLn2, a[8 * j + 1] * kLn2);
-          o4.y = pack_bf16x2(a[8 * j + 2] * kLn2, a[8 * j + 3] * kLn2);
-          o4.z = pack_bf16x2(a[8 * j + 4] * kLn2, a[8 * j + 5] * kLn2);
-          o4.w = pack_bf16x2(a[8 * j + 6] * kLn2, a[8 * j + 7] * kLn2);
-          dk4[(c0 >> 3) + j] = o4;
-          o4.x = pack_bf16x2(g[8 * j + 0], g[8 * j + 1]);
-          o4.y = pack_bf16x2(g[8 * j + 2], g[8 * j + 3]);
-          o4.z = pack_bf16x2(g[8 * j + 4], g[8 * j + 5]);
-          o4.w = pack_bf16x2(g[8 * j + 6], g[8 * j + 7]);
-          dv4[(c0 >> 3) + j] = o4;
+          for (int j = 0; j < 4; ++j) {
+            uint4 o4;
+            o4.x = pack_bf16x2(a[8 * j + 0] * kLn2, a[8 * j + 1] * kLn2);
+            o4.y = pack_bf16x2(a[8 * j + 2] * kLn2, a[8 * j + 3] * kLn2);
+            o4.z = pack_bf16x2(a[8 * j + 4] * kLn2, a[8 * j + 5] * kLn2);
+            o4.w = pack_bf16x2(a[8 * j + 6] * kLn2, a[8 * j + 7] * kLn2);
+            dk4[(c0 >> 3) + j] = o4;
+            o4.x = pack_bf16x2(g[8 * j + 0], g[8 * j + 1]);
+            o4.y = pack_bf16x2(g[8 * j + 2], g[8 * j + 3]);
+            o4.z = pack_bf16x2(g[8 * j + 4], g[8 * j + 5]);
+            o4.w = pack_bf16x2(g[8 * j + 6], g[8 * j + 7]);
+            dv4[(c0 >> 3) + j] = o4;
+          }
         }
       }
-    } else {
-      tmem_ld_wait();
     }
     tc_fence_before();
   }
@@ -387,10 +409,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
+  if (threadIdx.x == 0) APH_MARK(0, 1);
   if (warp == 5) tmem_alloc<kQTmemCols>(tmem_slot);
+  if (threadIdx.x == 160) APH_MARK(1, 1);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (threadIdx.x == 0) APH_MARK(2, 1);
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base;
   const uint32_t tmem_dp = tmem_base + 128;
@@ -401,9 +426,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
       mbar_arrive_expect_tx(q_full, 2 * kBwdTileBytes);
       tma_load_3d(s_q, &tm_q, q_full, 0, q0, bh);
       tma_load_3d(s_do, &tm_do, q_full, h * kBwdD, q0, b);
+      APH_MARK(3, 1);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
         mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        APH_MARK(3, 2 + j);
         mbar_arrive_expect_tx(&kv_full[st], 2 * kBwdTileBytes);
         tma_load_3d(s_k + st * kBwdTileBytes, &tm_k, &kv_full[st], 0, j * kBwdTile, bh);
         tma_load_3d(s_v + st * kBwdTileBytes, &tm_v, &kv_full[st], 0, j * kBwdTile, bh);
@@ -416,9 +443,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
       const uint64_t dds0 = umma_desc_sw128(smem_u32(s_ds));
       const uint64_t dds1 = umma_desc_sw128(smem_u32(s_ds + kBwdTileBytes));
       mbar_wait(q_full, 0);
+      APH_MARK(4, 1);
       auto issue_scores = [&](int j) {
         const int st = j & 1;
         mbar_wait(&kv_full[st], (j >> 1) & 1);
+        APH_MARK(4, 10 + j);
         tc_fence_after();
         const uint64_t dk = umma_desc_sw128(smem_u32(s_k + st * kBwdTileBytes));
         const uint64_t dv = umma_desc_sw128(smem_u32(s_v + st * kBwdTileBytes));
@@ -434,6 +463,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
         mbar_wait(ds_full, j & 1);
+        APH_MARK(5, 1 + j);
         tc_fence_after();
         const uint64_t bk = umma_desc_mn_sw128(smem_u32(s_k + st * kBwdTileBytes), kBwdTileBytes);
 #pragma unroll
@@ -459,6 +489,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
     const int sw = r & 7;
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
+      if (threadIdx.x == 0) APH_MARK(6, 1 + j);
       tc_fence_after();
       const int key0 = j * kBwdTile;
 #pragma unroll 1
@@ -479,22 +510,25 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
       mbar_arrive(ds_full);
     }
     mbar_wait(acc_full, 0);
+    if (threadIdx.x == 0) APH_MARK(7, 1);
     tc_fence_after();
-    if (row_in) {
+    {
       uint4* dq4 = reinterpret_cast<uint4*>(p.dqkv + (static_cast<long long>(b) * p.T + q0 + r) * hidden3 + h * kBwdD);
 #pragma unroll
       for (int c0 = 0; c0 < kBwdD; c0 += 32) {
         float a[32];
-        tmem_ld32(tmem_dq + lane_off + static_cast<uint32_t>(c0), a);
+        tmem_ld32(tmem_dq + lane_off + static_cast<uint32_t>(c0), a);  // warp-collective: outside the row guard
         tmem_ld_wait();
+        if (row_in) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 o4;
-          o4.x = pack_bf16x2(a[8 * j + 0] * q_grad_scale, a[8 * j + 1] * q_grad_scale);
-          o4.y = pack_bf16x2(a[8 * j + 2] * q_grad_scale, a[8 * j + 3] * q_grad_scale);
-          o4.z = pack_bf16x2(a[8 * j + 4] * q_grad_scale, a[8 * j + 5] * q_grad_scale);
-          o4.w = pack_bf16x2(a[8 * j + 6] * q_grad_scale, a[8 * j + 7] * q_grad_scale);
-          dq4[(c0 >> 3) + j] = o4;
+          for (int j = 0; j < 4; ++j) {
+            uint4 o4;
+            o4.x = pack_bf16x2(a[8 * j + 0] * q_grad_scale, a[8 * j + 1] * q_grad_scale);
+            o4.y = pack_bf16x2(a[8 * j + 2] * q_grad_scale, a[8 * j + 3] * q_grad_scale);
+            o4.z = pack_bf16x2(a[8 * j + 4] * q_grad_scale, a[8 * j + 5] * q_grad_scale);
+            o4.w = pack_bf16x2(a[8 * j + 6] * q_grad_scale, a[8 * j + 7] * q_grad_scale);
+            dq4[(c0 >> 3) + j] = o4;
+          }
         }
       }
     }
@@ -511,6 +545,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 }
 
 }  // namespace aph
+
+extern "C" int aph_debug_set_progress(int32_t* host_mapped) {
+  APH_CUDA_CHECK(cudaMemcpyToSymbol(aph::g_progress, &host_mapped, sizeof(host_mapped)));
+  return APH_OK;
+}
 
 extern "C" int aph_attention_backward_bf16(const void* q, const void* k, const void* v, const void* ctx, const void* d_ctx,
                                            const float* lse2, float* delta_scratch, void* dqkv,
@@ -550,6 +589,12 @@ extern "C" int aph_attention_backward_bf16(const void* q, const void* k, const v
     attr_set = true;
   }
   const long long rows = static_cast<long long>(n_utt) * T;
+  // APH_ATT_BWD_MASK (debug): bit 0 = delta, bit 1 = dK/dV kernel, bit 2 = dQ kernel
+  static const int mask = [] {
+    const char* e = getenv("APH_ATT_BWD_MASK");
+    return e ? atoi(e) : 7;
+  }();
+  if (mask & 1)
   attention_delta_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(ctx), static_cast<const __nv_bfloat16*>(d_ctx), rows, T, heads, delta_scratch);
   AttBwdParams p;
@@ -560,8 +605,8 @@ extern "C" int aph_attention_backward_bf16(const void* q, const void* k, const v
   p.T = T;
   p.heads = heads;
   dim3 grid(ceil_div(T, kBwdTile), static_cast<unsigned>(nh));
-  attention_bwd_kv_kernel<<<grid, kBwdThreads, kKvSmemBytes, stream>>>(tm_q, tm_k, tm_v, tm_do, p);
-  attention_bwd_q_kernel<<<grid, kBwdThreads, kQSmemBytes, stream>>>(tm_q, tm_k, tm_v, tm_do, p, 0.125f);
+  if (mask & 2) attention_bwd_kv_kernel<<<grid, kBwdThreads, kKvSmemBytes, stream>>>(tm_q, tm_k, tm_v, tm_do, p);
+  if (mask & 4) attention_bwd_q_kernel<<<grid, kBwdThreads, kQSmemBytes, stream>>>(tm_q, tm_k, tm_v, tm_do, p, 0.125f);
   APH_POST_LAUNCH(3);
   return APH_OK;
 }

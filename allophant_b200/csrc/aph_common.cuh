@@ -108,14 +108,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (→ launch error reported to the host)
-// instead of hanging the device.  try_wait suspends in hardware, so the bound
-// (~2^24 polls) is seconds, far above any legitimate wait.
+// Bounded wait: a protocol bug traps (→ launch error reported to the host) instead of hanging the
+// device.  The bound is wall-clock (~2 s of SM cycles), far above any legitimate wait.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const long long start = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {
-      printf("aph: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n", blockIdx.x,
+    if (clock64() - start > 4000000000LL) {
+      printf("aph: mbarrier wait timed out (block %d,%d thread %d bar %p parity %u)\n", blockIdx.x, blockIdx.y,
              threadIdx.x, (void*)bar, parity);
       __trap();
     }

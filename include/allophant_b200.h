@@ -148,6 +148,10 @@ int aph_attention_backward_bf16(const void* q, const void* k, const void* v, con
                                 void* dqkv, const int32_t* lengths, int32_t n_utt, int32_t heads,
                                 int32_t T, void* stream);
 
+/* Debug aid: progress markers of block (0,0) of the attention backward kernels are written to this
+ * host-mapped int32[16] array (NULL = off, the default). */
+int aph_debug_set_progress(int32_t* host_mapped);
+
 /* ---- waveform normalisation and frame bookkeeping ------------------------- */
 /* zero_mean_unit_var_norm, acoustic_model.py:762-767:
  *   mean = sum_all(x) / len; var = sum_valid((x-mean)^2) / len;

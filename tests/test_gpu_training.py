@@ -203,10 +203,13 @@ def test_attention_backward(seq, lengths):
     out.backward(d_ctx.float().cpu())
     ours = dqkv.float().cpu().view(n_utt, seq, 3, heads, d).permute(2, 0, 3, 1, 4)  # [3, N, heads, T, d]
     assert torch.isfinite(ours).all()
-    for b, length in enumerate(lengths):
-        for part, reference in enumerate((qr.grad, kr.grad, vr.grad)):
-            assert range_err(ours[part, b, :, :length], reference[b, :, :length]) < 2e-2, (b, part)
-            assert float(ours[part, b, :, length:].abs().max()) == 0.0 if length < seq else True, (b, part)
+    for part, reference in enumerate((qr.grad, kr.grad, vr.grad)):
+        scale = float(reference.abs().max())  # one scale per tensor: a single-frame utterance has an exactly zero dQ/dK
+        for b, length in enumerate(lengths):
+            error = float((ours[part, b, :, :length] - reference[b, :, :length]).abs().max()) / scale
+            assert error < 2e-2, (b, part, error)
+            if length < seq:
+                assert float(ours[part, b, :, length:].abs().max()) == 0.0, (b, part)
 
 
 # ------------------------------------------------------------------------------------------ positional conv
@@ -315,8 +318,8 @@ def test_training_step_matches_reference(training_case):
         assert parameter.grad.shape == reference[name].shape
         assert torch.isfinite(parameter.grad).all(), name
         scale = float(reference[name].norm())
-        if scale < 1e-10:  # e.g. k_proj.bias: the softmax is invariant to it
-            assert float(parameter.grad.norm()) < 1e-4
+        if scale < 1e-7:  # k_proj.bias: the softmax is invariant to it, the exact gradient is 0 (reference: ~1e-9 of round-off)
+            assert float(parameter.grad.norm()) < 1e-3
             continue
         worst[name] = norm_err(parameter.grad, reference[name])
         # the golden fingerprint comes from the UNMODIFIED reference
@@ -355,7 +358,7 @@ def test_frozen_encoder_trains_heads_only(training_case):
         for name, parameter in model.named_parameters():
             if name.startswith("_acoustic_model"):
                 assert parameter.grad is None
-            elif name in reference and float(reference[name].norm()) > 1e-10:
+            elif name in reference and float(reference[name].norm()) > 1e-7:
                 assert norm_err(parameter.grad, reference[name]) < GRAD_TOL, name
     finally:
         frozen = set(fixture["frozen"])
