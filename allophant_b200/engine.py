@@ -410,7 +410,13 @@ class EncoderPlan:
 
     # ------------------------------------------------------------------ backward (training plans only)
     @torch.no_grad()
-    def backward(self, d_x: Tensor, need_encoder: bool, need_projection: bool) -> Dict[str, Tensor]:
+    def backward(
+        self,
+        d_x: Tensor,
+        need_encoder: bool,
+        need_projection: bool,
+        on_group_ready: Optional[Callable[[Tensor, Dict[str, Tensor]], None]] = None,
+    ) -> Dict[str, Tensor]:
         """Backward pass of everything ``run`` enqueued, from the gradient of the classifier feature matrix.
 
         ``d_x`` fp32 ``[M, ldx]`` is dL/dX (X = ``[final LayerNorm | kept hidden states | ...]``).  Returns
@@ -422,7 +428,11 @@ class EncoderPlan:
         Every Linear contributes two tcgen05 GEMMs that read the forward pass's own buffers:
         ``dX = dY W`` (W as an MN-major B operand) and ``dW = dY^T X`` (both operands MN-major, split-K
         with TMA reduce-add stores); GELU' is fused into the FFN2 data-gradient epilogue and residual
-        accumulation into the LayerNorm backward kernel."""
+        accumulation into the LayerNorm backward kernel.
+
+        The gradients of one layer live in ONE flat buffer (the returned tensors are views of it);
+        ``on_group_ready(flat, views)`` is called as soon as the kernels producing a group are enqueued, so a
+        data-parallel caller can start that group's all-reduce while earlier layers are still computing."""
         if not self.training:
             raise RuntimeError("this EncoderPlan was built for inference: no activations were kept")
         p, cfg = self.packed, self.cfg
@@ -431,25 +441,50 @@ class EncoderPlan:
         heads, eps, seq = cfg.num_attention_heads, cfg.layer_norm_eps, self.seq
         dev = d_x.device
         grads: Dict[str, Tensor] = {}
-        new = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)  # noqa: E731
         n_layers = len(p.layers)
         dh, dh16 = self.dh, self.dh_bf16
 
-        def wgrad(dy: Tensor, ld_dy: int, m: int, x: Tensor, ld_x: int, n: int) -> Tensor:
-            out = new(m, n)
+        def group(shapes: Sequence[Tuple[str, Tuple[int, ...]]]) -> Tuple[Tensor, Dict[str, Tensor]]:
+            total = sum(int(torch.Size(shape).numel()) for _, shape in shapes)
+            flat = torch.empty(total, device=dev, dtype=torch.float32)
+            views, offset = {}, 0
+            for name, shape in shapes:
+                count = int(torch.Size(shape).numel())
+                views[name] = flat[offset : offset + count].view(shape)
+                offset += count
+            return flat, views
+
+        def done(flat: Tensor, views: Dict[str, Tensor], prefix: str) -> None:
+            named = {prefix + name: value for name, value in views.items()}
+            grads.update(named)
+            if on_group_ready is not None:
+                on_group_ready(flat, named)
+
+        def wgrad(out: Tensor, dy: Tensor, ld_dy: int, m: int, x: Tensor, ld_x: int, n: int) -> None:
             ops.run_gemm(ops.make_wgrad_args(dy, x, out, rows=M, m=m, ld_dy=ld_dy, n=n, ld_x=ld_x, ld_out=n))
-            return out
 
         # final LayerNorm (HF:792): X[:, :H] = LN(hs[L])
         gf, _ = p.final_ln
-        dg, db = (new(H), new(H)) if need_encoder else (None, None)
-        ops.layernorm_backward(self.hs[n_layers], H, d_x, self.ldx, M, H, gf, eps, None, 0, dh, H, dg, db)
+        flat, g = group([("weight", (H,)), ("bias", (H,))]) if need_encoder else (None, {})
+        ops.layernorm_backward(self.hs[n_layers], H, d_x, self.ldx, M, H, gf, eps, None, 0, dh, H, g.get("weight"), g.get("bias"))
         if need_encoder:
-            grads["encoder.layer_norm.weight"], grads["encoder.layer_norm.bias"] = dg, db
+            done(flat, g, "encoder.layer_norm.")
 
         for index in reversed(range(n_layers)):
             lw, sv = p.layers[index], self.saved[index]
-            prefix = f"encoder.layers.{index}."
+            if need_encoder:
+                flat, g = group(
+                    [
+                        ("feed_forward.output_dense.weight", (H, FF)), ("feed_forward.output_dense.bias", (H,)),
+                        ("feed_forward.intermediate_dense.weight", (FF, H)), ("feed_forward.intermediate_dense.bias", (FF,)),
+                        ("final_layer_norm.weight", (H,)), ("final_layer_norm.bias", (H,)),
+                        ("attention.out_proj.weight", (H, H)), ("attention.out_proj.bias", (H,)),
+                        ("attention.qkv.weight", (3 * H, H)), ("attention.qkv.bias", (3 * H,)),
+                        ("layer_norm.weight", (H,)), ("layer_norm.bias", (H,)),
+                    ]
+                )  # fmt: skip
+            else:
+                flat, g = None, {}
             column = self.hidden_blocks.get(index + 1)
             if column is not None and index + 1 < n_layers:  # hidden state index+1 is also a classifier input (OUTPUT_i)
                 ops.add_2d(dh, H, d_x[:, column:], self.ldx, M, H)
@@ -458,35 +493,34 @@ class EncoderPlan:
             ops.run_gemm(ops.make_dgrad_args(dh16, lw["w2"], rows=M, ld_dy=H, k=H, n=FF, ld_w=FF, gelu_bwd=sv["pre"], ld_gelu_bwd=FF,
                                              out_bf16=self.d_ff, ld_bf16=FF))  # fmt: skip
             if need_encoder:
-                grads[prefix + "feed_forward.output_dense.weight"] = wgrad(dh16, H, H, sv["act"], FF, FF)
-                grads[prefix + "feed_forward.output_dense.bias"] = ops.colsum_f32(dh, M, H, H)
-                grads[prefix + "feed_forward.intermediate_dense.weight"] = wgrad(self.d_ff, FF, FF, sv["ln2"], H, H)
-                grads[prefix + "feed_forward.intermediate_dense.bias"] = ops.colsum_bf16(self.d_ff, M, FF, FF)
+                wgrad(g["feed_forward.output_dense.weight"], dh16, H, H, sv["act"], FF, FF)
+                ops.colsum_f32(dh, M, H, H, out=g["feed_forward.output_dense.bias"])
+                wgrad(g["feed_forward.intermediate_dense.weight"], self.d_ff, FF, FF, sv["ln2"], H, H)
+                ops.colsum_bf16(self.d_ff, M, FF, FF, out=g["feed_forward.intermediate_dense.bias"])
             ops.run_gemm(ops.make_dgrad_args(self.d_ff, lw["w1"], rows=M, ld_dy=FF, k=FF, n=H, ld_w=H, out_f32=self.d_ln, ld_f32=H))
             g2, _ = lw["ln2"]
-            dg, db = (new(H), new(H)) if need_encoder else (None, None)
-            ops.layernorm_backward(self.mids[index], H, self.d_ln, H, M, H, g2, eps, dh, H, dh, H, dg, db)
-            if need_encoder:
-                grads[prefix + "final_layer_norm.weight"], grads[prefix + "final_layer_norm.bias"] = dg, db
+            ops.layernorm_backward(self.mids[index], H, self.d_ln, H, M, H, g2, eps, dh, H, dh, H,
+                                   g.get("final_layer_norm.weight"), g.get("final_layer_norm.bias"))  # fmt: skip
             # ---- attention block: h_mid = h_in + Wo attention(Wqkv LN1(h_in)) + bo
             ops.cast_bf16_2d(dh, H, dh16, H, M, H)
             ops.run_gemm(ops.make_dgrad_args(dh16, lw["wo"], rows=M, ld_dy=H, k=H, n=H, ld_w=H, out_bf16=self.d_ctx, ld_bf16=H))
             if need_encoder:
-                grads[prefix + "attention.out_proj.weight"] = wgrad(dh16, H, H, sv["ctx"], H, H)
-                grads[prefix + "attention.out_proj.bias"] = ops.colsum_f32(dh, M, H, H)
+                wgrad(g["attention.out_proj.weight"], dh16, H, H, sv["ctx"], H, H)
+                ops.colsum_f32(dh, M, H, H, out=g["attention.out_proj.bias"])
             ops.attention_backward(sv["q"], sv["k"], sv["v"], sv["ctx"], self.d_ctx, sv["lse"], self.delta, self.dqkv, self.att_lengths, N, heads, seq)
             if need_encoder:
-                grad_wqkv = wgrad(self.dqkv, 3 * H, 3 * H, sv["ln1"], H, H)
-                grad_bqkv = ops.colsum_bf16(self.dqkv, M, 3 * H, 3 * H)
-                for part, name in enumerate(("q_proj", "k_proj", "v_proj")):
-                    grads[prefix + f"attention.{name}.weight"] = grad_wqkv[part * H : (part + 1) * H]
-                    grads[prefix + f"attention.{name}.bias"] = grad_bqkv[part * H : (part + 1) * H]
+                wgrad(g["attention.qkv.weight"], self.dqkv, 3 * H, 3 * H, sv["ln1"], H, H)
+                ops.colsum_bf16(self.dqkv, M, 3 * H, 3 * H, out=g["attention.qkv.bias"])
             ops.run_gemm(ops.make_dgrad_args(self.dqkv, lw["wqkv"], rows=M, ld_dy=3 * H, k=3 * H, n=H, ld_w=H, out_f32=self.d_ln, ld_f32=H))
             g1, _ = lw["ln1"]
-            dg, db = (new(H), new(H)) if need_encoder else (None, None)
-            ops.layernorm_backward(self.hs[index], H, self.d_ln, H, M, H, g1, eps, dh, H, dh, H, dg, db)
+            ops.layernorm_backward(self.hs[index], H, self.d_ln, H, M, H, g1, eps, dh, H, dh, H, g.get("layer_norm.weight"), g.get("layer_norm.bias"))
             if need_encoder:
-                grads[prefix + "layer_norm.weight"], grads[prefix + "layer_norm.bias"] = dg, db
+                # the fused QKV gradient is handed out as its three nn.Linear slices (views of the same buffer)
+                wqkv, bqkv = g.pop("attention.qkv.weight"), g.pop("attention.qkv.bias")
+                for part, name in enumerate(("q_proj", "k_proj", "v_proj")):
+                    g[f"attention.{name}.weight"] = wqkv[part * H : (part + 1) * H]
+                    g[f"attention.{name}.bias"] = bqkv[part * H : (part + 1) * H]
+                done(flat, g, f"encoder.layers.{index}.")
 
         column = self.hidden_blocks.get(0)
         if column is not None and n_layers > 0:
@@ -494,18 +528,21 @@ class EncoderPlan:
         # ---- positional conv embedding (HF:764-765, 353-368): hs[0] = h_fp + gelu(conv(h_fp) + b)
         taps = cfg.num_conv_pos_embeddings
         pc = w.encoder.pos_conv_embed.conv
+        weight_g, weight_v = pc.parametrizations.weight.original0, pc.parametrizations.weight.original1
         ops.gelu_backward_bf16(dh, H, self.pos_pre, H, M, H, dh16, H)  # dh16 = d(conv output)
         if need_encoder:
-            grads["encoder.pos_conv_embed.conv.bias"] = ops.colsum_bf16(dh16, M, H, H)
-            raw = new(taps, H, 256)
+            flat, g = group(
+                [("bias", (H,)), ("parametrizations.weight.original0", tuple(weight_g.shape)), ("parametrizations.weight.original1", tuple(weight_v.shape))]
+            )
+            ops.colsum_bf16(dh16, M, H, H, out=g["bias"])
+            raw = torch.empty(taps, H, 256, device=dev, dtype=torch.float32)
             args = ops.make_wgrad_args(dh16, self.hidden_bf16, raw, rows=seq, m=H, ld_dy=H, n=H, ld_x=H, ld_out=256)
             args.mode, args.n_taps, args.tap_pad = _lib.APH_GEMM_DIAG_TAPS, taps, taps // 2
             args.k_batch, args.a_batch_stride, args.b_seg_stride = N, seq * H, seq * H
             args.out_batch_rows = H
             ops.run_gemm(args)
-            grad_g, grad_v = ops.posconv_weight_backward(raw, pc.parametrizations.weight.original0, pc.parametrizations.weight.original1)
-            grads["encoder.pos_conv_embed.conv.parametrizations.weight.original0"] = grad_g
-            grads["encoder.pos_conv_embed.conv.parametrizations.weight.original1"] = grad_v
+            ops.posconv_weight_backward(raw, weight_g, weight_v, g["parametrizations.weight.original0"], g["parametrizations.weight.original1"])
+            done(flat, g, "encoder.pos_conv_embed.conv.")
         if need_projection:
             # data gradient of the grouped conv: the same sliding-tap GEMM with flipped taps, accumulated onto dh
             ops.run_gemm(
@@ -518,11 +555,11 @@ class EncoderPlan:
             if self.use_lengths:
                 ops.mask_rows(dh, H, M, H, self.frames32, seq)
             ops.cast_bf16_2d(dh, H, dh16, H, M, H)
-            grads["feature_projection.projection.weight"] = wgrad(dh16, H, H, self.fp_in, 512, 512)
-            grads["feature_projection.projection.bias"] = ops.colsum_f32(dh, M, H, H)
+            flat, g = group([("projection.weight", (H, 512)), ("projection.bias", (H,)), ("layer_norm.weight", (512,)), ("layer_norm.bias", (512,))])
+            wgrad(g["projection.weight"], dh16, H, H, self.fp_in, 512, 512)
+            ops.colsum_f32(dh, M, H, H, out=g["projection.bias"])
             ops.run_gemm(ops.make_dgrad_args(dh16, p.fp_w, rows=M, ld_dy=H, k=H, n=512, ld_w=512, out_f32=self.d_fp_in, ld_f32=512))
             gp, _ = p.fp_ln
-            dg, db = new(512), new(512)
-            ops.layernorm_backward(self.conv_out, 512, self.d_fp_in, 512, M, 512, gp, eps, None, 0, self.d_fp_in, 512, dg, db)
-            grads["feature_projection.layer_norm.weight"], grads["feature_projection.layer_norm.bias"] = dg, db
+            ops.layernorm_backward(self.conv_out, 512, self.d_fp_in, 512, M, 512, gp, eps, None, 0, self.d_fp_in, 512, g["layer_norm.weight"], g["layer_norm.bias"])
+            done(flat, g, "feature_projection.")
         return grads

@@ -74,6 +74,7 @@ class HeadsRuntime:
         self._weights_version: Optional[Tuple[int, ...]] = None
         self._composed_cache: Dict[Tuple[Any, ...], Tuple[Tensor, int]] = {}
         self._index_cache: Dict[Tuple[Any, ...], Dict[str, Tensor]] = {}
+        self.gradient_reducer: Any = None  # allophant_b200.distributed.GradientReducer (data-parallel training)
 
     # ------------------------------------------------------------------ static layout
     def _build_layout(self) -> None:
@@ -566,11 +567,18 @@ class HeadsRuntime:
                 ops.run_gemm(ops.make_dgrad_args(grad_level_bf16, self.level_w[level_index], rows=rows, ld_dy=n_pad, k=n_pad, n=self.ldx, ld_w=self.ldx,
                                                  resid=resid, ld_resid=self.ldx, out_f32=d_x, ld_f32=self.ldx))  # fmt: skip
 
+        reducer = self.gradient_reducer
+        if reducer is not None:
+            param_grads = reducer.submit_tensors(param_grads)  # the heads' gradients travel while the encoder backward runs
         if through_encoder:
             assert d_x is not None
-            encoder_grads = plan.backward(d_x, state["need_encoder"], state["need_feature_projection"])
+            encoder_grads = plan.backward(
+                d_x, state["need_encoder"], state["need_feature_projection"], None if reducer is None else reducer.submit
+            )
             for name, value in encoder_grads.items():
                 param_grads[f"_acoustic_model._model.{name}"] = value
+        if reducer is not None:
+            reducer.finish()
         return [param_grads.get(name) for name in state["names"]]
 
     # ------------------------------------------------------------------ allophone layer

@@ -565,16 +565,18 @@ def transpose_cast_bf16(x: Tensor, rows: int, cols: int, ld_in: int, rows_padded
     return out
 
 
-def colsum_f32(x: Tensor, rows: int, cols: int, ld: int) -> Tensor:
-    _require_cuda(x)
-    out = torch.empty(cols, device=x.device, dtype=torch.float32)
+def colsum_f32(x: Tensor, rows: int, cols: int, ld: int, out: Optional[Tensor] = None) -> Tensor:
+    _require_cuda(x, out)
+    if out is None:
+        out = torch.empty(cols, device=x.device, dtype=torch.float32)
     check(lib.aph_colsum_f32(x.data_ptr(), ld, rows, cols, out.data_ptr(), _stream()), "aph_colsum_f32")
     return out
 
 
-def colsum_bf16(x: Tensor, rows: int, cols: int, ld: int) -> Tensor:
-    _require_cuda(x)
-    out = torch.empty(cols, device=x.device, dtype=torch.float32)
+def colsum_bf16(x: Tensor, rows: int, cols: int, ld: int, out: Optional[Tensor] = None) -> Tensor:
+    _require_cuda(x, out)
+    if out is None:
+        out = torch.empty(cols, device=x.device, dtype=torch.float32)
     check(lib.aph_colsum_bf16(x.data_ptr(), ld, rows, cols, out.data_ptr(), _stream()), "aph_colsum_bf16")
     return out
 
@@ -620,14 +622,18 @@ def pack_posconv_weight_dgrad(weight_g: Tensor, weight_v: Tensor) -> Tensor:
     return dst
 
 
-def posconv_weight_backward(raw: Tensor, weight_g: Tensor, weight_v: Tensor) -> Tuple[Tensor, Tensor]:
+def posconv_weight_backward(
+    raw: Tensor, weight_g: Tensor, weight_v: Tensor, grad_g: Optional[Tensor] = None, grad_v: Optional[Tensor] = None
+) -> Tuple[Tensor, Tensor]:
     """``raw`` fp32 [k, O, 256] from the DIAG_TAPS GEMM -> (grad of original0 [1,1,k], grad of original1 [O,Cg,k])."""
-    _require_cuda(raw, weight_g, weight_v)
+    _require_cuda(raw, weight_g, weight_v, grad_g, grad_v)
     g = weight_g.detach().float().contiguous()
     v = weight_v.detach().float().contiguous()
     o, cg, k = v.shape
-    grad_g = torch.empty(g.shape, device=v.device, dtype=torch.float32)
-    grad_v = torch.empty(v.shape, device=v.device, dtype=torch.float32)
+    if grad_g is None:
+        grad_g = torch.empty(g.shape, device=v.device, dtype=torch.float32)
+    if grad_v is None:
+        grad_v = torch.empty(v.shape, device=v.device, dtype=torch.float32)
     scratch = torch.empty(3 * k, device=v.device, dtype=torch.float32)
     check(lib.aph_posconv_weight_backward(raw.data_ptr(), g.data_ptr(), v.data_ptr(), scratch.data_ptr(), o, cg, k, grad_g.data_ptr(), grad_v.data_ptr(), _stream()), "aph_posconv_weight_backward")
     return grad_g, grad_v

@@ -379,6 +379,249 @@ def run_gpu_arm(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------------------------------
+# --workload train: BASELINE configs[2] — forward + multi-head CTC + backward (+ NCCL gradient all-reduce)
+# --------------------------------------------------------------------------------------------------
+TRAIN_BATCH = 8          # utterances per GPU (64 over 8 GPUs)
+TRAIN_LANGUAGES = 34
+TRAIN_PHONES = 500       # shared phones P and phoneme classes Q of the synthetic allophone layer
+
+
+def build_training_estimator(device: str):
+    """Default architecture (Multitask + allophone layer + composed phone embeddings) over a synthetic inventory."""
+    import numpy as np
+
+    from allophant_b200.config import Config
+    from allophant_b200.estimator import Estimator, attribute_graph_from_config
+    from allophant_b200.phonetic_features import AllophoneData, ArticulatoryAttributes, LanguageAllophoneMappings, PhoneticAttributeIndexer
+
+    torch.manual_seed(2)
+    config = Config.default()
+    names = [entry.name for entry in config.nn.projection.classes]
+    features = [name for name in names if name != "phoneme"]
+    rng = np.random.default_rng(1)
+    table = rng.integers(0, 3, size=(TRAIN_PHONES, len(features)))
+    table[:3, :] = np.arange(3)[:, None]
+    phones = [f"ph{index}" for index in range(TRAIN_PHONES)]
+    shared = ArticulatoryAttributes(phones, features, table, {f: ["0", "1", "2"] for f in features})
+    allophones = {}
+    for language in range(TRAIN_LANGUAGES):  # identity plus up to two more allophones per phoneme, 40-phoneme inventories
+        inventory = sorted(rng.choice(TRAIN_PHONES, size=40, replace=False).tolist())
+        allophones[language] = {
+            int(phoneme): sorted({int(phoneme), *[int(p) for p in rng.choice(TRAIN_PHONES, size=2, replace=False)]}) for phoneme in inventory
+        }
+    mappings = LanguageAllophoneMappings(allophones, [f"l{index}" for index in range(TRAIN_LANGUAGES)], phones)
+    indexer = PhoneticAttributeIndexer(
+        shared, [f"p{index}" for index in range(TRAIN_PHONES)], features, features + ["phoneme"], mappings, AllophoneData(shared)
+    )
+    graph = attribute_graph_from_config(config, indexer)
+    estimator = Estimator.from_config(config, 1, SAMPLE_RATE, graph, indexer, device=device, load_pretrained_weights=False)
+    return estimator, allophones
+
+
+def run_train_arm(args) -> None:
+    from allophant_b200 import ops
+    from allophant_b200.dataset_processing import Batch
+    from allophant_b200.distributed import GradientReducer, attach_gradient_reducer, global_label_count
+    from allophant_b200.loss_functions import multi_head_ctc_loss
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: allophant_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    device = f"cuda:{local_rank}"
+    distributed = world > 1
+    if distributed:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device(device))
+
+    estimator, allophones = build_training_estimator(device)
+    model = estimator.model
+    model.train()
+    reducer = GradientReducer() if distributed else None
+    attach_gradient_reducer(model, reducer)
+
+    # variable-length batch: U[3 s, 15 s] (BASELINE.md config 3), sorted, zero padded to the rank's longest utterance
+    generator = torch.Generator().manual_seed(3 + rank)
+    seconds = 3.0 + 12.0 * torch.rand(TRAIN_BATCH, generator=generator)
+    lengths = (seconds * SAMPLE_RATE).long().sort(descending=True).values
+    samples = int(lengths.max())
+    audio = 0.1 * torch.randn(TRAIN_BATCH, samples, generator=generator)
+    audio = audio * (torch.arange(samples)[None, :] < lengths[:, None])
+    languages = torch.randint(0, TRAIN_LANGUAGES, (TRAIN_BATCH,), generator=generator)
+    host_audio, host_lengths, host_languages = audio.pin_memory(), lengths.pin_memory(), languages.pin_memory()
+
+    frames = model.downsampled_lengths(lengths)
+    head_classes = {name: 4 for name in model.classes if name != "phoneme"}
+    head_classes["phoneme"] = TRAIN_PHONES + 1
+    names = [name for name in model.classes]
+    labels_host, label_lengths_host = {}, {}
+    for name in names:
+        head_lengths = (frames.double() * 0.25).floor().long()
+        head_labels = torch.zeros(TRAIN_BATCH, int(head_lengths.max()), dtype=torch.long)
+        for row, length in enumerate(head_lengths.tolist()):
+            if name == "phoneme":  # labels from the utterance's own language inventory (absent phonemes are fully masked)
+                inventory = torch.tensor(sorted(allophones[int(languages[row])]), dtype=torch.long) + 1
+                head_labels[row, :length] = inventory[torch.randint(0, len(inventory), (length,), generator=generator)]
+            else:
+                head_labels[row, :length] = torch.randint(1, head_classes[name], (length,), generator=generator)
+        labels_host[name], label_lengths_host[name] = head_labels.pin_memory(), head_lengths.pin_memory()
+    resident = Batch(host_audio.to(device), host_lengths.to(device), host_languages.to(device))
+    labels_dev = {name: value.to(device) for name, value in labels_host.items()}
+    label_lengths_dev = {name: value.to(device) for name, value in label_lengths_host.items()}
+    parameters = [parameter for parameter in model.parameters() if parameter.requires_grad]
+
+    def step(batch, labels, label_lengths):
+        for parameter in parameters:
+            parameter.grad = None
+        predictions = model(batch)
+        predictions.outputs.pop("phone", None)
+        order = list(predictions.outputs)
+        losses = multi_head_ctc_loss(
+            [predictions.outputs[name] for name in order], [labels[name] for name in order], predictions.lengths, [label_lengths[name] for name in order]
+        )
+        count = global_label_count([label_lengths[name] for name in order])  # all-reduced scalar: the loss normaliser of the WHOLE batch
+        loss = losses.sum() / count.to(losses.dtype)
+        loss.backward()
+        return loss
+
+    def device_step():
+        return step(resident, labels_dev, label_lengths_dev)
+
+    def e2e_step():
+        batch = Batch(host_audio, host_lengths, host_languages).to(device, non_blocking=True)
+        labels = {name: value.to(device, non_blocking=True) for name, value in labels_host.items()}
+        label_lengths = {name: value.to(device, non_blocking=True) for name, value in label_lengths_host.items()}
+        return float(step(batch, labels, label_lengths).item())
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        loss = device_step()
+    if not torch.isfinite(loss):
+        raise RuntimeError(f"training loss is not finite: {float(loss)}")
+    ops.reset_launch_count()
+    collectives_before = (reducer.issued, reducer.bytes) if reducer is not None else (0, 0)
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as sampler:
+        barrier()
+        start.record()
+        for _ in range(args.steps):
+            device_step()
+        end.record()
+        barrier()
+    collectives = None
+    if reducer is not None:
+        collectives = {
+            "collectives_per_step": (reducer.issued - collectives_before[0]) // args.steps,
+            "bytes_per_step": (reducer.bytes - collectives_before[1]) // args.steps,
+        }
+    elapsed = torch.tensor([start.elapsed_time(end)], device=device)
+    if distributed:
+        dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(elapsed.item())
+    launches = ops.launch_count() // args.steps
+    clocks = sampler.summary()
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    wall_start = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_seconds = torch.tensor([time.perf_counter() - wall_start], device=device)
+    local_audio = torch.tensor([float(lengths.sum()) / SAMPLE_RATE], device=device)
+    if distributed:
+        dist.all_reduce(e2e_seconds, op=dist.ReduceOp.MAX)
+        dist.all_reduce(local_audio, op=dist.ReduceOp.SUM)
+    audio_seconds = float(local_audio.item()) * args.steps
+    h2d_bytes = host_audio.numel() * 4 + 16 * TRAIN_BATCH + sum(v.numel() * 8 for v in labels_host.values()) + sum(
+        v.numel() * 8 for v in label_lengths_host.values()
+    )
+
+    roofline = None
+    if rank == 0:
+        plan_frames = int(frames.max())
+        gemm_events: List[Any] = []
+        original = ops.run_gemm
+        sizes = (1024, 3072, 4096)
+
+        def timed_gemm(gemm_args):
+            encoder_linear = gemm_args.mode == 0 and gemm_args.n in sizes and (
+                (not gemm_args.b_mn_major and gemm_args.k in sizes) or (gemm_args.b_mn_major and not gemm_args.a_mn_major and gemm_args.k_seq in sizes)
+                or (gemm_args.a_mn_major and gemm_args.a_rows in sizes)
+            )
+            if encoder_linear:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                original(gemm_args)
+                ev1.record()
+                gemm_events.append((ev0, ev1))
+            else:
+                original(gemm_args)
+
+        ops.run_gemm = timed_gemm
+        try:
+            device_step()
+            torch.cuda.synchronize()
+        finally:
+            ops.run_gemm = original
+        gemm_ms = sum(a.elapsed_time(b) for a, b in gemm_events)
+        flops = 3.0 * encoder_flops(plan_frames)["linear"] * TRAIN_BATCH  # forward + dgrad + wgrad over the padded frame count
+        peaks = measured_peaks()
+        achieved = flops / (gemm_ms / 1000.0) / 1e12
+        peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+        roofline = {
+            "kernel": "aph::gemm_bf16_kernel (encoder linears: forward, data-gradient and weight-gradient forms)",
+            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": f"bf16_tflops_sustained, {peaks['source']}", "launches": len(gemm_events),
+            "avg_launch_ms": gemm_ms / max(1, len(gemm_events)), "share_of_step": gemm_ms / (elapsed_ms / args.steps),
+        }  # fmt: skip
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": "audio-sec/sec, multitask training step (forward + multi-head CTC + backward + gradient all-reduce)",
+        "value": audio_seconds / (elapsed_ms / 1000.0),
+        "unit": UNIT,
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": max(3, args.warmup),
+        "ms_per_step": elapsed_ms / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "bf16",
+        "data": "synthetic",
+        "config": {
+            "workload": "BASELINE configs[2]: Allophant Multitask (XLS-R-300M shape, random init, allophone layer over "
+            f"{TRAIN_LANGUAGES} languages x {TRAIN_PHONES} phones, feature extractor frozen) training step: forward + 37-head CTC + backward"
+            f"{' + overlapped NCCL gradient all-reduce' if distributed else ''}; {TRAIN_BATCH} utterances per GPU, U[3 s, 15 s], eval-mode arithmetic "
+            "(no dropout / SpecAugment), no optimizer step",
+            "batch_per_gpu": TRAIN_BATCH,
+            "padded_seconds": samples / SAMPLE_RATE,
+            "parallelism": f"dp{world}",
+            "allreduce": collectives,
+            "l2": "per-step activations (>1 GB) exceed the 126 MB L2; no explicit flush between iterations",
+        },
+        "clocks": clocks,
+        "e2e": {"value": audio_seconds / float(e2e_seconds.item()), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": None,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main() -> None:
     parser = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     parser.add_argument("--gpus", type=int, default=1)
@@ -386,9 +629,13 @@ def main() -> None:
     parser.add_argument("--warmup", type=int, default=3)
     parser.add_argument("--impl", choices=["b200", "reference"], default="b200")
     parser.add_argument("--skip-cpu-baseline", action="store_true")
+    parser.add_argument("--workload", choices=["predict", "train"], default="predict",
+                        help="predict = BASELINE configs[1] (the headline, default); train = configs[2] training step")  # fmt: skip
     args = parser.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "train":
+        run_train_arm(args)
     else:
         run_gpu_arm(args)
 

@@ -36,6 +36,19 @@ def _worker(rank: int, world: int, port: int, results) -> None:
         assert issued == 2 and all(torch.equal(p.grad, torch.full_like(p, 3.0)) for p in params)
         total = global_label_count([torch.tensor([3, 4]) + rank, torch.tensor([1])])
         assert float(total) == (8 + 10)
+        # overlapped reducer: flat groups are reduced in place, small tensors are packed into one bucket
+        from allophant_b200.distributed import GradientReducer
+
+        reducer = GradientReducer()
+        flat = torch.full((64,), float(rank + 1))
+        views = {"a": flat[:16].view(4, 4), "b": flat[16:]}
+        reducer.submit(flat, views)
+        packed = reducer.submit_tensors({"w": torch.full((3, 5), float(rank)), "b": torch.full((7,), 2.0 * rank)})
+        reducer.finish()
+        assert reducer.issued == 2 and not reducer.works
+        assert torch.equal(views["a"], torch.full((4, 4), 3.0)) and torch.equal(views["b"], torch.full((48,), 3.0))
+        assert packed["w"].shape == (3, 5) and torch.equal(packed["w"], torch.full((3, 5), 1.0))
+        assert torch.equal(packed["b"], torch.full((7,), 2.0))
         results[rank] = indices
     finally:
         dist.destroy_process_group()
