@@ -105,6 +105,7 @@ _SIGNATURES = {
     "aph_attention_bf16_lse": [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
     "aph_attention_backward_bf16": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P],
     "aph_debug_set_progress": [_P],
+    "aph_debug_set_timeline": [_P],
     "aph_wave_stats": [_P, _P, _I32, _I32, _P, _P, _P],
     "aph_wave_norm": [_P, _P, _P, _I32, _I32, _P, _P],
     "aph_frame_lengths": [_P, _I32, _P, _P, _I32, _P, _P, _P],
@@ -117,6 +118,7 @@ _SIGNATURES = {
     "aph_dependency_softmax": [_P, _I64, _I64, _P, _P, _P, _I32, _I32, _P, _I64, _P],
     "aph_argmax_rows": [_P, _I64, _I64, _I32, _P, _P, _P],
     "aph_ctc_greedy_collapse": [_P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
+    "aph_ctc_pack_hypotheses": [_P, _P, _P, _I32, _I32, _P, _P, _P, _P],
     "aph_cast_bf16": [_P, _P, _I64, _P],
     "aph_cast_bf16_2d": [_P, _I64, _P, _I64, _I64, _I32, _P],
     "aph_pack_conv_weight": [_P, _P, _I32, _I32, _I32, _P],

@@ -3,30 +3,40 @@
 // derived from per-utterance frame counts instead of a dense [N,1,T,T] mask,
 // HF:758-762).
 //
-// One CTA = 128 query frames of one (utterance, head); head_dim = 64.
-//   warps 0..3  softmax: one query row per thread; S read from TMEM, online
-//               softmax in fp32, P written bf16 into 128B-swizzled smem, running
-//               output O kept in registers (64 fp32) and rescaled per KV block
-//   warp 4      TMA producer: Q once, then K_j [128 keys x 64] and Vt_j [64 x 128 keys]
-//               through a 2-stage ring
-//   warp 5      TMEM allocator + single-thread tcgen05.mma issuer:
-//               S = Q K_j^T (128x128x64), PV = P V_j (128x64x128)
-// Keys >= lengths[b] get probability exactly 0; KV blocks past the utterance's
-// last valid frame and query tiles that are entirely padding are skipped.
+// One CTA = 128 query frames of one (utterance, head); head_dim = 64; keys in blocks of 64;
+// two CTAs per SM.  With head_dim 64 the kernel is bound by the softmax, not by the tensor core
+// (one exp2 per score on the MUFU pipe, 16/clk/SM, and one TMEM read per score), so the design
+// keeps the four softmax warps of a CTA busy all the time:
+//   warps 0..3  softmax: one query row per thread; the 64 scores of a block are read from TMEM once
+//               and stay in registers (max, exp2, row sum, bf16 pack -> 128B-swizzled smem)
+//   warp 4      TMA producer: Q once, then K_j [64 keys x 64] and Vt_j [64 x 64 keys] through two
+//               independent 3-stage rings (a K tile is released as soon as its scores are issued)
+//   warp 5      TMEM allocator + single-thread tcgen05.mma issuer
+//   * scores run TWO blocks ahead: S is double-buffered in TMEM and S_{j+2} = Q K_{j+2}^T is issued the
+//     moment the softmax warps have read S_j, so its latency hides behind the softmax of block j+1;
+//   * the running output O stays in TMEM and is accumulated by the tensor core across key blocks
+//     (O += P_j V_j); it is rescaled only when a row's maximum grows by more than 2^8 (lazy rescaling:
+//     P is then expressed relative to a slightly stale maximum, which the final division by the row
+//     sum cancels exactly), so nobody waits for the PV product on the common path;
+//   * P is double-buffered in shared memory (the PV product of block j reads P_j while P_{j+1} is written).
+// Keys >= lengths[b] get probability exactly 0; key blocks past the utterance's last valid frame and
+// query tiles that are entirely padding are skipped.
 #include "aph_common.cuh"
 
 namespace aph {
 
 constexpr int kAttThreads = 192;
 constexpr int kAttQ = 128;    // query rows per CTA
-constexpr int kAttKV = 128;   // keys per block
+constexpr int kAttKV = 64;    // keys per block
 constexpr int kAttD = 64;     // head dim
-constexpr int kAttTileBytes = 128 * 64 * 2;  // 16 KB
-// 7 tiles + barriers = 114,944 B: two CTAs fit one SM (2 x (114,944 + 1,024 reserved) <= 233,472), so the
-// tensor core works on one CTA's MMAs while the other CTA's warps are in the softmax.
-constexpr int kAttSmemBytes = kAttTileBytes /*Q*/ + 2 * kAttTileBytes /*K*/ + 2 * kAttTileBytes /*Vt*/ +
-                              2 * kAttTileBytes /*P*/ + 256 /*barriers*/;
-constexpr uint32_t kAttTmemCols = 256;  // S: [0,128)  PV: [128,192)
+constexpr int kAttStages = 3;
+constexpr int kAttQBytes = kAttQ * kAttD * 2;    // 16 KB
+constexpr int kAttKVBytes = kAttKV * kAttD * 2;  // 8 KB
+constexpr int kAttPBytes = kAttQ * kAttKV * 2;   // 16 KB
+constexpr int kAttSmemBytes = kAttQBytes + kAttStages * kAttKVBytes /*K*/ + kAttStages * kAttKVBytes /*Vt*/ +
+                              2 * kAttPBytes + 256 /*barriers*/;
+constexpr uint32_t kAttTmemCols = 256;  // S0: [0,64)  S1: [64,128)  O: [128,192)
+constexpr float kAttRescaleThreshold = 8.0f;  // log2 units
 
 struct AttParams {
   __nv_bfloat16* ctx;  // [N*T, heads*64]
@@ -35,6 +45,19 @@ struct AttParams {
   int heads;
   float* lse2;         // [N*heads, T] log2-domain log-sum-exp of every query row (training) or nullptr
 };
+
+// Debug timeline (device buffer set through aph_debug_set_timeline; NULL in production): clock64 stamps of CTA (0,0)
+__device__ long long* g_timeline = nullptr;
+#define APH_STAMP(slot)                                                                       \
+  do {                                                                                        \
+    if (g_timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 0) g_timeline[slot] = clock64(); \
+  } while (0)
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __global__ void __launch_bounds__(kAttThreads, 2)
     attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -47,6 +70,7 @@ __global__ void __launch_bounds__(kAttThreads, 2)
   len = len < p.T ? len : p.T;
   if (q0 >= len) return;  // whole tile is padding (uniform per CTA, before any barrier/TMEM use)
   const int n_kv = (len + kAttKV - 1) / kAttKV;
+  if (threadIdx.x == 0) APH_STAMP(0);
 
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) {  // 128B-swizzled tiles need 1024-byte alignment
@@ -54,17 +78,21 @@ __global__ void __launch_bounds__(kAttThreads, 2)
     __trap();
   }
   uint8_t* s_q = smem;
-  uint8_t* s_k = s_q + kAttTileBytes;       // 2 stages
-  uint8_t* s_v = s_k + 2 * kAttTileBytes;   // 2 stages, each two 8 KB halves (keys 0-63 / 64-127)
-  uint8_t* s_p = s_v + 2 * kAttTileBytes;   // two 16 KB halves (keys 0-63 / 64-127)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 2 * kAttTileBytes);
+  uint8_t* s_k = s_q + kAttQBytes;                 // kAttStages tiles
+  uint8_t* s_v = s_k + kAttStages * kAttKVBytes;   // kAttStages tiles
+  uint8_t* s_p = s_v + kAttStages * kAttKVBytes;   // 2 tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 2 * kAttPBytes);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* k_full = bars + 1;    // [3]
+  uint64_t* k_empty = bars + 4;   // [3]
+  uint64_t* v_full = bars + 7;    // [3]
+  uint64_t* v_empty = bars + 10;  // [3]
+  uint64_t* s_full = bars + 13;   // [2]  scores of block j in TMEM buffer j & 1
+  uint64_t* p_full = bars + 15;   // [2]  probabilities of block j written (and S_j read, O rescaled), barrier j & 1:
+                                  //      a warp may run one block ahead of the slowest one (its scores are already
+                                  //      there), so consecutive blocks must not share a barrier
+  uint64_t* o_full = bars + 17;   // [2]  PV product of block j accumulated (barrier j & 1)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -74,13 +102,17 @@ __global__ void __launch_bounds__(kAttThreads, 2)
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+    for (int s = 0; s < kAttStages; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&o_full[s], 1);
+      mbar_init(&p_full[s], 128);
+    }
     fence_mbar_init();
   }
   if (warp == 5) tmem_alloc<kAttTmemCols>(tmem_slot);
@@ -88,163 +120,182 @@ __global__ void __launch_bounds__(kAttThreads, 2)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base;
-  const uint32_t tmem_pv = tmem_base + 128;
+  const uint32_t tmem_o = tmem_base + 128;
+  if (threadIdx.x == 0) APH_STAMP(1);
 
   if (warp == 4) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kAttTileBytes);
+      mbar_arrive_expect_tx(q_full, kAttQBytes);
       tma_load_3d(s_q, &tm_q, q_full, 0, q0, bh);
       for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[st], 2 * kAttTileBytes);
-        tma_load_3d(s_k + st * kAttTileBytes, &tm_k, &kv_full[st], 0, j * kAttKV, bh);
-        tma_load_3d(s_v + st * kAttTileBytes, &tm_v, &kv_full[st], j * kAttKV, 0, bh);
-        tma_load_3d(s_v + st * kAttTileBytes + kAttTileBytes / 2, &tm_v, &kv_full[st], j * kAttKV + 64, 0, bh);
+        const int st = j % kAttStages;
+        const uint32_t ph = static_cast<uint32_t>(j / kAttStages) & 1u;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], kAttKVBytes);
+        tma_load_3d(s_k + st * kAttKVBytes, &tm_k, &k_full[st], 0, j * kAttKV, bh);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], kAttKVBytes);
+        tma_load_3d(s_v + st * kAttKVBytes, &tm_v, &v_full[st], j * kAttKV, 0, bh);
       }
     }
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64);
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
       const uint64_t dq = umma_desc_sw128(smem_u32(s_q));
-      const uint64_t dp0 = umma_desc_sw128(smem_u32(s_p));
-      const uint64_t dp1 = umma_desc_sw128(smem_u32(s_p + kAttTileBytes));
       mbar_wait(q_full, 0);
-      auto issue_s = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&kv_full[st], (j >> 1) & 1);
+      APH_STAMP(2);
+      auto issue_s = [&](int j) {  // S_j = Q K_j^T into TMEM buffer j & 1
+        const int st = j % kAttStages;
+        mbar_wait(&k_full[st], static_cast<uint32_t>(j / kAttStages) & 1u);
         tc_fence_after();
-        const uint64_t dk = umma_desc_sw128(smem_u32(s_k + st * kAttTileBytes));
+        const uint64_t dk = umma_desc_sw128(smem_u32(s_k + st * kAttKVBytes));
+        const uint32_t tmem_s = tmem_base + static_cast<uint32_t>((j & 1) * 64);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc_s,
-                    k != 0 ? 1u : 0u);
-        umma_commit(s_full);
+          umma_bf16(tmem_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[j & 1]);
+        umma_commit(&k_empty[st]);  // the K tile is free once these MMAs have read it
       };
       issue_s(0);
+      if (n_kv > 1) issue_s(1);
       for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        mbar_wait(p_full, j & 1);
+        const int st = j % kAttStages;
+        mbar_wait(&p_full[j & 1], static_cast<uint32_t>(j >> 1) & 1u);  // P_j in smem, S_j read, O rescaled if needed
+        mbar_wait(&v_full[st], static_cast<uint32_t>(j / kAttStages) & 1u);
         tc_fence_after();
-        const uint64_t dv0 = umma_desc_sw128(smem_u32(s_v + st * kAttTileBytes));
-        const uint64_t dv1 = umma_desc_sw128(smem_u32(s_v + st * kAttTileBytes + kAttTileBytes / 2));
+        const uint64_t dp = umma_desc_sw128(smem_u32(s_p + (j & 1) * kAttPBytes));
+        const uint64_t dv = umma_desc_sw128(smem_u32(s_v + st * kAttKVBytes));
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t da = (k < 4 ? dp0 : dp1) + static_cast<uint64_t>(2 * (k & 3));
-          const uint64_t db = (k < 4 ? dv0 : dv1) + static_cast<uint64_t>(2 * (k & 3));
-          umma_bf16(tmem_pv, da, db, idesc_pv, k != 0 ? 1u : 0u);
-        }
-        umma_commit(o_full);
-        umma_commit(&kv_empty[st]);
-        if (j + 1 < n_kv) issue_s(j + 1);  // S is free: p_full(j) implies the softmax warps finished reading it
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_o, dp + static_cast<uint64_t>(2 * k), dv + static_cast<uint64_t>(2 * k), idesc, (j | k) != 0 ? 1u : 0u);
+        umma_commit(&o_full[j & 1]);
+        umma_commit(&v_empty[st]);
+        // S_{j+2} is issued AFTER PV_j and reuses the TMEM buffer of S_j.  tcgen05 operations of one thread complete
+        // in order and a commit tracks everything issued before it, so "S_{j+2} ready" also tells the softmax warps
+        // that PV_j has finished reading P buffer j & 1 — the buffer P_{j+2} goes to — without a second wait.
+        if (j + 2 < n_kv) issue_s(j + 2);
       }
     }
   } else {
     // ===================== softmax / output (one query row per thread) =====================
     const int r = warp * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-    float m_run = -INFINITY;
+    float m_ref = -INFINITY;  // reference maximum of the probabilities currently accumulated in O (log2 domain)
     float l_run = 0.f;
-    float o[kAttD];
-#pragma unroll
-    for (int d = 0; d < kAttD; ++d) o[d] = 0.f;
-    uint8_t* p_row = s_p + (r >> 3) * 1024 + (r & 7) * 128;
+    uint8_t* p_row0 = s_p + (r >> 3) * 1024 + (r & 7) * 128;
     const int sw = r & 7;
 
     for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(s_full, j & 1);
+      mbar_wait(&s_full[j & 1], static_cast<uint32_t>(j >> 1) & 1u);
       tc_fence_after();
       const int key0 = j * kAttKV;
-      const bool full_block = key0 + kAttKV <= len;  // no padded keys in this block (CTA-uniform)
-      // pass 1: row max (scores are already in the log2 domain: q carries head_dim^-0.5 * log2(e))
+      const uint32_t tmem_s = tmem_base + static_cast<uint32_t>((j & 1) * 64) + lane_off;
+      float va[32], vb[32];  // keys 0-31 / 32-63 of the block: two plain register arrays
+      auto load_scores = [&]() {
+        tmem_ld32(tmem_s, va);
+        tmem_ld32(tmem_s + 32u, vb);
+        tmem_ld_wait();
+        if (key0 + kAttKV > len) {  // padded keys in this block (CTA-uniform)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            va[i] = (key0 + i < len) ? va[i] : -INFINITY;
+            vb[i] = (key0 + 32 + i < len) ? vb[i] : -INFINITY;
+          }
+        }
+      };
+      load_scores();
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll 1
-      for (int c0 = 0; c0 < kAttKV; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_s + lane_off + static_cast<uint32_t>(c0), v);
-        tmem_ld_wait();
-        if (full_block) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], v[i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], (key0 + c0 + i < len) ? v[i] : -INFINITY);
-        }
+      for (int i = 0; i < 32; ++i) {
+        mx[i & 1] = fmaxf(mx[i & 1], va[i]);
+        mx[2 + (i & 1)] = fmaxf(mx[2 + (i & 1)], vb[i]);
       }
-      const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])));
-      const float alpha = exp2f(m_run - m_new);
-      // pass 2: probabilities -> smem (bf16, swizzled K-major), row sum
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-      for (int c0 = 0; c0 < kAttKV; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_s + lane_off + static_cast<uint32_t>(c0), v);
-        tmem_ld_wait();
-        if (full_block) {
+      const float m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      // lazy rescaling: only when this row's maximum outgrows the reference by more than 2^8
+      const bool grow = m_blk > m_ref + kAttRescaleThreshold;  // always true for the first block (m_ref = -inf)
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = grow ? m_blk : m_ref;
+        const float alpha = ex2_approx(m_ref - m_new);  // 1 for rows that keep their reference, 0 for the first block
+        if (j > 0) {
+          // O <- O * alpha in TMEM; the previous PV product must have landed first (warp-collective ld/st)
+          mbar_wait(&o_full[(j - 1) & 1], static_cast<uint32_t>((j - 1) >> 1) & 1u);
+          tc_fence_after();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            v[i] = exp2f(v[i] - m_new);
-            ls[i & 3] += v[i];
-          }
-        } else {
+          for (int c0 = 0; c0 < kAttD; c0 += 32) {
+            float o[32];
+            tmem_ld32(tmem_o + lane_off + static_cast<uint32_t>(c0), o);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            v[i] = (key0 + c0 + i < len) ? exp2f(v[i] - m_new) : 0.f;
-            ls[i & 3] += v[i];
+            for (int i = 0; i < 32; ++i) o[i] *= alpha;
+            tmem_st32(tmem_o + lane_off + static_cast<uint32_t>(c0), o);
           }
+          tmem_st_wait();
+          load_scores();  // re-read instead of keeping 64 scores live across the (rare) correction: no spills
         }
-        uint8_t* dst_half = p_row + (c0 >> 6) * kAttTileBytes;
-        const int chunk0 = (c0 & 63) >> 3;
+        l_run *= alpha;
+        m_ref = m_new;
+      }
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        va[i] = ex2_approx(va[i] - m_ref);
+        vb[i] = ex2_approx(vb[i] - m_ref);
+        ls[i & 1] += va[i];
+        ls[2 + (i & 1)] += vb[i];
+      }
+      l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      // P buffer j & 1 was last read by the PV product of block j - 2, which completed before S_j did (see the issuer)
+      uint8_t* p_row = p_row0 + (j & 1) * kAttPBytes;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 o4;
+        o4.x = pack_bf16x2(va[8 * i + 0], va[8 * i + 1]);
+        o4.y = pack_bf16x2(va[8 * i + 2], va[8 * i + 3]);
+        o4.z = pack_bf16x2(va[8 * i + 4], va[8 * i + 5]);
+        o4.w = pack_bf16x2(va[8 * i + 6], va[8 * i + 7]);
+        *reinterpret_cast<uint4*>(p_row + ((i ^ sw) << 4)) = o4;
+        o4.x = pack_bf16x2(vb[8 * i + 0], vb[8 * i + 1]);
+        o4.y = pack_bf16x2(vb[8 * i + 2], vb[8 * i + 3]);
+        o4.z = pack_bf16x2(vb[8 * i + 4], vb[8 * i + 5]);
+        o4.w = pack_bf16x2(vb[8 * i + 6], vb[8 * i + 7]);
+        *reinterpret_cast<uint4*>(p_row + (((4 + i) ^ sw) << 4)) = o4;
+      }
+      fence_proxy_async_smem();  // P visible to the tensor core's smem reads
+      tc_fence_before();         // our TMEM reads of S (and writes of O) are ordered before the next MMAs
+      mbar_arrive(&p_full[j & 1]);
+    }
+
+    mbar_wait(&o_full[(n_kv - 1) & 1], static_cast<uint32_t>((n_kv - 1) >> 1) & 1u);
+    if (threadIdx.x == 0) APH_STAMP(24);
+    tc_fence_after();
+    const bool row_in = q0 + r < p.T;
+    if (row_in && p.lse2 != nullptr) p.lse2[static_cast<long long>(bh) * p.T + q0 + r] = m_ref + log2f(l_run);
+    const float inv = 1.0f / l_run;
+    __nv_bfloat16* dst = p.ctx + (static_cast<long long>(b) * p.T + q0 + r) * (p.heads * kAttD) + h * kAttD;
+#pragma unroll
+    for (int c0 = 0; c0 < kAttD; c0 += 32) {
+      float o[32];
+      tmem_ld32(tmem_o + lane_off + static_cast<uint32_t>(c0), o);  // warp-collective: outside the row guard
+      tmem_ld_wait();
+      if (row_in) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 o4;
-          o4.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-          o4.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-          o4.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-          o4.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-          *reinterpret_cast<uint4*>(dst_half + (((chunk0 + i) ^ sw) << 4)) = o4;
+          o4.x = pack_bf16x2(o[8 * i + 0] * inv, o[8 * i + 1] * inv);
+          o4.y = pack_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
+          o4.z = pack_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
+          o4.w = pack_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
+          d4[i] = o4;
         }
       }
-      l_run = l_run * alpha + ((ls[0] + ls[1]) + (ls[2] + ls[3]));
-      m_run = m_new;
-      fence_proxy_async_smem();  // P visible to the tensor core's smem reads
-      tc_fence_before();         // our TMEM reads of S are ordered before the next S = Q K^T
-      mbar_arrive(p_full);
-
-      mbar_wait(o_full, j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c0 = 0; c0 < kAttD; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_pv + lane_off + static_cast<uint32_t>(c0), v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c0 + i] = fmaf(o[c0 + i], alpha, v[i]);
-      }
-      tc_fence_before();
     }
-
-    if (q0 + r < p.T) {
-      if (p.lse2 != nullptr) p.lse2[static_cast<long long>(bh) * p.T + q0 + r] = m_run + log2f(l_run);
-      const float inv = 1.0f / l_run;
-      __nv_bfloat16* dst = p.ctx + (static_cast<long long>(b) * p.T + q0 + r) * (p.heads * kAttD) + h * kAttD;
-      uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        uint4 o4;
-        o4.x = pack_bf16x2(o[8 * i + 0] * inv, o[8 * i + 1] * inv);
-        o4.y = pack_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
-        o4.z = pack_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
-        o4.w = pack_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
-        d4[i] = o4;
-      }
-    }
+    tc_fence_before();
   }
 
+  if (threadIdx.x == 0) APH_STAMP(25);
   tc_fence_before();
   __syncthreads();
   if (warp == 5) {
@@ -252,9 +303,16 @@ __global__ void __launch_bounds__(kAttThreads, 2)
     tc_fence_after();
     tmem_dealloc<kAttTmemCols>(tmem_base);
   }
+  if (threadIdx.x == 160) APH_STAMP(26);
 }
 
 }  // namespace aph
+
+extern "C" int aph_debug_set_timeline(int64_t* device_buffer) {
+  long long* ptr = reinterpret_cast<long long*>(device_buffer);
+  APH_CUDA_CHECK(cudaMemcpyToSymbol(aph::g_timeline, &ptr, sizeof(ptr)));
+  return APH_OK;
+}
 
 extern "C" int aph_attention_bf16(const void* q, const void* k, const void* vt, void* ctx,
                                   const int32_t* lengths, int32_t n_utt, int32_t heads, int32_t T,
@@ -275,16 +333,17 @@ extern "C" int aph_attention_bf16_lse(const void* q, const void* k, const void* 
   {
     const uint64_t dims[3] = {kAttD, static_cast<uint64_t>(T), nh};
     const uint64_t strides[2] = {kAttD * 2, static_cast<uint64_t>(T) * kAttD * 2};
-    const uint32_t box[3] = {kAttD, kAttQ, 1};
-    int rc = encode_tmap(&tm_q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, q, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    const uint32_t box_q[3] = {kAttD, kAttQ, 1};
+    const uint32_t box_k[3] = {kAttD, kAttKV, 1};
+    int rc = encode_tmap(&tm_q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, q, dims, strides, box_q, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != APH_OK) return rc;
-    rc = encode_tmap(&tm_k, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, k, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = encode_tmap(&tm_k, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, k, dims, strides, box_k, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != APH_OK) return rc;
   }
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(t_v), kAttD, nh};
     const uint64_t strides[2] = {static_cast<uint64_t>(t_v) * 2, static_cast<uint64_t>(t_v) * kAttD * 2};
-    const uint32_t box[3] = {64, kAttD, 1};
+    const uint32_t box[3] = {kAttKV, kAttD, 1};
     int rc = encode_tmap(&tm_v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, vt, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != APH_OK) return rc;
   }

@@ -360,9 +360,71 @@ __global__ void __launch_bounds__(128) ctc_greedy_collapse_kernel(const int* __r
   }
 }
 
+// Packs the padded [n_seq][T] results into two dense arrays (hypothesis s occupies [offsets[s], offsets[s+1])):
+// the host then splits one small tensor instead of mask-indexing n_seq * T elements.
+// Single block: an exclusive scan of counts (n_seq is heads * utterances, a few thousand), then a strided copy.
+__global__ void __launch_bounds__(1024) ctc_pack_kernel(const int* __restrict__ tokens, const int* __restrict__ timesteps,
+                                                        const int* __restrict__ counts, int n_seq, int T,
+                                                        int* __restrict__ offsets /*[n_seq + 1]*/, int* __restrict__ packed_tokens,
+                                                        int* __restrict__ packed_timesteps) {
+  __shared__ int warp_totals[32];
+  __shared__ int base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  for (int s0 = 0; s0 < n_seq; s0 += 1024) {
+    const int s = s0 + threadIdx.x;
+    const int c = s < n_seq ? counts[s] : 0;
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += up;
+    }
+    if (lane == 31) warp_totals[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_totals[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += up;
+      }
+      warp_totals[lane] = w;  // inclusive scan of the warp totals
+    }
+    __syncthreads();
+    const int before = base + (warp > 0 ? warp_totals[warp - 1] : 0) + inc - c;
+    if (s < n_seq) offsets[s] = before;
+    __syncthreads();
+    if (threadIdx.x == 0) base += warp_totals[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[n_seq] = base;
+  __syncthreads();
+  // copy: one warp per sequence
+  for (int s = warp; s < n_seq; s += 32) {
+    const int off = offsets[s], c = counts[s];
+    for (int i = lane; i < c; i += 32) {
+      packed_tokens[off + i] = tokens[static_cast<long long>(s) * T + i];
+      packed_timesteps[off + i] = timesteps[static_cast<long long>(s) * T + i];
+    }
+  }
+}
+
 }  // namespace aph
 
 using namespace aph;
+
+extern "C" int aph_ctc_pack_hypotheses(const int32_t* tokens, const int32_t* timesteps, const int32_t* counts, int32_t n_seq,
+                                       int32_t T, int32_t* offsets, int32_t* packed_tokens, int32_t* packed_timesteps,
+                                       void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  APH_REQUIRE(tokens && timesteps && counts && offsets && packed_tokens && packed_timesteps, "null pointer");
+  APH_REQUIRE(n_seq > 0 && T > 0, "bad shape");
+  ctc_pack_kernel<<<1, 1024, 0, stream>>>(tokens, timesteps, counts, n_seq, T, offsets, packed_tokens, packed_timesteps);
+  APH_POST_LAUNCH(1);
+  return APH_OK;
+}
 
 extern "C" int aph_compose_embeddings(const float* weight, int32_t n_categories, int32_t embedding_size, const int64_t* tfi,
                                       const int64_t* category_offsets, int32_t n_phonemes, int32_t n_features,

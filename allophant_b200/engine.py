@@ -45,6 +45,7 @@ class PackedEncoder:
         self.weights = weights
         self.cfg = weights.config
         self._version: Optional[Tuple[int, ...]] = None
+        self._params: Optional[List[Tensor]] = None
         self.device: Optional[torch.device] = None
 
     def _current_version(self) -> Tuple[int, ...]:
@@ -54,7 +55,9 @@ class PackedEncoder:
             except RuntimeError:  # inference tensors do not track a version counter
                 return -1
 
-        params = list(self.weights.parameters())
+        params = self._params
+        if params is None:  # the module tree is fixed after construction: walk it once
+            params = self._params = list(self.weights.parameters())
         return tuple(version(p) for p in params) + tuple(p.data_ptr() for p in params)
 
     def ensure(self) -> None:

@@ -131,7 +131,9 @@ class HeadsRuntime:
 
     # ------------------------------------------------------------------ weights
     def _params_version(self) -> Tuple[int, ...]:
-        params = list(self.model._projection.parameters())
+        params = getattr(self, "_projection_params", None)
+        if params is None:
+            params = self._projection_params = list(self.model._projection.parameters())
         return tuple(_version(p) for p in params) + tuple(p.data_ptr() for p in params)
 
     @torch.no_grad()

@@ -17,7 +17,14 @@ from . import _lib
 from ._lib import CtcHead, GemmArgs, check, lib
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def _stream() -> ctypes.c_void_p:
+    """``cudaStream_t`` of torch's current stream (raw accessors: ~1 us instead of ~12 us per launch)."""
+    if _raw_stream is not None and _raw_device is not None:
+        return ctypes.c_void_p(_raw_stream(_raw_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -480,6 +487,23 @@ def ctc_greedy_collapse(
         "aph_ctc_greedy_collapse",
     )
     return tokens, timesteps, counts, scores
+
+
+def ctc_pack_hypotheses(tokens: Tensor, timesteps: Tensor, counts: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """(offsets int32 [n_seq+1], packed tokens, packed timesteps): dense copies of the valid prefixes of every row."""
+    _require_cuda(tokens, timesteps, counts)
+    n_seq, seq = tokens.shape
+    dev = tokens.device
+    offsets = torch.empty(n_seq + 1, device=dev, dtype=torch.int32)
+    packed_tokens = torch.empty(n_seq * seq, device=dev, dtype=torch.int32)
+    packed_timesteps = torch.empty(n_seq * seq, device=dev, dtype=torch.int32)
+    check(
+        lib.aph_ctc_pack_hypotheses(
+            tokens.data_ptr(), timesteps.data_ptr(), counts.data_ptr(), n_seq, seq, offsets.data_ptr(), packed_tokens.data_ptr(), packed_timesteps.data_ptr(), _stream()
+        ),
+        "aph_ctc_pack_hypotheses",
+    )
+    return offsets, packed_tokens, packed_timesteps
 
 
 # --------------------------------------------------------------------------------------

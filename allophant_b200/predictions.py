@@ -24,18 +24,57 @@ class CTCHypothesis(NamedTuple):
     timesteps: torch.IntTensor
 
 
-def _hypotheses(tokens: Tensor, timesteps: Tensor, counts: Tensor, scores: Tensor, n_utt: int) -> List[List[List[CTCHypothesis]]]:
-    """Splits the padded device results into per-(head, utterance) hypotheses on the host.
+_PINNED: Dict[Any, List[Tensor]] = {}
 
-    One device-to-host copy per array, then a single masked compaction and ``Tensor.split`` (C++ loops):
-    the per-hypothesis Python work is only the NamedTuple construction."""
-    counts_h = counts.cpu()
-    lengths = counts_h.tolist()
-    frames = tokens.shape[1]
-    keep = torch.arange(frames).unsqueeze(0) < counts_h.unsqueeze(1)
-    token_parts = tokens.cpu()[keep].long().split(lengths)
-    timestep_parts = timesteps.cpu()[keep].long().split(lengths)
-    score_parts = scores.cpu().unbind(0)
+
+def _pinned_like(tensor: Tensor, slot: int) -> Tensor:
+    """Rotating pinned host buffers per (shape, dtype): ``cudaHostAlloc`` costs milliseconds, so they are kept."""
+    key = (tuple(tensor.shape), tensor.dtype)
+    ring = _PINNED.setdefault(key, [])
+    while len(ring) <= slot:
+        ring.append(torch.empty(tensor.shape, dtype=tensor.dtype, pin_memory=True))
+    return ring[slot]
+
+
+class PendingDecode:
+    """Greedy decoding in flight: the collapse kernel and the device-to-host copies are enqueued, nothing has
+    synchronised yet.  ``result()`` waits for the copies and builds the hypotheses; a streaming caller launches
+    the next batch first, so this host work overlaps the GPU work of that batch."""
+
+    _turn = 0
+
+    def __init__(self, tokens: Tensor, timesteps: Tensor, counts: Tensor, scores: Tensor, n_utt: int, selected: Optional[Dict[str, int]]):
+        slot = PendingDecode._turn % 3
+        PendingDecode._turn += 1
+        # dense packing on the device: the host splits one small tensor instead of mask-indexing n_seq x T elements
+        _, packed_tokens, packed_timesteps = ops.ctc_pack_hypotheses(tokens, timesteps, counts)
+        self._host = []
+        for index, tensor in enumerate((packed_tokens, packed_timesteps, counts, scores)):
+            host = _pinned_like(tensor, 4 * slot + index)
+            host.copy_(tensor, non_blocking=True)
+            self._host.append(host)
+        self._event = torch.cuda.Event()
+        self._event.record()
+        self._n_utt = n_utt
+        self._selected = selected
+        self._result: Any = None
+
+    def result(self):
+        if self._result is None:
+            self._event.synchronize()
+            per_head = _hypotheses(*self._host, self._n_utt)
+            self._result = per_head if self._selected is None else {name: per_head[index] for name, index in self._selected.items()}
+        return self._result
+
+
+def _hypotheses(packed_tokens: Tensor, packed_timesteps: Tensor, counts: Tensor, scores: Tensor, n_utt: int) -> List[List[List[CTCHypothesis]]]:
+    """Splits the packed results (already on the host) into per-(head, utterance) hypotheses: two ``Tensor.split``
+    calls (C++ loops); the per-hypothesis Python work is only the NamedTuple construction."""
+    lengths = counts.tolist()
+    total = sum(lengths)
+    token_parts = packed_tokens[:total].long().split(lengths)
+    timestep_parts = packed_timesteps[:total].long().split(lengths)
+    score_parts = scores.clone().unbind(0)
     n_heads = len(lengths) // n_utt
     result = []
     for head in range(n_heads):
@@ -68,7 +107,22 @@ class GreedyCTCDecoder:
         ops.argmax_rows(emissions, classes, rows, classes, argmax, maxlp)
         frames32 = lengths.to(device=device, dtype=torch.int32).contiguous()
         tokens, timesteps, counts, scores = ops.ctc_greedy_collapse(argmax, maxlp, frames32, n_utt, seq, n_utt, self._blank_index)
-        return _hypotheses(tokens, timesteps, counts, scores, n_utt)[0]
+        return PendingDecode(tokens, timesteps, counts, scores, n_utt, None).result()[0]
+
+
+def decode_predictions_async(predictions: Any, names: Optional[Iterable[str]] = None, blank_index: int = 0) -> PendingDecode:
+    """Enqueues the greedy decoding of all (or the named) heads of ``Estimator.predict``'s result (one collapse
+    launch + four device-to-host copies into pinned buffers) and returns without synchronising."""
+    cache = getattr(predictions, "_decode_cache", None)
+    if cache is None:
+        raise ValueError("decode_predictions_async needs the result of Estimator.predict / Allophant.predict_log_probabilities")
+    selected = list(predictions.outputs if names is None else names)
+    n_utt, seq = cache["n_utt"], cache["seq"]
+    n_heads = cache["argmax"].shape[0]
+    tokens, timesteps, counts, scores = ops.ctc_greedy_collapse(
+        cache["argmax"], cache["maxlp"], cache["frames32"], n_utt, seq, n_heads * n_utt, blank_index
+    )
+    return PendingDecode(tokens, timesteps, counts, scores, n_utt, {name: cache["head_index"][name] for name in selected})
 
 
 def decode_predictions(predictions: Any, names: Optional[Iterable[str]] = None, blank_index: int = 0) -> Dict[str, List[List[CTCHypothesis]]]:
@@ -76,18 +130,11 @@ def decode_predictions(predictions: Any, names: Optional[Iterable[str]] = None, 
 
     Equivalent to ``{name: GreedyCTCDecoder()(predictions.outputs[name].transpose(1, 0).contiguous(),
     predictions.lengths) for name in names}`` (``run.py:767-774``)."""
-    cache = getattr(predictions, "_decode_cache", None)
-    selected = list(predictions.outputs if names is None else names)
-    if cache is None:
+    if getattr(predictions, "_decode_cache", None) is None:
         decoder = GreedyCTCDecoder(blank_index)
+        selected = list(predictions.outputs if names is None else names)
         return {name: decoder(predictions.outputs[name].transpose(1, 0), predictions.lengths) for name in selected}
-    n_utt, seq = cache["n_utt"], cache["seq"]
-    n_heads = cache["argmax"].shape[0]
-    tokens, timesteps, counts, scores = ops.ctc_greedy_collapse(
-        cache["argmax"], cache["maxlp"], cache["frames32"], n_utt, seq, n_heads * n_utt, blank_index
-    )
-    per_head = _hypotheses(tokens, timesteps, counts, scores, n_utt)
-    return {name: per_head[cache["head_index"][name]] for name in selected}
+    return decode_predictions_async(predictions, names, blank_index).result()
 
 
 def _ctc_decoder(categories: Iterable[str], beam_width: int = 1, n_best: int = 1) -> GreedyCTCDecoder:

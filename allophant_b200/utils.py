@@ -31,6 +31,11 @@ def mask_sequence(
 def evaluation(model: nn.Module):
     """Temporarily switches a module to eval mode (``estimator.py:138-150``)."""
     was_training = model.training
+    if not was_training:
+        # already in eval mode (the usual case for inference): walking ~4000 sub-modules twice per call to set
+        # flags that are already set would cost more host time than enqueueing the whole forward pass
+        yield model
+        return
     model.eval()
     try:
         yield model

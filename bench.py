@@ -216,6 +216,8 @@ def workload_config(n_gpus: int) -> Dict[str, Any]:
         "seconds_per_utterance": SECONDS,
         "parallelism": f"dp{n_gpus} (independent utterance shards, no collective)",
         "l2": "per-step activations (>1 GB) exceed the 126 MB L2; no explicit flush between iterations",
+        "e2e": "a stream of 3 x steps batches through Estimator.predict + decode_predictions_async: pinned host audio copied in on a "
+        "copy stream, decoded tokens copied out, CTCHypothesis lists built on the host while the next batch computes",
     }
 
 
@@ -223,7 +225,7 @@ def workload_config(n_gpus: int) -> Dict[str, Any]:
 def run_gpu_arm(args) -> None:
     from allophant_b200 import ops
     from allophant_b200.dataset_processing import Batch
-    from allophant_b200.predictions import decode_predictions
+    from allophant_b200.predictions import decode_predictions_async
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -253,10 +255,33 @@ def run_gpu_arm(args) -> None:
         return ops.ctc_greedy_collapse(cache["argmax"], cache["maxlp"], cache["frames32"], cache["n_utt"], cache["seq"],
                                        cache["argmax"].shape[0] * cache["n_utt"], 0)  # fmt: skip
 
-    def e2e_step():
-        batch = Batch(host_audio, host_lengths, host_languages).to(device, non_blocking=True)
+    copy_stream = torch.cuda.Stream(device=device)
+
+    def e2e_launch():
+        """Host -> device copy of one batch from pinned memory (on a copy stream, so it overlaps the previous batch's
+        kernels), predict, greedy decode and the device -> host copy of the decoded tokens: everything is enqueued,
+        nothing synchronises."""
+        with torch.cuda.stream(copy_stream):
+            batch = Batch(host_audio, host_lengths, host_languages).to(device, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record()
+        torch.cuda.current_stream().wait_event(copied)
+        for tensor in (batch.audio_features, batch.lengths, batch.language_ids):
+            tensor.record_stream(torch.cuda.current_stream())
         predictions = estimator.predict(batch, tfi_dev)
-        return decode_predictions(predictions)
+        return decode_predictions_async(predictions)
+
+    def e2e_stream(steps: int):
+        """A streaming client of the public API: while the GPU works on batch i+1 the host turns the copied-back
+        tokens of batch i into CTCHypothesis lists.  Every batch is copied in, computed, copied out and decoded."""
+        pending, hypotheses = None, None
+        for _ in range(steps):
+            launched = e2e_launch()
+            if pending is not None:
+                hypotheses = pending.result()
+            pending = launched
+        hypotheses = pending.result()
+        return hypotheses
 
     def barrier():
         if distributed:
@@ -284,12 +309,12 @@ def run_gpu_arm(args) -> None:
     launches = ops.launch_count() // args.steps
     clocks = sampler.summary()
 
-    for _ in range(2):
-        e2e_step()
-    wall_start = time.perf_counter()
+    e2e_stream(2)
     barrier()
-    for _ in range(args.steps):
-        result = e2e_step()  # decode_predictions ends with a device-to-host copy: the step is complete on return
+    e2e_steps = 3 * args.steps  # a stream of batches: the one-batch pipeline fill is amortised over 3K batches
+    wall_start = time.perf_counter()
+    result = e2e_stream(e2e_steps)  # the last result() waits for the last device-to-host copy
+    assert len(result) == 37 and len(result["phoneme"]) == BATCH
     barrier()
     e2e_seconds = torch.tensor([time.perf_counter() - wall_start], device=device)
     if distributed:
@@ -302,7 +327,7 @@ def run_gpu_arm(args) -> None:
 
     audio_seconds = world * BATCH * SECONDS * args.steps
     value = audio_seconds / (elapsed_ms / 1000.0)
-    e2e_value = audio_seconds / float(e2e_seconds.item())
+    e2e_value = world * BATCH * SECONDS * e2e_steps / float(e2e_seconds.item())
 
     # ---- roofline of the dominant kernel: the tcgen05 GEMM over the encoder's 24 x {QKV, out, FFN1, FFN2} ----
     roofline = None
@@ -340,7 +365,11 @@ def run_gpu_arm(args) -> None:
             "peak": peak,
             "unit": "TFLOP/s",
             "frac": achieved / peak,
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over one layer's QKV / out-proj / FFN1 /
+            # FFN2 launches of the `ncu --set full` capture in profiles/r01_ncu_summary.md (83.4 / 110.8 / 117.3 / 249.7 MB):
+            # equal to the algorithmic operand + residual bytes, i.e. no re-reads
+            "traffic": 140.3e6,
+            "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_summary.md)",
             "peak_source": f"bf16_tflops_sustained, {peaks['source']}",
             "launches": len(gemm_events),
             "avg_launch_ms": gemm_ms / max(1, len(gemm_events)),

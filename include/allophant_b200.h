@@ -151,6 +151,8 @@ int aph_attention_backward_bf16(const void* q, const void* k, const void* v, con
 /* Debug aid: progress markers of block (0,0) of the attention backward kernels are written to this
  * host-mapped int32[16] array (NULL = off, the default). */
 int aph_debug_set_progress(int32_t* host_mapped);
+/* Debug aid: clock64 stamps of CTA (0,0) of the attention forward kernel go to this DEVICE int64[32] array (NULL = off). */
+int aph_debug_set_timeline(int64_t* device_buffer);
 
 /* ---- waveform normalisation and frame bookkeeping ------------------------- */
 /* zero_mean_unit_var_norm, acoustic_model.py:762-767:
@@ -236,6 +238,12 @@ int aph_ctc_greedy_collapse(const int32_t* argmax_in, const float* maxlp_in,
                             const int32_t* lengths, int32_t n_utt, int32_t T, int32_t n_seq,
                             int32_t blank, int32_t* tokens, int32_t* timesteps, int32_t* counts,
                             float* scores, void* stream);
+
+/* Dense packing of the collapse results for the device-to-host copy: offsets[n_seq+1] = exclusive scan of
+ * counts; packed_tokens / packed_timesteps (capacity n_seq*T) hold hypothesis s at [offsets[s], offsets[s+1]). */
+int aph_ctc_pack_hypotheses(const int32_t* tokens, const int32_t* timesteps, const int32_t* counts,
+                            int32_t n_seq, int32_t T, int32_t* offsets, int32_t* packed_tokens,
+                            int32_t* packed_timesteps, void* stream);
 
 /* ---- weight packing (once per weight version) ---------------------------------- */
 /* fp32 -> bf16 (nn.Linear weights are already the K-major B operand). */

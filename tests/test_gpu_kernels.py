@@ -131,6 +131,45 @@ def test_attention(n, heads, frames, lengths):
         assert range_err(ours[index, :length], reference[index, :length]) < 2e-2
 
 
+@pytest.mark.parametrize("sharpness", [8.0, 40.0])
+def test_attention_large_scores_exercise_lazy_rescaling(sharpness):
+    """Peaked score distributions (row maxima that keep growing by more than 2^8 from block to block) exercise the
+    in-TMEM rescaling of the running output and its barrier protocol; many CTAs run concurrently (warps of one CTA
+    drift apart by a block), repeated launches must agree bit for bit."""
+    ops = _ops()
+    torch.manual_seed(7)
+    n, heads, frames = 8, 16, 499
+    lengths = [499, 450, 400, 333, 257, 129, 64, 17]
+    t_v = (frames + 7) // 8 * 8
+    q = torch.randn(n, heads, frames, 64, device=DEV)
+    k = torch.randn(n, heads, frames, 64, device=DEV).bfloat16()
+    v = torch.randn(n, heads, frames, 64, device=DEV).bfloat16()
+    # later keys get larger scores: the running maximum grows along the key axis
+    k = (k.float() * (1.0 + torch.arange(frames, device=DEV)[None, None, :, None] / frames)).bfloat16()
+    vt = torch.zeros(n, heads, 64, t_v, device=DEV, dtype=torch.bfloat16)
+    vt[..., :frames] = v.transpose(2, 3)
+    q_scaled = (q * sharpness * 0.125 * math.log2(math.e)).bfloat16()
+    frame_lengths = torch.tensor(lengths, device=DEV, dtype=torch.int32)
+    results = []
+    for _ in range(3):
+        ctx = torch.zeros(n * frames, heads * 64, device=DEV, dtype=torch.bfloat16)
+        lse = torch.zeros(n * heads * frames, device=DEV, dtype=torch.float32)
+        ops.attention(q_scaled, k, vt, ctx, frame_lengths, n, heads, frames, t_v, lse)
+        results.append((ctx, lse))
+    torch.cuda.synchronize()
+    mask = torch.arange(frames)[None, :] < torch.tensor(lengths)[:, None]
+    scores = (q_scaled.float().cpu() / math.log2(math.e) @ k.float().cpu().transpose(2, 3)).masked_fill(~mask[:, None, None, :], float("-inf"))
+    reference = (torch.softmax(scores, -1) @ v.float().cpu()).permute(0, 2, 1, 3).reshape(n, frames, heads * 64)
+    lse_ref = torch.logsumexp(scores, -1) * math.log2(math.e)
+    ours = results[0][0].float().cpu().view(n, frames, heads * 64)
+    lse_ours = results[0][1].view(n, heads, frames).cpu()
+    for index, length in enumerate(lengths):
+        assert range_err(ours[index, :length], reference[index, :length]) < 2e-2
+        assert float((lse_ours[index, :, :length] - lse_ref[index, :, :length]).abs().max()) < 2e-2 * max(1.0, float(lse_ref[index, :, :length].abs().max()))
+    for ctx, lse in results[1:]:
+        assert torch.equal(ctx, results[0][0]) and torch.equal(lse, results[0][1])
+
+
 # ------------------------------------------------------------------------------------------ front end
 def test_wave_norm_and_frame_lengths():
     ops = _ops()
