@@ -575,33 +575,35 @@ def run_train_arm(args) -> None:
         v.numel() * 8 for v in label_lengths_host.values()
     )
 
+    # ---- roofline of the dominant kernel: every rank runs one more step (it contains collectives), rank 0 times its GEMMs
     roofline = None
+    gemm_events: List[Any] = []
+    original = ops.run_gemm
+    sizes = (1024, 3072, 4096)
+
+    def timed_gemm(gemm_args):
+        encoder_linear = gemm_args.mode == 0 and gemm_args.n in sizes and (
+            (not gemm_args.b_mn_major and gemm_args.k in sizes) or (gemm_args.b_mn_major and not gemm_args.a_mn_major and gemm_args.k_seq in sizes)
+            or (gemm_args.a_mn_major and gemm_args.a_rows in sizes)
+        )
+        if encoder_linear:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            original(gemm_args)
+            ev1.record()
+            gemm_events.append((ev0, ev1))
+        else:
+            original(gemm_args)
+
+    if rank == 0:
+        ops.run_gemm = timed_gemm
+    try:
+        device_step()
+        torch.cuda.synchronize()
+    finally:
+        ops.run_gemm = original
     if rank == 0:
         plan_frames = int(frames.max())
-        gemm_events: List[Any] = []
-        original = ops.run_gemm
-        sizes = (1024, 3072, 4096)
-
-        def timed_gemm(gemm_args):
-            encoder_linear = gemm_args.mode == 0 and gemm_args.n in sizes and (
-                (not gemm_args.b_mn_major and gemm_args.k in sizes) or (gemm_args.b_mn_major and not gemm_args.a_mn_major and gemm_args.k_seq in sizes)
-                or (gemm_args.a_mn_major and gemm_args.a_rows in sizes)
-            )
-            if encoder_linear:
-                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                ev0.record()
-                original(gemm_args)
-                ev1.record()
-                gemm_events.append((ev0, ev1))
-            else:
-                original(gemm_args)
-
-        ops.run_gemm = timed_gemm
-        try:
-            device_step()
-            torch.cuda.synchronize()
-        finally:
-            ops.run_gemm = original
         gemm_ms = sum(a.elapsed_time(b) for a, b in gemm_events)
         flops = 3.0 * encoder_flops(plan_frames)["linear"] * TRAIN_BATCH  # forward + dgrad + wgrad over the padded frame count
         peaks = measured_peaks()
@@ -661,6 +663,11 @@ def main() -> None:
     parser.add_argument("--workload", choices=["predict", "train"], default="predict",
                         help="predict = BASELINE configs[1] (the headline, default); train = configs[2] training step")  # fmt: skip
     args = parser.parse_args()
+    hang_dump = float(os.environ.get("BENCH_HANG_DUMP", "0"))
+    if hang_dump > 0:  # debugging aid: dump every thread's Python stack if the run is still going after this many seconds
+        import faulthandler
+
+        faulthandler.dump_traceback_later(hang_dump, exit=True)
     if args.impl == "reference":
         run_reference_arm(args)
     elif args.workload == "train":
