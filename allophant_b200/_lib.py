@@ -138,8 +138,8 @@ _SIGNATURES = {
     "aph_softmax_backward_cols": [_P, _I64, _P, _I64, _I64, _P, _P, _P, _I32, _I32, _P, _I64, _P],
     "aph_edit_statistics_batch": [_P, _P, _P, _P, _I64, _P, _P, _I32],
     "aph_ctc_states_pad": [_I32],
-    "aph_ctc_forward": [_P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
-    "aph_ctc_backward": [_P, POINTER(CtcHead), _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
+    "aph_ctc_forward": [POINTER(CtcHead), _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
+    "aph_ctc_backward": [POINTER(CtcHead), _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
 }
 
 EXPORTED_SYMBOLS = sorted(

@@ -14,6 +14,8 @@
 // heads gather only the label columns they need.  The blank index is 0
 // (config.py:555 BLANK_OFFSET) and labels are the padded int64 [N, S_max]
 // matrices of LabeledBatch (dataset_processing.py:132-162).
+#include <string.h>
+
 #include "aph_common.cuh"
 
 namespace aph {
@@ -22,16 +24,37 @@ constexpr int kCtcWarps = 4;
 constexpr int kCtcChunk = 32;    // frames staged per shared-memory refill
 constexpr int kCtcSmallC = 32;   // heads up to this many classes use the staged path
 
+// The recursions run in the LOG2 domain with the hardware approximations ex2.approx / lg2.approx (relative error
+// 2^-22; the error of a 700-frame loss stays ~1e-7 relative, see test_ctc_long_labels_and_empty_targets) and without
+// branches: the maximum is floored at a large finite value, so all-(-inf) inputs give lg2(0) = -inf by themselves.
+// expf()/logf() with their range reduction and the `m == -inf` branches made the dependent chain 3x longer.
+constexpr float kLog2E = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+__device__ __forceinline__ float ex2a(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2a(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float lse2(float a, float b) {
-  const float m = fmaxf(a, b);
-  if (m == -INFINITY) return -INFINITY;
-  return m + logf(expf(a - m) + expf(b - m));
+  const float m = fmaxf(fmaxf(a, b), -1e30f);
+  return m + lg2a(ex2a(a - m) + ex2a(b - m));
 }
 __device__ __forceinline__ float lse3(float a, float b, float c) {
-  const float m = fmaxf(a, fmaxf(b, c));
-  if (m == -INFINITY) return -INFINITY;
-  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+  const float m = fmaxf(fmaxf(a, fmaxf(b, c)), -1e30f);
+  return m + lg2a(ex2a(a - m) + ex2a(b - m) + ex2a(c - m));
 }
+
+// The per-head descriptors travel BY VALUE in the kernel parameters (<= 4 KB): no device copy of the array, hence
+// no synchronous pageable-memory transfer between the forward pass and the loss.
+constexpr int kCtcMaxHeads = 48;
+struct CtcHeadPack {
+  aph_ctc_head h[kCtcMaxHeads];
+};
 
 struct PairInfo {
   const float* lp;      // log-probs of this utterance: element (t, k) at lp[t*stride_t + k]
@@ -45,9 +68,9 @@ struct PairInfo {
   int s_pad;
 };
 
-__device__ __forceinline__ bool load_pair(const aph_ctc_head* heads, int h, int n, int n_utt, int T,
+__device__ __forceinline__ bool load_pair(const CtcHeadPack& heads, int h, int n, int n_utt, int T,
                                           const long long* input_lengths, float* alpha_ws, PairInfo& p) {
-  const aph_ctc_head& hd = heads[h];
+  const aph_ctc_head& hd = heads.h[h];
   p.lp = hd.log_probs + static_cast<long long>(n) * hd.stride_n;
   p.grad = hd.grad ? hd.grad + static_cast<long long>(n) * hd.stride_n : nullptr;
   p.stride_t = hd.stride_t;
@@ -66,7 +89,7 @@ __device__ __forceinline__ bool load_pair(const aph_ctc_head* heads, int h, int 
 // forward: alpha recursion, per-pair negative log-likelihood
 // ---------------------------------------------------------------------------
 template <int K>
-__global__ void __launch_bounds__(kCtcWarps * 32) ctc_alpha_kernel(const aph_ctc_head* __restrict__ heads, int n_heads,
+__global__ void __launch_bounds__(kCtcWarps * 32) ctc_alpha_kernel(const __grid_constant__ CtcHeadPack heads, int n_heads,
                                                                    int n_utt, int T,
                                                                    const long long* __restrict__ input_lengths,
                                                                    float* __restrict__ alpha_ws,
@@ -80,7 +103,7 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_alpha_kernel(const aph_ctc
   load_pair(heads, h, n, n_utt, T, input_lengths, alpha_ws, p);
   const int S2 = 2 * p.S + 1;
   float* out = nll_out + static_cast<long long>(h) * n_utt + n;
-  if (S2 > 32 * K || p.S > heads[h].label_stride) {  // host guarantees this never happens
+  if (S2 > 32 * K || p.S > heads.h[h].label_stride) {  // host guarantees this never happens
     if (lane == 0) *out = NAN;
     return;
   }
@@ -107,6 +130,14 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_alpha_kernel(const aph_ctc
   float* st = stage[warp];
   float a[K];
   float nll = 0.f;
+  float e_next[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) e_next[i] = 0.f;
+  if (!small_c) {
+    const float eb = __ldg(p.lp);
+#pragma unroll
+    for (int i = 0; i < K; ++i) e_next[i] = (((lane * K + i) & 1) ? __ldg(p.lp + lab[i]) : eb) * kLog2E;
+  }
 
   for (int t0 = 0; t0 < p.T_in; t0 += kCtcChunk) {
     const int nt = min(kCtcChunk, p.T_in - t0);
@@ -115,26 +146,32 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_alpha_kernel(const aph_ctc
       const int total = nt * p.c;
       if (p.stride_t == p.c) {
         const float* src = p.lp + static_cast<long long>(t0) * p.stride_t;
-        for (int i = lane; i < total; i += 32) st[i] = __ldg(src + i);
+        for (int i = lane; i < total; i += 32) st[i] = __ldg(src + i) * kLog2E;
       } else {
         for (int i = lane; i < total; i += 32) {
           const int tt = i / p.c, k = i - tt * p.c;
-          st[i] = __ldg(p.lp + static_cast<long long>(t0 + tt) * p.stride_t + k);
+          st[i] = __ldg(p.lp + static_cast<long long>(t0 + tt) * p.stride_t + k) * kLog2E;
         }
       }
       __syncwarp();
     }
     for (int tt = 0; tt < nt; ++tt) {
       const int t = t0 + tt;
-      float e[K];
+      float e[K];  // log2 emission probabilities
       if (small_c) {
 #pragma unroll
         for (int i = 0; i < K; ++i) e[i] = st[tt * p.c + lab[i]];
       } else {
-        const float* row = p.lp + static_cast<long long>(t) * p.stride_t;
-        const float eb = __ldg(row);
+        // wide head: the gathers of frame t+1 are issued now and consumed one iteration later (a single warp per
+        // scheduler cannot hide an L2 round trip behind anything else)
 #pragma unroll
-        for (int i = 0; i < K; ++i) e[i] = ((lane * K + i) & 1) ? __ldg(row + lab[i]) : eb;
+        for (int i = 0; i < K; ++i) e[i] = e_next[i];
+        if (t + 1 < p.T_in) {
+          const float* row = p.lp + static_cast<long long>(t + 1) * p.stride_t;
+          const float eb = __ldg(row);
+#pragma unroll
+          for (int i = 0; i < K; ++i) e_next[i] = (((lane * K + i) & 1) ? __ldg(row + lab[i]) : eb) * kLog2E;
+        }
       }
       if (t == 0) {
 #pragma unroll
@@ -175,7 +212,7 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_alpha_kernel(const aph_ctc
   }
   last1 = warp_max(last1);
   last2 = warp_max(last2);
-  nll = -lse2(last1, last2);
+  nll = -lse2(last1, last2) * kLn2;  // back to natural units
   if (lane == 0) *out = nll;
 }
 
@@ -188,7 +225,7 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_alpha_kernel(const aph_ctc
 // ctc_grad_init_kernel and the (few) label columns are corrected with atomics.
 // ---------------------------------------------------------------------------
 template <int K>
-__global__ void __launch_bounds__(kCtcWarps * 32) ctc_beta_kernel(const aph_ctc_head* __restrict__ heads, int n_heads, int n_utt,
+__global__ void __launch_bounds__(kCtcWarps * 32) ctc_beta_kernel(const __grid_constant__ CtcHeadPack heads, int n_heads, int n_utt,
                                                                   int T, const long long* __restrict__ input_lengths,
                                                                   const float* __restrict__ alpha_ws,
                                                                   const float* __restrict__ nll_in /*[H][N]*/,
@@ -204,6 +241,7 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_beta_kernel(const aph_ctc_
   if (p.grad == nullptr) return;
   const int S2 = 2 * p.S + 1;
   const float nll = nll_in[static_cast<long long>(h) * n_utt + n];
+  const float nll2 = nll * kLog2E;  // the recursions (and the alpha workspace) are in the log2 domain
   const float g = grad_scale ? grad_scale[h] : 1.f;
   const bool small_c = p.c <= kCtcSmallC;
   const bool dead = !(nll < INFINITY) || S2 > 32 * K;  // inf / nan loss -> zero gradient
@@ -232,6 +270,20 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_beta_kernel(const aph_ctc_
   float* st = stage[warp];
   float* cs = csum[warp];
   float b[K];
+  float al_next[K], e_next[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) al_next[i] = e_next[i] = 0.f;
+  if (lane * K < p.s_pad) {
+    const float* nrow = p.alpha + static_cast<long long>(p.T_in - 1) * p.s_pad + lane * K;
+#pragma unroll
+    for (int i = 0; i < K; ++i) al_next[i] = nrow[i];
+  }
+  if (!small_c) {
+    const float* row = p.lp + static_cast<long long>(p.T_in - 1) * p.stride_t;
+    const float eb = __ldg(row);
+#pragma unroll
+    for (int i = 0; i < K; ++i) e_next[i] = (((lane * K + i) & 1) ? __ldg(row + lab[i]) : eb) * kLog2E;
+  }
 
   const int n_chunks = (p.T_in + kCtcChunk - 1) / kCtcChunk;
   for (int ch = n_chunks - 1; ch >= 0; --ch) {
@@ -242,26 +294,38 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_beta_kernel(const aph_ctc_
       const int total = nt * p.c;
       if (p.stride_t == p.c) {
         const float* src = p.lp + static_cast<long long>(t0) * p.stride_t;
-        for (int i = lane; i < total; i += 32) st[i] = __ldg(src + i);
+        for (int i = lane; i < total; i += 32) st[i] = __ldg(src + i) * kLog2E;
       } else {
         for (int i = lane; i < total; i += 32) {
           const int tt = i / p.c, k = i - tt * p.c;
-          st[i] = __ldg(p.lp + static_cast<long long>(t0 + tt) * p.stride_t + k);
+          st[i] = __ldg(p.lp + static_cast<long long>(t0 + tt) * p.stride_t + k) * kLog2E;
         }
       }
       __syncwarp();
     }
     for (int tt = nt - 1; tt >= 0; --tt) {
       const int t = t0 + tt;
-      float e[K];
+      float e[K], al[K];
+      // alpha row of this frame was requested one iteration ago; request the one of frame t-1 now
+#pragma unroll
+      for (int i = 0; i < K; ++i) al[i] = al_next[i];
+      if (t > 0 && lane * K < p.s_pad) {
+        const float* nrow = p.alpha + static_cast<long long>(t - 1) * p.s_pad + lane * K;
+#pragma unroll
+        for (int i = 0; i < K; ++i) al_next[i] = nrow[i];
+      }
       if (small_c) {
 #pragma unroll
         for (int i = 0; i < K; ++i) e[i] = st[tt * p.c + lab[i]];
       } else {
-        const float* row = p.lp + static_cast<long long>(t) * p.stride_t;
-        const float eb = __ldg(row);
 #pragma unroll
-        for (int i = 0; i < K; ++i) e[i] = ((lane * K + i) & 1) ? __ldg(row + lab[i]) : eb;
+        for (int i = 0; i < K; ++i) e[i] = e_next[i];
+        if (t > 0) {
+          const float* row = p.lp + static_cast<long long>(t - 1) * p.stride_t;
+          const float eb = __ldg(row);
+#pragma unroll
+          for (int i = 0; i < K; ++i) e_next[i] = (((lane * K + i) & 1) ? __ldg(row + lab[i]) : eb) * kLog2E;
+        }
       }
       if (t == p.T_in - 1) {
 #pragma unroll
@@ -284,17 +348,13 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_beta_kernel(const aph_ctc_
         }
       }
       // occupation probabilities gamma_t(s)
-      const float* arow = p.alpha + static_cast<long long>(t) * p.s_pad + lane * K;
       float gam[K];
       float blank_sum = 0.f;
 #pragma unroll
       for (int i = 0; i < K; ++i) {
         const int s = lane * K + i;
         float gm = 0.f;
-        if (s < S2) {
-          const float x = arow[i] + b[i] - e[i] + nll;
-          gm = x > -80.f ? expf(x) : 0.f;
-        }
+        if (s < S2) gm = ex2a(al[i] + b[i] - e[i] + nll2);  // ex2.approx.ftz: tiny occupancies flush to 0
         gam[i] = gm;
         if (!(s & 1)) blank_sum += gm;
       }
@@ -310,7 +370,7 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_beta_kernel(const aph_ctc_
         __syncwarp();
         if (lane < p.c) {
           const float occ = cs[lane] + (lane == 0 ? blank_sum : 0.f);
-          p.grad[static_cast<long long>(t) * p.stride_t + lane] = g * (expf(st[tt * p.c + lane]) - occ);
+          p.grad[static_cast<long long>(t) * p.stride_t + lane] = g * (ex2a(st[tt * p.c + lane]) - occ);
         }
         __syncwarp();
       } else {
@@ -327,11 +387,10 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_beta_kernel(const aph_ctc_
 }
 
 // wide heads: grad[t][k] = g * exp(lp[t][k]) for valid frames of finite-loss pairs, else 0
-__global__ void __launch_bounds__(256) ctc_grad_init_kernel(const aph_ctc_head* __restrict__ heads, int h, int n_utt, int T,
+__global__ void __launch_bounds__(256) ctc_grad_init_kernel(const aph_ctc_head hd, int h, int n_utt, int T,
                                                             const long long* __restrict__ input_lengths,
                                                             const float* __restrict__ nll_in,
                                                             const float* __restrict__ grad_scale) {
-  const aph_ctc_head hd = heads[h];
   const int n = blockIdx.y;
   const float nll = nll_in[static_cast<long long>(h) * n_utt + n];
   const float g = grad_scale ? grad_scale[h] : 1.f;
@@ -361,7 +420,7 @@ __global__ void ctc_reduce_kernel(const float* __restrict__ nll, int n_heads, in
 }
 
 template <int K>
-static int launch_alpha(const aph_ctc_head* heads, int n_heads, int n_utt, int T, const int64_t* input_lengths, float* alpha_ws,
+static int launch_alpha(const CtcHeadPack& heads, int n_heads, int n_utt, int T, const int64_t* input_lengths, float* alpha_ws,
                         float* nll, cudaStream_t stream) {
   const int pairs = n_heads * n_utt;
   ctc_alpha_kernel<K><<<ceil_div(pairs, kCtcWarps), kCtcWarps * 32, 0, stream>>>(
@@ -369,7 +428,7 @@ static int launch_alpha(const aph_ctc_head* heads, int n_heads, int n_utt, int T
   return APH_OK;
 }
 template <int K>
-static int launch_beta(const aph_ctc_head* heads, int n_heads, int n_utt, int T, const int64_t* input_lengths,
+static int launch_beta(const CtcHeadPack& heads, int n_heads, int n_utt, int T, const int64_t* input_lengths,
                        const float* alpha_ws, const float* nll, const float* grad_scale, cudaStream_t stream) {
   const int pairs = n_heads * n_utt;
   ctc_beta_kernel<K><<<ceil_div(pairs, kCtcWarps), kCtcWarps * 32, 0, stream>>>(
@@ -393,25 +452,32 @@ extern "C" int aph_ctc_states_pad(int32_t max_label_len) {
   return k == 0 ? APH_ERR_UNSUPPORTED : 32 * k;
 }
 
-extern "C" int aph_ctc_forward(const aph_ctc_head* heads_dev, int32_t n_heads, int32_t n_utt, int32_t T,
+extern "C" int aph_ctc_forward(const aph_ctc_head* heads_host, int32_t n_heads, int32_t n_utt, int32_t T,
                                int32_t max_label_len, const int64_t* input_lengths, float* alpha_ws, float* nll_out,
                                float* loss_out, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  APH_REQUIRE(heads_dev && input_lengths && nll_out, "null pointer");
+  APH_REQUIRE(heads_host && input_lengths && nll_out, "null pointer");
   APH_REQUIRE(n_heads > 0 && n_utt > 0 && T > 0, "empty problem");
   const int k = pick_k(max_label_len);
   if (k == 0) {
     set_last_error("aph_ctc_forward", "label sequences longer than 511 are not supported", __FILE__, __LINE__);
     return APH_ERR_UNSUPPORTED;
   }
-  switch (k) {
-    case 2: launch_alpha<2>(heads_dev, n_heads, n_utt, T, input_lengths, alpha_ws, nll_out, stream); break;
-    case 4: launch_alpha<4>(heads_dev, n_heads, n_utt, T, input_lengths, alpha_ws, nll_out, stream); break;
-    case 8: launch_alpha<8>(heads_dev, n_heads, n_utt, T, input_lengths, alpha_ws, nll_out, stream); break;
-    case 16: launch_alpha<16>(heads_dev, n_heads, n_utt, T, input_lengths, alpha_ws, nll_out, stream); break;
-    default: launch_alpha<32>(heads_dev, n_heads, n_utt, T, input_lengths, alpha_ws, nll_out, stream); break;
+  int launched = 0;
+  for (int h0 = 0; h0 < n_heads; h0 += kCtcMaxHeads) {
+    const int nh = n_heads - h0 < kCtcMaxHeads ? n_heads - h0 : kCtcMaxHeads;
+    CtcHeadPack pack;
+    memcpy(pack.h, heads_host + h0, sizeof(aph_ctc_head) * nh);
+    float* nll = nll_out + static_cast<long long>(h0) * n_utt;
+    switch (k) {
+      case 2: launch_alpha<2>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll, stream); break;
+      case 4: launch_alpha<4>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll, stream); break;
+      case 8: launch_alpha<8>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll, stream); break;
+      case 16: launch_alpha<16>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll, stream); break;
+      default: launch_alpha<32>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll, stream); break;
+    }
+    ++launched;
   }
-  int launched = 1;
   if (loss_out) {
     ctc_reduce_kernel<<<n_heads, 32, 0, stream>>>(nll_out, n_heads, n_utt, loss_out);
     ++launched;
@@ -420,11 +486,11 @@ extern "C" int aph_ctc_forward(const aph_ctc_head* heads_dev, int32_t n_heads, i
   return APH_OK;
 }
 
-extern "C" int aph_ctc_backward(const aph_ctc_head* heads_dev, const aph_ctc_head* heads_host, int32_t n_heads, int32_t n_utt,
-                                int32_t T, int32_t max_label_len, const int64_t* input_lengths, const float* alpha_ws,
-                                const float* nll, const float* grad_scale, void* stream_) {
+extern "C" int aph_ctc_backward(const aph_ctc_head* heads_host, int32_t n_heads, int32_t n_utt, int32_t T,
+                                int32_t max_label_len, const int64_t* input_lengths, const float* alpha_ws, const float* nll,
+                                const float* grad_scale, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  APH_REQUIRE(heads_dev && heads_host && input_lengths && alpha_ws && nll, "null pointer");
+  APH_REQUIRE(heads_host && input_lengths && alpha_ws && nll, "null pointer");
   APH_REQUIRE(n_heads > 0 && n_utt > 0 && T > 0, "empty problem");
   const int k = pick_k(max_label_len);
   if (k == 0) {
@@ -437,17 +503,25 @@ extern "C" int aph_ctc_backward(const aph_ctc_head* heads_dev, const aph_ctc_hea
       long long blocks = (static_cast<long long>(T) * heads_host[h].n_classes + 255) / 256;
       if (blocks > 64) blocks = 64;
       ctc_grad_init_kernel<<<dim3(static_cast<unsigned>(blocks), n_utt), 256, 0, stream>>>(
-          heads_dev, h, n_utt, T, reinterpret_cast<const long long*>(input_lengths), nll, grad_scale);
+          heads_host[h], h, n_utt, T, reinterpret_cast<const long long*>(input_lengths), nll, grad_scale);
       ++launched;
     }
   }
-  switch (k) {
-    case 2: launch_beta<2>(heads_dev, n_heads, n_utt, T, input_lengths, alpha_ws, nll, grad_scale, stream); break;
-    case 4: launch_beta<4>(heads_dev, n_heads, n_utt, T, input_lengths, alpha_ws, nll, grad_scale, stream); break;
-    case 8: launch_beta<8>(heads_dev, n_heads, n_utt, T, input_lengths, alpha_ws, nll, grad_scale, stream); break;
-    case 16: launch_beta<16>(heads_dev, n_heads, n_utt, T, input_lengths, alpha_ws, nll, grad_scale, stream); break;
-    default: launch_beta<32>(heads_dev, n_heads, n_utt, T, input_lengths, alpha_ws, nll, grad_scale, stream); break;
+  for (int h0 = 0; h0 < n_heads; h0 += kCtcMaxHeads) {
+    const int nh = n_heads - h0 < kCtcMaxHeads ? n_heads - h0 : kCtcMaxHeads;
+    CtcHeadPack pack;
+    memcpy(pack.h, heads_host + h0, sizeof(aph_ctc_head) * nh);
+    const float* nll_h = nll + static_cast<long long>(h0) * n_utt;
+    const float* scale_h = grad_scale ? grad_scale + h0 : nullptr;
+    switch (k) {
+      case 2: launch_beta<2>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll_h, scale_h, stream); break;
+      case 4: launch_beta<4>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll_h, scale_h, stream); break;
+      case 8: launch_beta<8>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll_h, scale_h, stream); break;
+      case 16: launch_beta<16>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll_h, scale_h, stream); break;
+      default: launch_beta<32>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll_h, scale_h, stream); break;
+    }
+    ++launched;
   }
-  APH_POST_LAUNCH(launched + 1);
+  APH_POST_LAUNCH(launched);
   return APH_OK;
 }

@@ -734,9 +734,7 @@ class CtcProblem:
             hd.label_lengths = lab_len.data_ptr()
             hd.alpha_offset = alpha_total
             alpha_total += self.n_utt * self.seq * s_pad
-        self.heads_host = heads
-        raw = torch.frombuffer(bytearray(bytes(heads)), dtype=torch.uint8)
-        self.heads_dev = raw.to(dev)
+        self.heads_host = heads  # passed by value in the kernel parameters: no device copy, no synchronous transfer
         self.alpha = torch.empty(alpha_total, device=dev, dtype=torch.float32) if need_grad else None
         self.nll = torch.empty(self.n_heads, self.n_utt, device=dev, dtype=torch.float32)
         self.loss = torch.empty(self.n_heads, device=dev, dtype=torch.float32)
@@ -744,7 +742,7 @@ class CtcProblem:
     def forward(self) -> Tensor:
         check(
             lib.aph_ctc_forward(
-                self.heads_dev.data_ptr(), self.n_heads, self.n_utt, self.seq, self.max_label_len, self.input_lengths.data_ptr(), _ptr(self.alpha), self.nll.data_ptr(), self.loss.data_ptr(), _stream()
+                self.heads_host, self.n_heads, self.n_utt, self.seq, self.max_label_len, self.input_lengths.data_ptr(), _ptr(self.alpha), self.nll.data_ptr(), self.loss.data_ptr(), _stream()
             ),
             "aph_ctc_forward",
         )
@@ -756,7 +754,7 @@ class CtcProblem:
         grad_scale = grad_scale.to(dtype=torch.float32).contiguous()
         check(
             lib.aph_ctc_backward(
-                self.heads_dev.data_ptr(), self.heads_host, self.n_heads, self.n_utt, self.seq, self.max_label_len, self.input_lengths.data_ptr(), self.alpha.data_ptr(), self.nll.data_ptr(), grad_scale.data_ptr(), _stream()
+                self.heads_host, self.n_heads, self.n_utt, self.seq, self.max_label_len, self.input_lengths.data_ptr(), self.alpha.data_ptr(), self.nll.data_ptr(), grad_scale.data_ptr(), _stream()
             ),
             "aph_ctc_backward",
         )

@@ -282,15 +282,15 @@ typedef struct aph_ctc_head {
 int aph_ctc_states_pad(int32_t max_label_len);
 /* Forward: nll_out[h][n] = -log p(labels | log_probs) (inf when infeasible); loss_out[h] =
  * sum_n nll with infinities zeroed (may be NULL). alpha_ws (may be NULL when no gradient is
- * needed) receives the forward variables for aph_ctc_backward. heads_dev is a DEVICE array. */
-int aph_ctc_forward(const aph_ctc_head* heads_dev, int32_t n_heads, int32_t n_utt, int32_t T,
+ * needed) receives the forward variables for aph_ctc_backward. heads_host is a HOST array (the descriptors
+ * travel in the kernel parameters; the pointers inside are device pointers). */
+int aph_ctc_forward(const aph_ctc_head* heads_host, int32_t n_heads, int32_t n_utt, int32_t T,
                     int32_t max_label_len, const int64_t* input_lengths, float* alpha_ws,
                     float* nll_out, float* loss_out, void* stream);
 /* Backward: writes grad (w.r.t. the logits that produced log_probs) for every head with a
  * non-NULL grad pointer: grad_scale[h] * (softmax - state occupancies), zero for padded
- * frames and for pairs whose loss was infinite. heads_host is the same array in HOST memory. */
-int aph_ctc_backward(const aph_ctc_head* heads_dev, const aph_ctc_head* heads_host,
-                     int32_t n_heads, int32_t n_utt, int32_t T, int32_t max_label_len,
+ * frames and for pairs whose loss was infinite. */
+int aph_ctc_backward(const aph_ctc_head* heads_host, int32_t n_heads, int32_t n_utt, int32_t T, int32_t max_label_len,
                      const int64_t* input_lengths, const float* alpha_ws, const float* nll,
                      const float* grad_scale, void* stream);
 
