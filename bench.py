@@ -126,6 +126,9 @@ def measured_peaks() -> Dict[str, Any]:
 # --------------------------------------------------------------------------------------------------
 # model construction (random init of the named architecture; synthetic inventory — no network, no CSV)
 # --------------------------------------------------------------------------------------------------
+HIERARCHICAL = False  # --hierarchical: BASELINE configs[3] (phoneme head depends on OUTPUT + all 36 attribute heads)
+
+
 def build_estimator(device: str):
     from allophant_b200.config import Config, PhonemeLayerType
     from allophant_b200.estimator import Estimator, attribute_graph_from_config
@@ -135,7 +138,11 @@ def build_estimator(device: str):
     config = Config.default()
     config.nn.projection.phoneme_layer = PhonemeLayerType.SHARED
     names = [entry.name for entry in config.nn.projection.classes]
-    indexer = PhoneticAttributeIndexer.synthetic(109, names, n_categories=3, seed=1, training_inventory=60)
+    if HIERARCHICAL:
+        for entry in config.nn.projection.classes:
+            if entry.name == "phoneme":
+                entry.dependencies = ["OUTPUT", *[name for name in names if name != "phoneme"]]
+    indexer = PhoneticAttributeIndexer.synthetic(max(109, INVENTORY), names, n_categories=3, seed=1, training_inventory=60)
     graph = attribute_graph_from_config(config, indexer)
     estimator = Estimator.from_config(config, 1, SAMPLE_RATE, graph, indexer, device=device, load_pretrained_weights=False)
     inventory = [f"p{index}" for index in range(INVENTORY)]
@@ -208,8 +215,14 @@ def run_reference_arm(args) -> None:
 
 
 def workload_config(n_gpus: int) -> Dict[str, Any]:
+    if HIERARCHICAL:
+        name = "BASELINE configs[3]: Allophant Hierarchical (phoneme head over OUTPUT + 36 attribute posteriors, XLS-R-300M shape"
+    elif (BATCH, SECONDS, INVENTORY) == (32, 10, 25):
+        name = "BASELINE configs[1]: Allophant Multitask (XLS-R-300M shape"
+    else:
+        name = "BASELINE configs[4] sweep point: Allophant Multitask (XLS-R-300M shape"
     return {
-        "workload": "BASELINE configs[1]: Allophant Multitask (XLS-R-300M shape, random init) inference, "
+        "workload": f"{name}, random init) inference, "
         f"batch {BATCH} x {SECONDS} s synthetic 16 kHz audio per GPU, 36 attribute heads + composed phoneme head "
         f"(inventory {INVENTORY}), log_softmax + greedy CTC decode of all 37 heads",
         "batch_per_gpu": BATCH,
@@ -333,7 +346,10 @@ def run_gpu_arm(args) -> None:
     roofline = None
     cpu_baseline = None
     if rank == 0:
-        frames = estimator.model.acoustic_model.plan_for(BATCH, samples, 1024, {}).seq
+        length = samples
+        for kernel, stride in zip((10, 3, 3, 3, 3, 2, 2), (5, 2, 2, 2, 2, 2, 2)):
+            length = (length - kernel) // stride + 1
+        frames = length
         gemm_events: List[Any] = []
         original = ops.run_gemm
 
@@ -654,15 +670,21 @@ def run_train_arm(args) -> None:
 
 
 def main() -> None:
+    global BATCH, SECONDS, INVENTORY, HIERARCHICAL
     parser = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     parser.add_argument("--gpus", type=int, default=1)
     parser.add_argument("--steps", type=int, default=10)
     parser.add_argument("--warmup", type=int, default=3)
     parser.add_argument("--impl", choices=["b200", "reference"], default="b200")
     parser.add_argument("--skip-cpu-baseline", action="store_true")
+    parser.add_argument("--batch", type=int, default=BATCH, help="utterances per GPU (predict workload)")
+    parser.add_argument("--seconds", type=int, default=SECONDS, help="seconds per utterance (predict workload)")
+    parser.add_argument("--inventory", type=int, default=INVENTORY, help="phonemes of the target inventory (composed phoneme head)")
+    parser.add_argument("--hierarchical", action="store_true", help="BASELINE configs[3]: hierarchical phoneme head")
     parser.add_argument("--workload", choices=["predict", "train"], default="predict",
                         help="predict = BASELINE configs[1] (the headline, default); train = configs[2] training step")  # fmt: skip
     args = parser.parse_args()
+    BATCH, SECONDS, INVENTORY, HIERARCHICAL = args.batch, args.seconds, args.inventory, args.hierarchical
     hang_dump = float(os.environ.get("BENCH_HANG_DUMP", "0"))
     if hang_dump > 0:  # debugging aid: dump every thread's Python stack if the run is still going after this many seconds
         import faulthandler
