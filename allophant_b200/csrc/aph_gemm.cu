@@ -126,22 +126,30 @@ __device__ __forceinline__ WorkItem decode_work(const GemmParams& p, int work, i
   return w;
 }
 
-template <int BN>
+// Internal epilogue variant: the generic store epilogue with the fp32 residual fetched by TMA into a second
+// per-warp staging tile (one coalesced 4 KB box per 32 x 32 chunk, requested one chunk ahead) instead of one
+// 128-byte line per thread: row-strided residual loads cost 24 us of a 61 us out-proj GEMM.
+constexpr int kEpiStoreResidTma = 2;
+
+template <int BN, int EPI = APH_EPI_STORE>
 struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = (BN / 2) * kBK * 2;  // this CTA's half of the pair's B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
+  // one 32-row x 128-byte output staging tile per epilogue warp (+ one residual tile in the TMA-residual variant)
+  static constexpr int kEpiBytes = EPI == kEpiStoreResidTma ? 8 * 8192 : 8 * 4096;
+  static constexpr int kBudget = kSmemBudget - (kEpiBytes - 8 * 4096);
+  static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // double-buffered accumulator (128 lanes x BN columns per CTA)
-  static constexpr int kEpiBytes = 8 * 4096;  // one 32-row x 128-byte staging tile per epilogue warp
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 512 /*barriers*/;
 };
 
 template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                     const __grid_constant__ CUtensorMap tm_out, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+                     const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_resid,
+                     const GemmParams p) {
+  using Cfg = GemmCfg<BN, EPI>;
   constexpr int kStages = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -152,7 +160,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* resid_bar = tempty_bar + 2;  // [8] one per epilogue warp (TMA-residual variant)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resid_bar + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -161,6 +170,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
     if (p.staged) tma_prefetch_desc(&tm_out);
+    if (EPI == kEpiStoreResidTma) tma_prefetch_desc(&tm_resid);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 2);   // leader's copy is the one in use: one arrive.expect_tx per CTA of the pair
       mbar_init(&empty_bar[s], 1);  // released in both CTAs by the leader's tcgen05.commit multicast
@@ -169,6 +179,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 16);  // leader's copy: one arrival per epilogue warp of both CTAs
     }
+    for (int s = 0; s < 8; ++s) mbar_init(&resid_bar[s], 1);
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
@@ -288,6 +299,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     uint8_t* stage_row = stage_buf + lane * 128;
     const int sw = lane & 7;
     bool store_pending = false;  // a TMA store may still be reading stage_buf
+    // TMA-residual variant: second tile per warp, filled by cp.async.bulk.tensor one chunk ahead of its use
+    uint8_t* resid_buf = epi_smem + 8 * 4096 + warp * 4096;
+    const uint8_t* resid_row = resid_buf + lane * 128;
+    uint32_t resid_phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int work = cluster_id; work < total_work; work += n_clusters) {
@@ -305,6 +320,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
         utt = static_cast<int>(grow / p.len_period);
         tt = static_cast<int>(grow - static_cast<long long>(utt) * p.len_period);
         if (p.lengths != nullptr && row_ok) masked = tt >= p.lengths[utt];
+      }
+      const int t_tile_row0 = (mt % p.m_tiles_per_batch) * kBM + quad * 32;
+      const bool resid_tma = EPI == kEpiStoreResidTma && mt < tiles_m;  // warp-uniform
+      if (resid_tma && col_base + half * (BN / 2) < p.n && lane == 0) {  // first chunk: requested before the accumulator is ready
+        mbar_arrive_expect_tx(&resid_bar[warp], 4096);
+        tma_load_3d(resid_buf, &tm_resid, &resid_bar[warp], col_base + half * (BN / 2), t_tile_row0, b);
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -413,8 +434,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
               }
             }
           }
+          if (resid_tma) {
+            // this chunk's residual tile has landed (or lands now); copy the own row out, then hand the tile back to
+            // the TMA engine for the next chunk.  Rows / columns outside the matrix arrive as zeros.
+            mbar_wait(&resid_bar[warp], resid_phase);
+            resid_phase ^= 1;
+            float4 rv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rv[j] = *reinterpret_cast<const float4*>(resid_row + ((j ^ sw) << 4));
+            fence_proxy_async_smem();
+            __syncwarp();
+            const int c0_next = c0 + 32;
+            if (c0_next < (half + 1) * (BN / 2) && col_base + c0_next < p.n && lane == 0) {
+              mbar_arrive_expect_tx(&resid_bar[warp], 4096);
+              tma_load_3d(resid_buf, &tm_resid, &resid_bar[warp], col_base + c0_next, t_tile_row0, b);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[4 * j + 0] += rv[j].x;
+              v[4 * j + 1] += rv[j].y;
+              v[4 * j + 2] += rv[j].z;
+              v[4 * j + 3] += rv[j].w;
+            }
+          }
           if (row_ok) {
-            if (p.resid != nullptr) {
+            if (EPI != kEpiStoreResidTma && p.resid != nullptr) {
               const float4* rs = reinterpret_cast<const float4*>(p.resid + grow * p.ld_resid + col);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -532,7 +576,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 
 template <int BN, int EPI>
 static int launch_gemm(const aph_gemm_args* a, GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EPI>;
   CUtensorMap tm_a, tm_b;
   const int k_seq = a->k_seq;
   const int k_batch = a->k_batch > 0 ? a->k_batch : 1;
@@ -591,6 +635,18 @@ static int launch_gemm(const aph_gemm_args* a, GemmParams& p, cudaStream_t strea
                          f32 ? static_cast<const void*>(a->out_f32) : a->out_bf16, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != APH_OK) return rc;
   }
+  CUtensorMap tm_resid;
+  memset(&tm_resid, 0, sizeof(tm_resid));
+  if (EPI == kEpiStoreResidTma) {
+    const uint64_t ld = static_cast<uint64_t>(a->ld_resid);
+    const uint64_t dims[3] = {static_cast<uint64_t>(p.n), static_cast<uint64_t>(a->a_rows), static_cast<uint64_t>(a->batch)};
+    uint64_t batch_stride = static_cast<uint64_t>(a->out_batch_rows) * ld * 4;
+    if (a->batch == 1 || batch_stride == 0) batch_stride = static_cast<uint64_t>(a->a_rows) * ld * 4;
+    const uint64_t strides[2] = {ld * 4, batch_stride};
+    const uint32_t box[3] = {32u, 32u, 1u};
+    int rc = encode_tmap(&tm_resid, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, a->resid, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != APH_OK) return rc;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     APH_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI>,
@@ -622,7 +678,7 @@ static int launch_gemm(const aph_gemm_args* a, GemmParams& p, cudaStream_t strea
   }
   const int total_work = p.diag_taps > 0 ? m_pairs * p.diag_taps : m_pairs * p.n_tiles * p.split_k;
   const int grid = 2 * (total_work < max_clusters ? total_work : max_clusters);
-  gemm_bf16_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, tm_out, p);
+  gemm_bf16_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, tm_out, tm_resid, p);
   APH_POST_LAUNCH(1);
   return APH_OK;
 }
@@ -717,6 +773,7 @@ extern "C" int aph_gemm_bf16(const aph_gemm_args* a, void* stream_) {
     APH_REQUIRE(a->epilogue == APH_EPI_STORE, "taps mode supports the store epilogue only");
     p.n_tiles = a->n / 64;
     p.staged = a->out_f32 ? 1 : 0;  // 64-column tiles: only the fp32 staging granularity (32 columns) fits
+    if (a->resid && p.staged == 1) return launch_gemm<64, kEpiStoreResidTma>(a, p, stream);
     return launch_gemm<64, APH_EPI_STORE>(a, p, stream);
   }
   APH_REQUIRE(mn || a->a_inner >= a->k, "A rows shorter than k");
@@ -743,6 +800,8 @@ extern "C" int aph_gemm_bf16(const aph_gemm_args* a, void* stream_) {
   p.staged = a->out_f32 ? 1 : 2;
   if (a->n > 128) {
     p.n_tiles = ceil_div(a->n, 256);
+    // fp32 output with a residual (out-proj, FFN2, gradient accumulation): the residual comes in through TMA
+    if (a->resid && p.staged == 1 && !a->a_mn_major) return launch_gemm<256, kEpiStoreResidTma>(a, p, stream);
     return launch_gemm<256, APH_EPI_STORE>(a, p, stream);
   } else if (a->n > 64 || a->b_mn_major) {  // an MN-major B tile needs at least one 64-column chunk per CTA
     p.n_tiles = 1;
