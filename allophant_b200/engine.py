@@ -25,6 +25,20 @@ from . import _lib, ops
 from .network.wav2vec2 import Wav2Vec2EncoderConfig, Wav2Vec2Weights
 
 
+# Bumped by optimisers that update parameters through raw pointers (allophant_b200.optim.FusedAdam): torch's version
+# counters do not see such writes, so the packed bf16 operands key on this number as well.
+_WEIGHT_GENERATION = 0
+
+
+def bump_weight_generation() -> None:
+    global _WEIGHT_GENERATION
+    _WEIGHT_GENERATION += 1
+
+
+def weight_generation() -> int:
+    return _WEIGHT_GENERATION
+
+
 def conv_out_length(length: int, kernel: int, stride: int) -> int:
     return (length - kernel) // stride + 1
 
@@ -39,14 +53,22 @@ def frames_for(samples: int, cfg: Wav2Vec2EncoderConfig) -> List[int]:
 
 
 class PackedEncoder:
-    """bf16 GEMM operands packed from the fp32 master parameters (re-packed when they change)."""
+    """bf16 GEMM operands packed from the fp32 master parameters.
+
+    The operand buffers are allocated once per parameter layout (``layout_id``) and REFILLED in place when the
+    parameters change, so the launch lists of the ``EncoderPlan``s (which hold raw pointers) stay valid across
+    optimiser steps.  With ``allophant_b200.optim.FusedAdam`` the Linear operands are not even refilled: the Adam
+    kernel writes the bf16 copy itself (``shadow_map``), and ``after_fused_step`` refreshes the few derived tensors
+    (fused QKV bias, weight-normed positional conv)."""
 
     def __init__(self, weights: Wav2Vec2Weights) -> None:
         self.weights = weights
         self.cfg = weights.config
         self._version: Optional[Tuple[int, ...]] = None
         self._params: Optional[List[Tensor]] = None
+        self._pointers: Optional[Tuple[int, ...]] = None
         self.device: Optional[torch.device] = None
+        self.layout_id = 0
 
     def _current_version(self) -> Tuple[int, ...]:
         def version(p: Tensor) -> int:
@@ -58,70 +80,131 @@ class PackedEncoder:
         params = self._params
         if params is None:  # the module tree is fixed after construction: walk it once
             params = self._params = list(self.weights.parameters())
-        return tuple(version(p) for p in params) + tuple(p.data_ptr() for p in params)
+        return (weight_generation(),) + tuple(version(p) for p in params) + tuple(p.data_ptr() for p in params)
 
     def ensure(self) -> None:
         version = self._current_version()
         if version != self._version:
-            self._pack()
+            pointers = tuple(p.data_ptr() for p in self._params or [])
+            if pointers != self._pointers:  # first use, or the parameters moved (``.to(device)``, ``load_state_dict`` keeps them)
+                self._allocate()
+                self._pointers = pointers
+            self._fill()
             self._version = version
 
     @torch.no_grad()
-    def _pack(self) -> None:
-        w = self.weights
-        cfg = self.cfg
+    def _allocate(self) -> None:
+        w, cfg = self.weights, self.cfg
         first = next(w.parameters())
         if not first.is_cuda:
             raise RuntimeError("allophant_b200 runs on CUDA only: move the model to a GPU (`model.to('cuda')`)")
-        self.device = first.device
+        self.device = dev = first.device
         if cfg.hidden_size % 256 != 0 or cfg.head_dim != 64:
             raise NotImplementedError("the CUDA encoder supports head_dim 64 and hidden sizes that are multiples of 256")
         if any(c != 512 for c in cfg.conv_dim) or cfg.conv_kernel[0] != 10 or cfg.conv_stride[0] != 5:
             raise NotImplementedError("the CUDA feature extractor supports the wav2vec2 layout (7 x 512 channels, k0=10, s0=5)")
 
-        def f32(p: Tensor) -> Tensor:
+        def f32(p: Tensor) -> Tensor:  # fp32 contiguous parameters are used in place (no copy): always current
             return p.detach().float().contiguous()
 
+        bf16 = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.bfloat16)  # noqa: E731
+        H, FF = cfg.hidden_size, cfg.intermediate_size
         fe = w.feature_extractor.conv_layers
         self.conv0_w = f32(fe[0].conv.weight).view(512, 10)
         self.conv_bias = [f32(l.conv.bias) if l.conv.bias is not None else None for l in fe]
         self.conv_ln = [(f32(l.layer_norm.weight), f32(l.layer_norm.bias)) if hasattr(l, "layer_norm") else None for l in fe]
-        self.conv_w = [None] + [ops.pack_conv_weight(l.conv.weight) for l in fe[1:]]
+        self.conv_w = [None] + [bf16(l.conv.weight.shape[0], l.conv.weight.shape[2] * l.conv.weight.shape[1]) for l in fe[1:]]
         fp = w.feature_projection
         self.fp_ln = (f32(fp.layer_norm.weight), f32(fp.layer_norm.bias))
-        self.fp_w = ops.cast_bf16(fp.projection.weight)
+        self.fp_w = bf16(H, 512)
         self.fp_b = f32(fp.projection.bias)
         pc = w.encoder.pos_conv_embed.conv
-        self.pos_w = ops.pack_posconv_weight(pc.parametrizations.weight.original0, pc.parametrizations.weight.original1)
+        v = pc.parametrizations.weight.original1
+        self.pos_w = bf16(v.shape[0], v.shape[2] * v.shape[1])
         self.pos_b = f32(pc.bias)
         self.layers = []
         for layer in w.encoder.layers:
             att = layer.attention
-            wqkv = torch.cat([att.q_proj.weight.detach(), att.k_proj.weight.detach(), att.v_proj.weight.detach()], 0)
-            bqkv = torch.cat([att.q_proj.bias.detach(), att.k_proj.bias.detach(), att.v_proj.bias.detach()], 0)
             self.layers.append(
                 dict(
                     ln1=(f32(layer.layer_norm.weight), f32(layer.layer_norm.bias)),
-                    wqkv=ops.cast_bf16(wqkv),
-                    bqkv=f32(bqkv),
-                    wo=ops.cast_bf16(att.out_proj.weight),
+                    wqkv=bf16(3 * H, H),
+                    bqkv=torch.empty(3 * H, device=dev, dtype=torch.float32),
+                    wo=bf16(H, H),
                     bo=f32(att.out_proj.bias),
                     ln2=(f32(layer.final_layer_norm.weight), f32(layer.final_layer_norm.bias)),
-                    w1=ops.cast_bf16(layer.feed_forward.intermediate_dense.weight),
+                    w1=bf16(FF, H),
                     b1=f32(layer.feed_forward.intermediate_dense.bias),
-                    w2=ops.cast_bf16(layer.feed_forward.output_dense.weight),
+                    w2=bf16(H, FF),
                     b2=f32(layer.feed_forward.output_dense.bias),
                 )
             )
         self.final_ln = (f32(w.encoder.layer_norm.weight), f32(w.encoder.layer_norm.bias))
         self._pos_w_dgrad: Optional[Tensor] = None
+        self._pos_w_dgrad_valid = False
+        self.layout_id += 1
+
+    @torch.no_grad()
+    def _fill_derived(self) -> None:
+        """Operands that are functions of several parameters: fused QKV bias, weight-normed positional conv."""
+        w, H = self.weights, self.cfg.hidden_size
+        pc = w.encoder.pos_conv_embed.conv
+        ops.pack_posconv_weight(pc.parametrizations.weight.original0, pc.parametrizations.weight.original1, dst=self.pos_w)
+        self._pos_w_dgrad_valid = False
+        for layer, packed in zip(w.encoder.layers, self.layers):
+            att = layer.attention
+            for part, linear in enumerate((att.q_proj, att.k_proj, att.v_proj)):
+                packed["bqkv"][part * H : (part + 1) * H].copy_(linear.bias.detach())
+
+    @torch.no_grad()
+    def _fill(self) -> None:
+        w, H = self.weights, self.cfg.hidden_size
+        fe = w.feature_extractor.conv_layers
+        for index, layer in enumerate(fe[1:], start=1):
+            ops.pack_conv_weight(layer.conv.weight, dst=self.conv_w[index])
+        ops.cast_bf16(w.feature_projection.projection.weight, dst=self.fp_w)
+        for layer, packed in zip(w.encoder.layers, self.layers):
+            att = layer.attention
+            for part, linear in enumerate((att.q_proj, att.k_proj, att.v_proj)):
+                ops.cast_bf16(linear.weight, dst=packed["wqkv"][part * H : (part + 1) * H])
+            ops.cast_bf16(att.out_proj.weight, dst=packed["wo"])
+            ops.cast_bf16(layer.feed_forward.intermediate_dense.weight, dst=packed["w1"])
+            ops.cast_bf16(layer.feed_forward.output_dense.weight, dst=packed["w2"])
+        self._fill_derived()
+
+    # -- fused optimiser support ---------------------------------------------------------------
+    def shadow_map(self) -> Dict[Tensor, Tensor]:
+        """parameter -> bf16 operand (same shape, contiguous) that ``FusedAdam`` keeps up to date itself."""
+        self.ensure()
+        H = self.cfg.hidden_size
+        mapping: Dict[Tensor, Tensor] = {self.weights.feature_projection.projection.weight: self.fp_w}
+        for layer, packed in zip(self.weights.encoder.layers, self.layers):
+            att = layer.attention
+            for part, linear in enumerate((att.q_proj, att.k_proj, att.v_proj)):
+                mapping[linear.weight] = packed["wqkv"][part * H : (part + 1) * H]
+            mapping[att.out_proj.weight] = packed["wo"]
+            mapping[layer.feed_forward.intermediate_dense.weight] = packed["w1"]
+            mapping[layer.feed_forward.output_dense.weight] = packed["w2"]
+        return mapping
+
+    def after_fused_step(self) -> None:
+        """Called by ``FusedAdam`` after a step that wrote every shadowed operand: refresh the derived tensors and
+        mark the pack as current (the convolutional feature extractor is frozen or, if it trains, refilled)."""
+        if any(p.requires_grad for p in self.weights.feature_extractor.parameters()):
+            self._version = None  # conv operands are not shadowed: full refill on next use
+            return
+        self._fill_derived()
+        self._version = self._current_version()
 
     @property
     def pos_w_dgrad(self) -> Tensor:
         """B operand of the positional conv's data-gradient GEMM, packed on first use (training only)."""
-        if self._pos_w_dgrad is None:
-            pc = self.weights.encoder.pos_conv_embed.conv
-            self._pos_w_dgrad = ops.pack_posconv_weight_dgrad(pc.parametrizations.weight.original0, pc.parametrizations.weight.original1)
+        pc = self.weights.encoder.pos_conv_embed.conv
+        if self._pos_w_dgrad is None or not self._pos_w_dgrad_valid:
+            self._pos_w_dgrad = ops.pack_posconv_weight_dgrad(
+                pc.parametrizations.weight.original0, pc.parametrizations.weight.original1, dst=self._pos_w_dgrad
+            )
+            self._pos_w_dgrad_valid = True
         return self._pos_w_dgrad
 
 

@@ -134,7 +134,9 @@ class HeadsRuntime:
         params = getattr(self, "_projection_params", None)
         if params is None:
             params = self._projection_params = list(self.model._projection.parameters())
-        return tuple(_version(p) for p in params) + tuple(p.data_ptr() for p in params)
+        from .engine import weight_generation
+
+        return (weight_generation(),) + tuple(_version(p) for p in params) + tuple(p.data_ptr() for p in params)
 
     @torch.no_grad()
     def _ensure_weights(self, device: torch.device) -> None:

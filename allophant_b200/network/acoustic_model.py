@@ -353,15 +353,15 @@ class Wav2Vec2AcousticModel(AcousticModel):
         self._packed.ensure()
         key = (n_utt, samples, ldx, tuple(sorted(hidden_blocks.items())), training)
         plan = self._plans.get(key)
-        if plan is None or plan.packed_version != self._packed._version:
+        if plan is None or plan.layout_id != self._packed.layout_id:
             if plan is None and len(self._plans) >= 4:  # workspaces are large: keep a handful of shapes
                 self._plans.pop(next(iter(self._plans)))
-            if plan is not None and plan.packed_version != self._packed._version:
-                # same shape, new weights (an optimizer step): keep the workspaces, rebuild the launch list only
+            if plan is not None:
+                # same shape, re-allocated operands (the parameters moved): keep the workspaces, rebuild the launch list
                 plan.rebind(self._packed)
             else:
                 plan = EncoderPlan(self._packed, n_utt, samples, ldx, hidden_blocks, self._normalize, self._use_attention_mask, training)
-            plan.packed_version = self._packed._version
+            plan.layout_id = self._packed.layout_id
             self._plans[key] = plan
         return plan
 

@@ -525,23 +525,25 @@ def cast_bf16_2d(src: Tensor, ld_src: int, dst: Tensor, ld_dst: int, rows: int, 
     check(lib.aph_cast_bf16_2d(src.data_ptr(), ld_src, dst.data_ptr(), ld_dst, rows, cols, _stream()), "aph_cast_bf16_2d")
 
 
-def pack_conv_weight(weight: Tensor) -> Tensor:
+def pack_conv_weight(weight: Tensor, dst: Optional[Tensor] = None) -> Tensor:
     """Conv1d weight [O, C, k] fp32 -> bf16 [O, k*C]."""
-    _require_cuda(weight)
+    _require_cuda(weight, dst)
     w = weight.detach().float().contiguous()
     o, c, k = w.shape
-    dst = torch.empty(o, k * c, device=w.device, dtype=torch.bfloat16)
+    if dst is None:
+        dst = torch.empty(o, k * c, device=w.device, dtype=torch.bfloat16)
     check(lib.aph_pack_conv_weight(w.data_ptr(), dst.data_ptr(), o, c, k, _stream()), "aph_pack_conv_weight")
     return dst
 
 
-def pack_posconv_weight(weight_g: Tensor, weight_v: Tensor) -> Tensor:
+def pack_posconv_weight(weight_g: Tensor, weight_v: Tensor, dst: Optional[Tensor] = None) -> Tensor:
     """weight-normed grouped conv weight -> bf16 [O, k*Cg] (tap-major)."""
-    _require_cuda(weight_g, weight_v)
+    _require_cuda(weight_g, weight_v, dst)
     g = weight_g.detach().float().contiguous()
     v = weight_v.detach().float().contiguous()
     o, cg, k = v.shape
-    dst = torch.empty(o, k * cg, device=v.device, dtype=torch.bfloat16)
+    if dst is None:
+        dst = torch.empty(o, k * cg, device=v.device, dtype=torch.bfloat16)
     scratch = torch.empty(k, device=v.device, dtype=torch.float32)
     check(lib.aph_pack_posconv_weight(g.data_ptr(), v.data_ptr(), dst.data_ptr(), scratch.data_ptr(), o, cg, k, _stream()), "aph_pack_posconv_weight")
     return dst
@@ -634,13 +636,14 @@ def gelu_backward_bf16(dy: Tensor, ld_dy: int, pre: Tensor, ld_pre: int, rows: i
     check(lib.aph_gelu_backward_bf16(dy.data_ptr(), ld_dy, pre.data_ptr(), ld_pre, rows, cols, out.data_ptr(), ld_out, _stream()), "aph_gelu_backward_bf16")
 
 
-def pack_posconv_weight_dgrad(weight_g: Tensor, weight_v: Tensor) -> Tensor:
+def pack_posconv_weight_dgrad(weight_g: Tensor, weight_v: Tensor, dst: Optional[Tensor] = None) -> Tensor:
     """B operand of the positional conv's data-gradient GEMM (taps flipped, in/out channels swapped)."""
-    _require_cuda(weight_g, weight_v)
+    _require_cuda(weight_g, weight_v, dst)
     g = weight_g.detach().float().contiguous()
     v = weight_v.detach().float().contiguous()
     o, cg, k = v.shape
-    dst = torch.empty(o, k * cg, device=v.device, dtype=torch.bfloat16)
+    if dst is None:
+        dst = torch.empty(o, k * cg, device=v.device, dtype=torch.bfloat16)
     scratch = torch.empty(2 * k, device=v.device, dtype=torch.float32)
     check(lib.aph_pack_posconv_weight_dgrad(g.data_ptr(), v.data_ptr(), dst.data_ptr(), scratch.data_ptr(), o, cg, k, _stream()), "aph_pack_posconv_weight_dgrad")
     return dst

@@ -518,6 +518,10 @@ def run_train_arm(args) -> None:
     labels_dev = {name: value.to(device) for name, value in labels_host.items()}
     label_lengths_dev = {name: value.to(device) for name, value in label_lengths_host.items()}
     parameters = [parameter for parameter in model.parameters() if parameter.requires_grad]
+    from allophant_b200 import optim
+
+    # default_config.toml:107-121: Adam(0.9, 0.98), lr 1e-3 under the warm-up schedule; global-norm clipping folded into the Adam pass
+    optimizer = optim.adam_from_config(parameters, model.d_model, model=model)
 
     def step(batch, labels, label_lengths):
         for parameter in parameters:
@@ -531,6 +535,7 @@ def run_train_arm(args) -> None:
         count = global_label_count([label_lengths[name] for name in order])  # all-reduced scalar: the loss normaliser of the WHOLE batch
         loss = losses.sum() / count.to(losses.dtype)
         loss.backward()
+        optimizer.step(clip_norm=1.0)
         return loss
 
     def device_step():
@@ -637,7 +642,7 @@ def run_train_arm(args) -> None:
     if rank != 0:
         return
     line = {
-        "metric": "audio-sec/sec, multitask training step (forward + multi-head CTC + backward + gradient all-reduce)",
+        "metric": "audio-sec/sec, multitask training step (forward + multi-head CTC + backward + gradient all-reduce + optimizer)",
         "value": audio_seconds / (elapsed_ms / 1000.0),
         "unit": UNIT,
         "n_gpus": world,
@@ -652,8 +657,8 @@ def run_train_arm(args) -> None:
         "config": {
             "workload": "BASELINE configs[2]: Allophant Multitask (XLS-R-300M shape, random init, allophone layer over "
             f"{TRAIN_LANGUAGES} languages x {TRAIN_PHONES} phones, feature extractor frozen) training step: forward + 37-head CTC + backward"
-            f"{' + overlapped NCCL gradient all-reduce' if distributed else ''}; {TRAIN_BATCH} utterances per GPU, U[3 s, 15 s], eval-mode arithmetic "
-            "(no dropout / SpecAugment), no optimizer step",
+            f"{' + overlapped NCCL gradient all-reduce' if distributed else ''} + global-norm clip + Adam + warm-up LR; {TRAIN_BATCH} utterances per GPU, "
+            "U[3 s, 15 s], eval-mode arithmetic (no dropout / SpecAugment)",
             "batch_per_gpu": TRAIN_BATCH,
             "padded_seconds": samples / SAMPLE_RATE,
             "parallelism": f"dp{world}",

@@ -359,6 +359,24 @@ int aph_softmax_backward_cols(const float* grad_x, int64_t ld_gx, const void* x_
                               const int32_t* dst_col, int32_t n_deps, int32_t skip,
                               float* grad_logits, int64_t ld_gl, void* stream);
 
+/* ---- optimiser step (estimator.py:778-791; config.py:316-335) ------------------------------ */
+/* Multi-tensor kernels: `tensors_host` / `sizes_host` are HOST arrays of device pointers and element counts (the
+ * descriptors travel in the kernel parameters, up to 48 tensors per launch); all tensors are contiguous fp32.
+ * aph_multi_tensor_sumsq: *out (device double) = sum over all tensors of x^2 (nn.utils.clip_grad_norm_, norm 2).
+ * aph_multi_tensor_scale: x *= min(1, max_norm / (sqrt(*sumsq) + 1e-6)) in place (the clip itself).
+ * aph_multi_tensor_adam: torch.optim.Adam(betas, eps, weight_decay as L2 added to the gradient) for step `step`
+ *   (1-based); tensors_host is [n][4] = {param, grad, exp_avg, exp_avg_sq}; shadow_bf16_host[n] (entries may be
+ *   NULL) receive the updated parameter rounded to bf16 (the GEMM operand copy); with clip_sumsq != NULL the
+ *   gradients are scaled by the clip coefficient on the fly instead of in place. */
+int aph_multi_tensor_sumsq(void* const* tensors_host, const int64_t* sizes_host, int32_t n_tensors,
+                           double* out, void* stream);
+int aph_multi_tensor_scale(void* const* tensors_host, const int64_t* sizes_host, int32_t n_tensors,
+                           const double* sumsq, float max_norm, void* stream);
+int aph_multi_tensor_adam(void* const* tensors_host, void* const* shadow_bf16_host,
+                          const int64_t* sizes_host, int32_t n_tensors, float lr, float beta1,
+                          float beta2, float eps, float weight_decay, int64_t step,
+                          const double* clip_sumsq, float max_norm, void* stream);
+
 /* ---- edit distance (host) --------------------------------------------------------- */
 /* Batched replacement of the Rust extension `allophant.phonemes` (src/edit_distance.rs):
  * levensthein (70-96) and levensthein_statistics (601-608 -> 372-481, uniform costs 483-496)

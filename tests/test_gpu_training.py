@@ -372,3 +372,72 @@ def test_backward_after_overwrite_raises(training_case):
     model(batch)
     with pytest.raises(RuntimeError, match="overwritten"):
         next(iter(first.outputs.values())).sum().backward()
+
+
+# ------------------------------------------------------------------------------------------ optimiser step
+def test_fused_adam_and_clipping_match_torch():
+    """FusedAdam / clip_grad_norm_ (multi-tensor kernels) against torch.optim.Adam / nn.utils.clip_grad_norm_ on the same
+    parameters and gradients: fp32 arithmetic, 1e-6 relative."""
+    from allophant_b200 import optim
+
+    torch.manual_seed(11)
+    shapes = [(1024, 1024), (4096,), (3, 5, 7), (1,), (300, 1024)] + [(17,)] * 60  # more tensors than one launch packs
+    ours = [torch.nn.Parameter(torch.randn(*shape, device=DEV)) for shape in shapes]
+    theirs = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    fused = optim.FusedAdam(ours, lr=3e-3, betas=(0.9, 0.98), weight_decay=0.01)
+    shadow = torch.zeros(1024, 1024, device=DEV, dtype=torch.bfloat16)
+    fused.shadow[ours[0]] = shadow
+    reference = torch.optim.Adam(theirs, lr=3e-3, betas=(0.9, 0.98), weight_decay=0.01)
+    for step in range(4):
+        grads = [torch.randn_like(p) * (10.0 if step == 1 else 0.01) for p in ours]
+        for p, q, g in zip(ours, theirs, grads):
+            p.grad = g.clone()
+            q.grad = g.clone()
+        if step % 2 == 0:  # in-place clipping, then a plain step
+            norm = optim.clip_grad_norm_(ours, 1.5)
+            norm_ref = torch.nn.utils.clip_grad_norm_(theirs, 1.5)
+            assert abs(float(norm) - float(norm_ref)) <= 1e-5 * float(norm_ref)
+            for p, q in zip(ours, theirs):
+                assert range_err(p.grad, q.grad) < 1e-6
+            fused.step()
+        else:  # clipping folded into the Adam pass
+            torch.nn.utils.clip_grad_norm_(theirs, 1.5)
+            fused.step(clip_norm=1.5)
+        reference.step()
+        for index, (p, q) in enumerate(zip(ours, theirs)):
+            assert range_err(p, q) < 1e-5, (step, index)
+    assert torch.equal(shadow, ours[0].detach().bfloat16())
+    state = fused.state_dict()
+    assert set(state["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and float(state["state"][0]["step"]) == 4.0
+    torch.optim.Adam(theirs, lr=3e-3, betas=(0.9, 0.98)).load_state_dict(state)  # interchangeable with torch's state layout
+
+
+def test_training_loop_with_fused_optimizer_reduces_the_loss(training_case):
+    """A few full steps (forward, multi-head CTC, backward, clip + Adam, warm-up schedule): the packed bf16 operands follow the
+    updated fp32 parameters and the loss goes down."""
+    from allophant_b200 import optim
+
+    if training_case["name"] != "multitask_2layer":
+        pytest.skip("one architecture is enough")
+    fixture, model = training_case["fixture"], training_case["model"]
+    saved = {name: value.detach().clone() for name, value in model.state_dict().items()}
+    try:
+        parameters = [p for p in model.parameters() if p.requires_grad]
+        # peak rate 0.01 * 1024^-0.5 * 2^-0.5 = 2.2e-4: Adam moves every weight by about the rate per step
+        optimizer = optim.adam_from_config(parameters, model.d_model, model=model, warmup_steps=2, constant_steps=100, factor=0.01)
+        losses = []
+        for _ in range(4):
+            loss, _, _ = _training_step(model, training_case["batch"], fixture)
+            losses.append(float(loss))
+            optimizer.step(clip_norm=1.0)
+        print("losses", losses, "lr", optimizer.current_learning_rate())
+        assert all(torch.isfinite(torch.tensor(losses)))
+        assert losses[-1] < losses[0]
+        # the bf16 operands written by the Adam kernel are the rounded fp32 masters
+        packed = model.acoustic_model._packed
+        layer0 = model.acoustic_model.model.encoder.layers[0]
+        assert torch.equal(packed.layers[0]["w1"], layer0.feed_forward.intermediate_dense.weight.detach().bfloat16())
+        assert torch.equal(packed.layers[0]["wqkv"][1024:2048], layer0.attention.k_proj.weight.detach().bfloat16())
+        assert torch.equal(packed.layers[0]["bqkv"][:1024], layer0.attention.q_proj.bias.detach())
+    finally:
+        model.load_state_dict(saved)

@@ -133,3 +133,33 @@ def test_error_behaviour_mirrors_reference():
     with pytest.raises(ValueError, match="requires an attribute indexer"):
         HierarchicalProjection(1024, AttributeGraph([AttributeNode("phoneme", 3, None, ["OUTPUT"])]), 1,
                                embedding_composition_config=EmbeddingCompositionConfig(64))  # fmt: skip
+
+
+def test_warmup_schedule_matches_the_reference():
+    """WarmupScheduler (config.py:107-173) against learning rates produced by the unmodified reference class
+    (tests/golden/warmup_schedule.json, generated through oracle/reference_shim.py)."""
+    import json
+    import os
+
+    import torch
+
+    from allophant_b200.optim import WarmupInfo, WarmupScheduler
+
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "warmup_schedule.json")))
+    optimizer = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1.0)
+    scheduler = WarmupScheduler(optimizer, WarmupInfo(golden["model_size"]), golden["warmup_steps"], golden["constant_steps"], golden["factor"])
+    wanted = dict(zip(golden["steps"], golden["rates"]))
+    step = 1
+    assert scheduler.last_lr == wanted[1] and optimizer.param_groups[0]["lr"] == wanted[1]
+    while step < max(wanted):
+        scheduler.step()
+        step += 1
+        if step in wanted:
+            assert scheduler.last_lr == wanted[step], step
+            assert optimizer.param_groups[0]["lr"] == wanted[step]
+    state = scheduler.state_dict()
+    other = WarmupScheduler(optimizer, WarmupInfo(golden["model_size"]), golden["warmup_steps"], golden["constant_steps"], golden["factor"])
+    other.load_state_dict(state)
+    other.step()
+    scheduler.step()
+    assert other.last_lr == scheduler.last_lr
