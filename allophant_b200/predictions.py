@@ -32,7 +32,8 @@ def _pinned_like(tensor: Tensor, slot: int) -> Tensor:
     key = (tuple(tensor.shape), tensor.dtype)
     ring = _PINNED.setdefault(key, [])
     while len(ring) <= slot:
-        ring.append(torch.empty(tensor.shape, dtype=tensor.dtype, pin_memory=True))
+        with torch.inference_mode(False):  # the buffers outlive this call: they must not become inference tensors
+            ring.append(torch.empty(tensor.shape, dtype=tensor.dtype, pin_memory=True))
     return ring[slot]
 
 
