@@ -440,3 +440,29 @@ def test_ctc_long_labels_and_empty_targets():
         # size-independent property: on valid frames the gradient rows of a finite loss sum to zero
         row_sums = leaves[head].grad.sum(-1).cpu()
         assert float(row_sums.abs().max()) < 5e-3  # |nll| ~ 1e3 in fp32: 1e-6 relative on nll = 1e-3 on sum(gamma)
+
+
+def test_custom_ops_run_the_library_kernels():
+    """torch.ops.allophant_b200.* against torch's own ops (and autograd through log_softmax)."""
+    import allophant_b200.custom_ops  # noqa: F401  (registers the ops)
+
+    torch.manual_seed(5)
+    x = torch.randn(50, 3, 40, device=DEV, requires_grad=True)
+    out = torch.ops.allophant_b200.log_softmax(x)
+    assert range_err(out, F.log_softmax(x.detach(), -1)) < 1e-5
+    grad = torch.randn_like(out)
+    out.backward(grad)
+    reference = x.detach().clone().requires_grad_(True)
+    F.log_softmax(reference, -1).backward(grad)
+    assert range_err(x.grad, reference.grad) < 1e-5
+    weight, bias = torch.randn(64, 40, device=DEV) * 0.1, torch.randn(64, device=DEV)
+    linear = torch.ops.allophant_b200.linear_bf16(x.detach(), weight, bias, False)
+    assert range_err(linear, F.linear(x.detach().bfloat16().float(), weight.bfloat16().float(), bias)) < 1e-4
+    wide = torch.randn(33, 1024, device=DEV)
+    gamma, beta = torch.randn(1024, device=DEV), torch.randn(1024, device=DEV)
+    assert range_err(torch.ops.allophant_b200.layer_norm(wide, gamma, beta, 1e-5), F.layer_norm(wide, (1024,), gamma, beta, 1e-5)) < 1e-5
+    labels = torch.randint(1, 40, (3, 9), device=DEV)
+    lengths, label_lengths = torch.tensor([50, 40, 30], device=DEV), torch.tensor([9, 5, 1], device=DEV)
+    nll = torch.ops.allophant_b200.ctc_nll(out.detach(), labels, lengths, label_lengths)
+    reference = F.ctc_loss(out.detach().cpu(), labels.cpu(), lengths.cpu(), label_lengths.cpu(), reduction="none")
+    assert range_err(nll, reference) < 1e-4

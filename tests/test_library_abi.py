@@ -67,3 +67,23 @@ def test_product_never_imports_the_oracle():
             if name.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(directory, name), errors="replace").read()
                 assert "import oracle" not in text and "from oracle" not in text, f"{name} imports the oracle"
+
+
+def test_custom_ops_are_registered_with_fake_kernels():
+    """The C-ABI entry points a user composes by hand are PyTorch custom ops (namespace allophant_b200) with fake kernels,
+    and have no CPU implementation."""
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    from allophant_b200 import custom_ops
+
+    for name in custom_ops.REGISTERED:
+        assert hasattr(torch.ops.allophant_b200, name)
+    with FakeTensorMode():
+        x = torch.empty(7, 3, 40, device="cuda")
+        assert torch.ops.allophant_b200.log_softmax(x).shape == (7, 3, 40)
+        assert torch.ops.allophant_b200.linear_bf16(x, torch.empty(16, 40, device="cuda"), None, True).shape == (7, 3, 16)
+        assert torch.ops.allophant_b200.ctc_nll(x, torch.empty(3, 5, dtype=torch.long, device="cuda"), torch.empty(3, dtype=torch.long, device="cuda"),
+                                                 torch.empty(3, dtype=torch.long, device="cuda")).shape == (3,)  # fmt: skip
+    with pytest.raises(NotImplementedError):
+        torch.ops.allophant_b200.log_softmax(torch.zeros(2, 3))
