@@ -101,8 +101,8 @@ _F = c_float
 # name -> argtypes; every function returns int (APH_OK or a negative APH_ERR_* code)
 _SIGNATURES = {
     "aph_gemm_bf16": [POINTER(GemmArgs), _P],
-    "aph_attention_bf16": [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
-    "aph_attention_bf16_lse": [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
+    "aph_attention_bf16": [_P, _P, _P, _P, _P, _I32, _I32, _I32, _P],
+    "aph_attention_bf16_lse": [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P],
     "aph_attention_backward_bf16": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P],
     "aph_debug_set_progress": [_P],
     "aph_debug_set_timeline": [_P],

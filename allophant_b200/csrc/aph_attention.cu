@@ -9,8 +9,9 @@
 // keeps the four softmax warps of a CTA busy all the time:
 //   warps 0..3  softmax: one query row per thread; the 64 scores of a block are read from TMEM once
 //               and stay in registers (max, exp2, row sum, bf16 pack -> 128B-swizzled smem)
-//   warp 4      TMA producer: Q once, then K_j [64 keys x 64] and Vt_j [64 x 64 keys] through two
-//               independent 3-stage rings (a K tile is released as soon as its scores are issued)
+//   warp 4      TMA producer: Q once, then K_j and V_j [64 keys x 64] through two independent 3-stage
+//               rings (a K tile is released as soon as its scores are issued); V stays row-major and is
+//               read by O += P V as an MN-major B operand, so no transposed copy of V exists anywhere
 //   warp 5      TMEM allocator + single-thread tcgen05.mma issuer
 //   * scores run TWO blocks ahead: S is double-buffered in TMEM and S_{j+2} = Q K_{j+2}^T is issued the
 //     moment the softmax warps have read S_j, so its latency hides behind the softmax of block j+1;
@@ -136,13 +137,14 @@ __global__ void __launch_bounds__(kAttThreads, 2)
         tma_load_3d(s_k + st * kAttKVBytes, &tm_k, &k_full[st], 0, j * kAttKV, bh);
         mbar_wait(&v_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&v_full[st], kAttKVBytes);
-        tma_load_3d(s_v + st * kAttKVBytes, &tm_v, &v_full[st], j * kAttKV, 0, bh);
+        tma_load_3d(s_v + st * kAttKVBytes, &tm_v, &v_full[st], 0, j * kAttKV, bh);
       }
     }
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64) | kIdescBMnMajor;  // B = V [key rows][64 d]: N contiguous
       const uint64_t dq = umma_desc_sw128(smem_u32(s_q));
       mbar_wait(q_full, 0);
       APH_STAMP(2);
@@ -166,10 +168,10 @@ __global__ void __launch_bounds__(kAttThreads, 2)
         mbar_wait(&v_full[st], static_cast<uint32_t>(j / kAttStages) & 1u);
         tc_fence_after();
         const uint64_t dp = umma_desc_sw128(smem_u32(s_p + (j & 1) * kAttPBytes));
-        const uint64_t dv = umma_desc_sw128(smem_u32(s_v + st * kAttKVBytes));
+        const uint64_t dv = umma_desc_mn_sw128(smem_u32(s_v + st * kAttKVBytes), kAttKVBytes);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_o, dp + static_cast<uint64_t>(2 * k), dv + static_cast<uint64_t>(2 * k), idesc, (j | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k)  // 16 keys per UMMA_K step: +32 bytes along P's rows, +16 rows (2 KB) of V
+          umma_bf16(tmem_o, dp + static_cast<uint64_t>(2 * k), dv + static_cast<uint64_t>(128 * k), idesc_pv, (j | k) != 0 ? 1u : 0u);
         umma_commit(&o_full[j & 1]);
         umma_commit(&v_empty[st]);
         // S_{j+2} is issued AFTER PV_j and reuses the TMEM buffer of S_j.  tcgen05 operations of one thread complete
@@ -314,20 +316,17 @@ extern "C" int aph_debug_set_timeline(int64_t* device_buffer) {
   return APH_OK;
 }
 
-extern "C" int aph_attention_bf16(const void* q, const void* k, const void* vt, void* ctx,
-                                  const int32_t* lengths, int32_t n_utt, int32_t heads, int32_t T,
-                                  int32_t t_v, void* stream_) {
-  return aph_attention_bf16_lse(q, k, vt, ctx, nullptr, lengths, n_utt, heads, T, t_v, stream_);
+extern "C" int aph_attention_bf16(const void* q, const void* k, const void* v, void* ctx,
+                                  const int32_t* lengths, int32_t n_utt, int32_t heads, int32_t T, void* stream_) {
+  return aph_attention_bf16_lse(q, k, v, ctx, nullptr, lengths, n_utt, heads, T, stream_);
 }
 
-extern "C" int aph_attention_bf16_lse(const void* q, const void* k, const void* vt, void* ctx, float* lse2,
-                                      const int32_t* lengths, int32_t n_utt, int32_t heads, int32_t T,
-                                      int32_t t_v, void* stream_) {
+extern "C" int aph_attention_bf16_lse(const void* q, const void* k, const void* v, void* ctx, float* lse2,
+                                      const int32_t* lengths, int32_t n_utt, int32_t heads, int32_t T, void* stream_) {
   using namespace aph;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  APH_REQUIRE(q && k && vt && ctx && lengths, "null pointer");
+  APH_REQUIRE(q && k && v && ctx && lengths, "null pointer");
   APH_REQUIRE(n_utt > 0 && heads > 0 && T > 0, "empty problem");
-  APH_REQUIRE(t_v >= T && t_v % 8 == 0, "t_v must be >= T and a multiple of 8");
   const uint64_t nh = static_cast<uint64_t>(n_utt) * heads;
   CUtensorMap tm_q, tm_k, tm_v;
   {
@@ -339,12 +338,7 @@ extern "C" int aph_attention_bf16_lse(const void* q, const void* k, const void* 
     if (rc != APH_OK) return rc;
     rc = encode_tmap(&tm_k, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, k, dims, strides, box_k, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != APH_OK) return rc;
-  }
-  {
-    const uint64_t dims[3] = {static_cast<uint64_t>(t_v), kAttD, nh};
-    const uint64_t strides[2] = {static_cast<uint64_t>(t_v) * 2, static_cast<uint64_t>(t_v) * kAttD * 2};
-    const uint32_t box[3] = {kAttKV, kAttD, 1};
-    int rc = encode_tmap(&tm_v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, vt, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = encode_tmap(&tm_v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, v, dims, strides, box_k, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != APH_OK) return rc;
   }
   static bool attr_set = false;

@@ -362,20 +362,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
                 d4[j] = o;
               }
             } else {
-              __nv_bfloat16* dst = p.vt + (bh * 64 + d0) * p.t_v + tt;
+              // V row-major like Q and K: the attention kernels read it as an MN-major B operand (O = P V), so the
+              // transposed copy (32 scattered 2-byte stores per thread) is only written when a caller asks for it
+              uint4* d4 = reinterpret_cast<uint4*>(p.vmat + (bh * p.len_period + tt) * 64 + d0);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.t_v] = __float2bfloat16(v[j]);
-              if (p.vmat != nullptr) {  // training: V also row-major for the attention backward
-                uint4* d4 = reinterpret_cast<uint4*>(p.vmat + (bh * p.len_period + tt) * 64 + d0);
+              for (int j = 0; j < 4; ++j) {
+                uint4 o;
+                o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                d4[j] = o;
+              }
+              if (p.vt != nullptr) {
+                __nv_bfloat16* dst = p.vt + (bh * 64 + d0) * p.t_v + tt;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  uint4 o;
-                  o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                  o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                  o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                  o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                  d4[j] = o;
-                }
+                for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.t_v] = __float2bfloat16(v[j]);
               }
             }
           }
@@ -591,7 +593,10 @@ static int launch_gemm(const aph_gemm_args* a, GemmParams& p, cudaStream_t strea
     if (rc != APH_OK) return rc;
   } else {
     // a K-major A paired with an MN-major B contracts over k_seq columns only: clip the map so the tail reads zero
-    const uint64_t inner = a->b_mn_major && k_seq < a->a_inner ? k_seq : a->a_inner;
+    // clip the map to the contraction length: columns past it (K-major B zero-filled there, or an MN-major B with
+    // k_seq rows) read as zero instead of whatever follows in a wider A matrix
+    const int k_len = a->b_mn_major ? k_seq : (a->mode == APH_GEMM_ROWS ? a->k : a->a_inner);
+    const uint64_t inner = k_len < a->a_inner ? k_len : a->a_inner;
     const uint64_t dims[3] = {inner, static_cast<uint64_t>(a->a_rows), static_cast<uint64_t>(a->batch)};
     uint64_t batch_stride = static_cast<uint64_t>(a->a_batch_stride) * 2;
     if (a->batch == 1 && batch_stride == 0) batch_stride = static_cast<uint64_t>(a->a_row_stride) * 2;
@@ -691,7 +696,7 @@ extern "C" int aph_gemm_bf16(const aph_gemm_args* a, void* stream_) {
   APH_REQUIRE(a != nullptr, "null args");
   APH_REQUIRE(a->a != nullptr && a->b != nullptr, "null operand");
   const bool mn = a->a_mn_major || a->b_mn_major;
-  APH_REQUIRE(mn || (a->k > 0 && a->k % kBK == 0), "k must be a positive multiple of 64");
+  APH_REQUIRE(mn || (a->k > 0 && a->k % 8 == 0), "k must be a positive multiple of 8 (the tail of the last 64-wide block is TMA zero fill)");
   APH_REQUIRE(a->n > 0 && a->n % 8 == 0, "n must be a positive multiple of 8");
   APH_REQUIRE(a->a_rows > 0 && a->batch > 0, "empty A");
   APH_REQUIRE(a->a_row_stride % 8 == 0 && a->a_batch_stride % 8 == 0, "A strides must be multiples of 8 elements");
@@ -718,7 +723,7 @@ extern "C" int aph_gemm_bf16(const aph_gemm_args* a, void* stream_) {
     p.k_blocks = p.k_seq_blocks * (a->k_batch > 0 ? a->k_batch : 1);
   } else {
     p.k_seq_blocks = 1;
-    p.k_blocks = a->k / kBK;
+    p.k_blocks = ceil_div(a->k, kBK);
   }
   p.a_mn = a->a_mn_major ? 1 : 0;
   p.b_mn = a->b_mn_major ? 1 : 0;
@@ -780,9 +785,9 @@ extern "C" int aph_gemm_bf16(const aph_gemm_args* a, void* stream_) {
 
   if (a->epilogue == APH_EPI_QKV) {
     APH_REQUIRE(!mn, "qkv epilogue takes K-major operands");
-    APH_REQUIRE(a->q && a->kmat && a->vt && a->bias, "qkv epilogue needs q/k/vt/bias");
+    APH_REQUIRE(a->q && a->kmat && a->vmat && a->bias, "qkv epilogue needs q/k/v/bias");
     APH_REQUIRE(a->heads > 0 && a->n == 3 * a->heads * 64, "qkv epilogue: n == 3*heads*64");
-    APH_REQUIRE(a->len_period > 0 && a->t_v % 8 == 0 && a->t_v >= a->len_period, "qkv epilogue: bad lengths");
+    APH_REQUIRE(a->len_period > 0 && (!a->vt || (a->t_v % 8 == 0 && a->t_v >= a->len_period)), "qkv epilogue: bad lengths");
     APH_REQUIRE((a->heads * 64) % 256 == 0, "qkv epilogue: hidden must be a multiple of 256");
     p.n_tiles = ceil_div(a->n, 256);
     return launch_gemm<256, APH_EPI_QKV>(a, p, stream);

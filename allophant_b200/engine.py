@@ -268,10 +268,9 @@ class EncoderPlan:
         self.hidden = z(M, H, dtype=f32)
         self.hidden_bf16 = z(M, H)
         self.ln_out = z(M, H)
-        self.t_v = (self.seq + 7) // 8 * 8
         self.q = z(n_utt * heads * self.seq * 64)
         self.k = z(n_utt * heads * self.seq * 64)
-        self.vt = z(n_utt * heads * 64 * self.t_v)
+        self.v = z(n_utt * heads * self.seq * 64)
         self.ctx = z(M, H)
         self.ffn = z(M, cfg.intermediate_size)
         self.x = z(M, ldx)  # classifier feature matrix: [final LN | kept hidden states | dependency probabilities | 0]
@@ -289,7 +288,7 @@ class EncoderPlan:
             self.saved = [
                 dict(
                     ln1=z(M, H), q=z(n_utt * heads * self.seq * 64), k=z(n_utt * heads * self.seq * 64), v=z(n_utt * heads * self.seq * 64),
-                    vt=z(n_utt * heads * 64 * self.t_v), lse=z(n_utt * heads * self.seq, dtype=f32), ctx=z(M, H), ln2=z(M, H),
+                    lse=z(n_utt * heads * self.seq, dtype=f32), ctx=z(M, H), ln2=z(M, H),
                     pre=z(M, FF), act=z(M, FF),
                 )
                 for _ in range(n_layers)
@@ -415,21 +414,21 @@ class EncoderPlan:
             if self.training:
                 sv = self.saved[index]
                 h_in, h_mid, h_out = self.hs[index], self.mids[index], self.hs[index + 1]
-                ln1, ln2, q, k, vt, ctx, ffn = sv["ln1"], sv["ln2"], sv["q"], sv["k"], sv["vt"], sv["ctx"], sv["act"]
-                vmat, lse, pre = sv["v"], sv["lse"], sv["pre"]
+                ln1, ln2, q, k, v, ctx, ffn = sv["ln1"], sv["ln2"], sv["q"], sv["k"], sv["v"], sv["ctx"], sv["act"]
+                lse, pre = sv["lse"], sv["pre"]
             else:
                 h_in = h_mid = h_out = self.hidden
                 ln1 = ln2 = self.ln_out
-                q, k, vt, ctx, ffn = self.q, self.k, self.vt, self.ctx, self.ffn
-                vmat = lse = pre = None
+                q, k, v, ctx, ffn = self.q, self.k, self.v, self.ctx, self.ffn
+                lse = pre = None
             steps.append(lambda index=index, h_in=h_in: self._keep_hidden(index, h_in))
             g1, b1 = lw["ln1"]
             steps.append(lambda g1=g1, b1=b1, h_in=h_in, ln1=ln1: ops.layernorm_rows(h_in, M, H, H, g1, b1, eps, out_bf16=ln1, ld_bf16=H))
             steps.append(
-                self._gemm(ops.make_qkv_args(ln1, lw["wqkv"], lw["bqkv"], q, k, vt, rows=M, seq=self.seq, heads=heads, t_v=self.t_v, vmat=vmat))
+                self._gemm(ops.make_qkv_args(ln1, lw["wqkv"], lw["bqkv"], q, k, v, rows=M, seq=self.seq, heads=heads))
             )
             steps.append(
-                lambda q=q, k=k, vt=vt, ctx=ctx, lse=lse: ops.attention(q, k, vt, ctx, self.att_lengths, N, heads, self.seq, self.t_v, lse)
+                lambda q=q, k=k, v=v, ctx=ctx, lse=lse: ops.attention(q, k, v, ctx, self.att_lengths, N, heads, self.seq, lse)
             )
             steps.append(
                 self._gemm(

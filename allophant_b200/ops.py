@@ -173,11 +173,9 @@ def make_wgrad_args(
     return g
 
 
-def make_qkv_args(
-    a: Tensor, w_qkv: Tensor, bias_qkv: Tensor, q: Tensor, k: Tensor, vt: Tensor, *, rows: int, seq: int, heads: int, t_v: int,
-    vmat: Optional[Tensor] = None,
-) -> GemmArgs:
-    _require_cuda(a, w_qkv, bias_qkv, q, k, vt, vmat)
+def make_qkv_args(a: Tensor, w_qkv: Tensor, bias_qkv: Tensor, q: Tensor, k: Tensor, v: Tensor, *, rows: int, seq: int, heads: int) -> GemmArgs:
+    """QKV projection with the scatter epilogue: Q (pre-scaled), K and V as bf16 ``[n_utt*heads, seq, 64]``."""
+    _require_cuda(a, w_qkv, bias_qkv, q, k, v)
     hidden = heads * 64
     g = GemmArgs()
     g.a = a.data_ptr()
@@ -189,9 +187,8 @@ def make_qkv_args(
     g.scale = 1.0
     g.bias = bias_qkv.data_ptr()
     g.len_period = seq
-    g.q, g.kmat, g.vt = q.data_ptr(), k.data_ptr(), vt.data_ptr()
-    g.heads, g.t_v, g.q_scale = heads, t_v, 0.125 * 1.4426950408889634  # head_dim^-0.5 * log2(e)
-    g.vmat = _ptr(vmat)
+    g.q, g.kmat, g.vmat = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    g.heads, g.q_scale = heads, 0.125 * 1.4426950408889634  # head_dim^-0.5 * log2(e)
     return g
 
 
@@ -237,14 +234,11 @@ def linear_bf16(
 # --------------------------------------------------------------------------------------
 # attention
 # --------------------------------------------------------------------------------------
-def attention(
-    q: Tensor, k: Tensor, vt: Tensor, ctx: Tensor, frame_lengths: Tensor, n_utt: int, heads: int, seq: int, t_v: int, lse2: Optional[Tensor] = None
-) -> None:
-    _require_cuda(q, k, vt, ctx, frame_lengths, lse2)
+def attention(q: Tensor, k: Tensor, v: Tensor, ctx: Tensor, frame_lengths: Tensor, n_utt: int, heads: int, seq: int, lse2: Optional[Tensor] = None) -> None:
+    """``q``/``k``/``v`` bf16 ``[n_utt*heads, seq, 64]`` (q pre-scaled) -> ``ctx`` bf16 ``[n_utt*seq, heads*64]``."""
+    _require_cuda(q, k, v, ctx, frame_lengths, lse2)
     check(
-        lib.aph_attention_bf16_lse(
-            q.data_ptr(), k.data_ptr(), vt.data_ptr(), ctx.data_ptr(), _ptr(lse2), frame_lengths.data_ptr(), n_utt, heads, seq, t_v, _stream()
-        ),
+        lib.aph_attention_bf16_lse(q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), _ptr(lse2), frame_lengths.data_ptr(), n_utt, heads, seq, _stream()),
         "aph_attention_bf16_lse",
     )
 

@@ -57,7 +57,7 @@ void aph_reset_launch_count(void);
 #define APH_GEMM_DIAG_TAPS 2 /* weight gradient of the grouped positional conv (both operands MN-major):
                               * work item (tap j, 256-channel block q): D_j[q] = A[:, q]^T . shift_j(B[:, q]) */
 #define APH_EPI_STORE 0    /* generic epilogue described above                                   */
-#define APH_EPI_QKV 1      /* scatter bf16 into Q[b,h,t,64] (pre-scaled), K[b,h,t,64], Vt[b,h,64,t_v] */
+#define APH_EPI_QKV 1      /* scatter bf16 into Q[b,h,t,64] (pre-scaled), K[b,h,t,64], V[b,h,t,64] (= args.vmat) */
 
 typedef struct aph_gemm_args {
   /* A operand, bf16. Logical view [batch][a_rows][a_inner]. */
@@ -90,9 +90,9 @@ typedef struct aph_gemm_args {
   /* APH_EPI_QKV */
   void* q;
   void* kmat;
-  void* vt;
+  void* vt;               /* optional: V transposed [b,h,64,t_v] as well (NULL = not written; nothing in the library reads it) */
   int32_t heads;
-  int32_t t_v;            /* padded key length of Vt (multiple of 8) */
+  int32_t t_v;            /* padded key length of vt (multiple of 8) */
   float q_scale;
   /* ---- ABI 2: operand majors and training epilogues (all zero = ABI 1 behaviour) ---------------
    * MN-major operands let the backward GEMMs of nn.Linear read activations and weights in the
@@ -114,7 +114,7 @@ typedef struct aph_gemm_args {
   int64_t ld_aux;
   const void* gelu_bwd;   /* store epilogue: v *= gelu'(pre[row][col]) with pre bf16 [rows][ld_gelu_bwd] or NULL */
   int64_t ld_gelu_bwd;
-  void* vmat;             /* APH_EPI_QKV: additionally V row-major [b,h,t,64] (attention backward) or NULL */
+  void* vmat;             /* APH_EPI_QKV: V row-major [b,h,t,64] (required) */
 } aph_gemm_args;
 
 int aph_gemm_bf16(const aph_gemm_args* args, void* stream);
@@ -122,23 +122,18 @@ int aph_gemm_bf16(const aph_gemm_args* args, void* stream);
 /* ---- variable-length self-attention (tcgen05, flash-style online softmax) --- */
 /* Replaces the SDPA call of Wav2Vec2Attention (HF:466-549) and the dense
  * additive mask of HF:758-762: keys t >= lengths[b] get probability 0.
- *   q, k : bf16 [n_utt*heads][T][64]   (q already scaled by head_dim^-0.5 * log2(e): the kernel
- *          exponentiates with exp2)
- *   vt   : bf16 [n_utt*heads][64][t_v] (V transposed, keys contiguous, t_v % 8 == 0,
- *          columns [T, t_v) must be finite)
+ *   q, k, v : bf16 [n_utt*heads][T][64] (q already scaled by head_dim^-0.5 * log2(e): the kernel exponentiates
+ *          with exp2; v row-major, read as an MN-major tensor-core operand: no transposed copy)
  *   ctx  : bf16 [n_utt*T][heads*64]    rows of padded query tiles are left untouched
  */
-int aph_attention_bf16(const void* q, const void* k, const void* vt, void* ctx,
-                       const int32_t* lengths, int32_t n_utt, int32_t heads, int32_t T,
-                       int32_t t_v, void* stream);
-
+int aph_attention_bf16(const void* q, const void* k, const void* v, void* ctx,
+                       const int32_t* lengths, int32_t n_utt, int32_t heads, int32_t T, void* stream);
 /* Training variant: additionally writes lse2[n_utt*heads][T] = log2-domain log-sum-exp of every
  * query row of a non-skipped tile (NULL = same as aph_attention_bf16). */
-int aph_attention_bf16_lse(const void* q, const void* k, const void* vt, void* ctx, float* lse2,
-                           const int32_t* lengths, int32_t n_utt, int32_t heads, int32_t T,
-                           int32_t t_v, void* stream);
+int aph_attention_bf16_lse(const void* q, const void* k, const void* v, void* ctx, float* lse2,
+                           const int32_t* lengths, int32_t n_utt, int32_t heads, int32_t T, void* stream);
 /* Backward of the same call (autograd of HF:466-549, reached from loss.backward(), estimator.py:738).
- *   q, k, v : bf16 [n_utt*heads][T][64] as written by the QKV epilogue (q pre-scaled; v row-major = args.vmat)
+ *   q, k, v : bf16 [n_utt*heads][T][64] as written by the QKV epilogue (q pre-scaled)
  *   ctx, d_ctx : bf16 [n_utt*T][heads*64] forward output and its gradient (rows of padded frames must be 0 in d_ctx)
  *   lse2 : from aph_attention_bf16_lse; delta_scratch : fp32 [n_utt*heads][T]
  *   dqkv : bf16 [n_utt*T][3*heads*64] = (dQ | dK | dV), dQ w.r.t. the UNSCALED query projection;

@@ -28,7 +28,7 @@ def range_err(value, reference):
 
 
 # ------------------------------------------------------------------------------------------ GEMM
-@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (1000, 1024, 1024), (333, 784, 1024), (77, 32, 640), (4096, 4096, 1024)])
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (1000, 1024, 1024), (333, 784, 1024), (77, 32, 640), (4096, 4096, 1024), (150, 64, 40), (300, 256, 200)])
 def test_gemm_plain(m, n, k):
     ops = _ops()
     torch.manual_seed(m + n + k)
@@ -108,21 +108,35 @@ def test_gemm_positional_conv(frames):
     assert range_err(hidden, reference) < 1e-4
 
 
+def test_gemm_qkv_scatter_epilogue():
+    """Fused Q/K/V projection: Q pre-scaled by head_dim^-0.5 * log2(e), K and V, all as bf16 [utterance*head, frame, 64]."""
+    ops = _ops()
+    torch.manual_seed(21)
+    n_utt, seq, heads = 3, 249, 16
+    hidden, rows = heads * 64, 3 * 249
+    x = (torch.randn(rows, hidden, device=DEV) * 0.5).bfloat16()
+    w = (torch.randn(3 * hidden, hidden, device=DEV) * 0.03).bfloat16()
+    bias = torch.randn(3 * hidden, device=DEV)
+    q, k, v = (torch.full((n_utt * heads * seq * 64,), float("nan"), device=DEV, dtype=torch.bfloat16) for _ in range(3))
+    ops.run_gemm(ops.make_qkv_args(x, w, bias, q, k, v, rows=rows, seq=seq, heads=heads))
+    reference = (x.float() @ w.float().T + bias).view(n_utt, seq, 3, heads, 64).permute(2, 0, 3, 1, 4)  # [3, N, heads, T, 64]
+    scale = 0.125 * math.log2(math.e)
+    for ours, ref in ((q, reference[0] * scale), (k, reference[1]), (v, reference[2])):
+        assert range_err(ours.view(n_utt, heads, seq, 64), ref) < 1e-2
+
+
 # ------------------------------------------------------------------------------------------ attention
 @pytest.mark.parametrize("n,heads,frames,lengths", [(1, 1, 128, [128]), (2, 16, 499, [499, 300]), (3, 4, 749, [749, 1, 130]), (1, 2, 1499, [1000])])
 def test_attention(n, heads, frames, lengths):
     ops = _ops()
     torch.manual_seed(frames)
-    t_v = (frames + 7) // 8 * 8
     q = torch.randn(n, heads, frames, 64, device=DEV).bfloat16()
     k = torch.randn(n, heads, frames, 64, device=DEV).bfloat16()
     v = torch.randn(n, heads, frames, 64, device=DEV).bfloat16()
-    vt = torch.zeros(n, heads, 64, t_v, device=DEV, dtype=torch.bfloat16)
-    vt[..., :frames] = v.transpose(2, 3)
     q_scaled = (q.float() * 0.125 * math.log2(math.e)).bfloat16()  # the kernel works in the log2 domain
     ctx = torch.zeros(n * frames, heads * 64, device=DEV, dtype=torch.bfloat16)
     frame_lengths = torch.tensor(lengths, device=DEV, dtype=torch.int32)
-    ops.attention(q_scaled, k, vt, ctx, frame_lengths, n, heads, frames, t_v)
+    ops.attention(q_scaled, k, v, ctx, frame_lengths, n, heads, frames)
     mask = torch.arange(frames)[None, :] < torch.tensor(lengths)[:, None]
     scores = (q_scaled.float().cpu() / math.log2(math.e) @ k.float().cpu().transpose(2, 3)).masked_fill(~mask[:, None, None, :], float("-inf"))
     reference = (torch.softmax(scores, -1) @ v.float().cpu()).permute(0, 2, 1, 3).reshape(n, frames, heads * 64)
@@ -140,21 +154,18 @@ def test_attention_large_scores_exercise_lazy_rescaling(sharpness):
     torch.manual_seed(7)
     n, heads, frames = 8, 16, 499
     lengths = [499, 450, 400, 333, 257, 129, 64, 17]
-    t_v = (frames + 7) // 8 * 8
     q = torch.randn(n, heads, frames, 64, device=DEV)
     k = torch.randn(n, heads, frames, 64, device=DEV).bfloat16()
     v = torch.randn(n, heads, frames, 64, device=DEV).bfloat16()
     # later keys get larger scores: the running maximum grows along the key axis
     k = (k.float() * (1.0 + torch.arange(frames, device=DEV)[None, None, :, None] / frames)).bfloat16()
-    vt = torch.zeros(n, heads, 64, t_v, device=DEV, dtype=torch.bfloat16)
-    vt[..., :frames] = v.transpose(2, 3)
     q_scaled = (q * sharpness * 0.125 * math.log2(math.e)).bfloat16()
     frame_lengths = torch.tensor(lengths, device=DEV, dtype=torch.int32)
     results = []
     for _ in range(3):
         ctx = torch.zeros(n * frames, heads * 64, device=DEV, dtype=torch.bfloat16)
         lse = torch.zeros(n * heads * frames, device=DEV, dtype=torch.float32)
-        ops.attention(q_scaled, k, vt, ctx, frame_lengths, n, heads, frames, t_v, lse)
+        ops.attention(q_scaled, k, v, ctx, frame_lengths, n, heads, frames, lse)
         results.append((ctx, lse))
     torch.cuda.synchronize()
     mask = torch.arange(frames)[None, :] < torch.tensor(lengths)[:, None]

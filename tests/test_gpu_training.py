@@ -165,18 +165,15 @@ def test_attention_backward(seq, lengths):
     torch.manual_seed(seq)
     n_utt, heads, d = len(lengths), 4, 64
     hidden = heads * d
-    t_v = (seq + 7) // 8 * 8
     scale = 0.125 * 1.4426950408889634
     q_raw = torch.randn(n_utt, heads, seq, d, device=DEV)
     k = torch.randn(n_utt, heads, seq, d, device=DEV).bfloat16()
     v = torch.randn(n_utt, heads, seq, d, device=DEV).bfloat16()
     q_scaled = (q_raw * scale).bfloat16()
-    vt = torch.zeros(n_utt, heads, d, t_v, device=DEV, dtype=torch.bfloat16)
-    vt[..., :seq] = v.transpose(-1, -2)
     frames = torch.tensor(lengths, device=DEV, dtype=torch.int32)
     ctx = torch.zeros(n_utt * seq, hidden, device=DEV, dtype=torch.bfloat16)
     lse = torch.zeros(n_utt * heads * seq, device=DEV, dtype=torch.float32)
-    ops.attention(q_scaled.contiguous(), k.contiguous(), vt.contiguous(), ctx, frames, n_utt, heads, seq, t_v, lse)
+    ops.attention(q_scaled.contiguous(), k.contiguous(), v.contiguous(), ctx, frames, n_utt, heads, seq, lse)
 
     d_ctx = torch.randn(n_utt * seq, hidden, device=DEV)
     valid = torch.arange(seq, device=DEV)[None, :] < frames[:, None]  # [N, T]

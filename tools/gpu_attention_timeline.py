@@ -12,22 +12,22 @@ n_utt, heads, seq, d = 32, 16, 499, 64
 t_v = (seq + 7) // 8 * 8
 q = (torch.randn(n_utt * heads, seq, d, device=DEV) * 0.125 * 1.4427).bfloat16()  # bench-like: no rescaling after block 0
 k = torch.randn(n_utt * heads, seq, d, device=DEV).bfloat16()
-vt = torch.randn(n_utt * heads, d, t_v, device=DEV).bfloat16()
+v = torch.randn(n_utt * heads, seq, d, device=DEV).bfloat16()
 ctx = torch.zeros(n_utt * seq, heads * d, device=DEV, dtype=torch.bfloat16)
 frames = torch.full((n_utt,), seq, device=DEV, dtype=torch.int32)
 for _ in range(3):
-    ops.attention(q, k, vt, ctx, frames, n_utt, heads, seq, t_v)
+    ops.attention(q, k, v, ctx, frames, n_utt, heads, seq)
 torch.cuda.synchronize()
 start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 start.record()
 for _ in range(20):
-    ops.attention(q, k, vt, ctx, frames, n_utt, heads, seq, t_v)
+    ops.attention(q, k, v, ctx, frames, n_utt, heads, seq)
 end.record()
 torch.cuda.synchronize()
 print(f"attention kernel: {start.elapsed_time(end) / 20 * 1000:.1f} us per launch")
 timeline = torch.zeros(32, device=DEV, dtype=torch.int64)
 _lib.check(_lib.lib.aph_debug_set_timeline(timeline.data_ptr()), "timeline")
-ops.attention(q, k, vt, ctx, frames, n_utt, heads, seq, t_v)
+ops.attention(q, k, v, ctx, frames, n_utt, heads, seq)
 torch.cuda.synchronize()
 stamps = timeline.tolist()
 base = stamps[0]

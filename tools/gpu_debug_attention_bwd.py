@@ -27,7 +27,7 @@ frames = torch.tensor(lengths, device=DEV, dtype=torch.int32)
 ctx = torch.zeros(n_utt * seq, hidden, device=DEV, dtype=torch.bfloat16)
 lse = torch.zeros(n_utt * heads * seq, device=DEV, dtype=torch.float32)
 print("forward...", flush=True)
-ops.attention(q, k, vt.contiguous(), ctx, frames, n_utt, heads, seq, t_v, lse)
+ops.attention(q, k, v, ctx, frames, n_utt, heads, seq, lse)
 torch.cuda.synchronize()
 print("forward ok", float(ctx.float().abs().mean()), float(lse.mean()), flush=True)
 d_ctx = torch.randn(n_utt * seq, hidden, device=DEV).bfloat16()
