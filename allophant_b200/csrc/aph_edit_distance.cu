@@ -149,3 +149,41 @@ extern "C" float aph_word_error_rate(uint64_t insertions, uint64_t deletions, ui
   const float substituted_or_deleted = static_cast<float>(substitutions + deletions);
   return (substituted_or_deleted + static_cast<float>(insertions)) / (substituted_or_deleted + static_cast<float>(correct));
 }
+
+// ---- host-side collation (batching.py:171-215, rnn.pad_sequence of the audio) -------------------------------------
+// Copies n variable-length fp32 utterances into one zero-padded [n][max_len] matrix (normally a pinned staging buffer
+// that the host -> device copy then reads), spread over host threads.  ALL POINTERS ARE HOST POINTERS.
+#include <string.h>
+
+#include <thread>
+#include <vector>
+
+extern "C" int aph_collate_pad_f32(const float* const* utterances_host, const int64_t* lengths_host, int64_t n, int64_t max_len,
+                                   float* dst_host, int32_t n_threads) {
+  if (!utterances_host || !lengths_host || !dst_host || n < 0 || max_len < 0) return APH_ERR_INVALID;
+  for (int64_t i = 0; i < n; ++i)
+    if (lengths_host[i] < 0 || lengths_host[i] > max_len || (lengths_host[i] > 0 && utterances_host[i] == nullptr)) return APH_ERR_INVALID;
+  int threads = n_threads > 0 ? n_threads : static_cast<int>(std::thread::hardware_concurrency());
+  if (threads < 1) threads = 1;
+  if (threads > n) threads = static_cast<int>(n > 0 ? n : 1);
+  auto work = [&](int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < hi; ++i) {
+      float* row = dst_host + i * max_len;
+      const int64_t len = lengths_host[i];
+      if (len > 0) memcpy(row, utterances_host[i], sizeof(float) * static_cast<size_t>(len));
+      if (len < max_len) memset(row + len, 0, sizeof(float) * static_cast<size_t>(max_len - len));
+    }
+  };
+  if (threads == 1 || n * max_len < (1 << 18)) {
+    work(0, n);
+    return APH_OK;
+  }
+  std::vector<std::thread> pool;
+  const int64_t per = (n + threads - 1) / threads;
+  for (int t = 0; t < threads; ++t) {
+    const int64_t lo = t * per, hi = lo + per < n ? lo + per : n;
+    if (lo < hi) pool.emplace_back(work, lo, hi);
+  }
+  for (auto& th : pool) th.join();
+  return APH_OK;
+}

@@ -7,7 +7,8 @@ Field-for-field mirrors of ``allophant/dataset_processing.py`` ``Batch`` (49-85)
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, List, Tuple
+from enum import Enum
+from typing import Dict, Iterator, List, Tuple
 
 import torch
 from torch import Tensor
@@ -73,3 +74,45 @@ class LabeledBatch(Batch):
             [l.to(device, non_blocking=non_blocking, copy=copy) for l in self.label_lengths],
             label_length_indices=self.label_length_indices,
         )
+
+
+@dataclass(repr=False)
+class RawLabeledBatch(Batch):
+    """``dataset_processing.py:92-130``: audio with raw (string) transcriptions per G2P engine and utterance ids."""
+
+    raw_labels: List[List[List[str]]]
+    utterance_ids: List[str]
+
+    def to(self, device, non_blocking: bool = False, copy: bool = False):
+        return self.__class__(*self._inputs_to(device, non_blocking, copy), self.raw_labels, self.utterance_ids)
+
+    def split_by_language(self) -> Iterator[Tuple[int, "RawLabeledBatch"]]:
+        split_ids, split_indices = self.language_ids.unique_consecutive(return_counts=True)
+        split_indices.cumsum_(0)
+        offset = 0
+        for split_id, split_index, features, lengths, language_ids in zip(
+            split_ids,
+            split_indices,
+            self.audio_features.tensor_split(split_indices),
+            self.lengths.tensor_split(split_indices),
+            self.language_ids.tensor_split(split_indices),
+        ):
+            yield (
+                split_id,
+                self.__class__(
+                    features[..., : lengths.max()],
+                    lengths,
+                    language_ids,
+                    [labels[offset:split_index] for labels in self.raw_labels],
+                    self.utterance_ids[offset:split_index],
+                ),
+            )
+            offset = split_index
+
+
+class BatchType(Enum):
+    """``dataset_processing.py:165-173``."""
+
+    UNLABELED = 0
+    RAW = 1
+    INDEXED = 2

@@ -387,6 +387,13 @@ int aph_edit_statistics_batch(const int64_t* expected_host, const int64_t* expec
 float aph_word_error_rate(uint64_t insertions, uint64_t deletions, uint64_t substitutions,
                           uint64_t correct);
 
+/* ---- host feeding (batching.py:171-215) -------------------------------------------------------- */
+/* rnn.pad_sequence of the utterances of a batch: n fp32 arrays of lengths_host[i] samples -> zero-padded
+ * [n][max_len] (normally a pinned staging buffer), spread over n_threads host threads (<= 0: all cores).
+ * ALL POINTERS ARE HOST POINTERS. */
+int aph_collate_pad_f32(const float* const* utterances_host, const int64_t* lengths_host, int64_t n,
+                        int64_t max_len, float* dst_host, int32_t n_threads);
+
 #ifdef __cplusplus
 }
 #endif
