@@ -73,6 +73,9 @@ class GemmArgs(Structure):
         ("gelu_bwd", c_void_p),
         ("ld_gelu_bwd", c_int64),
         ("vmat", c_void_p),
+        ("drop_threshold", ctypes.c_uint32),
+        ("drop_seed", ctypes.c_uint32),
+        ("drop_scale", ctypes.c_float),
     ]
 
 
@@ -97,6 +100,7 @@ _P = c_void_p
 _I32 = c_int32
 _I64 = c_int64
 _F = c_float
+_U32 = ctypes.c_uint32
 
 # name -> argtypes; every function returns int (APH_OK or a negative APH_ERR_* code)
 _SIGNATURES = {
@@ -104,6 +108,12 @@ _SIGNATURES = {
     "aph_attention_bf16": [_P, _P, _P, _P, _P, _I32, _I32, _I32, _P],
     "aph_attention_bf16_lse": [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P],
     "aph_attention_backward_bf16": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P],
+    "aph_attention_bf16_dropout": [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _U32, _U32, c_float, _P],
+    "aph_attention_backward_bf16_dropout": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _U32, _U32, c_float, _P],
+    "aph_dropout_2d": [_P, _I64, _I64, _I32, _U32, _U32, c_float, _P, _P, _P, _I64, _P, _I64, _P],
+    "aph_dropout_bf16_2d": [_P, _I64, _I64, _I32, _U32, _U32, c_float, _P],
+    "aph_spec_augment_mask": [_P, _I32, _I32, c_float, _I32, _I32, _U32, _P, _P],
+    "aph_masked_rows_backward": [_P, _I64, _I64, _I32, _P, _P, _P],
     "aph_debug_set_progress": [_P],
     "aph_debug_set_timeline": [_P],
     "aph_wave_stats": [_P, _P, _I32, _I32, _P, _P, _P],

@@ -45,6 +45,11 @@ struct AttParams {
   int T;
   int heads;
   float* lse2;         // [N*heads, T] log2-domain log-sum-exp of every query row (training) or nullptr
+  // train-mode attention dropout (HF Wav2Vec2Attention: dropout of the softmax probabilities): element (b*heads+h, q, k)
+  // is kept iff the 16-bit half (k & 1) of drop_hash(drop_row_key(seed, (b*heads+h)*T + q), k >> 1) >= threshold
+  uint32_t drop_threshold;
+  uint32_t drop_seed;
+  float drop_scale;
 };
 
 // Debug timeline (device buffer set through aph_debug_set_timeline; NULL in production): clock64 stamps of CTA (0,0)
@@ -60,6 +65,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+template <bool kDrop>
 __global__ void __launch_bounds__(kAttThreads, 2)
     attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                      const __grid_constant__ CUtensorMap tm_v, const AttParams p) {
@@ -248,6 +254,21 @@ __global__ void __launch_bounds__(kAttThreads, 2)
         ls[2 + (i & 1)] += vb[i];
       }
       l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      if constexpr (kDrop) {
+        // dropout of the (still unnormalised) probabilities: the row sum above is taken before it, the 1/(1-p) scale is
+        // folded into the final normalisation
+        const uint32_t key = drop_row_key(p.drop_seed, static_cast<uint32_t>(bh) * static_cast<uint32_t>(p.T) + static_cast<uint32_t>(q0 + r));
+        const uint32_t pair0 = static_cast<uint32_t>(key0 >> 1);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const uint32_t ha = drop_hash(key, pair0 + i);
+          const uint32_t hb = drop_hash(key, pair0 + 16 + i);
+          va[2 * i + 0] = drop_keep(ha, 0, p.drop_threshold) ? va[2 * i + 0] : 0.f;
+          va[2 * i + 1] = drop_keep(ha, 1, p.drop_threshold) ? va[2 * i + 1] : 0.f;
+          vb[2 * i + 0] = drop_keep(hb, 0, p.drop_threshold) ? vb[2 * i + 0] : 0.f;
+          vb[2 * i + 1] = drop_keep(hb, 1, p.drop_threshold) ? vb[2 * i + 1] : 0.f;
+        }
+      }
       // P buffer j & 1 was last read by the PV product of block j - 2, which completed before S_j did (see the issuer)
       uint8_t* p_row = p_row0 + (j & 1) * kAttPBytes;
 #pragma unroll
@@ -274,7 +295,7 @@ __global__ void __launch_bounds__(kAttThreads, 2)
     tc_fence_after();
     const bool row_in = q0 + r < p.T;
     if (row_in && p.lse2 != nullptr) p.lse2[static_cast<long long>(bh) * p.T + q0 + r] = m_ref + log2f(l_run);
-    const float inv = 1.0f / l_run;
+    const float inv = (kDrop ? p.drop_scale : 1.0f) / l_run;
     __nv_bfloat16* dst = p.ctx + (static_cast<long long>(b) * p.T + q0 + r) * (p.heads * kAttD) + h * kAttD;
 #pragma unroll
     for (int c0 = 0; c0 < kAttD; c0 += 32) {
@@ -323,7 +344,14 @@ extern "C" int aph_attention_bf16(const void* q, const void* k, const void* v, v
 
 extern "C" int aph_attention_bf16_lse(const void* q, const void* k, const void* v, void* ctx, float* lse2,
                                       const int32_t* lengths, int32_t n_utt, int32_t heads, int32_t T, void* stream_) {
+  return aph_attention_bf16_dropout(q, k, v, ctx, lse2, lengths, n_utt, heads, T, 0u, 0u, 1.0f, stream_);
+}
+
+extern "C" int aph_attention_bf16_dropout(const void* q, const void* k, const void* v, void* ctx, float* lse2, const int32_t* lengths,
+                                          int32_t n_utt, int32_t heads, int32_t T, uint32_t drop_threshold, uint32_t drop_seed,
+                                          float drop_scale, void* stream_) {
   using namespace aph;
+  APH_REQUIRE(drop_threshold < 65536u, "drop_threshold is 16 bits (p < 1)");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   APH_REQUIRE(q && k && v && ctx && lengths, "null pointer");
   APH_REQUIRE(n_utt > 0 && heads > 0 && T > 0, "empty problem");
@@ -343,7 +371,8 @@ extern "C" int aph_attention_bf16_lse(const void* q, const void* k, const void* 
   }
   static bool attr_set = false;
   if (!attr_set) {
-    APH_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
+    APH_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
+    APH_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmemBytes));
     attr_set = true;
   }
   AttParams p;
@@ -353,7 +382,13 @@ extern "C" int aph_attention_bf16_lse(const void* q, const void* k, const void* 
   p.heads = heads;
   p.lse2 = lse2;
   dim3 grid(ceil_div(T, kAttQ), static_cast<unsigned>(nh));
-  attention_kernel<<<grid, kAttThreads, kAttSmemBytes, stream>>>(tm_q, tm_k, tm_v, p);
+  p.drop_threshold = drop_threshold;
+  p.drop_seed = drop_seed;
+  p.drop_scale = drop_scale;
+  if (drop_threshold != 0)
+    attention_kernel<true><<<grid, kAttThreads, kAttSmemBytes, stream>>>(tm_q, tm_k, tm_v, p);
+  else
+    attention_kernel<false><<<grid, kAttThreads, kAttSmemBytes, stream>>>(tm_q, tm_k, tm_v, p);
   APH_POST_LAUNCH(1);
   return APH_OK;
 }

@@ -35,6 +35,11 @@ struct AttBwdParams {
   const int* lengths;      // [N]
   int T;
   int heads;
+  // attention dropout of the forward pass (aph_attention_bf16_dropout): with keep mask M and scale c = 1/(1-p),
+  // O = (c M o P) V, so dV = (c M o P)^T dO and dS = P o (c M o dP - delta); delta = rowsum(dO o O) is unchanged
+  uint32_t drop_threshold;
+  uint32_t drop_seed;
+  float drop_scale;
 };
 
 // Debug progress markers (host-mapped memory set through aph_debug_set_progress; NULL in production)
@@ -114,7 +119,7 @@ __global__ void __launch_bounds__(256) attention_delta_kernel(const __nv_bfloat1
 // ------------------------------------------------------------------------------------------------
 // dK, dV: key-stationary
 // smem: K 16K | V 16K | Q 2x16K | dO 2x16K | P^T 32K | dS^T 32K | lse/delta 2x2x512 B | barriers
-constexpr int kKvSmemBytes = 2 * kBwdTileBytes + 4 * kBwdTileBytes + 4 * kBwdTileBytes + 2048 + 256;
+constexpr int kKvSmemBytes = 2 * kBwdTileBytes + 4 * kBwdTileBytes + 4 * kBwdTileBytes + 2048 + 1024 /*dropout row keys*/ + 256;
 constexpr uint32_t kKvTmemCols = 512;  // S^T [0,128) dP^T [128,256) dV [256,320) dK [320,384)
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -156,7 +161,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
   uint8_t* s_dst = s_pt + 2 * kBwdTileBytes;   // two 16 KB halves
   float* s_lse = reinterpret_cast<float*>(s_dst + 2 * kBwdTileBytes);  // [2][128]
   float* s_delta = s_lse + 2 * kBwdTile;                               // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + 2 * kBwdTile);
+  uint32_t* s_key = reinterpret_cast<uint32_t*>(s_delta + 2 * kBwdTile);  // [2][128] dropout row keys of the query tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_key + 2 * kBwdTile);
   uint64_t* kv_full = bars + 0;
   uint64_t* q_full = bars + 1;   // [2]
   uint64_t* q_empty = bars + 3;  // [2]
@@ -271,6 +277,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
         const bool ok = qi < p.T;
         lse_t[r] = ok ? p.lse2[static_cast<long long>(bh) * p.T + qi] : 0.f;
         delta_t[r] = ok ? p.delta[static_cast<long long>(bh) * p.T + qi] : 0.f;
+        if (p.drop_threshold != 0)
+          s_key[(i & 1) * kBwdTile + r] = drop_row_key(p.drop_seed, static_cast<uint32_t>(bh) * static_cast<uint32_t>(p.T) + static_cast<uint32_t>(qi));
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // the four compute warps only
       mbar_wait(s_full, i & 1);
@@ -281,7 +289,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
         tmem_ld32(tmem_st + lane_off + static_cast<uint32_t>(c0), s);
         tmem_ld32(tmem_dpt + lane_off + static_cast<uint32_t>(c0), dp);
         tmem_ld_wait();
-        if (key_ok) {
+        if (key_ok && p.drop_threshold != 0) {
+          const uint32_t* key_t = s_key + (i & 1) * kBwdTile + c0;
+          const uint32_t pair = static_cast<uint32_t>(k0 + r) >> 1;
+          const int odd = (k0 + r) & 1;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float pr = exp2f(s[j] - lse_t[c0 + j]);
+            const float keep = drop_keep(drop_hash(key_t[j], pair), odd, p.drop_threshold) ? p.drop_scale : 0.f;
+            s[j] = pr * keep;
+            dp[j] = pr * (keep * dp[j] - delta_t[c0 + j]);
+          }
+        } else if (key_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float pr = exp2f(s[j] - lse_t[c0 + j]);
@@ -485,6 +504,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
     const bool row_in = q0 + r < p.T;
     const float lse = row_in ? p.lse2[static_cast<long long>(bh) * p.T + q0 + r] : 0.f;
     const float dl = row_in ? p.delta[static_cast<long long>(bh) * p.T + q0 + r] : 0.f;
+    const uint32_t drop_key = drop_row_key(p.drop_seed, static_cast<uint32_t>(bh) * static_cast<uint32_t>(p.T) + static_cast<uint32_t>(q0 + r));
     uint8_t* ds_row = s_ds + (r >> 3) * 1024 + (r & 7) * 128;
     const int sw = r & 7;
     for (int j = 0; j < n_kv; ++j) {
@@ -498,6 +518,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
         tmem_ld32(tmem_s + lane_off + static_cast<uint32_t>(c0), s);
         tmem_ld32(tmem_dp + lane_off + static_cast<uint32_t>(c0), dp);
         tmem_ld_wait();
+        if (p.drop_threshold != 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t hh = drop_hash(drop_key, static_cast<uint32_t>((key0 + c0) >> 1) + i);
+            dp[2 * i + 0] = drop_keep(hh, 0, p.drop_threshold) ? dp[2 * i + 0] * p.drop_scale : 0.f;
+            dp[2 * i + 1] = drop_keep(hh, 1, p.drop_threshold) ? dp[2 * i + 1] * p.drop_scale : 0.f;
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const float pr = (key0 + c0 + i < len) ? exp2f(s[i] - lse) : 0.f;
@@ -555,7 +583,15 @@ extern "C" int aph_attention_backward_bf16(const void* q, const void* k, const v
                                            const float* lse2, float* delta_scratch, void* dqkv,
                                            const int32_t* lengths, int32_t n_utt, int32_t heads, int32_t T,
                                            void* stream_) {
+  return aph_attention_backward_bf16_dropout(q, k, v, ctx, d_ctx, lse2, delta_scratch, dqkv, lengths, n_utt, heads, T, 0u, 0u, 1.0f, stream_);
+}
+
+extern "C" int aph_attention_backward_bf16_dropout(const void* q, const void* k, const void* v, const void* ctx, const void* d_ctx,
+                                                   const float* lse2, float* delta_scratch, void* dqkv, const int32_t* lengths,
+                                                   int32_t n_utt, int32_t heads, int32_t T, uint32_t drop_threshold,
+                                                   uint32_t drop_seed, float drop_scale, void* stream_) {
   using namespace aph;
+  APH_REQUIRE(drop_threshold < 65536u, "drop_threshold is 16 bits (p < 1)");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   APH_REQUIRE(q && k && v && ctx && d_ctx && lse2 && delta_scratch && dqkv && lengths, "null pointer");
   APH_REQUIRE(n_utt > 0 && heads > 0 && T > 0, "empty problem");
@@ -604,6 +640,9 @@ extern "C" int aph_attention_backward_bf16(const void* q, const void* k, const v
   p.lengths = lengths;
   p.T = T;
   p.heads = heads;
+  p.drop_threshold = drop_threshold;
+  p.drop_seed = drop_seed;
+  p.drop_scale = drop_scale;
   dim3 grid(ceil_div(T, kBwdTile), static_cast<unsigned>(nh));
   if (mask & 2) attention_bwd_kv_kernel<<<grid, kBwdThreads, kKvSmemBytes, stream>>>(tm_q, tm_k, tm_v, tm_do, p);
   if (mask & 4) attention_bwd_q_kernel<<<grid, kBwdThreads, kQSmemBytes, stream>>>(tm_q, tm_k, tm_v, tm_do, p, 0.125f);

@@ -423,6 +423,25 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(fabsf(hx), 1.0f - r, hx);  // 0.5 x + 0.5 |x| erf(|x|/sqrt2) = 0.5 x (1 + erf(x/sqrt2))
 }
 // d/dx of the GELU above: Phi(x) + x phi(x), Phi from the same erf approximation
+// ---- counter-based keep masks for train-mode dropout ----------------------------------------------------------------
+// One 32-bit hash per (row, column pair) decides two adjacent elements with 16-bit thresholds: element (row, col) is
+// KEPT iff its 16-bit half of drop_hash(drop_row_key(seed, row), col >> 1) is >= threshold (= round(p * 65536)).  The
+// backward pass regenerates the mask from (seed, row, col) instead of storing it; tests/helpers.py restates this
+// function in numpy to feed the same masks to the oracle.
+__host__ __device__ __forceinline__ uint32_t drop_fmix(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x85EBCA6Bu;
+  x ^= x >> 13;
+  x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t drop_row_key(uint32_t seed, uint32_t row) { return drop_fmix(seed ^ (row * 0x9E3779B1u)); }
+__host__ __device__ __forceinline__ uint32_t drop_hash(uint32_t row_key, uint32_t pair) { return drop_fmix(row_key ^ (pair * 0x9E3779B1u)); }
+__host__ __device__ __forceinline__ bool drop_keep(uint32_t hash, int odd, uint32_t threshold) {
+  return ((odd ? (hash >> 16) : (hash & 0xFFFFu)) >= threshold);
+}
+
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float u = fabsf(x) * 0.70710678118654752440f;
   float d = fmaf(0.0000430638f, u, 0.0002765672f);

@@ -90,6 +90,9 @@ struct GemmParams {
   const __nv_bfloat16* gelu_bwd;
   long long ld_gelu_bwd;
   __nv_bfloat16* vmat;
+  uint32_t drop_threshold;
+  uint32_t drop_seed;
+  float drop_scale;
 };
 
 // Work item -> (n block, m pair, output batch, k-block range, B row shift)
@@ -436,6 +439,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
               }
             }
           }
+          if (p.drop_threshold != 0) {  // train-mode dropout of the branch output, before the residual joins
+            const uint32_t key = drop_row_key(p.drop_seed, static_cast<uint32_t>(grow));
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t h = drop_hash(key, static_cast<uint32_t>(col >> 1) + j);
+              v[2 * j + 0] = drop_keep(h, 0, p.drop_threshold) ? v[2 * j + 0] * p.drop_scale : 0.f;
+              v[2 * j + 1] = drop_keep(h, 1, p.drop_threshold) ? v[2 * j + 1] * p.drop_scale : 0.f;
+            }
+          }
           if (resid_tma) {
             // this chunk's residual tile has landed (or lands now); copy the own row out, then hand the tile back to
             // the TMA engine for the next chunk.  Rows / columns outside the matrix arrive as zeros.
@@ -748,6 +760,11 @@ extern "C" int aph_gemm_bf16(const aph_gemm_args* a, void* stream_) {
   p.kmat = static_cast<__nv_bfloat16*>(a->kmat);
   p.vt = static_cast<__nv_bfloat16*>(a->vt);
   p.vmat = static_cast<__nv_bfloat16*>(a->vmat);
+  p.drop_threshold = a->drop_threshold;
+  p.drop_seed = a->drop_seed;
+  p.drop_scale = a->drop_scale;
+  APH_REQUIRE(a->drop_threshold < 65536u, "drop_threshold is 16 bits (p < 1)");
+  APH_REQUIRE(a->drop_threshold == 0 || (a->epilogue == APH_EPI_STORE && !a->a_mn_major), "dropout: store epilogue of a forward GEMM only");
   p.heads = a->heads;
   p.t_v = a->t_v;
   p.q_scale = a->q_scale;

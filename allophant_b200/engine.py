@@ -16,7 +16,7 @@ with the host.
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Tuple
 
 import torch
 from torch import Tensor
@@ -211,6 +211,55 @@ class PackedEncoder:
 Step = Callable[[], None]
 
 
+@dataclass
+class Stochastic:
+    """The train()-mode regularisation of ONE forward/backward pair (Hugging Face ``modeling_wav2vec2.py``: feature
+    projection dropout 431-433, SpecAugment ``_mask_hidden_states``, encoder dropout 766, LayerDrop 774-777, attention
+    dropout, the two hidden dropouts of a layer 742/752).  ``seed`` keys the counter-based masks the forward and the
+    backward kernels regenerate (``aph_common.cuh``: ``drop_hash``); LayerDrop is drawn on the host like HF does."""
+
+    seed: int
+    hidden_dropout: float = 0.0
+    attention_dropout: float = 0.0
+    feat_proj_dropout: float = 0.0
+    layerdrop: float = 0.0
+    mask_time_prob: float = 0.0
+    mask_time_length: int = 10
+    mask_time_min_masks: int = 2
+    skip_layers: Optional[Sequence[bool]] = None  # explicit LayerDrop decisions (tests); None = draw from torch's CPU RNG
+
+    SITE_FEATURE_PROJECTION = 1_000_000
+    SITE_ENCODER_INPUT = 1_000_001
+    SITE_SPEC_AUGMENT = 1_000_002
+    SITE_CLASSIFIER_INPUT = 2_000_000  # + hidden-state index (acoustic_model.py:486-488)
+
+    @classmethod
+    def from_config(cls, cfg: Wav2Vec2EncoderConfig, seed: int) -> "Stochastic":
+        if cfg.activation_dropout > 0.0:
+            raise NotImplementedError("activation_dropout > 0 (dropout inside the feed-forward block) is not implemented")
+        if cfg.mask_feature_prob > 0.0 and cfg.apply_spec_augment:
+            raise NotImplementedError("SpecAugment along the feature axis (mask_feature_prob > 0) is not implemented")
+        return cls(
+            seed, cfg.hidden_dropout, cfg.attention_dropout, cfg.feat_proj_dropout, cfg.layerdrop,
+            cfg.mask_time_prob if cfg.apply_spec_augment else 0.0, cfg.mask_time_length, cfg.mask_time_min_masks,
+        )  # fmt: skip
+
+    def attention(self, layer: int) -> ops.Dropout:
+        return ops.Dropout.site(self.attention_dropout, self.seed, 8 * layer)
+
+    def attention_output(self, layer: int) -> ops.Dropout:
+        return ops.Dropout.site(self.hidden_dropout, self.seed, 8 * layer + 1)
+
+    def feed_forward_output(self, layer: int) -> ops.Dropout:
+        return ops.Dropout.site(self.hidden_dropout, self.seed, 8 * layer + 2)
+
+    def feature_projection(self) -> ops.Dropout:
+        return ops.Dropout.site(self.feat_proj_dropout, self.seed, self.SITE_FEATURE_PROJECTION)
+
+    def encoder_input(self) -> ops.Dropout:
+        return ops.Dropout.site(self.hidden_dropout, self.seed, self.SITE_ENCODER_INPUT)
+
+
 class EncoderPlan:
     """Workspaces + launch list for one (N, T) shape.  ``run`` enqueues ~200 kernels on the current stream."""
 
@@ -302,6 +351,11 @@ class EncoderPlan:
             self.dqkv = z(M, 3 * H)
             self.delta = z(n_utt * heads * self.seq, dtype=f32)
             self.d_fp_in = z(M, 512, dtype=f32)
+            self.spec_mask = z(M, dtype=torch.uint8)  # SpecAugment time mask of the last train()-mode run
+        self.stoch: Optional[Stochastic] = None       # regularisation of the last run (None: eval()-mode arithmetic)
+        self.skipped: List[bool] = [False] * len(packed.layers)  # LayerDrop decisions of the last run
+        self._layer_spans: List[Tuple[int, int]] = []
+        self._drop_gemms: List[Tuple[Any, int, bool]] = []  # (GEMM args, layer, is feed-forward output)
 
         self._steps: List[Step] = []
         self._build()
@@ -311,6 +365,8 @@ class EncoderPlan:
         list (whose GEMM descriptors point at the packed operands) is rebuilt."""
         self.packed = packed
         self._steps = []
+        self._layer_spans = []
+        self._drop_gemms = []
         self._build()
 
     # ------------------------------------------------------------------
@@ -375,6 +431,8 @@ class EncoderPlan:
                 )
             )
         )
+        if self.training:
+            steps.append(self._regularise_projection)
         # positional conv embedding: hidden += gelu(grouped_conv(hidden)) (HF:764-765, 353-368)
         taps = cfg.num_conv_pos_embeddings
         if H // cfg.num_conv_pos_embedding_groups != 64:
@@ -405,6 +463,8 @@ class EncoderPlan:
                 )
             )
         )
+        if self.training:
+            steps.append(self._regularise_encoder_input)
         if not cfg.do_stable_layer_norm:
             raise NotImplementedError("post-LN wav2vec2 encoders (do_stable_layer_norm=False) are not implemented yet")
 
@@ -422,19 +482,19 @@ class EncoderPlan:
                 q, k, v, ctx, ffn = self.q, self.k, self.v, self.ctx, self.ffn
                 lse = pre = None
             steps.append(lambda index=index, h_in=h_in: self._keep_hidden(index, h_in))
+            span_start = len(steps)
             g1, b1 = lw["ln1"]
             steps.append(lambda g1=g1, b1=b1, h_in=h_in, ln1=ln1: ops.layernorm_rows(h_in, M, H, H, g1, b1, eps, out_bf16=ln1, ld_bf16=H))
             steps.append(
                 self._gemm(ops.make_qkv_args(ln1, lw["wqkv"], lw["bqkv"], q, k, v, rows=M, seq=self.seq, heads=heads))
             )
             steps.append(
-                lambda q=q, k=k, v=v, ctx=ctx, lse=lse: ops.attention(q, k, v, ctx, self.att_lengths, N, heads, self.seq, lse)
-            )
-            steps.append(
-                self._gemm(
-                    ops.make_gemm_args(ctx, lw["wo"], a_rows=M, a_inner=H, a_row_stride=H, bias=lw["bo"], resid=h_in, ld_resid=H, out_f32=h_mid, ld_f32=H)
+                lambda q=q, k=k, v=v, ctx=ctx, lse=lse, index=index: ops.attention(
+                    q, k, v, ctx, self.att_lengths, N, heads, self.seq, lse, self.stoch.attention(index) if self.stoch else ops.NO_DROPOUT
                 )
             )
+            out_args = ops.make_gemm_args(ctx, lw["wo"], a_rows=M, a_inner=H, a_row_stride=H, bias=lw["bo"], resid=h_in, ld_resid=H, out_f32=h_mid, ld_f32=H)
+            steps.append(self._gemm(out_args))
             g2, b2 = lw["ln2"]
             steps.append(lambda g2=g2, b2=b2, h_mid=h_mid, ln2=ln2: ops.layernorm_rows(h_mid, M, H, H, g2, b2, eps, out_bf16=ln2, ld_bf16=H))
             steps.append(
@@ -444,15 +504,48 @@ class EncoderPlan:
                     )
                 )
             )
-            steps.append(
-                self._gemm(
-                    ops.make_gemm_args(ffn, lw["w2"], a_rows=M, a_inner=FF, a_row_stride=FF, bias=lw["b2"], resid=h_mid, ld_resid=H, out_f32=h_out, ld_f32=H)
-                )
-            )
+            ffn_args = ops.make_gemm_args(ffn, lw["w2"], a_rows=M, a_inner=FF, a_row_stride=FF, bias=lw["b2"], resid=h_mid, ld_resid=H, out_f32=h_out, ld_f32=H)
+            steps.append(self._gemm(ffn_args))
+            self._layer_spans.append((span_start, len(steps)))
+            if self.training:
+                self._drop_gemms += [(out_args, index, False), (ffn_args, index, True)]
         self.h_last = self.hs[len(p.layers)] if self.training else self.hidden
         gf, bf = p.final_ln
         steps.append(lambda: ops.layernorm_rows(self.h_last, M, H, H, gf, bf, eps, out_bf16=self.x, ld_bf16=self.ldx))
         steps.append(lambda: self._keep_hidden(len(p.layers), self.h_last))
+
+    def _regularise_projection(self) -> None:
+        """train() mode: dropout of the feature projection output (HF:431-433), then SpecAugment (HF
+        ``_mask_hidden_states``: masked frames <- ``masked_spec_embed``); fp32 in place + the bf16 copy the positional
+        convolution reads.  Padded frames are zero already and stay zero."""
+        st = self.stoch
+        if st is None:
+            return
+        H, M = self.cfg.hidden_size, self.rows
+        embed = getattr(self.packed.weights, "masked_spec_embed", None)
+        mask = None
+        if st.mask_time_prob > 0.0 and embed is not None:
+            ops.spec_augment_mask(
+                self.att_lengths, self.seq, st.mask_time_prob, st.mask_time_length, st.mask_time_min_masks,
+                ops.mix_seed(st.seed, Stochastic.SITE_SPEC_AUGMENT), self.spec_mask,
+            )  # fmt: skip
+            mask = self.spec_mask
+        drop = st.feature_projection()
+        if mask is None and drop.threshold == 0:
+            return
+        fill = embed.detach().float().contiguous() if mask is not None else None
+        ops.dropout_2d(self.hidden_fp, H, M, H, drop, out_f32=self.hidden_fp, ld_f32=H, out_bf16=self.hidden_bf16, ld_bf16=H, row_mask=mask, row_fill=fill)
+        self.spec_active = mask is not None
+
+    def _regularise_encoder_input(self) -> None:
+        """train() mode: ``hidden_states = self.dropout(hidden_states + position_embeddings)`` (HF:765-766)."""
+        st = self.stoch
+        if st is None:
+            return
+        drop = st.encoder_input()
+        if drop.threshold:
+            H = self.cfg.hidden_size
+            ops.dropout_2d(self.hidden, H, self.rows, H, drop, out_f32=self.hidden, ld_f32=H)
 
     def _keep_hidden(self, index: int, hidden: Tensor) -> None:
         """Hidden state ``index`` of HF's ``hidden_states`` tuple is live in ``hidden`` right now
@@ -468,13 +561,30 @@ class EncoderPlan:
             ops.cast_bf16_2d(hidden, self.cfg.hidden_size, self.x[:, column:], self.ldx, self.rows, self.cfg.hidden_size)
 
     # ------------------------------------------------------------------
-    def run(self, audio: Tensor, lengths: Tensor, frames64: Tensor, capture: bool = False) -> None:
+    def run(self, audio: Tensor, lengths: Tensor, frames64: Tensor, capture: bool = False, stochastic: Optional[Stochastic] = None) -> None:
         """Enqueues the whole encoder.  ``audio`` fp32 [N, T] and ``lengths`` int64 [N] on the device;
-        ``frames64`` (int64 [N], caller-owned) receives the per-utterance frame counts."""
+        ``frames64`` (int64 [N], caller-owned) receives the per-utterance frame counts.  ``stochastic`` (training
+        plans only) switches the train()-mode regularisation on for this run and the backward pass that follows it."""
         p, cfg = self.packed, self.cfg
         N = self.n_utt
         self.captured = [] if capture else None
         self.generation += 1
+        if stochastic is not None and not self.training:
+            raise RuntimeError("train()-mode regularisation needs a training plan")
+        self.stoch = stochastic
+        self.spec_active = False
+        n_layers = len(p.layers)
+        self.skipped = [False] * n_layers
+        if stochastic is not None:
+            if stochastic.skip_layers is not None:
+                self.skipped = [bool(flag) for flag in stochastic.skip_layers]
+            elif stochastic.layerdrop > 0.0:
+                self.skipped = (torch.rand(n_layers) < stochastic.layerdrop).tolist()  # HF:774-777, host RNG like HF
+        for args, layer, feed_forward in self._drop_gemms:
+            drop = ops.NO_DROPOUT
+            if stochastic is not None:
+                drop = stochastic.feed_forward_output(layer) if feed_forward else stochastic.attention_output(layer)
+            args.drop_threshold, args.drop_seed, args.drop_scale = drop.threshold, drop.seed, drop.scale
         ops.frame_lengths(lengths, self.kernels_dev, self.strides_dev, self.frames32, frames64)
         if self.use_lengths:
             self.att_lengths = self.frames32
@@ -490,7 +600,17 @@ class EncoderPlan:
         else:
             g, b = p.conv_ln[0]
             ops.conv0_gn_gelu(audio, lengths, mean_rstd, p.conv0_w, p.conv_bias[0], g, b, 1e-5, self.gn_raw, self.gn_stats, self.buf_a)
-        for step in self._steps:
+        position = 0
+        for layer, (start, end) in enumerate(self._layer_spans):
+            for step in self._steps[position:start]:
+                step()
+            if self.skipped[layer]:
+                self.hs[layer + 1].copy_(self.hs[layer])  # LayerDrop: the layer is the identity for this batch
+            else:
+                for step in self._steps[start:end]:
+                    step()
+            position = end
+        for step in self._steps[position:]:
             step()
 
     # ------------------------------------------------------------------ backward (training plans only)
@@ -528,6 +648,15 @@ class EncoderPlan:
         grads: Dict[str, Tensor] = {}
         n_layers = len(p.layers)
         dh, dh16 = self.dh, self.dh_bf16
+        st = self.stoch  # train()-mode regularisation of the forward pass this backward pass belongs to
+
+        def branch_gradient(drop: ops.Dropout) -> bool:
+            """dh16 <- bf16(dh o keep * scale): gradient of a residual branch behind the forward's epilogue dropout."""
+            if drop.threshold:
+                ops.dropout_2d(dh, H, M, H, drop, out_bf16=dh16, ld_bf16=H)
+                return True
+            ops.cast_bf16_2d(dh, H, dh16, H, M, H)
+            return False
 
         def group(shapes: Sequence[Tuple[str, Tuple[int, ...]]]) -> Tuple[Tensor, Dict[str, Tensor]]:
             total = sum(int(torch.Size(shape).numel()) for _, shape in shapes)
@@ -573,26 +702,44 @@ class EncoderPlan:
             column = self.hidden_blocks.get(index + 1)
             if column is not None and index + 1 < n_layers:  # hidden state index+1 is also a classifier input (OUTPUT_i)
                 ops.add_2d(dh, H, d_x[:, column:], self.ldx, M, H)
-            # ---- feed forward: h_out = h_mid + W2 gelu(W1 LN2(h_mid) + b1) + b2
-            ops.cast_bf16_2d(dh, H, dh16, H, M, H)
+            if self.skipped[index]:  # LayerDrop: identity in the forward pass, no gradient for its parameters
+                if need_encoder:
+                    flat.zero_()
+                    wqkv, bqkv = g.pop("attention.qkv.weight"), g.pop("attention.qkv.bias")
+                    for part, name in enumerate(("q_proj", "k_proj", "v_proj")):
+                        g[f"attention.{name}.weight"] = wqkv[part * H : (part + 1) * H]
+                        g[f"attention.{name}.bias"] = bqkv[part * H : (part + 1) * H]
+                    done(flat, g, f"encoder.layers.{index}.")
+                continue
+            # ---- feed forward: h_out = h_mid + dropout(W2 gelu(W1 LN2(h_mid) + b1) + b2)
+            dropped = branch_gradient(st.feed_forward_output(index) if st else ops.NO_DROPOUT)
             ops.run_gemm(ops.make_dgrad_args(dh16, lw["w2"], rows=M, ld_dy=H, k=H, n=FF, ld_w=FF, gelu_bwd=sv["pre"], ld_gelu_bwd=FF,
                                              out_bf16=self.d_ff, ld_bf16=FF))  # fmt: skip
             if need_encoder:
                 wgrad(g["feed_forward.output_dense.weight"], dh16, H, H, sv["act"], FF, FF)
-                ops.colsum_f32(dh, M, H, H, out=g["feed_forward.output_dense.bias"])
+                if dropped:
+                    ops.colsum_bf16(dh16, M, H, H, out=g["feed_forward.output_dense.bias"])
+                else:
+                    ops.colsum_f32(dh, M, H, H, out=g["feed_forward.output_dense.bias"])
                 wgrad(g["feed_forward.intermediate_dense.weight"], self.d_ff, FF, FF, sv["ln2"], H, H)
                 ops.colsum_bf16(self.d_ff, M, FF, FF, out=g["feed_forward.intermediate_dense.bias"])
             ops.run_gemm(ops.make_dgrad_args(self.d_ff, lw["w1"], rows=M, ld_dy=FF, k=FF, n=H, ld_w=H, out_f32=self.d_ln, ld_f32=H))
             g2, _ = lw["ln2"]
             ops.layernorm_backward(self.mids[index], H, self.d_ln, H, M, H, g2, eps, dh, H, dh, H,
                                    g.get("final_layer_norm.weight"), g.get("final_layer_norm.bias"))  # fmt: skip
-            # ---- attention block: h_mid = h_in + Wo attention(Wqkv LN1(h_in)) + bo
-            ops.cast_bf16_2d(dh, H, dh16, H, M, H)
+            # ---- attention block: h_mid = h_in + dropout(Wo attention(Wqkv LN1(h_in)) + bo)
+            dropped = branch_gradient(st.attention_output(index) if st else ops.NO_DROPOUT)
             ops.run_gemm(ops.make_dgrad_args(dh16, lw["wo"], rows=M, ld_dy=H, k=H, n=H, ld_w=H, out_bf16=self.d_ctx, ld_bf16=H))
             if need_encoder:
                 wgrad(g["attention.out_proj.weight"], dh16, H, H, sv["ctx"], H, H)
-                ops.colsum_f32(dh, M, H, H, out=g["attention.out_proj.bias"])
-            ops.attention_backward(sv["q"], sv["k"], sv["v"], sv["ctx"], self.d_ctx, sv["lse"], self.delta, self.dqkv, self.att_lengths, N, heads, seq)
+                if dropped:
+                    ops.colsum_bf16(dh16, M, H, H, out=g["attention.out_proj.bias"])
+                else:
+                    ops.colsum_f32(dh, M, H, H, out=g["attention.out_proj.bias"])
+            ops.attention_backward(
+                sv["q"], sv["k"], sv["v"], sv["ctx"], self.d_ctx, sv["lse"], self.delta, self.dqkv, self.att_lengths, N, heads, seq,
+                st.attention(index) if st else ops.NO_DROPOUT,
+            )  # fmt: skip
             if need_encoder:
                 wgrad(g["attention.qkv.weight"], self.dqkv, 3 * H, 3 * H, sv["ln1"], H, H)
                 ops.colsum_bf16(self.dqkv, M, 3 * H, 3 * H, out=g["attention.qkv.bias"])
@@ -610,7 +757,9 @@ class EncoderPlan:
         column = self.hidden_blocks.get(0)
         if column is not None and n_layers > 0:
             ops.add_2d(dh, H, d_x[:, column:], self.ldx, M, H)
-        # ---- positional conv embedding (HF:764-765, 353-368): hs[0] = h_fp + gelu(conv(h_fp) + b)
+        # ---- positional conv embedding (HF:764-766, 353-368): hs[0] = dropout(h_fp + gelu(conv(h_fp) + b))
+        if st is not None and st.encoder_input().threshold:
+            ops.dropout_2d(dh, H, M, H, st.encoder_input(), out_f32=dh, ld_f32=H)
         taps = cfg.num_conv_pos_embeddings
         pc = w.encoder.pos_conv_embed.conv
         weight_g, weight_v = pc.parametrizations.weight.original0, pc.parametrizations.weight.original1
@@ -628,7 +777,9 @@ class EncoderPlan:
             ops.run_gemm(args)
             ops.posconv_weight_backward(raw, weight_g, weight_v, g["parametrizations.weight.original0"], g["parametrizations.weight.original1"])
             done(flat, g, "encoder.pos_conv_embed.conv.")
-        if need_projection:
+        embed = getattr(w, "masked_spec_embed", None)
+        need_embed = st is not None and self.spec_active and embed is not None and embed.requires_grad
+        if need_projection or need_embed:
             # data gradient of the grouped conv: the same sliding-tap GEMM with flipped taps, accumulated onto dh
             ops.run_gemm(
                 ops.make_gemm_args(
@@ -636,6 +787,17 @@ class EncoderPlan:
                     tap_pad=taps // 2 - 1, n=H, k=taps * 64, resid=dh, ld_resid=H, out_f32=dh, ld_f32=H, out_batch_rows=seq,
                 )
             )  # fmt: skip
+            if st is not None:
+                # SpecAugment: masked frames were replaced by masked_spec_embed (its gradient: their sum), then the
+                # feature projection dropout; both are functions of (seed, row, column) only
+                if self.spec_active:
+                    flat, g = group([("masked_spec_embed", (H,))])
+                    ops.masked_rows_backward(dh, H, M, H, self.spec_mask, g["masked_spec_embed"])
+                    if need_embed:
+                        done(flat, g, "")
+                if st.feature_projection().threshold:
+                    ops.dropout_2d(dh, H, M, H, st.feature_projection(), out_f32=dh, ld_f32=H)
+        if need_projection:
             # ---- feature projection (HF:422-434) behind the padded-frame zeroing (HF:753-756)
             if self.use_lengths:
                 ops.mask_rows(dh, H, M, H, self.frames32, seq)

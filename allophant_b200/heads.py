@@ -17,7 +17,7 @@ from __future__ import annotations
 import math
 import re
 from dataclasses import dataclass, field
-from typing import Any, Dict, List, Optional, Tuple
+from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import torch
 from torch import Tensor
@@ -75,6 +75,8 @@ class HeadsRuntime:
         self._composed_cache: Dict[Tuple[Any, ...], Tuple[Tensor, int]] = {}
         self._index_cache: Dict[Tuple[Any, ...], Dict[str, Tensor]] = {}
         self.gradient_reducer: Any = None  # allophant_b200.distributed.GradientReducer (data-parallel training)
+        self.skip_layers_override: Optional[Sequence[bool]] = None  # explicit LayerDrop decisions for train() mode (tests)
+        self.last_regularisation: Dict[str, Any] = {}
 
     # ------------------------------------------------------------------ static layout
     def _build_layout(self) -> None:
@@ -401,6 +403,12 @@ class HeadsRuntime:
         )
         return predictions
 
+    @staticmethod
+    def _rank() -> int:
+        import torch.distributed as dist
+
+        return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
     # ------------------------------------------------------------------ differentiable path (training)
     def _forward_differentiable(self, batch: Batch, target_feature_indices: Optional[Tensor], predict: bool, need_encoder: bool, need_feature_projection: bool):
         """Training / validation forward with autograd: the whole model is ONE ``torch.autograd.Function``.
@@ -408,22 +416,41 @@ class HeadsRuntime:
         torch only carries the graph edge from the returned logits back to the parameters; forward and
         backward run in ``liballophant_b200.so`` (``EncoderPlan.run`` / ``EncoderPlan.backward`` for the
         wav2vec2 encoder, the level GEMMs and the small kernels of ``aph_train.cu`` for the heads).
-        Stochastic regularisation (HF dropout / LayerDrop / SpecAugment, the dropout on the acoustic-model
-        outputs, ``acoustic_model.py:486-488``) is not applied: the arithmetic is the ``eval()``-mode
-        arithmetic, which is what the parity tests pin against the reference."""
+        In ``train()`` mode the stochastic regularisation of the reference is applied — HF dropout / LayerDrop /
+        SpecAugment inside the encoder (``engine.Stochastic``) and the dropout on the acoustic-model outputs
+        (``acoustic_model.py:486-488``) — with counter-based masks seeded from torch's CPU generator; in ``eval()``
+        mode the arithmetic is deterministic, which is what the parity tests pin against the reference."""
+        from .engine import Stochastic
         from .network.acoustic_model import Predictions
 
         acoustic = self.model._acoustic_model
         through_encoder = need_encoder or need_feature_projection
+        stochastic = None
+        input_dropout: Dict[int, ops.Dropout] = {}  # column of X -> dropout of that classifier input block
+        if self.model.training:
+            seed = int(torch.randint(0, 2**31 - 1, (1,))) ^ (self._rank() * 0x9E3779B1 & 0x7FFFFFFF)
+            if acoustic._model.training:  # HF regularises by module mode, also when the encoder is frozen
+                stochastic = Stochastic.from_config(acoustic._model.config, seed)
+                stochastic.skip_layers = self.skip_layers_override
+            rate = self.model._projection._acoustic_model_dropout
+            if rate is not None and rate.p > 0:
+                blocks = {0: -1, **{column: index for index, column in self.hidden_blocks.items()}}
+                if sum(1 for name, column in self.x_cols.items() if column == 0) > 1:
+                    raise NotImplementedError("acoustic_model_dropout with both OUTPUT and the last OUTPUT_i as dependencies")
+                input_dropout = {column: ops.Dropout.site(rate.p, seed, Stochastic.SITE_CLASSIFIER_INPUT + index + 1) for column, index in blocks.items()}
         with torch.no_grad():
-            plan, frames = acoustic.encode(batch, self.ldx, self.hidden_blocks, training=through_encoder)
+            plan, frames = acoustic.encode(batch, self.ldx, self.hidden_blocks, training=through_encoder or stochastic is not None, stochastic=stochastic)
             self._ensure_weights(plan.x.device)
+            hidden = self.model._projection._output_features
+            for column, drop in input_dropout.items():
+                ops.dropout_bf16_2d(plan.x[:, column:], self.ldx, plan.rows, hidden, drop)
+        self.last_regularisation = dict(stochastic=stochastic, input_dropout=input_dropout, plan=plan)  # introspection (tests)
         named = [(f"_projection.{name}", parameter) for name, parameter in self.model._projection.named_parameters()]
         if through_encoder:
             named += [(f"_acoustic_model._model.{name}", parameter) for name, parameter in acoustic._model.named_parameters() if parameter.requires_grad]
         state: Dict[str, Any] = dict(
             batch=batch, tfi=target_feature_indices, predict=predict, plan=plan, names=[n for n, _ in named], generation=None,
-            need_encoder=need_encoder, need_feature_projection=need_feature_projection,
+            need_encoder=need_encoder, need_feature_projection=need_feature_projection, input_dropout=input_dropout,
         )  # fmt: skip
         outputs = _ProjectionFunction.apply(self, state, *[p for _, p in named])
         names = state["head_names"]
@@ -576,6 +603,10 @@ class HeadsRuntime:
             param_grads = reducer.submit_tensors(param_grads)  # the heads' gradients travel while the encoder backward runs
         if through_encoder:
             assert d_x is not None
+            hidden = projection._output_features
+            for column, drop in state["input_dropout"].items():  # acoustic_model.py:486-488, same masks as the forward
+                block = d_x[:, column:]
+                ops.dropout_2d(block, d_x.shape[1], rows, hidden, drop, out_f32=block, ld_f32=d_x.shape[1])
             encoder_grads = plan.backward(
                 d_x, state["need_encoder"], state["need_feature_projection"], None if reducer is None else reducer.submit
             )

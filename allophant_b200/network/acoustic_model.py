@@ -366,7 +366,7 @@ class Wav2Vec2AcousticModel(AcousticModel):
         return plan
 
     def encode(
-        self, batch: Batch, ldx: int, hidden_blocks: Dict[int, int], capture: bool = False, training: bool = False
+        self, batch: Batch, ldx: int, hidden_blocks: Dict[int, int], capture: bool = False, training: bool = False, stochastic: Any = None
     ) -> Tuple[EncoderPlan, Tensor]:
         audio = batch.audio_features
         if not audio.is_cuda:
@@ -379,7 +379,7 @@ class Wav2Vec2AcousticModel(AcousticModel):
         lengths = batch.lengths.to(device=audio.device, dtype=torch.int64).contiguous()
         plan = self.plan_for(audio.shape[0], audio.shape[1], ldx, hidden_blocks, training)
         frames = torch.empty(audio.shape[0], device=audio.device, dtype=torch.int64)
-        plan.run(audio, lengths, frames, capture)
+        plan.run(audio, lengths, frames, capture, stochastic)
         return plan, frames
 
     def forward(self, batch: Batch, _predict: bool = False) -> Tuple[List[Tensor], Tensor]:

@@ -35,7 +35,10 @@ class Wav2Vec2EncoderConfig:
     num_conv_pos_embeddings: int = 128
     num_conv_pos_embedding_groups: int = 16
     do_stable_layer_norm: bool = True
+    apply_spec_augment: bool = True
     mask_time_prob: float = 0.075
+    mask_time_length: int = 10
+    mask_time_min_masks: int = 2
     mask_feature_prob: float = 0.0
     hidden_dropout: float = 0.1
     attention_dropout: float = 0.1

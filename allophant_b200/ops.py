@@ -8,7 +8,7 @@ there is no CPU path.
 from __future__ import annotations
 
 import ctypes
-from typing import List, Optional, Sequence, Tuple
+from typing import List, NamedTuple, Optional, Sequence, Tuple
 
 import torch
 from torch import Tensor
@@ -234,27 +234,69 @@ def linear_bf16(
 # --------------------------------------------------------------------------------------
 # attention
 # --------------------------------------------------------------------------------------
-def attention(q: Tensor, k: Tensor, v: Tensor, ctx: Tensor, frame_lengths: Tensor, n_utt: int, heads: int, seq: int, lse2: Optional[Tensor] = None) -> None:
+class Dropout(NamedTuple):
+    """One dropout site of a train-mode step: ``threshold = round(p * 65536)`` (0 = off), the site's 32-bit seed and the
+    scale ``1 / (1 - threshold / 65536)`` of the kept values (``aph_common.cuh``: ``drop_hash``)."""
+
+    threshold: int = 0
+    seed: int = 0
+    scale: float = 1.0
+
+    @classmethod
+    def site(cls, probability: float, step_seed: int, site: int) -> "Dropout":
+        threshold = int(round(float(probability) * 65536.0))
+        if threshold <= 0:
+            return cls()
+        if threshold >= 65536:
+            raise ValueError(f"dropout probability has to be < 1, got {probability}")
+        return cls(threshold, mix_seed(step_seed, site), 65536.0 / (65536.0 - threshold))
+
+
+def _fmix32(x: int) -> int:
+    x &= 0xFFFFFFFF
+    x ^= x >> 16
+    x = (x * 0x85EBCA6B) & 0xFFFFFFFF
+    x ^= x >> 13
+    x = (x * 0xC2B2AE35) & 0xFFFFFFFF
+    x ^= x >> 16
+    return x
+
+
+def mix_seed(step_seed: int, site: int) -> int:
+    """The 32-bit seed of dropout site ``site`` within the step seeded ``step_seed``."""
+    return _fmix32((step_seed & 0xFFFFFFFF) ^ _fmix32((site + 1) * 0x9E3779B1))
+
+
+NO_DROPOUT = Dropout()
+
+
+def attention(
+    q: Tensor, k: Tensor, v: Tensor, ctx: Tensor, frame_lengths: Tensor, n_utt: int, heads: int, seq: int, lse2: Optional[Tensor] = None,
+    dropout: Dropout = NO_DROPOUT,
+) -> None:  # fmt: skip
     """``q``/``k``/``v`` bf16 ``[n_utt*heads, seq, 64]`` (q pre-scaled) -> ``ctx`` bf16 ``[n_utt*seq, heads*64]``."""
     _require_cuda(q, k, v, ctx, frame_lengths, lse2)
     check(
-        lib.aph_attention_bf16_lse(q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), _ptr(lse2), frame_lengths.data_ptr(), n_utt, heads, seq, _stream()),
-        "aph_attention_bf16_lse",
+        lib.aph_attention_bf16_dropout(
+            q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), _ptr(lse2), frame_lengths.data_ptr(), n_utt, heads, seq,
+            dropout.threshold, dropout.seed, dropout.scale, _stream(),
+        ),  # fmt: skip
+        "aph_attention_bf16_dropout",
     )
 
 
 def attention_backward(
     q: Tensor, k: Tensor, v: Tensor, ctx: Tensor, d_ctx: Tensor, lse2: Tensor, delta_scratch: Tensor, dqkv: Tensor,
-    frame_lengths: Tensor, n_utt: int, heads: int, seq: int,
+    frame_lengths: Tensor, n_utt: int, heads: int, seq: int, dropout: Dropout = NO_DROPOUT,
 ) -> None:  # fmt: skip
     """(dQ | dK | dV) bf16 ``[n_utt*seq, 3*heads*64]`` from the forward's q/k/v/ctx/lse2 and ``d_ctx``."""
     _require_cuda(q, k, v, ctx, d_ctx, lse2, delta_scratch, dqkv, frame_lengths)
     check(
-        lib.aph_attention_backward_bf16(
+        lib.aph_attention_backward_bf16_dropout(
             q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), d_ctx.data_ptr(), lse2.data_ptr(), delta_scratch.data_ptr(),
-            dqkv.data_ptr(), frame_lengths.data_ptr(), n_utt, heads, seq, _stream(),
+            dqkv.data_ptr(), frame_lengths.data_ptr(), n_utt, heads, seq, dropout.threshold, dropout.seed, dropout.scale, _stream(),
         ),  # fmt: skip
-        "aph_attention_backward_bf16",
+        "aph_attention_backward_bf16_dropout",
     )
 
 
@@ -517,6 +559,42 @@ def cast_bf16(src: Tensor, dst: Optional[Tensor] = None) -> Tensor:
 def cast_bf16_2d(src: Tensor, ld_src: int, dst: Tensor, ld_dst: int, rows: int, cols: int) -> None:
     _require_cuda(src, dst)
     check(lib.aph_cast_bf16_2d(src.data_ptr(), ld_src, dst.data_ptr(), ld_dst, rows, cols, _stream()), "aph_cast_bf16_2d")
+
+
+def dropout_2d(
+    x: Tensor, ld_x: int, rows: int, cols: int, dropout: Dropout, out_f32: Optional[Tensor] = None, ld_f32: int = 0,
+    out_bf16: Optional[Tensor] = None, ld_bf16: int = 0, row_mask: Optional[Tensor] = None, row_fill: Optional[Tensor] = None,
+) -> None:  # fmt: skip
+    """``out = x * keep * scale`` (fp32 ``x``; ``out_f32`` may be ``x``), rows flagged in ``row_mask`` replaced by ``row_fill``."""
+    _require_cuda(x, out_f32, out_bf16, row_mask, row_fill)
+    check(
+        lib.aph_dropout_2d(
+            x.data_ptr(), ld_x, rows, cols, dropout.threshold, dropout.seed, dropout.scale, _ptr(row_mask), _ptr(row_fill),
+            _ptr(out_f32), ld_f32, _ptr(out_bf16), ld_bf16, _stream(),
+        ),  # fmt: skip
+        "aph_dropout_2d",
+    )
+
+
+def dropout_bf16_2d(x: Tensor, ld: int, rows: int, cols: int, dropout: Dropout) -> None:
+    _require_cuda(x)
+    check(lib.aph_dropout_bf16_2d(x.data_ptr(), ld, rows, cols, dropout.threshold, dropout.seed, dropout.scale, _stream()), "aph_dropout_bf16_2d")
+
+
+def spec_augment_mask(frames32: Tensor, seq: int, mask_prob: float, mask_length: int, min_masks: int, seed: int, mask: Tensor) -> None:
+    """uint8 ``mask`` ``[n_utt, seq]`` <- SpecAugment time mask (HF ``_compute_mask_indices``)."""
+    _require_cuda(frames32, mask)
+    if mask_length > seq:
+        raise ValueError(f"`mask_length` has to be smaller than `sequence_length`, but got `mask_length`: {mask_length} and `sequence_length`: {seq}`")
+    check(
+        lib.aph_spec_augment_mask(frames32.data_ptr(), frames32.numel(), seq, mask_prob, mask_length, min_masks, seed & 0xFFFFFFFF, mask.data_ptr(), _stream()),
+        "aph_spec_augment_mask",
+    )
+
+
+def masked_rows_backward(d: Tensor, ld: int, rows: int, cols: int, row_mask: Tensor, d_fill: Tensor) -> None:
+    _require_cuda(d, row_mask, d_fill)
+    check(lib.aph_masked_rows_backward(d.data_ptr(), ld, rows, cols, row_mask.data_ptr(), d_fill.data_ptr(), _stream()), "aph_masked_rows_backward")
 
 
 def pack_conv_weight(weight: Tensor, dst: Optional[Tensor] = None) -> Tensor:

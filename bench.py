@@ -485,7 +485,9 @@ def run_train_arm(args) -> None:
 
     estimator, allophones = build_training_estimator(device)
     model = estimator.model
-    model.train()
+    # train() mode: HF dropout 0.1 / attention dropout 0.1 / LayerDrop 0.1 / SpecAugment 0.075 are
+    # applied by the CUDA path with counter-based masks; --eval-arithmetic times the deterministic arithmetic instead
+    model.train(not args.eval_arithmetic)
     reducer = GradientReducer() if distributed else None
     attach_gradient_reducer(model, reducer)
 
@@ -627,6 +629,8 @@ def run_train_arm(args) -> None:
         plan_frames = int(frames.max())
         gemm_ms = sum(a.elapsed_time(b) for a, b in gemm_events)
         flops = 3.0 * encoder_flops(plan_frames)["linear"] * TRAIN_BATCH  # forward + dgrad + wgrad over the padded frame count
+        skipped = list(model._heads.last_regularisation["plan"].skipped)  # LayerDrop decisions of this very step
+        flops *= (len(skipped) - sum(skipped)) / max(1, len(skipped))
         peaks = measured_peaks()
         achieved = flops / (gemm_ms / 1000.0) / 1e12
         peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
@@ -658,7 +662,8 @@ def run_train_arm(args) -> None:
             "workload": "BASELINE configs[2]: Allophant Multitask (XLS-R-300M shape, random init, allophone layer over "
             f"{TRAIN_LANGUAGES} languages x {TRAIN_PHONES} phones, feature extractor frozen) training step: forward + 37-head CTC + backward"
             f"{' + overlapped NCCL gradient all-reduce' if distributed else ''} + global-norm clip + Adam + warm-up LR; {TRAIN_BATCH} utterances per GPU, "
-            "U[3 s, 15 s], eval-mode arithmetic (no dropout / SpecAugment)",
+            "U[3 s, 15 s], " + ("eval()-mode arithmetic (no dropout / LayerDrop / SpecAugment)" if args.eval_arithmetic else
+                                "train() mode: hidden/attention/feature-projection dropout 0.1, LayerDrop 0.1, SpecAugment 0.075 x 10 frames"),
             "batch_per_gpu": TRAIN_BATCH,
             "padded_seconds": samples / SAMPLE_RATE,
             "parallelism": f"dp{world}",
@@ -682,6 +687,7 @@ def main() -> None:
     parser.add_argument("--warmup", type=int, default=3)
     parser.add_argument("--impl", choices=["b200", "reference"], default="b200")
     parser.add_argument("--skip-cpu-baseline", action="store_true")
+    parser.add_argument("--eval-arithmetic", action="store_true", help="train workload: eval()-mode arithmetic (no dropout / LayerDrop / SpecAugment)")
     parser.add_argument("--batch", type=int, default=BATCH, help="utterances per GPU (predict workload)")
     parser.add_argument("--seconds", type=int, default=SECONDS, help="seconds per utterance (predict workload)")
     parser.add_argument("--inventory", type=int, default=INVENTORY, help="phonemes of the target inventory (composed phoneme head)")

@@ -29,7 +29,7 @@ extern "C" {
 #define APH_ERR_CUDA (-2)        /* CUDA runtime / driver error                    */
 #define APH_ERR_UNSUPPORTED (-3) /* valid request outside the implemented envelope */
 
-#define APH_ABI_VERSION 2
+#define APH_ABI_VERSION 3
 
 /* ---- library ------------------------------------------------------------ */
 int aph_abi_version(void);
@@ -115,6 +115,12 @@ typedef struct aph_gemm_args {
   const void* gelu_bwd;   /* store epilogue: v *= gelu'(pre[row][col]) with pre bf16 [rows][ld_gelu_bwd] or NULL */
   int64_t ld_gelu_bwd;
   void* vmat;             /* APH_EPI_QKV: V row-major [b,h,t,64] (required) */
+  /* train-mode dropout of (acc*scale + bias [gelu]) BEFORE the residual is added (HF hidden_dropout of the attention
+   * and feed-forward blocks): keep iff the element's 16-bit hash >= drop_threshold (0 = off), kept values * drop_scale.
+   * The mask is a function of (drop_seed, output row, output column) only: see aph_dropout_2d. */
+  uint32_t drop_threshold;
+  uint32_t drop_seed;
+  float drop_scale;
 } aph_gemm_args;
 
 int aph_gemm_bf16(const aph_gemm_args* args, void* stream);
@@ -142,6 +148,40 @@ int aph_attention_backward_bf16(const void* q, const void* k, const void* v, con
                                 const void* d_ctx, const float* lse2, float* delta_scratch,
                                 void* dqkv, const int32_t* lengths, int32_t n_utt, int32_t heads,
                                 int32_t T, void* stream);
+
+/* Train-mode variants with attention dropout (HF Wav2Vec2Attention, `attention_dropout`): the softmax probabilities
+ * are dropped with a counter-based keep mask — element (b*heads+h, q, k) is kept iff the 16-bit half (k & 1) of
+ * hash(seed, (b*heads+h)*T + q, k >> 1) is >= drop_threshold (= round(p * 65536); 0 = no dropout) — and kept values are
+ * scaled by drop_scale = 1/(1-p).  The backward pass regenerates the mask from the same (threshold, seed). */
+int aph_attention_bf16_dropout(const void* q, const void* k, const void* v, void* ctx, float* lse2,
+                               const int32_t* lengths, int32_t n_utt, int32_t heads, int32_t T,
+                               uint32_t drop_threshold, uint32_t drop_seed, float drop_scale, void* stream);
+int aph_attention_backward_bf16_dropout(const void* q, const void* k, const void* v, const void* ctx,
+                                        const void* d_ctx, const float* lse2, float* delta_scratch, void* dqkv,
+                                        const int32_t* lengths, int32_t n_utt, int32_t heads, int32_t T,
+                                        uint32_t drop_threshold, uint32_t drop_seed, float drop_scale,
+                                        void* stream);
+
+/* ---- train-mode stochastic regularisation (HF modeling_wav2vec2.py dropout sites, SpecAugment; -------------
+ * ---- acoustic_model.py:486-488) -------------------------------------------------------------------------- */
+/* out = x * keep * scale for fp32 x [rows][ld_x] (cols % 4 == 0): element (row, col) is kept iff the 16-bit half
+ * (col & 1) of hash(seed, row, col >> 1) >= threshold.  Rows flagged in row_mask (uint8 [rows], optional: SpecAugment)
+ * are replaced by row_fill[cols] (NULL: zeros) instead.  out_f32 may alias x; out_bf16 optional.  The same call applied
+ * to a gradient is the backward pass. */
+int aph_dropout_2d(const float* x, int64_t ld_x, int64_t rows, int32_t cols, uint32_t threshold, uint32_t seed,
+                   float scale, const uint8_t* row_mask, const float* row_fill, float* out_f32, int64_t ld_f32,
+                   void* out_bf16, int64_t ld_bf16, void* stream);
+/* bf16 in place (blocks of the classifier feature matrix, acoustic_model.py:486-488) */
+int aph_dropout_bf16_2d(void* x_bf16, int64_t ld, int64_t rows, int32_t cols, uint32_t threshold, uint32_t seed,
+                        float scale, void* stream);
+/* SpecAugment time mask (HF _compute_mask_indices): uint8 mask [n_utt][seq], spans of mask_length frames drawn
+ * without replacement inside each utterance's frames[i] valid frames. */
+int aph_spec_augment_mask(const int32_t* frames, int32_t n_utt, int32_t seq, float mask_prob, int32_t mask_length,
+                          int32_t min_masks, uint32_t seed, uint8_t* mask, void* stream);
+/* backward of the row replacement: d_fill[col] = sum of d over flagged rows; flagged rows of d are zeroed */
+int aph_masked_rows_backward(float* d, int64_t ld, int64_t rows, int32_t cols, const uint8_t* row_mask,
+                             float* d_fill, void* stream);
+
 
 /* Debug aid: progress markers of block (0,0) of the attention backward kernels are written to this
  * host-mapped int32[16] array (NULL = off, the default). */

@@ -29,6 +29,7 @@ re-checks the restatement against those files wherever the tests run.
 """
 from __future__ import annotations
 
+import contextlib
 import math
 import re
 from dataclasses import dataclass, field
@@ -295,14 +296,72 @@ class OracleModel:
     ) -> Dict[str, Tensor]:
         return self._project(hidden_states, language_ids, target_feature_indices, predict)
 
-    def _encode(self, audio: Tensor, lengths: Tensor) -> Tuple[List[Tensor], Tensor]:
-        """Wav2Vec2AcousticModel.forward, acoustic_model.py:837-853 (do_normalize / return_attention_mask = True)."""
+    def _encode(self, audio: Tensor, lengths: Tensor, regularisation: Optional[Dict[str, object]] = None) -> Tuple[List[Tensor], Tensor]:
+        """Wav2Vec2AcousticModel.forward, acoustic_model.py:837-853 (do_normalize / return_attention_mask = True).
+
+        ``regularisation``: the train()-mode stochastic ops of the HF encoder with EXPLICIT masks instead of torch's RNG
+        (see ``explicit_regularisation``), so that a CUDA run with counter-based masks can be compared exactly."""
         mask = mask_sequence(lengths)
-        hidden_states = self.encoder(
-            zero_mean_unit_var_norm(audio, lengths, mask), mask.long(), output_hidden_states=True
-        ).hidden_states
         frames = conv_lengths(lengths, self.config.conv_kernel, self.config.conv_stride)
+        normed = zero_mean_unit_var_norm(audio, lengths, mask)
+        if regularisation is None:
+            hidden_states = self.encoder(normed, mask.long(), output_hidden_states=True).hidden_states
+        else:
+            with self.explicit_regularisation(regularisation):
+                hidden_states = self.encoder(
+                    normed, mask.long(), output_hidden_states=True, mask_time_indices=regularisation.get("spec")
+                ).hidden_states
+            if "classifier_input" in regularisation:  # acoustic_model.py:486-488 (batch-first masks by hidden-state index)
+                hidden_states = list(hidden_states)
+                for index, factor in regularisation["classifier_input"].items():
+                    hidden_states[index] = hidden_states[index] * factor
         return [h.transpose(0, 1) for h in hidden_states], frames
+
+    @contextlib.contextmanager
+    def explicit_regularisation(self, masks: Dict[str, object]):
+        """Runs the eval()-mode HF encoder with the train()-mode ops applied through EXPLICIT multiplicative masks:
+        ``feature_projection`` / ``encoder_input`` / ``attention_output.<l>`` / ``feed_forward_output.<l>``: fp32
+        ``[N, T', H]`` (keep / (1-p) or 0), ``attention.<l>``: ``[N, heads, T', T']``, ``skip``: LayerDrop decisions
+        (HF modeling_wav2vec2.py:431-433, 766, 774-786, 458, 643, 572); ``spec`` (bool ``[N, T']``) is passed to the model as
+        ``mask_time_indices``."""
+        from transformers.models.wav2vec2 import modeling_wav2vec2 as hf
+
+        handles = []
+
+        def scale_output(module: nn.Module, key: str) -> None:
+            if key in masks:
+                handles.append(module.register_forward_hook(lambda _m, _i, out, key=key: out * masks[key]))
+
+        scale_output(self.encoder.feature_projection.dropout, "feature_projection")
+        scale_output(self.encoder.encoder.dropout, "encoder_input")
+        skip = masks.get("skip") or []
+        for index, layer in enumerate(self.encoder.encoder.layers):
+            scale_output(layer.dropout, f"attention_output.{index}")
+            scale_output(layer.feed_forward.output_dropout, f"feed_forward_output.{index}")
+            layer.attention._oracle_index = index
+            if index < len(skip) and skip[index]:
+                handles.append(layer.register_forward_hook(lambda _m, args, _out: (args[0],)))
+        original, implementation = hf.eager_attention_forward, self.encoder.config._attn_implementation
+
+        def attention(module, query, key, value, attention_mask, scaling=None, dropout=0.0, **kwargs):
+            weights = torch.matmul(query, key.transpose(2, 3)) * (query.size(-1) ** -0.5 if scaling is None else scaling)
+            if attention_mask is not None:
+                weights = weights + attention_mask
+            weights = nn.functional.softmax(weights, dim=-1)
+            factor = masks.get(f"attention.{module._oracle_index}")
+            if factor is not None:
+                weights = weights * factor
+            return torch.matmul(weights, value).transpose(1, 2).contiguous(), weights
+
+        hf.eager_attention_forward = attention
+        self.encoder.config._attn_implementation = "eager"
+        try:
+            yield
+        finally:
+            hf.eager_attention_forward = original
+            self.encoder.config._attn_implementation = implementation
+            for handle in handles:
+                handle.remove()
 
     def _compose(self, inputs: Tensor, target_feature_indices: Optional[Tensor]) -> Tensor:
         """EmbeddingCompositionLayer.forward, acoustic_model.py:219-234."""
@@ -404,15 +463,16 @@ class OracleModel:
         label_lengths: Dict[str, Tensor],
         language_ids: Optional[Tensor] = None,
         target_feature_indices: Optional[Tensor] = None,
+        regularisation: Optional[Dict[str, object]] = None,
     ) -> Tuple[Tensor, Dict[str, float], Dict[str, Tensor]]:
-        """``estimator.py:708-738`` in eval()-mode arithmetic: ``model(batch)`` (predict=False), per-head
+        """``estimator.py:708-738`` in eval()-mode arithmetic (or with explicit train()-mode masks): ``model(batch)`` (predict=False), per-head
         ``CTCWrapper``, ``loss = sum_heads ctc / sum_heads sum_utt label_length``, ``backward()``.
         Returns (loss, per-head CTC sums, gradients by state_dict name)."""
         named = self.trainable_parameters()
         for parameter in named.values():
             parameter.grad = None
         with torch.enable_grad():
-            hidden_states, frames = self._encode(audio, lengths)
+            hidden_states, frames = self._encode(audio, lengths, regularisation)
             outputs = self._project(hidden_states, language_ids, target_feature_indices, predict=False)
             outputs.pop("phone", None)  # estimator.py:717-718
             total = torch.tensor(0, dtype=torch.float32)

@@ -108,3 +108,45 @@ def cuda_model_for_spec(spec: restatement.OracleSpec, oracle: restatement.Oracle
 
 def rel_err(value: torch.Tensor, reference: torch.Tensor) -> float:
     return float((value.double().cpu() - reference.double().cpu()).abs().max() / reference.double().abs().max().clamp_min(1e-12))
+
+
+# ------------------------------------------------------------------ train()-mode masks (restated from aph_common.cuh)
+def _fmix(x: np.ndarray) -> np.ndarray:
+    x = x.astype(np.uint64) & 0xFFFFFFFF
+    x ^= x >> 16
+    x = (x * 0x85EBCA6B) & 0xFFFFFFFF
+    x ^= x >> 13
+    x = (x * 0xC2B2AE35) & 0xFFFFFFFF
+    x ^= x >> 16
+    return x
+
+
+def keep_mask(dropout, rows: int, cols: int) -> torch.Tensor:
+    """fp32 [rows, cols] multiplicative mask (scale or 0) of ``allophant_b200.ops.Dropout`` — the numpy restatement of
+    ``drop_row_key`` / ``drop_hash`` / ``drop_keep`` (``aph_common.cuh``)."""
+    if dropout.threshold == 0:
+        return torch.ones(rows, cols)
+    row = np.arange(rows, dtype=np.uint64)[:, None]
+    col = np.arange(cols, dtype=np.uint64)[None, :]
+    key = _fmix(np.uint64(dropout.seed) ^ ((row * 0x9E3779B1) & 0xFFFFFFFF))
+    hashed = _fmix(key ^ (((col >> 1) * 0x9E3779B1) & 0xFFFFFFFF))
+    half = np.where(col & 1, hashed >> 16, hashed & 0xFFFF)
+    return torch.from_numpy((half >= dropout.threshold).astype(np.float32) * np.float32(dropout.scale))
+
+
+def regularisation_masks(stochastic, n_utt: int, seq: int, hidden: int, heads: int, n_layers: int, skipped, spec_mask=None):
+    """The explicit masks ``oracle.restatement.OracleModel.explicit_regularisation`` takes, equal to what the CUDA
+    kernels derive from ``stochastic`` (an ``allophant_b200.engine.Stochastic``)."""
+    rows = n_utt * seq
+    masks = {
+        "feature_projection": keep_mask(stochastic.feature_projection(), rows, hidden).view(n_utt, seq, hidden),
+        "encoder_input": keep_mask(stochastic.encoder_input(), rows, hidden).view(n_utt, seq, hidden),
+        "skip": list(skipped),
+    }
+    for layer in range(n_layers):
+        masks[f"attention.{layer}"] = keep_mask(stochastic.attention(layer), n_utt * heads * seq, seq).view(n_utt, heads, seq, seq)
+        masks[f"attention_output.{layer}"] = keep_mask(stochastic.attention_output(layer), rows, hidden).view(n_utt, seq, hidden)
+        masks[f"feed_forward_output.{layer}"] = keep_mask(stochastic.feed_forward_output(layer), rows, hidden).view(n_utt, seq, hidden)
+    if spec_mask is not None:
+        masks["spec"] = spec_mask.view(n_utt, seq).bool()
+    return masks
