@@ -149,6 +149,11 @@ _SIGNATURES = {
     "aph_multi_tensor_sumsq": [_P, _P, _I32, _P, _P],
     "aph_multi_tensor_scale": [_P, _P, _I32, _P, _F, _P],
     "aph_multi_tensor_adam": [_P, _P, _P, _I32, _F, _F, _F, _F, _F, _I64, _P, _F, _P],
+    "aph_layernorm_any": [_P, _I64, _I64, _I32, _P, _P, c_float, _P, _I64, _P, _I64, _P],
+    "aph_add_sinusoidal": [_P, _I64, _I32, _I32, _I32, _P, _P],
+    "aph_transpose_nfl": [_P, _I32, _I32, _I32, _P, _I64, _P],
+    "aph_reflect_pad_bf16": [_P, _I64, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P],
+    "aph_glu_rows": [_P, _I64, _I64, _I32, _P, _I64, _P],
     "aph_collate_pad_f32": [_P, _P, _I64, _I64, _P, _I32],
     "aph_edit_statistics_batch": [_P, _P, _P, _P, _I64, _P, _P, _I32],
     "aph_ctc_states_pad": [_I32],

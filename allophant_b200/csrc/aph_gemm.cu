@@ -419,9 +419,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
               }
             }
           }
-          if (p.gelu) {
+          if (p.gelu == 1) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if (p.gelu == 2) {  // APH_ACT_RELU
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (p.gelu == 3) {  // APH_ACT_LEAKY_RELU (negative slope 0.01, nn.LeakyReLU's default)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.01f * v[j];
           }
           if (p.gelu_bwd != nullptr && row_ok) {  // backward of GELU: dL/d(pre) = dL/d(act) * gelu'(pre)
             const uint4* s4 = reinterpret_cast<const uint4*>(p.gelu_bwd + grow * p.ld_gelu_bwd + col);
@@ -745,6 +751,7 @@ extern "C" int aph_gemm_bf16(const aph_gemm_args* a, void* stream_) {
   p.tap_pad = a->tap_pad;
   p.n = a->n;
   p.gelu = a->gelu;
+  APH_REQUIRE(a->gelu >= 0 && a->gelu <= 3, "gelu: 0 none, 1 GELU(erf), 2 ReLU, 3 LeakyReLU(0.01)");
   p.scale = a->scale;
   p.bias = a->bias;
   p.resid = a->resid;

@@ -1,0 +1,174 @@
+// Small kernels of the from-scratch pre-LN transformer acoustic model (acoustic_model.py:34-69, 564-759; frontend.py:98-276;
+// padding.py:24-53): LayerNorm over an arbitrary feature width with optional affine parameters, sinusoidal position
+// embeddings, [N, F, L] -> channels-last transpose, variable-length reflect padding and the gated linear unit.  All
+// HBM-bound elementwise / row kernels; the GEMMs and the attention of this model are the kernels of aph_gemm.cu /
+// aph_attention.cu.
+#include "aph_common.cuh"
+
+namespace aph {
+
+// nn.LayerNorm over the last axis, any width, elementwise_affine optional; warp per row, fp32 two-pass statistics.
+__global__ void __launch_bounds__(256) layernorm_any_kernel(const float* __restrict__ x, long long ld_x, long long rows, int cols,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                            float* out_f32, long long ld_f32, __nv_bfloat16* out_bf16, long long ld_bf16) {
+  const long long row = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* src = x + row * ld_x;
+  float sum = 0.f;
+  for (int c = lane; c < cols; c += 32) sum += src[c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / static_cast<float>(cols);
+  float sq = 0.f;
+  for (int c = lane; c < cols; c += 32) {
+    const float d = src[c] - mean;
+    sq += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / static_cast<float>(cols) + eps);
+  for (int c = lane; c < cols; c += 32) {
+    float v = (src[c] - mean) * rstd;
+    if (gamma != nullptr) v = v * gamma[c] + beta[c];
+    if (out_f32 != nullptr) out_f32[row * ld_f32 + c] = v;
+    if (out_bf16 != nullptr) out_bf16[row * ld_bf16 + c] = __float2bfloat16(v);
+  }
+}
+
+// x[n][t][c] += sin / cos(t * bases[c]) (even / odd c): SinusoidalPositionEmbeddings.forward, acoustic_model.py:58-69
+__global__ void __launch_bounds__(256) add_sinusoidal_kernel(float* x, long long ld, int seq, int cols, long long rows,
+                                                             const float* __restrict__ bases) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const long long row = i / cols;
+    const int c = static_cast<int>(i - row * cols);
+    const float angle = static_cast<float>(row % seq) * bases[c];
+    x[row * ld + c] += (c & 1) ? cosf(angle) : sinf(angle);
+  }
+}
+
+// [N][F][L] fp32 -> [N][L][F] fp32 (ld_out >= F), 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256) transpose_nfl_kernel(const float* __restrict__ in, int features, int length, float* __restrict__ out,
+                                                            long long ld_out) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int f0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float* src = in + static_cast<long long>(n) * features * length;
+  for (int j = ty; j < 32; j += 8)
+    if (f0 + j < features && l0 + tx < length) tile[j][tx] = src[static_cast<long long>(f0 + j) * length + l0 + tx];
+  __syncthreads();
+  float* dst = out + static_cast<long long>(n) * length * ld_out;
+  for (int j = ty; j < 32; j += 8)
+    if (l0 + j < length && f0 + tx < features) dst[static_cast<long long>(l0 + j) * ld_out + f0 + tx] = tile[tx][j];
+}
+
+// LengthWrapper masking + VariableLengthReflectPad (frontend.py:63-74, padding.py:41-53) on channels-last activations:
+// out[n][p][c], p in [0, L + left + right); q = p - left:
+//   q < 0: xm[left - p]      0 <= q < len: x[q]      len <= q < len + right: x[len - 2 - (q - len)]      else 0
+// with xm = x masked to the utterance's own length (frames >= len read as 0).  Output bf16 (the conv GEMM's A operand).
+__global__ void __launch_bounds__(256) reflect_pad_kernel(const float* __restrict__ x, long long ld_x, const int* __restrict__ lengths,
+                                                          int length, int channels, int left, int right, int reflect,
+                                                          __nv_bfloat16* __restrict__ out) {
+  const int padded = length + left + right;
+  const long long total = static_cast<long long>(gridDim.y) * padded * channels;
+  (void)total;
+  const int n = blockIdx.y;
+  const int len = min(lengths[n], length);
+  const float* src = x + static_cast<long long>(n) * length * ld_x;
+  __nv_bfloat16* dst = out + static_cast<long long>(n) * padded * channels;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < static_cast<long long>(padded) * channels; i += 256ll * gridDim.x) {
+    const int p = static_cast<int>(i / channels);
+    const int c = static_cast<int>(i - static_cast<long long>(p) * channels);
+    const int q = p - left;
+    int t = -1;
+    if (q < 0) {
+      if (reflect) t = left - p;
+    } else if (q < len) {
+      t = q;
+    } else if (reflect && q < len + right) {
+      t = len - 2 - (q - len);
+    }
+    const float v = (t >= 0 && t < len) ? src[static_cast<long long>(t) * ld_x + c] : 0.f;
+    dst[i] = __float2bfloat16(v);
+  }
+}
+
+// functional.glu over the channel axis of a channels-last matrix: out[r][c] = y[r][c] * sigmoid(y[r][O + c])
+__global__ void __launch_bounds__(256) glu_rows_kernel(const float* __restrict__ y, long long ld_y, long long rows, int out_channels,
+                                                       float* __restrict__ out, long long ld_out) {
+  const long long total = rows * out_channels;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const long long row = i / out_channels;
+    const int c = static_cast<int>(i - row * out_channels);
+    const float a = y[row * ld_y + c], g = y[row * ld_y + out_channels + c];
+    out[row * ld_out + c] = a / (1.0f + __expf(-g));
+  }
+}
+
+}  // namespace aph
+
+using namespace aph;
+
+static unsigned blocks_for(long long items) {
+  long long blocks = (items + 255) / 256;
+  const long long cap = 148ll * 16;
+  return static_cast<unsigned>(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+extern "C" int aph_layernorm_any(const float* x, int64_t ld_x, int64_t rows, int32_t cols, const float* gamma, const float* beta, float eps,
+                                 float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16, void* stream_) {
+  APH_REQUIRE(x && rows >= 0 && cols > 0, "layernorm_any: bad arguments");
+  APH_REQUIRE((gamma == nullptr) == (beta == nullptr), "layernorm_any: gamma and beta come together");
+  APH_REQUIRE(out_f32 || out_bf16, "layernorm_any: no output");
+  if (rows == 0) return APH_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  layernorm_any_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(x, ld_x, rows, cols, gamma, beta, eps, out_f32, ld_f32,
+                                                                                    static_cast<__nv_bfloat16*>(out_bf16), ld_bf16);
+  APH_POST_LAUNCH(1);
+  return APH_OK;
+}
+
+extern "C" int aph_add_sinusoidal(float* x, int64_t ld, int32_t n_utt, int32_t seq, int32_t cols, const float* bases, void* stream_) {
+  APH_REQUIRE(x && bases && n_utt >= 0 && seq > 0 && cols > 0, "add_sinusoidal: bad arguments");
+  if (n_utt == 0) return APH_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long rows = static_cast<long long>(n_utt) * seq;
+  add_sinusoidal_kernel<<<blocks_for(rows * cols), 256, 0, stream>>>(x, ld, seq, cols, rows, bases);
+  APH_POST_LAUNCH(1);
+  return APH_OK;
+}
+
+extern "C" int aph_transpose_nfl(const float* in, int32_t n_utt, int32_t features, int32_t length, float* out, int64_t ld_out, void* stream_) {
+  APH_REQUIRE(in && out && n_utt >= 0 && features > 0 && length > 0 && ld_out >= features, "transpose_nfl: bad arguments");
+  APH_REQUIRE(n_utt <= 65535, "transpose_nfl: at most 65535 utterances");
+  if (n_utt == 0) return APH_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  dim3 grid(static_cast<unsigned>((length + 31) / 32), static_cast<unsigned>((features + 31) / 32), static_cast<unsigned>(n_utt));
+  transpose_nfl_kernel<<<grid, 256, 0, stream>>>(in, features, length, out, ld_out);
+  APH_POST_LAUNCH(1);
+  return APH_OK;
+}
+
+extern "C" int aph_reflect_pad_bf16(const float* x, int64_t ld_x, const int32_t* lengths, int32_t n_utt, int32_t length, int32_t channels,
+                                    int32_t left, int32_t right, int32_t reflect, void* out_bf16, void* stream_) {
+  APH_REQUIRE(x && lengths && out_bf16 && n_utt >= 0 && length > 0 && channels > 0 && left >= 0 && right >= 0, "reflect_pad: bad arguments");
+  APH_REQUIRE(n_utt <= 65535, "reflect_pad: at most 65535 utterances");
+  if (n_utt == 0) return APH_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long per_utt = static_cast<long long>(length + left + right) * channels;
+  dim3 grid(blocks_for(per_utt), static_cast<unsigned>(n_utt));
+  reflect_pad_kernel<<<grid, 256, 0, stream>>>(x, ld_x, lengths, length, channels, left, right, reflect, static_cast<__nv_bfloat16*>(out_bf16));
+  APH_POST_LAUNCH(1);
+  return APH_OK;
+}
+
+extern "C" int aph_glu_rows(const float* y, int64_t ld_y, int64_t rows, int32_t out_channels, float* out, int64_t ld_out, void* stream_) {
+  APH_REQUIRE(y && out && rows >= 0 && out_channels > 0 && ld_y >= 2 * out_channels && ld_out >= out_channels, "glu_rows: bad arguments");
+  if (rows == 0) return APH_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  glu_rows_kernel<<<blocks_for(rows * out_channels), 256, 0, stream>>>(y, ld_y, rows, out_channels, out, ld_out);
+  APH_POST_LAUNCH(1);
+  return APH_OK;
+}

@@ -75,7 +75,7 @@ typedef struct aph_gemm_args {
   int32_t k;              /* multiple of 64 */
   /* epilogue */
   int32_t epilogue;       /* APH_EPI_* */
-  int32_t gelu;
+  int32_t gelu;           /* activation after bias: 0 none, 1 GELU (erf), 2 ReLU, 3 LeakyReLU(0.01) */
   float scale;
   const float* bias;      /* [n] or NULL */
   const float* resid;     /* fp32 [rows][ld_resid] or NULL; may alias out_f32 */
@@ -426,6 +426,26 @@ int aph_edit_statistics_batch(const int64_t* expected_host, const int64_t* expec
 /* EditStatistics.word_error_rate (src/edit_distance.rs:311-317): (S+D+I)/(S+D+C) in f32. */
 float aph_word_error_rate(uint64_t insertions, uint64_t deletions, uint64_t substitutions,
                           uint64_t correct);
+
+/* ---- from-scratch pre-LN transformer acoustic model (acoustic_model.py:34-69, 564-759; frontend.py; padding.py) */
+/* nn.LayerNorm over the last axis of fp32 x [rows][ld_x], any width; gamma/beta NULL = elementwise_affine=False. */
+int aph_layernorm_any(const float* x, int64_t ld_x, int64_t rows, int32_t cols, const float* gamma,
+                      const float* beta, float eps, float* out_f32, int64_t ld_f32, void* out_bf16,
+                      int64_t ld_bf16, void* stream);
+/* SinusoidalPositionEmbeddings.forward (acoustic_model.py:58-69): x[n][t][c] += sin|cos(t * bases[c]). */
+int aph_add_sinusoidal(float* x, int64_t ld, int32_t n_utt, int32_t seq, int32_t cols, const float* bases,
+                       void* stream);
+/* features [N][F][L] fp32 -> channels-last [N][L][ld_out] fp32 (the permute of acoustic_model.py:672). */
+int aph_transpose_nfl(const float* in, int32_t n_utt, int32_t features, int32_t length, float* out,
+                      int64_t ld_out, void* stream);
+/* LengthWrapper masking + VariableLengthReflectPad (frontend.py:63-74, padding.py:41-53) on channels-last fp32
+ * x [N][length][ld_x] -> bf16 [N][length+left+right][channels]; reflect = 0: zero padding. */
+int aph_reflect_pad_bf16(const float* x, int64_t ld_x, const int32_t* lengths, int32_t n_utt, int32_t length,
+                         int32_t channels, int32_t left, int32_t right, int32_t reflect, void* out_bf16,
+                         void* stream);
+/* functional.glu over channels (frontend.py:136): out[r][c] = y[r][c] * sigmoid(y[r][out_channels + c]). */
+int aph_glu_rows(const float* y, int64_t ld_y, int64_t rows, int32_t out_channels, float* out, int64_t ld_out,
+                 void* stream);
 
 /* ---- host feeding (batching.py:171-215) -------------------------------------------------------- */
 /* rnn.pad_sequence of the utterances of a batch: n fp32 arrays of lengths_host[i] samples -> zero-padded
