@@ -192,6 +192,119 @@ class Wav2Vec2PretrainedConfig:
         }
 
 
+# ---- from-scratch pre-LN transformer acoustic model (config.py:396-520, 716-735 of the reference) ----
+@dataclass
+class DropoutConfig:
+    TYPE: ClassVar[str] = "dropout"
+    rate: float = 0
+
+
+@dataclass
+class LayerNormConfig:
+    TYPE: ClassVar[str] = "layer_norm"
+    affine: bool = False
+
+
+@dataclass
+class Glu1dConfig:
+    TYPE: ClassVar[str] = "glu1d"
+    out_channels: int = 0
+    kernel: int = 1
+    stride: int = 1
+
+
+@dataclass
+class MaxPoolingConfig:
+    TYPE: ClassVar[str] = "max_pool"
+    size: int = 1
+
+
+_LAYER_TYPES = {cls.TYPE: cls for cls in (DropoutConfig, LayerNormConfig, Glu1dConfig, MaxPoolingConfig)}
+
+
+def _dump_keyed(value: Any, key: str = "type") -> Dict[str, Any]:
+    return {key: value.TYPE, **dataclasses.asdict(value)}
+
+
+@dataclass
+class SequentialFrontendConfig:
+    layers: List[Any] = field(default_factory=list)
+
+    @classmethod
+    def load(cls, mapping: Mapping[str, Any]) -> "SequentialFrontendConfig":
+        layers = []
+        for entry in mapping.get("layers", []):
+            kind = entry.get("type")
+            if kind not in _LAYER_TYPES:
+                raise ValueError(f"Unsupported layer type: {kind!r}")
+            layers.append(_LAYER_TYPES[kind](**{k: v for k, v in entry.items() if k != "type"}))
+        return cls(layers)
+
+    def dump(self) -> Dict[str, Any]:
+        return {"layers": [_dump_keyed(layer) for layer in self.layers]}
+
+
+@dataclass
+class DirectFrontendConfig:
+    TYPE: ClassVar[str] = "direct"
+    input_dropout: float = 0
+
+
+@dataclass
+class LinearFrontendConfig:
+    TYPE: ClassVar[str] = "linear"
+    neurons: int = 0
+    input_dropout: float = 0
+
+
+@dataclass
+class TransformerConfig:
+    TYPE: ClassVar[str] = "transformer"
+    feedforward_neurons: int = 0
+    heads: int = 1
+    activation: str = "relu"
+    num_layers: int = 1
+    dropout_rate: float = 0
+    positional_embeddings: bool = True
+
+    def __post_init__(self) -> None:
+        if self.activation not in ("relu", "gelu"):
+            raise ValueError(f"activation must be one of relu, gelu; got {self.activation!r}")
+
+
+@dataclass
+class TransformerAcousticModelConfig:
+    TYPE: ClassVar[str] = "pre-ln-transformer"
+
+    transformer: TransformerConfig
+    frontend: Any = field(default_factory=DirectFrontendConfig)
+    sequential_frontend: Optional[SequentialFrontendConfig] = None
+    elementwise_affine: bool = False
+
+    @classmethod
+    def load(cls, mapping: Mapping[str, Any]) -> "TransformerAcousticModelConfig":
+        transformer = TransformerConfig(**{k: v for k, v in mapping["transformer"].items() if k != "type"})
+        frontend_map = dict(mapping["frontend"])
+        architecture = frontend_map.pop("architecture")
+        if architecture == DirectFrontendConfig.TYPE:
+            frontend: Any = DirectFrontendConfig(**frontend_map)
+        elif architecture == LinearFrontendConfig.TYPE:
+            frontend = LinearFrontendConfig(**frontend_map)
+        else:
+            raise ValueError(f"Unsupported frontend architecture: {architecture!r}")
+        sequential = mapping.get("sequential_frontend")
+        return cls(transformer, frontend, None if sequential is None else SequentialFrontendConfig.load(sequential), mapping.get("elementwise_affine", False))
+
+    def dump(self) -> Dict[str, Any]:
+        return {
+            "type": self.TYPE,
+            "transformer": dataclasses.asdict(self.transformer),
+            "frontend": _dump_keyed(self.frontend, "architecture"),
+            "sequential_frontend": None if self.sequential_frontend is None else self.sequential_frontend.dump(),
+            "elementwise_affine": self.elementwise_affine,
+        }
+
+
 @dataclass
 class UnsupportedAcousticModelConfig:
     """``pre-ln-transformer`` / ``wav2vec2`` acoustic models: parsed, but outside this build's hot path."""
@@ -207,7 +320,9 @@ def _load_acoustic_model(mapping: Mapping[str, Any]):
     kind = mapping.get("type")
     if kind == Wav2Vec2PretrainedConfig.TYPE:
         return Wav2Vec2PretrainedConfig.load(mapping)
-    if kind in ("pre-ln-transformer", "wav2vec2"):
+    if kind == TransformerAcousticModelConfig.TYPE:
+        return TransformerAcousticModelConfig.load(mapping)
+    if kind in ("wav2vec2",):
         return UnsupportedAcousticModelConfig(kind, {k: v for k, v in mapping.items() if k != "type"})
     raise ValueError(f"Unknown acoustic model type: {kind!r}")
 

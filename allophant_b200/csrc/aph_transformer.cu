@@ -66,8 +66,11 @@ __global__ void __launch_bounds__(256) transpose_nfl_kernel(const float* __restr
 
 // LengthWrapper masking + VariableLengthReflectPad (frontend.py:63-74, padding.py:41-53) on channels-last activations:
 // out[n][p][c], p in [0, L + left + right); q = p - left:
-//   q < 0: xm[left - p]      0 <= q < len: x[q]      len <= q < len + right: x[len - 2 - (q - len)]      else 0
-// with xm = x masked to the utterance's own length (frames >= len read as 0).  Output bf16 (the conv GEMM's A operand).
+//   q < 0: xm0[left - p]     0 <= q < len: x[q]      len <= q < len + right: x[len - 2 - (q - len)]      else 0
+// xm0 is the (length-masked) FIRST utterance of the batch for every n: the reference gathers the left reflection with an
+// index tensor of batch size 1 (padding.py:44-46: `_left_pad_indices.repeat(1, feature_size, 1)`), which reads batch
+// element 0 only and broadcasts it over the batch; reproduced here because parity is defined by the reference's
+// results.  Output bf16 (the conv GEMM's A operand).
 __global__ void __launch_bounds__(256) reflect_pad_kernel(const float* __restrict__ x, long long ld_x, const int* __restrict__ lengths,
                                                           int length, int channels, int left, int right, int reflect,
                                                           __nv_bfloat16* __restrict__ out) {
@@ -84,7 +87,12 @@ __global__ void __launch_bounds__(256) reflect_pad_kernel(const float* __restric
     const int q = p - left;
     int t = -1;
     if (q < 0) {
-      if (reflect) t = left - p;
+      if (reflect) {  // left reflection of utterance 0, for every utterance (see above)
+        const int t0 = left - p;
+        const float v0 = t0 < min(lengths[0], length) ? x[static_cast<long long>(t0) * ld_x + c] : 0.f;
+        dst[i] = __float2bfloat16(v0);
+        continue;
+      }
     } else if (q < len) {
       t = q;
     } else if (reflect && q < len + right) {

@@ -82,7 +82,7 @@ class HeadsRuntime:
     def _build_layout(self) -> None:
         projection = self.model._projection
         hidden = projection._output_features
-        n_layers = self.model._acoustic_model._model.config.num_hidden_layers
+        n_layers = self.model._acoustic_model.hidden_state_count - 1  # index of the LAST hidden state (= OUTPUT)
         column = hidden
         self.x_cols: Dict[str, int] = {_OUTPUT: 0}
         self.hidden_blocks: Dict[int, int] = {}
@@ -319,7 +319,16 @@ class HeadsRuntime:
         if not self._layout_ready:
             self._build_layout()
         acoustic = model._acoustic_model
-        if torch.is_grad_enabled() and not log_probabilities:
+        if torch.is_grad_enabled() and not log_probabilities and not hasattr(acoustic, "_model"):
+            # from-scratch transformer encoder: no CUDA backward yet, the classifiers can still train on top of it
+            if any(p.requires_grad for p in acoustic.parameters()):
+                raise NotImplementedError(
+                    "allophant_b200: the from-scratch transformer encoder has no backward pass in this build; freeze its parameters "
+                    "or run under torch.no_grad()/inference_mode()"
+                )
+            if any(p.requires_grad for p in projection.parameters()):
+                return self._forward_differentiable(batch, target_feature_indices, predict, False, False)
+        elif torch.is_grad_enabled() and not log_probabilities:
             weights = acoustic._model
             if any(p.requires_grad for p in weights.feature_extractor.parameters()):
                 raise NotImplementedError(
@@ -429,7 +438,7 @@ class HeadsRuntime:
         input_dropout: Dict[int, ops.Dropout] = {}  # column of X -> dropout of that classifier input block
         if self.model.training:
             seed = int(torch.randint(0, 2**31 - 1, (1,))) ^ (self._rank() * 0x9E3779B1 & 0x7FFFFFFF)
-            if acoustic._model.training:  # HF regularises by module mode, also when the encoder is frozen
+            if hasattr(acoustic, "_model") and acoustic._model.training:  # HF regularises by module mode, also when the encoder is frozen
                 stochastic = Stochastic.from_config(acoustic._model.config, seed)
                 stochastic.skip_layers = self.skip_layers_override
             rate = self.model._projection._acoustic_model_dropout

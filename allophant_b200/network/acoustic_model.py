@@ -27,12 +27,19 @@ from ..config import (
     PhonemeLayerType,
     ProjectionConfig,
     ProjectionEntryConfig,
+    TransformerAcousticModelConfig,
     UnfreezeScheduleConfig,
     Wav2Vec2PretrainedConfig,
 )
 from ..dataset_processing import Batch
 from ..engine import EncoderPlan, PackedEncoder
 from . import frontend
+from .transformer import (  # noqa: F401  (drop-in names of acoustic_model.py:34-69, 552-759)
+    PreLMTransformerEncoderLayer,
+    SinusoidalPositionEmbeddings,
+    TransformerAcousticModel,
+    TransformerEncoderIntermediate,
+)
 from .wav2vec2 import Wav2Vec2Weights, encoder_config_for
 
 _PAD_VALUE = torch.finfo(torch.float32).min
@@ -336,6 +343,11 @@ class Wav2Vec2AcousticModel(AcousticModel):
         return self._output_size
 
     @property
+    def hidden_state_count(self) -> int:
+        """Entries of HF's ``hidden_states`` tuple: the encoder input plus one per layer."""
+        return self._model.config.num_hidden_layers + 1
+
+    @property
     def feature_size(self) -> int:
         return self._feature_size
 
@@ -511,10 +523,8 @@ class Allophant(nn.Module):
             )
         elif getattr(layer_config, "TYPE", None) == "wav2vec2":
             raise NotImplementedError("Training Wav2Vec2 from scratch is not yet implemented")
-        elif getattr(layer_config, "TYPE", None) == "pre-ln-transformer":
-            raise NotImplementedError(
-                "the from-scratch pre-LN transformer encoder is not part of this build (SURVEY.md §8f rank 2)"
-            )
+        elif isinstance(layer_config, TransformerAcousticModelConfig):
+            acoustic_model = TransformerAcousticModel.from_config(layer_config, feature_size)
         else:
             raise ValueError(f"Unsupported model type: {type(layer_config)}")
         return cls(acoustic_model, attribute_graph, architecture.loss.BLANK_OFFSET, architecture.projection, attribute_indexer)

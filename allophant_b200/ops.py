@@ -597,6 +597,43 @@ def masked_rows_backward(d: Tensor, ld: int, rows: int, cols: int, row_mask: Ten
     check(lib.aph_masked_rows_backward(d.data_ptr(), ld, rows, cols, row_mask.data_ptr(), d_fill.data_ptr(), _stream()), "aph_masked_rows_backward")
 
 
+def layernorm_any(
+    x: Tensor, ld_x: int, rows: int, cols: int, gamma: Optional[Tensor], beta: Optional[Tensor], eps: float,
+    out_f32: Optional[Tensor] = None, ld_f32: int = 0, out_bf16: Optional[Tensor] = None, ld_bf16: int = 0,
+) -> None:  # fmt: skip
+    """``nn.LayerNorm`` over the last axis of fp32 ``x`` (any width; ``gamma``/``beta`` ``None`` = no affine parameters)."""
+    _require_cuda(x, gamma, beta, out_f32, out_bf16)
+    check(
+        lib.aph_layernorm_any(x.data_ptr(), ld_x, rows, cols, _ptr(gamma), _ptr(beta), eps, _ptr(out_f32), ld_f32, _ptr(out_bf16), ld_bf16, _stream()),
+        "aph_layernorm_any",
+    )
+
+
+def add_sinusoidal(x: Tensor, ld: int, n_utt: int, seq: int, cols: int, bases: Tensor) -> None:
+    _require_cuda(x, bases)
+    check(lib.aph_add_sinusoidal(x.data_ptr(), ld, n_utt, seq, cols, bases.data_ptr(), _stream()), "aph_add_sinusoidal")
+
+
+def transpose_nfl(features: Tensor, out: Tensor, ld_out: int) -> None:
+    """fp32 ``[N, F, L]`` -> channels-last ``[N, L, ld_out]``."""
+    _require_cuda(features, out)
+    n, f, length = features.shape
+    check(lib.aph_transpose_nfl(features.data_ptr(), n, f, length, out.data_ptr(), ld_out, _stream()), "aph_transpose_nfl")
+
+
+def reflect_pad_bf16(x: Tensor, ld_x: int, lengths32: Tensor, n_utt: int, length: int, channels: int, left: int, right: int, reflect: bool, out: Tensor) -> None:
+    _require_cuda(x, lengths32, out)
+    check(
+        lib.aph_reflect_pad_bf16(x.data_ptr(), ld_x, lengths32.data_ptr(), n_utt, length, channels, left, right, int(reflect), out.data_ptr(), _stream()),
+        "aph_reflect_pad_bf16",
+    )
+
+
+def glu_rows(y: Tensor, ld_y: int, rows: int, out_channels: int, out: Tensor, ld_out: int) -> None:
+    _require_cuda(y, out)
+    check(lib.aph_glu_rows(y.data_ptr(), ld_y, rows, out_channels, out.data_ptr(), ld_out, _stream()), "aph_glu_rows")
+
+
 def pack_conv_weight(weight: Tensor, dst: Optional[Tensor] = None) -> Tensor:
     """Conv1d weight [O, C, k] fp32 -> bf16 [O, k*C]."""
     _require_cuda(weight, dst)

@@ -85,7 +85,7 @@ def build_spec(case: Dict[str, Any]) -> restatement.OracleSpec:
     return spec
 
 
-def reference_model(spec: restatement.OracleSpec):
+def reference_model(spec: restatement.OracleSpec, acoustic_model_factory=None, feature_size: int = 1):
     """The reference's own Allophant over a synthetic indexer (a namespace with five fields suffices)."""
     import pandas as pd
 
@@ -139,7 +139,7 @@ def reference_model(spec: restatement.OracleSpec):
         embedding_composition=None if spec.embedding_size is None else cfg.EmbeddingCompositionConfig(spec.embedding_size),
     )
     architecture = types.SimpleNamespace(
-        acoustic_model=cfg.Wav2Vec2PretrainedConfig("facebook/wav2vec2-xls-r-300m"),
+        acoustic_model=cfg.Wav2Vec2PretrainedConfig("facebook/wav2vec2-xls-r-300m") if acoustic_model_factory is None else acoustic_model_factory(cfg),
         projection=projection,
         loss=cfg.CTCLossConfig(),
     )
@@ -147,7 +147,7 @@ def reference_model(spec: restatement.OracleSpec):
         ref.attribute_graph.AttributeNode(c.name, c.size, None, list(c.dependencies)) for c in spec.classes
     )
     torch.manual_seed(spec.weight_seed)
-    model = ref.acoustic_model.Allophant.from_config(architecture, 1, 16000, graph, indexer, load_pretrained_weights=False)
+    model = ref.acoustic_model.Allophant.from_config(architecture, feature_size, 16000, graph, indexer, load_pretrained_weights=False)
     model.eval()
     estimator = types.SimpleNamespace(model=model)
     return ref, model, graph

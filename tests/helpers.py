@@ -52,8 +52,11 @@ def batch_for_case(fixture: Dict[str, Any]) -> Tuple[torch.Tensor, torch.Tensor,
     return audio, lengths, fixture["language_ids"]
 
 
-def cuda_model_for_spec(spec: restatement.OracleSpec, oracle: restatement.OracleModel, device: str = "cuda"):
-    """Builds allophant_b200's Allophant with the architecture of ``spec`` and loads the oracle's weights."""
+def cuda_model_for_spec(
+    spec: restatement.OracleSpec, oracle: Any, device: str = "cuda", acoustic_config: Any = None, feature_size: int = 1, state_dict: Any = None
+):
+    """Builds allophant_b200's Allophant with the architecture of ``spec`` and loads the oracle's weights (or ``state_dict``);
+    ``acoustic_config`` replaces the wav2vec2 encoder (the from-scratch transformer cases)."""
     from allophant_b200.attribute_graph import AttributeGraph, AttributeNode
     from allophant_b200.config import (
         Architecture,
@@ -98,10 +101,12 @@ def cuda_model_for_spec(spec: restatement.OracleSpec, oracle: restatement.Oracle
 
         model_id = "test/" + "-".join(f"{k}{v}" for k, v in sorted(spec.encoder_overrides.items()))
         wav2vec2.KNOWN_MODELS[model_id] = dataclasses.replace(wav2vec2.KNOWN_MODELS["facebook/wav2vec2-xls-r-300m"], **spec.encoder_overrides)
-    architecture = Architecture(16_000_000, projection, Wav2Vec2PretrainedConfig(model_id), loss=CTCLossConfig())
+    architecture = Architecture(
+        16_000_000, projection, Wav2Vec2PretrainedConfig(model_id) if acoustic_config is None else acoustic_config, loss=CTCLossConfig()
+    )
     graph = AttributeGraph(AttributeNode(c.name, c.size, None, list(c.dependencies)) for c in spec.classes)
-    model = Allophant.from_config(architecture, 1, 16000, graph, indexer, load_pretrained_weights=False)
-    result = model.load_state_dict(oracle.state_dict(), strict=True)
+    model = Allophant.from_config(architecture, feature_size, 16000, graph, indexer, load_pretrained_weights=False)
+    result = model.load_state_dict(oracle.state_dict() if state_dict is None else state_dict, strict=True)
     assert not result.missing_keys and not result.unexpected_keys
     return model.to(device).eval(), indexer
 
@@ -150,3 +155,26 @@ def regularisation_masks(stochastic, n_utt: int, seq: int, hidden: int, heads: i
     if spec_mask is not None:
         masks["spec"] = spec_mask.view(n_utt, seq).bool()
     return masks
+
+
+def transformer_model_for_golden(golden: Dict[str, Any], device: str = "cuda"):
+    """allophant_b200's Allophant over the from-scratch transformer encoder of a ``tests/golden/transformer_*.pt`` case
+    (same construction as oracle/make_golden_transformer.py), loaded with the REFERENCE's state_dict."""
+    from allophant_b200.config import TransformerAcousticModelConfig
+
+    case = golden["case"]
+    spec = restatement.multitask_spec(**case["spec"])
+    spec.embedding_size = 64
+    if case["output_layers"]:
+        first = spec.classes[0]
+        spec.classes[0] = restatement.ClassSpec(first.name, first.size, list(first.dependencies) + [f"OUTPUT_{i}" for i in case["output_layers"]])
+    options = case["acoustic"]
+    mapping = dict(
+        type="pre-ln-transformer",
+        transformer=options["transformer"],
+        frontend=options["frontend"],
+        sequential_frontend=None if options["sequential_frontend"] is None else {"layers": options["sequential_frontend"]},
+        elementwise_affine=options["elementwise_affine"],
+    )
+    config = TransformerAcousticModelConfig.load(mapping)
+    return cuda_model_for_spec(spec, None, device, config, case["feature_size"], golden["state_dict"])
