@@ -154,6 +154,7 @@ _SIGNATURES = {
     "aph_transpose_nfl": [_P, _I32, _I32, _I32, _P, _I64, _P],
     "aph_reflect_pad_bf16": [_P, _I64, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P],
     "aph_glu_rows": [_P, _I64, _I64, _I32, _P, _I64, _P],
+    "aph_edit_matrix": [_P, _I64, _P, _I64, _P],
     "aph_collate_pad_f32": [_P, _P, _I64, _I64, _P, _I32],
     "aph_edit_statistics_batch": [_P, _P, _P, _P, _I64, _P, _P, _I32],
     "aph_ctc_states_pad": [_I32],
@@ -164,6 +165,7 @@ _SIGNATURES = {
 EXPORTED_SYMBOLS = sorted(
     list(_SIGNATURES)
     + ["aph_abi_version", "aph_last_error", "aph_launch_count", "aph_reset_launch_count", "aph_word_error_rate"]
+    + ["aph_edit_operations", "aph_segmenter_create", "aph_segmenter_free", "aph_segmenter_find"]
 )
 
 
@@ -181,6 +183,14 @@ def _load() -> ctypes.CDLL:
     lib.aph_reset_launch_count.restype = None
     lib.aph_word_error_rate.argtypes = [ctypes.c_uint64] * 4
     lib.aph_word_error_rate.restype = c_float
+    lib.aph_edit_operations.argtypes = [_P, _I64, _P, _I64, _P, _P]
+    lib.aph_edit_operations.restype = c_int64
+    lib.aph_segmenter_create.argtypes = [c_char_p, _P, _I64]
+    lib.aph_segmenter_create.restype = c_void_p
+    lib.aph_segmenter_free.argtypes = [c_void_p]
+    lib.aph_segmenter_free.restype = None
+    lib.aph_segmenter_find.argtypes = [c_void_p, c_char_p, _I64, _P, _I64]
+    lib.aph_segmenter_find.restype = c_int64
     for name, argtypes in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

@@ -17,12 +17,17 @@ from ._lib import check, lib
 
 
 class Action(Enum):
-    INSERTION = 1
-    DELETION = 2
-    SUBSTITUTION = 3
+    """``src/edit_distance.rs:41-69``: the PyO3 enum's integer values are its Rust discriminants 0 / 1 / 2 (the ``.pyi`` stub of
+    the reference lists 1 / 2 / 3, but ``from_int`` and ``int()`` of the compiled extension use the discriminants)."""
+
+    INSERTION = 0
+    DELETION = 1
+    SUBSTITUTION = 2
 
     @staticmethod
     def from_int(integer: int) -> "Action":
+        if integer not in (0, 1, 2):
+            raise ValueError(f"Invalid enum value {integer}")
         return Action(integer)
 
     def __int__(self) -> int:
@@ -145,3 +150,116 @@ def levensthein(string_a: Sequence[Hashable], string_b: Sequence[Hashable]) -> i
         "aph_edit_statistics_batch",
     )
     return int(out[0])
+
+
+LevenstheinOperations = List[Tuple[Action, int, int]]
+
+
+def levensthein_operations(string_a: Sequence[Hashable], string_b: Sequence[Hashable]) -> Tuple[LevenstheinOperations, float]:
+    """First best edit path and its cost (``src/edit_distance.rs:116-218, 271-280``): ``(action, i, j)`` with the matrix
+    coordinates AFTER each step, matches are not listed."""
+    expected, _, actual, _ = _encode([(string_a, string_b)])
+    m, n = len(string_a), len(string_b)
+    out = np.zeros((max(1, m + n), 3), dtype=np.int64)
+    cost = ctypes.c_float(0.0)
+    count = lib.aph_edit_operations(_pointer(expected), m, _pointer(actual), n, _pointer(out), ctypes.byref(cost))
+    if count < 0:
+        check(int(count), "aph_edit_operations")
+    return [(Action.from_int(int(action)), int(i), int(j)) for action, i, j in out[:count].tolist()], float(cost.value)
+
+
+def levensthein_matrix(string_a: Sequence[Hashable], string_b: Sequence[Hashable]):
+    """The full fp32 cost matrix as a ``torch.Tensor`` ``[len(a) + 1, len(b) + 1]`` (``src/edit_distance.rs:220-269``)."""
+    import torch
+
+    expected, _, actual, _ = _encode([(string_a, string_b)])
+    m, n = len(string_a), len(string_b)
+    out = np.zeros((m + 1, n + 1), dtype=np.float32)
+    check(lib.aph_edit_matrix(_pointer(expected), m, _pointer(actual), n, _pointer(out)), "aph_edit_matrix")
+    return torch.from_numpy(out)
+
+
+def to_substitutions(string_a: Sequence[str], string_b: Sequence[str], operations: LevenstheinOperations) -> List[Tuple[Action, str, str]]:
+    """``src/edit_distance.rs:100-114``."""
+    result = []
+    for operation, a_index, b_index in operations:
+        if operation == Action.DELETION:
+            result.append((operation, string_a[a_index], ""))
+        elif operation == Action.INSERTION:
+            result.append((operation, "", string_b[b_index]))
+        else:
+            result.append((operation, string_a[a_index], string_b[b_index]))
+    return result
+
+
+class MissingSegmentError(ValueError):
+    """``src/ipa_segmenter.rs:11``."""
+
+
+def _debug(text: str) -> str:
+    """Rust's ``{:?}`` of a ``&str`` for the error message: double quotes, backslash escapes."""
+    return '"' + text.replace("\\", "\\\\").replace('"', '\\"').replace("\n", "\\n").replace("\t", "\\t").replace("\r", "\\r") + '"'
+
+
+class IpaSegmenter:
+    """Leftmost-longest segmentation of IPA transcriptions into a known segment vocabulary (``src/ipa_segmenter.rs``)."""
+
+    def __init__(self, ipa_segments: List[str]) -> None:
+        self.ipa_segments = list(ipa_segments)
+        encoded = [segment.encode("utf-8") for segment in self.ipa_segments]
+        offsets = np.zeros(len(encoded) + 1, dtype=np.int64)
+        np.cumsum([len(piece) for piece in encoded], out=offsets[1:])
+        self._handle = lib.aph_segmenter_create(b"".join(encoded), _pointer(offsets), len(encoded))
+        if not self._handle:
+            raise RuntimeError("aph_segmenter_create failed")
+
+    def __del__(self) -> None:
+        handle, self._handle = getattr(self, "_handle", None), None
+        if handle:
+            lib.aph_segmenter_free(handle)
+
+    def _matches(self, word: str) -> Tuple[bytes, List[Tuple[int, int]]]:
+        data = word.encode("utf-8")
+        bounds = np.zeros((max(1, len(data)), 2), dtype=np.int64)
+        count = lib.aph_segmenter_find(self._handle, data, len(data), _pointer(bounds), len(bounds))
+        if count < 0:
+            check(int(count), "aph_segmenter_find")
+        return data, [(int(start), int(end)) for start, end in bounds[:count].tolist()]
+
+    def _segment_word(self, word: str, include_missing: bool) -> List[str]:
+        data, matches = self._matches(word)
+        pieces: List[str] = []
+        last_end = 0
+        for start, end in matches:
+            if include_missing and start != last_end:
+                pieces.append(data[last_end:start].decode("utf-8"))
+            pieces.append(data[start:end].decode("utf-8"))
+            last_end = end
+        if include_missing and last_end != len(data):
+            pieces.append(data[last_end:].decode("utf-8"))
+        return pieces
+
+    def _segment_word_checked(self, word: str) -> List[str]:
+        data, matches = self._matches(word)
+        pieces: List[str] = []
+        last_end = 0
+        for start, end in matches:
+            if start != last_end:
+                raise MissingSegmentError(f"Segment {_debug(data[last_end:start].decode('utf-8'))} is missing from the vocabulary. Found in: {_debug(word)}")
+            pieces.append(data[start:end].decode("utf-8"))
+            last_end = end
+        if last_end != len(data):
+            raise MissingSegmentError(f"Segment {_debug(data[last_end:].decode('utf-8'))} is missing from the vocabulary. Found in: {_debug(word)}")
+        return pieces
+
+    def segment(self, transcription: str, include_missing: bool = False) -> List[str]:
+        return self._segment_word(transcription, include_missing)
+
+    def segment_checked(self, transcription: str) -> List[str]:
+        return self._segment_word_checked(transcription)
+
+    def segment_words(self, transcriped_words: List[str], include_missing: bool = False) -> List[str]:
+        return [piece for word in transcriped_words for piece in self._segment_word(word, include_missing)]
+
+    def segment_words_checked(self, transcriped_words: List[str]) -> List[str]:
+        return [piece for word in transcriped_words for piece in self._segment_word_checked(word)]

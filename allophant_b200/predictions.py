@@ -150,3 +150,190 @@ def feature_decoders(indexer: Any, beam_width: int = 1, feature_names: Optional[
         name: _ctc_decoder(indexer.feature_categories(name), beam_width, n_best)
         for name in (indexer.feature_names if feature_names is None else feature_names)
     }
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Prediction files: JSON lines, format 1.1.0 (allophant/predictions.py:29-186).  First line = metadata, then one
+# UtterancePrediction (or UtteranceEdits) per line; optional gzip, inferred from a ".gz" suffix.
+# ----------------------------------------------------------------------------------------------------------------------
+import dataclasses as _dataclasses
+import gzip as _gzip
+import io as _io
+import json as _json
+import os as _os
+from dataclasses import dataclass as _dataclass
+from typing import Iterator, Tuple, Union
+
+from . import __version__ as _PACKAGE_VERSION
+from . import phonemes as _phonemes
+from .config import FeatureSet
+
+CURRENT_FORMAT_VERSION = (1, 1, 0)
+SUPPORTED_VERSIONS = [CURRENT_FORMAT_VERSION]
+
+
+@_dataclass
+class PredictionMetaData:
+    """``predictions.py:34-47``; ``indexer_state`` is the serialised state of the attribute indexer (a plain dict here)."""
+
+    prediction_arguments: str
+    corpus_type: str
+    languages: List[str]
+    feature_set: FeatureSet
+    indexer_state: Any
+    classifiers: List[str]
+    label_inventories: Optional[Dict[str, List[str]]] = None
+    package_version: str = _PACKAGE_VERSION
+    format_version: Tuple[int, int, int] = CURRENT_FORMAT_VERSION
+
+    def dumps(self) -> str:
+        fields = _dataclasses.asdict(self)
+        fields["feature_set"] = self.feature_set.value
+        fields["format_version"] = list(self.format_version)
+        return _json.dumps(fields)
+
+    @classmethod
+    def loads(cls, line: str) -> "PredictionMetaData":
+        fields = _json.loads(line)
+        fields["feature_set"] = FeatureSet(fields["feature_set"])
+        fields["format_version"] = tuple(fields.get("format_version", CURRENT_FORMAT_VERSION))
+        if fields["format_version"] not in SUPPORTED_VERSIONS:
+            raise ValueError(f"Unsupported prediction format version {fields['format_version']}, supported: {SUPPORTED_VERSIONS}")
+        return cls(**fields)
+
+
+@_dataclass
+class UtterancePrediction:
+    """``predictions.py:50-55``: ``predictions`` maps a classifier name to its n-best label sequences."""
+
+    language: str
+    utterance_id: str
+    predictions: Dict[str, List[List[str]]]
+    labels: Optional[List[List[str]]] = None
+
+    def to_json(self) -> str:
+        return _json.dumps(_dataclasses.asdict(self))
+
+    @classmethod
+    def from_json(cls, line: str) -> "UtterancePrediction":
+        return cls(**_json.loads(line))
+
+
+@_dataclass
+class UtteranceEdits:
+    """``predictions.py:68-79``: edit operations per classifier; actions are stored as integers (``int(Action)``)."""
+
+    language: str
+    utterance_id: str
+    expected: Dict[str, List[str]]
+    edit_operations: Dict[str, List[Tuple[Any, str, str]]]
+
+    def to_json(self) -> str:
+        fields = _dataclasses.asdict(self)
+        fields["edit_operations"] = {
+            name: [[int(action), expected, actual] for action, expected, actual in operations] for name, operations in self.edit_operations.items()
+        }
+        return _json.dumps(fields)
+
+    @classmethod
+    def from_json(cls, line: str) -> "UtteranceEdits":
+        fields = _json.loads(line)
+        fields["edit_operations"] = {
+            name: [(_phonemes.Action.from_int(action), expected, actual) for action, expected, actual in operations]
+            for name, operations in fields["edit_operations"].items()
+        }
+        return cls(**fields)
+
+
+def levensthein_substitutions(expected: List[str], actual: List[str]) -> List[Tuple[Any, str, str]]:
+    """``predictions.py:58-59``."""
+    return _phonemes.to_substitutions(expected, actual, _phonemes.levensthein_operations(expected, actual)[0])
+
+
+PathOrFileBinary = Union[str, "_os.PathLike[str]", Any]
+
+
+def _file_path(file: PathOrFileBinary) -> str:
+    if isinstance(file, (str, _os.PathLike)):
+        return _os.fspath(file)
+    return getattr(file, "name", "")
+
+
+def _infer_gzip(file: PathOrFileBinary) -> bool:
+    return _os.path.splitext(_file_path(file))[1] == ".gz"
+
+
+def _binary(file: PathOrFileBinary, mode: str):
+    return open(file, mode) if isinstance(file, (str, _os.PathLike)) else file
+
+
+class JsonlWriter:
+    """``predictions.py:159-186``: exclusive creation ("x"), metadata line first."""
+
+    def __init__(self, file: PathOrFileBinary, metadata: PredictionMetaData, gzip: Optional[bool] = False) -> None:
+        self._wrapped_file = file
+        self._gzip = _infer_gzip(file) if gzip is None else gzip
+        self._meta_data = metadata
+
+    def __enter__(self) -> "JsonlWriter":
+        raw = _gzip.open(self._wrapped_file, "x") if self._gzip else _binary(self._wrapped_file, "xb")
+        self._file = _io.TextIOWrapper(raw, encoding="utf-8")
+        self._file.write(self._meta_data.dumps() + "\n")
+        return self
+
+    def __exit__(self, *_: Any) -> None:
+        self._file.close()
+
+    def write(self, serialized: Any) -> None:
+        self._file.write(str(serialized.to_json()) + "\n")
+
+
+class JsonlReader:
+    """``predictions.py:95-133``."""
+
+    def __init__(self, file: PathOrFileBinary, gzip: Optional[bool] = None) -> None:
+        self._wrapped_file = file
+        self._gzip = _infer_gzip(file) if gzip is None else gzip
+
+    def read_meta(self) -> Any:
+        return None
+
+    def process_line(self, line: str) -> Any:
+        return line
+
+    def __iter__(self) -> Iterator[Any]:
+        for line in self._file:
+            yield self.process_line(line)
+
+    def __enter__(self):
+        raw = _gzip.open(self._wrapped_file, "r") if self._gzip else _binary(self._wrapped_file, "rb")
+        self._file = _io.TextIOWrapper(raw, encoding="utf-8")
+        self._metadata = self.read_meta()
+        return self
+
+    def __exit__(self, *_: Any) -> None:
+        self._file.close()
+
+
+class PredictionReader(JsonlReader):
+    def read_meta(self) -> PredictionMetaData:
+        return PredictionMetaData.loads(self._file.readline())
+
+    @property
+    def metadata(self) -> PredictionMetaData:
+        return self._metadata
+
+    def process_line(self, line: str) -> UtterancePrediction:
+        return UtterancePrediction.from_json(line)
+
+
+class StatisticsReader(JsonlReader):
+    def read_meta(self) -> PredictionMetaData:
+        return PredictionMetaData.loads(self._file.readline())
+
+    @property
+    def metadata(self) -> PredictionMetaData:
+        return self._metadata
+
+    def process_line(self, line: str) -> UtteranceEdits:
+        return UtteranceEdits.from_json(line)

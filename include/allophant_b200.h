@@ -447,6 +447,19 @@ int aph_reflect_pad_bf16(const float* x, int64_t ld_x, const int32_t* lengths, i
 int aph_glu_rows(const float* y, int64_t ld_y, int64_t rows, int32_t out_channels, float* out, int64_t ld_out,
                  void* stream);
 
+/* ---- rest of the Rust extension allophant.phonemes (host; ALL POINTERS ARE HOST POINTERS) ------------------ */
+/* levensthein_matrix (src/edit_distance.rs:261-269): (m+1) x (n+1) fp32 uniform-cost matrix of int64 symbol ids. */
+int aph_edit_matrix(const int64_t* a, int64_t m, const int64_t* b, int64_t n, float* matrix_out);
+/* levensthein_operations (src/edit_distance.rs:116-218, 271-280): first best path, (action, i, j) triples in forward
+ * order (action 0 insertion / 1 deletion / 2 substitution), at most m + n; returns their number or a negative error. */
+int64_t aph_edit_operations(const int64_t* a, int64_t m, const int64_t* b, int64_t n, int64_t* ops_out,
+                            float* final_cost);
+/* IpaSegmenter (src/ipa_segmenter.rs): leftmost-longest non-overlapping vocabulary matches over UTF-8 bytes. */
+void* aph_segmenter_create(const char* blob, const int64_t* offsets, int64_t n);
+void aph_segmenter_free(void* handle);
+int64_t aph_segmenter_find(const void* handle, const char* text, int64_t text_len, int64_t* bounds_out,
+                           int64_t max_matches);
+
 /* ---- host feeding (batching.py:171-215) -------------------------------------------------------- */
 /* rnn.pad_sequence of the utterances of a batch: n fp32 arrays of lengths_host[i] samples -> zero-padded
  * [n][max_len] (normally a pinned staging buffer), spread over n_threads host threads (<= 0: all cores).

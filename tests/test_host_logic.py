@@ -163,3 +163,39 @@ def test_warmup_schedule_matches_the_reference():
     other.step()
     scheduler.step()
     assert other.last_lr == scheduler.last_lr
+
+
+def test_prediction_files_round_trip(tmp_path):
+    """JSON-lines prediction files, format 1.1.0 (allophant/predictions.py:29-186): metadata line + one record per utterance,
+    plain and gzip, exclusive creation, edit operations with integer actions."""
+    from allophant_b200 import predictions
+    from allophant_b200.config import FeatureSet
+    from allophant_b200.phonemes import Action
+
+    metadata = predictions.PredictionMetaData("--beam 1", "common-voice", ["de", "es"], FeatureSet.PHOIBLE, {"phonemes": ["a", "b"]}, ["phoneme", "syl"], {"phoneme": ["a", "b"]})
+    records = [
+        predictions.UtterancePrediction("de", "utt0", {"phoneme": [["a", "b"]], "syl": [["+", "-"]]}, [["a", "b"]]),
+        predictions.UtterancePrediction("es", "utt1", {"phoneme": [["t͡ʃ"]], "syl": [[]]}),
+    ]
+    for name in ("predictions.jsonl", "predictions.jsonl.gz"):
+        path = tmp_path / name
+        with predictions.JsonlWriter(path, metadata, gzip=None) as writer:
+            for record in records:
+                writer.write(record)
+        with pytest.raises(FileExistsError):
+            predictions.JsonlWriter(path, metadata, gzip=None).__enter__()
+        with predictions.PredictionReader(path) as reader:
+            assert reader.metadata == metadata and reader.metadata.format_version == (1, 1, 0)
+            assert list(reader) == records
+    import gzip
+    import json
+
+    first = json.loads(gzip.open(tmp_path / "predictions.jsonl.gz", "rt").readline())
+    assert list(first) == ["prediction_arguments", "corpus_type", "languages", "feature_set", "indexer_state", "classifiers", "label_inventories", "package_version", "format_version"]
+    assert first["feature_set"] == "phoible" and first["format_version"] == [1, 1, 0]
+    edits = predictions.UtteranceEdits("de", "utt0", {"phoneme": ["k", "a"]}, {"phoneme": predictions.levensthein_substitutions(["k", "a"], ["g", "a", "s"])})
+    assert edits.edit_operations["phoneme"] == [(Action.SUBSTITUTION, "k", "g"), (Action.INSERTION, "", "s")]
+    assert json.loads(edits.to_json())["edit_operations"]["phoneme"] == [[2, "k", "g"], [0, "", "s"]]
+    assert predictions.UtteranceEdits.from_json(edits.to_json()) == edits
+    with pytest.raises(ValueError, match="Unsupported prediction format version"):
+        predictions.PredictionMetaData.loads(json.dumps({**first, "format_version": [9, 0, 0]}))
