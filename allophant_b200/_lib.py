@@ -154,6 +154,7 @@ _SIGNATURES = {
     "aph_transpose_nfl": [_P, _I32, _I32, _I32, _P, _I64, _P],
     "aph_reflect_pad_bf16": [_P, _I64, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P],
     "aph_glu_rows": [_P, _I64, _I64, _I32, _P, _I64, _P],
+    "aph_ctc_beam_decode": [_P, _P, _I64, _I64, _I32, _I32, _I32, _I32, ctypes.c_double, _I32, _I32, _P, _P, _P, _P, _I32],
     "aph_edit_matrix": [_P, _I64, _P, _I64, _P],
     "aph_collate_pad_f32": [_P, _P, _I64, _I64, _P, _I32],
     "aph_edit_statistics_batch": [_P, _P, _P, _P, _I64, _P, _P, _I32],

@@ -138,11 +138,61 @@ def decode_predictions(predictions: Any, names: Optional[Iterable[str]] = None, 
     return decode_predictions_async(predictions, names, blank_index).result()
 
 
-def _ctc_decoder(categories: Iterable[str], beam_width: int = 1, n_best: int = 1) -> GreedyCTCDecoder:
+class BeamCTCDecoder:
+    """CTC beam search (``predictions.py:210-226``): the lexicon-free flashlight decoder behind
+    ``torchaudio.models.decoder.ctc_decoder(lexicon=None, lm=None, sil_token=blank, beam_size=beam_width, nbest=n_best,
+    log_add=True)`` with torchaudio's defaults (``beam_size_token`` = all tokens, ``beam_threshold`` = 50), restated in host
+    C++ (``aph_ctc_beam_decode``) and run over (utterance) threads.  Like the reference it scores paths by the SUM OF
+    PROBABILITIES (the decoder is fed ``log_emissions.exp()``)."""
+
+    BEAM_THRESHOLD = 50.0
+
+    def __init__(self, tokens: List[str], beam_width: int, n_best: int = 1, blank_index: int = 0) -> None:
+        self._tokens = list(tokens)
+        self._beam_width, self._n_best, self._blank_index = beam_width, n_best, blank_index
+
+    def __call__(self, log_emissions: Tensor, lengths: Optional[Tensor] = None) -> List[List[CTCHypothesis]]:
+        import ctypes
+
+        from ._lib import check, lib
+
+        emissions = log_emissions.detach().to(device="cpu", dtype=torch.float32).contiguous()
+        n_seq, t_max, classes = emissions.shape
+        if lengths is None:
+            lengths = torch.full((n_seq,), t_max, dtype=torch.int64)
+        host_lengths = lengths.detach().to(device="cpu", dtype=torch.int64).contiguous()
+        tokens = torch.zeros(n_seq, self._n_best, max(1, t_max), dtype=torch.int64)
+        timesteps = torch.zeros_like(tokens)
+        counts = torch.zeros(n_seq, self._n_best, dtype=torch.int64)
+        scores = torch.zeros(n_seq, self._n_best, dtype=torch.float64)
+        pointer = lambda tensor: ctypes.c_void_p(tensor.data_ptr())  # noqa: E731
+        check(
+            lib.aph_ctc_beam_decode(
+                pointer(emissions), pointer(host_lengths), n_seq, t_max, classes, self._blank_index, self._beam_width, 0, self.BEAM_THRESHOLD,
+                self._n_best, 1, pointer(tokens), pointer(timesteps), pointer(counts), pointer(scores), 0,
+            ),  # fmt: skip
+            "aph_ctc_beam_decode",
+        )
+        results: List[List[CTCHypothesis]] = []
+        for sequence in range(n_seq):
+            hypotheses = []
+            for rank in range(self._n_best):
+                count = int(counts[sequence, rank])
+                if count < 0:
+                    break
+                hypotheses.append(
+                    CTCHypothesis(tokens[sequence, rank, :count].clone(), [], float(scores[sequence, rank]), timesteps[sequence, rank, :count].to(torch.int32))
+                )
+            results.append(hypotheses)
+        return results
+
+
+def _ctc_decoder(categories: Iterable[str], beam_width: int = 1, n_best: int = 1) -> Any:
     assert n_best <= beam_width, "N-best can not exceed beam width"
+    # Optimized decoder for greedy decoding with log probabilities
     if beam_width == 1:
         return GreedyCTCDecoder()
-    raise NotImplementedError("beam search decoding (flashlight-text) is outside this build's hot path; use beam_width=1")
+    return BeamCTCDecoder(["<blank>", *categories], beam_width, n_best)
 
 
 def feature_decoders(indexer: Any, beam_width: int = 1, feature_names: Optional[Iterable[str]] = None, n_best: int = 1) -> Dict[str, GreedyCTCDecoder]:

@@ -460,6 +460,15 @@ void aph_segmenter_free(void* handle);
 int64_t aph_segmenter_find(const void* handle, const char* text, int64_t text_len, int64_t* bounds_out,
                            int64_t max_matches);
 
+/* CTC beam search (predictions.py:210-226 -> torchaudio ctc_decoder(lexicon=None, lm=None, log_add=True) -> flashlight-text
+ * LexiconFreeDecoder + ZeroLM, restated): log_emissions fp32 [n_seq][t_max][classes], lengths int64 [n_seq]; per sequence
+ * the nbest best token sequences: tokens / timesteps int64 [n_seq][nbest][t_max], counts int64 [n_seq][nbest] (-1 = none),
+ * scores fp64 [n_seq][nbest].  beam_size_token <= 0: all classes.  HOST pointers; n_threads <= 0: all cores. */
+int aph_ctc_beam_decode(const float* log_emissions, const int64_t* lengths, int64_t n_seq, int64_t t_max,
+                        int32_t classes, int32_t blank, int32_t beam_size, int32_t beam_size_token,
+                        double beam_threshold, int32_t nbest, int32_t log_add, int64_t* tokens_out,
+                        int64_t* timesteps_out, int64_t* counts_out, double* scores_out, int32_t n_threads);
+
 /* ---- host feeding (batching.py:171-215) -------------------------------------------------------- */
 /* rnn.pad_sequence of the utterances of a batch: n fp32 arrays of lengths_host[i] samples -> zero-padded
  * [n][max_len] (normally a pinned staging buffer), spread over n_threads host threads (<= 0: all cores).

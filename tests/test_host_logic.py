@@ -199,3 +199,61 @@ def test_prediction_files_round_trip(tmp_path):
     assert predictions.UtteranceEdits.from_json(edits.to_json()) == edits
     with pytest.raises(ValueError, match="Unsupported prediction format version"):
         predictions.PredictionMetaData.loads(json.dumps({**first, "format_version": [9, 0, 0]}))
+
+
+def _enumerate_alignments(log_emissions: torch.Tensor, blank: int = 0):
+    """Exhaustive CTC-style search with the reference's scoring (path score = sum of PROBABILITIES, merged by log-add):
+    {collapsed token tuple: log sum_paths exp(sum_t p_t(path_t))} and the best path's first-frame timesteps."""
+    import itertools
+    import math
+
+    probabilities = log_emissions.exp().double()
+    frames, classes = probabilities.shape
+    totals, best = {}, {}
+    for path in itertools.product(range(classes), repeat=frames):
+        score = sum(float(probabilities[t, c]) for t, c in enumerate(path))
+        tokens, steps = [], []
+        for t, c in enumerate(path):
+            if c != blank and (t == 0 or c != path[t - 1]):
+                tokens.append(c)
+                steps.append(t + 1)
+        key = tuple(tokens)
+        totals[key] = math.log(math.exp(totals[key]) + math.exp(score)) if key in totals else score
+        if key not in best or score > best[key][0]:
+            best[key] = (score, steps)
+    return totals, best
+
+
+def test_beam_ctc_decoder_equals_exhaustive_search():
+    """BeamCTCDecoder (predictions.py:210-226 -> flashlight lexicon-free decoder, restated in host C++): with a beam wide
+    enough to keep every hypothesis the result must equal exhaustive enumeration of all alignments."""
+    from allophant_b200 import predictions
+
+    generator = torch.Generator().manual_seed(4)
+    for frames, classes in [(1, 2), (3, 3), (5, 3), (4, 4), (6, 2)]:
+        log_emissions = torch.log_softmax(2.0 * torch.randn(2, frames, classes, generator=generator), -1)
+        lengths = torch.tensor([frames, max(1, frames - 1)])
+        decoder = predictions._ctc_decoder([f"c{i}" for i in range(1, classes)], beam_width=500, n_best=4)
+        assert isinstance(decoder, predictions.BeamCTCDecoder)
+        results = decoder(log_emissions, lengths)
+        assert len(results) == 2
+        for sequence, hypotheses in enumerate(results):
+            totals, best = _enumerate_alignments(log_emissions[sequence, : int(lengths[sequence])])
+            ranked = sorted(totals.items(), key=lambda item: -item[1])
+            assert len(hypotheses) == min(4, len(ranked))
+            for hypothesis, (tokens, score) in zip(hypotheses, ranked):
+                assert tuple(hypothesis.tokens.tolist()) == tokens
+                assert abs(hypothesis.score - score) < 1e-9 * max(1.0, abs(score))
+                assert hypothesis.words == [] and hypothesis.timesteps.dtype == torch.int32
+                assert len(hypothesis.timesteps) == len(tokens)
+            # 1-based first frames of the labels along the kept back pointers (the better-scoring parent at every merge)
+            steps = hypotheses[0].timesteps.tolist()
+            assert steps == sorted(set(steps)) and all(1 <= step <= int(lengths[sequence]) for step in steps)
+    # a narrow beam still returns valid, score-sorted hypotheses; beam 1 is the greedy decoder like in the reference
+    log_emissions = torch.log_softmax(torch.randn(3, 40, 6, generator=generator), -1)
+    narrow = predictions.BeamCTCDecoder(["<blank>"] + list("abcde"), 5, 3)(log_emissions, torch.tensor([40, 17, 1]))
+    assert all(len(h) == 3 and h[0].score >= h[1].score >= h[2].score for h in narrow[:2])
+    assert all(int(t.max()) <= length for h, length in zip(narrow, (40, 17, 1)) for t in [h[0].timesteps] if len(t))
+    assert isinstance(predictions._ctc_decoder(["a"], 1, 1), predictions.GreedyCTCDecoder)
+    with pytest.raises(AssertionError, match="N-best can not exceed beam width"):
+        predictions._ctc_decoder(["a"], 2, 3)
