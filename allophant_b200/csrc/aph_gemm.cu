@@ -141,7 +141,8 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   // one 32-row x 128-byte output staging tile per epilogue warp (+ one residual tile in the TMA-residual variant)
   static constexpr int kEpiBytes = EPI == kEpiStoreResidTma ? 8 * 8192 : 8 * 4096;
-  static constexpr int kBudget = kSmemBudget - (kEpiBytes - 8 * 4096);
+  // everything has to fit the 227 KB a CTA can opt into: stages + epilogue staging + alignment slack + barriers
+  static constexpr int kBudget = 232448 - kEpiBytes - 1024 - 512;
   static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // double-buffered accumulator (128 lanes x BN columns per CTA)
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 512 /*barriers*/;
@@ -828,10 +829,19 @@ extern "C" int aph_gemm_bf16(const aph_gemm_args* a, void* stream_) {
   // primary output goes through the staged TMA store (fp32 wins when both are requested)
   p.staged = a->out_f32 ? 1 : 2;
   if (a->n > 128) {
-    p.n_tiles = ceil_div(a->n, 256);
+    // Wave quantisation (80 tiles of 256 x 256 on 74 cluster slots for the 4.9 k x 1024 GEMMs of a training step) is NOT
+    // cured by 256 x 128 tiles: measured on the training step, they cost ~0.7 of a full tile each and the step gets 4 %
+    // slower (profiles/r01_gemm_bn128_ab.md).  Kept behind APH_GEMM_BN128=1 for experiments.
+    static const bool narrow_requested = [] {
+      const char* e = getenv("APH_GEMM_BN128");
+      return e != nullptr && atoi(e) == 1;
+    }();
+    const bool narrow = narrow_requested && !a->a_mn_major;
+    p.n_tiles = ceil_div(a->n, narrow ? 128 : 256);
     // fp32 output with a residual (out-proj, FFN2, gradient accumulation): the residual comes in through TMA
-    if (a->resid && p.staged == 1 && !a->a_mn_major) return launch_gemm<256, kEpiStoreResidTma>(a, p, stream);
-    return launch_gemm<256, APH_EPI_STORE>(a, p, stream);
+    if (a->resid && p.staged == 1 && !a->a_mn_major)
+      return narrow ? launch_gemm<128, kEpiStoreResidTma>(a, p, stream) : launch_gemm<256, kEpiStoreResidTma>(a, p, stream);
+    return narrow ? launch_gemm<128, APH_EPI_STORE>(a, p, stream) : launch_gemm<256, APH_EPI_STORE>(a, p, stream);
   } else if (a->n > 64 || a->b_mn_major) {  // an MN-major B tile needs at least one 64-column chunk per CTA
     p.n_tiles = 1;
     return launch_gemm<128, APH_EPI_STORE>(a, p, stream);

@@ -110,28 +110,51 @@ __global__ void __launch_bounds__(256) transpose_cast_kernel(const TIn* __restri
 template <typename TIn>
 __global__ void __launch_bounds__(256) colsum_kernel(const TIn* __restrict__ in, long long ld, long long R, int C,
                                                      float* __restrict__ out) {
-  // block = 32 columns x 8 row-lanes; grid.y splits the rows; partial sums combined with atomics (out pre-zeroed)
-  __shared__ float part[8][33];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  // block = 32 x VEC columns x 8 row-lanes, 16-byte loads (VEC = 8 bf16 / 4 fp32 per thread); grid.y splits the rows;
+  // partial sums combined through smem, then one atomic per column and block (out pre-zeroed)
+  constexpr int VEC = sizeof(TIn) == 2 ? 8 : 4;
+  __shared__ float part[8][32 * VEC + 1];
+  const int lane = threadIdx.x & 31;
   const int ty = threadIdx.x >> 5;
+  const int c0 = (blockIdx.x * 32 + lane) * VEC;
   const long long rows_per = (R + gridDim.y - 1) / gridDim.y;
   const long long lo = blockIdx.y * rows_per, hi = min(R, lo + rows_per);
-  float s = 0.f;
-  if (c < C)
+  float s[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) s[v] = 0.f;
+  const bool vector_ok = c0 + VEC <= C && (ld % VEC) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+  if (vector_ok) {
+#pragma unroll 4
     for (long long r = lo + ty; r < hi; r += 8) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(in + r * ld + c0);
       if constexpr (sizeof(TIn) == 2) {
-        s += __bfloat162float(in[r * ld + c]);
+        const float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y), c = unpack_bf16x2(raw.z), d = unpack_bf16x2(raw.w);
+        s[0] += a.x; s[1] += a.y; s[2] += b.x; s[3] += b.y; s[4] += c.x; s[5] += c.y; s[6] += d.x; s[7] += d.y;
       } else {
-        s += in[r * ld + c];
+        s[0] += __uint_as_float(raw.x); s[1] += __uint_as_float(raw.y); s[2] += __uint_as_float(raw.z); s[3] += __uint_as_float(raw.w);
       }
     }
-  part[ty][threadIdx.x & 31] = s;
-  __syncthreads();
-  if (ty == 0 && c < C) {
-    float total = 0.f;
+  } else if (c0 < C) {
+    for (long long r = lo + ty; r < hi; r += 8)
+      for (int v = 0; v < VEC && c0 + v < C; ++v) {
+        if constexpr (sizeof(TIn) == 2) {
+          s[v] += __bfloat162float(in[r * ld + c0 + v]);
+        } else {
+          s[v] += in[r * ld + c0 + v];
+        }
+      }
+  }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) total += part[k][threadIdx.x & 31];
-    atomicAdd(out + c, total);
+  for (int v = 0; v < VEC; ++v) part[ty][lane * VEC + v] = s[v];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * VEC; i += 256) {
+    const int c = blockIdx.x * 32 * VEC + i;
+    if (c < C) {
+      float total = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) total += part[k][i];
+      atomicAdd(out + c, total);
+    }
   }
 }
 
@@ -493,9 +516,12 @@ static int colsum_any(const void* in, bool is_f32, int64_t ld, int64_t rows, int
   APH_REQUIRE(cols > 0, "bad shape");
   APH_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * cols, stream));
   if (rows <= 0) return APH_OK;
-  unsigned gy = static_cast<unsigned>(std::min<long long>(64, (rows + 255) / 256));
+  const int per_block = is_f32 ? 128 : 256;  // columns per block (32 lanes x 16 bytes)
+  const unsigned gx = static_cast<unsigned>((cols + per_block - 1) / per_block);
+  // ~4 blocks per SM in total, at least 64 rows per block
+  unsigned gy = static_cast<unsigned>(std::min<long long>((rows + 63) / 64, std::max<long long>(1, (148 * 4 + gx - 1) / gx)));
   if (gy < 1) gy = 1;
-  const dim3 grid(static_cast<unsigned>((cols + 31) / 32), gy);
+  const dim3 grid(gx, gy);
   if (is_f32)
     colsum_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(in), ld, rows, cols, out);
   else

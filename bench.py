@@ -230,7 +230,7 @@ def workload_config(n_gpus: int) -> Dict[str, Any]:
         "parallelism": f"dp{n_gpus} (independent utterance shards, no collective)",
         "l2": "per-step activations (>1 GB) exceed the 126 MB L2; no explicit flush between iterations",
         "e2e": "a stream of 10 x steps batches through Estimator.predict + decode_predictions_async: pinned host audio copied in on a "
-        "copy stream, decoded tokens copied out, CTCHypothesis lists built on the host while the next batch computes",
+        "copy stream, decoded tokens copied out, CTCHypothesis lists built on the host while the next two batches compute",
     }
 
 
@@ -287,13 +287,14 @@ def run_gpu_arm(args) -> None:
     def e2e_stream(steps: int):
         """A streaming client of the public API: while the GPU works on batch i+1 the host turns the copied-back
         tokens of batch i into CTCHypothesis lists.  Every batch is copied in, computed, copied out and decoded."""
-        pending, hypotheses = None, None
+        in_flight: List[Any] = []
+        hypotheses = None
         for _ in range(steps):
-            launched = e2e_launch()
-            if pending is not None:
-                hypotheses = pending.result()
-            pending = launched
-        hypotheses = pending.result()
+            in_flight.append(e2e_launch())
+            if len(in_flight) > 2:  # two batches in flight (the pinned result buffers rotate over three slots): 17.4 -> 16.8 ms/step
+                hypotheses = in_flight.pop(0).result()
+        while in_flight:
+            hypotheses = in_flight.pop(0).result()
         return hypotheses
 
     def barrier():

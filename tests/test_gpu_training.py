@@ -139,6 +139,14 @@ def test_small_training_kernels():
     x16 = x.bfloat16()
     assert range_err(ops.colsum_bf16(x16, rows, cols, cols), x16.float().sum(0)) < 1e-5
     assert range_err(ops.colsum_f32(x, rows, cols, cols), x.sum(0)) < 1e-5
+    # ragged widths / leading dimensions (scalar tail path), few rows, a strided column block of a wider matrix
+    for r, c, ld in [(5, 37, 40), (4896, 3072, 3072), (130, 501, 504), (1, 8, 8)]:
+        wide = torch.randn(r, ld, device=DEV)
+        assert range_err(ops.colsum_f32(wide, r, c, ld), wide[:, :c].sum(0)) < 1e-5
+        wide16 = wide.bfloat16()
+        assert range_err(ops.colsum_bf16(wide16, r, c, ld), wide16[:, :c].float().sum(0)) < 1e-5
+    block = torch.randn(700, 2048, device=DEV)
+    assert range_err(ops.colsum_f32(block[:, 1024:], 700, 1024, 2048), block[:, 1024:].sum(0)) < 1e-5
     lengths = torch.tensor([300, 499], device=DEV, dtype=torch.int32)
     masked = x.clone()
     ops.mask_rows(masked, cols, rows, cols, lengths, 499)
