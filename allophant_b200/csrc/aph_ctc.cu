@@ -23,6 +23,7 @@ namespace aph {
 constexpr int kCtcWarps = 4;
 constexpr int kCtcChunk = 32;    // frames staged per shared-memory refill
 constexpr int kCtcSmallC = 32;   // heads up to this many classes use the staged path
+constexpr int kCtcTinyC = 8;     // heads up to this many classes sum their occupancies per class in registers
 
 // The recursions run in the LOG2 domain with the hardware approximations ex2.approx / lg2.approx (relative error
 // 2^-22; the error of a 700-frame loss stays ~1e-7 relative, see test_ctc_long_labels_and_empty_targets) and without
@@ -40,13 +41,19 @@ __device__ __forceinline__ float lg2a(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// The term of the maximum is exp2(0) = 1 and is not computed: lse2 costs 2 MUFU ops, lse3 3 (the recursions are bound by
+// the MUFU issue rate of the ONE scheduler a warp lives on).  All-(-inf) inputs: the differences are taken against the
+// floored maximum (finite), the result is built on the true one: -inf + lg2(1) = -inf.
 __device__ __forceinline__ float lse2(float a, float b) {
-  const float m = fmaxf(fmaxf(a, b), -1e30f);
-  return m + lg2a(ex2a(a - m) + ex2a(b - m));
+  const float m = fmaxf(a, b), lo = fminf(a, b);
+  const float mf = fmaxf(m, -1e30f);
+  return m + lg2a(1.0f + ex2a(lo - mf));
 }
 __device__ __forceinline__ float lse3(float a, float b, float c) {
-  const float m = fmaxf(fmaxf(a, fmaxf(b, c)), -1e30f);
-  return m + lg2a(ex2a(a - m) + ex2a(b - m) + ex2a(c - m));
+  const float hi = fmaxf(a, b), lo = fminf(a, b);
+  const float m = fmaxf(hi, c), mid = fminf(hi, c);
+  const float mf = fmaxf(m, -1e30f);
+  return m + lg2a(1.0f + ex2a(mid - mf) + ex2a(lo - mf));
 }
 
 // The per-head descriptors travel BY VALUE in the kernel parameters (<= 4 KB): no device copy of the array, hence
@@ -187,7 +194,8 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_alpha_kernel(const __grid_
 #pragma unroll
         for (int i = 0; i < K; ++i) {
           const float cur = a[i];
-          const float v = lse3(cur, prev1, skip[i] ? prev2 : -INFINITY) + e[i];
+          // blank states (even s; K is even, so the parity of i is the parity of s) have no skip transition
+          const float v = ((i & 1) ? lse3(cur, prev1, skip[i] ? prev2 : -INFINITY) : lse2(cur, prev1)) + e[i];
           prev2 = prev1;
           prev1 = cur;
           a[i] = (lane * K + i) < S2 ? v : -INFINITY;
@@ -341,7 +349,7 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_beta_kernel(const __grid_c
 #pragma unroll
         for (int i = K - 1; i >= 0; --i) {
           const float cur = b[i];
-          const float v = lse3(cur, next1, skip[i] ? next2 : -INFINITY) + e[i];
+          const float v = ((i & 1) ? lse3(cur, next1, skip[i] ? next2 : -INFINITY) : lse2(cur, next1)) + e[i];
           next2 = next1;
           next1 = cur;
           b[i] = (lane * K + i) < S2 ? v : -INFINITY;
@@ -360,12 +368,33 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_beta_kernel(const __grid_c
       }
       blank_sum = warp_sum(blank_sum);
       if (small_c) {
-        if (lane < p.c) cs[lane] = 0.f;
-        __syncwarp();
+        if (p.c <= kCtcTinyC) {
+          // attribute heads (a handful of categories): per-class sums in registers + warp reductions; 32 lanes hammering 3-4
+          // shared-memory addresses with atomics serialised the whole frame
+          float acc[kCtcTinyC];
 #pragma unroll
-        for (int i = 0; i < K; ++i) {
-          const int s = lane * K + i;
-          if ((s & 1) && s < S2 && gam[i] != 0.f) atomicAdd(&cs[lab[i]], gam[i]);
+          for (int k = 0; k < kCtcTinyC; ++k) acc[k] = 0.f;
+#pragma unroll
+          for (int i = 1; i < K; i += 2) {  // label states (gam is 0 past S2)
+#pragma unroll
+            for (int k = 1; k < kCtcTinyC; ++k) acc[k] += lab[i] == k ? gam[i] : 0.f;
+          }
+#pragma unroll
+          for (int k = 1; k < kCtcTinyC; ++k) acc[k] = warp_sum(acc[k]);
+          if (lane < p.c) {
+            float mine = 0.f;
+#pragma unroll
+            for (int k = 1; k < kCtcTinyC; ++k) mine = lane == k ? acc[k] : mine;
+            cs[lane] = mine;
+          }
+        } else {
+          if (lane < p.c) cs[lane] = 0.f;
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < K; ++i) {
+            const int s = lane * K + i;
+            if ((s & 1) && s < S2 && gam[i] != 0.f) atomicAdd(&cs[lab[i]], gam[i]);
+          }
         }
         __syncwarp();
         if (lane < p.c) {
@@ -438,7 +467,9 @@ static int launch_beta(const CtcHeadPack& heads, int n_heads, int n_utt, int T, 
 
 static int pick_k(int max_label_len) {
   const int states = 2 * max_label_len + 1;
-  for (int k = 2; k <= 32; k *= 2)
+  // even K only (the recursions specialise on the parity of the state); fine steps where the label lengths of speech live
+  static const int kChoices[] = {2, 4, 6, 8, 10, 12, 16, 20, 24, 32};
+  for (int k : kChoices)
     if (states <= 32 * k) return k;
   return 0;
 }
@@ -473,6 +504,11 @@ extern "C" int aph_ctc_forward(const aph_ctc_head* heads_host, int32_t n_heads, 
       case 2: launch_alpha<2>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll, stream); break;
       case 4: launch_alpha<4>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll, stream); break;
       case 8: launch_alpha<8>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll, stream); break;
+      case 6: launch_alpha<6>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll, stream); break;
+      case 10: launch_alpha<10>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll, stream); break;
+      case 12: launch_alpha<12>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll, stream); break;
+      case 20: launch_alpha<20>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll, stream); break;
+      case 24: launch_alpha<24>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll, stream); break;
       case 16: launch_alpha<16>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll, stream); break;
       default: launch_alpha<32>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll, stream); break;
     }
@@ -517,6 +553,11 @@ extern "C" int aph_ctc_backward(const aph_ctc_head* heads_host, int32_t n_heads,
       case 2: launch_beta<2>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll_h, scale_h, stream); break;
       case 4: launch_beta<4>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll_h, scale_h, stream); break;
       case 8: launch_beta<8>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll_h, scale_h, stream); break;
+      case 6: launch_beta<6>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll_h, scale_h, stream); break;
+      case 10: launch_beta<10>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll_h, scale_h, stream); break;
+      case 12: launch_beta<12>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll_h, scale_h, stream); break;
+      case 20: launch_beta<20>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll_h, scale_h, stream); break;
+      case 24: launch_beta<24>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll_h, scale_h, stream); break;
       case 16: launch_beta<16>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll_h, scale_h, stream); break;
       default: launch_beta<32>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll_h, scale_h, stream); break;
     }

@@ -289,12 +289,36 @@ def run_gpu_arm(args) -> None:
         tokens of batch i into CTCHypothesis lists.  Every batch is copied in, computed, copied out and decoded."""
         in_flight: List[Any] = []
         hypotheses = None
+        trace = os.environ.get("BENCH_E2E_TRACE") == "1"
+        host = {"launch": 0.0, "wait": 0.0, "assemble": 0.0}
+        marks = []
         for _ in range(steps):
+            t0 = time.perf_counter()
+            if trace:
+                begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                begin.record()
             in_flight.append(e2e_launch())
+            if trace:
+                end.record()
+                marks.append((begin, end))
+            host["launch"] += time.perf_counter() - t0
             if len(in_flight) > 2:  # two batches in flight (the pinned result buffers rotate over three slots): 17.4 -> 16.8 ms/step
-                hypotheses = in_flight.pop(0).result()
+                pending = in_flight.pop(0)
+                t1 = time.perf_counter()
+                if trace:
+                    pending._event.synchronize()
+                t2 = time.perf_counter()
+                hypotheses = pending.result()
+                host["wait"] += t2 - t1
+                host["assemble"] += time.perf_counter() - t2
         while in_flight:
             hypotheses = in_flight.pop(0).result()
+        if trace:
+            torch.cuda.synchronize()
+            busy = sum(a.elapsed_time(b) for a, b in marks) / steps
+            span = marks[0][0].elapsed_time(marks[-1][1]) / steps
+            print(f"[e2e trace] steps {steps}: GPU busy {busy:.2f} ms/step, GPU span {span:.2f} ms/step; host launch {host['launch'] / steps * 1e3:.2f}, "
+                  f"wait {host['wait'] / steps * 1e3:.2f}, assemble {host['assemble'] / steps * 1e3:.2f} ms/step", file=sys.stderr, flush=True)  # fmt: skip
         return hypotheses
 
     def barrier():
@@ -318,10 +342,14 @@ def run_gpu_arm(args) -> None:
     for _ in range(max(3, args.warmup)):
         device_step()
     ops.reset_launch_count()
-    with ClockSampler(local_rank) as sampler:
+    if os.environ.get("BENCH_NO_CLOCK_SAMPLER") == "1":  # diagnostic: is the nvidia-smi poller perturbing what follows?
         elapsed_ms = timed(device_step, args.steps)
+        clocks = {}
+    else:
+        with ClockSampler(local_rank) as sampler:
+            elapsed_ms = timed(device_step, args.steps)
+        clocks = sampler.summary()
     launches = ops.launch_count() // args.steps
-    clocks = sampler.summary()
 
     e2e_stream(2)
     barrier()
