@@ -166,7 +166,7 @@ _SIGNATURES = {
 EXPORTED_SYMBOLS = sorted(
     list(_SIGNATURES)
     + ["aph_abi_version", "aph_last_error", "aph_launch_count", "aph_reset_launch_count", "aph_word_error_rate"]
-    + ["aph_edit_operations", "aph_segmenter_create", "aph_segmenter_free", "aph_segmenter_find"]
+    + ["aph_edit_operations", "aph_edit_weighted", "aph_segmenter_create", "aph_segmenter_free", "aph_segmenter_find"]
 )
 
 
@@ -186,6 +186,8 @@ def _load() -> ctypes.CDLL:
     lib.aph_word_error_rate.restype = c_float
     lib.aph_edit_operations.argtypes = [_P, _I64, _P, _I64, _P, _P]
     lib.aph_edit_operations.restype = c_int64
+    lib.aph_edit_weighted.argtypes = [_I64, _I64, _P, c_float, c_float, _I32, _P, _P, _P, _P]
+    lib.aph_edit_weighted.restype = c_int64
     lib.aph_segmenter_create.argtypes = [c_char_p, _P, _I64]
     lib.aph_segmenter_create.restype = c_void_p
     lib.aph_segmenter_free.argtypes = [c_void_p]

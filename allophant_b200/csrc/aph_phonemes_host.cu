@@ -142,6 +142,102 @@ extern "C" int64_t aph_edit_operations(const int64_t* a, int64_t m, const int64_
   return count;
 }
 
+// ---- PropertyWeighting (src/edit_distance.rs:497-598): the same three walks over a WEIGHTED matrix.  The substitution cost
+// of every (i, j) pair comes in as sub_cost[i * n + j] (the host evaluates property_table[a_i].ne(property_table[b_j]).sum()
+// once per distinct symbol pair); row 0 is 0..n in unit steps and column 0 grows by deletion_cost, exactly like
+// levensthein_*_general (120-141: `(0..=n).map(|x| x as f32)`, `current_row[0] += deletion_cost`).
+static void weighted_matrix(int64_t m, int64_t n, const float* sub_cost, float insertion_cost, float deletion_cost, float* cost) {
+  const int64_t w = n + 1;
+  for (int64_t j = 0; j <= n; ++j) cost[j] = static_cast<float>(j);
+  for (int64_t i = 1; i <= m; ++i) {
+    const float* up = cost + (i - 1) * w;
+    float* row = cost + i * w;
+    row[0] = up[0] + deletion_cost;
+    for (int64_t j = 1; j <= n; ++j) {
+      const float insertion = row[j - 1] + insertion_cost;
+      const float deletion = up[j] + deletion_cost;
+      const float substitution = up[j - 1] + sub_cost[(i - 1) * n + (j - 1)];
+      row[j] = std::min(std::min(insertion, deletion), substitution);
+    }
+  }
+}
+
+// mode 0: matrix_out gets the (m+1) x (n+1) matrix.  mode 1: ops_out gets the first best path (see aph_edit_operations),
+// the return value is their number.  mode 2: stats_out gets (insertions, deletions, substitutions, correct).
+extern "C" int64_t aph_edit_weighted(int64_t m, int64_t n, const float* sub_cost, float insertion_cost, float deletion_cost, int32_t mode,
+                                     float* matrix_out, int64_t* ops_out, uint64_t* stats_out, float* final_cost) {
+  APH_REQUIRE(m >= 0 && n >= 0 && (m == 0 || n == 0 || sub_cost) && mode >= 0 && mode <= 2, "edit_weighted: bad arguments");
+  APH_REQUIRE((mode != 0 || matrix_out) && (mode != 1 || ops_out) && (mode != 2 || stats_out), "edit_weighted: missing output");
+  const int64_t w = n + 1;
+  std::vector<float> local;
+  float* cost = matrix_out;
+  if (mode != 0) {
+    local.resize(static_cast<size_t>((m + 1) * w));
+    cost = local.data();
+  }
+  weighted_matrix(m, n, sub_cost, insertion_cost, deletion_cost, cost);
+  if (final_cost) *final_cost = cost[m * w + n];
+  if (mode == 0) return 0;
+  int64_t i = m, j = n, count = 0;
+  uint64_t insertions = 0, deletions = 0, substitutions = 0, correct = 0;
+  float current = cost[m * w + n];
+  while (current != 0.0f) {
+    int action;
+    if (i == 0) {
+      if (j == 0) break;
+      action = 0;
+      current = cost[j - 1];
+    } else if (j == 0) {
+      action = 1;
+      current = cost[(i - 1) * w];
+    } else {
+      const float deletion = cost[(i - 1) * w + j];
+      const float insertion = cost[i * w + j - 1];
+      const float diagonal = cost[(i - 1) * w + j - 1];
+      float step;
+      if (deletion < insertion) {
+        action = 1;
+        step = deletion;
+      } else {
+        action = 0;
+        step = insertion;
+      }
+      if (diagonal <= step) {
+        action = diagonal == current ? -1 : 2;
+        step = diagonal;
+      }
+      current = step;
+    }
+    if (action == 0) {
+      --j;
+      ++insertions;
+    } else if (action == 1) {
+      --i;
+      ++deletions;
+    } else {
+      --i;
+      --j;
+      if (action == 2) ++substitutions; else ++correct;
+    }
+    if (mode == 1 && action >= 0) {
+      ops_out[3 * count + 0] = action;
+      ops_out[3 * count + 1] = i;
+      ops_out[3 * count + 2] = j;
+      ++count;
+    }
+  }
+  if (mode == 1) {
+    for (int64_t lo = 0, hi = count - 1; lo < hi; ++lo, --hi)
+      for (int c = 0; c < 3; ++c) std::swap(ops_out[3 * lo + c], ops_out[3 * hi + c]);
+    return count;
+  }
+  stats_out[0] = insertions;
+  stats_out[1] = deletions;
+  stats_out[2] = substitutions;
+  stats_out[3] = correct + static_cast<uint64_t>(i);  // the remaining prefix counts as correct (edit_distance.rs:473-474)
+  return 0;
+}
+
 // IpaSegmenter::new (ipa_segmenter.rs:96-104): vocabulary as one UTF-8 blob + n+1 byte offsets
 extern "C" void* aph_segmenter_create(const char* blob, const int64_t* offsets, int64_t n) {
   if ((n > 0 && (!blob || !offsets)) || n < 0) return nullptr;

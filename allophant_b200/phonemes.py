@@ -192,6 +192,48 @@ def to_substitutions(string_a: Sequence[str], string_b: Sequence[str], operation
     return result
 
 
+class PropertyWeighting:
+    """Edit distances whose substitution cost is the number of differing phonetic properties
+    (``src/edit_distance.rs:497-598``): ``property_table[symbol]`` is a 1-D tensor / array of properties."""
+
+    def __init__(self, insertion_cost: float, deletion_cost: float, property_table) -> None:
+        self._insertion_cost = float(insertion_cost)
+        self._deletion_cost = float(deletion_cost)
+        self._table = property_table
+
+    def _substitution_costs(self, string_a: Sequence, string_b: Sequence) -> np.ndarray:
+        rows_a = np.stack([np.asarray(self._table[symbol]) for symbol in string_a]) if len(string_a) else np.zeros((0, 1))
+        rows_b = np.stack([np.asarray(self._table[symbol]) for symbol in string_b]) if len(string_b) else np.zeros((0, 1))
+        if not len(string_a) or not len(string_b):
+            return np.zeros((max(1, len(string_a) * len(string_b)),), dtype=np.float32)
+        return np.ascontiguousarray((rows_a[:, None, :] != rows_b[None, :, :]).sum(-1).astype(np.float32))
+
+    def _run(self, string_a: Sequence, string_b: Sequence, mode: int):
+        m, n = len(string_a), len(string_b)
+        costs = self._substitution_costs(string_a, string_b)
+        matrix = np.zeros((m + 1, n + 1), dtype=np.float32) if mode == 0 else None
+        operations = np.zeros((max(1, m + n), 3), dtype=np.int64) if mode == 1 else None
+        stats = np.zeros(4, dtype=np.uint64) if mode == 2 else None
+        final = ctypes.c_float(0.0)
+        pointer = lambda array: None if array is None else _pointer(array)  # noqa: E731
+        count = lib.aph_edit_weighted(m, n, _pointer(costs), self._insertion_cost, self._deletion_cost, mode, pointer(matrix), pointer(operations), pointer(stats), ctypes.byref(final))
+        if count < 0:
+            check(int(count), "aph_edit_weighted")
+        return matrix, operations, stats, int(count), float(final.value)
+
+    def levensthein_matrix(self, string_a: Sequence, string_b: Sequence):
+        import torch
+
+        return torch.from_numpy(self._run(string_a, string_b, 0)[0])
+
+    def levensthein_operations(self, string_a: Sequence, string_b: Sequence) -> Tuple[LevenstheinOperations, float]:
+        _, operations, _, count, cost = self._run(string_a, string_b, 1)
+        return [(Action.from_int(int(action)), int(i), int(j)) for action, i, j in operations[:count].tolist()], cost
+
+    def levensthein_statistics(self, string_a: Sequence, string_b: Sequence) -> EditStatistics:
+        return EditStatistics(*self._run(string_a, string_b, 2)[2].tolist())
+
+
 class MissingSegmentError(ValueError):
     """``src/ipa_segmenter.rs:11``."""
 

@@ -454,6 +454,11 @@ int aph_edit_matrix(const int64_t* a, int64_t m, const int64_t* b, int64_t n, fl
  * order (action 0 insertion / 1 deletion / 2 substitution), at most m + n; returns their number or a negative error. */
 int64_t aph_edit_operations(const int64_t* a, int64_t m, const int64_t* b, int64_t n, int64_t* ops_out,
                             float* final_cost);
+/* PropertyWeighting (src/edit_distance.rs:497-598): weighted edit distance with sub_cost[i*n + j] = substitution cost of
+ * (a_i, b_j); mode 0 -> matrix_out (m+1)x(n+1), 1 -> ops_out (returns their number), 2 -> stats_out[4]. */
+int64_t aph_edit_weighted(int64_t m, int64_t n, const float* sub_cost, float insertion_cost, float deletion_cost,
+                          int32_t mode, float* matrix_out, int64_t* ops_out, uint64_t* stats_out,
+                          float* final_cost);
 /* IpaSegmenter (src/ipa_segmenter.rs): leftmost-longest non-overlapping vocabulary matches over UTF-8 bytes. */
 void* aph_segmenter_create(const char* blob, const int64_t* offsets, int64_t n);
 void aph_segmenter_free(void* handle);
