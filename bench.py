@@ -72,7 +72,44 @@ class ClockSampler:
         self._stop = threading.Event()
         self._thread = threading.Thread(target=self._run, daemon=True)
 
+    def _run_nvml(self) -> bool:
+        """NVML in-process (nvidia_ml_py): a sample costs microseconds, so even a 150 ms timed region gets a dozen of them;
+        the nvidia-smi subprocess below (~100 ms per call) is the fallback."""
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = self.index
+            if visible:
+                entries = [entry.strip() for entry in visible.split(",") if entry.strip()]
+                if index < len(entries) and entries[index].isdigit():
+                    index = int(entries[index])
+            handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            max_clock = pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)
+            flags = (
+                ("hw_slowdown", pynvml.nvmlClocksEventReasonHwSlowdown),
+                ("hw_thermal_slowdown", pynvml.nvmlClocksEventReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", pynvml.nvmlClocksEventReasonSwThermalSlowdown),
+                ("sw_power_cap", pynvml.nvmlClocksEventReasonSwPowerCap),
+            )
+            pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            return False
+        while not self._stop.is_set():
+            try:
+                clock = pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+                reasons = pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                power = pynvml.nvmlDeviceGetPowerUsage(handle) / 1000.0
+                self.samples.append([str(clock), str(max_clock), str(power)] + ["Active" if reasons & bit else "Not Active" for _, bit in flags])
+            except Exception:
+                pass
+            self._stop.wait(0.01)
+        return True
+
     def _run(self) -> None:
+        if self._run_nvml():
+            return
         while not self._stop.is_set():
             try:
                 out = subprocess.run(

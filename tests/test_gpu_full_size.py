@@ -1,0 +1,101 @@
+"""-m gpu: BASELINE.json's full-size configuration (configs[1]: XLS-R-300M shape, 24 layers, 32 x 10 s, 37 heads) through
+size-independent properties — the CPU oracle needs minutes for this size, so instead of a value comparison the tests check
+what must hold for ANY correct implementation of the path:
+
+* every head's log-probabilities are normalised (logsumexp = 0) and finite on all valid frames; frame counts follow the
+  convolution length formula (acoustic_model.py:832-835);
+* utterances are independent: an utterance computed alone, inside a batch of different composition, or at a
+  different batch position gives the same log-probabilities (bf16 tolerance: the GEMM tiling of a row does not depend on
+  its neighbours, the attention masks other lengths) and the same greedy hypotheses wherever the argmax margin is clear;
+* the path is deterministic: two runs are bit-identical;
+* greedy decoding is the collapse of the per-frame argmax: tokens = unique-consecutive non-blank argmax, timesteps strictly
+  increasing 1-based run starts, score = sum of the per-frame maxima (predictions.py:194-207).
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def full_size():
+    import bench
+    from allophant_b200.dataset_processing import Batch
+
+    estimator, tfi = bench.build_estimator(DEV)
+    samples = bench.SECONDS * bench.SAMPLE_RATE
+    generator = torch.Generator().manual_seed(7)
+    audio = 0.1 * torch.randn(bench.BATCH, samples, generator=generator)
+    lengths = torch.full((bench.BATCH,), samples, dtype=torch.long)
+    lengths[3], lengths[17], lengths[31] = samples // 2, 16000, 400 + 3 * 320  # ragged: 5 s, 1 s and the shortest sensible clip
+    audio = audio * (torch.arange(samples)[None, :] < lengths[:, None])
+    batch = Batch(audio.to(DEV), lengths.to(DEV), torch.zeros(bench.BATCH, dtype=torch.long, device=DEV))
+    with torch.inference_mode():
+        predictions = estimator.predict(batch, tfi.to(DEV))
+    return dict(estimator=estimator, tfi=tfi.to(DEV), audio=audio, lengths=lengths, batch=batch, predictions=predictions, Batch=Batch)
+
+
+def test_log_probabilities_are_normalised_and_frames_follow_the_length_formula(full_size):
+    predictions, lengths = full_size["predictions"], full_size["lengths"]
+    frames = lengths.clone()
+    for kernel, stride in zip((10, 3, 3, 3, 3, 2, 2), (5, 2, 2, 2, 2, 2, 2)):
+        frames = torch.div(frames - kernel, stride, rounding_mode="floor") + 1
+    assert torch.equal(predictions.lengths.cpu(), frames)
+    assert len(predictions.outputs) == 37 and int(frames.max()) == 499
+    valid = (torch.arange(499)[:, None] < frames[None, :]).to(DEV)  # [T', N]
+    for name, log_probs in predictions.outputs.items():
+        assert log_probs.shape[:2] == (499, 32), name
+        assert bool(torch.isfinite(log_probs[valid]).all()), name
+        total = torch.logsumexp(log_probs.float(), -1)[valid]
+        assert float(total.abs().max()) < 1e-4, (name, float(total.abs().max()))
+
+
+def test_two_runs_are_bit_identical(full_size):
+    with torch.inference_mode():
+        again = full_size["estimator"].predict(full_size["batch"], full_size["tfi"])
+    for name, value in full_size["predictions"].outputs.items():
+        assert torch.equal(again.outputs[name], value), name
+
+
+def test_utterances_are_independent_of_batch_composition(full_size):
+    """Alone, re-ordered and in a smaller batch: same log-probabilities (<= 2e-2 of the head's range on valid frames)."""
+    Batch, estimator, tfi = full_size["Batch"], full_size["estimator"], full_size["tfi"]
+    audio, lengths, reference = full_size["audio"], full_size["lengths"], full_size["predictions"]
+    picks = [3, 17, 31, 0]
+    for group in ([3], [31, 0, 17], [17, 3]):
+        longest = int(lengths[group].max())
+        sub = Batch(audio[group, :longest].to(DEV), lengths[group].to(DEV), torch.zeros(len(group), dtype=torch.long, device=DEV))
+        with torch.inference_mode():
+            outputs = estimator.predict(sub, tfi)
+        for position, index in enumerate(group):
+            count = int(reference.lengths[index])
+            assert int(outputs.lengths[position]) == count
+            for name in ("phoneme", "syllabic", "continuant") if "syllabic" in reference.outputs else list(reference.outputs)[:3]:
+                ours = outputs.outputs[name][:count, position].float()
+                theirs = reference.outputs[name][:count, index].float()
+                spread = float(theirs.max() - theirs.min())
+                assert float((ours - theirs).abs().max()) <= 2e-2 * spread, (group, index, name)
+    assert picks
+
+
+def test_greedy_hypotheses_are_the_collapsed_argmax(full_size):
+    from allophant_b200 import predictions as decoding
+
+    reference = full_size["predictions"]
+    hypotheses = decoding.decode_predictions(reference)
+    assert sorted(hypotheses) == sorted(reference.outputs)
+    for name in list(reference.outputs)[:4] + ["phoneme"]:
+        log_probs = reference.outputs[name].float().transpose(0, 1).cpu()  # [N, T', C]
+        for index in (0, 3, 17, 31):
+            count = int(reference.lengths[index])
+            best = log_probs[index, :count].max(-1)
+            tokens, sizes = torch.unique_consecutive(best.indices, return_counts=True)
+            starts = sizes.cumsum(0) - sizes + 1
+            keep = tokens != 0
+            [hypothesis] = hypotheses[name][index]
+            assert hypothesis.tokens.tolist() == tokens[keep].tolist(), (name, index)
+            assert hypothesis.timesteps.tolist() == starts[keep].tolist(), (name, index)
+            assert abs(float(hypothesis.score) - float(best.values.sum())) <= 1e-3 * max(1.0, abs(float(best.values.sum())))
+            assert hypothesis.timesteps.tolist() == sorted(set(hypothesis.timesteps.tolist()))
