@@ -99,3 +99,74 @@ def test_greedy_hypotheses_are_the_collapsed_argmax(full_size):
             assert hypothesis.timesteps.tolist() == starts[keep].tolist(), (name, index)
             assert abs(float(hypothesis.score) - float(best.values.sum())) <= 1e-3 * max(1.0, abs(float(best.values.sum())))
             assert hypothesis.timesteps.tolist() == sorted(set(hypothesis.timesteps.tolist()))
+
+
+def test_full_size_gradients_of_shards_sum_to_the_full_batch_gradient():
+    """BASELINE configs[2] at full model size (24 layers, allophone layer over 34 languages x 500 phones, 8 utterances of
+    3-15 s): the UN-NORMALISED gradient of the summed CTC losses is additive over utterances, so the gradients of two
+    half-batches must sum to the full-batch gradient — the property the data-parallel training step relies on (SURVEY.md §8e:
+    sum all-reduce + one global normaliser).  eval() arithmetic; tolerance 2e-2 norm-relative per parameter tensor (bf16
+    operands: the halves are padded to different lengths and tile differently)."""
+    import bench
+    from allophant_b200.dataset_processing import Batch
+    from allophant_b200.loss_functions import multi_head_ctc_loss
+
+    estimator, allophones = bench.build_training_estimator(DEV)
+    model = estimator.model
+    model.eval()
+    generator = torch.Generator().manual_seed(3)
+    count = bench.TRAIN_BATCH
+    seconds = 3.0 + 12.0 * torch.rand(count, generator=generator)
+    lengths = (seconds * bench.SAMPLE_RATE).long().sort(descending=True).values
+    samples = int(lengths.max())
+    audio = 0.1 * torch.randn(count, samples, generator=generator) * (torch.arange(samples)[None, :] < lengths[:, None])
+    languages = torch.randint(0, bench.TRAIN_LANGUAGES, (count,), generator=generator)
+    frames = model.downsampled_lengths(lengths)
+    names = list(model.classes)
+    labels, label_lengths = {}, {}
+    for name in names:
+        head_lengths = (frames.double() * 0.25).floor().long()
+        head_labels = torch.zeros(count, int(head_lengths.max()), dtype=torch.long)
+        for row, length in enumerate(head_lengths.tolist()):
+            if name == "phoneme":
+                inventory = torch.tensor(sorted(allophones[int(languages[row])]), dtype=torch.long) + 1
+                head_labels[row, :length] = inventory[torch.randint(0, len(inventory), (length,), generator=generator)]
+            else:
+                head_labels[row, :length] = torch.randint(1, 4, (length,), generator=generator)
+        labels[name], label_lengths[name] = head_labels, head_lengths
+    parameters = {name: parameter for name, parameter in model.named_parameters() if parameter.requires_grad}
+
+    def gradients(rows):
+        rows = list(rows)
+        longest = int(lengths[rows].max())
+        batch = Batch(audio[rows, :longest].to(DEV), lengths[rows].to(DEV), languages[rows].to(DEV))
+        for parameter in parameters.values():
+            parameter.grad = None
+        predictions = model(batch)
+        predictions.outputs.pop("phone", None)
+        order = list(predictions.outputs)
+        losses = multi_head_ctc_loss(
+            [predictions.outputs[name] for name in order],
+            [labels[name][rows][:, : int(label_lengths[name][rows].max())].to(DEV) for name in order],
+            predictions.lengths,
+            [label_lengths[name][rows].to(DEV) for name in order],
+        )
+        total = losses.sum()
+        total.backward()
+        return float(total.detach()), {name: parameter.grad.detach().clone() for name, parameter in parameters.items() if parameter.grad is not None}
+
+    full_loss, full = gradients(range(count))
+    first_loss, first = gradients(range(0, count, 2))
+    second_loss, second = gradients(range(1, count, 2))
+    assert abs(first_loss + second_loss - full_loss) <= 2e-3 * abs(full_loss)
+    assert len(full) > 400  # every trainable tensor of the 24-layer model got a gradient
+    worst = 0.0
+    for name, gradient in full.items():
+        combined = first[name].double() + second[name].double()
+        size = float(gradient.double().norm())
+        if size < 1e-6:
+            continue
+        worst = max(worst, float((combined - gradient.double()).norm()) / size)
+        assert torch.isfinite(gradient).all(), name
+    print(f"full-size shard additivity: loss {full_loss:.2f} = {first_loss:.2f} + {second_loss:.2f}; worst gradient deviation {worst:.3e}")
+    assert worst < 2e-2, worst
