@@ -8,8 +8,8 @@ mode with the train()-mode ops applied through explicit masks, ``OracleModel.exp
 2e-2 of range for bf16-operand kernels (as in test_gpu_training.py); 1e-1 norm-relative for the end-to-end gradients.
 The latter is read against the measured noise floor of the bf16 path on these tiny models: in eval() mode the worst
 per-tensor deviation moves between 2.1e-2 and 5.6e-2 over eight audio seeds (profiles/r01_regularisation_noise_floor.log,
-tools/gpu_debug_noise.py), and the train()-mode steps land in the same band (1.3e-2 ... 8.3e-2 over sites and seeds,
-tools/gpu_debug_regularisation.py), while a wrong mask at any single site moves the gradients by >= 3e-1.
+tests/diagnostics/gpu_noise_floor.py), and the train()-mode steps land in the same band (1.3e-2 ... 8.3e-2 over sites and seeds,
+tests/diagnostics/gpu_regularisation_sites.py), while a wrong mask at any single site moves the gradients by >= 3e-1.
 """
 import pytest
 import torch

@@ -5,9 +5,19 @@ import torch
 sys.path.insert(0, ".")
 from allophant_b200 import ops
 from allophant_b200.loss_functions import multi_head_ctc_loss
-from oracle import restatement
 
 dev = "cuda"
+
+
+def synthetic_labels(frames, n_classes, seed, fraction=0.25):
+    """Random label sequences in [1, n_classes) of length floor(fraction * frames)."""
+    generator = torch.Generator().manual_seed(seed)
+    lengths = (frames.double() * fraction).floor().long().clamp_min(1)
+    labels = torch.zeros(len(frames), int(lengths.max()), dtype=torch.long)
+    for row, length in enumerate(lengths.tolist()):
+        labels[row, :length] = torch.randint(1, n_classes, (length,), generator=generator)
+    return labels, lengths
+
 PEAK = 6542.7
 
 
@@ -82,7 +92,7 @@ for n_utt in (8, 64):
     logits_l, labels_l, lens_l = [], [], []
     for h, c in enumerate(classes):
         logits_l.append(torch.randn(n_utt, frames, c, device=dev).transpose(0, 1).requires_grad_(True))
-        lab, ll = restatement.synthetic_labels(input_lengths, c, seed=h)
+        lab, ll = synthetic_labels(input_lengths, c, seed=h)
         labels_l.append(lab.to(dev))
         lens_l.append(ll.to(dev))
     il = input_lengths.to(dev)
