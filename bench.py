@@ -21,7 +21,7 @@ import subprocess
 import sys
 import threading
 import time
-from typing import Any, Dict, List, Optional
+from typing import Any, Dict, List, Optional, Tuple
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -271,6 +271,57 @@ def workload_config(n_gpus: int) -> Dict[str, Any]:
     }
 
 
+def cupti_gemm_time(step, is_encoder_linear) -> Optional[Tuple[int, float]]:
+    """(launches, summed kernel milliseconds) of the encoder-linear GEMMs of one UN-BRACKETED step, from CUPTI kernel
+    records (torch.profiler): every `ops.run_gemm` call launches exactly one `gemm_bf16_kernel` on the one stream of the
+    step, so the k-th kernel record belongs to the k-th call; `is_encoder_linear(args)` picks the same launches the event
+    brackets time.  None when CUPTI is not available or the records do not line up."""
+    from allophant_b200 import ops
+
+    flags: List[bool] = []
+    original = ops.run_gemm
+
+    def recording_gemm(gemm_args):
+        flags.append(bool(is_encoder_linear(gemm_args)))
+        original(gemm_args)
+
+    try:
+        from torch.profiler import ProfilerActivity, profile
+
+        torch.cuda.synchronize()
+        ops.run_gemm = recording_gemm
+        try:
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                step()
+                torch.cuda.synchronize()
+        finally:
+            ops.run_gemm = original
+        kernels = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "gemm_bf16_kernel" in e.name),
+                         key=lambda e: e.time_range.start)  # fmt: skip
+    except Exception:
+        return None
+    if len(kernels) != len(flags) or not any(flags):
+        return None
+    total_us = sum(event.time_range.end - event.time_range.start for event, flag in zip(kernels, flags) if flag)
+    return sum(flags), total_us / 1000.0
+
+
+def kernel_only_roofline(step, is_encoder_linear, flops: float, peak: float, step_ms: float) -> Optional[Dict[str, Any]]:
+    """Cross-check of `roofline.achieved` without the event brackets: a CUDA event between two launches keeps the GPU front
+    end from overlapping the launch of the next kernel with the execution of the previous one, so every bracketed GEMM pays
+    its full launch latency (10-16 us for a kernel whose parameters hold four tensor maps)."""
+    measured = cupti_gemm_time(step, is_encoder_linear)
+    if measured is None:
+        return None
+    count, total_ms = measured
+    achieved = flops / (total_ms / 1000.0) / 1e12
+    return {
+        "source": "CUPTI kernel records of one un-bracketed step (torch.profiler), the same launches as the event brackets",
+        "launches": count, "avg_launch_ms": total_ms / max(1, count), "achieved": achieved, "frac": achieved / peak,
+        "share_of_step": total_ms / step_ms,
+    }  # fmt: skip
+
+
 # --------------------------------------------------------------------------------------------------
 def run_gpu_arm(args) -> None:
     from allophant_b200 import ops
@@ -457,6 +508,11 @@ def run_gpu_arm(args) -> None:
             "avg_launch_ms": gemm_ms / max(1, len(gemm_events)),
             "share_of_step": gemm_ms / (elapsed_ms / args.steps),
         }
+        kernel_only = kernel_only_roofline(
+            device_step, lambda g: g.k in (1024, 4096) and g.n in (1024, 3072, 4096) and g.mode == 0, flops, peak, elapsed_ms / args.steps
+        )
+        if kernel_only is not None:
+            roofline["kernel_only"] = kernel_only
         if not args.skip_cpu_baseline:
             baseline = time_cpu_reference(2, 3, 1)
             cpu_baseline = {k: baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -670,12 +726,14 @@ def run_train_arm(args) -> None:
     original = ops.run_gemm
     sizes = (1024, 3072, 4096)
 
-    def timed_gemm(gemm_args):
-        encoder_linear = gemm_args.mode == 0 and gemm_args.n in sizes and (
+    def is_encoder_linear(gemm_args) -> bool:
+        return gemm_args.mode == 0 and gemm_args.n in sizes and (
             (not gemm_args.b_mn_major and gemm_args.k in sizes) or (gemm_args.b_mn_major and not gemm_args.a_mn_major and gemm_args.k_seq in sizes)
             or (gemm_args.a_mn_major and gemm_args.a_rows in sizes)
         )
-        if encoder_linear:
+
+    def timed_gemm(gemm_args):
+        if is_encoder_linear(gemm_args):
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
             original(gemm_args)
@@ -706,6 +764,21 @@ def run_train_arm(args) -> None:
             "peak_source": f"bf16_tflops_sustained, {peaks['source']}", "launches": len(gemm_events),
             "avg_launch_ms": gemm_ms / max(1, len(gemm_events)), "share_of_step": gemm_ms / (elapsed_ms / args.steps),
         }  # fmt: skip
+    # one more step on every rank (collectives inside): rank 0 reads the un-bracketed kernel durations from CUPTI
+    if rank == 0:
+        unbracketed = cupti_gemm_time(device_step, is_encoder_linear)
+        if unbracketed is not None and roofline is not None:
+            count, total_ms = unbracketed
+            skipped = list(model._heads.last_regularisation["plan"].skipped)
+            step_flops = 3.0 * encoder_flops(int(frames.max()))["linear"] * TRAIN_BATCH * (len(skipped) - sum(skipped)) / max(1, len(skipped))
+            roofline["kernel_only"] = {
+                "source": "CUPTI kernel records of one un-bracketed step (torch.profiler), the same launches as the event brackets",
+                "launches": count, "avg_launch_ms": total_ms / max(1, count), "achieved": step_flops / (total_ms / 1000.0) / 1e12,
+                "frac": step_flops / (total_ms / 1000.0) / 1e12 / roofline["peak"], "share_of_step": total_ms / (elapsed_ms / args.steps),
+            }  # fmt: skip
+    else:
+        device_step()
+        torch.cuda.synchronize()
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
