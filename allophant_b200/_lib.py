@@ -76,6 +76,7 @@ class GemmArgs(Structure):
         ("drop_threshold", ctypes.c_uint32),
         ("drop_seed", ctypes.c_uint32),
         ("drop_scale", ctypes.c_float),
+        ("act_bwd", c_int32),
     ]
 
 
@@ -150,6 +151,8 @@ _SIGNATURES = {
     "aph_multi_tensor_scale": [_P, _P, _I32, _P, _F, _P],
     "aph_multi_tensor_adam": [_P, _P, _P, _I32, _F, _F, _F, _F, _F, _I64, _P, _F, _P],
     "aph_layernorm_any": [_P, _I64, _I64, _I32, _P, _P, c_float, _P, _I64, _P, _I64, _P],
+    "aph_layernorm_any_backward": [_P, _I64, _P, _I64, _I64, _I32, _P, c_float, _P, _I64, _P, _I64, _P, _P, _P],
+    "aph_activation_backward": [_P, _I64, _P, _I64, _I64, _I32, _I32, _P, _I64, _P],
     "aph_add_sinusoidal": [_P, _I64, _I32, _I32, _I32, _P, _P],
     "aph_transpose_nfl": [_P, _I32, _I32, _I32, _P, _I64, _P],
     "aph_reflect_pad_bf16": [_P, _I64, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P],

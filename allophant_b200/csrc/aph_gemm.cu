@@ -93,6 +93,7 @@ struct GemmParams {
   uint32_t drop_threshold;
   uint32_t drop_seed;
   float drop_scale;
+  int act_bwd;
 };
 
 // Work item -> (n block, m pair, output batch, k-block range, B row shift)
@@ -440,8 +441,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float2 pre = unpack_bf16x2(wds[e]);
-                  v[8 * j + 2 * e + 0] *= gelu_erf_grad(pre.x);
-                  v[8 * j + 2 * e + 1] *= gelu_erf_grad(pre.y);
+                  if (p.act_bwd >= 2) {  // ReLU / LeakyReLU(0.01)
+                    const float low = p.act_bwd == 3 ? 0.01f : 0.f;
+                    v[8 * j + 2 * e + 0] *= pre.x > 0.f ? 1.f : low;
+                    v[8 * j + 2 * e + 1] *= pre.y > 0.f ? 1.f : low;
+                  } else {
+                    v[8 * j + 2 * e + 0] *= gelu_erf_grad(pre.x);
+                    v[8 * j + 2 * e + 1] *= gelu_erf_grad(pre.y);
+                  }
                 }
               }
             }
@@ -771,6 +778,8 @@ extern "C" int aph_gemm_bf16(const aph_gemm_args* a, void* stream_) {
   p.drop_threshold = a->drop_threshold;
   p.drop_seed = a->drop_seed;
   p.drop_scale = a->drop_scale;
+  p.act_bwd = a->act_bwd;
+  APH_REQUIRE(a->act_bwd >= 0 && a->act_bwd <= 3, "act_bwd: 0/1 GELU, 2 ReLU, 3 LeakyReLU");
   APH_REQUIRE(a->drop_threshold < 65536u, "drop_threshold is 16 bits (p < 1)");
   APH_REQUIRE(a->drop_threshold == 0 || (a->epilogue == APH_EPI_STORE && !a->a_mn_major), "dropout: store epilogue of a forward GEMM only");
   p.heads = a->heads;

@@ -115,6 +115,76 @@ __global__ void __launch_bounds__(256) glu_rows_kernel(const float* __restrict__
   }
 }
 
+// Backward of nn.LayerNorm over the last axis, any width, optional affine parameters; warp per row, statistics recomputed.
+//   dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;   dx_out = dx (+ resid);  dgamma += dy * xhat, dbeta += dy
+// dgamma / dbeta are ACCUMULATED with atomics (the final LayerNorm of the transformer model is applied to several layer
+// outputs); they are only present for elementwise_affine models.
+__global__ void __launch_bounds__(256) layernorm_any_backward_kernel(const float* __restrict__ x, long long ld_x, const float* __restrict__ dy,
+                                                                     long long ld_dy, long long rows, int cols,
+                                                                     const float* __restrict__ gamma, float eps, const float* resid,
+                                                                     long long ld_resid, float* dx, long long ld_dx, float* dgamma,
+                                                                     float* dbeta) {
+  const long long row = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + row * ld_x;
+  const float* dyr = dy + row * ld_dy;
+  float sum = 0.f;
+  for (int c = lane; c < cols; c += 32) sum += xr[c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / static_cast<float>(cols);
+  float sq = 0.f;
+  for (int c = lane; c < cols; c += 32) {
+    const float d = xr[c] - mean;
+    sq += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / static_cast<float>(cols) + eps);
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane; c < cols; c += 32) {
+    const float g = dyr[c] * (gamma != nullptr ? gamma[c] : 1.f);
+    s1 += g;
+    s2 += g * (xr[c] - mean) * rstd;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  const float c1 = s1 / static_cast<float>(cols), c2 = s2 / static_cast<float>(cols);
+  for (int c = lane; c < cols; c += 32) {
+    const float xhat = (xr[c] - mean) * rstd;
+    const float d = dyr[c];
+    if (dx != nullptr) {
+      float v = rstd * (d * (gamma != nullptr ? gamma[c] : 1.f) - c1 - xhat * c2);
+      if (resid != nullptr) v += resid[row * ld_resid + c];
+      dx[row * ld_dx + c] = v;
+    }
+    if (dgamma != nullptr) {
+      atomicAdd(dgamma + c, d * xhat);
+      atomicAdd(dbeta + c, d);
+    }
+  }
+}
+
+// d_pre = d_out * act'(.) from the activation's OUTPUT y (kind 2 ReLU: y > 0; kind 3 LeakyReLU(0.01): y > 0 ? 1 : 0.01),
+// fp32 in place + optional bf16 copy (the operand of the weight-gradient GEMM)
+__global__ void __launch_bounds__(256) activation_backward_kernel(float* d, long long ld_d, const float* __restrict__ y, long long ld_y,
+                                                                  long long rows, int cols, int kind, __nv_bfloat16* out_bf16,
+                                                                  long long ld_bf16) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const long long row = i / cols;
+    const int c = static_cast<int>(i - row * cols);
+    const float slope = y[row * ld_y + c] > 0.f ? 1.f : (kind == 3 ? 0.01f : 0.f);
+    const float v = d[row * ld_d + c] * slope;
+    d[row * ld_d + c] = v;
+    if (out_bf16 != nullptr) out_bf16[row * ld_bf16 + c] = __float2bfloat16(v);
+  }
+}
+
 }  // namespace aph
 
 using namespace aph;
@@ -177,6 +247,31 @@ extern "C" int aph_glu_rows(const float* y, int64_t ld_y, int64_t rows, int32_t 
   if (rows == 0) return APH_OK;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   glu_rows_kernel<<<blocks_for(rows * out_channels), 256, 0, stream>>>(y, ld_y, rows, out_channels, out, ld_out);
+  APH_POST_LAUNCH(1);
+  return APH_OK;
+}
+
+extern "C" int aph_layernorm_any_backward(const float* x, int64_t ld_x, const float* dy, int64_t ld_dy, int64_t rows, int32_t cols,
+                                          const float* gamma, float eps, const float* resid, int64_t ld_resid, float* dx, int64_t ld_dx,
+                                          float* dgamma, float* dbeta, void* stream_) {
+  APH_REQUIRE(x && dy && rows >= 0 && cols > 0, "layernorm_any_backward: bad arguments");
+  APH_REQUIRE(dx || dgamma, "layernorm_any_backward: no output");
+  APH_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_any_backward: dgamma and dbeta come together");
+  if (rows == 0) return APH_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  layernorm_any_backward_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(x, ld_x, dy, ld_dy, rows, cols, gamma, eps, resid, ld_resid,
+                                                                                             dx, ld_dx, dgamma, dbeta);
+  APH_POST_LAUNCH(1);
+  return APH_OK;
+}
+
+extern "C" int aph_activation_backward(float* d, int64_t ld_d, const float* y, int64_t ld_y, int64_t rows, int32_t cols, int32_t kind,
+                                       void* out_bf16, int64_t ld_bf16, void* stream_) {
+  APH_REQUIRE(d && y && rows >= 0 && cols > 0 && (kind == 2 || kind == 3), "activation_backward: kind 2 (ReLU) or 3 (LeakyReLU)");
+  if (rows == 0) return APH_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  activation_backward_kernel<<<blocks_for(rows * cols), 256, 0, stream>>>(d, ld_d, y, ld_y, rows, cols, kind, static_cast<__nv_bfloat16*>(out_bf16),
+                                                                          ld_bf16);
   APH_POST_LAUNCH(1);
   return APH_OK;
 }

@@ -320,14 +320,10 @@ class HeadsRuntime:
             self._build_layout()
         acoustic = model._acoustic_model
         if torch.is_grad_enabled() and not log_probabilities and not hasattr(acoustic, "_model"):
-            # from-scratch transformer encoder: no CUDA backward yet, the classifiers can still train on top of it
-            if any(p.requires_grad for p in acoustic.parameters()):
-                raise NotImplementedError(
-                    "allophant_b200: the from-scratch transformer encoder has no backward pass in this build; freeze its parameters "
-                    "or run under torch.no_grad()/inference_mode()"
-                )
-            if any(p.requires_grad for p in projection.parameters()):
-                return self._forward_differentiable(batch, target_feature_indices, predict, False, False)
+            # from-scratch transformer encoder (network/transformer.py): its own plan type with its own backward pass
+            need_encoder = any(p.requires_grad for p in acoustic.parameters())
+            if need_encoder or any(p.requires_grad for p in projection.parameters()):
+                return self._forward_differentiable(batch, target_feature_indices, predict, need_encoder, False)
         elif torch.is_grad_enabled() and not log_probabilities:
             weights = acoustic._model
             if any(p.requires_grad for p in weights.feature_extractor.parameters()):
@@ -412,6 +408,10 @@ class HeadsRuntime:
         )
         return predictions
 
+    def _encoder_prefix(self) -> str:
+        """``state_dict`` prefix of the encoder parameters the plan's ``backward`` names its gradients by."""
+        return "_acoustic_model._model." if hasattr(self.model._acoustic_model, "_model") else "_acoustic_model."
+
     @staticmethod
     def _rank() -> int:
         import torch.distributed as dist
@@ -456,7 +456,8 @@ class HeadsRuntime:
         self.last_regularisation = dict(stochastic=stochastic, input_dropout=input_dropout, plan=plan)  # introspection (tests)
         named = [(f"_projection.{name}", parameter) for name, parameter in self.model._projection.named_parameters()]
         if through_encoder:
-            named += [(f"_acoustic_model._model.{name}", parameter) for name, parameter in acoustic._model.named_parameters() if parameter.requires_grad]
+            weights = acoustic._model if hasattr(acoustic, "_model") else acoustic
+            named += [(self._encoder_prefix() + name, parameter) for name, parameter in weights.named_parameters() if parameter.requires_grad]
         state: Dict[str, Any] = dict(
             batch=batch, tfi=target_feature_indices, predict=predict, plan=plan, names=[n for n, _ in named], generation=None,
             need_encoder=need_encoder, need_feature_projection=need_feature_projection, input_dropout=input_dropout,
@@ -620,7 +621,7 @@ class HeadsRuntime:
                 d_x, state["need_encoder"], state["need_feature_projection"], None if reducer is None else reducer.submit
             )
             for name, value in encoder_grads.items():
-                param_grads[f"_acoustic_model._model.{name}"] = value
+                param_grads[self._encoder_prefix() + name] = value
         if reducer is not None:
             reducer.finish()
         return [param_grads.get(name) for name in state["names"]]

@@ -5,8 +5,11 @@
 only as parameter holders: the arithmetic is ``TransformerPlan``, a launch list over the same tcgen05 GEMM, flash
 attention and row kernels the wav2vec2 path uses (``aph_gemm.cu``, ``aph_attention.cu``, ``aph_transformer.cu``).
 
-Inference / frozen-encoder only in this build: the encoder has no CUDA backward yet, a forward in grad mode with
-trainable encoder parameters raises ``NotImplementedError``; dropout layers are identities (``eval()`` arithmetic).
+Training: ``TransformerPlan(training=True)`` keeps the activations and ``TransformerPlan.backward`` runs the backward
+pass of the transformer layers, the final LayerNorm, the positional embeddings and the direct / linear front end on the same
+GEMM (data-gradient / weight-gradient forms), flash-attention-backward and row kernels as the wav2vec2 path.  The backward
+pass of the GLU convolution stack (``sequential_frontend``) is not built: models with one train their classifiers on a
+frozen encoder only.  Dropout layers are identities (``eval()`` arithmetic) in both directions.
 """
 from __future__ import annotations
 
@@ -93,10 +96,10 @@ class TransformerPlan:
     last layer in the first ``d`` columns, final LayerNorm of the kept layer outputs at ``hidden_blocks``), ``rows``,
     ``n_utt``, ``seq``, ``frames32``, ``generation``."""
 
-    training = False
-
-    def __init__(self, model: "TransformerAcousticModel", n_utt: int, features: int, length: int, ldx: int, hidden_blocks: Dict[int, int]) -> None:
+    def __init__(self, model: "TransformerAcousticModel", n_utt: int, features: int, length: int, ldx: int, hidden_blocks: Dict[int, int],
+                 training: bool = False) -> None:  # fmt: skip
         self.model = model
+        self.training = training
         device = next(model.parameters()).device
         if device.type != "cuda":
             raise RuntimeError("allophant_b200 runs on CUDA only: move the model to a GPU (`model.to('cuda')`)")
@@ -159,6 +162,25 @@ class TransformerPlan:
         self.ctx = z(M, d)
         self.ffn = z(M, self.ff)
         self.x = z(M, ldx)
+        if training:
+            if self.stages:
+                raise NotImplementedError(
+                    "the backward pass of the sequential frontend (GLU convolution stack) is not part of this build: freeze the "
+                    "acoustic model (classifier training works) or use a configuration without `sequential_frontend`"
+                )
+            n_layers = len(model._transformer.layers)
+            # everything the backward pass reads, per layer (only the attention probabilities are recomputed)
+            self.saved = [
+                dict(h_in=z(M, d, dtype=f32), src=z(M, d, dtype=f32), src16=z(M, d), q=z(M * d), k=z(M * d), v=z(M * d),
+                     lse=z(n_utt * heads * seq, dtype=f32), ctx=z(M, d), h_mid=z(M, d, dtype=f32), ln2=z(M, d), pre=z(M, self.ff),
+                     act=z(M, self.ff), h_out=z(M, d, dtype=f32))
+                for _ in range(n_layers)
+            ]  # fmt: skip
+            self.fe_normed = z(self.in_rows, features) if isinstance(model._frontend, LinearFrontend) else None
+            self.fe_out = z(M, d, dtype=f32) if isinstance(model._frontend, LinearFrontend) else None
+            self.dh, self.dh16 = z(M, d, dtype=f32), z(M, d)
+            self.d_ff, self.d_ln, self.d_ctx = z(M, self.ff), z(M, d, dtype=f32), z(M, d)
+            self.dqkv, self.delta = z(M, 3 * d), z(n_utt * heads * seq, dtype=f32)
         self._packed_version: Optional[Tuple[int, ...]] = None
         self._packed: Dict[str, Any] = {}
 
@@ -211,10 +233,10 @@ class TransformerPlan:
         frontend = model._frontend
         if isinstance(frontend, LinearFrontend):
             gamma, beta = packed["fe_ln"]
-            normed = torch.empty(self.in_rows, channels, device=self.device, dtype=torch.bfloat16)
+            normed = self.fe_normed if self.training else torch.empty(self.in_rows, channels, device=self.device, dtype=torch.bfloat16)
             ops.layernorm_any(current, channels, self.in_rows, channels, gamma, beta, frontend.layer_norm.eps, out_bf16=normed, ld_bf16=channels)
             neurons = frontend.output_dimensions
-            out = torch.empty(self.in_rows, neurons, device=self.device, dtype=torch.float32)
+            out = self.fe_out if self.training else torch.empty(self.in_rows, neurons, device=self.device, dtype=torch.float32)
             args = ops.make_gemm_args(normed, packed["fe_w"], a_rows=self.in_rows, a_inner=channels, a_row_stride=channels, bias=packed["fe_b"], out_f32=out, ld_f32=neurons)
             args.gelu = 3  # LeakyReLU(0.01)
             ops.run_gemm(args)
@@ -250,17 +272,28 @@ class TransformerPlan:
         final_gamma, final_beta = packed["final"]
         n_layers = len(packed["layers"])
         for index, lw in enumerate(packed["layers"]):
+            if self.training:  # per-layer buffers: the backward pass reads them
+                sv = self.saved[index]
+                sv["h_in"].copy_(hidden)
+                src, src16, q, k, v, ctx, ln2, ffn, pre, lse = sv["src"], sv["src16"], sv["q"], sv["k"], sv["v"], sv["ctx"], sv["ln2"], sv["act"], sv["pre"], sv["lse"]
+                h_mid, h_out = sv["h_mid"], sv["h_out"]
+            else:
+                src, src16, q, k, v, ctx, ln2, ffn, pre, lse = self.src, self.ln16, self.q, self.k, self.v, self.ctx, self.ln16, self.ffn, None, None
+                h_mid = h_out = hidden
             g1, b1 = lw["ln1"]
-            ops.layernorm_any(hidden, d, M, d, g1, b1, eps, out_f32=self.src, ld_f32=d, out_bf16=self.ln16, ld_bf16=d)
-            ops.run_gemm(ops.make_qkv_args(self.ln16, lw["wqkv"], lw["bqkv"], self.q, self.k, self.v, rows=M, seq=seq, heads=self.heads))
-            ops.attention(self.q, self.k, self.v, self.ctx, self.frames32, N, self.heads, seq)
-            ops.run_gemm(ops.make_gemm_args(self.ctx, lw["wo"], a_rows=M, a_inner=d, a_row_stride=d, bias=lw["bo"], resid=self.src, ld_resid=d, out_f32=hidden, ld_f32=d))
+            ops.layernorm_any(hidden, d, M, d, g1, b1, eps, out_f32=src, ld_f32=d, out_bf16=src16, ld_bf16=d)
+            ops.run_gemm(ops.make_qkv_args(src16, lw["wqkv"], lw["bqkv"], q, k, v, rows=M, seq=seq, heads=self.heads))
+            ops.attention(q, k, v, ctx, self.frames32, N, self.heads, seq, lse)
+            ops.run_gemm(ops.make_gemm_args(ctx, lw["wo"], a_rows=M, a_inner=d, a_row_stride=d, bias=lw["bo"], resid=src, ld_resid=d, out_f32=h_mid, ld_f32=d))
             g2, b2 = lw["ln2"]
-            ops.layernorm_any(hidden, d, M, d, g2, b2, eps, out_bf16=self.ln16, ld_bf16=d)
-            args = ops.make_gemm_args(self.ln16, lw["w1"], a_rows=M, a_inner=d, a_row_stride=d, bias=lw["b1"], out_bf16=self.ffn, ld_bf16=self.ff)
+            ops.layernorm_any(h_mid, d, M, d, g2, b2, eps, out_bf16=ln2, ld_bf16=d)
+            args = ops.make_gemm_args(ln2, lw["w1"], a_rows=M, a_inner=d, a_row_stride=d, bias=lw["b1"], out_bf16=ffn, ld_bf16=self.ff,
+                                      aux_bf16=pre, ld_aux=self.ff)  # fmt: skip
             args.gelu = self.act
             ops.run_gemm(args)
-            ops.run_gemm(ops.make_gemm_args(self.ffn, lw["w2"], a_rows=M, a_inner=self.ff, a_row_stride=self.ff, bias=lw["b2"], resid=hidden, ld_resid=d, out_f32=hidden, ld_f32=d))
+            ops.run_gemm(ops.make_gemm_args(ffn, lw["w2"], a_rows=M, a_inner=self.ff, a_row_stride=self.ff, bias=lw["b2"], resid=h_mid, ld_resid=d, out_f32=h_out, ld_f32=d))
+            if self.training:
+                hidden = h_out
             # acoustic_model.py:690: the final LayerNorm is applied to EVERY layer's output
             column = 0 if index == n_layers - 1 else self.hidden_blocks.get(index)
             if column is not None:
@@ -270,8 +303,112 @@ class TransformerPlan:
                 ops.layernorm_any(hidden, d, M, d, final_gamma, final_beta, model._final_layer_norm.eps, out_f32=state, ld_f32=d)
                 self.captured.append(state)
 
-    def backward(self, *args: Any, **kwargs: Any) -> Any:
-        raise NotImplementedError("the from-scratch transformer encoder has no CUDA backward pass in this build")
+    @torch.no_grad()
+    def backward(self, d_x: Tensor, need_encoder: bool = True, need_projection: bool = True, on_group_ready: Any = None) -> Dict[str, Tensor]:
+        """Backward pass of ``run`` from ``d_x`` = dL/dX (fp32 ``[rows, ldx]``): fp32 gradients keyed by the parameter names of
+        ``TransformerAcousticModel`` (``_transformer.layers.<i>.…``, ``_final_layer_norm.…``, ``_frontend._layer.<j>.…``).
+
+        Layer arithmetic (``acoustic_model.py:313-329``): ``src = LN1(h); m = src + Wo attn(Wqkv src); out = m + W2 act(W1 LN2(m))`` —
+        the attention branch joins the NORMALISED stream, so LN1's backward gets the sum of both paths and no residual
+        by-passes it.  ``on_group_ready(flat, views)`` is called per layer like in ``EncoderPlan.backward``."""
+        if not self.training:
+            raise RuntimeError("this TransformerPlan was built for inference: no activations were kept")
+        model, packed = self.model, self._packed
+        N, M, d, FF, heads, seq = self.n_utt, self.rows, self.d, self.ff, self.heads, self.seq
+        eps = 1e-5
+        dev = d_x.device
+        grads: Dict[str, Tensor] = {}
+        layers = model._transformer.layers
+        n_layers = len(layers)
+        affine = model._final_layer_norm.weight is not None
+        dh, dh16 = self.dh, self.dh16
+        dh.zero_()
+
+        def group(shapes):
+            total = sum(int(torch.Size(shape).numel()) for _, shape in shapes)
+            flat = torch.zeros(total, device=dev, dtype=torch.float32)
+            views, offset = {}, 0
+            for name, shape in shapes:
+                count = int(torch.Size(shape).numel())
+                views[name] = flat[offset : offset + count].view(shape)
+                offset += count
+            return flat, views
+
+        def done(flat, views, prefix):
+            named = {prefix + name: value for name, value in views.items()}
+            grads.update(named)
+            if on_group_ready is not None:
+                on_group_ready(flat, named)
+
+        def wgrad(out, dy, ld_dy, m, x, ld_x, n):
+            ops.run_gemm(ops.make_wgrad_args(dy, x, out, rows=M, m=m, ld_dy=ld_dy, n=n, ld_x=ld_x, ld_out=n))
+
+        final_flat, final_g = group([("weight", (d,)), ("bias", (d,))]) if affine else (None, {})
+        final_gamma, _ = packed["final"]
+        for index in reversed(range(n_layers)):
+            lw, sv = packed["layers"][index], self.saved[index]
+            shapes = [
+                ("self_attn.in_proj_weight", (3 * d, d)), ("self_attn.in_proj_bias", (3 * d,)),
+                ("self_attn.out_proj.weight", (d, d)), ("self_attn.out_proj.bias", (d,)),
+                ("linear1.weight", (FF, d)), ("linear1.bias", (FF,)), ("linear2.weight", (d, FF)), ("linear2.bias", (d,)),
+            ]  # fmt: skip
+            if affine:
+                shapes += [("norm1.weight", (d,)), ("norm1.bias", (d,)), ("norm2.weight", (d,)), ("norm2.bias", (d,))]
+            flat, g = group(shapes)
+            # every used layer output went through the final LayerNorm into a block of X (acoustic_model.py:690)
+            column = 0 if index == n_layers - 1 else self.hidden_blocks.get(index)
+            if column is not None:
+                ops.layernorm_any_backward(sv["h_out"], d, d_x[:, column:], self.ldx, M, d, final_gamma, model._final_layer_norm.eps, dh, d, dh, d,
+                                           final_g.get("weight"), final_g.get("bias"))  # fmt: skip
+            # ---- feed forward: out = m + W2 act(W1 LN2(m) + b1) + b2
+            ops.cast_bf16_2d(dh, d, dh16, d, M, d)
+            args = ops.make_dgrad_args(dh16, lw["w2"], rows=M, ld_dy=d, k=d, n=FF, ld_w=FF, gelu_bwd=sv["pre"], ld_gelu_bwd=FF, out_bf16=self.d_ff, ld_bf16=FF)
+            args.act_bwd = self.act
+            ops.run_gemm(args)
+            wgrad(g["linear2.weight"], dh16, d, d, sv["act"], FF, FF)
+            ops.colsum_f32(dh, M, d, d, out=g["linear2.bias"])
+            wgrad(g["linear1.weight"], self.d_ff, FF, FF, sv["ln2"], d, d)
+            ops.colsum_bf16(self.d_ff, M, FF, FF, out=g["linear1.bias"])
+            ops.run_gemm(ops.make_dgrad_args(self.d_ff, lw["w1"], rows=M, ld_dy=FF, k=FF, n=d, ld_w=d, out_f32=self.d_ln, ld_f32=d))
+            g2, _ = lw["ln2"]
+            ops.layernorm_any_backward(sv["h_mid"], d, self.d_ln, d, M, d, g2, eps, dh, d, dh, d, g.get("norm2.weight"), g.get("norm2.bias"))
+            # ---- attention block: m = src + Wo attn(Wqkv src) + bo, src = LN1(h)
+            ops.cast_bf16_2d(dh, d, dh16, d, M, d)
+            ops.run_gemm(ops.make_dgrad_args(dh16, lw["wo"], rows=M, ld_dy=d, k=d, n=d, ld_w=d, out_bf16=self.d_ctx, ld_bf16=d))
+            wgrad(g["self_attn.out_proj.weight"], dh16, d, d, sv["ctx"], d, d)
+            ops.colsum_f32(dh, M, d, d, out=g["self_attn.out_proj.bias"])
+            ops.attention_backward(sv["q"], sv["k"], sv["v"], sv["ctx"], self.d_ctx, sv["lse"], self.delta, self.dqkv, self.frames32, N, heads, seq)
+            wgrad(g["self_attn.in_proj_weight"], self.dqkv, 3 * d, 3 * d, sv["src16"], d, d)
+            ops.colsum_bf16(self.dqkv, M, 3 * d, 3 * d, out=g["self_attn.in_proj_bias"])
+            # d(src) = dh (the stream the branch joined) + dqkv Wqkv, in one GEMM with the residual epilogue
+            ops.run_gemm(ops.make_dgrad_args(self.dqkv, lw["wqkv"], rows=M, ld_dy=3 * d, k=3 * d, n=d, ld_w=d, resid=dh, ld_resid=d, out_f32=self.d_ln, ld_f32=d))
+            g1, _ = lw["ln1"]
+            ops.layernorm_any_backward(sv["h_in"], d, self.d_ln, d, M, d, g1, eps, None, 0, dh, d, g.get("norm1.weight"), g.get("norm1.bias"))
+            done(flat, g, f"_transformer.layers.{index}.")
+        if affine:
+            done(final_flat, final_g, "_final_layer_norm.")
+        # positional embeddings are an additive constant; dh is now the gradient of the frontend output
+        frontend = model._frontend
+        if isinstance(frontend, LinearFrontend) and any(p.requires_grad for p in frontend.parameters()):
+            neurons, features = frontend.output_dimensions, self.features
+            names = {id(module): index for index, module in enumerate(frontend._layer)}
+            linear_index, norm_index = names[id(frontend.linear)], names[id(frontend.layer_norm)]
+            shapes = [(f"{linear_index}.weight", (neurons, features)), (f"{linear_index}.bias", (neurons,))]
+            norm_affine = frontend.layer_norm.weight is not None
+            if norm_affine:
+                shapes += [(f"{norm_index}.weight", (features,)), (f"{norm_index}.bias", (features,))]
+            flat, g = group(shapes)
+            ops.activation_backward(dh, d, self.fe_out, d, M, d, 3, dh16, d)  # LeakyReLU, decided from its output
+            ops.run_gemm(ops.make_wgrad_args(dh16, self.fe_normed, g[f"{linear_index}.weight"], rows=M, m=neurons, ld_dy=neurons, n=features, ld_x=features, ld_out=features))
+            ops.colsum_f32(dh, M, neurons, neurons, out=g[f"{linear_index}.bias"])
+            if norm_affine:
+                d_normed = torch.empty(M, features, device=dev, dtype=torch.float32)
+                ops.run_gemm(ops.make_dgrad_args(dh16, packed["fe_w"], rows=M, ld_dy=neurons, k=neurons, n=features, ld_w=features, out_f32=d_normed, ld_f32=features))
+                gamma, _ = packed["fe_ln"]
+                ops.layernorm_any_backward(self.x_in, features, d_normed, features, M, features, gamma, frontend.layer_norm.eps, None, 0, None, 0,
+                                           g[f"{norm_index}.weight"], g[f"{norm_index}.bias"])  # fmt: skip
+            done(flat, g, "_frontend._layer.")
+        return grads
 
 
 class TransformerAcousticModel(nn.Module):
@@ -336,13 +473,13 @@ class TransformerAcousticModel(nn.Module):
             return lengths
         return self._sequential_frontend.downsampled_lengths(lengths)
 
-    def plan_for(self, n_utt: int, features: int, length: int, ldx: int, hidden_blocks: Dict[int, int]) -> TransformerPlan:
-        key = (n_utt, features, length, ldx, tuple(sorted(hidden_blocks.items())), str(next(self.parameters()).device))
+    def plan_for(self, n_utt: int, features: int, length: int, ldx: int, hidden_blocks: Dict[int, int], training: bool = False) -> TransformerPlan:
+        key = (n_utt, features, length, ldx, tuple(sorted(hidden_blocks.items())), str(next(self.parameters()).device), training)
         plan = self._plans.get(key)
         if plan is None:
             if len(self._plans) >= 8:
                 self._plans.pop(next(iter(self._plans)))
-            plan = self._plans[key] = TransformerPlan(self, n_utt, features, length, ldx, hidden_blocks)
+            plan = self._plans[key] = TransformerPlan(self, n_utt, features, length, ldx, hidden_blocks, training)
         return plan
 
     def encode(self, batch: Batch, ldx: int, hidden_blocks: Dict[int, int], capture: bool = False, training: bool = False, stochastic: Any = None) -> Tuple[TransformerPlan, Tensor]:
@@ -351,11 +488,9 @@ class TransformerAcousticModel(nn.Module):
             raise RuntimeError("allophant_b200 runs on CUDA only: move the batch to the GPU (`batch.to('cuda')`)")
         if features.dim() != 3:
             raise ValueError(f"expected acoustic features of shape [batch, features, frames], got {tuple(features.shape)}")
-        if training:
-            raise NotImplementedError("the from-scratch transformer encoder has no CUDA backward pass in this build: freeze it or run under torch.no_grad()")
         features = features.float().contiguous()
         lengths = batch.lengths.to(device=features.device, dtype=torch.int64).contiguous()
-        plan = self.plan_for(features.shape[0], features.shape[1], features.shape[2], ldx, hidden_blocks)
+        plan = self.plan_for(features.shape[0], features.shape[1], features.shape[2], ldx, hidden_blocks, training)
         frames = torch.empty(features.shape[0], device=features.device, dtype=torch.int64)
         plan.run(features, lengths, frames, capture)
         return plan, frames

@@ -609,6 +609,26 @@ def layernorm_any(
     )
 
 
+def layernorm_any_backward(
+    x: Tensor, ld_x: int, dy: Tensor, ld_dy: int, rows: int, cols: int, gamma: Optional[Tensor], eps: float,
+    resid: Optional[Tensor], ld_resid: int, dx: Optional[Tensor], ld_dx: int, dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None,
+) -> None:  # fmt: skip
+    """Backward of ``layernorm_any``: ``dx = LN'(dy) (+ resid)``; ``dgamma`` / ``dbeta`` are accumulated into."""
+    _require_cuda(x, dy, gamma, resid, dx, dgamma, dbeta)
+    check(
+        lib.aph_layernorm_any_backward(
+            x.data_ptr(), ld_x, dy.data_ptr(), ld_dy, rows, cols, _ptr(gamma), eps, _ptr(resid), ld_resid, _ptr(dx), ld_dx, _ptr(dgamma), _ptr(dbeta), _stream()
+        ),
+        "aph_layernorm_any_backward",
+    )
+
+
+def activation_backward(d: Tensor, ld_d: int, y: Tensor, ld_y: int, rows: int, cols: int, kind: int, out_bf16: Optional[Tensor] = None, ld_bf16: int = 0) -> None:
+    """``d *= act'`` decided from the activation output ``y`` (kind 2 ReLU, 3 LeakyReLU(0.01)); optional bf16 copy."""
+    _require_cuda(d, y, out_bf16)
+    check(lib.aph_activation_backward(d.data_ptr(), ld_d, y.data_ptr(), ld_y, rows, cols, kind, _ptr(out_bf16), ld_bf16, _stream()), "aph_activation_backward")
+
+
 def add_sinusoidal(x: Tensor, ld: int, n_utt: int, seq: int, cols: int, bases: Tensor) -> None:
     _require_cuda(x, bases)
     check(lib.aph_add_sinusoidal(x.data_ptr(), ld, n_utt, seq, cols, bases.data_ptr(), _stream()), "aph_add_sinusoidal")

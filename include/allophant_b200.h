@@ -29,7 +29,7 @@ extern "C" {
 #define APH_ERR_CUDA (-2)        /* CUDA runtime / driver error                    */
 #define APH_ERR_UNSUPPORTED (-3) /* valid request outside the implemented envelope */
 
-#define APH_ABI_VERSION 3
+#define APH_ABI_VERSION 4
 
 /* ---- library ------------------------------------------------------------ */
 int aph_abi_version(void);
@@ -112,7 +112,8 @@ typedef struct aph_gemm_args {
   int32_t n_taps;         /* DIAG_TAPS: number of taps; output [n_taps][a_rows][256] fp32 */
   void* aux_bf16;         /* store epilogue: value BEFORE gelu (after scale/bias), bf16 [rows][ld_aux] or NULL */
   int64_t ld_aux;
-  const void* gelu_bwd;   /* store epilogue: v *= gelu'(pre[row][col]) with pre bf16 [rows][ld_gelu_bwd] or NULL */
+  const void* gelu_bwd;   /* store epilogue: v *= act'(pre[row][col]) with pre bf16 [rows][ld_gelu_bwd] or NULL; the
+                           * activation is GELU unless act_bwd (last field) says ReLU (2) / LeakyReLU (3) */
   int64_t ld_gelu_bwd;
   void* vmat;             /* APH_EPI_QKV: V row-major [b,h,t,64] (required) */
   /* train-mode dropout of (acc*scale + bias [gelu]) BEFORE the residual is added (HF hidden_dropout of the attention
@@ -121,6 +122,7 @@ typedef struct aph_gemm_args {
   uint32_t drop_threshold;
   uint32_t drop_seed;
   float drop_scale;
+  int32_t act_bwd;        /* activation whose derivative gelu_bwd applies: 0 / 1 GELU (erf), 2 ReLU, 3 LeakyReLU(0.01) */
 } aph_gemm_args;
 
 int aph_gemm_bf16(const aph_gemm_args* args, void* stream);
@@ -432,6 +434,13 @@ float aph_word_error_rate(uint64_t insertions, uint64_t deletions, uint64_t subs
 int aph_layernorm_any(const float* x, int64_t ld_x, int64_t rows, int32_t cols, const float* gamma,
                       const float* beta, float eps, float* out_f32, int64_t ld_f32, void* out_bf16,
                       int64_t ld_bf16, void* stream);
+/* Backward of aph_layernorm_any: dx = LN'(dy) (+ resid); dgamma / dbeta are ACCUMULATED (pre-zero them). */
+int aph_layernorm_any_backward(const float* x, int64_t ld_x, const float* dy, int64_t ld_dy, int64_t rows,
+                               int32_t cols, const float* gamma, float eps, const float* resid, int64_t ld_resid,
+                               float* dx, int64_t ld_dx, float* dgamma, float* dbeta, void* stream);
+/* d <- d * act'(.) decided from the activation OUTPUT y; kind 2 = ReLU, 3 = LeakyReLU(0.01); optional bf16 copy. */
+int aph_activation_backward(float* d, int64_t ld_d, const float* y, int64_t ld_y, int64_t rows, int32_t cols,
+                            int32_t kind, void* out_bf16, int64_t ld_bf16, void* stream);
 /* SinusoidalPositionEmbeddings.forward (acoustic_model.py:58-69): x[n][t][c] += sin|cos(t * bases[c]). */
 int aph_add_sinusoidal(float* x, int64_t ld, int32_t n_utt, int32_t seq, int32_t cols, const float* bases,
                        void* stream);

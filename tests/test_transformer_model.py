@@ -57,6 +57,19 @@ def test_same_seed_gives_the_reference_initialisation():
     assert torch.equal(layers[0].linear1.weight, layers[1].linear1.weight)  # nn.TransformerEncoder deep-copies ONE layer
 
 
+def test_cpu_restatement_reproduces_the_reference(golden):
+    """oracle/restatement_transformer.py (the differentiable CPU restatement the GPU gradient tests compare with) against
+    the hidden states of the unmodified reference: fp32 round-off only."""
+    from oracle import restatement_transformer
+
+    with torch.no_grad():
+        outputs, frames = restatement_transformer.forward(golden["state_dict"], golden["case"]["acoustic"], golden["features"], golden["lengths"])
+    assert torch.equal(frames, golden["frames"]) and len(outputs) == len(golden["hidden_states"])
+    for ours, reference in zip(outputs, golden["hidden_states"]):
+        for utterance, length in enumerate(golden["frames"].tolist()):
+            assert float((ours[utterance, :length] - reference[:length, utterance]).abs().max()) < 2e-5
+
+
 def _range_err(value: torch.Tensor, reference: torch.Tensor) -> float:
     return float((value.double().cpu() - reference.double()).abs().max() / reference.double().abs().max())
 
@@ -99,14 +112,132 @@ def test_log_probabilities_match_reference(golden):
             assert error < 3e-2, (name, utterance, error)
 
 
+def _norm_err(value: torch.Tensor, reference: torch.Tensor) -> float:
+    return float((value.double().cpu() - reference.double()).norm() / reference.double().norm().clamp_min(1e-20))
+
+
+def _encoder_gradient_check(state_dict, options, feature_size, features, lengths, name, tolerance=5e-2):
+    """Backward pass of the encoder alone: L = sum(final hidden state * G) on the valid frames; every parameter gradient of
+    ``TransformerPlan.backward`` against autograd through the CPU restatement (norm-relative per tensor; bf16 operands)."""
+    from allophant_b200.config import TransformerAcousticModelConfig
+    from allophant_b200.dataset_processing import Batch
+    from allophant_b200.network.acoustic_model import TransformerAcousticModel
+    from oracle import restatement_transformer
+
+    mapping = dict(type="pre-ln-transformer", transformer=options["transformer"], frontend=options["frontend"],
+                   sequential_frontend=None, elementwise_affine=options["elementwise_affine"])  # fmt: skip
+    model = TransformerAcousticModel.from_config(TransformerAcousticModelConfig.load(mapping), feature_size)
+    own = {key[len("_acoustic_model."):]: value for key, value in state_dict.items() if key.startswith("_acoustic_model.")}
+    model.load_state_dict(own, strict=True)
+    model = model.cuda()
+    width = model.d_model
+    batch = Batch(features.cuda(), lengths.cuda(), torch.zeros(len(lengths)).cuda())
+    plan, frames = model.encode(batch, width, {}, training=True)
+    generator = torch.Generator().manual_seed(1)
+    weights = torch.randn(len(lengths), plan.seq, width, generator=generator)
+    weights = weights * (torch.arange(plan.seq)[None, :] < frames.cpu()[:, None])[..., None]
+    gradients = plan.backward(weights.view(-1, width).cuda().contiguous())
+
+    leaves = {key: value.clone().requires_grad_(True) for key, value in state_dict.items() if key.startswith("_acoustic_model.") and value.is_floating_point()}
+    outputs, _ = restatement_transformer.forward(leaves, options, features, lengths)
+    (outputs[-1] * weights).sum().backward()
+    worst = {}
+    for key, leaf in leaves.items():
+        short = key[len("_acoustic_model."):]
+        if leaf.grad is None or float(leaf.grad.norm()) < 1e-7:
+            continue
+        assert short in gradients, f"no gradient for {short}"
+        worst[short] = _norm_err(gradients[short], leaf.grad)
+    assert len(worst) >= 8 * len(model._transformer.layers)
+    ranked = sorted(worst.items(), key=lambda item: -item[1])
+    print(f"{name}: worst encoder gradient deviations " + ", ".join(f"{k}={v:.2e}" for k, v in ranked[:4]))
+    assert ranked[0][1] < tolerance, ranked[:8]
+
+
 @pytest.mark.gpu
-def test_classifiers_train_on_a_frozen_transformer_and_unfrozen_raises(golden):
+def test_encoder_backward_matches_the_restatement_direct_frontend():
+    golden = helpers.load_golden("transformer_direct_relu")  # ReLU, affine LayerNorms, no positional embeddings, ragged lengths
+    # ReLU has a discontinuous derivative: pre-activations within bf16 noise of 0 (about 1 % of the units of this small model)
+    # get the other branch than in the fp32 restatement, which shows up as ~6e-2 on the feed-forward gradients (measured);
+    # the smooth GELU case below holds 5e-2
+    _encoder_gradient_check(golden["state_dict"], golden["case"]["acoustic"], golden["case"]["feature_size"], golden["features"], golden["lengths"],
+                            "direct_relu", tolerance=1e-1)  # fmt: skip
+
+
+@pytest.mark.gpu
+def test_encoder_backward_matches_the_restatement_linear_frontend():
+    """Linear frontend (LayerNorm -> Linear -> LeakyReLU), GELU layers, sinusoidal positions, LayerNorms without parameters."""
+    from allophant_b200.config import TransformerAcousticModelConfig
+    from allophant_b200.network.acoustic_model import TransformerAcousticModel
+
+    options = dict(
+        transformer=dict(feedforward_neurons=320, heads=4, activation="gelu", num_layers=2, dropout_rate=0.0, positional_embeddings=True),
+        frontend=dict(architecture="linear", neurons=256, input_dropout=0.0), sequential_frontend=None, elementwise_affine=False,
+    )  # fmt: skip
+    torch.manual_seed(21)
+    model = TransformerAcousticModel.from_config(
+        TransformerAcousticModelConfig.load(dict(type="pre-ln-transformer", transformer=options["transformer"], frontend=options["frontend"])), 40
+    )
+    with torch.no_grad():
+        for index, layer in enumerate(model._transformer.layers):  # nn.TransformerEncoder deep-copies one layer: make them differ
+            for parameter in layer.parameters():
+                parameter.add_(0.03 * (index + 1) * torch.randn_like(parameter))
+    state = {"_acoustic_model." + key: value.detach().clone() for key, value in model.state_dict().items()}
+    lengths = torch.tensor([57, 90, 13])
+    features = torch.randn(3, 40, 90) * (torch.arange(90)[None, :] < lengths[:, None])[:, None, :]
+    _encoder_gradient_check(state, options, 40, features, lengths, "linear_gelu")
+
+
+@pytest.mark.gpu
+def test_transformer_model_trains_end_to_end_and_glu_stack_raises():
+    """`model(batch)` -> multi-head CTC -> backward through classifiers AND encoder: every trainable tensor gets a finite
+    gradient and a few Adam steps reduce the loss; the GLU convolution stack has no backward pass yet and says so."""
+    from allophant_b200.dataset_processing import Batch
+    from allophant_b200.loss_functions import multi_head_ctc_loss
+
+    golden = helpers.load_golden("transformer_direct_relu")
+    model, _ = helpers.transformer_model_for_golden(golden)
+    lengths = golden["lengths"]
+    batch = Batch(golden["features"].cuda(), lengths.cuda(), torch.zeros(len(lengths), dtype=torch.long).cuda())
+    generator = torch.Generator().manual_seed(0)
+    names = list(model.classes)
+    label_lengths = {name: (golden["frames"].double() * 0.25).floor().long().clamp_min(1) for name in names}
+    labels = {}
+    for name in names:
+        classes = 13 if name == "phoneme" else 4
+        labels[name] = torch.stack([torch.randint(1, classes, (int(label_lengths[name].max()),), generator=generator) for _ in lengths])
+    optimizer = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=2e-4)
+    losses = []
+    for _ in range(6):
+        optimizer.zero_grad(set_to_none=True)
+        predictions = model(batch)
+        order = list(predictions.outputs)
+        per_head = multi_head_ctc_loss(
+            [predictions.outputs[name] for name in order], [labels[name].cuda() for name in order], predictions.lengths,
+            [label_lengths[name].cuda() for name in order],
+        )  # fmt: skip
+        loss = per_head.sum() / sum(int(label_lengths[name].sum()) for name in order)
+        loss.backward()
+        if not losses:
+            missing = [name for name, p in model.named_parameters() if p.requires_grad and (p.grad is None or not torch.isfinite(p.grad).all())]
+            assert not missing, missing[:5]
+            assert any(float(p.grad.abs().max()) > 0 for name, p in model.named_parameters() if name.startswith("_acoustic_model._transformer"))
+        optimizer.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0], losses
+    glu = helpers.load_golden("transformer_linear_glu")
+    model, _ = helpers.transformer_model_for_golden(glu)
+    batch = Batch(glu["features"].cuda(), glu["lengths"].cuda(), torch.zeros(len(glu["lengths"]), dtype=torch.long).cuda())
+    with pytest.raises(NotImplementedError, match="sequential frontend"):
+        model(batch)
+
+
+@pytest.mark.gpu
+def test_classifiers_train_on_a_frozen_transformer(golden):
     from allophant_b200.dataset_processing import Batch
 
     model, _ = helpers.transformer_model_for_golden(golden)
     batch = Batch(golden["features"].cuda(), golden["lengths"].cuda(), torch.zeros(len(golden["lengths"]), dtype=torch.long).cuda())
-    with pytest.raises(NotImplementedError, match="no backward pass"):
-        model(batch)
     for parameter in model._acoustic_model.parameters():
         parameter.requires_grad = False
     outputs = model(batch)
