@@ -152,6 +152,8 @@ _SIGNATURES = {
     "aph_multi_tensor_adam": [_P, _P, _P, _I32, _F, _F, _F, _F, _F, _I64, _P, _F, _P],
     "aph_layernorm_any": [_P, _I64, _I64, _I32, _P, _P, c_float, _P, _I64, _P, _I64, _P],
     "aph_layernorm_any_backward": [_P, _I64, _P, _I64, _I64, _I32, _P, c_float, _P, _I64, _P, _I64, _P, _P, _P],
+    "aph_glu_backward_bf16": [_P, _I64, _P, _I64, _I64, _I32, _P, _I64, _P],
+    "aph_conv_input_backward": [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _I64, _P],
     "aph_activation_backward": [_P, _I64, _P, _I64, _I64, _I32, _I32, _P, _I64, _P],
     "aph_add_sinusoidal": [_P, _I64, _I32, _I32, _I32, _P, _P],
     "aph_transpose_nfl": [_P, _I32, _I32, _I32, _P, _I64, _P],

@@ -169,6 +169,71 @@ __global__ void __launch_bounds__(256) layernorm_any_backward_kernel(const float
   }
 }
 
+// Backward of functional.glu over channels: y = [a | g], out = a * sigmoid(g):
+//   d_a = d_out * sigmoid(g),   d_g = d_out * a * sigmoid(g) * (1 - sigmoid(g));   written as bf16 (the operand of the conv's
+//   data-gradient and weight-gradient GEMMs)
+__global__ void __launch_bounds__(256) glu_backward_kernel(const float* __restrict__ y, long long ld_y, const float* __restrict__ d_out,
+                                                           long long ld_d, long long rows, int out_channels,
+                                                           __nv_bfloat16* __restrict__ dy, long long ld_dy) {
+  const long long total = rows * out_channels;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const long long row = i / out_channels;
+    const int c = static_cast<int>(i - row * out_channels);
+    const float a = y[row * ld_y + c], g = y[row * ld_y + out_channels + c];
+    const float sig = 1.0f / (1.0f + __expf(-g));
+    const float d = d_out[row * ld_d + c];
+    dy[row * ld_dy + c] = __float2bfloat16(d * sig);
+    dy[row * ld_dy + out_channels + c] = __float2bfloat16(d * a * sig * (1.0f - sig));
+  }
+}
+
+// Backward of (LengthWrapper mask -> VariableLengthReflectPad -> Conv1d) w.r.t. the stage input, from the per-window
+// gradients d_cols[n][t][j*C + c] = (dY W)[n][t][j][c] of the convolution (one data-gradient GEMM):
+//   d_pad[n][p][c] = sum_{j < kernel, (p - j) % stride == 0, t = (p - j) / stride < out_len} d_cols[n][t][j*C + c]      (col2im)
+//   d_x[n][q][c]   = d_pad[n][q + left]                                             (the copied frame)
+//                  + d_pad[n][len + left + (len - 2 - q)]   if 0 <= len - 2 - q < right   (right reflection reads x[len-2-j])
+//                  + sum_n' d_pad[n'][left - q]             if n == 0 and 1 <= q <= left   (every utterance's left reflection
+//                                                                                            reads utterance 0, see the forward)
+// for q < len, and 0 for the masked frames q >= len.
+__device__ __forceinline__ float conv_pad_gradient(const float* __restrict__ d_cols, long long n, int p, int c, int out_len, int kernel,
+                                                   int stride, int channels) {
+  float sum = 0.f;
+  const long long width = static_cast<long long>(kernel) * channels;
+  for (int j = 0; j < kernel; ++j) {
+    const int r = p - j;
+    if (r < 0 || r % stride != 0) continue;
+    const int t = r / stride;
+    if (t >= out_len) continue;
+    sum += d_cols[(n * out_len + t) * width + static_cast<long long>(j) * channels + c];
+  }
+  return sum;
+}
+
+__global__ void __launch_bounds__(256) conv_input_backward_kernel(const float* __restrict__ d_cols, const int* __restrict__ lengths, int n_utt,
+                                                                  int length, int channels, int out_len, int kernel, int stride, int left,
+                                                                  int right, int reflect, float* __restrict__ d_x, long long ld_dx) {
+  const int n = blockIdx.y;
+  const int len = min(lengths[n], length);
+  const int len0 = min(lengths[0], length);
+  const long long total = static_cast<long long>(length) * channels;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const int q = static_cast<int>(i / channels);
+    const int c = static_cast<int>(i - static_cast<long long>(q) * channels);
+    float v = 0.f;
+    if (q < len) {
+      v = conv_pad_gradient(d_cols, n, q + left, c, out_len, kernel, stride, channels);
+      if (reflect) {
+        const int j = len - 2 - q;
+        if (j >= 0 && j < right) v += conv_pad_gradient(d_cols, n, len + left + j, c, out_len, kernel, stride, channels);
+        if (n == 0 && q >= 1 && q <= left && q < len0) {
+          for (int other = 0; other < n_utt; ++other) v += conv_pad_gradient(d_cols, other, left - q, c, out_len, kernel, stride, channels);
+        }
+      }
+    }
+    d_x[(static_cast<long long>(n) * length + q) * ld_dx + c] = v;
+  }
+}
+
 // d_pre = d_out * act'(.) from the activation's OUTPUT y (kind 2 ReLU: y > 0; kind 3 LeakyReLU(0.01): y > 0 ? 1 : 0.01),
 // fp32 in place + optional bf16 copy (the operand of the weight-gradient GEMM)
 __global__ void __launch_bounds__(256) activation_backward_kernel(float* d, long long ld_d, const float* __restrict__ y, long long ld_y,
@@ -272,6 +337,30 @@ extern "C" int aph_activation_backward(float* d, int64_t ld_d, const float* y, i
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   activation_backward_kernel<<<blocks_for(rows * cols), 256, 0, stream>>>(d, ld_d, y, ld_y, rows, cols, kind, static_cast<__nv_bfloat16*>(out_bf16),
                                                                           ld_bf16);
+  APH_POST_LAUNCH(1);
+  return APH_OK;
+}
+
+extern "C" int aph_glu_backward_bf16(const float* y, int64_t ld_y, const float* d_out, int64_t ld_d, int64_t rows, int32_t out_channels,
+                                     void* dy_bf16, int64_t ld_dy, void* stream_) {
+  APH_REQUIRE(y && d_out && dy_bf16 && rows >= 0 && out_channels > 0 && ld_y >= 2 * out_channels && ld_dy >= 2 * out_channels, "glu_backward: bad arguments");
+  if (rows == 0) return APH_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  glu_backward_kernel<<<blocks_for(rows * out_channels), 256, 0, stream>>>(y, ld_y, d_out, ld_d, rows, out_channels, static_cast<__nv_bfloat16*>(dy_bf16),
+                                                                            ld_dy);
+  APH_POST_LAUNCH(1);
+  return APH_OK;
+}
+
+extern "C" int aph_conv_input_backward(const float* d_cols, const int32_t* lengths, int32_t n_utt, int32_t length, int32_t channels,
+                                       int32_t out_len, int32_t kernel, int32_t stride, int32_t left, int32_t right, int32_t reflect,
+                                       float* d_x, int64_t ld_dx, void* stream_) {
+  APH_REQUIRE(d_cols && lengths && d_x && n_utt >= 0 && length > 0 && channels > 0 && out_len > 0 && kernel > 0 && stride > 0, "conv_input_backward: bad arguments");
+  APH_REQUIRE(n_utt <= 65535 && ld_dx >= channels, "conv_input_backward: at most 65535 utterances");
+  if (n_utt == 0) return APH_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  dim3 grid(blocks_for(static_cast<long long>(length) * channels), static_cast<unsigned>(n_utt));
+  conv_input_backward_kernel<<<grid, 256, 0, stream>>>(d_cols, lengths, n_utt, length, channels, out_len, kernel, stride, left, right, reflect, d_x, ld_dx);
   APH_POST_LAUNCH(1);
   return APH_OK;
 }

@@ -7,9 +7,9 @@ attention and row kernels the wav2vec2 path uses (``aph_gemm.cu``, ``aph_attenti
 
 Training: ``TransformerPlan(training=True)`` keeps the activations and ``TransformerPlan.backward`` runs the backward
 pass of the transformer layers, the final LayerNorm, the positional embeddings and the direct / linear front end on the same
-GEMM (data-gradient / weight-gradient forms), flash-attention-backward and row kernels as the wav2vec2 path.  The backward
-pass of the GLU convolution stack (``sequential_frontend``) is not built: models with one train their classifiers on a
-frozen encoder only.  Dropout layers are identities (``eval()`` arithmetic) in both directions.
+GEMM (data-gradient / weight-gradient forms), flash-attention-backward and row kernels as the wav2vec2 path, and of the GLU
+convolution stack (GLU', weight gradient with overlapping-row operands, data gradient + col2im with the reflections folded
+back).  Dropout layers are identities (``eval()`` arithmetic) in both directions.
 """
 from __future__ import annotations
 
@@ -115,7 +115,7 @@ class TransformerPlan:
         self.stages: List[Dict[str, Any]] = []
         sequential = model._sequential_frontend
         if sequential is not None:
-            for wrapper in sequential._layers.layers:
+            for position, wrapper in enumerate(sequential._layers.layers):
                 module = wrapper.module
                 if isinstance(module, Glu1d):
                     left, right = module.padding
@@ -125,11 +125,11 @@ class TransformerPlan:
                     out_len = (seq + left + right - kernel) // stride + 1
                     if (stride * channels) % 8 != 0 or (kernel * channels) % 8 != 0:
                         raise NotImplementedError("glu1d: stride * channels and kernel * channels have to be multiples of 8 (TMA alignment)")
-                    self.stages.append(dict(kind="glu", module=module, left=left, right=right, kernel=kernel, stride=stride, in_len=seq,
+                    self.stages.append(dict(kind="glu", position=position, module=module, left=left, right=right, kernel=kernel, stride=stride, in_len=seq,
                                             in_channels=channels, out_len=out_len, out_channels=out_channels))  # fmt: skip
                     seq, channels = out_len, out_channels
                 elif isinstance(module, nn.Sequential):  # Transpose, LayerNorm, Transpose
-                    self.stages.append(dict(kind="layer_norm", norm=module[1], channels=channels))
+                    self.stages.append(dict(kind="layer_norm", position=position, norm=module[1], channels=channels))
                 elif isinstance(module, nn.Dropout):
                     continue  # identity in eval() arithmetic
                 else:
@@ -163,11 +163,6 @@ class TransformerPlan:
         self.ffn = z(M, self.ff)
         self.x = z(M, ldx)
         if training:
-            if self.stages:
-                raise NotImplementedError(
-                    "the backward pass of the sequential frontend (GLU convolution stack) is not part of this build: freeze the "
-                    "acoustic model (classifier training works) or use a configuration without `sequential_frontend`"
-                )
             n_layers = len(model._transformer.layers)
             # everything the backward pass reads, per layer (only the attention probabilities are recomputed)
             self.saved = [
@@ -177,7 +172,7 @@ class TransformerPlan:
                 for _ in range(n_layers)
             ]  # fmt: skip
             self.fe_normed = z(self.in_rows, features) if isinstance(model._frontend, LinearFrontend) else None
-            self.fe_out = z(M, d, dtype=f32) if isinstance(model._frontend, LinearFrontend) else None
+            self.fe_out = z(self.in_rows, model._frontend.output_dimensions, dtype=f32) if isinstance(model._frontend, LinearFrontend) else None
             self.dh, self.dh16 = z(M, d, dtype=f32), z(M, d)
             self.d_ff, self.d_ln, self.d_ctx = z(M, self.ff), z(M, d, dtype=f32), z(M, d)
             self.dqkv, self.delta = z(M, 3 * d), z(n_utt * heads * seq, dtype=f32)
@@ -257,11 +252,19 @@ class TransformerPlan:
                 )  # fmt: skip
                 out = torch.empty(N * out_len, out_channels, device=self.device, dtype=torch.float32)
                 ops.glu_rows(gated, 2 * out_channels, N * out_len, out_channels, out, out_channels)
+                if self.training:  # the backward pass reads the padded input, the pre-gate output and the input lengths
+                    stage["kept"] = dict(padded=padded, gated=gated, lengths32=lengths32, in_len=seq, in_channels=channels)
                 lengths32 = torch.div(lengths32 + (left + right - kernel), stride, rounding_mode="floor") + 1
                 current, channels, seq = out, out_channels, out_len
             else:
                 gamma, beta = stage["affine"]
-                ops.layernorm_any(current, channels, N * seq, channels, gamma, beta, stage["norm"].eps, out_f32=current, ld_f32=channels)
+                if self.training:
+                    stage["kept"] = dict(x=current, rows=N * seq)
+                    normed = torch.empty_like(current)
+                    ops.layernorm_any(current, channels, N * seq, channels, gamma, beta, stage["norm"].eps, out_f32=normed, ld_f32=channels)
+                    current = normed
+                else:
+                    ops.layernorm_any(current, channels, N * seq, channels, gamma, beta, stage["norm"].eps, out_f32=current, ld_f32=channels)
         assert seq == self.seq and channels == d
         self.frames32.copy_(lengths32)
         frames64.copy_(lengths32)
@@ -387,10 +390,57 @@ class TransformerPlan:
             done(flat, g, f"_transformer.layers.{index}.")
         if affine:
             done(final_flat, final_g, "_final_layer_norm.")
-        # positional embeddings are an additive constant; dh is now the gradient of the frontend output
+        # positional embeddings are an additive constant; dh is now the gradient of the last front-end stage's output
+        d_cur, cur_rows, cur_channels = dh, M, d
+        for stage in reversed(self.stages):
+            kept, position = stage["kept"], stage["position"]
+            if stage["kind"] == "layer_norm":
+                norm = stage["norm"]
+                gamma, _ = stage["affine"]
+                flat, g = group([("weight", (cur_channels,)), ("bias", (cur_channels,))]) if gamma is not None else (None, {})
+                d_in = torch.empty(cur_rows, cur_channels, device=dev, dtype=torch.float32)
+                ops.layernorm_any_backward(kept["x"], cur_channels, d_cur, cur_channels, cur_rows, cur_channels, gamma, norm.eps, None, 0, d_in, cur_channels,
+                                           g.get("weight"), g.get("bias"))  # fmt: skip
+                if gamma is not None:
+                    done(flat, g, f"_sequential_frontend._layers.layers.{position}.module.1.")
+                d_cur = d_in
+                continue
+            module = stage["module"]
+            left, right, kernel, stride = stage["left"], stage["right"], stage["kernel"], stage["stride"]
+            in_len, in_channels, out_len, out_channels = kept["in_len"], kept["in_channels"], stage["out_len"], stage["out_channels"]
+            rows_out = N * out_len
+            width = kernel * in_channels
+            d_gated = torch.empty(rows_out, 2 * out_channels, device=dev, dtype=torch.bfloat16)
+            ops.glu_backward_bf16(kept["gated"], 2 * out_channels, d_cur, cur_channels, rows_out, out_channels, d_gated, 2 * out_channels)
+            flat, g = group([("weight", (2 * out_channels, kernel, in_channels)), ("bias", (2 * out_channels,))])
+            ops.colsum_bf16(d_gated, rows_out, 2 * out_channels, 2 * out_channels, out=g["bias"])
+            # dW[o][j][c] = sum_(n,t) dY[n][t][o] * Xpad[n][t*stride + j][c]: both operands frame-major, one K segment per utterance,
+            # the windows of Xpad are overlapping rows of stride `stride * C` (the same tensor map trick as the forward conv)
+            args = ops.make_wgrad_args(d_gated, kept["padded"], g["weight"].view(2 * out_channels, width), rows=out_len, m=2 * out_channels,
+                                       ld_dy=2 * out_channels, n=width, ld_x=stride * in_channels, ld_out=width)  # fmt: skip
+            args.k_batch, args.a_batch_stride, args.b_seg_stride = N, out_len * 2 * out_channels, (in_len + left + right) * in_channels
+            ops.run_gemm(args)
+            weight_gradient = g.pop("weight").permute(0, 2, 1).contiguous()  # [2O, k, C] -> Conv1d's [2O, C, k]
+            named = {f"_sequential_frontend._layers.layers.{position}.module._weights.weight": weight_gradient,
+                     f"_sequential_frontend._layers.layers.{position}.module._weights.bias": g["bias"]}  # fmt: skip
+            grads.update(named)
+            if on_group_ready is not None:
+                on_group_ready(weight_gradient.view(-1), {k: v for k, v in named.items() if k.endswith("weight")})
+                on_group_ready(g["bias"], {k: v for k, v in named.items() if k.endswith("bias")})
+            first_stage = stage is self.stages[0]
+            frontend_trains = isinstance(model._frontend, LinearFrontend) and any(p.requires_grad for p in model._frontend.parameters())
+            if first_stage and not frontend_trains:
+                d_cur = None  # nothing upstream needs a gradient
+                break
+            d_cols = torch.empty(rows_out, width, device=dev, dtype=torch.float32)
+            ops.run_gemm(ops.make_dgrad_args(d_gated, stage["w"], rows=rows_out, ld_dy=2 * out_channels, k=2 * out_channels, n=width, ld_w=width, out_f32=d_cols, ld_f32=width))
+            d_in = torch.empty(N * in_len, in_channels, device=dev, dtype=torch.float32)
+            ops.conv_input_backward(d_cols, kept["lengths32"], N, in_len, in_channels, out_len, kernel, stride, left, right, module._reflect_padding is not None, d_in, in_channels)
+            d_cur, cur_rows, cur_channels = d_in, N * in_len, in_channels
         frontend = model._frontend
-        if isinstance(frontend, LinearFrontend) and any(p.requires_grad for p in frontend.parameters()):
+        if d_cur is not None and isinstance(frontend, LinearFrontend) and any(p.requires_grad for p in frontend.parameters()):
             neurons, features = frontend.output_dimensions, self.features
+            rows_in = self.in_rows
             names = {id(module): index for index, module in enumerate(frontend._layer)}
             linear_index, norm_index = names[id(frontend.linear)], names[id(frontend.layer_norm)]
             shapes = [(f"{linear_index}.weight", (neurons, features)), (f"{linear_index}.bias", (neurons,))]
@@ -398,14 +448,15 @@ class TransformerPlan:
             if norm_affine:
                 shapes += [(f"{norm_index}.weight", (features,)), (f"{norm_index}.bias", (features,))]
             flat, g = group(shapes)
-            ops.activation_backward(dh, d, self.fe_out, d, M, d, 3, dh16, d)  # LeakyReLU, decided from its output
-            ops.run_gemm(ops.make_wgrad_args(dh16, self.fe_normed, g[f"{linear_index}.weight"], rows=M, m=neurons, ld_dy=neurons, n=features, ld_x=features, ld_out=features))
-            ops.colsum_f32(dh, M, neurons, neurons, out=g[f"{linear_index}.bias"])
+            d16 = torch.empty(rows_in, neurons, device=dev, dtype=torch.bfloat16)
+            ops.activation_backward(d_cur, neurons, self.fe_out, neurons, rows_in, neurons, 3, d16, neurons)  # LeakyReLU, decided from its output
+            ops.run_gemm(ops.make_wgrad_args(d16, self.fe_normed, g[f"{linear_index}.weight"], rows=rows_in, m=neurons, ld_dy=neurons, n=features, ld_x=features, ld_out=features))
+            ops.colsum_f32(d_cur, rows_in, neurons, neurons, out=g[f"{linear_index}.bias"])
             if norm_affine:
-                d_normed = torch.empty(M, features, device=dev, dtype=torch.float32)
-                ops.run_gemm(ops.make_dgrad_args(dh16, packed["fe_w"], rows=M, ld_dy=neurons, k=neurons, n=features, ld_w=features, out_f32=d_normed, ld_f32=features))
+                d_normed = torch.empty(rows_in, features, device=dev, dtype=torch.float32)
+                ops.run_gemm(ops.make_dgrad_args(d16, packed["fe_w"], rows=rows_in, ld_dy=neurons, k=neurons, n=features, ld_w=features, out_f32=d_normed, ld_f32=features))
                 gamma, _ = packed["fe_ln"]
-                ops.layernorm_any_backward(self.x_in, features, d_normed, features, M, features, gamma, frontend.layer_norm.eps, None, 0, None, 0,
+                ops.layernorm_any_backward(self.x_in, features, d_normed, features, rows_in, features, gamma, frontend.layer_norm.eps, None, 0, None, 0,
                                            g[f"{norm_index}.weight"], g[f"{norm_index}.bias"])  # fmt: skip
             done(flat, g, "_frontend._layer.")
         return grads

@@ -623,6 +623,22 @@ def layernorm_any_backward(
     )
 
 
+def glu_backward_bf16(y: Tensor, ld_y: int, d_out: Tensor, ld_d: int, rows: int, out_channels: int, dy: Tensor, ld_dy: int) -> None:
+    _require_cuda(y, d_out, dy)
+    check(lib.aph_glu_backward_bf16(y.data_ptr(), ld_y, d_out.data_ptr(), ld_d, rows, out_channels, dy.data_ptr(), ld_dy, _stream()), "aph_glu_backward_bf16")
+
+
+def conv_input_backward(
+    d_cols: Tensor, lengths32: Tensor, n_utt: int, length: int, channels: int, out_len: int, kernel: int, stride: int, left: int, right: int,
+    reflect: bool, d_x: Tensor, ld_dx: int,
+) -> None:  # fmt: skip
+    _require_cuda(d_cols, lengths32, d_x)
+    check(
+        lib.aph_conv_input_backward(d_cols.data_ptr(), lengths32.data_ptr(), n_utt, length, channels, out_len, kernel, stride, left, right, int(reflect), d_x.data_ptr(), ld_dx, _stream()),
+        "aph_conv_input_backward",
+    )
+
+
 def activation_backward(d: Tensor, ld_d: int, y: Tensor, ld_y: int, rows: int, cols: int, kind: int, out_bf16: Optional[Tensor] = None, ld_bf16: int = 0) -> None:
     """``d *= act'`` decided from the activation output ``y`` (kind 2 ReLU, 3 LeakyReLU(0.01)); optional bf16 copy."""
     _require_cuda(d, y, out_bf16)

@@ -438,6 +438,15 @@ int aph_layernorm_any(const float* x, int64_t ld_x, int64_t rows, int32_t cols, 
 int aph_layernorm_any_backward(const float* x, int64_t ld_x, const float* dy, int64_t ld_dy, int64_t rows,
                                int32_t cols, const float* gamma, float eps, const float* resid, int64_t ld_resid,
                                float* dx, int64_t ld_dx, float* dgamma, float* dbeta, void* stream);
+/* Backward of aph_glu_rows: dy bf16 [rows][2*out_channels] = (d_out * sigmoid(g) | d_out * a * sigmoid'(g)). */
+int aph_glu_backward_bf16(const float* y, int64_t ld_y, const float* d_out, int64_t ld_d, int64_t rows,
+                          int32_t out_channels, void* dy_bf16, int64_t ld_dy, void* stream);
+/* Backward of (mask -> aph_reflect_pad_bf16 -> strided Conv1d) w.r.t. the stage input from the per-window gradients
+ * d_cols fp32 [n_utt*out_len][kernel*channels] (= dY W): col2im overlap-add, the reflections folded back (the left one into
+ * utterance 0, like the forward reads it), masked frames zero.  d_x fp32 [n_utt][length][ld_dx]. */
+int aph_conv_input_backward(const float* d_cols, const int32_t* lengths, int32_t n_utt, int32_t length,
+                            int32_t channels, int32_t out_len, int32_t kernel, int32_t stride, int32_t left,
+                            int32_t right, int32_t reflect, float* d_x, int64_t ld_dx, void* stream);
 /* d <- d * act'(.) decided from the activation OUTPUT y; kind 2 = ReLU, 3 = LeakyReLU(0.01); optional bf16 copy. */
 int aph_activation_backward(float* d, int64_t ld_d, const float* y, int64_t ld_y, int64_t rows, int32_t cols,
                             int32_t kind, void* out_bf16, int64_t ld_bf16, void* stream);

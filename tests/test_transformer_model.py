@@ -124,8 +124,9 @@ def _encoder_gradient_check(state_dict, options, feature_size, features, lengths
     from allophant_b200.network.acoustic_model import TransformerAcousticModel
     from oracle import restatement_transformer
 
+    sequential = options.get("sequential_frontend")
     mapping = dict(type="pre-ln-transformer", transformer=options["transformer"], frontend=options["frontend"],
-                   sequential_frontend=None, elementwise_affine=options["elementwise_affine"])  # fmt: skip
+                   sequential_frontend=None if sequential is None else {"layers": sequential}, elementwise_affine=options["elementwise_affine"])  # fmt: skip
     model = TransformerAcousticModel.from_config(TransformerAcousticModelConfig.load(mapping), feature_size)
     own = {key[len("_acoustic_model."):]: value for key, value in state_dict.items() if key.startswith("_acoustic_model.")}
     model.load_state_dict(own, strict=True)
@@ -189,13 +190,26 @@ def test_encoder_backward_matches_the_restatement_linear_frontend():
 
 
 @pytest.mark.gpu
-def test_transformer_model_trains_end_to_end_and_glu_stack_raises():
-    """`model(batch)` -> multi-head CTC -> backward through classifiers AND encoder: every trainable tensor gets a finite
-    gradient and a few Adam steps reduce the loss; the GLU convolution stack has no backward pass yet and says so."""
+def test_encoder_backward_matches_the_restatement_glu_stack():
+    """The reference-made case with the full front end: linear frontend -> GLU conv (k3, s2, reflect pad) -> affine LayerNorm ->
+    dropout -> GLU conv (k5, s1) -> GELU transformer, ragged lengths (the left reflection of every utterance reads utterance 0)."""
+    golden = helpers.load_golden("transformer_linear_glu")
+    _encoder_gradient_check(golden["state_dict"], golden["case"]["acoustic"], golden["case"]["feature_size"], golden["features"], golden["lengths"],
+                            "linear_glu", tolerance=6e-2)  # fmt: skip
+
+
+@pytest.mark.gpu
+def test_transformer_model_trains_end_to_end():
+    """`model(batch)` -> multi-head CTC -> backward through classifiers AND encoder (both golden architectures): every
+    trainable tensor gets a finite gradient and a few Adam steps reduce the loss."""
     from allophant_b200.dataset_processing import Batch
     from allophant_b200.loss_functions import multi_head_ctc_loss
 
-    golden = helpers.load_golden("transformer_direct_relu")
+    for case in ("transformer_direct_relu", "transformer_linear_glu"):
+        _train_a_few_steps(helpers.load_golden(case), Batch, multi_head_ctc_loss)
+
+
+def _train_a_few_steps(golden, Batch, multi_head_ctc_loss):
     model, _ = helpers.transformer_model_for_golden(golden)
     lengths = golden["lengths"]
     batch = Batch(golden["features"].cuda(), lengths.cuda(), torch.zeros(len(lengths), dtype=torch.long).cuda())
@@ -221,15 +235,10 @@ def test_transformer_model_trains_end_to_end_and_glu_stack_raises():
         if not losses:
             missing = [name for name, p in model.named_parameters() if p.requires_grad and (p.grad is None or not torch.isfinite(p.grad).all())]
             assert not missing, missing[:5]
-            assert any(float(p.grad.abs().max()) > 0 for name, p in model.named_parameters() if name.startswith("_acoustic_model._transformer"))
+            assert all(float(p.grad.abs().max()) > 0 for name, p in model.named_parameters() if name.startswith("_acoustic_model.") and "bias" not in name)
         optimizer.step()
         losses.append(float(loss))
     assert losses[-1] < losses[0], losses
-    glu = helpers.load_golden("transformer_linear_glu")
-    model, _ = helpers.transformer_model_for_golden(glu)
-    batch = Batch(glu["features"].cuda(), glu["lengths"].cuda(), torch.zeros(len(glu["lengths"]), dtype=torch.long).cuda())
-    with pytest.raises(NotImplementedError, match="sequential frontend"):
-        model(batch)
 
 
 @pytest.mark.gpu
