@@ -441,6 +441,8 @@ class HeadsRuntime:
             if hasattr(acoustic, "_model") and acoustic._model.training:  # HF regularises by module mode, also when the encoder is frozen
                 stochastic = Stochastic.from_config(acoustic._model.config, seed)
                 stochastic.skip_layers = self.skip_layers_override
+            elif not hasattr(acoustic, "_model") and acoustic.training:
+                stochastic = seed  # the from-scratch transformer encoder takes the seed of its dropout masks
             rate = self.model._projection._acoustic_model_dropout
             if rate is not None and rate.p > 0:
                 blocks = {0: -1, **{column: index for index, column in self.hidden_blocks.items()}}

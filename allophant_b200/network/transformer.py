@@ -9,7 +9,8 @@ Training: ``TransformerPlan(training=True)`` keeps the activations and ``Transfo
 pass of the transformer layers, the final LayerNorm, the positional embeddings and the direct / linear front end on the same
 GEMM (data-gradient / weight-gradient forms), flash-attention-backward and row kernels as the wav2vec2 path, and of the GLU
 convolution stack (GLU', weight gradient with overlapping-row operands, data gradient + col2im with the reflections folded
-back).  Dropout layers are identities (``eval()`` arithmetic) in both directions.
+back).  In ``train()`` mode the reference's dropout layers are applied with the counter-based masks of the wav2vec2 path
+(GEMM-epilogue / attention / elementwise dropout; the backward pass regenerates them), in ``eval()`` mode they are identities.
 """
 from __future__ import annotations
 
@@ -107,6 +108,7 @@ class TransformerPlan:
         self.n_utt, self.features, self.length, self.ldx = n_utt, features, length, ldx
         self.hidden_blocks = dict(hidden_blocks)
         self.generation = 0
+        self.drop_seed: Optional[int] = None
         self.captured: Optional[List[Tensor]] = None
         if features != model._frontend_input_size:
             raise ValueError(f"expected {model._frontend_input_size} input features per frame, got {features}")
@@ -131,7 +133,7 @@ class TransformerPlan:
                 elif isinstance(module, nn.Sequential):  # Transpose, LayerNorm, Transpose
                     self.stages.append(dict(kind="layer_norm", position=position, norm=module[1], channels=channels))
                 elif isinstance(module, nn.Dropout):
-                    continue  # identity in eval() arithmetic
+                    self.stages.append(dict(kind="dropout", position=position, rate=float(module.p)))  # identity unless train() mode
                 else:
                     raise NotImplementedError(f"sequential frontend layer {type(module).__name__}")
         self.seq = seq
@@ -196,7 +198,7 @@ class TransformerPlan:
             if stage["kind"] == "glu":
                 conv = stage["module"]._weights
                 stage["w"], stage["b"] = ops.pack_conv_weight(conv.weight), f32(conv.bias)
-            else:
+            elif stage["kind"] == "layer_norm":
                 stage["affine"] = _affine(stage["norm"])
         layers = []
         for layer in model._transformer.layers:
@@ -214,17 +216,48 @@ class TransformerPlan:
         self._packed, self._packed_version = packed, version
 
     # ------------------------------------------------------------------ forward
+    @staticmethod
+    def _set_dropout(args: Any, drop: ops.Dropout) -> None:
+        args.drop_threshold, args.drop_seed, args.drop_scale = drop.threshold, drop.seed, drop.scale
+
+    SITE_FRONTEND_INPUT = 1_000_011
+    SITE_MODEL_INPUT = 1_000_010
+    SITE_SEQUENTIAL = 1_000_100  # + position of the Dropout layer in the sequential frontend
+
+    def _site(self, rate: float, site: int) -> ops.Dropout:
+        """The counter-based dropout of one site of the current train()-mode run (``aph_common.cuh``: ``drop_hash``)."""
+        if self.drop_seed is None:
+            return ops.NO_DROPOUT
+        return ops.Dropout.site(rate, self.drop_seed, site)
+
+    def _frontend_input_rate(self) -> float:
+        frontend = self.model._frontend
+        if isinstance(frontend, LinearFrontend):
+            first = frontend._layer[0]
+            return float(first.p) if isinstance(first, nn.Dropout) else 0.0
+        return float(frontend._dropout.p) if getattr(frontend, "_dropout", None) is not None else 0.0
+
     @torch.no_grad()
-    def run(self, features: Tensor, lengths: Tensor, frames64: Tensor, capture: bool = False) -> None:
+    def run(self, features: Tensor, lengths: Tensor, frames64: Tensor, capture: bool = False, stochastic: Optional[int] = None) -> None:
+        """``stochastic`` (training plans): the seed of a train()-mode run — the reference's dropout layers (front-end input
+        dropouts, ``_input_dropout``, the Dropout layers of the sequential frontend, attention dropout and the three dropouts
+        of every ``PreLMTransformerEncoderLayer``) are applied with counter-based masks the backward pass regenerates."""
         model, N, d, M = self.model, self.n_utt, self.d, self.rows
         self._pack()
         packed = self._packed
         self.generation += 1
         self.captured = [] if capture else None
+        if stochastic is not None and not self.training:
+            raise RuntimeError("train()-mode regularisation needs a training plan")
+        self.drop_seed = stochastic
+        layer_rate = float(model._transformer.layers[0].dropout.p)
         eps = 1e-5
         lengths32 = lengths.to(torch.int32)
         ops.transpose_nfl(features, self.x_in, self.features)
         current, channels, seq = self.x_in, self.features, self.length
+        drop = self._site(self._frontend_input_rate(), self.SITE_FRONTEND_INPUT)
+        if drop.threshold:
+            ops.dropout_2d(current, channels, self.in_rows, channels, drop, out_f32=current, ld_f32=channels)
         frontend = model._frontend
         if isinstance(frontend, LinearFrontend):
             gamma, beta = packed["fe_ln"]
@@ -236,8 +269,16 @@ class TransformerPlan:
             args.gelu = 3  # LeakyReLU(0.01)
             ops.run_gemm(args)
             current, channels = out, neurons
+        drop = self._site(float(model._input_dropout.p), self.SITE_MODEL_INPUT)  # acoustic_model.py:673
+        if drop.threshold:
+            ops.dropout_2d(current, channels, self.in_rows, channels, drop, out_f32=current, ld_f32=channels)
         for stage in self.stages:
-            if stage["kind"] == "glu":
+            if stage["kind"] == "dropout":
+                drop = self._site(stage["rate"], self.SITE_SEQUENTIAL + stage["position"])
+                if drop.threshold:
+                    ops.dropout_2d(current, channels, N * seq, channels, drop, out_f32=current, ld_f32=channels)
+                stage["kept"] = dict(rows=N * seq, channels=channels)
+            elif stage["kind"] == "glu":
                 left, right, kernel, stride = stage["left"], stage["right"], stage["kernel"], stage["stride"]
                 padded_len = seq + left + right
                 padded = torch.empty(N * padded_len, channels, device=self.device, dtype=torch.bfloat16)
@@ -286,15 +327,20 @@ class TransformerPlan:
             g1, b1 = lw["ln1"]
             ops.layernorm_any(hidden, d, M, d, g1, b1, eps, out_f32=src, ld_f32=d, out_bf16=src16, ld_bf16=d)
             ops.run_gemm(ops.make_qkv_args(src16, lw["wqkv"], lw["bqkv"], q, k, v, rows=M, seq=seq, heads=self.heads))
-            ops.attention(q, k, v, ctx, self.frames32, N, self.heads, seq, lse)
-            ops.run_gemm(ops.make_gemm_args(ctx, lw["wo"], a_rows=M, a_inner=d, a_row_stride=d, bias=lw["bo"], resid=src, ld_resid=d, out_f32=h_mid, ld_f32=d))
+            ops.attention(q, k, v, ctx, self.frames32, N, self.heads, seq, lse, self._site(layer_rate, 8 * index))
+            args = ops.make_gemm_args(ctx, lw["wo"], a_rows=M, a_inner=d, a_row_stride=d, bias=lw["bo"], resid=src, ld_resid=d, out_f32=h_mid, ld_f32=d)
+            self._set_dropout(args, self._site(layer_rate, 8 * index + 1))  # dropout1
+            ops.run_gemm(args)
             g2, b2 = lw["ln2"]
             ops.layernorm_any(h_mid, d, M, d, g2, b2, eps, out_bf16=ln2, ld_bf16=d)
             args = ops.make_gemm_args(ln2, lw["w1"], a_rows=M, a_inner=d, a_row_stride=d, bias=lw["b1"], out_bf16=ffn, ld_bf16=self.ff,
                                       aux_bf16=pre, ld_aux=self.ff)  # fmt: skip
             args.gelu = self.act
+            self._set_dropout(args, self._site(layer_rate, 8 * index + 3))  # self.dropout, after the activation
             ops.run_gemm(args)
-            ops.run_gemm(ops.make_gemm_args(ffn, lw["w2"], a_rows=M, a_inner=self.ff, a_row_stride=self.ff, bias=lw["b2"], resid=h_mid, ld_resid=d, out_f32=h_out, ld_f32=d))
+            args = ops.make_gemm_args(ffn, lw["w2"], a_rows=M, a_inner=self.ff, a_row_stride=self.ff, bias=lw["b2"], resid=h_mid, ld_resid=d, out_f32=h_out, ld_f32=d)
+            self._set_dropout(args, self._site(layer_rate, 8 * index + 2))  # dropout2
+            ops.run_gemm(args)
             if self.training:
                 hidden = h_out
             # acoustic_model.py:690: the final LayerNorm is applied to EVERY layer's output
@@ -346,6 +392,15 @@ class TransformerPlan:
         def wgrad(out, dy, ld_dy, m, x, ld_x, n):
             ops.run_gemm(ops.make_wgrad_args(dy, x, out, rows=M, m=m, ld_dy=ld_dy, n=n, ld_x=ld_x, ld_out=n))
 
+        def branch_gradient(drop: ops.Dropout) -> bool:
+            """dh16 <- bf16(dh o keep * scale): gradient of a residual branch behind the forward's epilogue dropout."""
+            if drop.threshold:
+                ops.dropout_2d(dh, d, M, d, drop, out_bf16=dh16, ld_bf16=d)
+                return True
+            ops.cast_bf16_2d(dh, d, dh16, d, M, d)
+            return False
+
+        layer_rate = float(layers[0].dropout.p)
         final_flat, final_g = group([("weight", (d,)), ("bias", (d,))]) if affine else (None, {})
         final_gamma, _ = packed["final"]
         for index in reversed(range(n_layers)):
@@ -363,24 +418,32 @@ class TransformerPlan:
             if column is not None:
                 ops.layernorm_any_backward(sv["h_out"], d, d_x[:, column:], self.ldx, M, d, final_gamma, model._final_layer_norm.eps, dh, d, dh, d,
                                            final_g.get("weight"), final_g.get("bias"))  # fmt: skip
-            # ---- feed forward: out = m + W2 act(W1 LN2(m) + b1) + b2
-            ops.cast_bf16_2d(dh, d, dh16, d, M, d)
+            # ---- feed forward: out = m + dropout2(W2 dropout(act(W1 LN2(m) + b1)) + b2)
+            dropped = branch_gradient(self._site(layer_rate, 8 * index + 2))
             args = ops.make_dgrad_args(dh16, lw["w2"], rows=M, ld_dy=d, k=d, n=FF, ld_w=FF, gelu_bwd=sv["pre"], ld_gelu_bwd=FF, out_bf16=self.d_ff, ld_bf16=FF)
             args.act_bwd = self.act
+            self._set_dropout(args, self._site(layer_rate, 8 * index + 3))  # the mask of the dropout behind the activation
             ops.run_gemm(args)
             wgrad(g["linear2.weight"], dh16, d, d, sv["act"], FF, FF)
-            ops.colsum_f32(dh, M, d, d, out=g["linear2.bias"])
+            if dropped:
+                ops.colsum_bf16(dh16, M, d, d, out=g["linear2.bias"])
+            else:
+                ops.colsum_f32(dh, M, d, d, out=g["linear2.bias"])
             wgrad(g["linear1.weight"], self.d_ff, FF, FF, sv["ln2"], d, d)
             ops.colsum_bf16(self.d_ff, M, FF, FF, out=g["linear1.bias"])
             ops.run_gemm(ops.make_dgrad_args(self.d_ff, lw["w1"], rows=M, ld_dy=FF, k=FF, n=d, ld_w=d, out_f32=self.d_ln, ld_f32=d))
             g2, _ = lw["ln2"]
             ops.layernorm_any_backward(sv["h_mid"], d, self.d_ln, d, M, d, g2, eps, dh, d, dh, d, g.get("norm2.weight"), g.get("norm2.bias"))
-            # ---- attention block: m = src + Wo attn(Wqkv src) + bo, src = LN1(h)
-            ops.cast_bf16_2d(dh, d, dh16, d, M, d)
+            # ---- attention block: m = src + dropout1(Wo attn(Wqkv src) + bo), src = LN1(h)
+            dropped = branch_gradient(self._site(layer_rate, 8 * index + 1))
             ops.run_gemm(ops.make_dgrad_args(dh16, lw["wo"], rows=M, ld_dy=d, k=d, n=d, ld_w=d, out_bf16=self.d_ctx, ld_bf16=d))
             wgrad(g["self_attn.out_proj.weight"], dh16, d, d, sv["ctx"], d, d)
-            ops.colsum_f32(dh, M, d, d, out=g["self_attn.out_proj.bias"])
-            ops.attention_backward(sv["q"], sv["k"], sv["v"], sv["ctx"], self.d_ctx, sv["lse"], self.delta, self.dqkv, self.frames32, N, heads, seq)
+            if dropped:
+                ops.colsum_bf16(dh16, M, d, d, out=g["self_attn.out_proj.bias"])
+            else:
+                ops.colsum_f32(dh, M, d, d, out=g["self_attn.out_proj.bias"])
+            ops.attention_backward(sv["q"], sv["k"], sv["v"], sv["ctx"], self.d_ctx, sv["lse"], self.delta, self.dqkv, self.frames32, N, heads, seq,
+                                   self._site(layer_rate, 8 * index))  # fmt: skip
             wgrad(g["self_attn.in_proj_weight"], self.dqkv, 3 * d, 3 * d, sv["src16"], d, d)
             ops.colsum_bf16(self.dqkv, M, 3 * d, 3 * d, out=g["self_attn.in_proj_bias"])
             # d(src) = dh (the stream the branch joined) + dqkv Wqkv, in one GEMM with the residual epilogue
@@ -394,6 +457,11 @@ class TransformerPlan:
         d_cur, cur_rows, cur_channels = dh, M, d
         for stage in reversed(self.stages):
             kept, position = stage["kept"], stage["position"]
+            if stage["kind"] == "dropout":
+                drop = self._site(stage["rate"], self.SITE_SEQUENTIAL + position)
+                if drop.threshold:
+                    ops.dropout_2d(d_cur, cur_channels, cur_rows, cur_channels, drop, out_f32=d_cur, ld_f32=cur_channels)
+                continue
             if stage["kind"] == "layer_norm":
                 norm = stage["norm"]
                 gamma, _ = stage["affine"]
@@ -427,7 +495,7 @@ class TransformerPlan:
             if on_group_ready is not None:
                 on_group_ready(weight_gradient.view(-1), {k: v for k, v in named.items() if k.endswith("weight")})
                 on_group_ready(g["bias"], {k: v for k, v in named.items() if k.endswith("bias")})
-            first_stage = stage is self.stages[0]
+            first_stage = all(earlier["kind"] == "dropout" for earlier in self.stages[: self.stages.index(stage)])
             frontend_trains = isinstance(model._frontend, LinearFrontend) and any(p.requires_grad for p in model._frontend.parameters())
             if first_stage and not frontend_trains:
                 d_cur = None  # nothing upstream needs a gradient
@@ -441,6 +509,9 @@ class TransformerPlan:
         if d_cur is not None and isinstance(frontend, LinearFrontend) and any(p.requires_grad for p in frontend.parameters()):
             neurons, features = frontend.output_dimensions, self.features
             rows_in = self.in_rows
+            drop = self._site(float(model._input_dropout.p), self.SITE_MODEL_INPUT)
+            if drop.threshold:
+                ops.dropout_2d(d_cur, neurons, rows_in, neurons, drop, out_f32=d_cur, ld_f32=neurons)
             names = {id(module): index for index, module in enumerate(frontend._layer)}
             linear_index, norm_index = names[id(frontend.linear)], names[id(frontend.layer_norm)]
             shapes = [(f"{linear_index}.weight", (neurons, features)), (f"{linear_index}.bias", (neurons,))]
@@ -543,7 +614,7 @@ class TransformerAcousticModel(nn.Module):
         lengths = batch.lengths.to(device=features.device, dtype=torch.int64).contiguous()
         plan = self.plan_for(features.shape[0], features.shape[1], features.shape[2], ldx, hidden_blocks, training)
         frames = torch.empty(features.shape[0], device=features.device, dtype=torch.int64)
-        plan.run(features, lengths, frames, capture)
+        plan.run(features, lengths, frames, capture, stochastic)
         return plan, frames
 
     def forward(self, batch: Batch, _predict: bool = False) -> Tuple[List[Tensor], Tensor]:

@@ -40,24 +40,35 @@ def _glu1d(h: Tensor, lengths: Tensor, weight: Tensor, bias: Tensor, kernel: int
     return out[..., :half] * torch.sigmoid(out[..., half:]), torch.div(lengths + left + right - kernel, stride, rounding_mode="floor") + 1
 
 
-def forward(state: Mapping[str, Tensor], options: Mapping[str, Any], features: Tensor, lengths: Tensor, prefix: str = "_acoustic_model.") -> Tuple[List[Tensor], Tensor]:
+def forward(
+    state: Mapping[str, Tensor], options: Mapping[str, Any], features: Tensor, lengths: Tensor, prefix: str = "_acoustic_model.",
+    masks: Optional[Mapping[str, Tensor]] = None,
+) -> Tuple[List[Tensor], Tensor]:  # fmt: skip
     """``options``: the ``acoustic`` dict of a golden case (``transformer`` / ``frontend`` / ``sequential_frontend`` /
     ``elementwise_affine``).  Returns every layer's output after the final LayerNorm, batch-first ``[N, L', d]``, and the frame
-    counts."""
+    counts.  ``masks``: the reference's train()-mode dropout layers as EXPLICIT multiplicative masks (keep / (1-p) or 0),
+    batch-first: ``frontend_input`` [N, L, F] (frontend.py:161-164, 173-180), ``input`` (acoustic_model.py:673),
+    ``sequential.<position>`` (frontend.py:236-237), ``attention.<l>`` [N, heads, T, T], ``attention_output.<l>`` (dropout1),
+    ``activation.<l>`` (dropout), ``feed_forward_output.<l>`` (dropout2) (acoustic_model.py:323-328)."""
     get = lambda name: state.get(prefix + name)  # noqa: E731
-    h = features.transpose(1, 2)  # [N, L, F]
+    masks = masks or {}
+    drop = lambda value, key: value * masks[key] if key in masks else value  # noqa: E731
+    h = drop(features.transpose(1, 2), "frontend_input")  # [N, L, F]
     frontend = options["frontend"]
     if frontend["architecture"] == "linear":
         shift = 1 if frontend.get("input_dropout", 0) > 0 else 0  # nn.Sequential: [Dropout,] LayerNorm, Linear, LeakyReLU
         h = F.layer_norm(h, (h.shape[-1],), get(f"_frontend._layer.{shift}.weight"), get(f"_frontend._layer.{shift}.bias"))
         h = F.leaky_relu(h @ get(f"_frontend._layer.{shift + 1}.weight").T + get(f"_frontend._layer.{shift + 1}.bias"))
+    h = drop(h, "input")
     for index, layer in enumerate(options.get("sequential_frontend") or []):
         base = f"_sequential_frontend._layers.layers.{index}.module."
         if layer["type"] == "glu1d":
             h, lengths = _glu1d(h, lengths, get(base + "_weights.weight"), get(base + "_weights.bias"), layer["kernel"], layer.get("stride", 1))
         elif layer["type"] == "layer_norm":
             h = F.layer_norm(h, (h.shape[-1],), get(base + "1.weight"), get(base + "1.bias"))
-        elif layer["type"] != "dropout":
+        elif layer["type"] == "dropout":
+            h = drop(h, f"sequential.{index}")
+        else:
             raise NotImplementedError(layer["type"])
     n_utt, frames, width = h.shape
     transformer = options["transformer"]
@@ -78,9 +89,10 @@ def forward(state: Mapping[str, Tensor], options: Mapping[str, Any], features: T
         split = lambda t: t.view(n_utt, frames, heads, width // heads).transpose(1, 2)  # noqa: E731
         scores = split(q) @ split(k).transpose(-1, -2) / math.sqrt(width // heads)
         scores = scores.masked_fill(padding[:, None, None, :], float("-inf"))
-        context = (torch.softmax(scores, -1) @ split(v)).transpose(1, 2).reshape(n_utt, frames, width)
-        h = src + context @ get(base + "self_attn.out_proj.weight").T + get(base + "self_attn.out_proj.bias")
+        context = (drop(torch.softmax(scores, -1), f"attention.{index}") @ split(v)).transpose(1, 2).reshape(n_utt, frames, width)
+        h = src + drop(context @ get(base + "self_attn.out_proj.weight").T + get(base + "self_attn.out_proj.bias"), f"attention_output.{index}")
         inner = activation(F.layer_norm(h, (width,), get(base + "norm2.weight"), get(base + "norm2.bias")) @ get(base + "linear1.weight").T + get(base + "linear1.bias"))
-        h = h + inner @ get(base + "linear2.weight").T + get(base + "linear2.bias")
+        inner = drop(inner, f"activation.{index}")
+        h = h + drop(inner @ get(base + "linear2.weight").T + get(base + "linear2.bias"), f"feed_forward_output.{index}")
         outputs.append(F.layer_norm(h, (width,), get("_final_layer_norm.weight"), get("_final_layer_norm.bias")))
     return outputs, lengths

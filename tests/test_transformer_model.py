@@ -116,7 +116,32 @@ def _norm_err(value: torch.Tensor, reference: torch.Tensor) -> float:
     return float((value.double().cpu() - reference.double()).norm() / reference.double().norm().clamp_min(1e-20))
 
 
-def _encoder_gradient_check(state_dict, options, feature_size, features, lengths, name, tolerance=5e-2):
+def _transformer_masks(plan, options, lengths):
+    """The explicit masks of oracle/restatement_transformer.forward for the dropout sites of a train()-mode TransformerPlan run
+    (same counter-based hash, restated in numpy by tests/helpers.keep_mask)."""
+    n_utt, width, heads, seq = plan.n_utt, plan.d, plan.heads, plan.seq
+    rate = float(plan.model._transformer.layers[0].dropout.p)
+    masks = {}
+    frontend_rate = plan._frontend_input_rate()
+    if frontend_rate > 0:
+        masks["frontend_input"] = helpers.keep_mask(plan._site(frontend_rate, plan.SITE_FRONTEND_INPUT), plan.in_rows, plan.features).view(n_utt, plan.length, plan.features)
+    if float(plan.model._input_dropout.p) > 0:
+        channels = plan.model._frontend.output_dimensions
+        masks["input"] = helpers.keep_mask(plan._site(float(plan.model._input_dropout.p), plan.SITE_MODEL_INPUT), plan.in_rows, channels).view(n_utt, plan.length, channels)
+    for stage in plan.stages:
+        if stage["kind"] == "dropout" and stage["rate"] > 0:
+            rows, channels = stage["kept"]["rows"], stage["kept"]["channels"]
+            masks[f"sequential.{stage['position']}"] = helpers.keep_mask(plan._site(stage["rate"], plan.SITE_SEQUENTIAL + stage["position"]), rows, channels).view(n_utt, rows // n_utt, channels)
+    if rate > 0:
+        for layer in range(len(plan.model._transformer.layers)):
+            masks[f"attention.{layer}"] = helpers.keep_mask(plan._site(rate, 8 * layer), n_utt * heads * seq, seq).view(n_utt, heads, seq, seq)
+            masks[f"attention_output.{layer}"] = helpers.keep_mask(plan._site(rate, 8 * layer + 1), n_utt * seq, width).view(n_utt, seq, width)
+            masks[f"feed_forward_output.{layer}"] = helpers.keep_mask(plan._site(rate, 8 * layer + 2), n_utt * seq, width).view(n_utt, seq, width)
+            masks[f"activation.{layer}"] = helpers.keep_mask(plan._site(rate, 8 * layer + 3), n_utt * seq, plan.ff).view(n_utt, seq, plan.ff)
+    return masks
+
+
+def _encoder_gradient_check(state_dict, options, feature_size, features, lengths, name, tolerance=5e-2, seed=None):
     """Backward pass of the encoder alone: L = sum(final hidden state * G) on the valid frames; every parameter gradient of
     ``TransformerPlan.backward`` against autograd through the CPU restatement (norm-relative per tensor; bf16 operands)."""
     from allophant_b200.config import TransformerAcousticModelConfig
@@ -133,14 +158,19 @@ def _encoder_gradient_check(state_dict, options, feature_size, features, lengths
     model = model.cuda()
     width = model.d_model
     batch = Batch(features.cuda(), lengths.cuda(), torch.zeros(len(lengths)).cuda())
-    plan, frames = model.encode(batch, width, {}, training=True)
+    plan, frames = model.encode(batch, width, {}, training=True, stochastic=seed)
+    masks = _transformer_masks(plan, options, lengths) if seed is not None else None
     generator = torch.Generator().manual_seed(1)
     weights = torch.randn(len(lengths), plan.seq, width, generator=generator)
     weights = weights * (torch.arange(plan.seq)[None, :] < frames.cpu()[:, None])[..., None]
     gradients = plan.backward(weights.view(-1, width).cuda().contiguous())
 
     leaves = {key: value.clone().requires_grad_(True) for key, value in state_dict.items() if key.startswith("_acoustic_model.") and value.is_floating_point()}
-    outputs, _ = restatement_transformer.forward(leaves, options, features, lengths)
+    outputs, _ = restatement_transformer.forward(leaves, options, features, lengths, masks=masks)
+    final = plan.x[:, :width].float().view(len(lengths), plan.seq, width).cpu()
+    for utterance, count in enumerate(frames.tolist()):  # forward parity on the same masks first
+        reference = outputs[-1][utterance, :count].detach()
+        assert float((final[utterance, :count] - reference).abs().max()) < 4e-2 * float(reference.abs().max()), (name, utterance)
     (outputs[-1] * weights).sum().backward()
     worst = {}
     for key, leaf in leaves.items():
@@ -196,6 +226,18 @@ def test_encoder_backward_matches_the_restatement_glu_stack():
     golden = helpers.load_golden("transformer_linear_glu")
     _encoder_gradient_check(golden["state_dict"], golden["case"]["acoustic"], golden["case"]["feature_size"], golden["features"], golden["lengths"],
                             "linear_glu", tolerance=6e-2)  # fmt: skip
+
+
+@pytest.mark.gpu
+def test_train_mode_dropout_matches_the_restatement_with_the_same_masks():
+    """train() mode of the from-scratch transformer model: every dropout layer of the reference (frontend input 0.1, model
+    input 0.1, the sequential frontend's Dropout layer, attention / dropout1 / dropout / dropout2 of every layer at 0.1) with
+    the counter-based masks, forward and backward against the restatement fed with the same masks."""
+    golden = helpers.load_golden("transformer_linear_glu")
+    options = golden["case"]["acoustic"]
+    assert options["transformer"]["dropout_rate"] == 0.1 and options["frontend"]["input_dropout"] == 0.1
+    _encoder_gradient_check(golden["state_dict"], options, golden["case"]["feature_size"], golden["features"], golden["lengths"],
+                            "linear_glu train()", tolerance=6e-2, seed=1234)  # fmt: skip
 
 
 @pytest.mark.gpu
