@@ -273,9 +273,15 @@ class EncoderPlan:
         normalize: bool = True,
         use_lengths: bool = True,
         training: bool = False,
+        train_extractor: bool = False,
     ) -> None:
         cfg = packed.cfg
         self.training = training
+        # the convolutional feature extractor trains too (freeze_feature_encoder = false / UnfreezeSchedule): its
+        # pre-LayerNorm conv outputs and activations are kept per layer instead of ping-ponging through two buffers
+        self.train_extractor = train_extractor
+        if train_extractor and (not training or cfg.feat_extract_norm != "layer"):
+            raise NotImplementedError("feature-extractor training is built for training plans of the layer-norm variant (XLS-R, wav2vec2-large)")
         self.generation = 0  # bumped by every run(): a backward pass checks that its activations are still there
         dev = packed.device
         assert dev is not None
@@ -351,6 +357,9 @@ class EncoderPlan:
             self.dqkv = z(M, 3 * H)
             self.delta = z(n_utt * heads * self.seq, dtype=f32)
             self.d_fp_in = z(M, 512, dtype=f32)
+            if train_extractor:
+                self.conv_pre = [z(n_utt * length * 512) for length in L]
+                self.conv_post = [z(n_utt * length * 512) for length in L]
             self.spec_mask = z(M, dtype=torch.uint8)  # SpecAugment time mask of the last train()-mode run
         self.stoch: Optional[Stochastic] = None       # regularisation of the last run (None: eval()-mode arithmetic)
         self.skipped: List[bool] = [False] * len(packed.layers)  # LayerDrop decisions of the last run
@@ -384,6 +393,8 @@ class EncoderPlan:
         src, dst = self.buf_a, self.buf_b
         for i in range(1, len(L)):
             kernel, stride = cfg.conv_kernel[i], cfg.conv_stride[i]
+            if self.train_extractor:
+                src, dst = self.conv_post[i - 1], self.conv_pre[i]
             args = ops.make_gemm_args(
                 src,
                 p.conv_w[i],
@@ -401,13 +412,14 @@ class EncoderPlan:
             steps.append(self._gemm(args))
             if layer_norm:
                 g, b = p.conv_ln[i]
+                activated = self.conv_post[i] if self.train_extractor else dst
                 steps.append(
-                    lambda dst=dst, rows=N * L[i], g=g, b=b: ops.layernorm_rows(
-                        dst, rows, 512, 512, g, b, 1e-5, gelu=True, out_bf16=dst, ld_bf16=512
+                    lambda dst=dst, rows=N * L[i], g=g, b=b, activated=activated: ops.layernorm_rows(
+                        dst, rows, 512, 512, g, b, 1e-5, gelu=True, out_bf16=activated, ld_bf16=512
                     )
                 )
             src, dst = dst, src
-        conv_out = src  # [N, T', 512]
+        conv_out = self.conv_post[-1] if self.train_extractor else src  # [N, T', 512]
         self.conv_out = conv_out
 
         # feature projection: LN -> Linear, padded frames zeroed (HF:753-756), fp32 residual stream + bf16 copy
@@ -594,7 +606,12 @@ class EncoderPlan:
         if self.normalize:
             ops.wave_stats(audio, lengths, self.stats, self.mean_rstd)
             mean_rstd = self.mean_rstd
-        if cfg.feat_extract_norm == "layer":
+        if self.train_extractor:
+            g, b = p.conv_ln[0]
+            self._wave = (audio, lengths, mean_rstd)  # the backward pass of the first convolution reads the waveform again
+            ops.conv0_raw(audio, lengths, mean_rstd, p.conv0_w, p.conv_bias[0], self.conv_pre[0])
+            ops.layernorm_rows(self.conv_pre[0], N * self.conv_lengths[0], 512, 512, g, b, 1e-5, gelu=True, out_bf16=self.conv_post[0], ld_bf16=512)
+        elif cfg.feat_extract_norm == "layer":
             g, b = p.conv_ln[0]
             ops.conv0_ln_gelu(audio, lengths, mean_rstd, p.conv0_w, p.conv_bias[0], g, b, 1e-5, self.buf_a, self.use_lengths)
         else:
@@ -621,14 +638,15 @@ class EncoderPlan:
         need_encoder: bool,
         need_projection: bool,
         on_group_ready: Optional[Callable[[Tensor, Dict[str, Tensor]], None]] = None,
+        need_extractor: bool = False,
     ) -> Dict[str, Tensor]:
         """Backward pass of everything ``run`` enqueued, from the gradient of the classifier feature matrix.
 
         ``d_x`` fp32 ``[M, ldx]`` is dL/dX (X = ``[final LayerNorm | kept hidden states | ...]``).  Returns
         fp32 gradients keyed by the Hugging Face parameter names of ``Wav2Vec2Weights`` for the transformer
-        (``need_encoder``) and the feature projection (``need_projection``).  The convolutional feature
-        extractor is frozen in the reference's configurations (``default_config.toml:40``,
-        ``acoustic_model.py:806-807``); its backward is not part of this build.
+        (``need_encoder``), the feature projection (``need_projection``) and — on plans built with
+        ``train_extractor=True`` — the convolutional feature extractor (``need_extractor``; frozen in the reference's
+        default configuration, ``default_config.toml:40``, trained after its ``UnfreezeSchedule`` fires).
 
         Every Linear contributes two tcgen05 GEMMs that read the forward pass's own buffers:
         ``dX = dY W`` (W as an MN-major B operand) and ``dW = dY^T X`` (both operands MN-major, split-K
@@ -779,7 +797,9 @@ class EncoderPlan:
             done(flat, g, "encoder.pos_conv_embed.conv.")
         embed = getattr(w, "masked_spec_embed", None)
         need_embed = st is not None and self.spec_active and embed is not None and embed.requires_grad
-        if need_projection or need_embed:
+        if need_extractor and not self.train_extractor:
+            raise RuntimeError("this EncoderPlan did not keep the feature extractor's activations (train_extractor=False)")
+        if need_projection or need_embed or need_extractor:
             # data gradient of the grouped conv: the same sliding-tap GEMM with flipped taps, accumulated onto dh
             ops.run_gemm(
                 ops.make_gemm_args(
@@ -797,7 +817,7 @@ class EncoderPlan:
                         done(flat, g, "")
                 if st.feature_projection().threshold:
                     ops.dropout_2d(dh, H, M, H, st.feature_projection(), out_f32=dh, ld_f32=H)
-        if need_projection:
+        if need_projection or need_extractor:
             # ---- feature projection (HF:422-434) behind the padded-frame zeroing (HF:753-756)
             if self.use_lengths:
                 ops.mask_rows(dh, H, M, H, self.frames32, seq)
@@ -809,4 +829,45 @@ class EncoderPlan:
             gp, _ = p.fp_ln
             ops.layernorm_backward(self.conv_out, 512, self.d_fp_in, 512, M, 512, gp, eps, None, 0, self.d_fp_in, 512, g["layer_norm.weight"], g["layer_norm.bias"])
             done(flat, g, "feature_projection.")
+        if need_extractor:
+            self._backward_extractor(self.d_fp_in, group, done)
         return grads
+
+    def _backward_extractor(self, d_post: Tensor, group: Any, done: Any) -> None:
+        """Backward pass of the convolutional feature extractor (HF:275-323, 382-419, layer-norm variant) from ``d_post`` =
+        gradient of its output (fp32 ``[N * T', 512]``).  Per layer: LayerNorm + GELU backward from the kept pre-LayerNorm conv
+        output (one fused kernel, also the conv bias gradient), weight gradient as a GEMM over overlapping-row windows of the
+        kept input activation (one K segment per utterance), data gradient GEMM + col2im; the first convolution reads the
+        normalised waveform again."""
+        p, cfg = self.packed, self.cfg
+        N, L = self.n_utt, self.conv_lengths
+        dev = d_post.device
+        audio, lengths, mean_rstd = self._wave
+        layers = p.weights.feature_extractor.conv_layers
+        for i in reversed(range(len(L))):
+            kernel, stride = cfg.conv_kernel[i], cfg.conv_stride[i]
+            has_bias = p.conv_bias[i] is not None
+            shapes = [("conv.weight", tuple(layers[i].conv.weight.shape)), ("layer_norm.weight", (512,)), ("layer_norm.bias", (512,))]
+            if has_bias:
+                shapes.append(("conv.bias", (512,)))
+            flat, g = group(shapes)
+            gamma, beta = p.conv_ln[i]
+            rows = N * L[i]
+            d_pre = torch.empty(rows, 512, device=dev, dtype=torch.bfloat16)
+            ops.ln_gelu_backward_512(self.conv_pre[i], d_post, 512, rows, gamma, beta, 1e-5, d_pre, g["layer_norm.weight"], g["layer_norm.bias"], g.get("conv.bias"))
+            if i == 0:
+                ops.conv0_weight_backward(d_pre, audio, lengths, mean_rstd, g["conv.weight"].view(512, kernel))
+            else:
+                width = kernel * 512
+                raw = torch.empty(512, width, device=dev, dtype=torch.float32)
+                args = ops.make_wgrad_args(d_pre, self.conv_post[i - 1], raw, rows=L[i], m=512, ld_dy=512, n=width, ld_x=stride * 512, ld_out=width)
+                args.k_batch, args.a_batch_stride, args.b_seg_stride = N, L[i] * 512, L[i - 1] * 512
+                ops.run_gemm(args)
+                g["conv.weight"].copy_(raw.view(512, kernel, 512).permute(0, 2, 1))  # [O][k][C] -> Conv1d's [O][C][k]
+                d_cols = torch.empty(rows, width, device=dev, dtype=torch.float32)
+                ops.run_gemm(ops.make_dgrad_args(d_pre, p.conv_w[i], rows=rows, ld_dy=512, k=512, n=width, ld_w=width, out_f32=d_cols, ld_f32=width))
+                d_in = torch.empty(N * L[i - 1], 512, device=dev, dtype=torch.float32)
+                full = torch.full((N,), L[i - 1], device=dev, dtype=torch.int32)
+                ops.conv_input_backward(d_cols, full, N, L[i - 1], 512, L[i], kernel, stride, 0, 0, False, d_in, 512)
+                d_post = d_in
+            done(flat, g, f"feature_extractor.conv_layers.{i}.")

@@ -326,16 +326,11 @@ class HeadsRuntime:
                 return self._forward_differentiable(batch, target_feature_indices, predict, need_encoder, False)
         elif torch.is_grad_enabled() and not log_probabilities:
             weights = acoustic._model
-            if any(p.requires_grad for p in weights.feature_extractor.parameters()):
-                raise NotImplementedError(
-                    "allophant_b200: the backward pass of the convolutional feature extractor is not part of this build; keep "
-                    "nn.acoustic_model.freeze_feature_encoder = true (the reference's default, default_config.toml:40) or run "
-                    "under torch.no_grad()/inference_mode()"
-                )
+            need_extractor = any(p.requires_grad for p in weights.feature_extractor.parameters())
             need_encoder = any(p.requires_grad for p in weights.encoder.parameters())
             need_feature_projection = any(p.requires_grad for p in weights.feature_projection.parameters())
-            if need_encoder or need_feature_projection or any(p.requires_grad for p in projection.parameters()):
-                return self._forward_differentiable(batch, target_feature_indices, predict, need_encoder, need_feature_projection)
+            if need_encoder or need_feature_projection or need_extractor or any(p.requires_grad for p in projection.parameters()):
+                return self._forward_differentiable(batch, target_feature_indices, predict, need_encoder, need_feature_projection, need_extractor)
         plan, frames = acoustic.encode(batch, self.ldx, self.hidden_blocks)
         device = plan.x.device
         self._ensure_weights(device)
@@ -419,7 +414,10 @@ class HeadsRuntime:
         return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
 
     # ------------------------------------------------------------------ differentiable path (training)
-    def _forward_differentiable(self, batch: Batch, target_feature_indices: Optional[Tensor], predict: bool, need_encoder: bool, need_feature_projection: bool):
+    def _forward_differentiable(
+        self, batch: Batch, target_feature_indices: Optional[Tensor], predict: bool, need_encoder: bool, need_feature_projection: bool,
+        need_extractor: bool = False,
+    ):  # fmt: skip
         """Training / validation forward with autograd: the whole model is ONE ``torch.autograd.Function``.
 
         torch only carries the graph edge from the returned logits back to the parameters; forward and
@@ -433,7 +431,7 @@ class HeadsRuntime:
         from .network.acoustic_model import Predictions
 
         acoustic = self.model._acoustic_model
-        through_encoder = need_encoder or need_feature_projection
+        through_encoder = need_encoder or need_feature_projection or need_extractor
         stochastic = None
         input_dropout: Dict[int, ops.Dropout] = {}  # column of X -> dropout of that classifier input block
         if self.model.training:
@@ -450,7 +448,8 @@ class HeadsRuntime:
                     raise NotImplementedError("acoustic_model_dropout with both OUTPUT and the last OUTPUT_i as dependencies")
                 input_dropout = {column: ops.Dropout.site(rate.p, seed, Stochastic.SITE_CLASSIFIER_INPUT + index + 1) for column, index in blocks.items()}
         with torch.no_grad():
-            plan, frames = acoustic.encode(batch, self.ldx, self.hidden_blocks, training=through_encoder or stochastic is not None, stochastic=stochastic)
+            extra = dict(train_extractor=True) if need_extractor else {}
+            plan, frames = acoustic.encode(batch, self.ldx, self.hidden_blocks, training=through_encoder or stochastic is not None, stochastic=stochastic, **extra)
             self._ensure_weights(plan.x.device)
             hidden = self.model._projection._output_features
             for column, drop in input_dropout.items():
@@ -462,7 +461,7 @@ class HeadsRuntime:
             named += [(self._encoder_prefix() + name, parameter) for name, parameter in weights.named_parameters() if parameter.requires_grad]
         state: Dict[str, Any] = dict(
             batch=batch, tfi=target_feature_indices, predict=predict, plan=plan, names=[n for n, _ in named], generation=None,
-            need_encoder=need_encoder, need_feature_projection=need_feature_projection, input_dropout=input_dropout,
+            need_encoder=need_encoder, need_feature_projection=need_feature_projection, need_extractor=need_extractor, input_dropout=input_dropout,
         )  # fmt: skip
         outputs = _ProjectionFunction.apply(self, state, *[p for _, p in named])
         names = state["head_names"]
@@ -495,7 +494,7 @@ class HeadsRuntime:
         device = x.device
         skip = 0 if projection._dependency_blanks else projection._blank_offset
         param_grads: Dict[str, Tensor] = {}
-        through_encoder = state["need_encoder"] or state["need_feature_projection"]
+        through_encoder = state["need_encoder"] or state["need_feature_projection"] or state.get("need_extractor", False)
         need_dx = through_encoder or any(layout.feeds_later for layout in self.levels)
 
         # gradient of every classifier's final logits, keyed by classifier name, fp32 [rows, width]
@@ -619,8 +618,9 @@ class HeadsRuntime:
             for column, drop in state["input_dropout"].items():  # acoustic_model.py:486-488, same masks as the forward
                 block = d_x[:, column:]
                 ops.dropout_2d(block, d_x.shape[1], rows, hidden, drop, out_f32=block, ld_f32=d_x.shape[1])
+            extra = dict(need_extractor=True) if state.get("need_extractor") else {}
             encoder_grads = plan.backward(
-                d_x, state["need_encoder"], state["need_feature_projection"], None if reducer is None else reducer.submit
+                d_x, state["need_encoder"], state["need_feature_projection"], None if reducer is None else reducer.submit, **extra
             )
             for name, value in encoder_grads.items():
                 param_grads[self._encoder_prefix() + name] = value

@@ -361,9 +361,9 @@ class Wav2Vec2AcousticModel(AcousticModel):
         return lengths
 
     # -- engine access ---------------------------------------------------------------------
-    def plan_for(self, n_utt: int, samples: int, ldx: int, hidden_blocks: Dict[int, int], training: bool = False) -> EncoderPlan:
+    def plan_for(self, n_utt: int, samples: int, ldx: int, hidden_blocks: Dict[int, int], training: bool = False, train_extractor: bool = False) -> EncoderPlan:
         self._packed.ensure()
-        key = (n_utt, samples, ldx, tuple(sorted(hidden_blocks.items())), training)
+        key = (n_utt, samples, ldx, tuple(sorted(hidden_blocks.items())), training, train_extractor)
         plan = self._plans.get(key)
         if plan is None or plan.layout_id != self._packed.layout_id:
             if plan is None and len(self._plans) >= 4:  # workspaces are large: keep a handful of shapes
@@ -372,14 +372,15 @@ class Wav2Vec2AcousticModel(AcousticModel):
                 # same shape, re-allocated operands (the parameters moved): keep the workspaces, rebuild the launch list
                 plan.rebind(self._packed)
             else:
-                plan = EncoderPlan(self._packed, n_utt, samples, ldx, hidden_blocks, self._normalize, self._use_attention_mask, training)
+                plan = EncoderPlan(self._packed, n_utt, samples, ldx, hidden_blocks, self._normalize, self._use_attention_mask, training, train_extractor)
             plan.layout_id = self._packed.layout_id
             self._plans[key] = plan
         return plan
 
     def encode(
-        self, batch: Batch, ldx: int, hidden_blocks: Dict[int, int], capture: bool = False, training: bool = False, stochastic: Any = None
-    ) -> Tuple[EncoderPlan, Tensor]:
+        self, batch: Batch, ldx: int, hidden_blocks: Dict[int, int], capture: bool = False, training: bool = False, stochastic: Any = None,
+        train_extractor: bool = False,
+    ) -> Tuple[EncoderPlan, Tensor]:  # fmt: skip
         audio = batch.audio_features
         if not audio.is_cuda:
             raise RuntimeError("allophant_b200 runs on CUDA only: move the batch to the GPU (`batch.to('cuda')`)")
@@ -389,7 +390,7 @@ class Wav2Vec2AcousticModel(AcousticModel):
             raise ValueError(f"expected raw audio of shape [batch, samples], got {tuple(audio.shape)}")
         audio = audio.float().contiguous()
         lengths = batch.lengths.to(device=audio.device, dtype=torch.int64).contiguous()
-        plan = self.plan_for(audio.shape[0], audio.shape[1], ldx, hidden_blocks, training)
+        plan = self.plan_for(audio.shape[0], audio.shape[1], ldx, hidden_blocks, training, train_extractor)
         frames = torch.empty(audio.shape[0], device=audio.device, dtype=torch.int64)
         plan.run(audio, lengths, frames, capture, stochastic)
         return plan, frames

@@ -597,6 +597,22 @@ def masked_rows_backward(d: Tensor, ld: int, rows: int, cols: int, row_mask: Ten
     check(lib.aph_masked_rows_backward(d.data_ptr(), ld, rows, cols, row_mask.data_ptr(), d_fill.data_ptr(), _stream()), "aph_masked_rows_backward")
 
 
+def conv0_raw(audio: Tensor, lengths: Tensor, mean_rstd: Optional[Tensor], weight: Tensor, bias: Optional[Tensor], out: Tensor) -> None:
+    """Pre-LayerNorm output of the first wav2vec2 convolution, bf16 ``[N, L0, 512]`` (feature-extractor training)."""
+    _require_cuda(audio, lengths, mean_rstd, weight, bias, out)
+    check(lib.aph_conv0_raw_bf16(audio.data_ptr(), lengths.data_ptr(), _ptr(mean_rstd), audio.shape[0], audio.shape[1], weight.data_ptr(), _ptr(bias), out.data_ptr(), _stream()), "aph_conv0_raw_bf16")
+
+
+def ln_gelu_backward_512(x: Tensor, d_out: Tensor, ld_d: int, rows: int, gamma: Tensor, beta: Tensor, eps: float, dx: Tensor, dgamma: Tensor, dbeta: Tensor, dbias: Optional[Tensor]) -> None:
+    _require_cuda(x, d_out, gamma, beta, dx, dgamma, dbeta, dbias)
+    check(lib.aph_ln_gelu_backward_512(x.data_ptr(), d_out.data_ptr(), ld_d, rows, gamma.data_ptr(), beta.data_ptr(), eps, dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _ptr(dbias), _stream()), "aph_ln_gelu_backward_512")
+
+
+def conv0_weight_backward(dy: Tensor, audio: Tensor, lengths: Tensor, mean_rstd: Optional[Tensor], dw: Tensor) -> None:
+    _require_cuda(dy, audio, lengths, mean_rstd, dw)
+    check(lib.aph_conv0_weight_backward(dy.data_ptr(), audio.data_ptr(), lengths.data_ptr(), _ptr(mean_rstd), audio.shape[0], audio.shape[1], dw.data_ptr(), _stream()), "aph_conv0_weight_backward")
+
+
 def layernorm_any(
     x: Tensor, ld_x: int, rows: int, cols: int, gamma: Optional[Tensor], beta: Optional[Tensor], eps: float,
     out_f32: Optional[Tensor] = None, ld_f32: int = 0, out_bf16: Optional[Tensor] = None, ld_bf16: int = 0,

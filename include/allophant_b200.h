@@ -429,6 +429,21 @@ int aph_edit_statistics_batch(const int64_t* expected_host, const int64_t* expec
 float aph_word_error_rate(uint64_t insertions, uint64_t deletions, uint64_t substitutions,
                           uint64_t correct);
 
+/* ---- training of the wav2vec2 convolutional feature extractor (freeze_feature_encoder = false / UnfreezeSchedule; ----
+ * ---- HF modeling_wav2vec2.py:275-323, 382-419, layer-norm variant) -------------------------------------------------- */
+/* conv(1 -> 512, k 10, s 5) of the normalised waveform BEFORE LayerNorm, bf16 [n_utt][L0][512] (kept for the backward). */
+int aph_conv0_raw_bf16(const float* x, const int64_t* lengths, const float* mean_rstd, int32_t n_utt, int32_t T,
+                       const float* w, const float* bias, void* out_bf16, void* stream);
+/* Backward of LayerNorm(512) -> GELU from the kept pre-LayerNorm conv output x (bf16 [rows][512]) and the gradient of the
+ * GELU output d_out (fp32 [rows][ld_d]): dx bf16 [rows][512]; dgamma, dbeta and (optional) dbias = column sums of dx are
+ * OVERWRITTEN. */
+int aph_ln_gelu_backward_512(const void* x_bf16, const float* d_out, int64_t ld_d, int64_t rows, const float* gamma,
+                             const float* beta, float eps, void* dx_bf16, float* dgamma, float* dbeta, float* dbias,
+                             void* stream);
+/* dW0 fp32 [512][10] = sum_(n,t) dY[n][t][o] * normalised_waveform[n][5 t + j]. */
+int aph_conv0_weight_backward(const void* dy_bf16, const float* x, const int64_t* lengths, const float* mean_rstd,
+                              int32_t n_utt, int32_t T, float* dw, void* stream);
+
 /* ---- from-scratch pre-LN transformer acoustic model (acoustic_model.py:34-69, 564-759; frontend.py; padding.py) */
 /* nn.LayerNorm over the last axis of fp32 x [rows][ld_x], any width; gamma/beta NULL = elementwise_affine=False. */
 int aph_layernorm_any(const float* x, int64_t ld_x, int64_t rows, int32_t cols, const float* gamma,

@@ -464,11 +464,12 @@ class OracleModel:
         language_ids: Optional[Tensor] = None,
         target_feature_indices: Optional[Tensor] = None,
         regularisation: Optional[Dict[str, object]] = None,
+        freeze_feature_encoder: bool = True,
     ) -> Tuple[Tensor, Dict[str, float], Dict[str, Tensor]]:
         """``estimator.py:708-738`` in eval()-mode arithmetic (or with explicit train()-mode masks): ``model(batch)`` (predict=False), per-head
         ``CTCWrapper``, ``loss = sum_heads ctc / sum_heads sum_utt label_length``, ``backward()``.
         Returns (loss, per-head CTC sums, gradients by state_dict name)."""
-        named = self.trainable_parameters()
+        named = self.trainable_parameters(freeze_feature_encoder)
         for parameter in named.values():
             parameter.grad = None
         with torch.enable_grad():

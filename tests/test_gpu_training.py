@@ -349,6 +349,43 @@ def test_training_forward_equals_inference_forward(training_case):
         assert torch.equal(training.outputs[name].detach(), value), name
 
 
+def test_unfrozen_feature_extractor_trains(training_case):
+    """freeze_feature_encoder = false (or after the reference's UnfreezeSchedule fired): the convolutional feature
+    extractor gets gradients too — conv weights / biases and their LayerNorms, all seven layers — against the oracle with
+    the extractor unfrozen.  Same tolerance as the rest of the step."""
+    if training_case["name"] != "multitask_2layer":
+        pytest.skip("one architecture is enough")
+    fixture, model, oracle = training_case["fixture"], training_case["model"], training_case["oracle"]
+    model.eval()
+    extractor = [(name, parameter) for name, parameter in model.named_parameters() if ".feature_extractor." in name]
+    assert len(extractor) == 28 and not any(parameter.requires_grad for _, parameter in extractor)
+    try:
+        for _, parameter in extractor:
+            parameter.requires_grad = True
+        loss, _, _ = _training_step(model, training_case["batch"], fixture)
+        gradients = {name: parameter.grad.detach().clone() for name, parameter in model.named_parameters() if parameter.grad is not None}
+    finally:
+        for _, parameter in extractor:
+            parameter.requires_grad = False
+            parameter.grad = None
+    reference_loss, _, reference = oracle.training_step(
+        training_case["audio"], training_case["lengths"], fixture["labels"], fixture["label_lengths"], fixture["language_ids"], freeze_feature_encoder=False
+    )
+    oracle.trainable_parameters(True)  # freeze it again for the other tests
+    assert abs(float(loss) - float(reference_loss)) <= 2e-2 * abs(float(reference_loss))
+    worst = {}
+    for name, _ in extractor:
+        assert name in gradients, f"no gradient for {name}"
+        assert torch.isfinite(gradients[name]).all(), name
+        worst[name] = norm_err(gradients[name], reference[name])
+    ranked = sorted(worst.items(), key=lambda item: -item[1])
+    print("unfrozen feature extractor, worst gradient deviations: " + ", ".join(f"{k.split('feature_extractor.')[-1]}={v:.3e}" for k, v in ranked[:6]))
+    assert ranked[0][1] < GRAD_TOL, ranked[:10]
+    # the rest of the model still gets the gradients it got with the frozen extractor
+    for name in ("_acoustic_model._model.encoder.layers.0.attention.out_proj.weight", "_acoustic_model._model.feature_projection.projection.weight"):
+        assert norm_err(gradients[name], reference[name]) < GRAD_TOL, name
+
+
 def test_frozen_encoder_trains_heads_only(training_case):
     fixture, model = training_case["fixture"], training_case["model"]
     if training_case["name"] != "hierarchical_2layer":
