@@ -149,6 +149,7 @@ _SIGNATURES = {
     "aph_softmax_backward_cols": [_P, _I64, _P, _I64, _I64, _P, _P, _P, _I32, _I32, _P, _I64, _P],
     "aph_multi_tensor_sumsq": [_P, _P, _I32, _P, _P],
     "aph_multi_tensor_scale": [_P, _P, _I32, _P, _F, _P],
+    "aph_multi_tensor_sgd": [_P, _P, _P, _I32, _F, _F, _F, _I32, _P, _F, _P],
     "aph_multi_tensor_adam": [_P, _P, _P, _I32, _F, _F, _F, _F, _F, _I64, _P, _F, _P],
     "aph_conv0_raw_bf16": [_P, _P, _P, _I32, _I32, _P, _P, _P, _P],
     "aph_ln_gelu_backward_512": [_P, _P, _I64, _I64, _P, _P, c_float, _P, _P, _P, _P, _P],

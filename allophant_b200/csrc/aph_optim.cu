@@ -123,6 +123,34 @@ __global__ void __launch_bounds__(kMtBlock) mt_adam_kernel(const __grid_constant
   }
 }
 
+// torch.optim.SGD (dampening 0, no Nesterov): g += wd * p; buf = first ? g : momentum * buf + g; p -= lr * (momentum ? buf : g)
+__global__ void __launch_bounds__(kMtBlock) mt_sgd_kernel(const __grid_constant__ MtPack pack, float lr, float momentum, float weight_decay,
+                                                          int first_step, float max_norm, const double* __restrict__ sumsq,
+                                                          const __grid_constant__ MtPack shadow) {
+  const float coef = clip_coefficient(sumsq, max_norm);
+  const int total_chunks = pack.chunk_start[pack.count];
+  for (int chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+    const int t = mt_find(pack, chunk);
+    float* p = static_cast<float*>(pack.p[t][0]);
+    const float* g = static_cast<const float*>(pack.p[t][1]);
+    float* buf = static_cast<float*>(pack.p[t][2]);
+    __nv_bfloat16* sh = static_cast<__nv_bfloat16*>(shadow.p[t][0]);
+    const long long base = static_cast<long long>(chunk - pack.chunk_start[t]) * kMtChunk;
+    const long long end = min(pack.n[t], base + kMtChunk);
+    for (long long i = base + threadIdx.x; i < end; i += kMtBlock) {
+      const float pi = p[i];
+      float gi = fmaf(weight_decay, pi, g[i] * coef);
+      if (buf != nullptr) {
+        gi = first_step ? gi : fmaf(momentum, buf[i], gi);
+        buf[i] = gi;
+      }
+      const float pn = fmaf(-lr, gi, pi);
+      p[i] = pn;
+      if (sh != nullptr) sh[i] = __float2bfloat16(pn);
+    }
+  }
+}
+
 static int build_pack(MtPack& pack, void* const* ptrs, int roles, const int64_t* sizes, int first, int count) {
   memset(&pack, 0, sizeof(pack));
   pack.count = count;
@@ -205,6 +233,26 @@ extern "C" int aph_multi_tensor_adam(void* const* tensors_host /*[n][4]: param, 
     build_pack(shadow, shadow_bf16_host, 1, sizes_host, first, count);
     if (chunks == 0) continue;
     mt_adam_kernel<<<mt_grid(chunks), kMtBlock, 0, stream>>>(pack, h, clip_sumsq, shadow);
+    ++launched;
+  }
+  APH_POST_LAUNCH(launched);
+  return APH_OK;
+}
+
+extern "C" int aph_multi_tensor_sgd(void* const* tensors_host /*[n][3]: param, grad, momentum buffer (or NULL)*/,
+                                    void* const* shadow_bf16_host /*[n] or NULL*/, const int64_t* sizes_host, int32_t n_tensors, float lr,
+                                    float momentum, float weight_decay, int32_t first_step, const double* clip_sumsq, float max_norm,
+                                    void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  APH_REQUIRE(tensors_host && sizes_host && n_tensors >= 0, "bad arguments");
+  int launched = 0;
+  for (int first = 0; first < n_tensors; first += kMtTensors) {
+    const int count = n_tensors - first < kMtTensors ? n_tensors - first : kMtTensors;
+    MtPack pack, shadow;
+    const int chunks = build_pack(pack, tensors_host, 3, sizes_host, first, count);
+    build_pack(shadow, shadow_bf16_host, 1, sizes_host, first, count);
+    if (chunks == 0) continue;
+    mt_sgd_kernel<<<mt_grid(chunks), kMtBlock, 0, stream>>>(pack, lr, momentum, weight_decay, first_step, clip_sumsq ? max_norm : 0.f, clip_sumsq, shadow);
     ++launched;
   }
   APH_POST_LAUNCH(launched);

@@ -184,7 +184,9 @@ class TransformerPlan:
     # ------------------------------------------------------------------ weights
     def _pack(self) -> None:
         model = self.model
-        version = tuple(p._version for p in model.parameters()) + (id(next(model.parameters())),)
+        from ..engine import weight_generation  # fused optimiser steps write parameters behind torch's version counters
+
+        version = tuple(p._version for p in model.parameters()) + (id(next(model.parameters())), weight_generation())
         if version == self._packed_version:
             return
         packed: Dict[str, Any] = {}

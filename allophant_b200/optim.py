@@ -73,7 +73,9 @@ class FusedAdam(torch.optim.Optimizer):
     def attach_model(self, model: Any) -> None:
         """Lets the Adam kernel write the bf16 GEMM operands of ``model`` (an ``Allophant``) itself: no re-pack pass
         after the step, and the encoder's launch lists (raw pointers into those operands) stay valid."""
-        packed = model._acoustic_model._packed
+        packed = getattr(model._acoustic_model, "_packed", None)
+        if packed is None:  # the from-scratch transformer encoder re-packs its (small) operands from the weight generation counter
+            return
         self.shadow.update(packed.shadow_map())
         self.post_step_hooks.append(packed.after_fused_step)
 
@@ -116,6 +118,60 @@ class FusedAdam(torch.optim.Optimizer):
                 )
         engine.bump_weight_generation()  # parameters changed behind torch's version counters: packed operands are stale
         for hook in self.post_step_hooks:  # ... except the ones this step refreshed itself
+            hook()
+        return loss
+
+
+class FusedSGD(torch.optim.Optimizer):
+    """``torch.optim.SGD(lr, momentum, weight_decay)`` (dampening 0, no Nesterov: what ``config.py:300-312`` builds) as one
+    multi-tensor launch, with the same clipping / bf16-shadow extras as ``FusedAdam``."""
+
+    def __init__(self, params, lr: float = 1e-3, momentum: float = 0.0, weight_decay: float = 0.0) -> None:
+        super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay))
+        self.shadow: Dict[Tensor, Tensor] = {}
+        self.post_step_hooks: List[Any] = []
+
+    attach_model = FusedAdam.attach_model
+
+    @torch.no_grad()
+    def step(self, closure=None, clip_norm: Optional[float] = None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        sumsq = None
+        if clip_norm is not None:
+            grads = [p.grad for group in self.param_groups for p in group["params"] if p.grad is not None]
+            if grads:
+                sumsq = sum_of_squares(_checked(grads))
+        for group in self.param_groups:
+            momentum = float(group["momentum"])
+            fresh, seasoned = [], []
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                state = self.state[p]
+                first = momentum != 0.0 and "momentum_buffer" not in state
+                if first:
+                    state["momentum_buffer"] = torch.empty_like(p, memory_format=torch.preserve_format)
+                (fresh if first else seasoned).append(p)
+            for first_step, params in ((1, fresh), (0, seasoned)):
+                if not params:
+                    continue
+                _checked(params)
+                _checked([p.grad for p in params])
+                rows = [[p, p.grad, self.state[p].get("momentum_buffer")] for p in params]
+                shadows = [self.shadow.get(p) for p in params]
+                check(
+                    lib.aph_multi_tensor_sgd(
+                        _pointer_table(rows), _pointer_table([[s] for s in shadows]), _sizes(params), len(params), float(group["lr"]), momentum,
+                        float(group["weight_decay"]), first_step, None if sumsq is None else sumsq.data_ptr(),
+                        0.0 if clip_norm is None else float(clip_norm), ops._stream(),
+                    ),  # fmt: skip
+                    "aph_multi_tensor_sgd",
+                )
+        engine.bump_weight_generation()
+        for hook in self.post_step_hooks:
             hook()
         return loss
 
@@ -185,7 +241,7 @@ class OptimizerWrapper:
         return self._optimizer
 
     def step(self, clip_norm: Optional[float] = None) -> None:
-        if clip_norm is not None and isinstance(self._optimizer, FusedAdam):
+        if clip_norm is not None and isinstance(self._optimizer, (FusedAdam, FusedSGD)):
             self._optimizer.step(clip_norm=clip_norm)
         else:
             self._optimizer.step()
@@ -217,3 +273,42 @@ def adam_from_config(parameters: Iterable[Tensor], model_size: int, *, model: An
     wrapper = OptimizerWrapper(adam, WarmupInfo(model_size))
     wrapper.add_schedulers(warmup_steps, constant_steps, factor)
     return wrapper
+
+
+def sgd_from_config(parameters: Iterable[Tensor], model_size: int, *, model: Any = None, learning_rate: float = 0.01, momentum: float = 0.0,
+                    l2_regularization: float = 0.0, warmup_steps: Optional[int] = None, constant_steps: int = 0, factor: float = 2) -> OptimizerWrapper:
+    """``SGD.get_optimizer`` (``config.py:300-312``) + ``OptimizerWrapper.add_schedulers``."""
+    sgd = FusedSGD(parameters, learning_rate, momentum, l2_regularization)
+    if model is not None:
+        sgd.attach_model(model)
+    wrapper = OptimizerWrapper(sgd, WarmupInfo(model_size))
+    wrapper.add_schedulers(warmup_steps, constant_steps, factor)
+    return wrapper
+
+
+def optimizer_from_config(architecture: Any, model: Any) -> OptimizerWrapper:
+    """``config.nn.optimizer.get_optimizer(model.parameters(), WarmupInfo(model.d_model))`` + ``add_schedulers(config.nn.lr_schedule)``
+    (``estimator.py:982-983``, ``config.py:300-335``) for an ``allophant_b200.config.Architecture``: ``algorithm`` "adam" or
+    "sgd", the warm-up schedule when ``lr_schedule`` is of type "warmup"."""
+    options = dict(architecture.optimizer or {})
+    algorithm = options.pop("algorithm", "adam")
+    schedule = dict(architecture.lr_schedule or {})
+    if schedule and schedule.get("type", "warmup") != "warmup":
+        raise ValueError(f"Unsupported learning rate schedule: {schedule.get('type')!r}")
+    schedule_options = dict(
+        warmup_steps=schedule.get("warmup_steps") if schedule else None,
+        constant_steps=schedule.get("constant_steps", 0),
+        factor=schedule.get("factor", 2),
+    )
+    parameters = [parameter for parameter in model.parameters() if parameter.requires_grad]
+    if algorithm == "adam":
+        return adam_from_config(
+            parameters, model.d_model, model=model, learning_rate=options.get("learning_rate", 0.01), beta_1=options.get("beta_1", 0.9),
+            beta_2=options.get("beta_2", 0.98), l2_regularization=options.get("l2_regularization", 0.0), **schedule_options,
+        )  # fmt: skip
+    if algorithm == "sgd":
+        return sgd_from_config(
+            parameters, model.d_model, model=model, learning_rate=options["learning_rate"], momentum=options.get("momentum", 0.0),
+            l2_regularization=options.get("l2_regularization", 0.0), **schedule_options,
+        )  # fmt: skip
+    raise ValueError(f"Unknown optimizer algorithm: {algorithm!r}")

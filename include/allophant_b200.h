@@ -413,6 +413,11 @@ int aph_multi_tensor_adam(void* const* tensors_host, void* const* shadow_bf16_ho
                           const int64_t* sizes_host, int32_t n_tensors, float lr, float beta1,
                           float beta2, float eps, float weight_decay, int64_t step,
                           const double* clip_sumsq, float max_norm, void* stream);
+/* torch.optim.SGD(lr, momentum, weight_decay; dampening 0, no Nesterov) (config.py:300-312), same multi-tensor form:
+ * tensors_host [n][3] = param, grad, momentum buffer (NULL without momentum); first_step: buffers are initialised. */
+int aph_multi_tensor_sgd(void* const* tensors_host, void* const* shadow_bf16_host, const int64_t* sizes_host,
+                         int32_t n_tensors, float lr, float momentum, float weight_decay, int32_t first_step,
+                         const double* clip_sumsq, float max_norm, void* stream);
 
 /* ---- edit distance (host) --------------------------------------------------------- */
 /* Batched replacement of the Rust extension `allophant.phonemes` (src/edit_distance.rs):

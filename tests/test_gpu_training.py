@@ -483,3 +483,27 @@ def test_training_loop_with_fused_optimizer_reduces_the_loss(training_case):
         assert torch.equal(packed.layers[0]["bqkv"][:1024], layer0.attention.q_proj.bias.detach())
     finally:
         model.load_state_dict(saved)
+
+
+@pytest.mark.parametrize("momentum,weight_decay,clip", [(0.0, 0.0, None), (0.9, 1e-3, None), (0.9, 0.0, 0.5)])
+def test_fused_sgd_matches_torch(momentum, weight_decay, clip):
+    """FusedSGD (config.py:300-312: torch.optim.SGD(lr, momentum, weight_decay)) against torch on the same gradients, three
+    steps, more tensors than one launch holds; clipping folded into the step like ``clip_grad_norm_`` + ``step``."""
+    from allophant_b200 import optim
+
+    torch.manual_seed(0)
+    shapes = [(33,), (128, 64), (7, 5, 3)] * 20  # 60 tensors: two launches
+    ours = [torch.nn.Parameter(torch.randn(shape, device=DEV)) for shape in shapes]
+    theirs = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    fused = optim.FusedSGD(ours, lr=0.05, momentum=momentum, weight_decay=weight_decay)
+    reference = torch.optim.SGD(theirs, lr=0.05, momentum=momentum, weight_decay=weight_decay)
+    for step in range(3):
+        for a, b in zip(ours, theirs):
+            gradient = torch.randn_like(a) * (step + 1)
+            a.grad, b.grad = gradient.clone(), gradient.clone()
+        if clip is not None:
+            torch.nn.utils.clip_grad_norm_(theirs, clip)
+        fused.step(clip_norm=clip)
+        reference.step()
+        for a, b in zip(ours, theirs):
+            assert torch.allclose(a, b, rtol=2e-6, atol=2e-6)
