@@ -477,11 +477,11 @@ class EncoderPlan:
         )
         if self.training:
             steps.append(self._regularise_encoder_input)
-        if not cfg.do_stable_layer_norm:
-            raise NotImplementedError("post-LN wav2vec2 encoders (do_stable_layer_norm=False) are not implemented yet")
-
         heads = cfg.num_attention_heads
         FF = cfg.intermediate_size
+        if not cfg.do_stable_layer_norm:
+            self._build_post_ln(steps, heads, FF)
+            return
         for index, lw in enumerate(p.layers):
             if self.training:
                 sv = self.saved[index]
@@ -525,6 +525,46 @@ class EncoderPlan:
         gf, bf = p.final_ln
         steps.append(lambda: ops.layernorm_rows(self.h_last, M, H, H, gf, bf, eps, out_bf16=self.x, ld_bf16=self.ldx))
         steps.append(lambda: self._keep_hidden(len(p.layers), self.h_last))
+
+    def _build_post_ln(self, steps: List[Step], heads: int, FF: int) -> None:
+        """The post-LN encoder ordering of wav2vec2-base style checkpoints (``do_stable_layer_norm = False``; HF
+        ``Wav2Vec2Encoder`` / ``Wav2Vec2EncoderLayer``): the encoder LayerNorm follows the positional convolution, every layer is
+        ``h = LN(h + attention(h)); h = final_LN(h + FFN(h))`` and hidden state ``i`` is the input of layer ``i``.  Inference
+        only: the fp32 stream is normalised in place and the same kernel writes the bf16 GEMM operand."""
+        if self.training:
+            raise NotImplementedError("training of post-LN wav2vec2 encoders (do_stable_layer_norm=False) is not implemented")
+        p, cfg = self.packed, self.cfg
+        N, M, H, eps = self.n_utt, self.rows, cfg.hidden_size, cfg.layer_norm_eps
+        hidden, ln16 = self.hidden, self.ln_out
+        n_layers = len(p.layers)
+
+        def normalise(gamma: Tensor, beta: Tensor, target: Tensor, ld_target: int) -> None:
+            """fp32 stream normalised in place + the bf16 copy the next GEMM (or the classifiers) read"""
+            if H in (512, 1024):
+                ops.layernorm_rows(hidden, M, H, H, gamma, beta, eps, out_f32=hidden, ld_f32=H, out_bf16=target, ld_bf16=ld_target)
+            else:
+                ops.layernorm_any(hidden, H, M, H, gamma, beta, eps, out_f32=hidden, ld_f32=H, out_bf16=target, ld_bf16=ld_target)
+
+        ge, be = p.final_ln  # encoder.layer_norm
+        first_target, first_ld = (self.x, self.ldx) if n_layers == 0 else (ln16, H)
+        steps.append(lambda: normalise(ge, be, first_target, first_ld))
+        for index, lw in enumerate(p.layers):
+            steps.append(lambda index=index: self._keep_hidden(index, hidden))
+            span_start = len(steps)
+            steps.append(self._gemm(ops.make_qkv_args(ln16, lw["wqkv"], lw["bqkv"], self.q, self.k, self.v, rows=M, seq=self.seq, heads=heads)))
+            steps.append(lambda: ops.attention(self.q, self.k, self.v, self.ctx, self.att_lengths, N, heads, self.seq))
+            steps.append(self._gemm(ops.make_gemm_args(self.ctx, lw["wo"], a_rows=M, a_inner=H, a_row_stride=H, bias=lw["bo"], resid=hidden, ld_resid=H, out_f32=hidden, ld_f32=H)))
+            g1, b1 = lw["ln1"]
+            steps.append(lambda g1=g1, b1=b1: normalise(g1, b1, ln16, H))
+            steps.append(self._gemm(ops.make_gemm_args(ln16, lw["w1"], a_rows=M, a_inner=H, a_row_stride=H, bias=lw["b1"], gelu=True, out_bf16=self.ffn, ld_bf16=FF)))
+            steps.append(self._gemm(ops.make_gemm_args(self.ffn, lw["w2"], a_rows=M, a_inner=FF, a_row_stride=FF, bias=lw["b2"], resid=hidden, ld_resid=H, out_f32=hidden, ld_f32=H)))
+            g2, b2 = lw["ln2"]
+            last = index == n_layers - 1
+            target, ld_target = (self.x, self.ldx) if last else (ln16, H)  # the last hidden state is the classifier input OUTPUT
+            steps.append(lambda g2=g2, b2=b2, target=target, ld_target=ld_target: normalise(g2, b2, target, ld_target))
+            self._layer_spans.append((span_start, len(steps)))
+        self.h_last = hidden
+        steps.append(lambda: self._keep_hidden(n_layers, hidden))
 
     def _regularise_projection(self) -> None:
         """train() mode: dropout of the feature projection output (HF:431-433), then SpecAugment (HF

@@ -62,6 +62,11 @@ KNOWN_MODELS: Dict[str, Wav2Vec2EncoderConfig] = {
     "facebook/wav2vec2-xls-r-300m": Wav2Vec2EncoderConfig(),
     "facebook/wav2vec2-large-xlsr-53": Wav2Vec2EncoderConfig(mask_time_prob=0.075),
     "facebook/wav2vec2-xls-r-1b": Wav2Vec2EncoderConfig(hidden_size=1280, num_hidden_layers=48, intermediate_size=5120),
+    # post-LN encoder, GroupNorm feature extractor without conv biases, no attention mask (preprocessor: return_attention_mask
+    # false).  (wav2vec2-base has the same ordering but 48-channel positional-conv groups, which the tap GEMM does not cover.)
+    "facebook/wav2vec2-large": Wav2Vec2EncoderConfig(
+        feat_extract_norm="group", conv_bias=False, do_stable_layer_norm=False, mask_time_prob=0.05, return_attention_mask=False,
+    ),
 }
 
 

@@ -180,3 +180,33 @@ def test_estimator_checkpoint_roundtrip(case):
     for name in first.outputs:
         assert torch.equal(first.outputs[name], second.outputs[name]), name
     assert second.outputs["phoneme"].shape[-1] == 5
+
+
+def test_post_ln_group_norm_encoder_matches_oracle():
+    """wav2vec2-large style checkpoints (``do_stable_layer_norm = False``, GroupNorm feature extractor without conv biases):
+    the post-LN encoder ordering — LayerNorm after the positional convolution, ``h = LN(h + attention(h)); h = LN(h + FFN(h))`` —
+    against the Hugging Face model of that configuration (the oracle's encoder), hidden states and log-probabilities."""
+    from allophant_b200.dataset_processing import Batch
+
+    overrides = dict(num_hidden_layers=2, do_stable_layer_norm=False, feat_extract_norm="group", conv_bias=False)
+    spec = restatement.multitask_spec(n_train_phonemes=20, encoder_overrides=overrides, weight_seed=4)
+    oracle = restatement.OracleModel(spec)
+    assert not oracle.config.do_stable_layer_norm and oracle.config.feat_extract_norm == "group"
+    model, _ = helpers.cuda_model_for_spec(spec, oracle)
+    lengths = torch.tensor([16000, 9000, 12345])
+    audio = restatement.synthetic_audio(3, 16000, seed=5) * restatement.mask_sequence(lengths)
+    batch = Batch(audio.cuda(), lengths.cuda(), torch.zeros(3, dtype=torch.long).cuda())
+    hidden_ref, frames_ref = oracle.encode(audio, lengths)
+    with torch.inference_mode():
+        hidden, frames = model.acoustic_model(batch)
+        predictions = model.predict_log_probabilities(batch)
+    assert torch.equal(frames.cpu(), frames_ref) and len(hidden) == len(hidden_ref) == 3
+    for index, (ours, reference) in enumerate(zip(hidden, hidden_ref)):
+        error = _range_error(ours.float().cpu(), reference, frames_ref.tolist())
+        assert error < RANGE_TOL, f"hidden state {index}: {error:.3e} of range"
+    outputs, _ = oracle.predict(audio, lengths)
+    for name, reference in outputs.items():
+        error = _range_error(predictions.outputs[name].float().cpu(), reference, frames_ref.tolist())
+        assert error < RANGE_TOL, f"{name}: {error:.3e} of range"
+    with pytest.raises(NotImplementedError, match="post-LN"):  # the encoder's parameters require gradients: training plan
+        model(batch)
