@@ -281,7 +281,7 @@ class EncoderPlan:
         # pre-LayerNorm conv outputs and activations are kept per layer instead of ping-ponging through two buffers
         self.train_extractor = train_extractor
         if train_extractor and (not training or cfg.feat_extract_norm != "layer"):
-            raise NotImplementedError("feature-extractor training is built for training plans of the layer-norm variant (XLS-R, wav2vec2-large)")
+            raise NotImplementedError("feature-extractor training is built for training plans of the layer-norm variant (XLS-R, wav2vec2-large-xlsr-53)")
         self.generation = 0  # bumped by every run(): a backward pass checks that its activations are still there
         dev = packed.device
         assert dev is not None
