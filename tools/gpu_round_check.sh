@@ -9,3 +9,5 @@ timeout 600 python bench.py --workload train --skip-cpu-baseline > gpurun_out/fi
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/final_launches_predict.csv python bench.py --steps 1 --warmup 3 --skip-cpu-baseline > gpurun_out/final_launches.log 2>&1; echo "launch list rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_kernel -s 400 -c 8 -f -o gpurun_out/r01_gemm_final python bench.py --steps 1 --warmup 3 --skip-cpu-baseline > gpurun_out/final_ncu_gemm.log 2>&1; echo "ncu gemm rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_kernel -s 80 -c 2 -f -o gpurun_out/r01_attention_final python bench.py --steps 1 --warmup 3 --skip-cpu-baseline > gpurun_out/final_ncu_att.log 2>&1; echo "ncu att rc=$?"
+timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/final_bench_reference.json 2> gpurun_out/final_bench_reference.err; tail -c 600 gpurun_out/final_bench_reference.json
+timeout 300 python tools/bench_transformer.py 2>/dev/null | tail -1 > gpurun_out/final_bench_transformer.json; tail -c 300 gpurun_out/final_bench_transformer.json
