@@ -302,3 +302,46 @@ def test_classifiers_train_on_a_frozen_transformer(golden):
     loss = sum(value.float().square().mean() for value in outputs.outputs.values())
     loss.backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model._projection.parameters() if p.requires_grad)
+
+
+@pytest.mark.gpu
+def test_transformer_estimator_checkpoint_roundtrip():
+    """Estimator.save / Estimator.restore with a ``pre-ln-transformer`` acoustic model: the configuration (front ends, GLU
+    stack, transformer options) survives the checkpoint dict and the restored model predicts identically."""
+    import io
+
+    from allophant_b200.config import Config, PhonemeLayerType, TransformerAcousticModelConfig
+    from allophant_b200.dataset_processing import Batch
+    from allophant_b200.estimator import Estimator, attribute_graph_from_config
+    from allophant_b200.phonetic_features import PhoneticAttributeIndexer
+
+    config = Config.default()
+    config.nn.projection.phoneme_layer = PhonemeLayerType.SHARED
+    config.nn.acoustic_model = TransformerAcousticModelConfig.load(
+        dict(
+            type="pre-ln-transformer",
+            transformer=dict(feedforward_neurons=256, heads=4, activation="gelu", num_layers=2, dropout_rate=0.1),
+            frontend=dict(architecture="linear", neurons=128),
+            sequential_frontend={"layers": [dict(type="glu1d", out_channels=256, kernel=3, stride=2), dict(type="layer_norm", affine=True), dict(type="dropout", rate=0.1)]},
+            elementwise_affine=True,
+        )
+    )
+    names = [entry.name for entry in config.nn.projection.classes]
+    indexer = PhoneticAttributeIndexer.synthetic(80, names, training_inventory=50)
+    graph = attribute_graph_from_config(config, indexer)
+    estimator = Estimator.from_config(config, 40, 16000, graph, indexer, "cuda", load_pretrained_weights=False)
+    lengths = torch.tensor([120, 64])
+    features = torch.randn(2, 40, 120) * (torch.arange(120)[None, :] < lengths[:, None])[:, None, :]
+    batch = Batch(features.cuda(), lengths.cuda(), torch.zeros(2, dtype=torch.long).cuda())
+    tfi = indexer.composition_feature_matrix(["p3", "p7", "p11"]).cuda()
+    first = estimator.predict(batch, tfi)
+    buffer = io.BytesIO()
+    estimator.save(buffer, indexer)
+    buffer.seek(0)
+    restored, restored_indexer = Estimator.restore(buffer, "cuda")
+    assert isinstance(restored.model._acoustic_model, type(estimator.model._acoustic_model))
+    assert restored.config.nn.acoustic_model.dump() == config.nn.acoustic_model.dump()
+    second = restored.predict(batch, restored_indexer.composition_feature_matrix(["p3", "p7", "p11"]).cuda())
+    assert first.lengths.tolist() == second.lengths.tolist() == [61, 33]  # (L + 1 + 2 - 3) // 2 + 1
+    for name in first.outputs:
+        assert torch.equal(first.outputs[name], second.outputs[name]), name
