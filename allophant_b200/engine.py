@@ -222,6 +222,7 @@ class Stochastic:
     hidden_dropout: float = 0.0
     attention_dropout: float = 0.0
     feat_proj_dropout: float = 0.0
+    activation_dropout: float = 0.0
     layerdrop: float = 0.0
     mask_time_prob: float = 0.0
     mask_time_length: int = 10
@@ -235,12 +236,10 @@ class Stochastic:
 
     @classmethod
     def from_config(cls, cfg: Wav2Vec2EncoderConfig, seed: int) -> "Stochastic":
-        if cfg.activation_dropout > 0.0:
-            raise NotImplementedError("activation_dropout > 0 (dropout inside the feed-forward block) is not implemented")
         if cfg.mask_feature_prob > 0.0 and cfg.apply_spec_augment:
             raise NotImplementedError("SpecAugment along the feature axis (mask_feature_prob > 0) is not implemented")
         return cls(
-            seed, cfg.hidden_dropout, cfg.attention_dropout, cfg.feat_proj_dropout, cfg.layerdrop,
+            seed, cfg.hidden_dropout, cfg.attention_dropout, cfg.feat_proj_dropout, cfg.activation_dropout, cfg.layerdrop,
             cfg.mask_time_prob if cfg.apply_spec_augment else 0.0, cfg.mask_time_length, cfg.mask_time_min_masks,
         )  # fmt: skip
 
@@ -252,6 +251,10 @@ class Stochastic:
 
     def feed_forward_output(self, layer: int) -> ops.Dropout:
         return ops.Dropout.site(self.hidden_dropout, self.seed, 8 * layer + 2)
+
+    def activation(self, layer: int) -> ops.Dropout:
+        """``intermediate_dropout`` behind the feed-forward activation (HF:566-569, ``activation_dropout``)."""
+        return ops.Dropout.site(self.activation_dropout, self.seed, 8 * layer + 3)
 
     def feature_projection(self) -> ops.Dropout:
         return ops.Dropout.site(self.feat_proj_dropout, self.seed, self.SITE_FEATURE_PROJECTION)
@@ -364,7 +367,7 @@ class EncoderPlan:
         self.stoch: Optional[Stochastic] = None       # regularisation of the last run (None: eval()-mode arithmetic)
         self.skipped: List[bool] = [False] * len(packed.layers)  # LayerDrop decisions of the last run
         self._layer_spans: List[Tuple[int, int]] = []
-        self._drop_gemms: List[Tuple[Any, int, bool]] = []  # (GEMM args, layer, is feed-forward output)
+        self._drop_gemms: List[Tuple[Any, int, str]] = []  # (GEMM args, layer, "attention_output" | "feed_forward_output" | "activation")
 
         self._steps: List[Step] = []
         self._build()
@@ -509,18 +512,15 @@ class EncoderPlan:
             steps.append(self._gemm(out_args))
             g2, b2 = lw["ln2"]
             steps.append(lambda g2=g2, b2=b2, h_mid=h_mid, ln2=ln2: ops.layernorm_rows(h_mid, M, H, H, g2, b2, eps, out_bf16=ln2, ld_bf16=H))
-            steps.append(
-                self._gemm(
-                    ops.make_gemm_args(
-                        ln2, lw["w1"], a_rows=M, a_inner=H, a_row_stride=H, bias=lw["b1"], gelu=True, out_bf16=ffn, ld_bf16=FF, aux_bf16=pre, ld_aux=FF
-                    )
-                )
+            inner_args = ops.make_gemm_args(
+                ln2, lw["w1"], a_rows=M, a_inner=H, a_row_stride=H, bias=lw["b1"], gelu=True, out_bf16=ffn, ld_bf16=FF, aux_bf16=pre, ld_aux=FF
             )
+            steps.append(self._gemm(inner_args))
             ffn_args = ops.make_gemm_args(ffn, lw["w2"], a_rows=M, a_inner=FF, a_row_stride=FF, bias=lw["b2"], resid=h_mid, ld_resid=H, out_f32=h_out, ld_f32=H)
             steps.append(self._gemm(ffn_args))
             self._layer_spans.append((span_start, len(steps)))
             if self.training:
-                self._drop_gemms += [(out_args, index, False), (ffn_args, index, True)]
+                self._drop_gemms += [(out_args, index, "attention_output"), (ffn_args, index, "feed_forward_output"), (inner_args, index, "activation")]
         self.h_last = self.hs[len(p.layers)] if self.training else self.hidden
         gf, bf = p.final_ln
         steps.append(lambda: ops.layernorm_rows(self.h_last, M, H, H, gf, bf, eps, out_bf16=self.x, ld_bf16=self.ldx))
@@ -632,10 +632,8 @@ class EncoderPlan:
                 self.skipped = [bool(flag) for flag in stochastic.skip_layers]
             elif stochastic.layerdrop > 0.0:
                 self.skipped = (torch.rand(n_layers) < stochastic.layerdrop).tolist()  # HF:774-777, host RNG like HF
-        for args, layer, feed_forward in self._drop_gemms:
-            drop = ops.NO_DROPOUT
-            if stochastic is not None:
-                drop = stochastic.feed_forward_output(layer) if feed_forward else stochastic.attention_output(layer)
+        for args, layer, site in self._drop_gemms:
+            drop = ops.NO_DROPOUT if stochastic is None else getattr(stochastic, site)(layer)
             args.drop_threshold, args.drop_seed, args.drop_scale = drop.threshold, drop.seed, drop.scale
         ops.frame_lengths(lengths, self.kernels_dev, self.strides_dev, self.frames32, frames64)
         if self.use_lengths:
@@ -771,8 +769,11 @@ class EncoderPlan:
                 continue
             # ---- feed forward: h_out = h_mid + dropout(W2 gelu(W1 LN2(h_mid) + b1) + b2)
             dropped = branch_gradient(st.feed_forward_output(index) if st else ops.NO_DROPOUT)
-            ops.run_gemm(ops.make_dgrad_args(dh16, lw["w2"], rows=M, ld_dy=H, k=H, n=FF, ld_w=FF, gelu_bwd=sv["pre"], ld_gelu_bwd=FF,
-                                             out_bf16=self.d_ff, ld_bf16=FF))  # fmt: skip
+            args = ops.make_dgrad_args(dh16, lw["w2"], rows=M, ld_dy=H, k=H, n=FF, ld_w=FF, gelu_bwd=sv["pre"], ld_gelu_bwd=FF,
+                                       out_bf16=self.d_ff, ld_bf16=FF)  # fmt: skip
+            inner = st.activation(index) if st else ops.NO_DROPOUT  # the mask of the dropout behind the activation
+            args.drop_threshold, args.drop_seed, args.drop_scale = inner.threshold, inner.seed, inner.scale
+            ops.run_gemm(args)
             if need_encoder:
                 wgrad(g["feed_forward.output_dense.weight"], dh16, H, H, sv["act"], FF, FF)
                 if dropped:

@@ -321,7 +321,7 @@ class OracleModel:
     def explicit_regularisation(self, masks: Dict[str, object]):
         """Runs the eval()-mode HF encoder with the train()-mode ops applied through EXPLICIT multiplicative masks:
         ``feature_projection`` / ``encoder_input`` / ``attention_output.<l>`` / ``feed_forward_output.<l>``: fp32
-        ``[N, T', H]`` (keep / (1-p) or 0), ``attention.<l>``: ``[N, heads, T', T']``, ``skip``: LayerDrop decisions
+        ``[N, T', H]`` (keep / (1-p) or 0), ``activation.<l>``: ``[N, T', FF]`` (``activation_dropout``), ``attention.<l>``: ``[N, heads, T', T']``, ``skip``: LayerDrop decisions
         (HF modeling_wav2vec2.py:431-433, 766, 774-786, 458, 643, 572); ``spec`` (bool ``[N, T']``) is passed to the model as
         ``mask_time_indices``."""
         from transformers.models.wav2vec2 import modeling_wav2vec2 as hf
@@ -338,6 +338,7 @@ class OracleModel:
         for index, layer in enumerate(self.encoder.encoder.layers):
             scale_output(layer.dropout, f"attention_output.{index}")
             scale_output(layer.feed_forward.output_dropout, f"feed_forward_output.{index}")
+            scale_output(layer.feed_forward.intermediate_dropout, f"activation.{index}")
             layer.attention._oracle_index = index
             if index < len(skip) and skip[index]:
                 handles.append(layer.register_forward_hook(lambda _m, args, _out: (args[0],)))

@@ -139,7 +139,7 @@ def keep_mask(dropout, rows: int, cols: int) -> torch.Tensor:
     return torch.from_numpy((half >= dropout.threshold).astype(np.float32) * np.float32(dropout.scale))
 
 
-def regularisation_masks(stochastic, n_utt: int, seq: int, hidden: int, heads: int, n_layers: int, skipped, spec_mask=None):
+def regularisation_masks(stochastic, n_utt: int, seq: int, hidden: int, heads: int, n_layers: int, skipped, spec_mask=None, intermediate: int = 0):
     """The explicit masks ``oracle.restatement.OracleModel.explicit_regularisation`` takes, equal to what the CUDA
     kernels derive from ``stochastic`` (an ``allophant_b200.engine.Stochastic``)."""
     rows = n_utt * seq
@@ -152,6 +152,8 @@ def regularisation_masks(stochastic, n_utt: int, seq: int, hidden: int, heads: i
         masks[f"attention.{layer}"] = keep_mask(stochastic.attention(layer), n_utt * heads * seq, seq).view(n_utt, heads, seq, seq)
         masks[f"attention_output.{layer}"] = keep_mask(stochastic.attention_output(layer), rows, hidden).view(n_utt, seq, hidden)
         masks[f"feed_forward_output.{layer}"] = keep_mask(stochastic.feed_forward_output(layer), rows, hidden).view(n_utt, seq, hidden)
+        if intermediate and stochastic.activation(layer).threshold:
+            masks[f"activation.{layer}"] = keep_mask(stochastic.activation(layer), rows, intermediate).view(n_utt, seq, intermediate)
     if spec_mask is not None:
         masks["spec"] = spec_mask.view(n_utt, seq).bool()
     return masks

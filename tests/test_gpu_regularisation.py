@@ -260,3 +260,50 @@ def test_train_mode_is_seeded_and_eval_mode_is_untouched(case):
         a = model(case["batch"], predict=True)
         b = model(case["batch"], predict=True)
     assert all(torch.equal(a.outputs[name], b.outputs[name]) for name in a.outputs)
+
+
+def test_activation_dropout_matches_oracle_with_the_same_masks():
+    """``activation_dropout > 0`` (HF ``intermediate_dropout`` behind the feed-forward GELU; 0 in the XLS-R configuration): the
+    FFN1 epilogue drops the activation, the FFN2 data-gradient epilogue applies the same mask.  Only this site is enabled."""
+    from allophant_b200.dataset_processing import Batch
+
+    fixture = helpers.load_golden("training_multitask_2layer")
+    case_config = dict(fixture["case_config"])
+    case_config["spec"] = dict(case_config["spec"])
+    overrides = dict(case_config["spec"].get("encoder_overrides") or {})
+    overrides.update(activation_dropout=0.25, hidden_dropout=0.0, attention_dropout=0.0, feat_proj_dropout=0.0, layerdrop=0.0, mask_time_prob=0.0)
+    case_config["spec"]["encoder_overrides"] = overrides
+    spec = helpers.spec_for_case(case_config)
+    oracle = restatement.OracleModel(spec)
+    model, _ = helpers.cuda_model_for_spec(spec, oracle)
+    model._projection._acoustic_model_dropout.p = 0.0
+    lengths = fixture["lengths"]
+    audio = restatement.synthetic_audio(len(lengths), int(lengths.max()), seed=0) * restatement.mask_sequence(lengths)
+    batch = Batch(audio.cuda(), lengths.cuda(), fixture["language_ids"].cuda())
+    model.train()
+    try:
+        torch.manual_seed(3)
+        loss, _, _ = _training_step(model, batch, fixture)
+        state = model._heads.last_regularisation
+    finally:
+        model.eval()
+    stochastic, plan = state["stochastic"], state["plan"]
+    assert stochastic.activation_dropout == 0.25 and stochastic.activation(0).threshold == 16384
+    cfg = plan.cfg
+    masks = helpers.regularisation_masks(
+        stochastic, plan.n_utt, plan.seq, cfg.hidden_size, cfg.num_attention_heads, cfg.num_hidden_layers, plan.skipped, None, cfg.intermediate_size
+    )
+    assert "activation.0" in masks and abs(float((masks["activation.1"] == 0).float().mean()) - 0.25) < 0.01
+    reference_loss, _, reference = oracle.training_step(
+        audio, lengths, fixture["labels"], fixture["label_lengths"], fixture["language_ids"], regularisation=masks
+    )
+    assert abs(float(loss) - float(reference_loss)) <= 2e-2 * abs(float(reference_loss))
+    assert abs(float(reference_loss) - fixture["loss"]) > 1e-4 * abs(fixture["loss"])
+    worst = {}
+    for name, parameter in model.named_parameters():
+        if parameter.grad is None or name not in reference or float(reference[name].norm()) < 1e-7:
+            continue
+        worst[name] = norm_err(parameter.grad, reference[name])
+    ranked = sorted(worst.items(), key=lambda item: -item[1])
+    print("activation dropout: worst " + ", ".join(f"{k.split('._model.')[-1]}={v:.3e}" for k, v in ranked[:4]))
+    assert ranked[0][1] < TRAIN_MODE_TOL, ranked[:8]
