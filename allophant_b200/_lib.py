@@ -114,6 +114,7 @@ _SIGNATURES = {
     "aph_dropout_2d": [_P, _I64, _I64, _I32, _U32, _U32, c_float, _P, _P, _P, _I64, _P, _I64, _P],
     "aph_dropout_bf16_2d": [_P, _I64, _I64, _I32, _U32, _U32, c_float, _P],
     "aph_spec_augment_mask": [_P, _I32, _I32, c_float, _I32, _I32, _U32, _P, _P],
+    "aph_mask_columns": [_P, _I64, _I32, _I32, _I32, _P, _P, _I64, _P],
     "aph_masked_rows_backward": [_P, _I64, _I64, _I32, _P, _P, _P],
     "aph_debug_set_progress": [_P],
     "aph_debug_set_timeline": [_P],

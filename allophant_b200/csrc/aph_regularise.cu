@@ -107,6 +107,21 @@ __global__ void __launch_bounds__(128) spec_augment_mask_kernel(const int* __res
   }
 }
 
+// SpecAugment along the feature axis (HF _mask_hidden_states, mask_feature_prob): x[n][t][c] = 0 where col_mask[n][c];
+// fp32 in place + the optional bf16 copy.  The same call on a gradient is the backward pass.
+__global__ void __launch_bounds__(256) mask_columns_kernel(float* x, long long ld, long long rows, int seq, int cols,
+                                                           const uint8_t* __restrict__ col_mask, __nv_bfloat16* x_bf16, long long ld_bf16) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const long long row = i / cols;
+    const int c = static_cast<int>(i - row * cols);
+    if (col_mask[(row / seq) * cols + c]) {
+      x[row * ld + c] = 0.f;
+      if (x_bf16 != nullptr) x_bf16[row * ld_bf16 + c] = __float2bfloat16(0.f);
+    }
+  }
+}
+
 // backward of the masked rows: d_fill[col] += sum over masked rows of d[row][col]; those rows of d become 0.
 __global__ void __launch_bounds__(256) masked_rows_backward_kernel(float* d, long long ld, long long rows, int cols,
                                                                    const uint8_t* __restrict__ row_mask, float* __restrict__ d_fill) {
@@ -184,6 +199,17 @@ extern "C" int aph_masked_rows_backward(float* d, int64_t ld, int64_t rows, int3
   APH_CUDA_CHECK(cudaMemsetAsync(d_fill, 0, sizeof(float) * static_cast<size_t>(cols), stream));
   dim3 grid(static_cast<unsigned>((cols + 255) / 256), static_cast<unsigned>(rows < 64 ? 1 : (rows / 64 > 296 ? 296 : rows / 64)));
   masked_rows_backward_kernel<<<grid, 256, 0, stream>>>(d, ld, rows, cols, row_mask, d_fill);
+  APH_POST_LAUNCH(1);
+  return APH_OK;
+}
+
+extern "C" int aph_mask_columns(float* x, int64_t ld, int32_t n_utt, int32_t seq, int32_t cols, const uint8_t* col_mask, void* x_bf16,
+                                int64_t ld_bf16, void* stream_) {
+  APH_REQUIRE(x && col_mask && n_utt >= 0 && seq > 0 && cols > 0, "mask_columns: bad arguments");
+  if (n_utt == 0) return APH_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long rows = static_cast<long long>(n_utt) * seq;
+  mask_columns_kernel<<<grid_for(rows * cols), 256, 0, stream>>>(x, ld, rows, seq, cols, col_mask, static_cast<__nv_bfloat16*>(x_bf16), ld_bf16);
   APH_POST_LAUNCH(1);
   return APH_OK;
 }

@@ -227,20 +227,23 @@ class Stochastic:
     mask_time_prob: float = 0.0
     mask_time_length: int = 10
     mask_time_min_masks: int = 2
+    mask_feature_prob: float = 0.0
+    mask_feature_length: int = 10
+    mask_feature_min_masks: int = 0
     skip_layers: Optional[Sequence[bool]] = None  # explicit LayerDrop decisions (tests); None = draw from torch's CPU RNG
 
     SITE_FEATURE_PROJECTION = 1_000_000
     SITE_ENCODER_INPUT = 1_000_001
     SITE_SPEC_AUGMENT = 1_000_002
+    SITE_SPEC_FEATURE = 1_000_003
     SITE_CLASSIFIER_INPUT = 2_000_000  # + hidden-state index (acoustic_model.py:486-488)
 
     @classmethod
     def from_config(cls, cfg: Wav2Vec2EncoderConfig, seed: int) -> "Stochastic":
-        if cfg.mask_feature_prob > 0.0 and cfg.apply_spec_augment:
-            raise NotImplementedError("SpecAugment along the feature axis (mask_feature_prob > 0) is not implemented")
         return cls(
             seed, cfg.hidden_dropout, cfg.attention_dropout, cfg.feat_proj_dropout, cfg.activation_dropout, cfg.layerdrop,
             cfg.mask_time_prob if cfg.apply_spec_augment else 0.0, cfg.mask_time_length, cfg.mask_time_min_masks,
+            cfg.mask_feature_prob if cfg.apply_spec_augment else 0.0, cfg.mask_feature_length, cfg.mask_feature_min_masks,
         )  # fmt: skip
 
     def attention(self, layer: int) -> ops.Dropout:
@@ -364,6 +367,7 @@ class EncoderPlan:
                 self.conv_pre = [z(n_utt * length * 512) for length in L]
                 self.conv_post = [z(n_utt * length * 512) for length in L]
             self.spec_mask = z(M, dtype=torch.uint8)  # SpecAugment time mask of the last train()-mode run
+            self.feature_mask = z(n_utt, H, dtype=torch.uint8)  # ... and its feature-axis mask (mask_feature_prob)
         self.stoch: Optional[Stochastic] = None       # regularisation of the last run (None: eval()-mode arithmetic)
         self.skipped: List[bool] = [False] * len(packed.layers)  # LayerDrop decisions of the last run
         self._layer_spans: List[Tuple[int, int]] = []
@@ -583,11 +587,16 @@ class EncoderPlan:
             )  # fmt: skip
             mask = self.spec_mask
         drop = st.feature_projection()
-        if mask is None and drop.threshold == 0:
-            return
-        fill = embed.detach().float().contiguous() if mask is not None else None
-        ops.dropout_2d(self.hidden_fp, H, M, H, drop, out_f32=self.hidden_fp, ld_f32=H, out_bf16=self.hidden_bf16, ld_bf16=H, row_mask=mask, row_fill=fill)
+        if mask is not None or drop.threshold != 0:
+            fill = embed.detach().float().contiguous() if mask is not None else None
+            ops.dropout_2d(self.hidden_fp, H, M, H, drop, out_f32=self.hidden_fp, ld_f32=H, out_bf16=self.hidden_bf16, ld_bf16=H, row_mask=mask, row_fill=fill)
         self.spec_active = mask is not None
+        self.feature_active = st.mask_feature_prob > 0.0
+        if self.feature_active:  # HF _mask_hidden_states: spans along the hidden axis are zeroed for every frame of an utterance
+            full = torch.full((self.n_utt,), H, device=self.hidden_fp.device, dtype=torch.int32)
+            ops.spec_augment_mask(full, H, st.mask_feature_prob, st.mask_feature_length, st.mask_feature_min_masks,
+                                  ops.mix_seed(st.seed, Stochastic.SITE_SPEC_FEATURE), self.feature_mask)  # fmt: skip
+            ops.mask_columns(self.hidden_fp, H, self.n_utt, self.seq, H, self.feature_mask, self.hidden_bf16, H)
 
     def _regularise_encoder_input(self) -> None:
         """train() mode: ``hidden_states = self.dropout(hidden_states + position_embeddings)`` (HF:765-766)."""
@@ -625,6 +634,7 @@ class EncoderPlan:
             raise RuntimeError("train()-mode regularisation needs a training plan")
         self.stoch = stochastic
         self.spec_active = False
+        self.feature_active = False
         n_layers = len(p.layers)
         self.skipped = [False] * n_layers
         if stochastic is not None:
@@ -851,6 +861,8 @@ class EncoderPlan:
             if st is not None:
                 # SpecAugment: masked frames were replaced by masked_spec_embed (its gradient: their sum), then the
                 # feature projection dropout; both are functions of (seed, row, column) only
+                if self.feature_active:
+                    ops.mask_columns(dh, H, N, seq, H, self.feature_mask)
                 if self.spec_active:
                     flat, g = group([("masked_spec_embed", (H,))])
                     ops.masked_rows_backward(dh, H, M, H, self.spec_mask, g["masked_spec_embed"])

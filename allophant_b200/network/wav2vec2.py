@@ -40,6 +40,8 @@ class Wav2Vec2EncoderConfig:
     mask_time_length: int = 10
     mask_time_min_masks: int = 2
     mask_feature_prob: float = 0.0
+    mask_feature_length: int = 10
+    mask_feature_min_masks: int = 0
     hidden_dropout: float = 0.1
     attention_dropout: float = 0.1
     feat_proj_dropout: float = 0.1

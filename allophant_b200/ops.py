@@ -592,6 +592,12 @@ def spec_augment_mask(frames32: Tensor, seq: int, mask_prob: float, mask_length:
     )
 
 
+def mask_columns(x: Tensor, ld: int, n_utt: int, seq: int, cols: int, col_mask: Tensor, x_bf16: Optional[Tensor] = None, ld_bf16: int = 0) -> None:
+    """``x[n, t, c] = 0`` where ``col_mask[n, c]`` (SpecAugment along the feature axis); fp32 in place + optional bf16 copy."""
+    _require_cuda(x, col_mask, x_bf16)
+    check(lib.aph_mask_columns(x.data_ptr(), ld, n_utt, seq, cols, col_mask.data_ptr(), _ptr(x_bf16), ld_bf16, _stream()), "aph_mask_columns")
+
+
 def masked_rows_backward(d: Tensor, ld: int, rows: int, cols: int, row_mask: Tensor, d_fill: Tensor) -> None:
     _require_cuda(d, row_mask, d_fill)
     check(lib.aph_masked_rows_backward(d.data_ptr(), ld, rows, cols, row_mask.data_ptr(), d_fill.data_ptr(), _stream()), "aph_masked_rows_backward")

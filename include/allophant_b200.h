@@ -180,6 +180,10 @@ int aph_dropout_bf16_2d(void* x_bf16, int64_t ld, int64_t rows, int32_t cols, ui
  * without replacement inside each utterance's frames[i] valid frames. */
 int aph_spec_augment_mask(const int32_t* frames, int32_t n_utt, int32_t seq, float mask_prob, int32_t mask_length,
                           int32_t min_masks, uint32_t seed, uint8_t* mask, void* stream);
+/* SpecAugment along the feature axis (HF mask_feature_prob): x[n][t][c] = 0 where col_mask[n][c] (uint8 [n_utt][cols], made
+ * by aph_spec_augment_mask with seq = cols); fp32 in place + optional bf16 copy.  The same call on a gradient is the backward. */
+int aph_mask_columns(float* x, int64_t ld, int32_t n_utt, int32_t seq, int32_t cols, const uint8_t* col_mask,
+                     void* x_bf16, int64_t ld_bf16, void* stream);
 /* backward of the row replacement: d_fill[col] = sum of d over flagged rows; flagged rows of d are zeroed */
 int aph_masked_rows_backward(float* d, int64_t ld, int64_t rows, int32_t cols, const uint8_t* row_mask,
                              float* d_fill, void* stream);

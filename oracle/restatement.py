@@ -343,6 +343,14 @@ class OracleModel:
             if index < len(skip) and skip[index]:
                 handles.append(layer.register_forward_hook(lambda _m, args, _out: (args[0],)))
         original, implementation = hf.eager_attention_forward, self.encoder.config._attn_implementation
+        mask_hidden_states = self.encoder._mask_hidden_states
+        if "spec_feature" in masks:  # HF zeroes the feature-axis spans after the time mask (bool [N, H])
+
+            def masked(hidden_states, *args, **kwargs):
+                hidden_states = mask_hidden_states(hidden_states, *args, **kwargs)
+                return hidden_states * (~masks["spec_feature"])[:, None, :].to(hidden_states.dtype)
+
+            self.encoder._mask_hidden_states = masked
 
         def attention(module, query, key, value, attention_mask, scaling=None, dropout=0.0, **kwargs):
             weights = torch.matmul(query, key.transpose(2, 3)) * (query.size(-1) ** -0.5 if scaling is None else scaling)
@@ -361,6 +369,8 @@ class OracleModel:
         finally:
             hf.eager_attention_forward = original
             self.encoder.config._attn_implementation = implementation
+            if "spec_feature" in masks:
+                del self.encoder._mask_hidden_states  # back to the class's method
             for handle in handles:
                 handle.remove()
 

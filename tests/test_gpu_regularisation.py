@@ -307,3 +307,53 @@ def test_activation_dropout_matches_oracle_with_the_same_masks():
     ranked = sorted(worst.items(), key=lambda item: -item[1])
     print("activation dropout: worst " + ", ".join(f"{k.split('._model.')[-1]}={v:.3e}" for k, v in ranked[:4]))
     assert ranked[0][1] < TRAIN_MODE_TOL, ranked[:8]
+
+
+def test_feature_axis_spec_augment_matches_oracle_with_the_same_masks():
+    """``mask_feature_prob > 0`` (HF ``_mask_hidden_states``: spans along the hidden axis zeroed for every frame of an
+    utterance, after the time mask): forward and gradients against the oracle fed with the masks the kernels drew."""
+    from allophant_b200.dataset_processing import Batch
+
+    fixture = helpers.load_golden("training_multitask_2layer")
+    case_config = dict(fixture["case_config"])
+    case_config["spec"] = dict(case_config["spec"])
+    overrides = dict(case_config["spec"].get("encoder_overrides") or {})
+    overrides.update(mask_feature_prob=0.1, mask_feature_length=10, hidden_dropout=0.0, attention_dropout=0.0, feat_proj_dropout=0.0, layerdrop=0.0)
+    case_config["spec"]["encoder_overrides"] = overrides
+    spec = helpers.spec_for_case(case_config)
+    oracle = restatement.OracleModel(spec)
+    model, _ = helpers.cuda_model_for_spec(spec, oracle)
+    model._projection._acoustic_model_dropout.p = 0.0
+    lengths = fixture["lengths"]
+    audio = restatement.synthetic_audio(len(lengths), int(lengths.max()), seed=0) * restatement.mask_sequence(lengths)
+    batch = Batch(audio.cuda(), lengths.cuda(), fixture["language_ids"].cuda())
+    model.train()
+    try:
+        torch.manual_seed(9)
+        loss, _, _ = _training_step(model, batch, fixture)
+        state = model._heads.last_regularisation
+    finally:
+        model.eval()
+    stochastic, plan = state["stochastic"], state["plan"]
+    assert plan.feature_active and plan.spec_active and stochastic.mask_feature_prob == 0.1
+    cfg = plan.cfg
+    feature_mask = plan.feature_mask.cpu().bool()
+    per_utterance = feature_mask.sum(1)
+    assert feature_mask.shape == (plan.n_utt, cfg.hidden_size) and int(per_utterance.min()) >= 10 and int(per_utterance.max()) <= 110
+    masks = helpers.regularisation_masks(
+        stochastic, plan.n_utt, plan.seq, cfg.hidden_size, cfg.num_attention_heads, cfg.num_hidden_layers, plan.skipped, plan.spec_mask.cpu()
+    )
+    masks["spec_feature"] = feature_mask
+    reference_loss, _, reference = oracle.training_step(
+        audio, lengths, fixture["labels"], fixture["label_lengths"], fixture["language_ids"], regularisation=masks
+    )
+    assert abs(float(loss) - float(reference_loss)) <= 2e-2 * abs(float(reference_loss))
+    worst = {}
+    for name, parameter in model.named_parameters():
+        if parameter.grad is None or name not in reference or float(reference[name].norm()) < 1e-7:
+            continue
+        worst[name] = norm_err(parameter.grad, reference[name])
+    ranked = sorted(worst.items(), key=lambda item: -item[1])
+    print("feature-axis SpecAugment: worst " + ", ".join(f"{k.split('._model.')[-1]}={v:.3e}" for k, v in ranked[:4]))
+    assert "_acoustic_model._model.masked_spec_embed" in worst
+    assert ranked[0][1] < TRAIN_MODE_TOL, ranked[:8]
