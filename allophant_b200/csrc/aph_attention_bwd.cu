@@ -28,6 +28,14 @@ constexpr int kBwdTile = 128;
 constexpr int kBwdD = 64;
 constexpr int kBwdTileBytes = kBwdTile * kBwdD * 2;  // 16 KB
 
+// probabilities are recomputed as 2^(s - lse): the hardware approximation (relative error 2^-22) like in the forward kernel;
+// exp2f() adds range handling for denormal results that a probability rounded to bf16 never needs
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct AttBwdParams {
   __nv_bfloat16* dqkv;     // [N*T][3*heads*64]
   const float* lse2;       // [N*heads][T]
@@ -295,7 +303,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
           const int odd = (k0 + r) & 1;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float pr = exp2f(s[j] - lse_t[c0 + j]);
+            const float pr = ex2_fast(s[j] - lse_t[c0 + j]);
             const float keep = drop_keep(drop_hash(key_t[j], pair), odd, p.drop_threshold) ? p.drop_scale : 0.f;
             s[j] = pr * keep;
             dp[j] = pr * (keep * dp[j] - delta_t[c0 + j]);
@@ -303,7 +311,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
         } else if (key_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float pr = exp2f(s[j] - lse_t[c0 + j]);
+            const float pr = ex2_fast(s[j] - lse_t[c0 + j]);
             s[j] = pr;
             dp[j] = pr * (dp[j] - delta_t[c0 + j]);
           }
@@ -528,7 +536,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float pr = (key0 + c0 + i < len) ? exp2f(s[i] - lse) : 0.f;
+          const float pr = (key0 + c0 + i < len) ? ex2_fast(s[i] - lse) : 0.f;
           dp[i] = pr * (dp[i] - dl);
         }
         store_chunk_swizzled(ds_row, c0, sw, dp);
