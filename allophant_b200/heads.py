@@ -400,6 +400,7 @@ class HeadsRuntime:
             frames32=plan.frames32.clone(),
             n_utt=n_utt,
             seq=seq,
+            flat=out,  # the one buffer every head's log-probabilities are views of (Estimator._predict_graphed copies it)
         )
         return predictions
 

@@ -210,3 +210,46 @@ def test_post_ln_group_norm_encoder_matches_oracle():
         assert error < RANGE_TOL, f"{name}: {error:.3e} of range"
     with pytest.raises(NotImplementedError, match="post-LN"):  # the encoder's parameters require gradients: training plan
         model(batch)
+
+
+def test_cuda_graph_predict_equals_eager(case):
+    """``Estimator.predict(..., cuda_graph=True)``: the whole step replayed as one CUDA graph gives bit-identical
+    log-probabilities and hypotheses, for new inputs of the same shape, and notices weight changes."""
+    if case["name"] != "multitask_2layer":
+        pytest.skip("one architecture is enough")
+    from allophant_b200 import predictions as decoding
+    from allophant_b200.dataset_processing import Batch
+    from allophant_b200.estimator import Estimator
+
+    estimator = Estimator.__new__(Estimator)
+    estimator.model = case["model"]
+    tfi = case["fixture"]["target_feature_indices"]
+    tfi = None if tfi is None else tfi.cuda()
+    batch = case["batch"]
+    other = Batch(torch.flip(batch.audio_features, dims=(0,)).contiguous(), torch.flip(batch.lengths, dims=(0,)).contiguous(), batch.language_ids)
+    for current in (batch, other, batch):
+        eager = estimator.predict(current, tfi)
+        graphed = estimator.predict(current, tfi, cuda_graph=True)
+        assert torch.equal(eager.lengths, graphed.lengths)
+        for name, value in eager.outputs.items():
+            assert torch.equal(value, graphed.outputs[name]), name
+        first, second = decoding.decode_predictions(eager), decoding.decode_predictions(graphed)
+        for name in first:
+            assert [h[0].tokens.tolist() for h in first[name]] == [h[0].tokens.tolist() for h in second[name]], name
+    assert len(estimator._graphs) == 1
+    kept = graphed.outputs["phoneme"].clone()
+    estimator.predict(other, tfi, cuda_graph=True)  # results are copies: an earlier result does not change under a later replay
+    assert torch.equal(kept, graphed.outputs["phoneme"])
+    parameter = next(p for n, p in case["model"].named_parameters() if n.endswith("layers.1.feed_forward.output_dense.bias"))
+    original = parameter.detach().clone()
+    try:
+        with torch.no_grad():
+            parameter.add_(0.5)
+        eager = estimator.predict(batch, tfi)
+        graphed = estimator.predict(batch, tfi, cuda_graph=True)
+        assert not torch.equal(eager.outputs["phoneme"], kept)
+        for name, value in eager.outputs.items():
+            assert torch.equal(value, graphed.outputs[name]), name
+    finally:
+        with torch.no_grad():
+            parameter.copy_(original)
