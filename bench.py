@@ -163,6 +163,9 @@ def measured_peaks() -> Dict[str, Any]:
 # --------------------------------------------------------------------------------------------------
 # model construction (random init of the named architecture; synthetic inventory — no network, no CSV)
 # --------------------------------------------------------------------------------------------------
+# the end-to-end stream calls the public API with its CUDA-graph option (one captured graph per input shape, bit-identical to the
+# eager step: tests/test_gpu_e2e_parity.py::test_cuda_graph_predict_equals_eager); BENCH_E2E_GRAPH=0 times the eager call
+E2E_CUDA_GRAPH = os.environ.get("BENCH_E2E_GRAPH", "1") != "0"
 HIERARCHICAL = False  # --hierarchical: BASELINE configs[3] (phoneme head depends on OUTPUT + all 36 attribute heads)
 
 
@@ -267,7 +270,8 @@ def workload_config(n_gpus: int) -> Dict[str, Any]:
         "parallelism": f"dp{n_gpus} (independent utterance shards, no collective)",
         "l2": "per-step activations (>1 GB) exceed the 126 MB L2; no explicit flush between iterations",
         "e2e": "a stream of 10 x steps batches through Estimator.predict + decode_predictions_async: pinned host audio copied in on a "
-        "copy stream, decoded tokens copied out, CTCHypothesis lists built on the host while the next two batches compute",
+        "copy stream, decoded tokens copied out, CTCHypothesis lists built on the host while the next two batches compute" + (
+            "; predict(cuda_graph=True)" if E2E_CUDA_GRAPH else ""),
     }
 
 
@@ -369,7 +373,7 @@ def run_gpu_arm(args) -> None:
         torch.cuda.current_stream().wait_event(copied)
         for tensor in (batch.audio_features, batch.lengths, batch.language_ids):
             tensor.record_stream(torch.cuda.current_stream())
-        predictions = estimator.predict(batch, tfi_dev)
+        predictions = estimator.predict(batch, tfi_dev, cuda_graph=E2E_CUDA_GRAPH)
         return decode_predictions_async(predictions)
 
     def e2e_stream(steps: int):
