@@ -292,12 +292,16 @@ def cupti_gemm_time(step, is_encoder_linear) -> Optional[Tuple[int, float]]:
     try:
         from torch.profiler import ProfilerActivity, profile
 
+        import warnings
+
         torch.cuda.synchronize()
         ops.run_gemm = recording_gemm
         try:
-            with profile(activities=[ProfilerActivity.CUDA]) as prof:
-                step()
-                torch.cuda.synchronize()
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                    step()
+                    torch.cuda.synchronize()
         finally:
             ops.run_gemm = original
         kernels = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "gemm_bf16_kernel" in e.name),
