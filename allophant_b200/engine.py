@@ -15,6 +15,7 @@ with the host.
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass
 from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Tuple
 
@@ -725,13 +726,12 @@ class EncoderPlan:
             return False
 
         def group(shapes: Sequence[Tuple[str, Tuple[int, ...]]]) -> Tuple[Tensor, Dict[str, Tensor]]:
-            total = sum(int(torch.Size(shape).numel()) for _, shape in shapes)
-            flat = torch.empty(total, device=dev, dtype=torch.float32)
-            views, offset = {}, 0
-            for name, shape in shapes:
-                count = int(torch.Size(shape).numel())
-                views[name] = flat[offset : offset + count].view(shape)
-                offset += count
+            # one allocation, one split, one view per matrix: the host enqueues the backward pass barely ahead of the GPU, and
+            # slicing + viewing every gradient separately was 2 ms of Python per step
+            sizes = [math.prod(shape) for _, shape in shapes]
+            flat = torch.empty(sum(sizes), device=dev, dtype=torch.float32)
+            parts = flat.split_with_sizes(sizes)
+            views = {name: (part if len(shape) == 1 else part.view(shape)) for (name, shape), part in zip(shapes, parts)}
             return flat, views
 
         def done(flat: Tensor, views: Dict[str, Tensor], prefix: str) -> None:
@@ -818,9 +818,9 @@ class EncoderPlan:
             if need_encoder:
                 # the fused QKV gradient is handed out as its three nn.Linear slices (views of the same buffer)
                 wqkv, bqkv = g.pop("attention.qkv.weight"), g.pop("attention.qkv.bias")
-                for part, name in enumerate(("q_proj", "k_proj", "v_proj")):
-                    g[f"attention.{name}.weight"] = wqkv[part * H : (part + 1) * H]
-                    g[f"attention.{name}.bias"] = bqkv[part * H : (part + 1) * H]
+                for name, weight_part, bias_part in zip(("q_proj", "k_proj", "v_proj"), wqkv.split(H), bqkv.split(H)):
+                    g[f"attention.{name}.weight"] = weight_part
+                    g[f"attention.{name}.bias"] = bias_part
                 done(flat, g, f"encoder.layers.{index}.")
 
         column = self.hidden_blocks.get(0)
