@@ -100,9 +100,13 @@ class GradientReducer:
     divide the loss by the global label count (``global_label_count``) to reproduce the reference's
     single-device arithmetic (``estimator.py:737``) exactly."""
 
-    def __init__(self, group: Optional[dist.ProcessGroup] = None) -> None:
+    def __init__(self, group: Optional[dist.ProcessGroup] = None, wire_dtype: Optional[torch.dtype] = None) -> None:
+        """``wire_dtype=torch.bfloat16`` sends the gradients as bf16 (half the bytes over NVLink; the sum then carries bf16
+        rounding, so the default keeps fp32 and the reference's single-device arithmetic)."""
         self.group = group
+        self.wire_dtype = wire_dtype
         self.works: List[Any] = []
+        self._compressed: List[Tuple[Tensor, Tensor]] = []
         self.issued = 0
         self.bytes = 0
 
@@ -113,9 +117,13 @@ class GradientReducer:
     def submit(self, flat: Tensor, views: Optional[Dict[str, Tensor]] = None) -> None:
         if not self.active:
             return
-        self.works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        wire = flat
+        if self.wire_dtype is not None and flat.dtype != self.wire_dtype:
+            wire = flat.to(self.wire_dtype)
+            self._compressed.append((flat, wire))
+        self.works.append(dist.all_reduce(wire, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         self.issued += 1
-        self.bytes += flat.numel() * flat.element_size()
+        self.bytes += wire.numel() * wire.element_size()
 
     def submit_tensors(self, named: Dict[str, Tensor]) -> Dict[str, Tensor]:
         """Packs small tensors (the classifier heads' gradients) into one bucket; returns views of the bucket."""
@@ -133,6 +141,9 @@ class GradientReducer:
         for work in self.works:
             work.wait()
         self.works.clear()
+        for flat, wire in self._compressed:  # back into the fp32 buffers the .grad tensors are views of
+            flat.copy_(wire)
+        self._compressed.clear()
 
 
 def attach_gradient_reducer(model: Any, reducer: Optional[GradientReducer]) -> None:

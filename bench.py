@@ -618,7 +618,8 @@ def run_train_arm(args) -> None:
     # train() mode: HF dropout 0.1 / attention dropout 0.1 / LayerDrop 0.1 / SpecAugment 0.075 are
     # applied by the CUDA path with counter-based masks; --eval-arithmetic times the deterministic arithmetic instead
     model.train(not args.eval_arithmetic)
-    reducer = GradientReducer() if distributed else None
+    wire = torch.bfloat16 if os.environ.get("BENCH_ALLREDUCE_BF16") == "1" else None  # experiment: gradients as bf16 on the wire
+    reducer = GradientReducer(wire_dtype=wire) if distributed else None
     attach_gradient_reducer(model, reducer)
 
     # variable-length batch: U[3 s, 15 s], sorted, zero padded to the rank's longest utterance

@@ -49,6 +49,13 @@ def _worker(rank: int, world: int, port: int, results) -> None:
         assert torch.equal(views["a"], torch.full((4, 4), 3.0)) and torch.equal(views["b"], torch.full((48,), 3.0))
         assert packed["w"].shape == (3, 5) and torch.equal(packed["w"], torch.full((3, 5), 1.0))
         assert torch.equal(packed["b"], torch.full((7,), 2.0))
+        # bf16 on the wire: half the bytes, the fp32 buffer (and its views) receive the rounded sum
+        compressed = GradientReducer(wire_dtype=torch.bfloat16)
+        flat = torch.full((32,), 1.0 + rank)
+        view = flat[:8]
+        compressed.submit(flat, {"v": view})
+        compressed.finish()
+        assert compressed.bytes == 64 and torch.equal(view, torch.full((8,), 3.0)) and flat.dtype == torch.float32
         results[rank] = indices
     finally:
         dist.destroy_process_group()
