@@ -364,6 +364,17 @@ class EncoderPlan:
             self.dqkv = z(M, 3 * H)
             self.delta = z(n_utt * heads * self.seq, dtype=f32)
             self.d_fp_in = z(M, 512, dtype=f32)
+            if not cfg.do_stable_layer_norm:
+                # post-LN ordering: hidden state i is the (normalised) input of layer i; per layer the pre-LayerNorm sums are kept
+                self.hs16 = [z(M, H) for _ in range(n_layers)]
+                self.e_pre = z(M, H, dtype=f32)  # positional-conv output, before the encoder LayerNorm
+                self.mids = []
+                self.saved = [
+                    dict(q=z(n_utt * heads * self.seq * 64), k=z(n_utt * heads * self.seq * 64), v=z(n_utt * heads * self.seq * 64),
+                         lse=z(n_utt * heads * self.seq, dtype=f32), ctx=z(M, H), u=z(M, H, dtype=f32), h1=z(M, H, dtype=f32), h1_16=z(M, H),
+                         pre=z(M, FF), act=z(M, FF), v2=z(M, H, dtype=f32))
+                    for _ in range(n_layers)
+                ]  # fmt: skip
             if train_extractor:
                 self.conv_pre = [z(n_utt * length * 512) for length in L]
                 self.conv_post = [z(n_utt * length * 512) for length in L]
@@ -536,10 +547,11 @@ class EncoderPlan:
         ``Wav2Vec2Encoder`` / ``Wav2Vec2EncoderLayer``): the encoder LayerNorm follows the positional convolution, every layer is
         ``h = LN(h + attention(h)); h = final_LN(h + FFN(h))`` and hidden state ``i`` is the input of layer ``i``.  Inference
         only: the fp32 stream is normalised in place and the same kernel writes the bf16 GEMM operand."""
-        if self.training:
-            raise NotImplementedError("training of post-LN wav2vec2 encoders (do_stable_layer_norm=False) is not implemented")
         p, cfg = self.packed, self.cfg
         N, M, H, eps = self.n_utt, self.rows, cfg.hidden_size, cfg.layer_norm_eps
+        if self.training:
+            self._build_post_ln_training(steps, heads, FF)
+            return
         hidden, ln16 = self.hidden, self.ln_out
         n_layers = len(p.layers)
 
@@ -570,6 +582,140 @@ class EncoderPlan:
             self._layer_spans.append((span_start, len(steps)))
         self.h_last = hidden
         steps.append(lambda: self._keep_hidden(n_layers, hidden))
+
+    def _build_post_ln_training(self, steps: List[Step], heads: int, FF: int) -> None:
+        """Post-LN ordering with everything the backward pass reads kept per layer (``_backward_post_ln_layers``)."""
+        p, cfg = self.packed, self.cfg
+        N, M, H, eps = self.n_utt, self.rows, cfg.hidden_size, cfg.layer_norm_eps
+        if H not in (512, 1024):
+            raise NotImplementedError("training of post-LN encoders is built for hidden sizes 512 and 1024")
+        n_layers = len(p.layers)
+        hs, hs16 = self.hs, self.hs16
+        ge, be = p.final_ln  # encoder.layer_norm
+
+        def first_target() -> Tuple[Tensor, int]:
+            return (self.x, self.ldx) if n_layers == 0 else (hs16[0], H)
+
+        def encoder_norm() -> None:
+            self.e_pre.copy_(self.hidden)  # hs[0] is self.hidden: keep the pre-LayerNorm value for the backward pass
+            target, ld = first_target()
+            ops.layernorm_rows(self.hidden, M, H, H, ge, be, eps, out_f32=hs[0], ld_f32=H, out_bf16=target, ld_bf16=ld)
+            st = self.stoch
+            if st is not None and st.encoder_input().threshold:  # HF: hidden_states = self.dropout(self.layer_norm(hidden_states))
+                ops.dropout_2d(hs[0], H, M, H, st.encoder_input(), out_f32=hs[0], ld_f32=H, out_bf16=target, ld_bf16=ld)
+
+        steps.append(encoder_norm)
+        for index, lw in enumerate(p.layers):
+            sv = self.saved[index]
+            h_in, h_in16 = hs[index], hs16[index]
+            last = index == n_layers - 1
+            steps.append(lambda index=index, h_in=h_in: self._keep_hidden(index, h_in))
+            span_start = len(steps)
+            steps.append(self._gemm(ops.make_qkv_args(h_in16, lw["wqkv"], lw["bqkv"], sv["q"], sv["k"], sv["v"], rows=M, seq=self.seq, heads=heads)))
+            steps.append(
+                lambda sv=sv, index=index: ops.attention(
+                    sv["q"], sv["k"], sv["v"], sv["ctx"], self.att_lengths, N, heads, self.seq, sv["lse"],
+                    self.stoch.attention(index) if self.stoch else ops.NO_DROPOUT,
+                )
+            )
+            out_args = ops.make_gemm_args(sv["ctx"], lw["wo"], a_rows=M, a_inner=H, a_row_stride=H, bias=lw["bo"], resid=h_in, ld_resid=H, out_f32=sv["u"], ld_f32=H)
+            steps.append(self._gemm(out_args))
+            g1, b1 = lw["ln1"]
+            steps.append(lambda sv=sv, g1=g1, b1=b1: ops.layernorm_rows(sv["u"], M, H, H, g1, b1, eps, out_f32=sv["h1"], ld_f32=H, out_bf16=sv["h1_16"], ld_bf16=H))
+            inner_args = ops.make_gemm_args(sv["h1_16"], lw["w1"], a_rows=M, a_inner=H, a_row_stride=H, bias=lw["b1"], gelu=True, out_bf16=sv["act"], ld_bf16=FF,
+                                            aux_bf16=sv["pre"], ld_aux=FF)  # fmt: skip
+            steps.append(self._gemm(inner_args))
+            ffn_args = ops.make_gemm_args(sv["act"], lw["w2"], a_rows=M, a_inner=FF, a_row_stride=FF, bias=lw["b2"], resid=sv["h1"], ld_resid=H, out_f32=sv["v2"], ld_f32=H)
+            steps.append(self._gemm(ffn_args))
+            g2, b2 = lw["ln2"]
+            target, ld_target = (self.x, self.ldx) if last else (hs16[index + 1], H)
+            steps.append(lambda sv=sv, g2=g2, b2=b2, index=index, target=target, ld_target=ld_target: ops.layernorm_rows(
+                sv["v2"], M, H, H, g2, b2, eps, out_f32=hs[index + 1], ld_f32=H, out_bf16=target, ld_bf16=ld_target))  # fmt: skip
+            self._layer_spans.append((span_start, len(steps)))
+            self._drop_gemms += [(out_args, index, "attention_output"), (ffn_args, index, "feed_forward_output"), (inner_args, index, "activation")]
+        self.h_last = hs[n_layers]
+        steps.append(lambda: self._keep_hidden(n_layers, hs[n_layers]))
+
+    def _backward_post_ln_layers(self, d_x: Tensor, need_encoder: bool, group: Any, done: Any, wgrad: Any, branch_gradient: Any) -> None:
+        """Backward pass of the post-LN layers: on return ``self.dh`` is the gradient of hidden state 0 (the encoder LayerNorm's
+        output).  Per layer ``u = h + Wo attn(h); h1 = LN1(u); v2 = h1 + W2 gelu(W1 h1); out = LN2(v2)``."""
+        p, cfg, st = self.packed, self.cfg, self.stoch
+        N, M, H, FF, heads, seq, eps = self.n_utt, self.rows, cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads, self.seq, cfg.layer_norm_eps
+        dh, dh16 = self.dh, self.dh_bf16
+        n_layers = len(p.layers)
+        dh.copy_(d_x[:, :H])  # the last hidden state IS the classifier input OUTPUT (no final LayerNorm in this ordering)
+        for index in reversed(range(n_layers)):
+            lw, sv = p.layers[index], self.saved[index]
+            column = self.hidden_blocks.get(index + 1)
+            if column is not None and index + 1 < n_layers:
+                ops.add_2d(dh, H, d_x[:, column:], self.ldx, M, H)
+            if need_encoder:
+                flat, g = group(
+                    [
+                        ("feed_forward.output_dense.weight", (H, FF)), ("feed_forward.output_dense.bias", (H,)),
+                        ("feed_forward.intermediate_dense.weight", (FF, H)), ("feed_forward.intermediate_dense.bias", (FF,)),
+                        ("final_layer_norm.weight", (H,)), ("final_layer_norm.bias", (H,)),
+                        ("attention.out_proj.weight", (H, H)), ("attention.out_proj.bias", (H,)),
+                        ("attention.qkv.weight", (3 * H, H)), ("attention.qkv.bias", (3 * H,)),
+                        ("layer_norm.weight", (H,)), ("layer_norm.bias", (H,)),
+                    ]
+                )  # fmt: skip
+            else:
+                flat, g = None, {}
+
+            def finish_group() -> None:
+                if need_encoder:
+                    wqkv, bqkv = g.pop("attention.qkv.weight"), g.pop("attention.qkv.bias")
+                    for name, weight_part, bias_part in zip(("q_proj", "k_proj", "v_proj"), wqkv.split(H), bqkv.split(H)):
+                        g[f"attention.{name}.weight"] = weight_part
+                        g[f"attention.{name}.bias"] = bias_part
+                    done(flat, g, f"encoder.layers.{index}.")
+
+            if self.skipped[index]:
+                if need_encoder:
+                    flat.zero_()
+                finish_group()
+                continue
+            # out = LN2(v2)
+            g2, _ = lw["ln2"]
+            ops.layernorm_backward(sv["v2"], H, dh, H, M, H, g2, eps, None, 0, dh, H, g.get("final_layer_norm.weight"), g.get("final_layer_norm.bias"))
+            # v2 = h1 + dropout(W2 dropout(gelu(W1 h1 + b1)) + b2): dh is d(v2)
+            dropped = branch_gradient(st.feed_forward_output(index) if st else ops.NO_DROPOUT)
+            args = ops.make_dgrad_args(dh16, lw["w2"], rows=M, ld_dy=H, k=H, n=FF, ld_w=FF, gelu_bwd=sv["pre"], ld_gelu_bwd=FF, out_bf16=self.d_ff, ld_bf16=FF)
+            inner = st.activation(index) if st else ops.NO_DROPOUT
+            args.drop_threshold, args.drop_seed, args.drop_scale = inner.threshold, inner.seed, inner.scale
+            ops.run_gemm(args)
+            if need_encoder:
+                wgrad(g["feed_forward.output_dense.weight"], dh16, H, H, sv["act"], FF, FF)
+                if dropped:
+                    ops.colsum_bf16(dh16, M, H, H, out=g["feed_forward.output_dense.bias"])
+                else:
+                    ops.colsum_f32(dh, M, H, H, out=g["feed_forward.output_dense.bias"])
+                wgrad(g["feed_forward.intermediate_dense.weight"], self.d_ff, FF, FF, sv["h1_16"], H, H)
+                ops.colsum_bf16(self.d_ff, M, FF, FF, out=g["feed_forward.intermediate_dense.bias"])
+            # d(h1) = d(v2) + d_ff W1 (residual epilogue), then h1 = LN1(u)
+            ops.run_gemm(ops.make_dgrad_args(self.d_ff, lw["w1"], rows=M, ld_dy=FF, k=FF, n=H, ld_w=H, resid=dh, ld_resid=H, out_f32=self.d_ln, ld_f32=H))
+            g1, _ = lw["ln1"]
+            ops.layernorm_backward(sv["u"], H, self.d_ln, H, M, H, g1, eps, None, 0, dh, H, g.get("layer_norm.weight"), g.get("layer_norm.bias"))
+            # u = h + dropout(Wo attn(Wqkv h) + bo): dh is d(u)
+            dropped = branch_gradient(st.attention_output(index) if st else ops.NO_DROPOUT)
+            ops.run_gemm(ops.make_dgrad_args(dh16, lw["wo"], rows=M, ld_dy=H, k=H, n=H, ld_w=H, out_bf16=self.d_ctx, ld_bf16=H))
+            if need_encoder:
+                wgrad(g["attention.out_proj.weight"], dh16, H, H, sv["ctx"], H, H)
+                if dropped:
+                    ops.colsum_bf16(dh16, M, H, H, out=g["attention.out_proj.bias"])
+                else:
+                    ops.colsum_f32(dh, M, H, H, out=g["attention.out_proj.bias"])
+            ops.attention_backward(
+                sv["q"], sv["k"], sv["v"], sv["ctx"], self.d_ctx, sv["lse"], self.delta, self.dqkv, self.att_lengths, N, heads, seq,
+                st.attention(index) if st else ops.NO_DROPOUT,
+            )  # fmt: skip
+            if need_encoder:
+                wgrad(g["attention.qkv.weight"], self.dqkv, 3 * H, 3 * H, self.hs16[index], H, H)
+                ops.colsum_bf16(self.dqkv, M, 3 * H, 3 * H, out=g["attention.qkv.bias"])
+            # d(h) = d(u) + dqkv Wqkv, in place through the residual epilogue
+            ops.run_gemm(ops.make_dgrad_args(self.dqkv, lw["wqkv"], rows=M, ld_dy=3 * H, k=3 * H, n=H, ld_w=H, resid=dh, ld_resid=H, out_f32=dh, ld_f32=H))
+            finish_group()
 
     def _regularise_projection(self) -> None:
         """train() mode: dropout of the feature projection output (HF:431-433), then SpecAugment (HF
@@ -602,7 +748,7 @@ class EncoderPlan:
     def _regularise_encoder_input(self) -> None:
         """train() mode: ``hidden_states = self.dropout(hidden_states + position_embeddings)`` (HF:765-766)."""
         st = self.stoch
-        if st is None:
+        if st is None or not self.cfg.do_stable_layer_norm:  # post-LN: the dropout follows the encoder LayerNorm (_build_post_ln)
             return
         drop = st.encoder_input()
         if drop.threshold:
@@ -672,6 +818,11 @@ class EncoderPlan:
                 step()
             if self.skipped[layer]:
                 self.hs[layer + 1].copy_(self.hs[layer])  # LayerDrop: the layer is the identity for this batch
+                if not cfg.do_stable_layer_norm:  # post-LN: the bf16 operand of the next layer (or the classifier input) follows
+                    if layer + 1 < n_layers:
+                        self.hs16[layer + 1].copy_(self.hs16[layer])
+                    else:
+                        ops.cast_bf16_2d(self.hs[layer], cfg.hidden_size, self.x, self.ldx, self.rows, cfg.hidden_size)
             else:
                 for step in self._steps[start:end]:
                     step()
@@ -743,14 +894,18 @@ class EncoderPlan:
         def wgrad(out: Tensor, dy: Tensor, ld_dy: int, m: int, x: Tensor, ld_x: int, n: int) -> None:
             ops.run_gemm(ops.make_wgrad_args(dy, x, out, rows=M, m=m, ld_dy=ld_dy, n=n, ld_x=ld_x, ld_out=n))
 
-        # final LayerNorm (HF:792): X[:, :H] = LN(hs[L])
+        post_ln = not cfg.do_stable_layer_norm
         gf, _ = p.final_ln
-        flat, g = group([("weight", (H,)), ("bias", (H,))]) if need_encoder else (None, {})
-        ops.layernorm_backward(self.hs[n_layers], H, d_x, self.ldx, M, H, gf, eps, None, 0, dh, H, g.get("weight"), g.get("bias"))
-        if need_encoder:
-            done(flat, g, "encoder.layer_norm.")
+        if post_ln:
+            self._backward_post_ln_layers(d_x, need_encoder, group, done, wgrad, branch_gradient)
+        else:
+            # final LayerNorm (HF:792): X[:, :H] = LN(hs[L])
+            flat, g = group([("weight", (H,)), ("bias", (H,))]) if need_encoder else (None, {})
+            ops.layernorm_backward(self.hs[n_layers], H, d_x, self.ldx, M, H, gf, eps, None, 0, dh, H, g.get("weight"), g.get("bias"))
+            if need_encoder:
+                done(flat, g, "encoder.layer_norm.")
 
-        for index in reversed(range(n_layers)):
+        for index in (() if post_ln else reversed(range(n_layers))):
             lw, sv = p.layers[index], self.saved[index]
             if need_encoder:
                 flat, g = group(
@@ -829,6 +984,11 @@ class EncoderPlan:
         # ---- positional conv embedding (HF:764-766, 353-368): hs[0] = dropout(h_fp + gelu(conv(h_fp) + b))
         if st is not None and st.encoder_input().threshold:
             ops.dropout_2d(dh, H, M, H, st.encoder_input(), out_f32=dh, ld_f32=H)
+        if post_ln:  # hidden state 0 = dropout(LN_enc(h_fp + gelu(conv(h_fp)))): through the encoder LayerNorm
+            flat, g = group([("weight", (H,)), ("bias", (H,))]) if need_encoder else (None, {})
+            ops.layernorm_backward(self.e_pre, H, dh, H, M, H, gf, eps, None, 0, dh, H, g.get("weight"), g.get("bias"))
+            if need_encoder:
+                done(flat, g, "encoder.layer_norm.")
         taps = cfg.num_conv_pos_embeddings
         pc = w.encoder.pos_conv_embed.conv
         weight_g, weight_v = pc.parametrizations.weight.original0, pc.parametrizations.weight.original1

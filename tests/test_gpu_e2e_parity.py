@@ -208,8 +208,33 @@ def test_post_ln_group_norm_encoder_matches_oracle():
     for name, reference in outputs.items():
         error = _range_error(predictions.outputs[name].float().cpu(), reference, frames_ref.tolist())
         assert error < RANGE_TOL, f"{name}: {error:.3e} of range"
-    with pytest.raises(NotImplementedError, match="post-LN"):  # the encoder's parameters require gradients: training plan
-        model(batch)
+    # training through the post-LN ordering: loss and every gradient against autograd through the Hugging Face model
+    from allophant_b200.loss_functions import multi_head_ctc_loss
+
+    head_classes = {c.name: c.size + 1 for c in spec.classes}
+    labels, label_lengths = restatement.training_labels(spec, head_classes, frames_ref, None, seed=6)
+    model.eval()
+    for parameter in model.parameters():
+        parameter.grad = None
+    outputs = model(batch)
+    outputs.outputs.pop("phone", None)
+    order = list(outputs.outputs)
+    losses = multi_head_ctc_loss([outputs.outputs[n] for n in order], [labels[n].cuda() for n in order], outputs.lengths, [label_lengths[n].cuda() for n in order])
+    loss = losses.sum() / sum(int(label_lengths[n].sum()) for n in order)
+    loss.backward()
+    reference_loss, _, reference = oracle.training_step(audio, lengths, labels, label_lengths, torch.zeros(3, dtype=torch.long))
+    assert abs(float(loss) - float(reference_loss)) <= 2e-2 * abs(float(reference_loss))
+    worst = {}
+    for name, parameter in model.named_parameters():
+        if name not in reference or float(reference[name].norm()) < 1e-7:
+            continue
+        assert parameter.grad is not None, name
+        worst[name] = float((parameter.grad.double().cpu() - reference[name].double()).norm() / reference[name].double().norm())
+    ranked = sorted(worst.items(), key=lambda item: -item[1])
+    print("post-LN training: worst " + ", ".join(f"{k.split('._model.')[-1]}={v:.3e}" for k, v in ranked[:4]))
+    # 1e-1: the bf16 noise band of these tiny random-init models (profiles/r01_regularisation_noise_floor.log: 2e-2 ... 6e-2 in the
+    # stable-LN ordering; here every layer output is re-normalised, measured worst 7.2e-2); an ordering or residual mistake shows as >= 3e-1
+    assert len(worst) > 40 and ranked[0][1] < 1e-1, ranked[:8]
 
 
 def test_cuda_graph_predict_equals_eager(case):
