@@ -87,27 +87,24 @@ class RawLabeledBatch(Batch):
         return self.__class__(*self._inputs_to(device, non_blocking, copy), self.raw_labels, self.utterance_ids)
 
     def split_by_language(self) -> Iterator[Tuple[int, "RawLabeledBatch"]]:
-        split_ids, split_indices = self.language_ids.unique_consecutive(return_counts=True)
-        split_indices.cumsum_(0)
-        offset = 0
-        for split_id, split_index, features, lengths, language_ids in zip(
-            split_ids,
-            split_indices,
-            self.audio_features.tensor_split(split_indices),
-            self.lengths.tensor_split(split_indices),
-            self.language_ids.tensor_split(split_indices),
-        ):
+        """One sub-batch per run of consecutive equal language ids (``dataset_processing.py:103-130``), each re-padded to its
+        own longest utterance; yields ``(language id, batch)``."""
+        languages, run_lengths = self.language_ids.unique_consecutive(return_counts=True)
+        start = 0
+        for language, run in zip(languages, run_lengths.tolist()):
+            stop = start + run
+            lengths = self.lengths[start:stop]
             yield (
-                split_id,
-                self.__class__(
-                    features[..., : lengths.max()],
+                language,
+                type(self)(
+                    self.audio_features[start:stop, ..., : int(lengths.max())],
                     lengths,
-                    language_ids,
-                    [labels[offset:split_index] for labels in self.raw_labels],
-                    self.utterance_ids[offset:split_index],
+                    self.language_ids[start:stop],
+                    [engine_labels[start:stop] for engine_labels in self.raw_labels],
+                    self.utterance_ids[start:stop],
                 ),
             )
-            offset = split_index
+            start = stop
 
 
 class BatchType(Enum):
