@@ -357,3 +357,59 @@ def test_feature_axis_spec_augment_matches_oracle_with_the_same_masks():
     print("feature-axis SpecAugment: worst " + ", ".join(f"{k.split('._model.')[-1]}={v:.3e}" for k, v in ranked[:4]))
     assert "_acoustic_model._model.masked_spec_embed" in worst
     assert ranked[0][1] < TRAIN_MODE_TOL, ranked[:8]
+
+
+def test_post_ln_train_mode_matches_oracle_with_the_same_masks():
+    """The post-LN encoder ordering in train() mode: the encoder-input dropout FOLLOWS the encoder LayerNorm there (HF
+    ``Wav2Vec2Encoder``), every other site as in the stable ordering; one layer dropped by LayerDrop."""
+    from allophant_b200.dataset_processing import Batch
+
+    fixture = helpers.load_golden("training_multitask_2layer")
+    case_config = dict(fixture["case_config"])
+    case_config["spec"] = dict(case_config["spec"])
+    overrides = dict(case_config["spec"].get("encoder_overrides") or {})
+    overrides.update(do_stable_layer_norm=False)
+    case_config["spec"]["encoder_overrides"] = overrides
+    spec = helpers.spec_for_case(case_config)
+    oracle = restatement.OracleModel(spec)
+    model, _ = helpers.cuda_model_for_spec(spec, oracle)
+    lengths = fixture["lengths"]
+    audio = restatement.synthetic_audio(len(lengths), int(lengths.max()), seed=0) * restatement.mask_sequence(lengths)
+    batch = Batch(audio.cuda(), lengths.cuda(), fixture["language_ids"].cuda())
+    for skip_layers in ([False, False], [True, False]):
+        model.train()
+        model._heads.skip_layers_override = skip_layers
+        try:
+            torch.manual_seed(12)
+            loss, _, _ = _training_step(model, batch, fixture)
+            state = model._heads.last_regularisation
+        finally:
+            model._heads.skip_layers_override = None
+            model.eval()
+        stochastic, plan = state["stochastic"], state["plan"]
+        cfg = plan.cfg
+        assert not cfg.do_stable_layer_norm and plan.skipped == skip_layers
+        masks = helpers.regularisation_masks(
+            stochastic, plan.n_utt, plan.seq, cfg.hidden_size, cfg.num_attention_heads, cfg.num_hidden_layers, plan.skipped, plan.spec_mask.cpu()
+        )
+        blocks = {0: cfg.num_hidden_layers, **{column: index for index, column in model._heads.hidden_blocks.items()}}
+        masks["classifier_input"] = {
+            blocks[column]: helpers.keep_mask(drop, plan.n_utt * plan.seq, cfg.hidden_size).view(plan.n_utt, plan.seq, cfg.hidden_size)
+            for column, drop in state["input_dropout"].items()
+        }
+        reference_loss, _, reference = oracle.training_step(
+            audio, lengths, fixture["labels"], fixture["label_lengths"], fixture["language_ids"], regularisation=masks
+        )
+        assert abs(float(loss) - float(reference_loss)) <= 2e-2 * abs(float(reference_loss)), (float(loss), float(reference_loss))
+        worst = {}
+        for name, parameter in model.named_parameters():
+            if parameter.grad is None or name not in reference or float(reference[name].norm()) < 1e-7:
+                continue
+            if any(f".encoder.layers.{index}." in name for index, flag in enumerate(skip_layers) if flag):
+                assert float(parameter.grad.abs().max()) == 0.0, name
+                continue
+            worst[name] = norm_err(parameter.grad, reference[name])
+        ranked = sorted(worst.items(), key=lambda item: -item[1])
+        print(f"post-LN train() skip={skip_layers}: loss {float(loss):.5f} / {float(reference_loss):.5f}; worst "
+              + ", ".join(f"{k.split('._model.')[-1]}={v:.3e}" for k, v in ranked[:4]))  # fmt: skip
+        assert ranked[0][1] < TRAIN_MODE_TOL, ranked[:8]
