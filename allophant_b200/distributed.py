@@ -153,7 +153,7 @@ def attach_gradient_reducer(model: Any, reducer: Optional[GradientReducer]) -> N
 
 def global_label_count(local_label_lengths: Sequence[Tensor], group: Optional[dist.ProcessGroup] = None) -> Tensor:
     """Σ label lengths over all heads and all ranks — the divisor of the step loss (``estimator.py:737``)."""
-    total = torch.stack([lengths.sum() for lengths in local_label_lengths]).sum().to(torch.float64)
+    total = torch.cat([lengths.reshape(-1) for lengths in local_label_lengths]).sum().to(torch.float64)  # two launches, not one per head
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
     return total
