@@ -485,6 +485,10 @@ def log_softmax(x: Tensor) -> Tensor:
     """``functional.log_softmax(x, -1)`` for an fp32 CUDA tensor of any shape (``acoustic_model.py:1051-1052``)."""
     _require_cuda(x)
     width = x.shape[-1]
+    if x.dim() == 3 and x.dtype == torch.float32 and not x.is_contiguous() and x.transpose(0, 1).is_contiguous():
+        # the time-first view of a batch-first block (what Allophant.forward returns): normalise the block where it lies and hand
+        # back the same view — no transposing copy here, none of the gradient on the way back
+        return log_softmax(x.transpose(0, 1)).transpose(0, 1)
     flat = x.float().reshape(-1, width)
     if flat.stride(-1) != 1 or flat.stride(0) != width:
         flat = flat.contiguous()
