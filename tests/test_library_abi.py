@@ -32,6 +32,13 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib.aph_abi_version() == 4
 
 
+def test_integration_guide_indexes_every_entry_point():
+    """INTEGRATION.md section 5 (tools/abi_index.py) names every declared symbol with the reference interface it replaces."""
+    guide = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [symbol for symbol in declared_symbols() if f"| `{symbol}` |" not in guide]
+    assert not missing, f"run tools/abi_index.py: INTEGRATION.md lacks {missing}"
+
+
 def test_argument_validation_needs_no_gpu():
     """Launchers validate before touching CUDA and report through aph_last_error()."""
     from allophant_b200 import _lib
