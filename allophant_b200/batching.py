@@ -4,7 +4,7 @@
   behaviour (including the empty first batch the reference yields when the very first utterance exceeds the budget).
 * ``build_batch`` (``batching.py:171-215``, ``_build_batch``): merges single-entry batches into one dense ``Batch`` /
   ``LabeledBatch`` / ``RawLabeledBatch``.  The audio is collated by ``aph_collate_pad_f32`` (host C++ threads) straight
-  into a PINNED staging buffer taken from a small ring, so the host -> device copy that follows is a single asynchronous
+  into a PINNED buffer the batch owns, so the host -> device copy that follows is a single asynchronous
   DMA from page-locked memory (``torch.nn.utils.rnn.pad_sequence`` + pageable ``.to(device)`` costs two extra passes over
   the batch and a synchronous copy).
 * ``shard_for_rank``: per-rank, length-balanced sub-batches for data-parallel runs (``distributed.shard_indices``).
@@ -63,23 +63,15 @@ class SkipBatchSampler(BatchSampler):
         return samples
 
 
-_STAGING: Dict[int, List[Tensor]] = {}
-_STAGING_TURN = 0
-
-
-def _pinned_staging(elements: int) -> Tensor:
-    """A pinned fp32 buffer of at least ``elements`` from a ring of four per size class (power of two): a batch stays
-    valid while the next three are assembled, long enough for its asynchronous host -> device copy."""
-    global _STAGING_TURN
-    size = 1 << max(10, (elements - 1).bit_length())
-    ring = _STAGING.setdefault(size, [])
-    slot = _STAGING_TURN % 4
-    _STAGING_TURN += 1
-    while len(ring) <= slot:
-        pin = torch.cuda.is_available()
-        with torch.inference_mode(False):
-            ring.append(torch.empty(size, dtype=torch.float32, pin_memory=pin))
-    return ring[slot]
+def _pinned_staging(count: int, longest: int) -> Tensor:
+    """An OWNED page-locked fp32 ``[count, longest]`` tensor for one batch.  It comes from torch's caching host allocator, which
+    recycles a block only after the tensor died AND every asynchronous copy recorded on it finished — so any number of
+    batches can be alive at once (the reference's ``_training_batch_accumulation`` holds ``accumulation_factor`` host
+    batches before ``.to(device)``; a prefetching consumer holds more) and none aliases another.  Inside a forked
+    ``DataLoader`` worker (CUDA must not be initialised there) and without a GPU the buffer is pageable."""
+    pin = torch.cuda.is_available() and torch.utils.data.get_worker_info() is None
+    with torch.inference_mode(False):
+        return torch.empty(count, longest, dtype=torch.float32, pin_memory=pin)
 
 
 def collate_audio(utterances: Sequence[Tensor], pinned: bool = True, n_threads: int = 0) -> Tensor:
@@ -92,7 +84,7 @@ def collate_audio(utterances: Sequence[Tensor], pinned: bool = True, n_threads: 
     if any(u.is_cuda for u in sources):
         raise RuntimeError("collate_audio assembles HOST batches; move the finished batch to the GPU with Batch.to")
     if pinned:
-        out = _pinned_staging(max(1, count * longest))[: count * longest].view(count, longest)
+        out = _pinned_staging(count, longest)
     else:
         out = torch.empty(count, longest, dtype=torch.float32)
     if count == 0 or longest == 0:

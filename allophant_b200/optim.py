@@ -244,6 +244,8 @@ class OptimizerWrapper:
         if clip_norm is not None and isinstance(self._optimizer, (FusedAdam, FusedSGD)):
             self._optimizer.step(clip_norm=clip_norm)
         else:
+            if clip_norm is not None:  # any other optimizer (a plain torch.optim.Adam as in the reference): clip first, as estimator.py:778-791 does
+                clip_grad_norm_([p for group in self._optimizer.param_groups for p in group["params"]], clip_norm)
             self._optimizer.step()
         if self._lr_scheduler is not None:
             self._lr_scheduler.step()
@@ -300,7 +302,10 @@ def optimizer_from_config(architecture: Any, model: Any) -> OptimizerWrapper:
         constant_steps=schedule.get("constant_steps", 0),
         factor=schedule.get("factor", 2),
     )
-    parameters = [parameter for parameter in model.parameters() if parameter.requires_grad]
+    # ALL parameters, as the reference passes them (estimator.py:982): `freeze_feature_encoder` defaults to true, and what
+    # `UnfreezeSchedule.step` unfreezes later must already be in the optimizer; Adam / SGD skip parameters without a `.grad`,
+    # and the param_groups then match the reference's, so its optimizer state_dict loads
+    parameters = list(model.parameters())
     if algorithm == "adam":
         return adam_from_config(
             parameters, model.d_model, model=model, learning_rate=options.get("learning_rate", 0.01), beta_1=options.get("beta_1", 0.9),

@@ -11,6 +11,9 @@ The JSON line follows the driver's contract: `value` is device-timed with inputs
 same metric through the public API (Estimator.predict + decode_predictions) with pinned-host inputs copied in and
 decoded tokens copied out inside the timed region, `roofline` describes the dominant kernel (the tcgen05 GEMM over
 the encoder's linear layers), `cpu_baseline` is the oracle timed on this box's host cores on a bounded sample.
+Two sub-records ride on the same line so that the driver's `--gpus N` runs cover them too: `train` (BASELINE configs[2]:
+the training step with the NCCL gradient all-reduce, the same per-rank batch on every rank, all-reduce bytes and exposed
+milliseconds) and, at N = 1, `membound` (achieved GB/s of the HBM-bound kernels against the measured copy bandwidth).
 """
 from __future__ import annotations
 
@@ -197,7 +200,7 @@ def cpu_reference_step(oracle, audio, lengths, tfi) -> None:
         restatement.greedy_ctc_decode(value.transpose(1, 0).contiguous(), frames)
 
 
-def time_cpu_reference(n_utt: int, steps: int, warmup: int) -> Dict[str, Any]:
+def time_cpu_reference(n_utt: int, steps: int, warmup: int, budget_s: float = 1e9) -> Dict[str, Any]:
     """The reference's CPU path (oracle port: HF encoder + restated heads/decoder) on this box's host cores."""
     from oracle import restatement
 
@@ -216,23 +219,31 @@ def time_cpu_reference(n_utt: int, steps: int, warmup: int) -> Dict[str, Any]:
         start = time.perf_counter()
         cpu_reference_step(oracle, audio, lengths, tfi)
         times.append(time.perf_counter() - start)
+        if sum(times) > budget_s:
+            break
     total = sum(times)
+    timed = len(times)
     return {
-        "value": n_utt * SECONDS * steps / total,
+        "value": n_utt * SECONDS * timed / total,
         "unit": UNIT,
         "cores": cores,
         "kind": "port",
-        "sample": f"{steps} x (batch {n_utt} x {SECONDS} s, fp32, all 37 heads + greedy decode), {warmup} warm-up",
-        "ms_per_step": 1000.0 * total / steps,
+        "sample": f"{timed} x (batch {n_utt} x {SECONDS} s, fp32, all 37 heads + greedy decode), {warmup} warm-up"
+        + ("" if timed == steps else f"; stopped after {timed} of {steps} steps (time budget {budget_s:.0f} s)"),
+        "ms_per_step": 1000.0 * total / timed,
+        "steps_timed": timed,
     }
 
 
 def run_reference_arm(args) -> None:
+    """The reference's CPU path on this arm's own configuration: every step is one whole batch (BATCH x SECONDS, all 37 heads
+    + greedy decode) through the oracle port on all host cores.  One warm-up step; timing stops early (and says so in
+    `cpu_baseline.sample` / `steps_timed`) once `BENCH_REFERENCE_BUDGET_S` (default 240 s) of CPU time is spent, so that a
+    box with few cores still finishes within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_utt = 2
-    result = time_cpu_reference(n_utt, max(1, args.steps), max(1, min(args.warmup, 2)))
+    result = time_cpu_reference(BATCH, max(1, args.steps), 1, budget_s=float(os.environ.get("BENCH_REFERENCE_BUDGET_S", "240")))
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -249,6 +260,7 @@ def run_reference_arm(args) -> None:
         "data": "synthetic",
         "config": workload_config(args.gpus),
         "cpu_baseline": {k: result[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "steps_timed": result["steps_timed"],
         "e2e": {"value": result["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -336,18 +348,10 @@ def run_gpu_arm(args) -> None:
     from allophant_b200.dataset_processing import Batch
     from allophant_b200.predictions import decode_predictions_async
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: allophant_b200 has no CPU path (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    device = f"cuda:{local_rank}"
-    distributed = world > 1
+    process = setup_process()
+    world, rank, local_rank, device, distributed = process
     if distributed:
         import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=torch.device(device))
 
     estimator, tfi = build_estimator(device)
     tfi_dev = tfi.to(device)
@@ -510,7 +514,8 @@ def run_gpu_arm(args) -> None:
             # FFN2 launches of the `ncu --set full` capture in profiles/r01_ncu_summary.md (83.4 / 110.8 / 117.3 / 249.7 MB):
             # equal to the algorithmic operand + residual bytes, i.e. no re-reads
             "traffic": 140.3e6,
-            "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_summary.md)",
+            "traffic_unit": "bytes per launch",
+            "traffic_source": "constant from profiles/r01_ncu_summary.md (one `ncu --set full` capture of this step; not re-measured per run)",
             "peak_source": f"bf16_tflops_sustained, {peaks['source']}",
             "launches": len(gemm_events),
             "avg_launch_ms": gemm_ms / max(1, len(gemm_events)),
@@ -521,10 +526,22 @@ def run_gpu_arm(args) -> None:
         )
         if kernel_only is not None:
             roofline["kernel_only"] = kernel_only
-        if not args.skip_cpu_baseline:
-            baseline = time_cpu_reference(2, 3, 1)
+        if not args.skip_cpu_baseline and world == 1:  # rank 0 at N = 1 only: a bounded sample (~10 s of CPU work) of the same workload
+            baseline = time_cpu_reference(8, 3, 1)
             cpu_baseline = {k: baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    # ---- sub-records: the training / data-parallel path (BASELINE configs[2]) and the HBM-bound kernels, measured in this same run
+    del estimator, resident
+    torch.cuda.empty_cache()
+    train = None
+    if not args.skip_train:
+        record = measure_training(process, args.train_steps, 3, False, detail=True)
+        if record is not None:
+            train = {key: record[key] for key in ("metric", "value", "unit", "ms_per_step", "steps", "gpu_launches", "e2e", "roofline")}
+            train["config"] = record["config"]
+    membound = None
+    if rank == 0 and world == 1 and not args.skip_membound:
+        membound = measure_membound(device)
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
@@ -550,8 +567,125 @@ def run_gpu_arm(args) -> None:
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "tflops_per_gpu": utterance_flops(samples) * BATCH / (elapsed_ms / args.steps / 1000.0) / 1e12,
+        "train": train,
+        "membound": membound,
     }
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# HBM-bound kernels at BASELINE sizes: achieved GB/s (algorithmic bytes) against the measured copy bandwidth
+# --------------------------------------------------------------------------------------------------
+def measure_membound(device: str) -> List[Dict[str, Any]]:
+    from allophant_b200 import ops
+
+    peak = float(measured_peaks()["hbm_gbs"])
+    records: List[Dict[str, Any]] = []
+
+    def timeit(fn, iters=20, warm=3) -> float:
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(iters):
+            fn()
+        end.record()
+        torch.cuda.synchronize()
+        return start.elapsed_time(end) / iters
+
+    def report(kernel: str, shape: str, ms: float, nbytes: float, note: str = "") -> None:
+        gbs = nbytes / ms / 1e6
+        records.append({"kernel": kernel, "shape": shape, "us": ms * 1e3, "algorithmic_bytes": nbytes, "achieved_gbs": gbs, "peak_gbs": peak,
+                        "frac": gbs / peak, "note": note})  # fmt: skip
+
+    def synthetic_labels(frames, n_classes, seed, fraction=0.25):
+        generator = torch.Generator().manual_seed(seed)
+        lengths = (frames.double() * fraction).floor().long().clamp_min(1)
+        labels = torch.zeros(len(frames), int(lengths.max()), dtype=torch.long)
+        for row, length in enumerate(lengths.tolist()):
+            labels[row, :length] = torch.randint(1, n_classes, (length,), generator=generator)
+        return labels, lengths
+
+    # configs[3]: the wide composed phoneme head, 128 x 499 frames x 3184 classes (0.81 GB of logits: far beyond L2)
+    rows, width = 128 * 499, 3184
+    logits = torch.randn(rows, width, device=device)
+    out = torch.empty_like(logits)
+    am = torch.empty(rows, dtype=torch.int32, device=device)
+    mx = torch.empty(rows, device=device)
+    report("log_softmax_wide (+argmax, max)", "63872 x 3184 fp32", timeit(lambda: ops.log_softmax_wide(logits, width, rows, width, out, width, am, mx)), 2.0 * rows * width * 4)
+    report("torch.log_softmax (library, same shape)", "63872 x 3184 fp32", timeit(lambda: torch.log_softmax(logits, -1), iters=10), 2.0 * rows * width * 4, "library bar")
+    del logits, out
+
+    # configs[1]: the 36 narrow heads packed [15968 x 144]
+    rows2 = 32 * 499
+    packed = torch.randn(rows2, 144, device=device)
+    col = torch.arange(0, 144, 4, dtype=torch.int32, device=device)
+    wid = torch.full((36,), 4, dtype=torch.int32, device=device)
+    off = torch.arange(36, dtype=torch.int64, device=device) * rows2 * 4
+    out2 = torch.empty(rows2 * 144, device=device)
+    am2 = torch.empty(36, rows2, dtype=torch.int32, device=device)
+    mx2 = torch.empty(36, rows2, device=device)
+    report("log_softmax_heads 36 heads (+argmax, max)", "15968 x 144 fp32", timeit(lambda: ops.log_softmax_heads(packed, 144, rows2, 0, 144, col, wid, off, 36, out2, am2, mx2)),
+           2.0 * rows2 * 144 * 4 + 36 * rows2 * 8, "18 MB: latency-bound at this size")
+
+    # LayerNorm of the residual stream: rotate over 4 inputs so that the 65 MB rows do not stay in the 126 MB L2
+    xs = [torch.randn(rows2, 1024, device=device) for _ in range(4)]
+    g, b = torch.ones(1024, device=device), torch.zeros(1024, device=device)
+    o16 = torch.empty(rows2, 1024, device=device, dtype=torch.bfloat16)
+
+    def layer_norms():
+        for x in xs:
+            ops.layernorm_rows(x, rows2, 1024, 1024, g, b, 1e-5, out_bf16=o16, ld_bf16=1024)
+
+    report("layernorm_rows fp32 -> bf16", "15968 x 1024", timeit(layer_norms) / 4, rows2 * 1024 * 6.0)
+    del xs
+    rows3 = 32 * 15999
+    xb = torch.randn(rows3, 512, device=device).bfloat16()
+    g5, b5 = torch.ones(512, device=device), torch.zeros(512, device=device)
+    report("layernorm_rows + GELU bf16 in place (conv layer 1)", "511968 x 512", timeit(lambda: ops.layernorm_rows(xb, rows3, 512, 512, g5, b5, 1e-5, gelu=True, out_bf16=xb, ld_bf16=512), iters=10), rows3 * 512 * 4.0)
+    del xb
+
+    # conv0 fused (waveform normalisation + conv 1->512 k10 s5 + LayerNorm + GELU): 32 x 160000 samples -> [32, 31999, 512] bf16
+    audio = torch.randn(32, 160000, device=device) * 0.1
+    lengths = torch.full((32,), 160000, dtype=torch.int64, device=device)
+    stats = torch.empty(32, 3, dtype=torch.float64, device=device)
+    mr = torch.empty(32, 2, device=device)
+    ops.wave_stats(audio, lengths, stats, mr)
+    w0 = torch.randn(512, 10, device=device) * 0.3
+    o0 = torch.empty(32, 31999, 512, device=device, dtype=torch.bfloat16)
+    report("conv0 + waveform norm + LayerNorm + GELU", "32 x 160000 -> 32 x 31999 x 512 bf16", timeit(lambda: ops.conv0_ln_gelu(audio, lengths, mr, w0, g5, g5, b5, 1e-5, o0), iters=10),
+           32 * 160000 * 4.0 + 32 * 31999 * 512 * 2.0)
+    del o0, audio
+
+    # CTC, configs[2] shape per GPU (8 utterances) and the whole global batch (64): 36 heads c=4 + phoneme c=501, T' = 749
+    for n_utt in (8, 64):
+        frames = 749
+        input_lengths = torch.randint(150, frames + 1, (n_utt,), generator=torch.Generator().manual_seed(4))
+        input_lengths[0] = frames
+        classes = [4] * 36 + [501]
+        log_probs, labels_l, lens_l = [], [], []
+        for head, c in enumerate(classes):
+            log_probs.append(torch.log_softmax(torch.randn(frames, n_utt, c, device=device), -1))
+            labels, label_lengths = synthetic_labels(input_lengths, c, seed=head)
+            labels_l.append(labels.to(device))
+            lens_l.append(label_lengths.to(device))
+        il = input_lengths.to(device)
+        problem = ops.CtcProblem(log_probs, labels_l, lens_l, il, batch_first=False, need_grad=True)
+        scale = torch.ones(len(classes), device=device)
+        valid = int(input_lengths.sum())
+        lp_bytes = float(sum(valid * c * 4 for c in classes))
+        alpha_bytes = float(valid * problem.s_pad * 4 * len(classes))
+        note = "latency-bound recursion over T' sequential frames: bytes / time is far from the HBM roofline by construction"
+        report("ctc_forward (alpha kept)", f"{n_utt} utt x 37 heads, T' <= 749", timeit(problem.forward, iters=10), lp_bytes + alpha_bytes, note)
+        report("ctc_backward (beta + gradient)", f"{n_utt} utt x 37 heads, T' <= 749", timeit(lambda: problem.backward(scale), iters=10), 2 * lp_bytes + alpha_bytes, note)
+
+    am3 = torch.randint(0, 4, (37, rows2), dtype=torch.int32, device=device)
+    mx3 = torch.randn(37, rows2, device=device)
+    fl = torch.full((32,), 499, dtype=torch.int32, device=device)
+    report("ctc_greedy_collapse", "37 heads x 32 utt x 499", timeit(lambda: ops.ctc_greedy_collapse(am3, mx3, fl, 32, 499, 37 * 32, 0)), 37 * rows2 * 8.0, "4.7 MB: latency-bound")
+    torch.cuda.empty_cache()
+    return records
 
 
 # --------------------------------------------------------------------------------------------------
@@ -594,36 +728,50 @@ def build_training_estimator(device: str):
     return estimator, allophones
 
 
-def run_train_arm(args) -> None:
-    from allophant_b200 import ops
-    from allophant_b200.dataset_processing import Batch
-    from allophant_b200.distributed import GradientReducer, attach_gradient_reducer, global_label_count
-    from allophant_b200.loss_functions import multi_head_ctc_loss
-
+def setup_process():
+    """(world, rank, local_rank, device, distributed) of this process; joins the NCCL group when launched under torchrun."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: allophant_b200 has no CPU path")
+        raise RuntimeError("bench.py needs a CUDA device: allophant_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     device = f"cuda:{local_rank}"
     distributed = world > 1
     if distributed:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=torch.device(device))
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device(device))
+    return world, rank, local_rank, device, distributed
+
+
+def measure_training(process, steps: int, warmup: int, eval_arithmetic: bool, detail: bool = True) -> Optional[Dict[str, Any]]:
+    """BASELINE configs[2] on this process group: forward + 37-head CTC + backward (+ overlapped NCCL gradient all-reduce) +
+    global-norm clip + Adam + warm-up LR.  EVERY rank runs the SAME per-rank batch (8 utterances, U[3 s, 15 s], seed 3), so
+    the per-rank work does not depend on N and the weak-scaling curve isolates the exchange step.  Returns the record on
+    rank 0 (None elsewhere): device-timed step, end-to-end step, launches, the GEMM roofline and — for N > 1 — the all-reduce
+    bytes and its EXPOSED time (step with the reducer minus the same step without it, both max over ranks)."""
+    from allophant_b200 import ops, optim
+    from allophant_b200.dataset_processing import Batch
+    from allophant_b200.distributed import GradientReducer, attach_gradient_reducer, global_label_count
+    from allophant_b200.loss_functions import multi_head_ctc_loss
+
+    world, rank, local_rank, device, distributed = process
+    if distributed:
+        import torch.distributed as dist
 
     estimator, allophones = build_training_estimator(device)
     model = estimator.model
     # train() mode (SURVEY.md §8d config 3): HF dropout 0.1 / attention dropout 0.1 / LayerDrop 0.1 / SpecAugment 0.075 are
     # applied by the CUDA path with counter-based masks; --eval-arithmetic times the deterministic arithmetic instead
-    model.train(not args.eval_arithmetic)
+    model.train(not eval_arithmetic)
     wire = torch.bfloat16 if os.environ.get("BENCH_ALLREDUCE_BF16") == "1" else None  # experiment: gradients as bf16 on the wire
     reducer = GradientReducer(wire_dtype=wire) if distributed else None
     attach_gradient_reducer(model, reducer)
 
-    # variable-length batch: U[3 s, 15 s], sorted, zero padded to the rank's longest utterance
-    generator = torch.Generator().manual_seed(3 + rank)
+    # variable-length batch: U[3 s, 15 s] (BASELINE.md config 3), sorted, zero padded to the longest utterance; the same on every rank
+    generator = torch.Generator().manual_seed(3)
     seconds = 3.0 + 12.0 * torch.rand(TRAIN_BATCH, generator=generator)
     lengths = (seconds * SAMPLE_RATE).long().sort(descending=True).values
     samples = int(lengths.max())
@@ -650,8 +798,7 @@ def run_train_arm(args) -> None:
     resident = Batch(host_audio.to(device), host_lengths.to(device), host_languages.to(device))
     labels_dev = {name: value.to(device) for name, value in labels_host.items()}
     label_lengths_dev = {name: value.to(device) for name, value in label_lengths_host.items()}
-    parameters = [parameter for parameter in model.parameters() if parameter.requires_grad]
-    from allophant_b200 import optim
+    parameters = list(model.parameters())  # all of them, as the reference hands them to the optimizer (estimator.py:982)
 
     # default_config.toml:107-121: Adam(0.9, 0.98), lr 1e-3 under the warm-up schedule; global-norm clipping folded into the Adam pass
     optimizer = optim.adam_from_config(parameters, model.d_model, model=model)
@@ -685,122 +832,138 @@ def run_train_arm(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
+    def timed_steps(count: int) -> float:
+        """milliseconds for `count` steps: barrier + synchronize on both sides, device events, max over ranks"""
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        start.record()
+        for _ in range(count):
+            device_step()
+        end.record()
+        barrier()
+        elapsed = torch.tensor([start.elapsed_time(end)], device=device)
+        if distributed:
+            dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+        return float(elapsed.item())
+
+    for _ in range(max(3, warmup)):
         loss = device_step()
     if not torch.isfinite(loss):
         raise RuntimeError(f"training loss is not finite: {float(loss)}")
     ops.reset_launch_count()
     collectives_before = (reducer.issued, reducer.bytes) if reducer is not None else (0, 0)
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as sampler:
-        barrier()
-        start.record()
-        for _ in range(args.steps):
-            device_step()
-        end.record()
-        barrier()
+        elapsed_ms = timed_steps(steps)
     collectives = None
     if reducer is not None:
         collectives = {
-            "collectives_per_step": (reducer.issued - collectives_before[0]) // args.steps,
-            "bytes_per_step": (reducer.bytes - collectives_before[1]) // args.steps,
+            "collectives_per_step": (reducer.issued - collectives_before[0]) // steps,
+            "bytes_per_step": (reducer.bytes - collectives_before[1]) // steps,
+            "wire_dtype": "bf16" if wire is not None else "f32",
         }
-    elapsed = torch.tensor([start.elapsed_time(end)], device=device)
-    if distributed:
-        dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(elapsed.item())
-    launches = ops.launch_count() // args.steps
+    launches = ops.launch_count() // steps
     clocks = sampler.summary()
+    if reducer is not None:
+        # the same steps WITHOUT the exchange (every rank keeps its local gradients): the difference is what the all-reduce
+        # adds to the step, i.e. the part of it that the backward pass does not hide
+        attach_gradient_reducer(model, None)
+        device_step()
+        local_ms = timed_steps(steps)
+        attach_gradient_reducer(model, reducer)
+        device_step()
+        collectives["step_ms_without_allreduce"] = local_ms / steps
+        collectives["exposed_ms_per_step"] = (elapsed_ms - local_ms) / steps
 
     for _ in range(2):
         e2e_step()
     barrier()
     wall_start = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         e2e_step()
     barrier()
     e2e_seconds = torch.tensor([time.perf_counter() - wall_start], device=device)
-    local_audio = torch.tensor([float(lengths.sum()) / SAMPLE_RATE], device=device)
     if distributed:
         dist.all_reduce(e2e_seconds, op=dist.ReduceOp.MAX)
-        dist.all_reduce(local_audio, op=dist.ReduceOp.SUM)
-    audio_seconds = float(local_audio.item()) * args.steps
+    audio_seconds = world * float(lengths.sum()) / SAMPLE_RATE * steps
     h2d_bytes = host_audio.numel() * 4 + 16 * TRAIN_BATCH + sum(v.numel() * 8 for v in labels_host.values()) + sum(
         v.numel() * 8 for v in label_lengths_host.values()
     )
 
     # ---- roofline of the dominant kernel: every rank runs one more step (it contains collectives), rank 0 times its GEMMs
     roofline = None
-    gemm_events: List[Any] = []
-    original = ops.run_gemm
-    sizes = (1024, 3072, 4096)
+    if detail:
+        gemm_events: List[Any] = []
+        original = ops.run_gemm
+        sizes = (1024, 3072, 4096)
 
-    def is_encoder_linear(gemm_args) -> bool:
-        return gemm_args.mode == 0 and gemm_args.n in sizes and (
-            (not gemm_args.b_mn_major and gemm_args.k in sizes) or (gemm_args.b_mn_major and not gemm_args.a_mn_major and gemm_args.k_seq in sizes)
-            or (gemm_args.a_mn_major and gemm_args.a_rows in sizes)
-        )
+        def is_encoder_linear(gemm_args) -> bool:
+            return gemm_args.mode == 0 and gemm_args.n in sizes and (
+                (not gemm_args.b_mn_major and gemm_args.k in sizes) or (gemm_args.b_mn_major and not gemm_args.a_mn_major and gemm_args.k_seq in sizes)
+                or (gemm_args.a_mn_major and gemm_args.a_rows in sizes)
+            )
 
-    def timed_gemm(gemm_args):
-        if is_encoder_linear(gemm_args):
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()
-            original(gemm_args)
-            ev1.record()
-            gemm_events.append((ev0, ev1))
-        else:
-            original(gemm_args)
+        def timed_gemm(gemm_args):
+            if is_encoder_linear(gemm_args):
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                original(gemm_args)
+                ev1.record()
+                gemm_events.append((ev0, ev1))
+            else:
+                original(gemm_args)
 
-    if rank == 0:
-        ops.run_gemm = timed_gemm
-    try:
-        device_step()
-        torch.cuda.synchronize()
-    finally:
-        ops.run_gemm = original
-    if rank == 0:
-        plan_frames = int(frames.max())
-        gemm_ms = sum(a.elapsed_time(b) for a, b in gemm_events)
-        flops = 3.0 * encoder_flops(plan_frames)["linear"] * TRAIN_BATCH  # forward + dgrad + wgrad over the padded frame count
-        skipped = list(model._heads.last_regularisation["plan"].skipped)  # LayerDrop decisions of this very step
-        flops *= (len(skipped) - sum(skipped)) / max(1, len(skipped))
-        peaks = measured_peaks()
-        achieved = flops / (gemm_ms / 1000.0) / 1e12
-        peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
-        roofline = {
-            "kernel": "aph::gemm_bf16_kernel (encoder linears: forward, data-gradient and weight-gradient forms)",
-            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-            "peak_source": f"bf16_tflops_sustained, {peaks['source']}", "launches": len(gemm_events),
-            "avg_launch_ms": gemm_ms / max(1, len(gemm_events)), "share_of_step": gemm_ms / (elapsed_ms / args.steps),
-        }  # fmt: skip
-    # one more step on every rank (collectives inside): rank 0 reads the un-bracketed kernel durations from CUPTI
-    if rank == 0:
-        unbracketed = cupti_gemm_time(device_step, is_encoder_linear)
-        if unbracketed is not None and roofline is not None:
-            count, total_ms = unbracketed
-            skipped = list(model._heads.last_regularisation["plan"].skipped)
-            step_flops = 3.0 * encoder_flops(int(frames.max()))["linear"] * TRAIN_BATCH * (len(skipped) - sum(skipped)) / max(1, len(skipped))
-            roofline["kernel_only"] = {
-                "source": "CUPTI kernel records of one un-bracketed step (torch.profiler), the same launches as the event brackets",
-                "launches": count, "avg_launch_ms": total_ms / max(1, count), "achieved": step_flops / (total_ms / 1000.0) / 1e12,
-                "frac": step_flops / (total_ms / 1000.0) / 1e12 / roofline["peak"], "share_of_step": total_ms / (elapsed_ms / args.steps),
+        if rank == 0:
+            ops.run_gemm = timed_gemm
+        try:
+            device_step()
+            torch.cuda.synchronize()
+        finally:
+            ops.run_gemm = original
+        if rank == 0:
+            plan_frames = int(frames.max())
+            gemm_ms = sum(a.elapsed_time(b) for a, b in gemm_events)
+            flops = 3.0 * encoder_flops(plan_frames)["linear"] * TRAIN_BATCH  # forward + dgrad + wgrad over the padded frame count
+            skipped = list(model._heads.last_regularisation["plan"].skipped)  # LayerDrop decisions of this very step
+            flops *= (len(skipped) - sum(skipped)) / max(1, len(skipped))
+            peaks = measured_peaks()
+            achieved = flops / (gemm_ms / 1000.0) / 1e12
+            peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+            roofline = {
+                "kernel": "aph::gemm_bf16_kernel (encoder linears: forward, data-gradient and weight-gradient forms)",
+                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": f"bf16_tflops_sustained, {peaks['source']}", "launches": len(gemm_events),
+                "avg_launch_ms": gemm_ms / max(1, len(gemm_events)), "share_of_step": gemm_ms / (elapsed_ms / steps),
             }  # fmt: skip
-    else:
-        device_step()
-        torch.cuda.synchronize()
+        # one more step on every rank (collectives inside): rank 0 reads the un-bracketed kernel durations from CUPTI
+        if rank == 0:
+            unbracketed = cupti_gemm_time(device_step, is_encoder_linear)
+            if unbracketed is not None and roofline is not None:
+                count, total_ms = unbracketed
+                skipped = list(model._heads.last_regularisation["plan"].skipped)
+                step_flops = 3.0 * encoder_flops(int(frames.max()))["linear"] * TRAIN_BATCH * (len(skipped) - sum(skipped)) / max(1, len(skipped))
+                roofline["kernel_only"] = {
+                    "source": "CUPTI kernel records of one un-bracketed step (torch.profiler), the same launches as the event brackets",
+                    "launches": count, "avg_launch_ms": total_ms / max(1, count), "achieved": step_flops / (total_ms / 1000.0) / 1e12,
+                    "frac": step_flops / (total_ms / 1000.0) / 1e12 / roofline["peak"], "share_of_step": total_ms / (elapsed_ms / steps),
+                }  # fmt: skip
+        else:
+            device_step()
+            torch.cuda.synchronize()
+    attach_gradient_reducer(model, None)
+    del optimizer, estimator, model
+    torch.cuda.empty_cache()
     if distributed:
         dist.barrier()
-        dist.destroy_process_group()
     if rank != 0:
-        return
-    line = {
+        return None
+    return {
         "metric": "audio-sec/sec, multitask training step (forward + multi-head CTC + backward + gradient all-reduce + optimizer)",
         "value": audio_seconds / (elapsed_ms / 1000.0),
         "unit": UNIT,
         "n_gpus": world,
-        "steps": args.steps,
-        "warmup": max(3, args.warmup),
-        "ms_per_step": elapsed_ms / args.steps,
+        "steps": steps,
+        "warmup": max(3, warmup),
+        "ms_per_step": elapsed_ms / steps,
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
@@ -809,10 +972,11 @@ def run_train_arm(args) -> None:
         "config": {
             "workload": "BASELINE configs[2]: Allophant Multitask (XLS-R-300M shape, random init, allophone layer over "
             f"{TRAIN_LANGUAGES} languages x {TRAIN_PHONES} phones, feature extractor frozen) training step: forward + 37-head CTC + backward"
-            f"{' + overlapped NCCL gradient all-reduce' if distributed else ''} + global-norm clip + Adam + warm-up LR; {TRAIN_BATCH} utterances per GPU, "
-            "U[3 s, 15 s], " + ("eval()-mode arithmetic (no dropout / LayerDrop / SpecAugment)" if args.eval_arithmetic else
+            f"{' + overlapped NCCL gradient all-reduce' if distributed else ''} + global-norm clip + Adam + warm-up LR; {TRAIN_BATCH} utterances per GPU "
+            "(the same batch on every rank), U[3 s, 15 s], " + ("eval()-mode arithmetic (no dropout / LayerDrop / SpecAugment)" if eval_arithmetic else
                                 "train() mode: hidden/attention/feature-projection dropout 0.1, LayerDrop 0.1, SpecAugment 0.075 x 10 frames"),
             "batch_per_gpu": TRAIN_BATCH,
+            "audio_seconds_per_gpu": float(lengths.sum()) / SAMPLE_RATE,
             "padded_seconds": samples / SAMPLE_RATE,
             "parallelism": f"dp{world}",
             "allreduce": collectives,
@@ -824,7 +988,17 @@ def run_train_arm(args) -> None:
         "roofline": roofline,
         "cpu_baseline": None,
     }
-    print(json.dumps(line), flush=True)
+
+
+def run_train_arm(args) -> None:
+    process = setup_process()
+    line = measure_training(process, args.steps, args.warmup, args.eval_arithmetic)
+    if process[4]:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 def main() -> None:
@@ -835,6 +1009,9 @@ def main() -> None:
     parser.add_argument("--warmup", type=int, default=3)
     parser.add_argument("--impl", choices=["b200", "reference"], default="b200")
     parser.add_argument("--skip-cpu-baseline", action="store_true")
+    parser.add_argument("--skip-train", action="store_true", help="predict workload: leave out the `train` sub-record (configs[2] step on the same ranks)")
+    parser.add_argument("--skip-membound", action="store_true", help="predict workload: leave out the `membound` sub-record (HBM-bound kernels, N = 1)")
+    parser.add_argument("--train-steps", type=int, default=5, help="timed steps of the `train` sub-record")
     parser.add_argument("--eval-arithmetic", action="store_true", help="train workload: eval()-mode arithmetic (no dropout / LayerDrop / SpecAugment)")
     parser.add_argument("--batch", type=int, default=BATCH, help="utterances per GPU (predict workload)")
     parser.add_argument("--seconds", type=int, default=SECONDS, help="seconds per utterance (predict workload)")

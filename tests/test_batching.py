@@ -116,3 +116,25 @@ def test_shard_for_rank_covers_the_batch():
         assert shard.audio_features.shape[1] == int(shard.lengths.max())
         seen += shard.language_ids.tolist()
     assert sorted(seen) == [0, 1, 2, 3, 4]
+
+
+def test_live_batches_do_not_alias_each_other():
+    """Any number of collated batches may be alive at once (the reference's ``_training_batch_accumulation`` holds
+    ``accumulation_factor`` host batches before ``.to(device)``): every batch owns its buffer."""
+    import torch
+
+    from allophant_b200.batching import build_batch
+    from allophant_b200.dataset_processing import Batch, BatchType
+
+    collate = build_batch(BatchType.UNLABELED)
+    batches = []
+    for value in range(7):
+        entries = [Batch(torch.full((100 + 10 * i,), float(value + 1)), torch.tensor(100 + 10 * i), torch.tensor(0)) for i in range(3)]
+        batches.append(collate(entries))
+    pointers = {batch.audio_features.data_ptr() for batch in batches}
+    assert len(pointers) == len(batches)
+    for value, batch in enumerate(batches):
+        assert batch.audio_features.shape == (3, 120)
+        for row in range(3):
+            assert bool((batch.audio_features[row, : 100 + 10 * row] == value + 1).all())
+            assert bool((batch.audio_features[row, 100 + 10 * row :] == 0).all())

@@ -416,6 +416,58 @@ def test_backward_after_overwrite_raises(training_case):
         next(iter(first.outputs.values())).sum().backward()
 
 
+def test_optimizer_holds_parameters_that_are_unfrozen_later(training_case):
+    """``optimizer_from_config`` hands the optimizer ALL parameters like the reference (``estimator.py:982``): the feature
+    extractor is frozen at construction (``freeze_feature_encoder`` defaults to true) and unfrozen by ``UnfreezeSchedule.step``
+    afterwards — it must then be updated (and the packed conv operands refreshed), and the param_groups must be the
+    reference's (one group holding every parameter, so that a reference optimizer state_dict loads)."""
+    if training_case["name"] != "multitask_2layer":
+        pytest.skip("one architecture is enough")
+    from allophant_b200 import optim
+    from allophant_b200.config import Architecture, ProjectionConfig
+    from allophant_b200.network.acoustic_model import UnfreezeSchedule
+
+    fixture, model = training_case["fixture"], training_case["model"]
+    model.eval()
+    extractor = [(name, parameter) for name, parameter in model.named_parameters() if ".feature_extractor." in name]
+    assert not any(parameter.requires_grad for _, parameter in extractor)
+    before = {name: parameter.detach().clone() for name, parameter in model.named_parameters()}
+    architecture = Architecture(1, ProjectionConfig([]), None, optimizer=dict(algorithm="adam", learning_rate=1e-4), lr_schedule=None)
+    wrapper = optim.optimizer_from_config(architecture, model)
+    assert [len(group["params"]) for group in wrapper.param_groups] == [len(list(model.parameters()))]
+    schedule = UnfreezeSchedule(feature_extractor=1)
+    try:
+        _training_step(model, training_case["batch"], fixture)
+        wrapper.step(clip_norm=1.0)
+        assert all(torch.equal(parameter, before[name]) for name, parameter in extractor)  # still frozen: untouched
+        schedule.step(model.acoustic_model)
+        assert all(parameter.requires_grad for _, parameter in extractor)
+        first_logits = None
+        for _ in range(2):
+            _training_step(model, training_case["batch"], fixture)
+            wrapper.step(clip_norm=1.0)
+        moved = [name for name, parameter in extractor if not torch.equal(parameter, before[name])]
+        assert len(moved) == len(extractor), sorted(set(n for n, _ in extractor) - set(moved))[:4]
+        # the forward pass sees the updated conv operands (the pack is refilled, not stale)
+        with torch.inference_mode():
+            first_logits = model(training_case["batch"], predict=True).outputs["stress"].clone()
+        state = wrapper.state_dict()["optimizer"]
+        assert len(state["param_groups"][0]["params"]) == len(before)
+    finally:
+        with torch.no_grad():
+            for name, parameter in model.named_parameters():
+                parameter.copy_(before[name])
+                parameter.grad = None
+        for _, parameter in extractor:
+            parameter.requires_grad = False
+        from allophant_b200 import engine
+
+        engine.bump_weight_generation()
+    with torch.inference_mode():
+        restored = model(training_case["batch"], predict=True).outputs["stress"]
+    assert first_logits is not None and not torch.equal(first_logits, restored)
+
+
 # ------------------------------------------------------------------------------------------ optimiser step
 def test_fused_adam_and_clipping_match_torch():
     """FusedAdam / clip_grad_norm_ (multi-tensor kernels) against torch.optim.Adam / nn.utils.clip_grad_norm_ on the same
