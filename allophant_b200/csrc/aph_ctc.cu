@@ -442,7 +442,7 @@ __global__ void ctc_reduce_kernel(const float* __restrict__ nll, int n_heads, in
   float s = 0.f;
   for (int n = lane; n < n_utt; n += 32) {
     const float v = nll[static_cast<long long>(h) * n_utt + n];
-    if (v < INFINITY) s += v;
+    if (v != INFINITY) s += v;  // zero_infinity drops +inf only: a NaN loss (diverged logits) stays visible, as in torch
   }
   s = warp_sum(s);
   if (lane == 0) loss_out[h] = s;

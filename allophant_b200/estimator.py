@@ -125,7 +125,27 @@ class Estimator:
         return self.model.map_allophones(phone_logits, language_ids)
 
     # -- checkpoints --------------------------------------------------------------------------
-    def checkpoint(self, attribute_indexer: Optional[PhoneticAttributeIndexer] = None) -> Dict[str, Any]:
+    @staticmethod
+    def _indexer_state(state: Any) -> Optional[Dict[str, Any]]:
+        """``PhoneticIndexerState`` as the plain dictionary a checkpoint holds; an indexer is asked for its state."""
+        if state is None or isinstance(state, dict):
+            return state
+        if hasattr(state, "state"):
+            return state.state()
+        allophones = state.language_allophones
+        if allophones is not None and not isinstance(allophones, dict):
+            allophones = {"allophones": allophones.allophones, "languages": allophones.languages, "shared_phones": allophones.shared_phones}
+        return {"phoneme_inventory": list(state.phoneme_inventory), "language_allophones": allophones, "table_file": state.table_file}
+
+    def checkpoint(
+        self,
+        phonetic_indexer_state: Any = None,
+        optimizer_state: Optional[Dict[str, Any]] = None,
+        additional_parameters: Optional[Dict[str, Any]] = None,
+    ) -> Dict[str, Any]:
+        """The checkpoint dictionary (``estimator.py:199-227``).  ``optimizer_state`` is the ``state_dict()`` of the optimizer
+        (or of the ``OptimizerWrapper``, which includes the schedule's step); there is no gradient scaler (bf16 operands,
+        fp32 master weights), so ``grad_scaler`` is always ``None``."""
         return {
             "config": self.config.dump(),
             "allophant_version": __version__,
@@ -133,16 +153,29 @@ class Estimator:
             "sample_rate": self.sample_rate,
             "attribute_graph": self.attribute_graph.state(),
             "epoch": dict(self.epoch),
-            "phonetic_indexer_state": None if attribute_indexer is None else attribute_indexer.state(),
+            "phonetic_indexer_state": self._indexer_state(phonetic_indexer_state),
             "dataset_meta_data": list(self.dataset_meta_data),
             "model_state": self.model.state_dict(),
-            "additional": {},
+            "additional": additional_parameters,
             "history": list(self.history),
-            "optimization_states": None,
+            "optimization_states": None if optimizer_state is None else {"optimizer": optimizer_state, "grad_scaler": None},
         }
 
-    def save(self, file: Any, attribute_indexer: Optional[PhoneticAttributeIndexer] = None) -> None:
-        torch.save(self.checkpoint(attribute_indexer), file)
+    def save(
+        self,
+        file: Any,
+        optimizer_state: Any = None,
+        phonetic_indexer_state: Any = None,
+        additional_parameters: Optional[Dict[str, Any]] = None,
+    ) -> None:
+        """``save(file, optimizer_state, phonetic_indexer_state, additional_parameters)`` as in ``estimator.py:1051-1083``.
+        For convenience the indexer itself may be passed instead of its state, also in the second position
+        (``save(file, indexer)``, the form earlier versions of this package used)."""
+        if phonetic_indexer_state is None and optimizer_state is not None and hasattr(optimizer_state, "phonemes"):
+            optimizer_state, phonetic_indexer_state = None, optimizer_state
+        if phonetic_indexer_state is None:
+            raise ValueError("a checkpoint needs the phonetic indexer state (the reference's Checkpoint schema requires it)")
+        torch.save(self.checkpoint(phonetic_indexer_state, optimizer_state, additional_parameters), file)
 
     @classmethod
     def restore(
@@ -163,7 +196,7 @@ class Estimator:
             entry.name for entry in config.nn.projection.classes if entry.name != ProjectionEntryConfig.PHONEME_LAYER
         ]
         if attribute_indexer is None:
-            attribute_indexer = PhoneticAttributeIndexer.from_state(checkpoint["phonetic_indexer_state"], composition_features)
+            attribute_indexer = PhoneticAttributeIndexer.from_state(checkpoint["phonetic_indexer_state"], composition_features, config)
         graph = AttributeGraph.from_state(checkpoint["attribute_graph"])
         estimator = cls.from_config(
             config, checkpoint["feature_size"], checkpoint["sample_rate"], graph, attribute_indexer, device, load_pretrained_weights=False
