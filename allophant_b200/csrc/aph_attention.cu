@@ -69,14 +69,11 @@ template <bool kDrop>
 __global__ void __launch_bounds__(kAttThreads, 2)
     attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                      const __grid_constant__ CUtensorMap tm_v, const AttParams p) {
+  pdl_trigger();
   const int bh = blockIdx.y;
   const int b = bh / p.heads;
   const int h = bh - b * p.heads;
   const int q0 = blockIdx.x * kAttQ;
-  int len = p.lengths[b];
-  len = len < p.T ? len : p.T;
-  if (q0 >= len) return;  // whole tile is padding (uniform per CTA, before any barrier/TMEM use)
-  const int n_kv = (len + kAttKV - 1) / kAttKV;
   if (threadIdx.x == 0) APH_STAMP(0);
 
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -129,8 +126,15 @@ __global__ void __launch_bounds__(kAttThreads, 2)
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + 128;
   if (threadIdx.x == 0) APH_STAMP(1);
+  // Everything above (barriers, TMEM) overlapped the previous kernel's tail; frame counts, Q, K and V are its results.
+  pdl_wait();
+  int len = p.lengths[b];
+  len = len < p.T ? len : p.T;
+  const int n_kv = (len + kAttKV - 1) / kAttKV;
+  const bool active = q0 < len;  // false: the whole tile is padding (uniform per CTA) -> straight to the teardown
 
-  if (warp == 4) {
+  if (!active) {
+  } else if (warp == 4) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, kAttQBytes);
@@ -386,9 +390,9 @@ extern "C" int aph_attention_bf16_dropout(const void* q, const void* k, const vo
   p.drop_seed = drop_seed;
   p.drop_scale = drop_scale;
   if (drop_threshold != 0)
-    attention_kernel<true><<<grid, kAttThreads, kAttSmemBytes, stream>>>(tm_q, tm_k, tm_v, p);
+    APH_CUDA_CHECK(launch_pdl(attention_kernel<true>, grid, dim3(kAttThreads), kAttSmemBytes, stream, tm_q, tm_k, tm_v, p));
   else
-    attention_kernel<false><<<grid, kAttThreads, kAttSmemBytes, stream>>>(tm_q, tm_k, tm_v, p);
+    APH_CUDA_CHECK(launch_pdl(attention_kernel<false>, grid, dim3(kAttThreads), kAttSmemBytes, stream, tm_q, tm_k, tm_v, p));
   APH_POST_LAUNCH(1);
   return APH_OK;
 }

@@ -19,6 +19,8 @@ namespace aph {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) wave_stats_kernel(const float* __restrict__ x, const long long* __restrict__ lengths,
                                                          int T, double* __restrict__ stats) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const long long len = lengths[b];
   const float* row = x + static_cast<long long>(b) * T;
@@ -64,6 +66,8 @@ __global__ void __launch_bounds__(256) wave_stats_kernel(const float* __restrict
 // mean / rstd per utterance from the three sums (fp64, then rounded to fp32)
 __global__ void wave_finalize_kernel(const double* __restrict__ stats, const long long* __restrict__ lengths, int n,
                                      float2* __restrict__ mean_rstd) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n) return;
   const double len = static_cast<double>(lengths[b]);
@@ -90,6 +94,8 @@ __global__ void __launch_bounds__(256) wave_norm_kernel(const float* __restrict_
 __global__ void frame_lengths_kernel(const long long* __restrict__ lengths, int n, const int* __restrict__ kernels,
                                      const int* __restrict__ strides, int n_layers, int* __restrict__ frames32,
                                      long long* __restrict__ frames64) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n) return;
   long long L = lengths[b];
@@ -126,6 +132,8 @@ __global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ x,
                                                     float* __restrict__ raw_out /*GroupNorm path: fp32 conv output*/,
                                                     double* __restrict__ gn_stats /*[N][512][2] or null*/,
                                                     int skip_padded) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float w_s[kK0][kC0];
   __shared__ float b_s[kC0], g_s[kC0], be_s[kC0];
   for (int i = threadIdx.x; i < kC0 * kK0; i += blockDim.x) w_s[i % kK0][i / kK0] = w[i];
@@ -199,9 +207,9 @@ __global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ x,
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int c = 2 * lane + 64 * i;
-          const float v0 = gelu_erf((acc[tt][2 * i] - mean) * rstd * g_s[c] + be_s[c]);
-          const float v1 = gelu_erf((acc[tt][2 * i + 1] - mean) * rstd * g_s[c + 1] + be_s[c + 1]);
-          *reinterpret_cast<uint32_t*>(dst + c) = pack_bf16x2(v0, v1);
+          const float2 v = gelu_erf2(make_float2((acc[tt][2 * i] - mean) * rstd * g_s[c] + be_s[c],
+                                                 (acc[tt][2 * i + 1] - mean) * rstd * g_s[c + 1] + be_s[c + 1]));
+          *reinterpret_cast<uint32_t*>(dst + c) = pack_bf16x2(v.x, v.y);
         }
       } else {
         // GroupNorm(512 groups): statistics run over the whole (padded) time axis per channel
@@ -271,6 +279,8 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const TIn* __restri
                                                              float eps, int gelu, __nv_bfloat16* __restrict__ out_bf16,
                                                              long long ld_bf16, float* __restrict__ out_f32,
                                                              long long ld_f32) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int kPer = kCols / 32;  // elements per lane
   constexpr int kVec = 8;           // elements per vector chunk
   constexpr int kChunks = kPer / kVec;
@@ -325,9 +335,14 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const TIn* __restri
     const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     float o[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      o[i] = (v[c * kVec + i] - mean) * rstd * g[i] + be[i];
-      if (gelu) o[i] = gelu_erf(o[i]);
+    for (int i = 0; i < 8; ++i) o[i] = (v[c * kVec + i] - mean) * rstd * g[i] + be[i];
+    if (gelu) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 a = gelu_erf2(make_float2(o[2 * i], o[2 * i + 1]));
+        o[2 * i] = a.x;
+        o[2 * i + 1] = a.y;
+      }
     }
     if (out_bf16) {
       uint4 u;
@@ -362,10 +377,10 @@ extern "C" int aph_wave_stats(const float* x, const int64_t* lengths, int32_t n_
   APH_REQUIRE(n_utt > 0 && T > 0, "empty batch");
   APH_CUDA_CHECK(cudaMemsetAsync(stats_scratch, 0, sizeof(double) * 3 * n_utt, stream));
   const int chunks = grid_for(T, 256 * 16, ceil_div(4 * sm_count(), n_utt) > 0 ? ceil_div(4 * sm_count(), n_utt) : 1);
-  wave_stats_kernel<<<dim3(chunks, n_utt), 256, 0, stream>>>(x, reinterpret_cast<const long long*>(lengths), T,
-                                                            stats_scratch);
-  wave_finalize_kernel<<<ceil_div(n_utt, 128), 128, 0, stream>>>(stats_scratch, reinterpret_cast<const long long*>(lengths),
-                                                                 n_utt, reinterpret_cast<float2*>(mean_rstd));
+  APH_CUDA_CHECK(launch_pdl(wave_stats_kernel, dim3(chunks, n_utt), dim3(256), 0, stream, x, reinterpret_cast<const long long*>(lengths), T,
+                            stats_scratch));
+  APH_CUDA_CHECK(launch_pdl(wave_finalize_kernel, dim3(ceil_div(n_utt, 128)), dim3(128), 0, stream, stats_scratch,
+                            reinterpret_cast<const long long*>(lengths), n_utt, reinterpret_cast<float2*>(mean_rstd)));
   APH_POST_LAUNCH(2);
   return APH_OK;
 }
@@ -387,9 +402,9 @@ extern "C" int aph_frame_lengths(const int64_t* lengths, int32_t n_utt, const in
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   APH_REQUIRE(lengths && kernels && strides, "null pointer");
   APH_REQUIRE(n_utt > 0 && n_layers >= 0, "empty batch");
-  frame_lengths_kernel<<<ceil_div(n_utt, 128), 128, 0, stream>>>(reinterpret_cast<const long long*>(lengths), n_utt, kernels,
-                                                                 strides, n_layers, frames32,
-                                                                 reinterpret_cast<long long*>(frames64));
+  APH_CUDA_CHECK(launch_pdl(frame_lengths_kernel, dim3(ceil_div(n_utt, 128)), dim3(128), 0, stream,
+                            reinterpret_cast<const long long*>(lengths), n_utt, kernels, strides, n_layers, frames32,
+                            reinterpret_cast<long long*>(frames64)));
   APH_POST_LAUNCH(1);
   return APH_OK;
 }
@@ -402,10 +417,10 @@ extern "C" int aph_conv0_ln_gelu(const float* x, const int64_t* lengths, const f
   APH_REQUIRE(n_utt > 0 && T >= kK0, "waveform shorter than the first conv kernel");
   const int L0 = (T - kK0) / kS0 + 1;
   const int gx = grid_for(L0, 8 * kTT * 4, ceil_div(8 * sm_count(), n_utt) > 0 ? ceil_div(8 * sm_count(), n_utt) : 1);
-  conv0_kernel<true><<<dim3(gx, n_utt), 256, 0, stream>>>(x, reinterpret_cast<const long long*>(lengths),
-                                                         reinterpret_cast<const float2*>(mean_rstd), T, L0, w, bias, gamma,
-                                                         beta, eps, static_cast<__nv_bfloat16*>(out_bf16), nullptr, nullptr,
-                                                         skip_padded_frames);
+  APH_CUDA_CHECK(launch_pdl(conv0_kernel<true>, dim3(gx, n_utt), dim3(256), 0, stream, x, reinterpret_cast<const long long*>(lengths),
+                            reinterpret_cast<const float2*>(mean_rstd), T, L0, w, bias, gamma, beta, eps,
+                            static_cast<__nv_bfloat16*>(out_bf16), static_cast<float*>(nullptr), static_cast<double*>(nullptr),
+                            skip_padded_frames));
   APH_POST_LAUNCH(1);
   return APH_OK;
 }
@@ -419,9 +434,9 @@ extern "C" int aph_conv0_gn_gelu(const float* x, const int64_t* lengths, const f
   const int L0 = (T - kK0) / kS0 + 1;
   APH_CUDA_CHECK(cudaMemsetAsync(stats_scratch, 0, sizeof(double) * 2 * kC0 * n_utt, stream));
   const int gx = grid_for(L0, 8 * kTT * 16, ceil_div(4 * sm_count(), n_utt) > 0 ? ceil_div(4 * sm_count(), n_utt) : 1);
-  conv0_kernel<false><<<dim3(gx, n_utt), 256, 0, stream>>>(x, reinterpret_cast<const long long*>(lengths),
-                                                          reinterpret_cast<const float2*>(mean_rstd), T, L0, w, bias,
-                                                          nullptr, nullptr, eps, nullptr, raw_scratch, stats_scratch, 0);
+  APH_CUDA_CHECK(launch_pdl(conv0_kernel<false>, dim3(gx, n_utt), dim3(256), 0, stream, x, reinterpret_cast<const long long*>(lengths),
+                            reinterpret_cast<const float2*>(mean_rstd), T, L0, w, bias, static_cast<const float*>(nullptr),
+                            static_cast<const float*>(nullptr), eps, static_cast<__nv_bfloat16*>(nullptr), raw_scratch, stats_scratch, 0));
   const int gy = grid_for(static_cast<long long>(L0) * kC0 / 4, 256 * 8, 2048);
   groupnorm_apply_kernel<<<dim3(gy, n_utt), 256, 0, stream>>>(raw_scratch, stats_scratch, L0, gamma, beta, eps,
                                                              static_cast<__nv_bfloat16*>(out_bf16));
@@ -443,15 +458,15 @@ extern "C" int aph_layernorm_rows(const void* in, int32_t in_is_f32, int64_t ld_
   if (in_is_f32) {
     const float* p = static_cast<const float*>(in);
     if (cols == 512)
-      layernorm_rows_kernel<float, 512><<<grid, 256, 0, stream>>>(p, ld_in, rows, gamma, beta, eps, gelu, ob, ld_bf16, out_f32, ld_f32);
+      APH_CUDA_CHECK(launch_pdl(layernorm_rows_kernel<float, 512>, dim3(grid), dim3(256), 0, stream, p, ld_in, rows, gamma, beta, eps, gelu, ob, ld_bf16, out_f32, ld_f32));
     else
-      layernorm_rows_kernel<float, 1024><<<grid, 256, 0, stream>>>(p, ld_in, rows, gamma, beta, eps, gelu, ob, ld_bf16, out_f32, ld_f32);
+      APH_CUDA_CHECK(launch_pdl(layernorm_rows_kernel<float, 1024>, dim3(grid), dim3(256), 0, stream, p, ld_in, rows, gamma, beta, eps, gelu, ob, ld_bf16, out_f32, ld_f32));
   } else {
     const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(in);
     if (cols == 512)
-      layernorm_rows_kernel<__nv_bfloat16, 512><<<grid, 256, 0, stream>>>(p, ld_in, rows, gamma, beta, eps, gelu, ob, ld_bf16, out_f32, ld_f32);
+      APH_CUDA_CHECK(launch_pdl(layernorm_rows_kernel<__nv_bfloat16, 512>, dim3(grid), dim3(256), 0, stream, p, ld_in, rows, gamma, beta, eps, gelu, ob, ld_bf16, out_f32, ld_f32));
     else
-      layernorm_rows_kernel<__nv_bfloat16, 1024><<<grid, 256, 0, stream>>>(p, ld_in, rows, gamma, beta, eps, gelu, ob, ld_bf16, out_f32, ld_f32);
+      APH_CUDA_CHECK(launch_pdl(layernorm_rows_kernel<__nv_bfloat16, 1024>, dim3(grid), dim3(256), 0, stream, p, ld_in, rows, gamma, beta, eps, gelu, ob, ld_bf16, out_f32, ld_f32));
   }
   APH_POST_LAUNCH(1);
   return APH_OK;

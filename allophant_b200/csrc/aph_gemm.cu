@@ -171,6 +171,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_trigger();  // the next kernel in the stream may start its prologue while this one runs
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
@@ -192,6 +193,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
   cluster_sync_all();  // barrier inits visible cluster-wide before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   // Work item = (N tile, pair of M tiles); the two CTAs of a cluster take the two M tiles.
   const int cta_rank = static_cast<int>(cluster_ctarank());
@@ -423,7 +425,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           }
           if (p.gelu == 1) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            for (int j = 0; j < 16; ++j) {
+              const float2 g2 = gelu_erf2(make_float2(v[2 * j], v[2 * j + 1]));
+              v[2 * j] = g2.x;
+              v[2 * j + 1] = g2.y;
+            }
           } else if (p.gelu == 2) {  // APH_ACT_RELU
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -709,7 +715,7 @@ static int launch_gemm(const aph_gemm_args* a, GemmParams& p, cudaStream_t strea
   }
   const int total_work = p.diag_taps > 0 ? m_pairs * p.diag_taps : m_pairs * p.n_tiles * p.split_k;
   const int grid = 2 * (total_work < max_clusters ? total_work : max_clusters);
-  gemm_bf16_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, tm_out, tm_resid, p);
+  APH_CUDA_CHECK(launch_pdl(gemm_bf16_kernel<BN, EPI>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tm_a, tm_b, tm_out, tm_resid, p));
   APH_POST_LAUNCH(1);
   return APH_OK;
 }

@@ -4,6 +4,8 @@
 #include <mutex>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "aph_common.cuh"
 
 namespace aph {
@@ -80,9 +82,27 @@ int sm_count() {
   return n;
 }
 
+// -1 = not decided yet (first use reads APH_PDL from the environment; default on)
+static std::atomic<int> g_pdl{-1};
+bool pdl_enabled() {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("APH_PDL");
+    v = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+    g_pdl.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
+
 }  // namespace aph
 
 extern "C" {
+
+int aph_set_pdl(int enabled) {
+  const int before = aph::pdl_enabled() ? 1 : 0;
+  aph::g_pdl.store(enabled ? 1 : 0);
+  return before;
+}
 
 int aph_abi_version(void) { return APH_ABI_VERSION; }
 const char* aph_last_error(void) { return aph::g_last_error; }

@@ -49,6 +49,12 @@ def reset_launch_count() -> None:
     lib.aph_reset_launch_count()
 
 
+def set_pdl(enabled: bool) -> bool:
+    """Programmatic dependent launch between the library's kernels (on by default; ``APH_PDL=0`` disables it at start-up).
+    Returns the previous setting."""
+    return bool(lib.aph_set_pdl(1 if enabled else 0))
+
+
 # --------------------------------------------------------------------------------------
 # GEMM
 # --------------------------------------------------------------------------------------

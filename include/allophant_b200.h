@@ -38,6 +38,10 @@ const char* aph_last_error(void);
  * reports it as `gpu_launches`). */
 int64_t aph_launch_count(void);
 void aph_reset_launch_count(void);
+/* Programmatic dependent launch between the library's kernels (each kernel's prologue overlaps the tail of its
+ * predecessor in the stream; results are identical).  On by default, APH_PDL=0 in the environment or this call turn it
+ * off.  Returns the previous setting.  No reference counterpart: torch launches its kernels in plain stream order. */
+int aph_set_pdl(int enabled);
 
 /* ---- tensor-core GEMM (tcgen05 + TMEM accumulators, TMA-fed) ------------- */
 /* One kernel serves every dense contraction of the path:
