@@ -77,6 +77,13 @@ class GemmArgs(Structure):
         ("drop_seed", ctypes.c_uint32),
         ("drop_scale", ctypes.c_float),
         ("act_bwd", c_int32),
+        ("row_stats", c_void_p),
+        ("row_stats_slots", c_int32),
+        ("ln_stats", c_void_p),
+        ("ln_slots", c_int32),
+        ("ln_cols", c_int32),
+        ("ln_colsum", c_void_p),
+        ("ln_eps", c_float),
     ]
 
 
@@ -168,6 +175,7 @@ _SIGNATURES = {
     "aph_edit_matrix": [_P, _I64, _P, _I64, _P],
     "aph_collate_pad_f32": [_P, _P, _I64, _I64, _P, _I32],
     "aph_edit_statistics_batch": [_P, _P, _P, _P, _I64, _P, _P, _I32],
+    "aph_fold_layernorm_linear": [_P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P],
     "aph_ctc_states_pad": [_I32],
     "aph_ctc_forward": [POINTER(CtcHead), _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
     "aph_ctc_backward": [POINTER(CtcHead), _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],

@@ -489,6 +489,58 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   const float2 e = f2_fma(r, f2_splat(-1.0f), f2_splat(1.0f));  // 1 - r, one rounding like the scalar subtraction
   return f2_fma(ahx, e, hx);
 }
+// Eight pairs at once with the order of operations pinned (volatile asm): Horner step by Horner step ACROSS the pairs, so that
+// eight independent dependency chains are in flight.  Left to itself the compiler interleaves only two or three of the sixteen
+// chains of a 32-column chunk (register-pressure heuristics), and one warp's epilogue became a serial chain as long as the
+// K = 1024 mainloop of its tile (profiles/r02_gemm_epilogue.md).  Same arithmetic as gelu_erf2, bit for bit.
+__device__ __forceinline__ void f2v_fma(float2& d, const float2& a, const float2& b, const float2& c) {
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;"
+               : "=l"(*reinterpret_cast<uint64_t*>(&d))
+               : "l"(*reinterpret_cast<const uint64_t*>(&a)), "l"(*reinterpret_cast<const uint64_t*>(&b)),
+                 "l"(*reinterpret_cast<const uint64_t*>(&c)));
+}
+__device__ __forceinline__ void f2v_mul(float2& d, const float2& a, const float2& b) {
+  asm volatile("mul.rn.f32x2 %0, %1, %2;"
+               : "=l"(*reinterpret_cast<uint64_t*>(&d))
+               : "l"(*reinterpret_cast<const uint64_t*>(&a)), "l"(*reinterpret_cast<const uint64_t*>(&b)));
+}
+__device__ __forceinline__ void gelu_erf2_x8(float2 (&x)[8]) {
+  float2 u[8], d[8];
+  const float2 c0 = f2_splat(0.70710678118654752440f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f2v_mul(u[i], make_float2(fabsf(x[i].x), fabsf(x[i].y)), c0);
+  const float2 k6 = f2_splat(0.0000430638f), k5 = f2_splat(0.0002765672f), k4 = f2_splat(0.0001520143f), k3 = f2_splat(0.0092705272f),
+               k2 = f2_splat(0.0422820123f), k1 = f2_splat(0.0705230784f), one = f2_splat(1.0f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f2v_fma(d[i], k6, u[i], k5);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f2v_fma(d[i], d[i], u[i], k4);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f2v_fma(d[i], d[i], u[i], k3);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f2v_fma(d[i], d[i], u[i], k2);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f2v_fma(d[i], d[i], u[i], k1);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f2v_fma(d[i], d[i], u[i], one);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f2v_mul(d[i], d[i], d[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(d[i].x) : "f"(d[i].x));
+    asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(d[i].y) : "f"(d[i].y));
+  }
+  const float2 half = f2_splat(0.5f), minus_one = f2_splat(-1.0f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f2v_mul(u[i], x[i], half);                  // hx
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f2v_fma(d[i], d[i], minus_one, one);        // 1 - r
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f2v_fma(x[i], make_float2(fabsf(u[i].x), fabsf(u[i].y)), d[i], u[i]);
+}
 // d/dx of the GELU above: Phi(x) + x phi(x), Phi from the same erf approximation
 // ---- counter-based keep masks for train-mode dropout ----------------------------------------------------------------
 // One 32-bit hash per (row, column pair) decides two adjacent elements with 16-bit thresholds: element (row, col) is

@@ -94,6 +94,14 @@ struct GemmParams {
   uint32_t drop_seed;
   float drop_scale;
   int act_bwd;
+  // ---- LayerNorm folded into the surrounding GEMMs (inference)
+  float2* row_stats;        // producer: [rows][row_stats_slots] (sum, sum of squares) of the stored fp32 values per column slot
+  int row_stats_slots;
+  const float2* ln_stats;   // consumer: statistics of the A rows, same layout
+  int ln_slots;
+  const float* ln_colsum;   // consumer: sum_k B[n][k] of the gamma-folded weight
+  float ln_inv_cols;        // 1 / (number of columns the statistics run over)
+  float ln_eps;
 };
 
 // Work item -> (n block, m pair, output batch, k-block range, B row shift)
@@ -134,6 +142,10 @@ __device__ __forceinline__ WorkItem decode_work(const GemmParams& p, int work, i
 // per-warp staging tile (one coalesced 4 KB box per 32 x 32 chunk, requested one chunk ahead) instead of one
 // 128-byte line per thread: row-strided residual loads cost 24 us of a 61 us out-proj GEMM.
 constexpr int kEpiStoreResidTma = 2;
+// Same, and the kernel also (a) writes a bf16 copy of the stored values through a third per-warp staging tile + TMA and (b)
+// leaves per-row partial sums / sums of squares of the stored values: the LayerNorm that follows in the encoder is then applied
+// inside the NEXT GEMM's epilogue (`ln_stats`), which reads the bf16 copy as its A operand — no LayerNorm kernel runs.
+constexpr int kEpiStoreResidStats = 3;
 
 template <int BN, int EPI = APH_EPI_STORE>
 struct GemmCfg {
@@ -141,7 +153,7 @@ struct GemmCfg {
   static constexpr int kBBytes = (BN / 2) * kBK * 2;  // this CTA's half of the pair's B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   // one 32-row x 128-byte output staging tile per epilogue warp (+ one residual tile in the TMA-residual variant)
-  static constexpr int kEpiBytes = EPI == kEpiStoreResidTma ? 8 * 8192 : 8 * 4096;
+  static constexpr int kEpiBytes = EPI == kEpiStoreResidStats ? 8 * 12288 : (EPI == kEpiStoreResidTma ? 8 * 8192 : 8 * 4096);
   // everything has to fit the 227 KB a CTA can opt into: stages + epilogue staging + alignment slack + barriers
   static constexpr int kBudget = 232448 - kEpiBytes - 1024 - 512;
   static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
@@ -153,7 +165,7 @@ template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                      const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_resid,
-                     const GemmParams p) {
+                     const __grid_constant__ CUtensorMap tm_copy, const GemmParams p) {
   using Cfg = GemmCfg<BN, EPI>;
   constexpr int kStages = Cfg::kStages;
 
@@ -175,8 +187,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
-    if (p.staged) tma_prefetch_desc(&tm_out);
-    if (EPI == kEpiStoreResidTma) tma_prefetch_desc(&tm_resid);
+    if (p.staged || EPI == APH_EPI_QKV) tma_prefetch_desc(&tm_out);
+    if (EPI == APH_EPI_QKV) {
+      tma_prefetch_desc(&tm_resid);
+      tma_prefetch_desc(&tm_copy);
+    }
+    if (EPI == kEpiStoreResidTma || EPI == kEpiStoreResidStats) tma_prefetch_desc(&tm_resid);
+    if (EPI == kEpiStoreResidStats) tma_prefetch_desc(&tm_copy);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 2);   // leader's copy is the one in use: one arrive.expect_tx per CTA of the pair
       mbar_init(&empty_bar[s], 1);  // released in both CTAs by the leader's tcgen05.commit multicast
@@ -205,7 +222,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 
   if (warp == 8) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop (coordinates and barrier addresses stay warp-uniform, so they live in uniform
+    // registers) and ONE elected lane issues; under `if (lane == 0)` every TMA / MMA instruction was wrapped in an
+    // ELECT + R2UR + BRA.U.ANY waterfall, ~20 dependent instructions per tcgen05.mma on the issuing thread.
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int work = cluster_id; work < total_work; work += n_clusters) {
@@ -219,6 +239,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
+          if (elect_one()) {
           // both CTAs' bytes are accounted on the LEADER's full barrier (the leader issues the pair's MMA)
           if (cta_rank == 0) {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -247,6 +268,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           } else {
             tma_load_2d_pair(sb, &tm_b, &full_bar[stage], kb * kBK, n_blk * BN + cta_rank * (BN / 2));
           }
+          }
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -256,7 +279,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     }
   } else if (warp == 9) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0 && cta_rank == 0) {
+    if (cta_rank == 0) {
       const uint32_t idesc = p.idesc;
       // descriptor advance per UMMA_K = 16: 32 bytes along K inside the swizzle atom (K-major) or 16 rows of
       // 128 bytes (MN-major), in 16-byte units
@@ -277,18 +300,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t da = p.a_mn ? umma_desc_mn_sw128(sa, 64 * kBK * 2) : umma_desc_sw128(sa);
           const uint64_t db = p.b_mn ? umma_desc_mn_sw128(sa + Cfg::kABytes, 64 * kBK * 2) : umma_desc_sw128(sa + Cfg::kABytes);
+          if (elect_one()) {  // the same lane every time: tcgen05.commit tracks the MMAs of the thread that issues it
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            umma_bf16_pair(tmem_d, da + static_cast<uint64_t>(k) * a_step, db + static_cast<uint64_t>(k) * b_step, idesc,
-                           (kb != w.kb_lo || k != 0) ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; ++k) {
+              umma_bf16_pair(tmem_d, da + static_cast<uint64_t>(k) * a_step, db + static_cast<uint64_t>(k) * b_step, idesc,
+                             (kb != w.kb_lo || k != 0) ? 1u : 0u);
+            }
+            umma_commit_pair(&empty_bar[stage], static_cast<uint16_t>(3));  // frees the stage in both CTAs
           }
-          umma_commit_pair(&empty_bar[stage], static_cast<uint16_t>(3));  // frees the stage in both CTAs
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_pair(&tfull_bar[acc], static_cast<uint16_t>(3));  // accumulator ready in both CTAs
+        if (elect_one()) umma_commit_pair(&tfull_bar[acc], static_cast<uint16_t>(3));  // accumulator ready in both CTAs
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -310,6 +337,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     uint8_t* resid_buf = epi_smem + 8 * 4096 + warp * 4096;
     const uint8_t* resid_row = resid_buf + lane * 128;
     uint32_t resid_phase = 0;
+    // stats variant: third tile per warp, 32 rows x 64 bf16 columns (two chunks), for the bf16 copy of the output
+    uint8_t* copy_buf = epi_smem + 16 * 4096 + warp * 4096;
+    uint8_t* copy_row = copy_buf + lane * 128;
+    constexpr bool kResid = EPI == kEpiStoreResidTma || EPI == kEpiStoreResidStats;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int work = cluster_id; work < total_work; work += n_clusters) {
@@ -329,10 +360,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
         if (p.lengths != nullptr && row_ok) masked = tt >= p.lengths[utt];
       }
       const int t_tile_row0 = (mt % p.m_tiles_per_batch) * kBM + quad * 32;
-      const bool resid_tma = EPI == kEpiStoreResidTma && mt < tiles_m;  // warp-uniform
+      const bool resid_tma = kResid && mt < tiles_m;  // warp-uniform
+      float row_sum = 0.f, row_sq = 0.f;  // stats variant: this thread's row over this warp's columns
+      // LayerNorm of the A rows applied here: y = rstd * (acc - mean * colsum[n]) + bias'[n]
+      float ln_rstd = 1.f, ln_nmr = 0.f;
+      if (p.ln_stats != nullptr && row_ok) {
+        // all partial sums of the row in flight at once (one L2 round trip, not ln_slots of them): 16-byte loads of two
+        // slots each, ln_slots even and <= 16 (checked by the launcher)
+        const float4* st = reinterpret_cast<const float4*>(p.ln_stats + grow * p.ln_slots);
+        float4 part[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) part[i] = 2 * i < p.ln_slots ? __ldg(st + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s1 += part[i].x + part[i].z;
+          s2 += part[i].y + part[i].w;
+        }
+        const float mean = s1 * p.ln_inv_cols;
+        const float var = fmaxf(s2 * p.ln_inv_cols - mean * mean, 0.f);
+        ln_rstd = rsqrtf(var + p.ln_eps);
+        ln_nmr = -mean * ln_rstd;
+      }
       if (resid_tma && col_base + half * (BN / 2) < p.n && lane == 0) {  // first chunk: requested before the accumulator is ready
         mbar_arrive_expect_tx(&resid_bar[warp], 4096);
         tma_load_3d(resid_buf, &tm_resid, &resid_bar[warp], col_base + half * (BN / 2), t_tile_row0, b);
+      }
+      // The per-column vectors of this warp's 128 columns (bias, folded-LayerNorm column sums: 4 lines each) are pulled into
+      // L1 while the accumulator is still being computed; the per-chunk loads below then hit L1 instead of waiting on L2.
+      {
+        const int vcol = col_base + half * (BN / 2) + (lane & 3) * 32;
+        if (vcol < p.n) {
+          if (lane < 4 && p.bias != nullptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + vcol));
+          if (lane >= 4 && lane < 8 && p.ln_colsum != nullptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.ln_colsum + vcol));
+        }
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -352,45 +413,92 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           const int h = hc >> 6;
           const int d0 = hc & 63;
           const float sc = which == 0 ? p.q_scale : 1.0f;
+          {
+            // bias (and, with a folded LayerNorm, the column sums) as 16-byte loads: col % 32 == 0 keeps them aligned.  As 32
+            // scalar loads per chunk they were the largest single stall of this epilogue (profiles/r02_gemm_stalls.md).
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+            if (p.ln_stats != nullptr) {
+              const float4* c4 = reinterpret_cast<const float4*>(p.ln_colsum + col);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = (v[j] + __ldg(p.bias + col + j)) * sc;
-          if (row_ok) {
-            const long long bh = static_cast<long long>(utt) * p.heads + h;
-            if (which < 2) {
-              __nv_bfloat16* dst = (which == 0 ? p.q : p.kmat) + (bh * p.len_period + tt) * 64 + d0;
-              uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 o;
-                o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                d4[j] = o;
+              for (int j = 0; j < 8; ++j) {
+                const float4 bv = __ldg(b4 + j);
+                const float4 cv = __ldg(c4 + j);
+                v[4 * j + 0] = fmaf(v[4 * j + 0], ln_rstd, fmaf(ln_nmr, cv.x, bv.x)) * sc;
+                v[4 * j + 1] = fmaf(v[4 * j + 1], ln_rstd, fmaf(ln_nmr, cv.y, bv.y)) * sc;
+                v[4 * j + 2] = fmaf(v[4 * j + 2], ln_rstd, fmaf(ln_nmr, cv.z, bv.z)) * sc;
+                v[4 * j + 3] = fmaf(v[4 * j + 3], ln_rstd, fmaf(ln_nmr, cv.w, bv.w)) * sc;
               }
             } else {
-              // V row-major like Q and K: the attention kernels read it as an MN-major B operand (O = P V), so the
-              // transposed copy (32 scattered 2-byte stores per thread) is only written when a caller asks for it
-              uint4* d4 = reinterpret_cast<uint4*>(p.vmat + (bh * p.len_period + tt) * 64 + d0);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 o;
-                o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                d4[j] = o;
-              }
-              if (p.vt != nullptr) {
-                __nv_bfloat16* dst = p.vt + (bh * 64 + d0) * p.t_v + tt;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.t_v] = __float2bfloat16(v[j]);
+              for (int j = 0; j < 8; ++j) {
+                const float4 bv = __ldg(b4 + j);
+                v[4 * j + 0] = (v[4 * j + 0] + bv.x) * sc;
+                v[4 * j + 1] = (v[4 * j + 1] + bv.y) * sc;
+                v[4 * j + 2] = (v[4 * j + 2] + bv.z) * sc;
+                v[4 * j + 3] = (v[4 * j + 3] + bv.w) * sc;
               }
             }
           }
+          // Q / K / V [utterance*heads + head][frame][64]: the 64 columns of a head are two chunks; they go through the warp's
+          // staging tile (32 frames x 128 bytes, 128B swizzle) and ONE TMA store — the map's frame axis ends at the utterance's
+          // last frame, so rows that belong to the next utterance are clipped; the (few) lanes holding such rows copy their
+          // 128 bytes out of the staging tile themselves (a TMA store may not start at a negative coordinate).  As 16-byte
+          // row-strided stores from registers this epilogue was longer than the K = 1024 mainloop.
+          {
+            const int part = (c0 >> 5) & 1;
+            if (part == 0 && store_pending) {
+              if (lane == 0) bulk_store_wait_read<0>();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+              o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              *reinterpret_cast<uint4*>(stage_row + (((4 * part + j) ^ sw) << 4)) = o;
+            }
+            if (part == 1) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              const long long grow0 = static_cast<long long>(mt) * kBM + quad * 32;  // batch == 1: first row of this warp
+              const int utt0 = static_cast<int>(grow0 / p.len_period);
+              const int tt0 = static_cast<int>(grow0 - static_cast<long long>(utt0) * p.len_period);
+              if (lane == 0 && grow0 < p.a_rows) {
+                const CUtensorMap* tm = which == 0 ? &tm_out : (which == 1 ? &tm_resid : &tm_copy);
+                tma_store_3d(tm, stage_buf, 0, tt0, utt0 * p.heads + h);
+              }
+              store_pending = true;
+              if (row_ok && utt != utt0) {  // this row opens the next utterance
+                __nv_bfloat16* base = which == 0 ? p.q : (which == 1 ? p.kmat : p.vmat);
+                uint4* d4 = reinterpret_cast<uint4*>(base + ((static_cast<long long>(utt) * p.heads + h) * p.len_period + tt) * 64);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) d4[j] = *reinterpret_cast<const uint4*>(stage_row + ((j ^ sw) << 4));
+              }
+            }
+          }
+          if (which == 2 && p.vt != nullptr && row_ok) {  // optional transposed copy of V (nothing in the library reads it)
+            const long long bh = static_cast<long long>(utt) * p.heads + h;
+            __nv_bfloat16* dst = p.vt + (bh * 64 + d0) * p.t_v + tt;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.t_v] = __float2bfloat16(v[j]);
+          }
         } else {
           const bool full_chunk = col + 32 <= p.n;
-          if (p.bias != nullptr) {
+          if (p.ln_stats != nullptr) {  // full chunks only (checked by the launcher): bias' and the column sums are [n]
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+            const float4* c4 = reinterpret_cast<const float4*>(p.ln_colsum + col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bv = __ldg(b4 + j);
+              const float4 cv = __ldg(c4 + j);
+              v[4 * j + 0] = fmaf(v[4 * j + 0], ln_rstd, fmaf(ln_nmr, cv.x, bv.x));
+              v[4 * j + 1] = fmaf(v[4 * j + 1], ln_rstd, fmaf(ln_nmr, cv.y, bv.y));
+              v[4 * j + 2] = fmaf(v[4 * j + 2], ln_rstd, fmaf(ln_nmr, cv.z, bv.z));
+              v[4 * j + 3] = fmaf(v[4 * j + 3], ln_rstd, fmaf(ln_nmr, cv.w, bv.w));
+            }
+          } else if (p.bias != nullptr) {
             if (full_chunk) {
               const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);  // col % 32 == 0: aligned
 #pragma unroll
@@ -425,10 +533,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           }
           if (p.gelu == 1) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float2 g2 = gelu_erf2(make_float2(v[2 * j], v[2 * j + 1]));
-              v[2 * j] = g2.x;
-              v[2 * j + 1] = g2.y;
+            for (int g = 0; g < 2; ++g) {
+              float2 x[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x[j] = make_float2(v[16 * g + 2 * j], v[16 * g + 2 * j + 1]);
+              gelu_erf2_x8(x);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                v[16 * g + 2 * j] = x[j].x;
+                v[16 * g + 2 * j + 1] = x[j].y;
+              }
             }
           } else if (p.gelu == 2) {  // APH_ACT_RELU
 #pragma unroll
@@ -492,7 +606,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
             }
           }
           if (row_ok) {
-            if (EPI != kEpiStoreResidTma && p.resid != nullptr) {
+            if (!kResid && p.resid != nullptr) {
               const float4* rs = reinterpret_cast<const float4*>(p.resid + grow * p.ld_resid + col);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -517,7 +631,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
                   d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
               }
             }
-            if (p.out_bf16 != nullptr && p.staged != 2) {
+            if (p.out_bf16 != nullptr && p.staged != 2 && EPI != kEpiStoreResidStats) {
               uint4* d4 = reinterpret_cast<uint4*>(p.out_bf16 + grow * p.ld_bf16 + col);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -547,6 +661,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 #pragma unroll
               for (int j = 0; j < 8; ++j)
                 *reinterpret_cast<float4*>(stage_row + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if (EPI == kEpiStoreResidStats) {
+                // (the wait above covered the previous bf16-copy store as well: one bulk-group queue per thread)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  row_sum += v[j];
+                  row_sq = fmaf(v[j], v[j], row_sq);
+                }
+                const int part = (c0 >> 5) & 1;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint4 o;
+                  o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                  o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                  o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                  o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                  *reinterpret_cast<uint4*>(copy_row + (((4 * part + j) ^ sw) << 4)) = o;
+                }
+              }
               fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0) {
@@ -557,6 +689,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
                 }
               }
               store_pending = true;
+              if (EPI == kEpiStoreResidStats) {
+                const int part = (c0 >> 5) & 1;
+                const bool last_chunk = c0 + 32 >= (half + 1) * (BN / 2) || col + 32 >= p.n;
+                if ((part == 1 || last_chunk) && lane == 0) tma_store_3d(&tm_copy, copy_buf, col - 32 * part, t_row0, b);
+              }
             } else {
               // bf16: two consecutive 32-column chunks fill the 128-byte rows (64 columns per store)
               const int part = (c0 >> 5) & 1;
@@ -584,6 +721,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           }
         }
       }
+      if (EPI == kEpiStoreResidStats && row_ok && col_base + half * (BN / 2) < p.n)
+        p.row_stats[grow * p.row_stats_slots + n_blk * 2 + half] = make_float2(row_sum, row_sq);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {  // the accumulator of BOTH CTAs must be drained before the leader overwrites it
@@ -674,7 +813,7 @@ static int launch_gemm(const aph_gemm_args* a, GemmParams& p, cudaStream_t strea
   }
   CUtensorMap tm_resid;
   memset(&tm_resid, 0, sizeof(tm_resid));
-  if (EPI == kEpiStoreResidTma) {
+  if (EPI == kEpiStoreResidTma || EPI == kEpiStoreResidStats) {
     const uint64_t ld = static_cast<uint64_t>(a->ld_resid);
     const uint64_t dims[3] = {static_cast<uint64_t>(p.n), static_cast<uint64_t>(a->a_rows), static_cast<uint64_t>(a->batch)};
     uint64_t batch_stride = static_cast<uint64_t>(a->out_batch_rows) * ld * 4;
@@ -682,6 +821,29 @@ static int launch_gemm(const aph_gemm_args* a, GemmParams& p, cudaStream_t strea
     const uint64_t strides[2] = {ld * 4, batch_stride};
     const uint32_t box[3] = {32u, 32u, 1u};
     int rc = encode_tmap(&tm_resid, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, a->resid, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != APH_OK) return rc;
+  }
+  CUtensorMap tm_copy;
+  memset(&tm_copy, 0, sizeof(tm_copy));
+  if (EPI == APH_EPI_QKV) {  // Q, K, V [utterance*heads + head][frame][64] ride in the three output-side map slots
+    const uint64_t n_utt = static_cast<uint64_t>(ceil_div(a->a_rows, a->len_period));
+    const uint64_t dims[3] = {64, static_cast<uint64_t>(a->len_period), n_utt * static_cast<uint64_t>(a->heads)};
+    const uint64_t strides[2] = {128, static_cast<uint64_t>(a->len_period) * 128};
+    const uint32_t box[3] = {64u, 32u, 1u};
+    int rc = encode_tmap(&tm_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->q, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc == APH_OK) rc = encode_tmap(&tm_resid, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->kmat, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc == APH_OK) rc = encode_tmap(&tm_copy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->vmat, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != APH_OK) return rc;
+  }
+  if (EPI == kEpiStoreResidStats) {  // bf16 copy of the fp32 output: 64-column x 32-row boxes
+    const uint64_t ld = static_cast<uint64_t>(a->ld_bf16);
+    const uint64_t dims[3] = {static_cast<uint64_t>(p.n), static_cast<uint64_t>(a->a_rows), static_cast<uint64_t>(a->batch)};
+    uint64_t batch_stride = static_cast<uint64_t>(a->out_batch_rows) * ld * 2;
+    if (a->batch == 1 || batch_stride == 0) batch_stride = static_cast<uint64_t>(a->a_rows) * ld * 2;
+    const uint64_t strides[2] = {ld * 2, batch_stride};
+    const uint32_t box[3] = {BN >= 128 ? 64u : 32u, 32u, 1u};
+    int rc = encode_tmap(&tm_copy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->out_bf16, dims, strides, box,
+                         BN >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc != APH_OK) return rc;
   }
   static bool attr_set = false;
@@ -715,7 +877,7 @@ static int launch_gemm(const aph_gemm_args* a, GemmParams& p, cudaStream_t strea
   }
   const int total_work = p.diag_taps > 0 ? m_pairs * p.diag_taps : m_pairs * p.n_tiles * p.split_k;
   const int grid = 2 * (total_work < max_clusters ? total_work : max_clusters);
-  APH_CUDA_CHECK(launch_pdl(gemm_bf16_kernel<BN, EPI>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tm_a, tm_b, tm_out, tm_resid, p));
+  APH_CUDA_CHECK(launch_pdl(gemm_bf16_kernel<BN, EPI>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tm_a, tm_b, tm_out, tm_resid, tm_copy, p));
   APH_POST_LAUNCH(1);
   return APH_OK;
 }
@@ -798,6 +960,24 @@ extern "C" int aph_gemm_bf16(const aph_gemm_args* a, void* stream_) {
   p.staged = 0;
   p.split_k = 1;
   p.kb_per_split = p.k_blocks;
+  // LayerNorm folded into the GEMMs around it
+  p.row_stats = reinterpret_cast<float2*>(a->row_stats);
+  p.row_stats_slots = a->row_stats_slots;
+  p.ln_stats = reinterpret_cast<const float2*>(a->ln_stats);
+  p.ln_slots = a->ln_slots;
+  p.ln_colsum = a->ln_colsum;
+  p.ln_inv_cols = a->ln_cols > 0 ? 1.0f / static_cast<float>(a->ln_cols) : 0.f;
+  p.ln_eps = a->ln_eps;
+  const bool stats_out = a->row_stats != nullptr;
+  const bool stats_in = a->ln_stats != nullptr;
+  APH_REQUIRE(!stats_in || (a->ln_slots > 0 && a->ln_slots <= 16 && a->ln_slots % 2 == 0 && a->ln_cols > 0 && a->ln_colsum && a->bias && !mn && a->mode == APH_GEMM_ROWS && a->batch == 1 &&
+                            a->n % 32 == 0 && a->scale == 1.0f && (reinterpret_cast<uintptr_t>(a->ln_colsum) & 15) == 0 &&
+                            (reinterpret_cast<uintptr_t>(a->ln_stats) & 15) == 0),
+              "ln_stats: plain K-major GEMM with bias, scale 1, n % 32 == 0, batch 1, even ln_slots <= 16, ln_cols / ln_colsum set");
+  APH_REQUIRE(!stats_out || (a->resid && a->out_f32 && a->out_bf16 && !mn && a->mode == APH_GEMM_ROWS && a->epilogue == APH_EPI_STORE &&
+                             a->n > 128 && a->n % 64 == 0 && a->row_stats_slots == 2 * ceil_div(a->n, 256) &&
+                             (reinterpret_cast<uintptr_t>(a->row_stats) & 7) == 0),
+              "row_stats: fp32 output with residual and a bf16 copy, n a multiple of 64 above 128, row_stats_slots == 2 * ceil(n / 256)");
 
   if (a->mode == APH_GEMM_DIAG_TAPS) {
     // dW of the grouped positional conv: for tap j and 256-channel block q,
@@ -826,6 +1006,9 @@ extern "C" int aph_gemm_bf16(const aph_gemm_args* a, void* stream_) {
   if (a->epilogue == APH_EPI_QKV) {
     APH_REQUIRE(!mn, "qkv epilogue takes K-major operands");
     APH_REQUIRE(a->q && a->kmat && a->vmat && a->bias, "qkv epilogue needs q/k/v/bias");
+    APH_REQUIRE(a->batch == 1 && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0, "qkv epilogue: batch 1, bias 16-byte aligned");
+    APH_REQUIRE(((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->kmat) | reinterpret_cast<uintptr_t>(a->vmat)) & 15) == 0,
+                "qkv epilogue: q / k / v must be 16-byte aligned");
     APH_REQUIRE(a->heads > 0 && a->n == 3 * a->heads * 64, "qkv epilogue: n == 3*heads*64");
     APH_REQUIRE(a->len_period > 0 && (!a->vt || (a->t_v % 8 == 0 && a->t_v >= a->len_period)), "qkv epilogue: bad lengths");
     APH_REQUIRE((a->heads * 64) % 256 == 0, "qkv epilogue: hidden must be a multiple of 256");
@@ -854,6 +1037,10 @@ extern "C" int aph_gemm_bf16(const aph_gemm_args* a, void* stream_) {
     const bool narrow = narrow_requested && !a->a_mn_major;
     p.n_tiles = ceil_div(a->n, narrow ? 128 : 256);
     // fp32 output with a residual (out-proj, FFN2, gradient accumulation): the residual comes in through TMA
+    if (stats_out) {
+      p.n_tiles = ceil_div(a->n, 256);
+      return launch_gemm<256, kEpiStoreResidStats>(a, p, stream);
+    }
     if (a->resid && p.staged == 1 && !a->a_mn_major)
       return narrow ? launch_gemm<128, kEpiStoreResidTma>(a, p, stream) : launch_gemm<256, kEpiStoreResidTma>(a, p, stream);
     return narrow ? launch_gemm<128, APH_EPI_STORE>(a, p, stream) : launch_gemm<256, APH_EPI_STORE>(a, p, stream);

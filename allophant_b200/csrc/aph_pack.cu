@@ -68,9 +68,59 @@ __global__ void __launch_bounds__(256) posconv_tap_scale_kernel(const float* __r
   if (threadIdx.x == 0) tap_scale[j] = static_cast<float>(static_cast<double>(g[j]) / sqrt(red[0]));
 }
 
+// LayerNorm folded into the Linear behind it: Linear(LayerNorm(x)) = rstd * (x W'^T - mean * colsum) + bias' with
+//   W'[n][k] = W[n][k] * gamma[k] (bf16 GEMM operand),  colsum[n] = sum_k W'[n][k] (of the ROUNDED operand, so that a row
+//   of equal values cancels exactly),  bias'[n] = bias[n] + sum_k W[n][k] * beta[k].
+// One block per output feature.
+__global__ void __launch_bounds__(256) fold_layernorm_linear_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                    int k, __nv_bfloat16* __restrict__ out_w, float* __restrict__ out_colsum,
+                                                                    float* __restrict__ out_bias) {
+  const int n = blockIdx.x;
+  const float* row = w + static_cast<long long>(n) * k;
+  __nv_bfloat16* dst = out_w + static_cast<long long>(n) * k;
+  float cs = 0.f, bs = 0.f;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const float wv = row[i];
+    const __nv_bfloat16 folded = __float2bfloat16(wv * gamma[i]);
+    dst[i] = folded;
+    cs += __bfloat162float(folded);
+    bs = fmaf(wv, beta[i], bs);
+  }
+  __shared__ float red[2][8];
+  cs = warp_sum(cs);
+  bs = warp_sum(bs);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    red[0][warp] = cs;
+    red[1][warp] = bs;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < 8; ++i) {
+      a += red[0][i];
+      b += red[1][i];
+    }
+    out_colsum[n] = a;
+    out_bias[n] = (bias ? bias[n] : 0.f) + b;
+  }
+}
+
 }  // namespace aph
 
 using namespace aph;
+
+extern "C" int aph_fold_layernorm_linear(const float* weight, const float* bias, const float* gamma, const float* beta, int32_t n,
+                                         int32_t k, void* out_weight_bf16, float* out_colsum, float* out_bias, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  APH_REQUIRE(weight && gamma && beta && out_weight_bf16 && out_colsum && out_bias, "null pointer");
+  APH_REQUIRE(n > 0 && k > 0, "bad shape");
+  fold_layernorm_linear_kernel<<<n, 256, 0, stream>>>(weight, bias, gamma, beta, k, static_cast<__nv_bfloat16*>(out_weight_bf16),
+                                                      out_colsum, out_bias);
+  APH_POST_LAUNCH(1);
+  return APH_OK;
+}
 
 extern "C" int aph_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

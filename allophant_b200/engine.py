@@ -16,6 +16,7 @@ with the host.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Tuple
 
@@ -70,6 +71,9 @@ class PackedEncoder:
         self._pointers: Optional[Tuple[int, ...]] = None
         self.device: Optional[torch.device] = None
         self.layout_id = 0
+        self._folded: Optional[List[Dict[str, Tensor]]] = None
+        self._folded_layout = -1
+        self._folded_version: Optional[Tuple[int, ...]] = None
 
     def _current_version(self) -> Tuple[int, ...]:
         def version(p: Tensor) -> int:
@@ -196,6 +200,35 @@ class PackedEncoder:
             return
         self._fill_derived()
         self._version = self._current_version()
+
+    # -- LayerNorm folded into the q/k/v and the first feed-forward projections (inference launch lists) -------------
+    def ensure_folded(self) -> List[Dict[str, Tensor]]:
+        """Per layer: ``wqkv`` / ``w1`` with the LayerNorm weight folded in, their column sums and folded biases
+        (``ops.fold_layernorm_linear``).  Allocated once per parameter layout and refilled in place whenever the parameters
+        change, like the other packed operands (launch lists keep raw pointers)."""
+        self.ensure()
+        if self._folded is None or self._folded_layout != self.layout_id:
+            dev, H, FF = self.device, self.cfg.hidden_size, self.cfg.intermediate_size
+            bf16 = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.bfloat16)  # noqa: E731
+            f32 = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)  # noqa: E731
+            self._folded = [
+                dict(wqkv=bf16(3 * H, H), sqkv=f32(3 * H), bqkv=f32(3 * H), w1=bf16(FF, H), s1=f32(FF), b1=f32(FF)) for _ in self.layers
+            ]
+            self._folded_layout = self.layout_id
+            self._folded_version = None
+        if self._folded_version != self._version:
+            H = self.cfg.hidden_size
+            with torch.no_grad():
+                for layer, folded in zip(self.weights.encoder.layers, self._folded):
+                    att = layer.attention
+                    g1, b1 = layer.layer_norm.weight, layer.layer_norm.bias
+                    for part, linear in enumerate((att.q_proj, att.k_proj, att.v_proj)):
+                        rows = slice(part * H, (part + 1) * H)
+                        ops.fold_layernorm_linear(linear.weight, linear.bias, g1, b1, folded["wqkv"][rows], folded["sqkv"][rows], folded["bqkv"][rows])
+                    dense = layer.feed_forward.intermediate_dense
+                    ops.fold_layernorm_linear(dense.weight, dense.bias, layer.final_layer_norm.weight, layer.final_layer_norm.bias, folded["w1"], folded["s1"], folded["b1"])
+            self._folded_version = self._version
+        return self._folded
 
     @property
     def pos_w_dgrad(self) -> Tensor:
@@ -501,6 +534,14 @@ class EncoderPlan:
         if not cfg.do_stable_layer_norm:
             self._build_post_ln(steps, heads, FF)
             return
+        # Inference: the two LayerNorms of a layer are folded into the GEMMs around them.  out-proj / FFN2 leave a bf16 copy of
+        # the residual stream and per-row (sum, sum of squares); the q/k/v and FFN1 projections read that copy, a gamma-folded
+        # weight and apply mean / rstd in their epilogue (ops.with_row_stats / with_layernorm).  Only the first LayerNorm of
+        # layer 0 (its input comes from the positional conv) and the encoder's final LayerNorm still run as kernels.
+        self.fold_ln = (not self.training) and os.environ.get("APH_FOLD_LN", "1") != "0" and H % 256 == 0
+        folded = p.ensure_folded() if self.fold_ln else None
+        if self.fold_ln:
+            self.row_stats = torch.zeros(M, 2 * (H // 256), 2, device=self.hidden.device, dtype=torch.float32)
         for index, lw in enumerate(p.layers):
             if self.training:
                 sv = self.saved[index]
@@ -515,24 +556,40 @@ class EncoderPlan:
             steps.append(lambda index=index, h_in=h_in: self._keep_hidden(index, h_in))
             span_start = len(steps)
             g1, b1 = lw["ln1"]
-            steps.append(lambda g1=g1, b1=b1, h_in=h_in, ln1=ln1: ops.layernorm_rows(h_in, M, H, H, g1, b1, eps, out_bf16=ln1, ld_bf16=H))
-            steps.append(
-                self._gemm(ops.make_qkv_args(ln1, lw["wqkv"], lw["bqkv"], q, k, v, rows=M, seq=self.seq, heads=heads))
-            )
+            if self.fold_ln and index > 0:
+                qkv_args = ops.make_qkv_args(self.hidden_bf16, folded[index]["wqkv"], folded[index]["bqkv"], q, k, v, rows=M, seq=self.seq, heads=heads)
+                steps.append(self._gemm(ops.with_layernorm(qkv_args, self.row_stats, folded[index]["sqkv"], H, eps)))
+            else:
+                steps.append(lambda g1=g1, b1=b1, h_in=h_in, ln1=ln1: ops.layernorm_rows(h_in, M, H, H, g1, b1, eps, out_bf16=ln1, ld_bf16=H))
+                steps.append(
+                    self._gemm(ops.make_qkv_args(ln1, lw["wqkv"], lw["bqkv"], q, k, v, rows=M, seq=self.seq, heads=heads))
+                )
             steps.append(
                 lambda q=q, k=k, v=v, ctx=ctx, lse=lse, index=index: ops.attention(
                     q, k, v, ctx, self.att_lengths, N, heads, self.seq, lse, self.stoch.attention(index) if self.stoch else ops.NO_DROPOUT
                 )
             )
             out_args = ops.make_gemm_args(ctx, lw["wo"], a_rows=M, a_inner=H, a_row_stride=H, bias=lw["bo"], resid=h_in, ld_resid=H, out_f32=h_mid, ld_f32=H)
+            if self.fold_ln:
+                out_args.out_bf16, out_args.ld_bf16 = self.hidden_bf16.data_ptr(), H
+                ops.with_row_stats(out_args, self.row_stats)
             steps.append(self._gemm(out_args))
             g2, b2 = lw["ln2"]
-            steps.append(lambda g2=g2, b2=b2, h_mid=h_mid, ln2=ln2: ops.layernorm_rows(h_mid, M, H, H, g2, b2, eps, out_bf16=ln2, ld_bf16=H))
-            inner_args = ops.make_gemm_args(
-                ln2, lw["w1"], a_rows=M, a_inner=H, a_row_stride=H, bias=lw["b1"], gelu=True, out_bf16=ffn, ld_bf16=FF, aux_bf16=pre, ld_aux=FF
-            )
+            if self.fold_ln:
+                inner_args = ops.make_gemm_args(
+                    self.hidden_bf16, folded[index]["w1"], a_rows=M, a_inner=H, a_row_stride=H, bias=folded[index]["b1"], gelu=True, out_bf16=ffn, ld_bf16=FF
+                )
+                ops.with_layernorm(inner_args, self.row_stats, folded[index]["s1"], H, eps)
+            else:
+                steps.append(lambda g2=g2, b2=b2, h_mid=h_mid, ln2=ln2: ops.layernorm_rows(h_mid, M, H, H, g2, b2, eps, out_bf16=ln2, ld_bf16=H))
+                inner_args = ops.make_gemm_args(
+                    ln2, lw["w1"], a_rows=M, a_inner=H, a_row_stride=H, bias=lw["b1"], gelu=True, out_bf16=ffn, ld_bf16=FF, aux_bf16=pre, ld_aux=FF
+                )
             steps.append(self._gemm(inner_args))
             ffn_args = ops.make_gemm_args(ffn, lw["w2"], a_rows=M, a_inner=FF, a_row_stride=FF, bias=lw["b2"], resid=h_mid, ld_resid=H, out_f32=h_out, ld_f32=H)
+            if self.fold_ln and index + 1 < len(p.layers):
+                ffn_args.out_bf16, ffn_args.ld_bf16 = self.hidden_bf16.data_ptr(), H
+                ops.with_row_stats(ffn_args, self.row_stats)
             steps.append(self._gemm(ffn_args))
             self._layer_spans.append((span_start, len(steps)))
             if self.training:
@@ -775,6 +832,8 @@ class EncoderPlan:
         plans only) switches the train()-mode regularisation on for this run and the backward pass that follows it."""
         p, cfg = self.packed, self.cfg
         N = self.n_utt
+        if getattr(self, "fold_ln", False):
+            p.ensure_folded()  # refilled in place when the parameters changed since the last run
         self.captured = [] if capture else None
         self.generation += 1
         if stochastic is not None and not self.training:

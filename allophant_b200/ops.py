@@ -202,6 +202,45 @@ def run_gemm(args: GemmArgs) -> None:
     check(lib.aph_gemm_bf16(ctypes.byref(args), _stream()), "aph_gemm_bf16")
 
 
+def fold_layernorm_linear(weight: Tensor, bias: Optional[Tensor], gamma: Tensor, beta: Tensor, out_weight: Tensor, out_colsum: Tensor, out_bias: Tensor) -> None:
+    """LayerNorm folded into the Linear behind it: ``out_weight = bf16(weight * gamma)``, ``out_colsum = out_weight.sum(1)``,
+    ``out_bias = bias + weight @ beta`` (all written in place; ``out_weight`` may be a row slice of a larger operand)."""
+    _require_cuda(weight, bias, gamma, beta, out_weight, out_colsum, out_bias)
+    w = weight.detach().float().contiguous()
+    n, k = w.shape
+    if not out_weight.is_contiguous() or out_weight.shape != (n, k) or out_weight.dtype != torch.bfloat16:
+        raise ValueError("out_weight must be a contiguous bf16 [n, k] tensor")
+    b = None if bias is None else bias.detach().float().contiguous()
+    check(
+        lib.aph_fold_layernorm_linear(
+            w.data_ptr(), _ptr(b), gamma.detach().float().contiguous().data_ptr(), beta.detach().float().contiguous().data_ptr(), n, k,
+            out_weight.data_ptr(), out_colsum.data_ptr(), out_bias.data_ptr(), _stream(),
+        ),
+        "aph_fold_layernorm_linear",
+    )  # fmt: skip
+
+
+def with_row_stats(args: GemmArgs, stats: Tensor) -> GemmArgs:
+    """Producer side of a folded LayerNorm: the GEMM (fp32 output + residual + bf16 copy) also leaves per-row partial sums and
+    sums of squares in ``stats`` fp32 ``[rows, 2 * ceil(n / 256), 2]``."""
+    _require_cuda(stats)
+    args.row_stats = stats.data_ptr()
+    args.row_stats_slots = stats.shape[1]
+    return args
+
+
+def with_layernorm(args: GemmArgs, stats: Tensor, colsum: Tensor, cols: int, eps: float) -> GemmArgs:
+    """Consumer side: ``args.a`` holds the UN-normalised rows (bf16), ``args.b`` the gamma-folded weight, ``args.bias`` the folded
+    bias; the epilogue applies the row statistics (``fold_layernorm_linear``, ``with_row_stats``)."""
+    _require_cuda(stats, colsum)
+    args.ln_stats = stats.data_ptr()
+    args.ln_slots = stats.shape[1]
+    args.ln_cols = cols
+    args.ln_colsum = colsum.data_ptr()
+    args.ln_eps = eps
+    return args
+
+
 def linear_bf16(
     x: Tensor,
     w: Tensor,

@@ -29,7 +29,7 @@ extern "C" {
 #define APH_ERR_CUDA (-2)        /* CUDA runtime / driver error                    */
 #define APH_ERR_UNSUPPORTED (-3) /* valid request outside the implemented envelope */
 
-#define APH_ABI_VERSION 4
+#define APH_ABI_VERSION 5
 
 /* ---- library ------------------------------------------------------------ */
 int aph_abi_version(void);
@@ -127,6 +127,22 @@ typedef struct aph_gemm_args {
   uint32_t drop_seed;
   float drop_scale;
   int32_t act_bwd;        /* activation whose derivative gelu_bwd applies: 0 / 1 GELU (erf), 2 ReLU, 3 LeakyReLU(0.01) */
+  /* ---- ABI 5: LayerNorm folded into the GEMMs around it (inference; all zero = off) -------------------------------
+   * The pre-LN encoder computes y = Linear(LayerNorm(x)) with x the fp32 residual stream the previous Linear just wrote
+   * (HF:730-756: layer_norm -> attention, final_layer_norm -> feed_forward).  Instead of a LayerNorm kernel between them,
+   *   producer  (fp32 output + residual): also stores a bf16 copy of the output (out_bf16 / ld_bf16, through TMA) and, per
+   *             output row and column slot s = column / 128, the pair (sum, sum of squares) of the stored values in
+   *             row_stats[row][s] (float2); row_stats_slots = 2 * ceil(n / 256);
+   *   consumer  reads that bf16 copy as A, a weight with gamma folded in (B[n][k] = W[n][k] * gamma[k]), bias' = bias +
+   *             W beta, and applies y = rstd * (acc - mean * ln_colsum[n]) + bias'[n] with mean / rstd from ln_stats
+   *             (summed over ln_slots) over ln_cols columns; ln_colsum[n] = sum_k B[n][k] (aph_fold_layernorm_linear). */
+  float* row_stats;
+  int32_t row_stats_slots;
+  const float* ln_stats;
+  int32_t ln_slots;
+  int32_t ln_cols;
+  const float* ln_colsum;
+  float ln_eps;
 } aph_gemm_args;
 
 int aph_gemm_bf16(const aph_gemm_args* args, void* stream);
@@ -305,6 +321,12 @@ int aph_pack_conv_weight(const float* src, void* dst_bf16, int32_t out_channels,
 int aph_pack_posconv_weight(const float* weight_g, const float* weight_v, void* dst_bf16,
                             float* tap_scale_scratch, int32_t out_channels,
                             int32_t group_channels, int32_t kernel, void* stream);
+
+/* LayerNorm folded into the nn.Linear that follows it (HF:735-736 layer_norm -> q/k/v_proj, HF:749-750 final_layer_norm ->
+ * intermediate_dense): out_weight[n][k] = bf16(weight[n][k] * gamma[k]), out_colsum[n] = sum_k out_weight[n][k],
+ * out_bias[n] = bias[n] + sum_k weight[n][k] * beta[k].  The GEMM consumes them through aph_gemm_args.ln_* (ABI 5). */
+int aph_fold_layernorm_linear(const float* weight /*[n][k]*/, const float* bias /*[n] or NULL*/, const float* gamma, const float* beta,
+                              int32_t n, int32_t k, void* out_weight_bf16, float* out_colsum, float* out_bias, void* stream);
 
 /* ---- multi-head CTC loss -------------------------------------------------------- */
 /* CTCWrapper (loss_functions.py:19-27): nn.CTCLoss(reduction="sum", zero_infinity=True) on

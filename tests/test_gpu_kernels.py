@@ -62,6 +62,62 @@ def test_gemm_residual_mask_and_scale():
     assert range_err(out, reference) < 1e-4
 
 
+@pytest.mark.parametrize("m,period,lengths", [(998, 499, [300, 499]), (130, 130, [130]), (1537, 1537, [1500])])
+def test_gemm_folded_layernorm_pair(m, period, lengths):
+    """LayerNorm folded into the GEMMs around it (HF:730-756, inference launch list): the producer (out-proj form: bias +
+    residual, fp32 in place) leaves a bf16 copy and per-row (sum, sum of squares); the consumers (FFN1 form: GELU, bf16 out;
+    q/k/v form: scatter epilogue) read the copy and a gamma-folded weight and apply mean / rstd themselves."""
+    ops = _ops()
+    torch.manual_seed(m)
+    h, ff, heads = 1024, 4096, 16
+    ctx = (torch.randn(m, h, device=DEV) * 0.5).bfloat16()
+    wo = (torch.randn(h, h, device=DEV) * 0.03).bfloat16()
+    bo = torch.randn(h, device=DEV)
+    resid = torch.randn(m, h, device=DEV) * 2 + 0.7  # a row mean that is not zero
+    resid[:, 5] += 40.0  # and an outlier channel, as real wav2vec2 residual streams have
+    lens = torch.tensor(lengths, device=DEV, dtype=torch.int32)
+    hidden = resid.clone()
+    copy16 = torch.zeros(m, h, device=DEV, dtype=torch.bfloat16)
+    stats = torch.zeros(m, 2 * (h // 256), 2, device=DEV)
+    producer = ops.make_gemm_args(ctx, wo, a_rows=m, a_inner=h, a_row_stride=h, bias=bo, resid=hidden, ld_resid=h, out_f32=hidden, ld_f32=h,
+                                  out_bf16=copy16, ld_bf16=h, lengths=lens, len_period=period)  # fmt: skip
+    ops.run_gemm(ops.with_row_stats(producer, stats))
+    expected_hidden = ctx.float() @ wo.float().T + bo + resid
+    rows = torch.arange(m, device=DEV)
+    expected_hidden[(rows % period) >= lens[rows // period]] = 0
+    assert range_err(hidden, expected_hidden) < 1e-4
+    assert torch.equal(copy16, hidden.bfloat16())
+    sums = stats.sum(1)
+    assert range_err(sums[:, 0], hidden.sum(1)) < 1e-5 and range_err(sums[:, 1], (hidden * hidden).sum(1)) < 1e-5
+
+    gamma, beta = torch.rand(h, device=DEV) + 0.5, torch.randn(h, device=DEV) * 0.3
+    normalised = F.layer_norm(hidden, (h,), gamma, beta, 1e-5)
+    # FFN1 form
+    w1, b1 = torch.randn(ff, h, device=DEV) * 0.03, torch.randn(ff, device=DEV)
+    w1_folded, colsum, bias_folded = torch.empty(ff, h, device=DEV, dtype=torch.bfloat16), torch.empty(ff, device=DEV), torch.empty(ff, device=DEV)
+    ops.fold_layernorm_linear(w1, b1, gamma, beta, w1_folded, colsum, bias_folded)
+    assert torch.equal(w1_folded, (w1 * gamma).bfloat16())
+    assert range_err(colsum, w1_folded.float().sum(1)) < 1e-5 and range_err(bias_folded, b1 + w1 @ beta) < 1e-5
+    act = torch.zeros(m, ff, device=DEV, dtype=torch.bfloat16)
+    consumer = ops.make_gemm_args(copy16, w1_folded, a_rows=m, a_inner=h, a_row_stride=h, bias=bias_folded, gelu=True, out_bf16=act, ld_bf16=ff)
+    ops.run_gemm(ops.with_layernorm(consumer, stats, colsum, h, 1e-5))
+    reference = F.gelu(normalised @ w1.T + b1)
+    unfused = F.gelu(normalised.bfloat16().float() @ w1.bfloat16().float().T + b1)  # what the LayerNorm kernel + plain GEMM compute
+    assert range_err(act, reference) < 1e-2
+    assert range_err(act, reference) < 2.0 * range_err(unfused.bfloat16(), reference) + 1e-3  # as close to fp32 as the unfused path
+    # q/k/v form
+    wqkv, bqkv = torch.randn(3 * h, h, device=DEV) * 0.03, torch.randn(3 * h, device=DEV)
+    wq_folded, sq, bq = torch.empty(3 * h, h, device=DEV, dtype=torch.bfloat16), torch.empty(3 * h, device=DEV), torch.empty(3 * h, device=DEV)
+    ops.fold_layernorm_linear(wqkv, bqkv, gamma, beta, wq_folded, sq, bq)
+    n_utt = m // period
+    q, k, v = (torch.zeros(n_utt * heads, period, 64, device=DEV, dtype=torch.bfloat16) for _ in range(3))
+    args = ops.make_qkv_args(copy16, wq_folded, bq, q, k, v, rows=m, seq=period, heads=heads)
+    ops.run_gemm(ops.with_layernorm(args, stats, sq, h, 1e-5))
+    projected = (normalised @ wqkv.T + bqkv).view(n_utt, period, 3, heads, 64).permute(2, 0, 3, 1, 4).reshape(3, n_utt * heads, period, 64)
+    assert range_err(q, projected[0] * (0.125 * 1.4426950408889634)) < 1e-2
+    assert range_err(k, projected[1]) < 1e-2 and range_err(v, projected[2]) < 1e-2
+
+
 @pytest.mark.parametrize("length_in,kernel,stride", [(1001, 3, 2), (3999, 3, 2), (999, 2, 2)])
 def test_gemm_strided_conv(length_in, kernel, stride):
     """Implicit-GEMM Conv1d over a channels-last activation through an overlapping-row TMA view (HF:281-299)."""
