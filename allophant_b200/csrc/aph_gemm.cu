@@ -155,10 +155,13 @@ struct GemmCfg {
   // one 32-row x 128-byte output staging tile per epilogue warp (+ one residual tile in the TMA-residual variant)
   static constexpr int kEpiBytes = EPI == kEpiStoreResidStats ? 8 * 12288 : (EPI == kEpiStoreResidTma ? 8 * 8192 : 8 * 4096);
   // everything has to fit the 227 KB a CTA can opt into: stages + epilogue staging + alignment slack + barriers
-  static constexpr int kBudget = 232448 - kEpiBytes - 1024 - 512;
+  // per-tile column vectors (bias | folded-LayerNorm column sums), BN floats each; the dynamic shared memory base must be
+  // 1024-byte aligned (checked at kernel entry), so no alignment slack is reserved
+  static constexpr int kVecBytes = 2048;
+  static constexpr int kBudget = 232448 - kEpiBytes - kVecBytes - 512;
   static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // double-buffered accumulator (128 lanes x BN columns per CTA)
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kVecBytes + 512 /*barriers*/;
 };
 
 template <int BN, int EPI>
@@ -169,11 +172,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
   using Cfg = GemmCfg<BN, EPI>;
   constexpr int kStages = Cfg::kStages;
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) {  // 128B-swizzled tiles need 1024-byte alignment
+    if (threadIdx.x == 0) printf("aph: GEMM shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   uint8_t* epi_smem = smem + kStages * Cfg::kStageBytes;  // 1024-byte aligned (stage sizes are multiples of 8 KB)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + Cfg::kEpiBytes);
+  float* vec_smem = reinterpret_cast<float*>(epi_smem + Cfg::kEpiBytes);  // [0, 256) bias, [256, 512) LayerNorm column sums
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + Cfg::kEpiBytes + Cfg::kVecBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -322,6 +329,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     }
   } else {
     // ===================== epilogue (8 warps: 128 rows x 2 column halves) =====================
+    constexpr bool kResid = EPI == kEpiStoreResidTma || EPI == kEpiStoreResidStats;
     const int quad = warp & 3;           // TMEM lane quadrant this warp may access
     const int half = warp >> 2;          // which half of the tile's columns this warp drains
     const int r = quad * 32 + lane;
@@ -340,13 +348,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     // stats variant: third tile per warp, 32 rows x 64 bf16 columns (two chunks), for the bf16 copy of the output
     uint8_t* copy_buf = epi_smem + 16 * 4096 + warp * 4096;
     uint8_t* copy_row = copy_buf + lane * 128;
-    constexpr bool kResid = EPI == kEpiStoreResidTma || EPI == kEpiStoreResidStats;
+
     int acc = 0;
     uint32_t acc_phase = 0;
+    // Column vectors of the tile (bias, LayerNorm column sums): thread i of the 256 epilogue threads owns column i of the tile,
+    // fetches its two values ONE TILE AHEAD into registers and parks them in shared memory at the start of the tile; the chunks
+    // then read them as broadcast LDS.  As 8 x LDG.128 per chunk they cost 400-1000 cycles of L2 latency per chunk on the one
+    // warp whose 4 chunks in series set the tile period (profiles/r02_gemm_epilogue_timeline.md).
+    const bool has_bias = p.bias != nullptr, has_colsum = p.ln_colsum != nullptr;
+    // epilogue options read once (kernel parameters live in the constant bank: tested per chunk they cost a constant load and a
+    // dependent branch each, ~500 cycles per chunk in the timeline)
+    const int act = p.gelu, staged = p.staged;
+    const bool has_ln = p.ln_stats != nullptr, has_aux = p.aux_bf16 != nullptr, has_act_bwd = p.gelu_bwd != nullptr;
+    const bool has_drop = p.drop_threshold != 0, plain_resid = !kResid && p.resid != nullptr;
+    const bool direct_f32 = p.out_f32 != nullptr && staged != 1;
+    const bool direct_bf16 = p.out_bf16 != nullptr && staged != 2 && EPI != kEpiStoreResidStats;
+    const float out_scale = p.scale;
+    auto fetch_vectors = [&](int work_item, float& bias_value, float& colsum_value) {
+      bias_value = 0.f;
+      colsum_value = 0.f;
+      if (work_item < total_work && static_cast<int>(threadIdx.x) < BN) {
+        const WorkItem wn = decode_work(p, work_item, m_pairs);
+        const int vcol = (wn.out_batch >= 0 ? 0 : wn.n_blk * BN) + static_cast<int>(threadIdx.x);
+        if (vcol < p.n) {
+          if (has_bias) bias_value = __ldg(p.bias + vcol);
+          if (has_colsum) colsum_value = __ldg(p.ln_colsum + vcol);
+        }
+      }
+    };
+    float bias_next, colsum_next;
+    fetch_vectors(cluster_id, bias_next, colsum_next);
     for (int work = cluster_id; work < total_work; work += n_clusters) {
       const WorkItem w = decode_work(p, work, m_pairs);
       const int n_blk = w.n_blk;
       const int mt = 2 * w.m_pair + cta_rank;
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // every epilogue warp is done with the previous tile's vectors
+      if (static_cast<int>(threadIdx.x) < BN) {
+        vec_smem[threadIdx.x] = bias_next;
+        vec_smem[256 + threadIdx.x] = colsum_next;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      fetch_vectors(work + n_clusters, bias_next, colsum_next);  // in flight while this tile drains
       const int b = w.out_batch >= 0 ? w.out_batch : mt / p.m_tiles_per_batch;
       const int t = (mt % p.m_tiles_per_batch) * kBM + r;
       const int col_base = w.out_batch >= 0 ? 0 : n_blk * BN;  // DIAG_TAPS: the 256 columns of the diagonal block
@@ -364,7 +406,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
       float row_sum = 0.f, row_sq = 0.f;  // stats variant: this thread's row over this warp's columns
       // LayerNorm of the A rows applied here: y = rstd * (acc - mean * colsum[n]) + bias'[n]
       float ln_rstd = 1.f, ln_nmr = 0.f;
-      if (p.ln_stats != nullptr && row_ok) {
+      if (has_ln && row_ok) {
         // all partial sums of the row in flight at once (one L2 round trip, not ln_slots of them): 16-byte loads of two
         // slots each, ln_slots even and <= 16 (checked by the launcher)
         const float4* st = reinterpret_cast<const float4*>(p.ln_stats + grow * p.ln_slots);
@@ -385,15 +427,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
       if (resid_tma && col_base + half * (BN / 2) < p.n && lane == 0) {  // first chunk: requested before the accumulator is ready
         mbar_arrive_expect_tx(&resid_bar[warp], 4096);
         tma_load_3d(resid_buf, &tm_resid, &resid_bar[warp], col_base + half * (BN / 2), t_tile_row0, b);
-      }
-      // The per-column vectors of this warp's 128 columns (bias, folded-LayerNorm column sums: 4 lines each) are pulled into
-      // L1 while the accumulator is still being computed; the per-chunk loads below then hit L1 instead of waiting on L2.
-      {
-        const int vcol = col_base + half * (BN / 2) + (lane & 3) * 32;
-        if (vcol < p.n) {
-          if (lane < 4 && p.bias != nullptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + vcol));
-          if (lane >= 4 && lane < 8 && p.ln_colsum != nullptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.ln_colsum + vcol));
-        }
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -416,13 +449,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           {
             // bias (and, with a folded LayerNorm, the column sums) as 16-byte loads: col % 32 == 0 keeps them aligned.  As 32
             // scalar loads per chunk they were the largest single stall of this epilogue (profiles/r02_gemm_stalls.md).
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
-            if (p.ln_stats != nullptr) {
-              const float4* c4 = reinterpret_cast<const float4*>(p.ln_colsum + col);
+            const float4* b4 = reinterpret_cast<const float4*>(vec_smem + c0);
+            if (has_ln) {
+              const float4* c4 = reinterpret_cast<const float4*>(vec_smem + 256 + c0);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 bv = __ldg(b4 + j);
-                const float4 cv = __ldg(c4 + j);
+                const float4 bv = b4[j];
+                const float4 cv = c4[j];
                 v[4 * j + 0] = fmaf(v[4 * j + 0], ln_rstd, fmaf(ln_nmr, cv.x, bv.x)) * sc;
                 v[4 * j + 1] = fmaf(v[4 * j + 1], ln_rstd, fmaf(ln_nmr, cv.y, bv.y)) * sc;
                 v[4 * j + 2] = fmaf(v[4 * j + 2], ln_rstd, fmaf(ln_nmr, cv.z, bv.z)) * sc;
@@ -431,7 +464,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
             } else {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 bv = __ldg(b4 + j);
+                const float4 bv = b4[j];
                 v[4 * j + 0] = (v[4 * j + 0] + bv.x) * sc;
                 v[4 * j + 1] = (v[4 * j + 1] + bv.y) * sc;
                 v[4 * j + 2] = (v[4 * j + 2] + bv.z) * sc;
@@ -486,38 +519,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           }
         } else {
           const bool full_chunk = col + 32 <= p.n;
-          if (p.ln_stats != nullptr) {  // full chunks only (checked by the launcher): bias' and the column sums are [n]
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
-            const float4* c4 = reinterpret_cast<const float4*>(p.ln_colsum + col);
+          if (has_ln) {
+            const float4* b4 = reinterpret_cast<const float4*>(vec_smem + c0);
+            const float4* c4 = reinterpret_cast<const float4*>(vec_smem + 256 + c0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 bv = __ldg(b4 + j);
-              const float4 cv = __ldg(c4 + j);
+              const float4 bv = b4[j];
+              const float4 cv = c4[j];
               v[4 * j + 0] = fmaf(v[4 * j + 0], ln_rstd, fmaf(ln_nmr, cv.x, bv.x));
               v[4 * j + 1] = fmaf(v[4 * j + 1], ln_rstd, fmaf(ln_nmr, cv.y, bv.y));
               v[4 * j + 2] = fmaf(v[4 * j + 2], ln_rstd, fmaf(ln_nmr, cv.z, bv.z));
               v[4 * j + 3] = fmaf(v[4 * j + 3], ln_rstd, fmaf(ln_nmr, cv.w, bv.w));
             }
-          } else if (p.bias != nullptr) {
-            if (full_chunk) {
-              const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);  // col % 32 == 0: aligned
+          } else if (has_bias) {  // columns past n hold 0 in the staged vector
+            const float4* b4 = reinterpret_cast<const float4*>(vec_smem + c0);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 bv = __ldg(b4 + j);
-                v[4 * j + 0] = fmaf(v[4 * j + 0], p.scale, bv.x);
-                v[4 * j + 1] = fmaf(v[4 * j + 1], p.scale, bv.y);
-                v[4 * j + 2] = fmaf(v[4 * j + 2], p.scale, bv.z);
-                v[4 * j + 3] = fmaf(v[4 * j + 3], p.scale, bv.w);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], p.scale, col + j < p.n ? __ldg(p.bias + col + j) : 0.f);
+            for (int j = 0; j < 8; ++j) {
+              const float4 bv = b4[j];
+              v[4 * j + 0] = fmaf(v[4 * j + 0], out_scale, bv.x);
+              v[4 * j + 1] = fmaf(v[4 * j + 1], out_scale, bv.y);
+              v[4 * j + 2] = fmaf(v[4 * j + 2], out_scale, bv.z);
+              v[4 * j + 3] = fmaf(v[4 * j + 3], out_scale, bv.w);
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= p.scale;
+            for (int j = 0; j < 32; ++j) v[j] *= out_scale;
           }
-          if (p.aux_bf16 != nullptr && row_ok) {  // training forward: keep the pre-activation for the backward pass
+          if (has_aux && row_ok) {  // training forward: keep the pre-activation for the backward pass
             uint4* d4 = reinterpret_cast<uint4*>(p.aux_bf16 + grow * p.ld_aux + col);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -531,7 +559,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
               }
             }
           }
-          if (p.gelu == 1) {
+          if (act == 1) {
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               float2 x[8];
@@ -544,14 +572,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
                 v[16 * g + 2 * j + 1] = x[j].y;
               }
             }
-          } else if (p.gelu == 2) {  // APH_ACT_RELU
+          } else if (act == 2) {  // APH_ACT_RELU
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          } else if (p.gelu == 3) {  // APH_ACT_LEAKY_RELU (negative slope 0.01, nn.LeakyReLU's default)
+          } else if (act == 3) {  // APH_ACT_LEAKY_RELU (negative slope 0.01, nn.LeakyReLU's default)
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.01f * v[j];
           }
-          if (p.gelu_bwd != nullptr && row_ok) {  // backward of GELU: dL/d(pre) = dL/d(act) * gelu'(pre)
+          if (has_act_bwd && row_ok) {  // backward of GELU: dL/d(pre) = dL/d(act) * gelu'(pre)
             const uint4* s4 = reinterpret_cast<const uint4*>(p.gelu_bwd + grow * p.ld_gelu_bwd + col);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -573,7 +601,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
               }
             }
           }
-          if (p.drop_threshold != 0) {  // train-mode dropout of the branch output, before the residual joins
+          if (has_drop) {  // train-mode dropout of the branch output, before the residual joins
             const uint32_t key = drop_row_key(p.drop_seed, static_cast<uint32_t>(grow));
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -606,7 +634,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
             }
           }
           if (row_ok) {
-            if (!kResid && p.resid != nullptr) {
+            if (plain_resid) {
               const float4* rs = reinterpret_cast<const float4*>(p.resid + grow * p.ld_resid + col);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -623,7 +651,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = 0.f;
             }
-            if (p.out_f32 != nullptr && p.staged != 1) {
+            if (direct_f32) {
               float4* d4 = reinterpret_cast<float4*>(p.out_f32 + grow * p.ld_f32 + col);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -631,7 +659,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
                   d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
               }
             }
-            if (p.out_bf16 != nullptr && p.staged != 2 && EPI != kEpiStoreResidStats) {
+            if (direct_bf16) {
               uint4* d4 = reinterpret_cast<uint4*>(p.out_bf16 + grow * p.ld_bf16 + col);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -646,13 +674,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
               }
             }
           }
-          if (p.staged != 0 && mt < tiles_m) {  // warp-uniform
+          if (staged != 0 && mt < tiles_m) {  // warp-uniform
             if (masked || !row_ok) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = 0.f;
             }
             const int t_row0 = (mt % p.m_tiles_per_batch) * kBM + quad * 32;
-            if (p.staged == 1) {
+            if (staged == 1) {
               // fp32: this 32-column chunk is a full 128-byte row of the staging tile
               if (store_pending) {
                 if (lane == 0) bulk_store_wait_read<0>();

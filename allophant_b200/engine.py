@@ -54,6 +54,73 @@ def frames_for(samples: int, cfg: Wav2Vec2EncoderConfig) -> List[int]:
     return lengths
 
 
+def min_samples_for(frames: int, cfg: Wav2Vec2EncoderConfig) -> int:
+    """Smallest sample count whose convolutional feature extractor output has ``frames`` frames."""
+    length = frames
+    for kernel, stride in zip(reversed(cfg.conv_kernel), reversed(cfg.conv_stride)):
+        length = (length - 1) * stride + kernel
+    return length
+
+
+def bucket_samples(samples: int, cfg: Wav2Vec2EncoderConfig, frame_multiple: int) -> Tuple[int, int]:
+    """``(padded sample count, frames of the unpadded input)``: inputs are padded (with silence, behind every utterance's own
+    length) up to the LARGEST sample count whose frame count is the next multiple of ``frame_multiple``, so that a stream of
+    ragged batches (``MaxFrameBatchSampler``, ``batching.py:94-139``) maps onto a few launch lists instead of one per length."""
+    frames = frames_for(samples, cfg)[-1]
+    if frame_multiple <= 1 or frames < 1:
+        return samples, frames
+    target = -(-frames // frame_multiple) * frame_multiple
+    return max(samples, min_samples_for(target + 1, cfg) - 1), frames
+
+
+class WorkspaceArena:
+    """One grow-only device buffer that the inference launch lists of a model overlay (each ``EncoderPlan`` carves its
+    workspaces from offset 0): a ragged stream switches between launch lists without allocating.  Everything a plan reads
+    before writing is either rewritten or cleared at the start of each run (``EncoderPlan.run``)."""
+
+    ALIGN = 1024
+
+    def __init__(self) -> None:
+        self.buffer: Optional[Tensor] = None
+        self.generation = 0  # bumped when the buffer is replaced: every plan carved from the old one is void
+
+    def capacity(self) -> int:
+        return 0 if self.buffer is None else self.buffer.numel()
+
+    def reserve(self, n_bytes: int, device: torch.device) -> None:
+        if self.capacity() < n_bytes:
+            self.buffer = None  # release first: two generations of a multi-GB arena need not coexist
+            self.buffer = torch.empty(n_bytes, device=device, dtype=torch.uint8)
+            self.generation += 1
+
+    def carver(self) -> "ArenaCarver":
+        return ArenaCarver(self)
+
+
+class ArenaCarver:
+    """Bump allocation over a ``WorkspaceArena``; requests beyond its capacity are served by ordinary allocations and counted,
+    so the caller learns the size to reserve and rebuilds."""
+
+    def __init__(self, arena: WorkspaceArena) -> None:
+        self.arena = arena
+        self.offset = 0
+        self.overflow = False
+
+    def zeros(self, *shape: int, device: torch.device, dtype: torch.dtype) -> Tensor:
+        numel = 1
+        for extent in shape:
+            numel *= int(extent)
+        n_bytes = numel * torch.empty((), dtype=dtype).element_size()
+        start = self.offset
+        self.offset = (start + n_bytes + WorkspaceArena.ALIGN - 1) // WorkspaceArena.ALIGN * WorkspaceArena.ALIGN
+        if self.arena.buffer is None or self.offset > self.arena.capacity():
+            self.overflow = True
+            return torch.zeros(*shape, device=device, dtype=dtype)
+        view = self.arena.buffer[start : start + n_bytes].view(dtype).view(*shape)
+        view.zero_()
+        return view
+
+
 class PackedEncoder:
     """bf16 GEMM operands packed from the fp32 master parameters.
 
@@ -314,9 +381,14 @@ class EncoderPlan:
         use_lengths: bool = True,
         training: bool = False,
         train_extractor: bool = False,
+        arena: Optional[WorkspaceArena] = None,
     ) -> None:
         cfg = packed.cfg
         self.training = training
+        self.arena = arena
+        self.arena_generation = arena.generation if arena is not None else 0
+        self.carver = arena.carver() if arena is not None else None
+        self.seq_out: Optional[int] = None  # frames of the unpadded input when the batch was padded up to a bucket
         # the convolutional feature extractor trains too (freeze_feature_encoder = false / UnfreezeSchedule): its
         # pre-LayerNorm conv outputs and activations are kept per layer instead of ping-ponging through two buffers
         self.train_extractor = train_extractor
@@ -344,7 +416,11 @@ class EncoderPlan:
         heads = cfg.num_attention_heads
         M = self.rows
         bf16, f32 = torch.bfloat16, torch.float32
-        z = lambda *shape, dtype=bf16: torch.zeros(*shape, device=dev, dtype=dtype)  # noqa: E731
+        if self.carver is not None:
+            z = lambda *shape, dtype=bf16: self.carver.zeros(*shape, device=dev, dtype=dtype)  # noqa: E731
+        else:
+            z = lambda *shape, dtype=bf16: torch.zeros(*shape, device=dev, dtype=dtype)  # noqa: E731
+        self._zeros = z
 
         self.stats = z(n_utt, 3, dtype=torch.float64)
         self.mean_rstd = z(n_utt, 2, dtype=f32)
@@ -369,6 +445,8 @@ class EncoderPlan:
         self.ctx = z(M, H)
         self.ffn = z(M, cfg.intermediate_size)
         self.x = z(M, ldx)  # classifier feature matrix: [final LN | kept hidden states | dependency probabilities | 0]
+        self.row_stats = None if training else z(M, 2 * max(1, H // 256), 2, dtype=f32)  # folded LayerNorms (ops.with_row_stats)
+        self.audio_in = None if training else z(n_utt, samples, dtype=f32)  # batches shorter than the bucket are padded into this
         self.captured: Optional[List[Tensor]] = None
         if training:
             # Everything the backward pass reads is kept per layer (sized for 180 GB of HBM: nothing is recomputed
@@ -540,8 +618,6 @@ class EncoderPlan:
         # layer 0 (its input comes from the positional conv) and the encoder's final LayerNorm still run as kernels.
         self.fold_ln = (not self.training) and os.environ.get("APH_FOLD_LN", "1") != "0" and H % 256 == 0
         folded = p.ensure_folded() if self.fold_ln else None
-        if self.fold_ln:
-            self.row_stats = torch.zeros(M, 2 * (H // 256), 2, device=self.hidden.device, dtype=torch.float32)
         for index, lw in enumerate(p.layers):
             if self.training:
                 sv = self.saved[index]
@@ -834,6 +910,12 @@ class EncoderPlan:
         N = self.n_utt
         if getattr(self, "fold_ln", False):
             p.ensure_folded()  # refilled in place when the parameters changed since the last run
+        if self.arena is not None:
+            if self.arena_generation != self.arena.generation:
+                raise RuntimeError("this launch list was carved from a workspace arena that has been replaced")
+            # other launch lists overlay the same memory: the zero padding columns of X must be zero again (everything else a run
+            # reads it has written itself; the attention kernel clears the context rows of query tiles it skips)
+            self.x.zero_()
         self.captured = [] if capture else None
         self.generation += 1
         if stochastic is not None and not self.training:

@@ -337,9 +337,11 @@ class HeadsRuntime:
         rows, n_utt, seq = plan.rows, plan.n_utt, plan.seq
         heads, _ = self._run_levels(plan, batch, target_feature_indices, predict, keep=None)
 
+        # frames the caller sees: fewer than the launch list's when the batch was padded up to a length bucket
+        shown = getattr(plan, "seq_out", None) or seq
         if not log_probabilities:
             outputs = {
-                name: buffer[:, column : column + width].reshape(n_utt, seq, width).transpose(0, 1)
+                name: buffer[:, column : column + width].reshape(n_utt, seq, width).transpose(0, 1)[:shown]
                 for name, buffer, ld, column, width in heads
             }
             return Predictions(outputs, frames)
@@ -355,7 +357,7 @@ class HeadsRuntime:
         position = 0
         for name, buffer, ld, column, width in heads:
             out_offsets.append(position)
-            outputs[name] = out[position : position + rows * width].view(n_utt, seq, width).transpose(0, 1)
+            outputs[name] = out[position : position + rows * width].view(n_utt, seq, width).transpose(0, 1)[:shown]
             position += rows * width
         # group heads by source buffer; narrow heads of one buffer go into a single launch
         index = 0

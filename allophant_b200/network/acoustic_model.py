@@ -11,6 +11,7 @@ reference's; internally they are batch-first contiguous blocks, so the caller's 
 from __future__ import annotations
 
 import math
+import os
 import typing
 from dataclasses import dataclass
 from typing import Any, Dict, List, Optional, Tuple, Type, TypeVar
@@ -32,7 +33,7 @@ from ..config import (
     Wav2Vec2PretrainedConfig,
 )
 from ..dataset_processing import Batch
-from ..engine import EncoderPlan, PackedEncoder
+from ..engine import EncoderPlan, PackedEncoder, WorkspaceArena, bucket_samples
 from . import frontend
 from .transformer import (  # noqa: F401  (drop-in names of acoustic_model.py:34-69, 552-759)
     PreLMTransformerEncoderLayer,
@@ -321,6 +322,13 @@ class Wav2Vec2AcousticModel(AcousticModel):
         ]
         self._packed = PackedEncoder(self._model)
         self._plans: Dict[Tuple[int, int, int, Tuple[Tuple[int, int], ...]], EncoderPlan] = {}
+        # Inference launch lists: inputs are padded up to a multiple of `bucket_frames` frames (0 = exact shapes) and all lists
+        # of the model overlay ONE workspace arena, so a ragged stream (MaxFrameBatchSampler) neither allocates nor thrashes a
+        # small cache of multi-GB plans.  GroupNorm feature extractors normalise over the padded time axis (HF:302-323): padding
+        # further would change their output, so they keep exact shapes.
+        self.bucket_frames = int(os.environ.get("APH_BUCKET_FRAMES", "64"))
+        self._arena = WorkspaceArena()
+        self.plan_builds = 0  # launch lists built so far (bench.py's ragged sweep reports the count after warm-up)
 
     def _load_pretrained(self, model_id: str) -> None:
         try:
@@ -365,16 +373,38 @@ class Wav2Vec2AcousticModel(AcousticModel):
         self._packed.ensure()
         key = (n_utt, samples, ldx, tuple(sorted(hidden_blocks.items())), training, train_extractor)
         plan = self._plans.get(key)
+        if plan is not None and plan.arena is not None and plan.arena_generation != plan.arena.generation:
+            plan = None  # carved from an arena that has been replaced since
+            del self._plans[key]
         if plan is None or plan.layout_id != self._packed.layout_id:
-            if plan is None and len(self._plans) >= 4:  # workspaces are large: keep a handful of shapes
-                self._plans.pop(next(iter(self._plans)))
+            pooled = not training
+            limit = 64 if pooled else 4  # pooled launch lists own no memory; training plans keep GBs of activations each
+            owned = [k for k, cached in self._plans.items() if (cached.arena is not None) == pooled]
+            if plan is None and len(owned) >= limit:
+                self._plans.pop(owned[0])
             if plan is not None:
                 # same shape, re-allocated operands (the parameters moved): keep the workspaces, rebuild the launch list
                 plan.rebind(self._packed)
             else:
-                plan = EncoderPlan(self._packed, n_utt, samples, ldx, hidden_blocks, self._normalize, self._use_attention_mask, training, train_extractor)
+                plan = self._build_plan(n_utt, samples, ldx, hidden_blocks, training, train_extractor, self._arena if pooled else None)
             plan.layout_id = self._packed.layout_id
             self._plans[key] = plan
+        return plan
+
+    def _build_plan(self, n_utt: int, samples: int, ldx: int, hidden_blocks: Dict[int, int], training: bool, train_extractor: bool,
+                    arena: Optional[WorkspaceArena]) -> EncoderPlan:  # fmt: skip
+        self.plan_builds += 1
+        plan = EncoderPlan(self._packed, n_utt, samples, ldx, hidden_blocks, self._normalize, self._use_attention_mask, training, train_extractor, arena)
+        if arena is not None and plan.carver.overflow:
+            # the arena is too small for this shape: reserve (with headroom for somewhat larger batches), which voids every list
+            # carved from the old buffer, and build again
+            needed = plan.carver.offset
+            del plan
+            for key in [k for k, cached in self._plans.items() if cached.arena is arena]:
+                del self._plans[key]
+            arena.reserve(int(needed * 1.15), self._packed.device)
+            plan = EncoderPlan(self._packed, n_utt, samples, ldx, hidden_blocks, self._normalize, self._use_attention_mask, training, train_extractor, arena)
+            assert not plan.carver.overflow
         return plan
 
     def encode(
@@ -390,7 +420,17 @@ class Wav2Vec2AcousticModel(AcousticModel):
             raise ValueError(f"expected raw audio of shape [batch, samples], got {tuple(audio.shape)}")
         audio = audio.float().contiguous()
         lengths = batch.lengths.to(device=audio.device, dtype=torch.int64).contiguous()
-        plan = self.plan_for(audio.shape[0], audio.shape[1], ldx, hidden_blocks, training, train_extractor)
+        samples, seq_out = audio.shape[1], None
+        if not training and self.bucket_frames > 1 and self._model.config.feat_extract_norm == "layer":
+            samples, seq_out = bucket_samples(audio.shape[1], self._model.config, self.bucket_frames)
+        plan = self.plan_for(audio.shape[0], samples, ldx, hidden_blocks, training, train_extractor)
+        if samples != audio.shape[1]:
+            # silence behind the batch's longest utterance: every kernel masks by the per-utterance lengths, frames past the
+            # unpadded frame count are dropped from what the caller sees (HeadsRuntime.forward)
+            plan.audio_in[:, : audio.shape[1]].copy_(audio)
+            plan.audio_in[:, audio.shape[1] :].zero_()
+            audio = plan.audio_in
+        plan.seq_out = seq_out if seq_out is not None and seq_out != plan.seq else None
         frames = torch.empty(audio.shape[0], device=audio.device, dtype=torch.int64)
         plan.run(audio, lengths, frames, capture, stochastic)
         return plan, frames
@@ -400,7 +440,8 @@ class Wav2Vec2AcousticModel(AcousticModel):
         plan, frames = self.encode(batch, self._d_model, {}, capture=True)
         assert plan.captured is not None
         n, seq = plan.n_utt, plan.seq
-        return [state.view(n, seq, -1).transpose(0, 1) for state in plan.captured], frames
+        shown = plan.seq_out or seq
+        return [state.view(n, seq, -1).transpose(0, 1)[:shown] for state in plan.captured], frames
 
 
 class UnfreezeSchedule:
