@@ -134,6 +134,15 @@ __global__ void __launch_bounds__(kAttThreads, 2)
   const bool active = q0 < len;  // false: the whole tile is padding (uniform per CTA) -> straight to the teardown
 
   if (!active) {
+    // A tile of padded queries only: its context rows are cleared rather than left as they were — the workspace may be shared
+    // with other launch lists (engine.WorkspaceArena), and whatever bit patterns they left there would flow through the
+    // output projection into K / V rows that P = 0 multiplies (0 x NaN).
+    const int r = static_cast<int>(threadIdx.x);
+    if (r < kAttQ && q0 + r < p.T) {
+      uint4* dst = reinterpret_cast<uint4*>(p.ctx + (static_cast<long long>(b) * p.T + q0 + r) * (p.heads * kAttD) + h * kAttD);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
   } else if (warp == 4) {
     // ===================== TMA producer =====================
     if (lane == 0) {

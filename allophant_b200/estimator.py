@@ -86,13 +86,21 @@ class Estimator:
             parameters = self._graph_parameters = list(self.model.parameters())
         # the graph bakes in raw pointers to packed weights and workspaces: any weight change retires it
         version = (weight_generation(),) + tuple(p._version for p in parameters)
-        key = (tuple(audio.shape), audio.dtype, str(audio.device), None if tfi is None else (tfi.data_ptr(), tfi._version, tuple(tfi.shape)))
+        # one graph per launch list: batches that pad up to the same length bucket (engine.bucket_samples) replay the same graph
+        samples = audio.shape[1]
+        acoustic = self.model.acoustic_model
+        if getattr(acoustic, "bucket_frames", 0) > 1 and audio.dim() == 2 and hasattr(acoustic, "_model") and acoustic._model.config.feat_extract_norm == "layer":
+            from .engine import bucket_samples
+
+            samples, _ = bucket_samples(audio.shape[1], acoustic._model.config, acoustic.bucket_frames)
+        key = ((audio.shape[0], samples) + tuple(audio.shape[2:]), audio.dtype, str(audio.device), None if tfi is None else (tfi.data_ptr(), tfi._version, tuple(tfi.shape)))
         graphs = self.__dict__.setdefault("_graphs", {})
         entry = graphs.get(key)
         if entry is not None and entry["version"] != version:
             entry = None
         if entry is None:
-            static = Batch(audio.clone(), batch.lengths.clone(), batch.language_ids.clone())
+            padded = audio if samples == audio.shape[1] else torch.nn.functional.pad(audio, (0, samples - audio.shape[1]))
+            static = Batch(padded.clone(), batch.lengths.clone(), batch.language_ids.clone())
             self.model.predict_log_probabilities(static, tfi)  # eager warm-up: plans, packed weights, composed embeddings, attributes
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
@@ -102,7 +110,9 @@ class Estimator:
                 graphs.pop(next(iter(graphs)))
             entry = graphs[key] = dict(graph=graph, batch=static, predictions=captured, version=version)
         static = entry["batch"]
-        static.audio_features.copy_(audio)
+        static.audio_features[:, : audio.shape[1]].copy_(audio)
+        if samples != audio.shape[1]:
+            static.audio_features[:, audio.shape[1] :].zero_()
         static.lengths.copy_(batch.lengths)
         static.language_ids.copy_(batch.language_ids)
         entry["graph"].replay()
@@ -110,8 +120,11 @@ class Estimator:
         flat = captured._decode_cache["flat"]
         fresh = flat.clone()
         offset = flat.storage_offset()
+        # the graph was captured on a batch of exactly the bucket's length; this batch may have fewer frames
+        frames_shown = self.model.acoustic_model.downsampled_lengths(torch.tensor([audio.shape[1]])).item() if samples != audio.shape[1] else None
         outputs = {
-            name: torch.as_strided(fresh, value.size(), value.stride(), value.storage_offset() - offset) for name, value in captured.outputs.items()
+            name: torch.as_strided(fresh, value.size(), value.stride(), value.storage_offset() - offset)[: frames_shown or value.shape[0]]
+            for name, value in captured.outputs.items()
         }
         predictions = Predictions(outputs, captured.lengths.clone())
         cache = dict(captured._decode_cache)

@@ -152,7 +152,7 @@ int aph_gemm_bf16(const aph_gemm_args* args, void* stream);
  * additive mask of HF:758-762: keys t >= lengths[b] get probability 0.
  *   q, k, v : bf16 [n_utt*heads][T][64] (q already scaled by head_dim^-0.5 * log2(e): the kernel exponentiates
  *          with exp2; v row-major, read as an MN-major tensor-core operand: no transposed copy)
- *   ctx  : bf16 [n_utt*T][heads*64]    rows of padded query tiles are left untouched
+ *   ctx  : bf16 [n_utt*T][heads*64]    rows of query tiles that hold padded frames only are set to zero
  */
 int aph_attention_bf16(const void* q, const void* k, const void* v, void* ctx,
                        const int32_t* lengths, int32_t n_utt, int32_t heads, int32_t T, void* stream);

@@ -278,3 +278,64 @@ def test_cuda_graph_predict_equals_eager(case):
     finally:
         with torch.no_grad():
             parameter.copy_(original)
+
+
+def test_length_buckets_are_invisible_and_share_one_arena():
+    from allophant_b200.dataset_processing import Batch
+    from allophant_b200.estimator import Estimator
+
+    _length_buckets_body(Batch, Estimator)
+
+
+def _length_buckets_body(Batch, Estimator):
+    """Inference pads each batch up to a 64-frame length bucket (engine.bucket_samples) and all launch lists overlay ONE workspace
+    arena: the log-probabilities of the valid frames are bit-identical to the exact-shape run, the caller sees the unpadded
+    frame count, and a ragged stream builds no launch list (and allocates no workspace) after its buckets have been seen."""
+    import os
+
+    spec = restatement.multitask_spec(n_train_phonemes=40)
+    spec.encoder_overrides = dict(num_hidden_layers=2)
+    oracle = restatement.OracleModel(spec)
+    model, _ = helpers.cuda_model_for_spec(spec, oracle)
+    acoustic = model.acoustic_model
+    generator = torch.Generator().manual_seed(3)
+
+    def batch_of(n, samples):
+        lengths = torch.randint(samples // 2, samples + 1, (n,), generator=generator)
+        lengths[0] = samples
+        audio = restatement.synthetic_audio(n, samples, seed=int(samples)) * restatement.mask_sequence(lengths)
+        return Batch(audio.cuda(), lengths.cuda(), torch.zeros(n, dtype=torch.long).cuda())
+
+    shapes = [(3, 40_000), (3, 47_111), (2, 52_345), (3, 33_333), (3, 44_000), (2, 51_000)]
+    batches = [batch_of(n, samples) for n, samples in shapes]
+    exact = []
+    acoustic.bucket_frames = 0
+    with torch.inference_mode():
+        for batch in batches:
+            exact.append({name: value.clone() for name, value in model.predict_log_probabilities(batch).outputs.items()})
+    acoustic._plans.clear()
+    acoustic.bucket_frames = 64
+    builds_before = acoustic.plan_builds
+    with torch.inference_mode():
+        for batch, reference in zip(batches, exact):
+            outputs = model.predict_log_probabilities(batch).outputs
+            for name, value in outputs.items():
+                assert value.shape == reference[name].shape, name
+                assert torch.equal(value, reference[name]), name
+        builds_first_pass = acoustic.plan_builds - builds_before
+        arena = acoustic._arena.buffer
+        assert arena is not None
+        for batch, reference in zip(reversed(batches), reversed(exact)):  # switching back and forth between the launch lists
+            outputs = model.predict_log_probabilities(batch).outputs
+            for name, value in outputs.items():
+                assert torch.equal(value, reference[name]), name
+        assert acoustic.plan_builds - builds_before == builds_first_pass  # nothing rebuilt
+        assert acoustic._arena.buffer is arena  # nothing reallocated
+    # 40 000 / 44 000 samples (124 / 137 frames) and 47 111 / 52 345 / 51 000 (147 / 163 / 159) share a bucket per batch size
+    assert len({key[:2] for key in acoustic._plans}) < len(shapes)
+    with torch.inference_mode():
+        estimator = Estimator(None, 1, 16000, None, model, {})  # type: ignore[arg-type]
+        for batch, reference in zip(batches[:3], exact[:3]):
+            graphed = estimator.predict(batch, cuda_graph=True).outputs
+            for name, value in graphed.items():
+                assert value.shape == reference[name].shape and torch.equal(value, reference[name]), name

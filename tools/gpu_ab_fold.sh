@@ -4,8 +4,8 @@ mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_e2e_parity.py tests/test_gpu_full_size.py tests/test_gpu_full_size_parity.py -m gpu -x -q > gpurun_out/ab_fold_tests.log 2>&1; echo "tests rc=$?"
 tail -5 gpurun_out/ab_fold_tests.log
 grep -E "^\[config" gpurun_out/ab_fold_tests.log | cut -c1-400
-APH_FOLD_LN=0 timeout 600 python bench.py --skip-cpu-baseline --skip-train --skip-membound > gpurun_out/ab_fold_off.json 2> gpurun_out/ab_fold_off.err; echo "off rc=$?"
-APH_FOLD_LN=1 timeout 600 python bench.py --skip-cpu-baseline --skip-train --skip-membound > gpurun_out/ab_fold_on.json 2> gpurun_out/ab_fold_on.err; echo "on rc=$?"
+APH_FOLD_LN=0 timeout 600 python bench.py --skip-cpu-baseline --skip-train --skip-membound --skip-ragged > gpurun_out/ab_fold_off.json 2> gpurun_out/ab_fold_off.err; echo "off rc=$?"
+APH_FOLD_LN=1 timeout 600 python bench.py --skip-cpu-baseline --skip-train --skip-membound --skip-ragged > gpurun_out/ab_fold_on.json 2> gpurun_out/ab_fold_on.err; echo "on rc=$?"
 python - <<'PY'
 import json
 for name in ("off", "on"):

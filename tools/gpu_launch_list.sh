@@ -2,7 +2,7 @@
 # ncu launch list (durations only) of one predict step; $1 = output tag, rest = env assignments
 tag=$1; shift
 mkdir -p gpurun_out
-env "$@" timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_${tag}.csv python bench.py --steps 1 --warmup 3 --skip-cpu-baseline --skip-train --skip-membound > gpurun_out/launches_${tag}.log 2>&1; echo "launch list ${tag} rc=$?"
+env "$@" timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_${tag}.csv python bench.py --steps 1 --warmup 3 --skip-cpu-baseline --skip-train --skip-membound --skip-ragged > gpurun_out/launches_${tag}.log 2>&1; echo "launch list ${tag} rc=$?"
 python - <<PY
 import csv, re, collections
 rows = list(csv.reader(open("gpurun_out/launches_${tag}.csv")))
