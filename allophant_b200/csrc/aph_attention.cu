@@ -145,39 +145,52 @@ __global__ void __launch_bounds__(kAttThreads, 2)
     }
   } else if (warp == 4) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // Whole warp in the loop, ONE elected lane issues (here and in the MMA warp): addresses and coordinates stay warp-uniform
+    // and live in uniform registers; under `if (lane == 0)` the compiler wraps every TMA / tcgen05 instruction in an
+    // ELECT + R2UR + BRA.U.ANY waterfall (~20 dependent instructions each, profiles/r02_gemm_epilogue_timeline.md).
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, kAttQBytes);
       tma_load_3d(s_q, &tm_q, q_full, 0, q0, bh);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j % kAttStages;
-        const uint32_t ph = static_cast<uint32_t>(j / kAttStages) & 1u;
-        mbar_wait(&k_empty[st], ph ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j % kAttStages;
+      const uint32_t ph = static_cast<uint32_t>(j / kAttStages) & 1u;
+      mbar_wait(&k_empty[st], ph ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&k_full[st], kAttKVBytes);
         tma_load_3d(s_k + st * kAttKVBytes, &tm_k, &k_full[st], 0, j * kAttKV, bh);
-        mbar_wait(&v_empty[st], ph ^ 1);
+      }
+      __syncwarp();
+      mbar_wait(&v_empty[st], ph ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&v_full[st], kAttKVBytes);
         tma_load_3d(s_v + st * kAttKVBytes, &tm_v, &v_full[st], 0, j * kAttKV, bh);
       }
+      __syncwarp();
     }
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64) | kIdescBMnMajor;  // B = V [key rows][64 d]: N contiguous
       const uint64_t dq = umma_desc_sw128(smem_u32(s_q));
       mbar_wait(q_full, 0);
-      APH_STAMP(2);
+      if (lane == 0) APH_STAMP(2);
       auto issue_s = [&](int j) {  // S_j = Q K_j^T into TMEM buffer j & 1
         const int st = j % kAttStages;
         mbar_wait(&k_full[st], static_cast<uint32_t>(j / kAttStages) & 1u);
         tc_fence_after();
         const uint64_t dk = umma_desc_sw128(smem_u32(s_k + st * kAttKVBytes));
         const uint32_t tmem_s = tmem_base + static_cast<uint32_t>((j & 1) * 64);
+        if (elect_one()) {  // the same lane every time: tcgen05.commit tracks the MMAs of the thread that issues it
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc, k != 0 ? 1u : 0u);
-        umma_commit(&s_full[j & 1]);
-        umma_commit(&k_empty[st]);  // the K tile is free once these MMAs have read it
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc, k != 0 ? 1u : 0u);
+          umma_commit(&s_full[j & 1]);
+          umma_commit(&k_empty[st]);  // the K tile is free once these MMAs have read it
+        }
+        __syncwarp();
       };
       issue_s(0);
       if (n_kv > 1) issue_s(1);
@@ -188,11 +201,14 @@ __global__ void __launch_bounds__(kAttThreads, 2)
         tc_fence_after();
         const uint64_t dp = umma_desc_sw128(smem_u32(s_p + (j & 1) * kAttPBytes));
         const uint64_t dv = umma_desc_mn_sw128(smem_u32(s_v + st * kAttKVBytes), kAttKVBytes);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // 16 keys per UMMA_K step: +32 bytes along P's rows, +16 rows (2 KB) of V
-          umma_bf16(tmem_o, dp + static_cast<uint64_t>(2 * k), dv + static_cast<uint64_t>(128 * k), idesc_pv, (j | k) != 0 ? 1u : 0u);
-        umma_commit(&o_full[j & 1]);
-        umma_commit(&v_empty[st]);
+          for (int k = 0; k < 4; ++k)  // 16 keys per UMMA_K step: +32 bytes along P's rows, +16 rows (2 KB) of V
+            umma_bf16(tmem_o, dp + static_cast<uint64_t>(2 * k), dv + static_cast<uint64_t>(128 * k), idesc_pv, (j | k) != 0 ? 1u : 0u);
+          umma_commit(&o_full[j & 1]);
+          umma_commit(&v_empty[st]);
+        }
+        __syncwarp();
         // S_{j+2} is issued AFTER PV_j and reuses the TMEM buffer of S_j.  tcgen05 operations of one thread complete
         // in order and a commit tracks everything issued before it, so "S_{j+2} ready" also tells the softmax warps
         // that PV_j has finished reading P buffer j & 1 — the buffer P_{j+2} goes to — without a second wait.

@@ -206,21 +206,28 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 
   if (warp == 4) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      mbar_arrive_expect_tx(kv_full, 2 * kBwdTileBytes);
-      tma_load_3d(s_k, &tm_k, kv_full, 0, k0, bh);
-      tma_load_3d(s_v, &tm_v, kv_full, 0, k0, bh);
+    // (whole warp in the loop, one elected lane issues — see aph_attention.cu: no waterfall around the TMA / MMA instructions)
+    {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(kv_full, 2 * kBwdTileBytes);
+        tma_load_3d(s_k, &tm_k, kv_full, 0, k0, bh);
+        tma_load_3d(s_v, &tm_v, kv_full, 0, k0, bh);
+      }
+      __syncwarp();
       for (int i = 0; i < n_q; ++i) {
         const int st = i & 1;
         mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&q_full[st], 2 * kBwdTileBytes);
-        tma_load_3d(s_q + st * kBwdTileBytes, &tm_q, &q_full[st], 0, i * kBwdTile, bh);
-        tma_load_3d(s_do + st * kBwdTileBytes, &tm_do, &q_full[st], h * kBwdD, i * kBwdTile, b);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&q_full[st], 2 * kBwdTileBytes);
+          tma_load_3d(s_q + st * kBwdTileBytes, &tm_q, &q_full[st], 0, i * kBwdTile, bh);
+          tma_load_3d(s_do + st * kBwdTileBytes, &tm_do, &q_full[st], h * kBwdD, i * kBwdTile, b);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {
       const uint64_t dk = umma_desc_sw128(smem_u32(s_k));
       const uint64_t dv = umma_desc_sw128(smem_u32(s_v));
       const uint64_t dpt0 = umma_desc_sw128(smem_u32(s_pt));
@@ -234,13 +241,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
         tc_fence_after();
         const uint64_t dq = umma_desc_sw128(smem_u32(s_q + st * kBwdTileBytes));
         const uint64_t ddo = umma_desc_sw128(smem_u32(s_do + st * kBwdTileBytes));
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // S^T[key][query] = sum_d K[key][d] Q[query][d]
-          umma_bf16(tmem_st, dk + static_cast<uint64_t>(2 * k), dq + static_cast<uint64_t>(2 * k), kIdescS, k != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)  // S^T[key][query] = sum_d K[key][d] Q[query][d]
+            umma_bf16(tmem_st, dk + static_cast<uint64_t>(2 * k), dq + static_cast<uint64_t>(2 * k), kIdescS, k != 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // dP^T[key][query] = sum_d V[key][d] dO[query][d]
-          umma_bf16(tmem_dpt, dv + static_cast<uint64_t>(2 * k), ddo + static_cast<uint64_t>(2 * k), kIdescS, k != 0 ? 1u : 0u);
-        umma_commit(s_full);
+          for (int k = 0; k < 4; ++k)  // dP^T[key][query] = sum_d V[key][d] dO[query][d]
+            umma_bf16(tmem_dpt, dv + static_cast<uint64_t>(2 * k), ddo + static_cast<uint64_t>(2 * k), kIdescS, k != 0 ? 1u : 0u);
+          umma_commit(s_full);
+        }
+        __syncwarp();
       };
       issue_scores(0);
       for (int i = 0; i < n_q; ++i) {
@@ -250,22 +260,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
         // B operands: the same Q / dO tiles, read MN-major ([128 query rows][64 d]); 16 rows per UMMA_K step
         const uint64_t bq = umma_desc_mn_sw128(smem_u32(s_q + st * kBwdTileBytes), kBwdTileBytes);
         const uint64_t bdo = umma_desc_mn_sw128(smem_u32(s_do + st * kBwdTileBytes), kBwdTileBytes);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {  // dV[key][d] += sum_query P^T[key][query] dO[query][d]
-          const uint64_t da = (k < 4 ? dpt0 : dpt1) + static_cast<uint64_t>(2 * (k & 3));
-          umma_bf16(tmem_dv, da, bdo + static_cast<uint64_t>(128 * k), kIdescAcc, (i | k) != 0 ? 1u : 0u);
-        }
+          for (int k = 0; k < 8; ++k) {  // dV[key][d] += sum_query P^T[key][query] dO[query][d]
+            const uint64_t da = (k < 4 ? dpt0 : dpt1) + static_cast<uint64_t>(2 * (k & 3));
+            umma_bf16(tmem_dv, da, bdo + static_cast<uint64_t>(128 * k), kIdescAcc, (i | k) != 0 ? 1u : 0u);
+          }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {  // dK[key][d] += sum_query dS^T[key][query] Q[query][d]
-          const uint64_t da = (k < 4 ? dst0 : dst1) + static_cast<uint64_t>(2 * (k & 3));
-          umma_bf16(tmem_dk, da, bq + static_cast<uint64_t>(128 * k), kIdescAcc, (i | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 8; ++k) {  // dK[key][d] += sum_query dS^T[key][query] Q[query][d]
+            const uint64_t da = (k < 4 ? dst0 : dst1) + static_cast<uint64_t>(2 * (k & 3));
+            umma_bf16(tmem_dk, da, bq + static_cast<uint64_t>(128 * k), kIdescAcc, (i | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&q_empty[st]);
+          if (i + 1 >= n_q) umma_commit(acc_full);
         }
-        umma_commit(&q_empty[st]);
-        if (i + 1 < n_q) {
-          issue_scores(i + 1);  // S^T / dP^T are free: pt_full(i) means the compute warps finished reading them
-        } else {
-          umma_commit(acc_full);
-        }
+        __syncwarp();
+        if (i + 1 < n_q) issue_scores(i + 1);  // S^T / dP^T are free: pt_full(i) means the compute warps finished reading them
       }
     }
   } else {
@@ -449,61 +459,70 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
   const uint32_t tmem_dq = tmem_base + 256;
 
   if (warp == 4) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, 2 * kBwdTileBytes);
-      tma_load_3d(s_q, &tm_q, q_full, 0, q0, bh);
-      tma_load_3d(s_do, &tm_do, q_full, h * kBwdD, q0, b);
-      APH_MARK(3, 1);
+    {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, 2 * kBwdTileBytes);
+        tma_load_3d(s_q, &tm_q, q_full, 0, q0, bh);
+        tma_load_3d(s_do, &tm_do, q_full, h * kBwdD, q0, b);
+      }
+      __syncwarp();
+      if (lane == 0) APH_MARK(3, 1);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
         mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-        APH_MARK(3, 2 + j);
-        mbar_arrive_expect_tx(&kv_full[st], 2 * kBwdTileBytes);
-        tma_load_3d(s_k + st * kBwdTileBytes, &tm_k, &kv_full[st], 0, j * kBwdTile, bh);
-        tma_load_3d(s_v + st * kBwdTileBytes, &tm_v, &kv_full[st], 0, j * kBwdTile, bh);
+        if (lane == 0) APH_MARK(3, 2 + j);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&kv_full[st], 2 * kBwdTileBytes);
+          tma_load_3d(s_k + st * kBwdTileBytes, &tm_k, &kv_full[st], 0, j * kBwdTile, bh);
+          tma_load_3d(s_v + st * kBwdTileBytes, &tm_v, &kv_full[st], 0, j * kBwdTile, bh);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
+    {
       const uint64_t dq = umma_desc_sw128(smem_u32(s_q));
       const uint64_t ddo = umma_desc_sw128(smem_u32(s_do));
       const uint64_t dds0 = umma_desc_sw128(smem_u32(s_ds));
       const uint64_t dds1 = umma_desc_sw128(smem_u32(s_ds + kBwdTileBytes));
       mbar_wait(q_full, 0);
-      APH_MARK(4, 1);
+      if (lane == 0) APH_MARK(4, 1);
       auto issue_scores = [&](int j) {
         const int st = j & 1;
         mbar_wait(&kv_full[st], (j >> 1) & 1);
-        APH_MARK(4, 10 + j);
+        if (lane == 0) APH_MARK(4, 10 + j);
         tc_fence_after();
         const uint64_t dk = umma_desc_sw128(smem_u32(s_k + st * kBwdTileBytes));
         const uint64_t dv = umma_desc_sw128(smem_u32(s_v + st * kBwdTileBytes));
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // S[query][key]
-          umma_bf16(tmem_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), kIdescS, k != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)  // S[query][key]
+            umma_bf16(tmem_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), kIdescS, k != 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // dP[query][key] = sum_d dO[query][d] V[key][d]
-          umma_bf16(tmem_dp, ddo + static_cast<uint64_t>(2 * k), dv + static_cast<uint64_t>(2 * k), kIdescS, k != 0 ? 1u : 0u);
-        umma_commit(s_full);
+          for (int k = 0; k < 4; ++k)  // dP[query][key] = sum_d dO[query][d] V[key][d]
+            umma_bf16(tmem_dp, ddo + static_cast<uint64_t>(2 * k), dv + static_cast<uint64_t>(2 * k), kIdescS, k != 0 ? 1u : 0u);
+          umma_commit(s_full);
+        }
+        __syncwarp();
       };
       issue_scores(0);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
         mbar_wait(ds_full, j & 1);
-        APH_MARK(5, 1 + j);
+        if (lane == 0) APH_MARK(5, 1 + j);
         tc_fence_after();
         const uint64_t bk = umma_desc_mn_sw128(smem_u32(s_k + st * kBwdTileBytes), kBwdTileBytes);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {  // dQ[query][d] += sum_key dS[query][key] K[key][d]
-          const uint64_t da = (k < 4 ? dds0 : dds1) + static_cast<uint64_t>(2 * (k & 3));
-          umma_bf16(tmem_dq, da, bk + static_cast<uint64_t>(128 * k), kIdescAcc, (j | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 8; ++k) {  // dQ[query][d] += sum_key dS[query][key] K[key][d]
+            const uint64_t da = (k < 4 ? dds0 : dds1) + static_cast<uint64_t>(2 * (k & 3));
+            umma_bf16(tmem_dq, da, bk + static_cast<uint64_t>(128 * k), kIdescAcc, (j | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&kv_empty[st]);
+          if (j + 1 >= n_kv) umma_commit(acc_full);
         }
-        umma_commit(&kv_empty[st]);
-        if (j + 1 < n_kv) {
-          issue_scores(j + 1);
-        } else {
-          umma_commit(acc_full);
-        }
+        __syncwarp();
+        if (j + 1 < n_kv) issue_scores(j + 1);
       }
     }
   } else {
