@@ -612,11 +612,15 @@ class EncoderPlan:
         if not cfg.do_stable_layer_norm:
             self._build_post_ln(steps, heads, FF)
             return
-        # Inference: the two LayerNorms of a layer are folded into the GEMMs around them.  out-proj / FFN2 leave a bf16 copy of
-        # the residual stream and per-row (sum, sum of squares); the q/k/v and FFN1 projections read that copy, a gamma-folded
-        # weight and apply mean / rstd in their epilogue (ops.with_row_stats / with_layernorm).  Only the first LayerNorm of
-        # layer 0 (its input comes from the positional conv) and the encoder's final LayerNorm still run as kernels.
-        self.fold_ln = (not self.training) and os.environ.get("APH_FOLD_LN", "1") != "0" and H % 256 == 0
+        # Inference option (APH_FOLD_LN=1): the two LayerNorms of a layer folded into the GEMMs around them.  out-proj / FFN2 leave a
+        # bf16 copy of the residual stream and per-row (sum, sum of squares); the q/k/v and FFN1 projections read that copy, a
+        # gamma-folded weight and apply mean / rstd in their epilogue (ops.with_row_stats / with_layernorm).  Only the first
+        # LayerNorm of layer 0 (its input comes from the positional conv) and the encoder's final LayerNorm still run as kernels:
+        # 146 launches instead of 193.  Measured (profiles/r02_layernorm_fold.md): the 47 LayerNorm launches it removes (0.94 ms)
+        # are paid back almost entirely inside the producing GEMMs (third staging tile -> 4 instead of 5 pipeline stages, +14 us per
+        # FFN2), the step gains 1.2 % and the GEMM's own roofline figure drops by 7 points because its time now includes the
+        # LayerNorm work — so it is off by default.
+        self.fold_ln = (not self.training) and os.environ.get("APH_FOLD_LN", "0") == "1" and H % 256 == 0
         folded = p.ensure_folded() if self.fold_ln else None
         for index, lw in enumerate(p.layers):
             if self.training:
