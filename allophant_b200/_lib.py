@@ -84,6 +84,7 @@ class GemmArgs(Structure):
         ("ln_cols", c_int32),
         ("ln_colsum", c_void_p),
         ("ln_eps", c_float),
+        ("taps_span", c_int32),
     ]
 
 

@@ -465,6 +465,136 @@ static int launch_beta(const CtcHeadPack& heads, int n_heads, int n_utt, int T, 
   return APH_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Long label sequences (more than 511 labels: 2S+1 states no longer fit 32 lanes x 32 registers).  nn.CTCLoss has no such
+// limit (loss_functions.py:24); contour attributes emit several labels per phoneme and 30 s utterances can get there.  This is
+// the plain formulation: one block per (utterance, head), the states strided over the threads, two alpha (beta) rows in shared
+// memory, one block barrier per frame, natural-log arithmetic with expf / logf.  It is a correctness path — a batch whose longest
+// label sequence stays within 511 never takes it.
+// ---------------------------------------------------------------------------
+constexpr int kCtcLongThreads = 256;
+
+__device__ __forceinline__ float lse_nat(float a, float b) {
+  const float m = fmaxf(a, b);
+  if (m == -INFINITY) return -INFINITY;
+  return m + logf(expf(a - m) + expf(b - m));
+}
+
+__global__ void __launch_bounds__(kCtcLongThreads) ctc_long_alpha_kernel(const __grid_constant__ CtcHeadPack heads, int n_heads, int n_utt, int T,
+                                                                         const long long* __restrict__ input_lengths,
+                                                                         float* __restrict__ alpha_ws, float* __restrict__ nll_out) {
+  extern __shared__ float long_smem[];  // [2][s_pad] rows, then int symbols[s_pad]
+  const int pair = blockIdx.x;
+  const int h = pair / n_utt, n = pair - h * n_utt;
+  PairInfo p;
+  load_pair(heads, h, n, n_utt, T, input_lengths, alpha_ws, p);
+  const int S2 = 2 * p.S + 1;
+  float* out = nll_out + static_cast<long long>(h) * n_utt + n;
+  if (S2 > p.s_pad || p.S > heads.h[h].label_stride) {
+    if (threadIdx.x == 0) *out = NAN;
+    return;
+  }
+  if (p.T_in == 0) {
+    if (threadIdx.x == 0) *out = p.S == 0 ? 0.f : INFINITY;
+    return;
+  }
+  float* row0 = long_smem;
+  float* row1 = long_smem + p.s_pad;
+  int* symbol = reinterpret_cast<int*>(long_smem + 2 * p.s_pad);
+  for (int s = threadIdx.x; s < S2; s += blockDim.x) {
+    symbol[s] = (s & 1) ? static_cast<int>(p.labels[s >> 1]) : 0;
+    row0[s] = s < 2 ? p.lp[symbol[s]] : -INFINITY;
+  }
+  __syncthreads();
+  if (p.alpha != nullptr)
+    for (int s = threadIdx.x; s < S2; s += blockDim.x) p.alpha[s] = row0[s];
+  float* prev = row0;
+  float* cur = row1;
+  for (int t = 1; t < p.T_in; ++t) {
+    const float* lp_t = p.lp + static_cast<long long>(t) * p.stride_t;
+    for (int s = threadIdx.x; s < S2; s += blockDim.x) {
+      float v = prev[s];
+      if (s > 0) v = lse_nat(v, prev[s - 1]);
+      if ((s & 1) && s > 2 && symbol[s] != symbol[s - 2]) v = lse_nat(v, prev[s - 2]);
+      v += lp_t[symbol[s]];
+      cur[s] = v;
+      if (p.alpha != nullptr) p.alpha[static_cast<long long>(t) * p.s_pad + s] = v;
+    }
+    __syncthreads();
+    float* swap = prev;
+    prev = cur;
+    cur = swap;
+  }
+  if (threadIdx.x == 0) {
+    float total = prev[S2 - 1];
+    if (S2 > 1) total = lse_nat(total, prev[S2 - 2]);
+    *out = -total;
+  }
+}
+
+// beta recursion + gradient with respect to the logits behind the log_softmax: g * (exp(lp) - occupancy)
+__global__ void __launch_bounds__(kCtcLongThreads) ctc_long_beta_kernel(const __grid_constant__ CtcHeadPack heads, int n_heads, int n_utt, int T,
+                                                                        const long long* __restrict__ input_lengths,
+                                                                        const float* __restrict__ alpha_ws, const float* __restrict__ nll_in,
+                                                                        const float* __restrict__ grad_scale) {
+  extern __shared__ float long_smem[];
+  const int pair = blockIdx.x;
+  const int h = pair / n_utt, n = pair - h * n_utt;
+  PairInfo p;
+  load_pair(heads, h, n, n_utt, T, input_lengths, const_cast<float*>(alpha_ws), p);
+  if (p.grad == nullptr) return;
+  const int S2 = 2 * p.S + 1;
+  const float nll = nll_in[static_cast<long long>(h) * n_utt + n];
+  const float g = grad_scale ? grad_scale[h] : 1.f;
+  const bool dead = !(nll < INFINITY) || S2 > p.s_pad;
+  const int t_valid = dead ? 0 : p.T_in;
+  // frames past the utterance (all frames of a zeroed loss): zero gradient; valid frames start from g * softmax
+  for (long long i = threadIdx.x; i < static_cast<long long>(T) * p.c; i += blockDim.x) {
+    const int t = static_cast<int>(i / p.c);
+    const int k = static_cast<int>(i - static_cast<long long>(t) * p.c);
+    const long long off = static_cast<long long>(t) * p.stride_t + k;
+    p.grad[off] = t < t_valid ? g * expf(p.lp[off]) : 0.f;
+  }
+  if (dead || p.T_in == 0) return;
+  __syncthreads();
+  float* row0 = long_smem;
+  float* row1 = long_smem + p.s_pad;
+  int* symbol = reinterpret_cast<int*>(long_smem + 2 * p.s_pad);
+  const int t_last = p.T_in - 1;
+  for (int s = threadIdx.x; s < S2; s += blockDim.x) {
+    symbol[s] = (s & 1) ? static_cast<int>(p.labels[s >> 1]) : 0;
+    row0[s] = s >= S2 - 2 ? p.lp[static_cast<long long>(t_last) * p.stride_t + symbol[s]] : -INFINITY;
+  }
+  __syncthreads();
+  float* next = row0;
+  float* cur = row1;
+  for (int t = t_last; t >= 0; --t) {
+    const float* lp_t = p.lp + static_cast<long long>(t) * p.stride_t;
+    float* grad_t = p.grad + static_cast<long long>(t) * p.stride_t;
+    const float* alpha_t = p.alpha + static_cast<long long>(t) * p.s_pad;
+    if (t < t_last) {
+      for (int s = threadIdx.x; s < S2; s += blockDim.x) {
+        float v = next[s];
+        if (s + 1 < S2) v = lse_nat(v, next[s + 1]);
+        if ((s & 1) && s + 2 < S2 && symbol[s] != symbol[s + 2]) v = lse_nat(v, next[s + 2]);
+        cur[s] = v + lp_t[symbol[s]];
+      }
+      __syncthreads();
+      float* swap = next;
+      next = cur;
+      cur = swap;
+    }
+    // `next` now holds beta[t]
+    for (int s = threadIdx.x; s < S2; s += blockDim.x) {
+      const float lcab = alpha_t[s] + next[s];
+      if (lcab > -INFINITY) atomicAdd(grad_t + symbol[s], -g * expf(lcab - lp_t[symbol[s]] + nll));
+    }
+    __syncthreads();
+  }
+}
+
+static size_t long_smem_bytes(int s_pad) { return static_cast<size_t>(s_pad) * 12; }
+
 static int pick_k(int max_label_len) {
   const int states = 2 * max_label_len + 1;
   // even K only (the recursions specialise on the parity of the state); fine steps where the label lengths of speech live
@@ -478,9 +608,14 @@ static int pick_k(int max_label_len) {
 
 using namespace aph;
 
+// Longest label sequence the block-per-pair path takes: two rows of 2S+1 floats and the symbols in 200 KB of shared memory
+constexpr int kCtcLongMaxLabels = 8000;
+
 extern "C" int aph_ctc_states_pad(int32_t max_label_len) {
   const int k = pick_k(max_label_len);
-  return k == 0 ? APH_ERR_UNSUPPORTED : 32 * k;
+  if (k != 0) return 32 * k;
+  if (max_label_len > kCtcLongMaxLabels) return APH_ERR_UNSUPPORTED;
+  return (2 * max_label_len + 1 + 31) / 32 * 32;  // block-per-pair path
 }
 
 extern "C" int aph_ctc_forward(const aph_ctc_head* heads_host, int32_t n_heads, int32_t n_utt, int32_t T,
@@ -490,16 +625,26 @@ extern "C" int aph_ctc_forward(const aph_ctc_head* heads_host, int32_t n_heads, 
   APH_REQUIRE(heads_host && input_lengths && nll_out, "null pointer");
   APH_REQUIRE(n_heads > 0 && n_utt > 0 && T > 0, "empty problem");
   const int k = pick_k(max_label_len);
-  if (k == 0) {
-    set_last_error("aph_ctc_forward", "label sequences longer than 511 are not supported", __FILE__, __LINE__);
+  if (k == 0 && max_label_len > kCtcLongMaxLabels) {
+    set_last_error("aph_ctc_forward", "label sequences longer than 8000 are not supported", __FILE__, __LINE__);
     return APH_ERR_UNSUPPORTED;
   }
   int launched = 0;
+  if (k == 0) {
+    const size_t smem = long_smem_bytes(aph_ctc_states_pad(max_label_len));
+    APH_CUDA_CHECK(cudaFuncSetAttribute(ctc_long_alpha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  }
   for (int h0 = 0; h0 < n_heads; h0 += kCtcMaxHeads) {
     const int nh = n_heads - h0 < kCtcMaxHeads ? n_heads - h0 : kCtcMaxHeads;
     CtcHeadPack pack;
     memcpy(pack.h, heads_host + h0, sizeof(aph_ctc_head) * nh);
     float* nll = nll_out + static_cast<long long>(h0) * n_utt;
+    if (k == 0) {
+      ctc_long_alpha_kernel<<<nh * n_utt, kCtcLongThreads, long_smem_bytes(aph_ctc_states_pad(max_label_len)), stream>>>(
+          pack, nh, n_utt, T, reinterpret_cast<const long long*>(input_lengths), alpha_ws, nll);
+      ++launched;
+      continue;
+    }
     switch (k) {
       case 2: launch_alpha<2>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll, stream); break;
       case 4: launch_alpha<4>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll, stream); break;
@@ -529,11 +674,26 @@ extern "C" int aph_ctc_backward(const aph_ctc_head* heads_host, int32_t n_heads,
   APH_REQUIRE(heads_host && input_lengths && alpha_ws && nll, "null pointer");
   APH_REQUIRE(n_heads > 0 && n_utt > 0 && T > 0, "empty problem");
   const int k = pick_k(max_label_len);
-  if (k == 0) {
-    set_last_error("aph_ctc_backward", "label sequences longer than 511 are not supported", __FILE__, __LINE__);
+  if (k == 0 && max_label_len > kCtcLongMaxLabels) {
+    set_last_error("aph_ctc_backward", "label sequences longer than 8000 are not supported", __FILE__, __LINE__);
     return APH_ERR_UNSUPPORTED;
   }
   int launched = 0;
+  if (k == 0) {  // block-per-pair path: initialises the gradient itself
+    const size_t smem = long_smem_bytes(aph_ctc_states_pad(max_label_len));
+    APH_CUDA_CHECK(cudaFuncSetAttribute(ctc_long_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    for (int h0 = 0; h0 < n_heads; h0 += kCtcMaxHeads) {
+      const int nh = n_heads - h0 < kCtcMaxHeads ? n_heads - h0 : kCtcMaxHeads;
+      CtcHeadPack pack;
+      memcpy(pack.h, heads_host + h0, sizeof(aph_ctc_head) * nh);
+      ctc_long_beta_kernel<<<nh * n_utt, kCtcLongThreads, smem, stream>>>(pack, nh, n_utt, T, reinterpret_cast<const long long*>(input_lengths),
+                                                                         alpha_ws, nll + static_cast<long long>(h0) * n_utt,
+                                                                         grad_scale ? grad_scale + h0 : nullptr);
+      ++launched;
+    }
+    APH_POST_LAUNCH(launched);
+    return APH_OK;
+  }
   for (int h = 0; h < n_heads; ++h) {
     if (heads_host[h].n_classes > kCtcSmallC && heads_host[h].grad != nullptr) {
       long long blocks = (static_cast<long long>(T) * heads_host[h].n_classes + 255) / 256;

@@ -102,6 +102,7 @@ struct GemmParams {
   const float* ln_colsum;   // consumer: sum_k B[n][k] of the gamma-folded weight
   float ln_inv_cols;        // 1 / (number of columns the statistics run over)
   float ln_eps;
+  int taps_span;            // TAPS: input channels one N tile contracts over per tap (64, or a block-diagonal super group)
 };
 
 // Work item -> (n block, m pair, output batch, k-block range, B row shift)
@@ -263,7 +264,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
             tma_load_3d_pair(sa, &tm_a, &full_bar[stage], mt * kBM, r0, seg);
             tma_load_3d_pair(sa + Cfg::kABytes / 2, &tm_a, &full_bar[stage], mt * kBM + 64, r0, seg);
           } else if (p.mode == APH_GEMM_TAPS) {
-            tma_load_3d_pair(sa, &tm_a, &full_bar[stage], n_blk * kBK, t0 - p.tap_pad + kb, b);
+            // k-block kb = (tap, 64-channel slice of the span this output tile contracts over)
+            const int kpt = p.taps_span / kBK;
+            const int tap = kb / kpt;
+            const int chan = (n_blk * kBK / p.taps_span) * p.taps_span + (kb - tap * kpt) * kBK;
+            tma_load_3d_pair(sa, &tm_a, &full_bar[stage], chan, t0 - p.tap_pad + tap, b);
           } else {
             tma_load_3d_pair(sa, &tm_a, &full_bar[stage], kb * kBK, t0, b);
           }
@@ -1023,6 +1028,8 @@ extern "C" int aph_gemm_bf16(const aph_gemm_args* a, void* stream_) {
   if (a->mode == APH_GEMM_TAPS) {
     // one 64-channel group per N tile; k-block j is tap j of that group
     APH_REQUIRE(a->n % 64 == 0 && a->a_inner == a->n, "taps mode: n == channels, multiple of 64");
+    p.taps_span = a->taps_span > 0 ? a->taps_span : 64;
+    APH_REQUIRE(p.taps_span % 64 == 0 && a->n % p.taps_span == 0 && a->k % p.taps_span == 0, "taps mode: taps_span a multiple of 64 dividing n and k");
     APH_REQUIRE(a->epilogue == APH_EPI_STORE, "taps mode supports the store epilogue only");
     p.n_tiles = a->n / 64;
     p.staged = a->out_f32 ? 1 : 0;  // 64-column tiles: only the fp32 staging granularity (32 columns) fits

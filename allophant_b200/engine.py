@@ -192,7 +192,15 @@ class PackedEncoder:
         self.fp_b = f32(fp.projection.bias)
         pc = w.encoder.pos_conv_embed.conv
         v = pc.parametrizations.weight.original1
-        self.pos_w = bf16(v.shape[0], v.shape[2] * v.shape[1])
+        # Groups that are not 64 channels wide (wav2vec2-base: 16 groups of 48): the tap GEMM contracts every 64-column output
+        # tile over a block-diagonal super group of `pos_span` channels (the smallest common multiple of the group width and 64)
+        # and the operand carries zeros where input and output channel belong to different groups (aph_gemm_args.taps_span).
+        group = v.shape[1]
+        self.pos_span = 64 if group == 64 else group * 64 // math.gcd(group, 64)
+        if H % self.pos_span != 0:
+            raise NotImplementedError(f"positional conv groups of {group} channels do not tile the hidden size {H}")
+        self.pos_w = bf16(v.shape[0], v.shape[2] * self.pos_span)
+        self.pos_w_grouped = self.pos_w if group == 64 else bf16(v.shape[0], v.shape[2] * group)
         self.pos_b = f32(pc.bias)
         self.layers = []
         for layer in w.encoder.layers:
@@ -221,7 +229,16 @@ class PackedEncoder:
         """Operands that are functions of several parameters: fused QKV bias, weight-normed positional conv."""
         w, H = self.weights, self.cfg.hidden_size
         pc = w.encoder.pos_conv_embed.conv
-        ops.pack_posconv_weight(pc.parametrizations.weight.original0, pc.parametrizations.weight.original1, dst=self.pos_w)
+        ops.pack_posconv_weight(pc.parametrizations.weight.original0, pc.parametrizations.weight.original1, dst=self.pos_w_grouped)
+        if self.pos_w_grouped is not self.pos_w:
+            # [O][tap][group] -> [O][tap][span], the group's columns at its offset inside the super group, zeros elsewhere
+            out_channels, group, span = self.pos_w.shape[0], pc.parametrizations.weight.original1.shape[1], self.pos_span
+            taps = self.pos_w_grouped.shape[1] // group
+            wide = self.pos_w.view(out_channels, taps, span)
+            wide.zero_()
+            offsets = (torch.arange(out_channels, device=wide.device) % span) // group * group  # first column of each row's group
+            columns = offsets[:, None] + torch.arange(group, device=wide.device)[None, :]
+            wide.scatter_(2, columns[:, None, :].expand(out_channels, taps, group), self.pos_w_grouped.view(out_channels, taps, group))
         self._pos_w_dgrad_valid = False
         for layer, packed in zip(w.encoder.layers, self.layers):
             att = layer.attention
@@ -577,34 +594,32 @@ class EncoderPlan:
             steps.append(self._regularise_projection)
         # positional conv embedding: hidden += gelu(grouped_conv(hidden)) (HF:764-765, 353-368)
         taps = cfg.num_conv_pos_embeddings
-        if H // cfg.num_conv_pos_embedding_groups != 64:
-            raise NotImplementedError("positional conv groups must be 64 channels wide")
-        steps.append(
-            self._gemm(
-                ops.make_gemm_args(
-                    self.hidden_bf16,
-                    p.pos_w,
-                    a_rows=self.seq,
-                    a_inner=H,
-                    a_row_stride=H,
-                    batch=N,
-                    a_batch_stride=self.seq * H,
-                    mode=_lib.APH_GEMM_TAPS,
-                    tap_pad=taps // 2,
-                    n=H,
-                    k=taps * 64,
-                    bias=p.pos_b,
-                    gelu=True,
-                    resid=self.hidden_fp if self.training else self.hidden,
-                    ld_resid=H,
-                    out_f32=self.hidden,
-                    ld_f32=H,
-                    out_batch_rows=self.seq,
-                    aux_bf16=self.pos_pre if self.training else None,
-                    ld_aux=H,
-                )
-            )
+        if p.pos_span != 64 and self.training:
+            raise NotImplementedError("training through positional conv groups that are not 64 channels wide (wav2vec2-base) is not built")
+        pos_args = ops.make_gemm_args(
+            self.hidden_bf16,
+            p.pos_w,
+            a_rows=self.seq,
+            a_inner=H,
+            a_row_stride=H,
+            batch=N,
+            a_batch_stride=self.seq * H,
+            mode=_lib.APH_GEMM_TAPS,
+            tap_pad=taps // 2,
+            n=H,
+            k=taps * p.pos_span,
+            bias=p.pos_b,
+            gelu=True,
+            resid=self.hidden_fp if self.training else self.hidden,
+            ld_resid=H,
+            out_f32=self.hidden,
+            ld_f32=H,
+            out_batch_rows=self.seq,
+            aux_bf16=self.pos_pre if self.training else None,
+            ld_aux=H,
         )
+        pos_args.taps_span = p.pos_span
+        steps.append(self._gemm(pos_args))
         if self.training:
             steps.append(self._regularise_encoder_input)
         heads = cfg.num_attention_heads

@@ -171,9 +171,15 @@ class SequentialFrontend(Frontend):
                     LengthWrapper(nn.Sequential(Transpose(-1, -2), nn.LayerNorm(previous_output_size, elementwise_affine=layer.affine), Transpose(-2, -1)))
                 )
             elif isinstance(layer, MaxPoolingConfig):
-                # The reference pools with stride = size but declares the lengths of a stride-1 pool (frontend.py:258-259), so
-                # its masks stop matching the activations after this layer; the layer is not reproduced here.
-                raise NotImplementedError("max_pool layers of the sequential frontend are not implemented")
+                # The reference pools with stride = size but declares the lengths of a "same"-padded stride-1 pool
+                # (frontend.py:258-259: conv_length(size) -> lengths + 1 for size 2), so behind this layer its frame counts exceed
+                # the frames that exist and its own transformer fails on the key-padding mask ("Expected key_padded_mask.shape[1]
+                # to be 15, but got 31"; tests/golden/max_pool_reference_behaviour.json holds the unmodified reference's exception).
+                # There is no behaviour to reproduce: the configuration is rejected up front with the reason.
+                raise NotImplementedError(
+                    "max_pool layers cannot be run: the reference declares frame counts for them that exceed the pooled frames "
+                    "(allophant/network/frontend.py:258-259) and its own forward pass fails on the attention mask"
+                )
             else:
                 raise ValueError(f"Unsupported layer config of type: {layer.__class__.__name__}")
         return cls(LengthSequential(*layers), previous_output_size, upscale_factor)

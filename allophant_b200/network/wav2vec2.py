@@ -65,9 +65,15 @@ KNOWN_MODELS: Dict[str, Wav2Vec2EncoderConfig] = {
     "facebook/wav2vec2-large-xlsr-53": Wav2Vec2EncoderConfig(mask_time_prob=0.075),
     "facebook/wav2vec2-xls-r-1b": Wav2Vec2EncoderConfig(hidden_size=1280, num_hidden_layers=48, intermediate_size=5120),
     # post-LN encoder, GroupNorm feature extractor without conv biases, no attention mask (preprocessor: return_attention_mask
-    # false).  (wav2vec2-base has the same ordering but 48-channel positional-conv groups, which the tap GEMM does not cover.)
+    # false)
     "facebook/wav2vec2-large": Wav2Vec2EncoderConfig(
         feat_extract_norm="group", conv_bias=False, do_stable_layer_norm=False, mask_time_prob=0.05, return_attention_mask=False,
+    ),
+    # the same ordering at width 768: 12 layers, 12 heads of 64, 3072 feed-forward units, positional conv in 16 groups of 48
+    # channels (run as four block-diagonal super groups of 192, engine.PackedEncoder.pos_span); inference only
+    "facebook/wav2vec2-base": Wav2Vec2EncoderConfig(
+        hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072, feat_extract_norm="group", conv_bias=False,
+        do_stable_layer_norm=False, mask_time_prob=0.05, return_attention_mask=False,
     ),
 }
 

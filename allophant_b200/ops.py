@@ -921,7 +921,7 @@ class CtcProblem:
         self.max_label_len = max(int(l.shape[1]) if l.dim() == 2 else 0 for l in labels)
         s_pad = int(lib.aph_ctc_states_pad(self.max_label_len))
         if s_pad < 0:
-            raise NotImplementedError(f"CTC label sequences longer than 511 are not supported (got {self.max_label_len})")
+            raise NotImplementedError(f"CTC label sequences longer than 8000 are not supported (got {self.max_label_len})")
         self.s_pad = s_pad
         self.keep: List[Tensor] = []
         self.grads: List[Optional[Tensor]] = []

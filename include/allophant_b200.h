@@ -143,6 +143,11 @@ typedef struct aph_gemm_args {
   int32_t ln_cols;
   const float* ln_colsum;
   float ln_eps;
+  /* APH_GEMM_TAPS with groups that are not 64 channels wide (wav2vec2-base: 768 channels in 16 groups of 48, HF:326-368): the
+   * grouped conv is run block-diagonally over super groups of taps_span channels (a common multiple of the group width and 64:
+   * 192), k = taps * taps_span, and B is packed [n][tap][taps_span] with zeros where input and output channel are in different
+   * groups.  0 = 64 (one 64-channel group per output tile). */
+  int32_t taps_span;
 } aph_gemm_args;
 
 int aph_gemm_bf16(const aph_gemm_args* args, void* stream);

@@ -110,5 +110,49 @@ def main() -> None:
               "heads", len(result["log_probabilities"]), os.path.getsize(path), "bytes")
 
 
+def max_pool_reference_behaviour() -> Dict[str, Any]:
+    """What the UNMODIFIED reference does with a ``max_pool`` layer (``frontend.py:258-259``): the sequential frontend runs, but
+    reports MORE frames than it produced, and the transformer acoustic model behind it raises on the key-padding mask.  Frozen in
+    ``tests/golden/max_pool_reference_behaviour.json`` as the justification for rejecting such configurations."""
+    import importlib
+    import json
+
+    ref = reference_shim.reference_modules()
+    cfg = ref.config
+    frontend = importlib.import_module("allophant.network.frontend")
+    acoustic = importlib.import_module("allophant.network.acoustic_model")
+    dataset = importlib.import_module("allophant.dataset_processing")
+    torch.manual_seed(0)
+    lengths = torch.tensor([30, 21, 9])
+    sequential = frontend.SequentialFrontend.from_config(cfg.SequentialFrontendConfig([cfg.MaxPoolingConfig(2)]), 8)
+    pooled = sequential(dataset.Batch(torch.randn(3, 8, 30), lengths, torch.zeros(3)))
+    options = dict(
+        transformer=dict(feedforward_neurons=128, heads=4, activation="gelu", num_layers=1, dropout_rate=0.0, positional_embeddings=True),
+        frontend=dict(architecture="linear", neurons=64, input_dropout=0.0),
+        sequential_frontend=[dict(type="glu1d", out_channels=64, kernel=3, stride=1)],
+        elementwise_affine=False,
+    )
+    config = acoustic_config(cfg, options)
+    config.sequential_frontend.layers.append(cfg.MaxPoolingConfig(2))
+    model = acoustic.TransformerAcousticModel.from_config(config, 40).eval()
+    try:
+        model(dataset.Batch(torch.randn(3, 40, 30), lengths, torch.zeros(3)))
+        outcome = {"raised": None}
+    except Exception as error:  # noqa: BLE001 - the point is to record whatever the reference does
+        outcome = {"raised": type(error).__name__, "message": str(error)}
+    record = {
+        "input_frames": 30,
+        "input_lengths": lengths.tolist(),
+        "frontend_output_frames": int(pooled.audio_features.shape[-1]),
+        "frontend_declared_lengths": pooled.lengths.tolist(),
+        "transformer_model": outcome,
+    }
+    with open(os.path.join(OUT_DIR, "max_pool_reference_behaviour.json"), "w") as file:
+        json.dump(record, file, indent=1)
+    return record
+
+
 if __name__ == "__main__":
-    main()
+    if os.environ.get("ONLY_MAX_POOL") != "1":
+        main()
+    print(max_pool_reference_behaviour())

@@ -280,6 +280,37 @@ def test_cuda_graph_predict_equals_eager(case):
             parameter.copy_(original)
 
 
+def test_wav2vec2_base_shape_matches_oracle():
+    """wav2vec2-base (the GroupNorm variant north_star names): width 768, 12 heads, 3072 feed-forward units, post-LN ordering and a
+    positional convolution in 16 groups of 48 channels (HF:326-368) — run as four block-diagonal super groups of 192 channels by the
+    tap GEMM (``aph_gemm_args.taps_span``).  Hidden states and log-probabilities against the Hugging Face model of that shape."""
+    from allophant_b200.dataset_processing import Batch
+
+    overrides = dict(
+        hidden_size=768, num_attention_heads=12, intermediate_size=3072, num_hidden_layers=2, do_stable_layer_norm=False,
+        feat_extract_norm="group", conv_bias=False,
+    )  # fmt: skip
+    spec = restatement.multitask_spec(n_train_phonemes=20, encoder_overrides=overrides, weight_seed=8)
+    oracle = restatement.OracleModel(spec)
+    assert oracle.config.hidden_size == 768 and oracle.config.num_conv_pos_embedding_groups == 16
+    model, _ = helpers.cuda_model_for_spec(spec, oracle)
+    lengths = torch.tensor([24000, 9000, 17345])
+    audio = restatement.synthetic_audio(3, 24000, seed=9) * restatement.mask_sequence(lengths)
+    batch = Batch(audio.cuda(), lengths.cuda(), torch.zeros(3, dtype=torch.long).cuda())
+    hidden_ref, frames_ref = oracle.encode(audio, lengths)
+    with torch.inference_mode():
+        hidden, frames = model.acoustic_model(batch)
+        predictions = model.predict_log_probabilities(batch)
+    assert torch.equal(frames.cpu(), frames_ref) and len(hidden) == len(hidden_ref) == 3
+    for index, (ours, reference) in enumerate(zip(hidden, hidden_ref)):
+        error = _range_error(ours.float().cpu(), reference, frames_ref.tolist())
+        assert error < RANGE_TOL, f"hidden state {index}: {error:.3e} of range"
+    outputs, _ = oracle.predict(audio, lengths)
+    for name, reference in outputs.items():
+        error = _range_error(predictions.outputs[name].float().cpu(), reference, frames_ref.tolist())
+        assert error < RANGE_TOL, f"{name}: {error:.3e} of range"
+
+
 def test_length_buckets_are_invisible_and_share_one_arena():
     from allophant_b200.dataset_processing import Batch
     from allophant_b200.estimator import Estimator

@@ -509,6 +509,44 @@ def test_ctc_long_labels_and_empty_targets():
         assert float(row_sums.abs().max()) < 5e-3  # |nll| ~ 1e3 in fp32: 1e-6 relative on nll = 1e-3 on sum(gamma)
 
 
+def test_ctc_label_sequences_beyond_511():
+    """More than 511 labels (2S+1 states no longer fit a warp's registers): the block-per-pair path, against the fp64 recursion.
+    nn.CTCLoss has no cap (loss_functions.py:24); contour attributes and 30 s utterances can exceed 511 labels."""
+    from allophant_b200.loss_functions import multi_head_ctc_loss
+
+    torch.manual_seed(5)
+    n_utt, frames = 3, 1499
+    class_counts = [4, 40]
+    input_lengths = torch.tensor([1499, 1300, 900])
+    label_lengths = [torch.tensor([700, 520, 0]), torch.tensor([600, 3, 450])]
+    logits, labels = [], []
+    for classes, lengths in zip(class_counts, label_lengths):
+        logits.append(torch.randn(frames, n_utt, classes) * 2)  # time-first, like the model's outputs
+        head_labels = torch.randint(1, classes, (n_utt, int(max(lengths))))
+        head_labels[0, 10:14] = 1  # repeats need blanks between them
+        labels.append(head_labels)
+    leaves = [t.cuda().requires_grad_(True) for t in logits]
+    losses = multi_head_ctc_loss(leaves, [l.cuda() for l in labels], input_lengths.cuda(), [l.cuda() for l in label_lengths])
+    weights = torch.tensor([1.0, 0.5], device=DEV)
+    (losses * weights).sum().backward()
+    for head in range(2):
+        leaf64 = logits[head].double().requires_grad_(True)
+        exact = restatement.ctc_wrapper(leaf64, labels[head], input_lengths, label_lengths[head])
+        exact.backward()
+        assert abs(float(losses[head]) - float(exact)) <= 1e-3 * abs(float(exact)), (float(losses[head]), float(exact))
+        ours = leaves[head].grad.cpu().double() / float(weights[head])
+        scale = float(leaf64.grad.abs().max())
+        # 1 499-frame log-space recursions in fp32 (|alpha| ~ 4e3, 2.4e-4 absolute per operation): judged like the 700-frame case,
+        # against what torch's own fp32 CTC loses to the fp64 recursion
+        leaf32 = logits[head].clone().requires_grad_(True)
+        restatement.ctc_wrapper(leaf32, labels[head], input_lengths, label_lengths[head]).backward()
+        torch_error = float((leaf32.grad.double() - leaf64.grad).abs().max())
+        ours_error = float((ours - leaf64.grad).abs().max())
+        print(f"ctc beyond 511 labels, head {head}: ours vs fp64 {ours_error:.2e}, torch fp32 vs fp64 {torch_error:.2e}")
+        assert ours_error <= max(3 * torch_error, 2e-3 * scale)
+        assert float(ours[900:, 2].abs().max()) == 0.0  # frames past the utterance
+
+
 def test_custom_ops_run_the_library_kernels():
     """torch.ops.allophant_b200.* against torch's own ops (and autograd through log_softmax)."""
     import allophant_b200.custom_ops  # noqa: F401  (registers the ops)

@@ -257,3 +257,21 @@ def test_beam_ctc_decoder_equals_exhaustive_search():
     assert isinstance(predictions._ctc_decoder(["a"], 1, 1), predictions.GreedyCTCDecoder)
     with pytest.raises(AssertionError, match="N-best can not exceed beam width"):
         predictions._ctc_decoder(["a"], 2, 3)
+
+
+def test_max_pool_layers_are_rejected_like_the_reference_fails():
+    """``max_pool`` layers of the sequential frontend (``frontend.py:258-259``): the unmodified reference declares more frames than
+    the pool produces and its transformer then fails on the key-padding mask (golden record made by
+    ``oracle/make_golden_transformer.py::max_pool_reference_behaviour``).  Here the configuration is rejected when the model is built."""
+    import json
+    import os
+
+    from allophant_b200.config import MaxPoolingConfig, SequentialFrontendConfig
+    from allophant_b200.network.frontend import SequentialFrontend
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "max_pool_reference_behaviour.json")) as file:
+        record = json.load(file)
+    assert record["frontend_output_frames"] == 15 and min(record["frontend_declared_lengths"]) >= 10 and max(record["frontend_declared_lengths"]) == 31
+    assert record["transformer_model"]["raised"] == "AssertionError" and "key_padded_mask" in record["transformer_model"]["message"]
+    with pytest.raises(NotImplementedError, match="max_pool"):
+        SequentialFrontend.from_config(SequentialFrontendConfig([MaxPoolingConfig(2)]), 8)

@@ -51,7 +51,8 @@ def test_argument_validation_needs_no_gpu():
         _lib.check(rc, "aph_gemm_bf16")
     assert _lib.lib.aph_ctc_states_pad(100) == 256
     assert _lib.lib.aph_ctc_states_pad(511) == 1024
-    assert _lib.lib.aph_ctc_states_pad(512) == _lib.APH_ERR_UNSUPPORTED
+    assert _lib.lib.aph_ctc_states_pad(512) == 1056  # block-per-pair path: 2 * 512 + 1 states rounded up to 32
+    assert _lib.lib.aph_ctc_states_pad(8001) == _lib.APH_ERR_UNSUPPORTED
 
 
 def test_no_cpu_fallback():
