@@ -177,6 +177,7 @@ _SIGNATURES = {
     "aph_collate_pad_f32": [_P, _P, _I64, _I64, _P, _I32],
     "aph_edit_statistics_batch": [_P, _P, _P, _P, _I64, _P, _P, _I32],
     "aph_fold_layernorm_linear": [_P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P],
+    "aph_attention_small": [_P, _I64, _P, _I64, _P, _I32, _I32, _I32, _I32, _P],
     "aph_ctc_states_pad": [_I32],
     "aph_ctc_forward": [POINTER(CtcHead), _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
     "aph_ctc_backward": [POINTER(CtcHead), _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],

@@ -250,6 +250,62 @@ __global__ void __launch_bounds__(256) activation_backward_kernel(float* d, long
   }
 }
 
+// ---------------------------------------------------------------------------
+// Self-attention over TIME for narrow sequences of vectors: the time layer of a classifier head
+// (ProjectingMultiheadAttention, acoustic_model.py:237-268: nn.MultiheadAttention over the head's projected classes, a few
+// channels per head, with the key-padding mask of the utterance lengths).  head_dim is arbitrary (the tcgen05 kernel of the
+// encoder needs 64), so this runs on the CUDA cores: one warp per query frame, scores of all keys in shared memory (two passes:
+// softmax statistics, then the weighted sum with the lanes spread over the head's channels).
+//   qkv  fp32 [n_utt*T][ld]: q at column 0, k at column hidden, v at column 2*hidden (nn.MultiheadAttention's in_proj order)
+//   ctx  bf16 [n_utt*T][ld_ctx], columns [0, hidden); rows of padded frames are written too (computed over the valid keys)
+// ---------------------------------------------------------------------------
+constexpr int kSmallAttWarps = 8;
+
+__global__ void __launch_bounds__(kSmallAttWarps * 32) attention_small_kernel(const float* __restrict__ qkv, long long ld,
+                                                                             __nv_bfloat16* __restrict__ ctx, long long ld_ctx,
+                                                                             const int* __restrict__ lengths, int T, int heads,
+                                                                             int head_dim, float scale) {
+  extern __shared__ float small_att_smem[];  // [warps][T] scores, then [warps][head_dim] the query
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nh = blockIdx.y;
+  const int n = nh / heads, h = nh - n * heads;
+  const int q_index = blockIdx.x * kSmallAttWarps + warp;
+  if (q_index >= T) return;
+  const int hidden = heads * head_dim;
+  int len = lengths[n];
+  len = len < T ? (len < 0 ? 0 : len) : T;
+  float* scores = small_att_smem + static_cast<long long>(warp) * T;
+  float* query = small_att_smem + static_cast<long long>(kSmallAttWarps) * T + warp * head_dim;
+  const float* base = qkv + static_cast<long long>(n) * T * ld + h * head_dim;
+  for (int j = lane; j < head_dim; j += 32) query[j] = base[static_cast<long long>(q_index) * ld + j] * scale;
+  __syncwarp();
+  float m = -INFINITY;
+  for (int key = lane; key < len; key += 32) {
+    const float* k_row = base + static_cast<long long>(key) * ld + hidden;
+    float dot = 0.f;
+    for (int j = 0; j < head_dim; ++j) dot = fmaf(query[j], k_row[j], dot);
+    scores[key] = dot;
+    m = fmaxf(m, dot);
+  }
+  m = warp_max(m);
+  float total = 0.f;
+  for (int key = lane; key < len; key += 32) {
+    const float e = __expf(scores[key] - m);
+    scores[key] = e;
+    total += e;
+  }
+  total = warp_sum(total);
+  __syncwarp();
+  const float inv = len > 0 ? 1.0f / total : 0.f;
+  __nv_bfloat16* out = ctx + (static_cast<long long>(n) * T + q_index) * ld_ctx + h * head_dim;
+  for (int j = lane; j < head_dim; j += 32) {
+    const float* v_col = base + 2 * hidden + j;
+    float acc = 0.f;
+    for (int key = 0; key < len; ++key) acc = fmaf(scores[key], v_col[static_cast<long long>(key) * ld], acc);
+    out[j] = __float2bfloat16(acc * inv);
+  }
+}
+
 }  // namespace aph
 
 using namespace aph;
@@ -361,6 +417,26 @@ extern "C" int aph_conv_input_backward(const float* d_cols, const int32_t* lengt
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   dim3 grid(blocks_for(static_cast<long long>(length) * channels), static_cast<unsigned>(n_utt));
   conv_input_backward_kernel<<<grid, 256, 0, stream>>>(d_cols, lengths, n_utt, length, channels, out_len, kernel, stride, left, right, reflect, d_x, ld_dx);
+  APH_POST_LAUNCH(1);
+  return APH_OK;
+}
+
+extern "C" int aph_attention_small(const float* qkv, int64_t ld, void* ctx_bf16, int64_t ld_ctx, const int32_t* lengths, int32_t n_utt,
+                                   int32_t heads, int32_t T, int32_t head_dim, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  APH_REQUIRE(qkv && ctx_bf16 && lengths, "null pointer");
+  APH_REQUIRE(n_utt > 0 && heads > 0 && T > 0 && head_dim > 0, "empty problem");
+  APH_REQUIRE(ld >= 3LL * heads * head_dim && ld_ctx >= static_cast<int64_t>(heads) * head_dim, "leading dimensions too small");
+  const size_t smem = sizeof(float) * (static_cast<size_t>(kSmallAttWarps) * T + static_cast<size_t>(kSmallAttWarps) * head_dim);
+  APH_REQUIRE(smem <= 200 * 1024, "sequence too long for the shared-memory staged scores");
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    APH_CUDA_CHECK(cudaFuncSetAttribute(attention_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    smem_set = 200 * 1024;
+  }
+  const dim3 grid(ceil_div(T, kSmallAttWarps), static_cast<unsigned>(n_utt) * heads);
+  attention_small_kernel<<<grid, kSmallAttWarps * 32, smem, stream>>>(qkv, ld, static_cast<__nv_bfloat16*>(ctx_bf16), ld_ctx, lengths, T, heads,
+                                                                      head_dim, 1.0f / sqrtf(static_cast<float>(head_dim)));
   APH_POST_LAUNCH(1);
   return APH_OK;
 }

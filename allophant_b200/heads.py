@@ -153,6 +153,11 @@ class HeadsRuntime:
             bias = torch.zeros(layout.n_pad, device=device, dtype=torch.float32)
             for spec in layout.specs:
                 linear = projection._layers[spec.name]._time_distributed_layer
+                if not isinstance(linear, torch.nn.Linear):
+                    # time layer (ProjectingMultiheadAttention): its input projection is the Linear of the level GEMM, the
+                    # attention behind it runs on the level's columns afterwards (_run_time_layer)
+                    self._pack_time_layer(spec.name, linear, device)
+                    linear = linear.input_projection
                 if not linear.weight.is_cuda:
                     raise RuntimeError("allophant_b200 runs on CUDA only: move the model to a GPU (`model.to('cuda')`)")
                 row = layout.offsets[spec.name]
@@ -171,6 +176,55 @@ class HeadsRuntime:
             self.level_b.append(bias)
         self._composed_cache.clear()
         self._weights_version = version
+
+    # ------------------------------------------------------------------ time layers (acoustic_model.py:237-268)
+    def _pack_time_layer(self, name: str, layer: Any, device: torch.device) -> None:
+        """bf16 operands of nn.MultiheadAttention's in_proj / out_proj, zero-padded to the GEMM's granularity (8)."""
+        hidden = layer.hidden_dimensions
+        h_pad, qkv_pad = _round_up(hidden, 8), _round_up(3 * hidden, 8)
+        attention = layer.attention
+        in_w = torch.zeros(qkv_pad, h_pad, device=device, dtype=torch.float32)
+        in_w[: 3 * hidden, :hidden] = attention.in_proj_weight.detach().float()
+        in_b = torch.zeros(qkv_pad, device=device, dtype=torch.float32)
+        in_b[: 3 * hidden] = attention.in_proj_bias.detach().float()
+        out_w = torch.zeros(h_pad, h_pad, device=device, dtype=torch.float32)
+        out_w[:hidden, :hidden] = attention.out_proj.weight.detach().float()
+        out_b = torch.zeros(h_pad, device=device, dtype=torch.float32)
+        out_b[:hidden] = attention.out_proj.bias.detach().float()
+        if not hasattr(self, "_time_layers"):
+            self._time_layers: Dict[str, Dict[str, Any]] = {}
+        self._time_layers[name] = dict(
+            hidden=hidden, h_pad=h_pad, qkv_pad=qkv_pad, heads=layer.num_heads, in_w=ops.cast_bf16(in_w), in_b=in_b, out_w=ops.cast_bf16(out_w), out_b=out_b,
+            gamma=layer.layer_norm.weight.detach().float().contiguous(), beta=layer.layer_norm.bias.detach().float().contiguous(),
+            eps=layer.layer_norm.eps, bases=None if layer.positional_embeddings is None else layer.positional_embeddings._bases.to(device),
+        )  # fmt: skip
+
+    def _run_time_layer(self, name: str, plan, logits: Tensor, ld: int, offset: int, logits_bf16: Optional[Tensor]) -> None:
+        """``logits[:, offset : offset + hidden]`` holds the input projection of head ``name``; on return it holds
+        ``MultiheadAttention(LayerNorm(projection) (+ positions))`` over the frames of every utterance (eval(): no dropout)."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.model._projection._layers[name].parameters()):
+            raise NotImplementedError("training through a multi-head-attention time layer is not built (inference only)")
+        t = self._time_layers[name]
+        rows, n_utt, seq, hidden, h_pad = plan.rows, plan.n_utt, plan.seq, t["hidden"], t["h_pad"]
+        device = logits.device
+        projected = logits[:, offset:]
+        normalised = torch.zeros(rows, h_pad, device=device, dtype=torch.float32) if t["bases"] is not None else None
+        operand = torch.zeros(rows, h_pad, device=device, dtype=torch.bfloat16)
+        if t["bases"] is None:
+            ops.layernorm_any(projected, ld, rows, hidden, t["gamma"], t["beta"], t["eps"], out_bf16=operand, ld_bf16=h_pad)
+        else:
+            ops.layernorm_any(projected, ld, rows, hidden, t["gamma"], t["beta"], t["eps"], out_f32=normalised, ld_f32=h_pad)
+            ops.add_sinusoidal(normalised, h_pad, n_utt, seq, hidden, t["bases"])
+            ops.cast_bf16_2d(normalised, h_pad, operand, h_pad, rows, h_pad)
+        qkv = torch.empty(rows, t["qkv_pad"], device=device, dtype=torch.float32)
+        ops.run_gemm(ops.make_gemm_args(operand, t["in_w"], a_rows=rows, a_inner=h_pad, a_row_stride=h_pad, bias=t["in_b"], out_f32=qkv, ld_f32=t["qkv_pad"]))
+        context = torch.zeros(rows, h_pad, device=device, dtype=torch.bfloat16)
+        ops.attention_small(qkv, t["qkv_pad"], context, h_pad, plan.frames32, n_utt, t["heads"], seq, hidden // t["heads"])
+        attended = torch.empty(rows, h_pad, device=device, dtype=torch.float32)
+        ops.run_gemm(ops.make_gemm_args(context, t["out_w"], a_rows=rows, a_inner=h_pad, a_row_stride=h_pad, bias=t["out_b"], out_f32=attended, ld_f32=h_pad))
+        projected[:, :hidden].copy_(attended[:, :hidden])
+        if logits_bf16 is not None:
+            logits_bf16[:, offset : offset + hidden].copy_(attended[:, :hidden])
 
     def _composed_embeddings(self, name: str, target_feature_indices: Optional[Tensor], device: torch.device) -> Tuple[Tensor, int]:
         """bf16 [Vpad, E] table of blank + composed phoneme embeddings and the number of classes V+1."""
@@ -246,6 +300,10 @@ class HeadsRuntime:
             for spec in layout.specs:
                 classifier = projection._layers[spec.name]
                 offset = layout.offsets[spec.name]
+                if classifier._lengths_required:  # time layer: attention over the frames on this head's columns
+                    if keep is not None:
+                        raise NotImplementedError("training through a multi-head-attention time layer is not built (inference only)")
+                    self._run_time_layer(spec.name, plan, logits, layout.n_pad, offset, logits_bf16)
                 if classifier._composition_layer is not None:
                     table, classes = self._composed_embeddings(spec.name, target_feature_indices, device)
                     embedding = classifier._composition_layer.embedding_size

@@ -107,10 +107,30 @@ class EmbeddingCompositionLayer(_ParamHolder):
         self.embedding_size = embedding_size
 
 
+class ProjectingMultiheadAttention(_ParamHolder):
+    """Time layer of a classifier head (``acoustic_model.py:237-268``): ``Linear -> LayerNorm (-> + sinusoidal positions) ->
+    nn.MultiheadAttention over the frames of each utterance (key-padding mask from the frame counts) -> Dropout``.  The module
+    owns the reference's parameters under the reference's names; ``HeadsRuntime`` evaluates it (level GEMM for the input
+    projection, ``aph_layernorm_any``, in_proj / out_proj as tcgen05 GEMMs, ``aph_attention_small`` for the heads).  Inference
+    only: a training step through a time layer raises."""
+
+    def __init__(self, input_dimensions: int, hidden_dimensions: int, num_heads: int, add_positional_embeddings: bool = False, dropout_rate: float = 0) -> None:
+        super().__init__()
+        if hidden_dimensions % num_heads != 0:
+            raise ValueError("embed_dim must be divisible by num_heads")  # nn.MultiheadAttention's own check
+        self.input_projection = nn.Linear(input_dimensions, hidden_dimensions)
+        self.positional_embeddings = SinusoidalPositionEmbeddings(hidden_dimensions) if add_positional_embeddings else None
+        self.layer_norm = nn.LayerNorm(hidden_dimensions)
+        self.attention = nn.MultiheadAttention(hidden_dimensions, num_heads)
+        self.dropout = nn.Dropout(dropout_rate)
+        self.num_heads = num_heads
+        self.hidden_dimensions = hidden_dimensions
+
+
 class HierarchicalClassifier(_ParamHolder):
     def __init__(
         self,
-        time_distributed_layer: nn.Linear,
+        time_distributed_layer: "nn.Linear | ProjectingMultiheadAttention",
         composition_layer: Optional[EmbeddingCompositionLayer] = None,
         allophone_layer: Optional[AllophoneMapping] = None,
     ) -> None:
@@ -203,10 +223,15 @@ class HierarchicalProjection(nn.Module):
                 projection_output_size = output_size
 
             if node.time_layer_config is not None:
-                raise NotImplementedError(
-                    "multi-head-attention time layers (ProjectingMultiheadAttention) are outside this build's hot path"
+                time_distributed_layer = ProjectingMultiheadAttention(
+                    layer_input_neurons,
+                    projection_output_size,
+                    node.time_layer_config.num_heads,
+                    node.time_layer_config.positional_embeddings,
+                    acoustic_model_dropout_rate,
                 )
-            time_distributed_layer = nn.Linear(layer_input_neurons, projection_output_size)
+            else:
+                time_distributed_layer = nn.Linear(layer_input_neurons, projection_output_size)
 
             if is_phoneme_layer and embedding_composition_config is not None:
                 if attribute_indexer is None:

@@ -716,6 +716,13 @@ def activation_backward(d: Tensor, ld_d: int, y: Tensor, ld_y: int, rows: int, c
     check(lib.aph_activation_backward(d.data_ptr(), ld_d, y.data_ptr(), ld_y, rows, cols, kind, _ptr(out_bf16), ld_bf16, _stream()), "aph_activation_backward")
 
 
+def attention_small(qkv: Tensor, ld: int, ctx: Tensor, ld_ctx: int, lengths: Tensor, n_utt: int, heads: int, seq: int, head_dim: int) -> None:
+    """Self-attention over time for the time layer of a classifier head (any head_dim): ``qkv`` fp32 ``[n_utt*seq, ld]`` holds
+    q | k | v, ``ctx`` bf16 ``[n_utt*seq, ld_ctx]`` receives the per-head outputs; keys at or beyond ``lengths[n]`` are masked."""
+    _require_cuda(qkv, ctx, lengths)
+    check(lib.aph_attention_small(qkv.data_ptr(), ld, ctx.data_ptr(), ld_ctx, lengths.data_ptr(), n_utt, heads, seq, head_dim, _stream()), "aph_attention_small")
+
+
 def add_sinusoidal(x: Tensor, ld: int, n_utt: int, seq: int, cols: int, bases: Tensor) -> None:
     _require_cuda(x, bases)
     check(lib.aph_add_sinusoidal(x.data_ptr(), ld, n_utt, seq, cols, bases.data_ptr(), _stream()), "aph_add_sinusoidal")

@@ -508,6 +508,13 @@ int aph_activation_backward(float* d, int64_t ld_d, const float* y, int64_t ld_y
 /* SinusoidalPositionEmbeddings.forward (acoustic_model.py:58-69): x[n][t][c] += sin|cos(t * bases[c]). */
 int aph_add_sinusoidal(float* x, int64_t ld, int32_t n_utt, int32_t seq, int32_t cols, const float* bases,
                        void* stream);
+
+/* Time layer of a classifier head: nn.MultiheadAttention over the frames of an utterance on the head's projected classes
+ * (ProjectingMultiheadAttention, acoustic_model.py:237-268, used at 406-413) with the key-padding mask of the frame counts.
+ * qkv fp32 [n_utt*T][ld] = in_proj output (q | k | v, `heads * head_dim` columns each); ctx bf16 [n_utt*T][ld_ctx] receives the
+ * heads' outputs, the operand of out_proj.  Any head_dim (CUDA cores; the encoder's tcgen05 attention needs 64). */
+int aph_attention_small(const float* qkv, int64_t ld, void* ctx_bf16, int64_t ld_ctx, const int32_t* lengths, int32_t n_utt,
+                        int32_t heads, int32_t T, int32_t head_dim, void* stream);
 /* features [N][F][L] fp32 -> channels-last [N][L][ld_out] fp32 (the permute of acoustic_model.py:672). */
 int aph_transpose_nfl(const float* in, int32_t n_utt, int32_t features, int32_t length, float* out,
                       int64_t ld_out, void* stream);
