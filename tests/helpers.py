@@ -53,7 +53,8 @@ def batch_for_case(fixture: Dict[str, Any]) -> Tuple[torch.Tensor, torch.Tensor,
 
 
 def cuda_model_for_spec(
-    spec: restatement.OracleSpec, oracle: Any, device: str = "cuda", acoustic_config: Any = None, feature_size: int = 1, state_dict: Any = None
+    spec: restatement.OracleSpec, oracle: Any, device: str = "cuda", acoustic_config: Any = None, feature_size: int = 1, state_dict: Any = None,
+    time_layers: Any = None, extra_dependencies: Any = None,
 ):
     """Builds allophant_b200's Allophant with the architecture of ``spec`` and loads the oracle's weights (or ``state_dict``);
     ``acoustic_config`` replaces the wav2vec2 encoder (the from-scratch transformer cases)."""
@@ -88,8 +89,17 @@ def cuda_model_for_spec(
             shared, [f"p{i}" for i in range(phoneme_class.size)], features, features + ["phoneme"], mappings, AllophoneData(shared)
         )
         phoneme_layer = PhonemeLayerType.ALLOPHONES
+    from allophant_b200.config import MultiheadAttentionConfig
+
+    def time_layer(name):
+        options = (time_layers or {}).get(name)
+        return None if options is None else MultiheadAttentionConfig(options["num_heads"], options["positional_embeddings"])
+
+    def dependencies_of(c):
+        return list(c.dependencies) + list((extra_dependencies or {}).get(c.name, []))
+
     projection = ProjectionConfig(
-        [ProjectionEntryConfig(c.name, list(c.dependencies)) for c in spec.classes],
+        [ProjectionEntryConfig(c.name, dependencies_of(c), time_layer(c.name)) for c in spec.classes],
         phoneme_layer=phoneme_layer,
         acoustic_model_dropout=0.2,
         dependency_blanks=spec.dependency_blanks,
@@ -104,7 +114,7 @@ def cuda_model_for_spec(
     architecture = Architecture(
         16_000_000, projection, Wav2Vec2PretrainedConfig(model_id) if acoustic_config is None else acoustic_config, loss=CTCLossConfig()
     )
-    graph = AttributeGraph(AttributeNode(c.name, c.size, None, list(c.dependencies)) for c in spec.classes)
+    graph = AttributeGraph(AttributeNode(c.name, c.size, time_layer(c.name), dependencies_of(c)) for c in spec.classes)
     model = Allophant.from_config(architecture, feature_size, 16000, graph, indexer, load_pretrained_weights=False)
     result = model.load_state_dict(oracle.state_dict() if state_dict is None else state_dict, strict=True)
     assert not result.missing_keys and not result.unexpected_keys

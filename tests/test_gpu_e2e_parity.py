@@ -311,6 +311,43 @@ def test_wav2vec2_base_shape_matches_oracle():
         assert error < RANGE_TOL, f"{name}: {error:.3e} of range"
 
 
+def test_time_layer_heads_match_the_reference():
+    """Classifier heads with a multi-head-attention time layer (``ProjectingMultiheadAttention``, acoustic_model.py:237-268):
+    ``Linear -> LayerNorm (-> + positions) -> MultiheadAttention over the frames (key-padding mask) `` on three attribute heads — two
+    heads of two channels with sinusoidal positions, one head of four, four heads of one — and a phoneme head that depends on
+    them.  Log-probabilities of all 37 heads against the UNMODIFIED reference (``oracle/make_golden_time_layers.py``)."""
+    from allophant_b200.dataset_processing import Batch
+
+    fixture = helpers.load_golden("time_layers_2layer")
+    spec = restatement.multitask_spec(**fixture["spec"])
+    oracle = restatement.OracleModel(spec)  # the encoder's seeded weights (the reference builds the encoder first)
+    state = {key: value for key, value in oracle.state_dict().items() if not key.startswith("_projection.")}
+    state.update(fixture["projection_state"])
+    model, _ = helpers.cuda_model_for_spec(
+        spec, oracle, state_dict=state, time_layers=fixture["time_layers"], extra_dependencies={"phoneme": list(fixture["time_layers"])}
+    )
+    lengths = fixture["lengths"]
+    audio = restatement.synthetic_audio(len(lengths), int(lengths.max()), seed=0) * restatement.mask_sequence(lengths)
+    batch = Batch(audio.cuda(), lengths.cuda(), torch.zeros(len(lengths), dtype=torch.long).cuda())
+    with torch.inference_mode():
+        predictions = model.predict_log_probabilities(batch)
+    assert torch.equal(predictions.lengths.cpu(), fixture["frames"])
+    assert list(predictions.outputs) == fixture["head_order"]
+    frames = fixture["frames"].tolist()
+    for name, reference in fixture["log_probs"].items():
+        ours = predictions.outputs[name].float().cpu()
+        assert ours.shape == reference.shape, name
+        error = _range_error(ours, reference, frames)
+        assert error < RANGE_TOL, f"{name}: {error:.3e} of range"
+    # a training step through a time layer is not built: it must say so instead of returning a wrong gradient
+    model.train()
+    try:
+        with pytest.raises(NotImplementedError, match="time layer"):
+            model(batch)
+    finally:
+        model.eval()
+
+
 def test_length_buckets_are_invisible_and_share_one_arena():
     from allophant_b200.dataset_processing import Batch
     from allophant_b200.estimator import Estimator
