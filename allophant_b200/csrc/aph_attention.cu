@@ -8,7 +8,7 @@
 // (one exp2 per score on the MUFU pipe, 16/clk/SM, and one TMEM read per score), so the design
 // keeps the four softmax warps of a CTA busy all the time:
 //   warps 0..3  softmax: one query row per thread; the 64 scores of a block are read from TMEM once
-//               and stay in registers (max, exp2, row sum, bf16 pack -> 128B-swizzled smem)
+//               and stay in registers (max, exp2, row sum, bf16 pack -> TMEM)
 //   warp 4      TMA producer: Q once, then K_j and V_j [64 keys x 64] through two independent 3-stage
 //               rings (a K tile is released as soon as its scores are issued); V stays row-major and is
 //               read by O += P V as an MN-major B operand, so no transposed copy of V exists anywhere
@@ -19,7 +19,9 @@
 //     (O += P_j V_j); it is rescaled only when a row's maximum grows by more than 2^8 (lazy rescaling:
 //     P is then expressed relative to a slightly stale maximum, which the final division by the row
 //     sum cancels exactly), so nobody waits for the PV product on the common path;
-//   * P is double-buffered in shared memory (the PV product of block j reads P_j while P_{j+1} is written).
+//   * P never touches shared memory: the softmax warps write it (bf16 pairs, tcgen05.st) into the first 32 columns of S_j's own
+//     TMEM buffer and O += P V reads it from there as the A operand (the TS form of tcgen05.mma): 32 KB less shared-memory
+//     traffic per block and no proxy fence; S_{j+2}, the next writer of that buffer, is issued behind PV_j by the same thread.
 // Keys >= lengths[b] get probability exactly 0; key blocks past the utterance's last valid frame and
 // query tiles that are entirely padding are skipped.
 #include "aph_common.cuh"
@@ -33,9 +35,7 @@ constexpr int kAttD = 64;     // head dim
 constexpr int kAttStages = 3;
 constexpr int kAttQBytes = kAttQ * kAttD * 2;    // 16 KB
 constexpr int kAttKVBytes = kAttKV * kAttD * 2;  // 8 KB
-constexpr int kAttPBytes = kAttQ * kAttKV * 2;   // 16 KB
-constexpr int kAttSmemBytes = kAttQBytes + kAttStages * kAttKVBytes /*K*/ + kAttStages * kAttKVBytes /*Vt*/ +
-                              2 * kAttPBytes + 256 /*barriers*/;
+constexpr int kAttSmemBytes = kAttQBytes + kAttStages * kAttKVBytes /*K*/ + kAttStages * kAttKVBytes /*V*/ + 256 /*barriers*/;
 constexpr uint32_t kAttTmemCols = 256;  // S0: [0,64)  S1: [64,128)  O: [128,192)
 constexpr float kAttRescaleThreshold = 8.0f;  // log2 units
 
@@ -84,8 +84,7 @@ __global__ void __launch_bounds__(kAttThreads, 2)
   uint8_t* s_q = smem;
   uint8_t* s_k = s_q + kAttQBytes;                 // kAttStages tiles
   uint8_t* s_v = s_k + kAttStages * kAttKVBytes;   // kAttStages tiles
-  uint8_t* s_p = s_v + kAttStages * kAttKVBytes;   // 2 tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 2 * kAttPBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_v + kAttStages * kAttKVBytes);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;    // [3]
   uint64_t* k_empty = bars + 4;   // [3]
@@ -199,12 +198,12 @@ __global__ void __launch_bounds__(kAttThreads, 2)
         mbar_wait(&p_full[j & 1], static_cast<uint32_t>(j >> 1) & 1u);  // P_j in smem, S_j read, O rescaled if needed
         mbar_wait(&v_full[st], static_cast<uint32_t>(j / kAttStages) & 1u);
         tc_fence_after();
-        const uint64_t dp = umma_desc_sw128(smem_u32(s_p + (j & 1) * kAttPBytes));
+        const uint32_t tmem_p = tmem_base + static_cast<uint32_t>((j & 1) * 64);  // P_j sits in the first columns of S_j's buffer
         const uint64_t dv = umma_desc_mn_sw128(smem_u32(s_v + st * kAttKVBytes), kAttKVBytes);
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // 16 keys per UMMA_K step: +32 bytes along P's rows, +16 rows (2 KB) of V
-            umma_bf16(tmem_o, dp + static_cast<uint64_t>(2 * k), dv + static_cast<uint64_t>(128 * k), idesc_pv, (j | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)  // 16 keys per UMMA_K step: +8 TMEM columns of P (two bf16 each), +16 rows (2 KB) of V
+            umma_bf16_ts(tmem_o, tmem_p + static_cast<uint32_t>(8 * k), dv + static_cast<uint64_t>(128 * k), idesc_pv, (j | k) != 0 ? 1u : 0u);
           umma_commit(&o_full[j & 1]);
           umma_commit(&v_empty[st]);
         }
@@ -221,8 +220,6 @@ __global__ void __launch_bounds__(kAttThreads, 2)
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
     float m_ref = -INFINITY;  // reference maximum of the probabilities currently accumulated in O (log2 domain)
     float l_run = 0.f;
-    uint8_t* p_row0 = s_p + (r >> 3) * 1024 + (r & 7) * 128;
-    const int sw = r & 7;
 
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[j & 1], static_cast<uint32_t>(j >> 1) & 1u);
@@ -298,24 +295,20 @@ __global__ void __launch_bounds__(kAttThreads, 2)
           vb[2 * i + 1] = drop_keep(hb, 1, p.drop_threshold) ? vb[2 * i + 1] : 0.f;
         }
       }
-      // P buffer j & 1 was last read by the PV product of block j - 2, which completed before S_j did (see the issuer)
-      uint8_t* p_row = p_row0 + (j & 1) * kAttPBytes;
+      // P_j goes into the first 32 columns of S_j's own TMEM buffer (two bf16 per column: the A operand layout of the TS form).
+      // Every thread of the warp has read its S row by now, and S_{j+2} — the next writer of this buffer — is issued after
+      // PV_j by the same thread, so the tensor core reads P_j before anything overwrites it.
+      {
+        uint32_t packed[32];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint4 o4;
-        o4.x = pack_bf16x2(va[8 * i + 0], va[8 * i + 1]);
-        o4.y = pack_bf16x2(va[8 * i + 2], va[8 * i + 3]);
-        o4.z = pack_bf16x2(va[8 * i + 4], va[8 * i + 5]);
-        o4.w = pack_bf16x2(va[8 * i + 6], va[8 * i + 7]);
-        *reinterpret_cast<uint4*>(p_row + ((i ^ sw) << 4)) = o4;
-        o4.x = pack_bf16x2(vb[8 * i + 0], vb[8 * i + 1]);
-        o4.y = pack_bf16x2(vb[8 * i + 2], vb[8 * i + 3]);
-        o4.z = pack_bf16x2(vb[8 * i + 4], vb[8 * i + 5]);
-        o4.w = pack_bf16x2(vb[8 * i + 6], vb[8 * i + 7]);
-        *reinterpret_cast<uint4*>(p_row + (((4 + i) ^ sw) << 4)) = o4;
+        for (int i = 0; i < 16; ++i) {
+          packed[i] = pack_bf16x2(va[2 * i], va[2 * i + 1]);
+          packed[16 + i] = pack_bf16x2(vb[2 * i], vb[2 * i + 1]);
+        }
+        tmem_st32(tmem_s, reinterpret_cast<const float*>(packed));
+        tmem_st_wait();
       }
-      fence_proxy_async_smem();  // P visible to the tensor core's smem reads
-      tc_fence_before();         // our TMEM reads of S (and writes of O) are ordered before the next MMAs
+      tc_fence_before();         // our TMEM accesses (S read, P / O written) are ordered before the next MMAs
       mbar_arrive(&p_full[j & 1]);
     }
 
