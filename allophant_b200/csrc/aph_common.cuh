@@ -62,6 +62,7 @@ int sm_count();
 // launched this way MUST call `pdl_wait()` before its first global-memory access; kernels call `pdl_trigger()` at their top
 // so that their own successor can start early.  APH_PDL=0 in the environment turns the attribute off (plain stream order).
 bool pdl_enabled();
+bool tail_split_enabled();  // aph_gemm.cu: the tiles of a partly filled last wave are computed as two half-width items
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {

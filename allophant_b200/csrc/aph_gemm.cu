@@ -103,6 +103,10 @@ struct GemmParams {
   float ln_inv_cols;        // 1 / (number of columns the statistics run over)
   float ln_eps;
   int taps_span;            // TAPS: input channels one N tile contracts over per tap (64, or a block-diagonal super group)
+  // ---- tail split: the tiles of the last, partly filled wave are computed as two 256 x BN/2 halves (see decode_work)
+  int total_work;           // work items of the launch (tiles x split_k, or full-wave tiles + 2 x tail tiles)
+  int tail_first;           // first work item of the tail (== total_work: no tail split)
+  uint32_t idesc_narrow;    // instruction descriptor of the half-width UMMA (N = BN / 2)
 };
 
 // Work item -> (n block, m pair, output batch, k-block range, B row shift)
@@ -113,10 +117,30 @@ struct WorkItem {
   int kb_hi;
   int shift;
   int out_batch;  // DIAG_TAPS: tap index (output batch); otherwise -1
+  int narrow;     // 0: whole tile; 1 + h: column half h of the tile (tail split)
 };
 
+// Tail split.  With T tiles on C cluster slots the last wave holds R = T mod C tiles; when 2 R <= C each of them becomes
+// TWO work items, the left and the right 256 x BN/2 half of the tile (UMMA N = BN/2, half the B rows per stage, two instead of
+// four 32-column chunks per epilogue warp).  Every output element still accumulates the same k-blocks in the same order, so
+// the result is bit-identical to the unsplit kernel; a half costs ~0.6 of a mainloop (A is read by both) and half an epilogue.
+// out-proj / FFN2 of the 32 x 10 s batch have 252-256 tiles on 74 slots (3.4 waves -> 4), the 4.9 k x 1024 GEMMs of a
+// training step 80 (1.08 waves -> 2).
 __device__ __forceinline__ WorkItem decode_work(const GemmParams& p, int work, int m_pairs) {
   WorkItem w;
+  w.narrow = 0;
+  if (work >= p.tail_first) {
+    const int j = work - p.tail_first;
+    const int tile = p.tail_first + (j >> 1);
+    w.n_blk = tile % p.n_tiles;
+    w.m_pair = tile / p.n_tiles;
+    w.kb_lo = 0;
+    w.kb_hi = p.k_blocks;
+    w.shift = p.b_k_shift;
+    w.out_batch = -1;
+    w.narrow = 1 + (j & 1);
+    return w;
+  }
   if (p.diag_taps > 0) {
     const int tap = work / m_pairs;
     w.m_pair = work - tap * m_pairs;
@@ -169,7 +193,8 @@ template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                      const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_resid,
-                     const __grid_constant__ CUtensorMap tm_copy, const GemmParams p) {
+                     const __grid_constant__ CUtensorMap tm_copy, const __grid_constant__ CUtensorMap tm_b_narrow,
+                     const GemmParams p) {
   using Cfg = GemmCfg<BN, EPI>;
   constexpr int kStages = Cfg::kStages;
 
@@ -202,6 +227,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     }
     if (EPI == kEpiStoreResidTma || EPI == kEpiStoreResidStats) tma_prefetch_desc(&tm_resid);
     if (EPI == kEpiStoreResidStats) tma_prefetch_desc(&tm_copy);
+    if (p.tail_first < p.total_work && !p.b_mn) tma_prefetch_desc(&tm_b_narrow);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 2);   // leader's copy is the one in use: one arrive.expect_tx per CTA of the pair
       mbar_init(&empty_bar[s], 1);  // released in both CTAs by the leader's tcgen05.commit multicast
@@ -226,7 +252,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
   const int n_clusters = gridDim.x >> 1;
   const int tiles_m = p.m_tiles_per_batch * p.batch;
   const int m_pairs = (tiles_m + 1) >> 1;
-  const int total_work = p.diag_taps > 0 ? m_pairs * p.diag_taps : m_pairs * p.n_tiles * p.split_k;
+  const int total_work = p.total_work;
 
   if (warp == 8) {
     // ===================== TMA producer =====================
@@ -249,10 +275,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           uint8_t* sb = sa + Cfg::kABytes;
           if (elect_one()) {
           // both CTAs' bytes are accounted on the LEADER's full barrier (the leader issues the pair's MMA)
+          const uint32_t stage_bytes = w.narrow != 0 ? Cfg::kABytes + Cfg::kBBytes / 2 : Cfg::kStageBytes;
           if (cta_rank == 0) {
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
           } else {
-            mbar_arrive_expect_tx_remote(&full_bar[stage], 0, Cfg::kStageBytes);
+            mbar_arrive_expect_tx_remote(&full_bar[stage], 0, stage_bytes);
           }
           int seg = 0, r0 = kb * kBK;
           if (p.a_mn | p.b_mn) {
@@ -272,7 +299,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           } else {
             tma_load_3d_pair(sa, &tm_a, &full_bar[stage], kb * kBK, t0, b);
           }
-          if (p.b_mn) {
+          if (w.narrow != 0) {  // column half of a tail tile: this CTA feeds BN/4 of its BN/2 B rows
+            const int n0 = n_blk * BN + (w.narrow - 1) * (BN / 2) + cta_rank * (BN / 4);
+            if (p.b_mn) {
+#pragma unroll
+              for (int c = 0; c < (BN / 4) / 64; ++c)
+                tma_load_3d_pair(sb + c * (64 * kBK * 2), &tm_b, &full_bar[stage], n0 + 64 * c, r0 + w.shift, seg);
+            } else {
+              tma_load_2d_pair(sb, &tm_b_narrow, &full_bar[stage], kb * kBK, n0);
+            }
+          } else if (p.b_mn) {
             const int n0 = n_blk * BN + cta_rank * (BN / 2);
 #pragma unroll
             for (int c = 0; c < (BN / 2) / 64; ++c)
@@ -306,6 +342,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+        const uint32_t item_idesc = w.narrow != 0 ? p.idesc_narrow : idesc;
         for (int kb = w.kb_lo; kb < w.kb_hi; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -315,7 +352,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           if (elect_one()) {  // the same lane every time: tcgen05.commit tracks the MMAs of the thread that issues it
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) {
-              umma_bf16_pair(tmem_d, da + static_cast<uint64_t>(k) * a_step, db + static_cast<uint64_t>(k) * b_step, idesc,
+              umma_bf16_pair(tmem_d, da + static_cast<uint64_t>(k) * a_step, db + static_cast<uint64_t>(k) * b_step, item_idesc,
                              (kb != w.kb_lo || k != 0) ? 1u : 0u);
             }
             umma_commit_pair(&empty_bar[stage], static_cast<uint16_t>(3));  // frees the stage in both CTAs
@@ -429,16 +466,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
         ln_rstd = rsqrtf(var + p.ln_eps);
         ln_nmr = -mean * ln_rstd;
       }
-      if (resid_tma && col_base + half * (BN / 2) < p.n && lane == 0) {  // first chunk: requested before the accumulator is ready
+      // columns this warp finishes: its half of the tile, or — tail split — its half of the item's column half, which sits in
+      // the first BN/2 accumulator columns
+      int c_begin = half * (BN / 2), c_end = c_begin + BN / 2, tmem_shift = 0;
+      if (w.narrow != 0) {
+        tmem_shift = (w.narrow - 1) * (BN / 2);
+        c_begin = tmem_shift + half * (BN / 4);
+        c_end = c_begin + BN / 4;
+      }
+      if (resid_tma && col_base + c_begin < p.n && lane == 0) {  // first chunk: requested before the accumulator is ready
         mbar_arrive_expect_tx(&resid_bar[warp], 4096);
-        tma_load_3d(resid_buf, &tm_resid, &resid_bar[warp], col_base + half * (BN / 2), t_tile_row0, b);
+        tma_load_3d(resid_buf, &tm_resid, &resid_bar[warp], col_base + c_begin, t_tile_row0, b);
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr0 =
-          tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+          tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN - tmem_shift);
 #pragma unroll 1
-      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         const int col = col_base + c0;
         if (col >= p.n) break;  // warp-uniform
         float v[32];
@@ -626,7 +671,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
             fence_proxy_async_smem();
             __syncwarp();
             const int c0_next = c0 + 32;
-            if (c0_next < (half + 1) * (BN / 2) && col_base + c0_next < p.n && lane == 0) {
+            if (c0_next < c_end && col_base + c0_next < p.n && lane == 0) {
               mbar_arrive_expect_tx(&resid_bar[warp], 4096);
               tma_load_3d(resid_buf, &tm_resid, &resid_bar[warp], col_base + c0_next, t_tile_row0, b);
             }
@@ -724,7 +769,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
               store_pending = true;
               if (EPI == kEpiStoreResidStats) {
                 const int part = (c0 >> 5) & 1;
-                const bool last_chunk = c0 + 32 >= (half + 1) * (BN / 2) || col + 32 >= p.n;
+                const bool last_chunk = c0 + 32 >= c_end || col + 32 >= p.n;
                 if ((part == 1 || last_chunk) && lane == 0) tma_store_3d(&tm_copy, copy_buf, col - 32 * part, t_row0, b);
               }
             } else {
@@ -743,7 +788,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
                 o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
                 *reinterpret_cast<uint4*>(stage_row + (((4 * part + j) ^ sw) << 4)) = o;
               }
-              const bool last_chunk = c0 + 32 >= (half + 1) * (BN / 2) || col + 32 >= p.n;
+              const bool last_chunk = c0 + 32 >= c_end || col + 32 >= p.n;
               if (part == 1 || last_chunk) {
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -908,9 +953,32 @@ static int launch_gemm(const aph_gemm_args* a, GemmParams& p, cudaStream_t strea
       }
     }
   }
-  const int total_work = p.diag_taps > 0 ? m_pairs * p.diag_taps : m_pairs * p.n_tiles * p.split_k;
+  int total_work = p.diag_taps > 0 ? m_pairs * p.diag_taps : m_pairs * p.n_tiles * p.split_k;
+  p.tail_first = total_work;
+  // tail split (decode_work): the R tiles of a partly filled last wave are computed as 2 R half-width items
+  CUtensorMap tm_b_narrow;
+  memset(&tm_b_narrow, 0, sizeof(tm_b_narrow));
+  if (BN == 256 && (EPI == APH_EPI_STORE || EPI == kEpiStoreResidTma || EPI == APH_EPI_QKV) && p.split_k == 1 && p.diag_taps == 0 && !p.a_mn &&
+      p.mode == APH_GEMM_ROWS && p.n % 128 == 0 && tail_split_enabled()) {
+    const int full = (total_work / max_clusters) * max_clusters;
+    const int rest = total_work - full;
+    if (rest > 0 && 2 * rest <= max_clusters) {
+      if (!a->b_mn_major) {  // a K-major B is fetched as [BN/4 rows][64] boxes by the half-width items
+        const uint64_t row_stride = static_cast<uint64_t>(a->b_row_stride > 0 ? a->b_row_stride : a->k) * 2;
+        const uint64_t dims[2] = {static_cast<uint64_t>(a->k), static_cast<uint64_t>(a->n)};
+        const uint64_t strides[1] = {row_stride};
+        const uint32_t box[2] = {kBK, static_cast<uint32_t>(BN / 4)};
+        int rc = encode_tmap(&tm_b_narrow, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->b, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc != APH_OK) return rc;
+      }
+      p.idesc_narrow = umma_idesc_bf16(2 * kBM, BN / 2) | (p.a_mn ? kIdescAMnMajor : 0u) | (p.b_mn ? kIdescBMnMajor : 0u);
+      p.tail_first = full;
+      total_work = full + 2 * rest;
+    }
+  }
+  p.total_work = total_work;
   const int grid = 2 * (total_work < max_clusters ? total_work : max_clusters);
-  APH_CUDA_CHECK(launch_pdl(gemm_bf16_kernel<BN, EPI>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tm_a, tm_b, tm_out, tm_resid, tm_copy, p));
+  APH_CUDA_CHECK(launch_pdl(gemm_bf16_kernel<BN, EPI>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tm_a, tm_b, tm_out, tm_resid, tm_copy, tm_b_narrow, p));
   APH_POST_LAUNCH(1);
   return APH_OK;
 }

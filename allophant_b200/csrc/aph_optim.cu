@@ -107,14 +107,45 @@ __global__ void __launch_bounds__(kMtBlock) mt_adam_kernel(const __grid_constant
     __nv_bfloat16* sh = static_cast<__nv_bfloat16*>(shadow.p[t][0]);
     const long long base = static_cast<long long>(chunk - pack.chunk_start[t]) * kMtChunk;
     const long long end = min(pack.n[t], base + kMtChunk);
-    for (long long i = base + threadIdx.x; i < end; i += kMtBlock) {
-      const float pi = p[i];
-      float gi = g[i] * coef;
-      gi = fmaf(h.weight_decay, pi, gi);
-      const float mi = fmaf(h.beta1, m[i], (1.f - h.beta1) * gi);
-      const float vi = fmaf(h.beta2, v[i], (1.f - h.beta2) * gi * gi);
+    auto update = [&](float pi, float gi, float& mi, float& vi) -> float {
+      gi = fmaf(h.weight_decay, pi, gi * coef);
+      mi = fmaf(h.beta1, mi, (1.f - h.beta1) * gi);
+      vi = fmaf(h.beta2, vi, (1.f - h.beta2) * gi * gi);
       const float denom = sqrtf(vi) / h.bias_correction2_sqrt + h.eps;
-      const float pn = pi - step_size * (mi / denom);
+      return pi - step_size * (mi / denom);
+    };
+    // chunks start at multiples of 8192 elements: 16-byte accesses whenever the tensors themselves are 16-byte aligned
+    const bool wide = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                        reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(sh) & 7) == 0;
+    long long done = base;
+    if (wide) {
+      const long long quads = (end - base) >> 2;
+      for (long long q = threadIdx.x; q < quads; q += kMtBlock) {
+        const long long i = base + 4 * q;
+        float4 pq = *reinterpret_cast<const float4*>(p + i);
+        const float4 gq = __ldcs(reinterpret_cast<const float4*>(g + i));  // the gradient is not read again
+        float4 mq = *reinterpret_cast<const float4*>(m + i);
+        float4 vq = *reinterpret_cast<const float4*>(v + i);
+        pq.x = update(pq.x, gq.x, mq.x, vq.x);
+        pq.y = update(pq.y, gq.y, mq.y, vq.y);
+        pq.z = update(pq.z, gq.z, mq.z, vq.z);
+        pq.w = update(pq.w, gq.w, mq.w, vq.w);
+        *reinterpret_cast<float4*>(m + i) = mq;
+        *reinterpret_cast<float4*>(v + i) = vq;
+        *reinterpret_cast<float4*>(p + i) = pq;
+        if (sh != nullptr) {
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(pq.x, pq.y), hi = __floats2bfloat162_rn(pq.z, pq.w);
+          uint2 packed;
+          packed.x = *reinterpret_cast<const uint32_t*>(&lo);
+          packed.y = *reinterpret_cast<const uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(sh + i) = packed;
+        }
+      }
+      done = base + 4 * quads;
+    }
+    for (long long i = done + threadIdx.x; i < end; i += kMtBlock) {
+      float mi = m[i], vi = v[i];
+      const float pn = update(p[i], g[i], mi, vi);
       m[i] = mi;
       v[i] = vi;
       p[i] = pn;

@@ -94,9 +94,27 @@ bool pdl_enabled() {
   return v != 0;
 }
 
+// same scheme for the GEMM's tail split (APH_GEMM_TAIL_SPLIT; default on)
+static std::atomic<int> g_tail_split{-1};
+bool tail_split_enabled() {
+  int v = g_tail_split.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("APH_GEMM_TAIL_SPLIT");
+    v = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+    g_tail_split.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
+
 }  // namespace aph
 
 extern "C" {
+
+int aph_set_gemm_tail_split(int enabled) {
+  const int before = aph::tail_split_enabled() ? 1 : 0;
+  aph::g_tail_split.store(enabled ? 1 : 0);
+  return before;
+}
 
 int aph_set_pdl(int enabled) {
   const int before = aph::pdl_enabled() ? 1 : 0;

@@ -73,6 +73,7 @@ class HeadsRuntime:
         self._layout_ready = False
         self._weights_version: Optional[Tuple[int, ...]] = None
         self._composed_cache: Dict[Tuple[Any, ...], Tuple[Tensor, int]] = {}
+        self._checked_inventories: set = set()  # index tensors whose categories were range-checked already
         self._index_cache: Dict[Tuple[Any, ...], Dict[str, Tensor]] = {}
         self.gradient_reducer: Any = None  # allophant_b200.distributed.GradientReducer (data-parallel training)
         self.skip_layers_override: Optional[Sequence[bool]] = None  # explicit LayerDrop decisions for train() mode (tests)
@@ -249,8 +250,16 @@ class HeadsRuntime:
         table = torch.empty(rows, weight.shape[1], device=device, dtype=torch.bfloat16)
         err = torch.zeros(1, device=device, dtype=torch.int32)
         ops.compose_embeddings(weight.detach().float().contiguous(), indices_dev, offsets_dev, rows, err, out_bf16=table)
-        if int(err.item()) != 0:  # one-time check per inventory (EmbeddingBag raises on out-of-range indices too)
-            raise IndexError("target_feature_indices contain a category outside the attribute embedding table")
+        # one-time check per inventory (EmbeddingBag raises on out-of-range indices too).  Only the first composition of an
+        # inventory reads the flag back: while training the table is recomposed after every optimizer step, and a
+        # device-to-host read there would drain the stream once per step
+        checked = key[1:5] + (int(weight.shape[0]),)
+        if checked not in self._checked_inventories:
+            if int(err.item()) != 0:
+                raise IndexError("target_feature_indices contain a category outside the attribute embedding table")
+            if len(self._checked_inventories) >= 64:
+                self._checked_inventories.clear()
+            self._checked_inventories.add(checked)
         if len(self._composed_cache) >= 8:
             self._composed_cache.pop(next(iter(self._composed_cache)))
         self._composed_cache[key] = (table, classes)

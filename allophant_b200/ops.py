@@ -55,6 +55,12 @@ def set_pdl(enabled: bool) -> bool:
     return bool(lib.aph_set_pdl(1 if enabled else 0))
 
 
+def set_gemm_tail_split(enabled: bool) -> bool:
+    """Tail split of the tcgen05 GEMM (see ``aph_set_gemm_tail_split`` in ``include/allophant_b200.h``; on by default,
+    ``APH_GEMM_TAIL_SPLIT=0`` disables it at start-up).  Returns the previous setting."""
+    return bool(lib.aph_set_gemm_tail_split(1 if enabled else 0))
+
+
 # --------------------------------------------------------------------------------------
 # GEMM
 # --------------------------------------------------------------------------------------

@@ -29,7 +29,7 @@ extern "C" {
 #define APH_ERR_CUDA (-2)        /* CUDA runtime / driver error                    */
 #define APH_ERR_UNSUPPORTED (-3) /* valid request outside the implemented envelope */
 
-#define APH_ABI_VERSION 5
+#define APH_ABI_VERSION 6
 
 /* ---- library ------------------------------------------------------------ */
 int aph_abi_version(void);
@@ -42,6 +42,11 @@ void aph_reset_launch_count(void);
  * predecessor in the stream; results are identical).  On by default, APH_PDL=0 in the environment or this call turn it
  * off.  Returns the previous setting.  No reference counterpart: torch launches its kernels in plain stream order. */
 int aph_set_pdl(int enabled);
+/* Tail split of aph_gemm_bf16: when the last wave of 256 x 256 output tiles fills at most half of the cluster slots, each of
+ * its tiles is computed as two 256 x 128 halves on two clusters (results bit-identical to the unsplit kernel: every output
+ * element accumulates the same products in the same order).  On by default, APH_GEMM_TAIL_SPLIT=0 or this call turn it
+ * off; returns the previous setting.  No reference counterpart. */
+int aph_set_gemm_tail_split(int enabled);
 
 /* ---- tensor-core GEMM (tcgen05 + TMEM accumulators, TMA-fed) ------------- */
 /* One kernel serves every dense contraction of the path:

@@ -62,6 +62,63 @@ def test_gemm_residual_mask_and_scale():
     assert range_err(out, reference) < 1e-4
 
 
+@pytest.mark.parametrize(
+    "m,n,k,form",
+    [
+        (1024, 1024, 1024, "residual"),   # 16 tiles on 74 cluster slots: every tile becomes two half-width items
+        (5120, 1024, 1024, "residual"),   # 80 tiles: one full wave + 6 tail tiles (the out-proj of a training step)
+        (4904, 1024, 4096, "residual"),   # ragged last row tile, K = 4096 (FFN2)
+        (16384, 1024, 1024, "residual"),  # 256 tiles: 3 full waves + 34 tail tiles (out-proj of the 32 x 10 s batch)
+        (5120, 4096, 1024, "gelu_bf16"),  # 320 tiles: 4 waves + 24 tail tiles, bf16 output through 64-column stores
+        (4904, 1024, 3072, "dgrad"),      # MN-major B, plain fp32 store
+        (2048, 512, 520, "plain"),        # odd number of k-blocks (9)
+    ],
+)
+def test_gemm_tail_split_matches_the_unsplit_kernel(m, n, k, form):
+    """The tiles of a partly filled last wave are computed as two half-width work items on two clusters: every output
+    element accumulates the same products in the same order, so the result equals the unsplit kernel's bit for bit."""
+    ops = _ops()
+    torch.manual_seed(m + k)
+    a = (torch.randn(m, k, device=DEV) * 0.5).bfloat16()
+    bias = torch.randn(n, device=DEV)
+    resid = torch.randn(m, n, device=DEV)
+
+    def run():
+        if form == "dgrad":
+            w = (torch.randn(k, n, device=DEV) * 0.05).bfloat16()  # stored [out = k][in = n], as the forward pass keeps it
+            out = torch.empty(m, n, device=DEV)
+            ops.run_gemm(ops.make_dgrad_args(a, w, rows=m, ld_dy=k, k=k, n=n, ld_w=n, out_f32=out, ld_f32=n))
+            return out, a.float() @ w.float()
+        w = (torch.randn(n, k, device=DEV) * 0.05).bfloat16()
+        product = a.float() @ w.float().T
+        if form == "residual":
+            out = resid.clone()
+            ops.run_gemm(ops.make_gemm_args(a, w, a_rows=m, a_inner=k, a_row_stride=k, bias=bias, resid=out, ld_resid=n, out_f32=out, ld_f32=n))
+            return out, product + bias + resid
+        if form == "gelu_bf16":
+            out = torch.empty(m, n, device=DEV, dtype=torch.bfloat16)
+            ops.run_gemm(ops.make_gemm_args(a, w, a_rows=m, a_inner=k, a_row_stride=k, bias=bias, gelu=True, out_bf16=out, ld_bf16=n))
+            return out.float(), torch.nn.functional.gelu(product + bias)
+        out = torch.empty(m, n, device=DEV)
+        ops.run_gemm(ops.make_gemm_args(a, w, a_rows=m, a_inner=k, a_row_stride=k, out_f32=out, ld_f32=n))
+        return out, product
+
+    before = ops.set_gemm_tail_split(True)
+    try:
+        torch.manual_seed(7)
+        split, reference = run()
+        torch.manual_seed(7)
+        again, _ = run()
+        ops.set_gemm_tail_split(False)
+        torch.manual_seed(7)
+        whole, _ = run()
+    finally:
+        ops.set_gemm_tail_split(before)
+    assert torch.equal(split, again)
+    assert torch.equal(split, whole)
+    assert range_err(split, reference) < (1e-2 if form == "gelu_bf16" else 1e-4)
+
+
 @pytest.mark.parametrize("m,period,lengths", [(998, 499, [300, 499]), (130, 130, [130]), (1537, 1537, [1500])])
 def test_gemm_folded_layernorm_pair(m, period, lengths):
     """LayerNorm folded into the GEMMs around it (HF:730-756, inference launch list): the producer (out-proj form: bias +

@@ -37,7 +37,10 @@ for name in model.classes:
             head_labels[row, :length] = torch.randint(1, classes, (length,), generator=generator)
     labels[name], label_lengths[name] = head_labels.to(device), head_lengths.to(device)
 batch = Batch(audio.to(device), lengths.to(device), languages.to(device))
-parameters = [p for p in model.parameters() if p.requires_grad]
+parameters = list(model.parameters())
+from allophant_b200 import optim
+
+optimizer = optim.adam_from_config(parameters, model.d_model, model=model)
 
 
 def step(timers=None):
@@ -54,17 +57,20 @@ def step(timers=None):
     t2 = time.perf_counter()
     loss.backward()
     t3 = time.perf_counter()
+    optimizer.step(clip_norm=1.0)
+    t4 = time.perf_counter()
     if timers is not None:
         timers["forward"] += t1 - t0
         timers["loss"] += t2 - t1
         timers["backward"] += t3 - t2
+        timers["optimizer"] += t4 - t3
     return loss
 
 
 for _ in range(3):
     step()
 torch.cuda.synchronize()
-timers = {"forward": 0.0, "loss": 0.0, "backward": 0.0}
+timers = {"forward": 0.0, "loss": 0.0, "backward": 0.0, "optimizer": 0.0}
 start = time.perf_counter()
 for _ in range(5):
     step(timers)
