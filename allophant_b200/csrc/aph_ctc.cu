@@ -56,6 +56,66 @@ __device__ __forceinline__ float lse3(float a, float b, float c) {
   return m + lg2a(1.0f + ex2a(mid - mf) + ex2a(lo - mf));
 }
 
+// One frame of the recursion for the K states of a lane:  out[i] = lse(cur[i], n1[i], n2[i] for odd i) + e[i]  (blank states,
+// even i, have no skip transition; K is even, so the parity of i is the parity of the state).  The K evaluations are
+// independent, but written one after the other the compiler also SCHEDULES them one after the other — max, subtract,
+// ex2, add, lg2, add form a ~90-cycle dependent chain, K of them in series were ~900 cycles per frame on a warp that is
+// alone on its scheduler (profiles/r02_ctc_recursion.md).  Here the work is laid out stage by stage over groups of up to 8
+// states and the MUFU instructions are `asm volatile`, which keeps them in this order: a group's exponentials issue back to
+// back, then its logarithms.
+__device__ __forceinline__ float ex2v(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2v(float x) {
+  float y;
+  asm volatile("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <int K>
+__device__ __forceinline__ void lse_frame(const float (&cur)[K], const float (&n1)[K], const float (&n2)[K], const float (&e)[K],
+                                          float (&out)[K]) {
+  constexpr int G = 8;
+#pragma unroll
+  for (int g0 = 0; g0 < K; g0 += G) {
+    float m[G], d1[G], d2[G], x1[G], x2[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const int i = g0 + j;
+      if (i < K) {
+        const float hi = fmaxf(cur[i], n1[i]), lo = fminf(cur[i], n1[i]);
+        if (i & 1) {
+          m[j] = fmaxf(hi, n2[i]);
+          const float mid = fminf(hi, n2[i]);
+          const float mf = fmaxf(m[j], -1e30f);
+          d1[j] = mid - mf;
+          d2[j] = lo - mf;
+        } else {
+          m[j] = hi;
+          d1[j] = lo - fmaxf(hi, -1e30f);
+          d2[j] = 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < G; ++j)
+      if (g0 + j < K) x1[j] = ex2v(d1[j]);
+#pragma unroll
+    for (int j = 1; j < G; j += 2)
+      if (g0 + j < K) x2[j] = ex2v(d2[j]);
+#pragma unroll
+    for (int j = 0; j < G; ++j)
+      if (g0 + j < K) x1[j] = (j & 1) ? (1.0f + x1[j]) + x2[j] : 1.0f + x1[j];
+#pragma unroll
+    for (int j = 0; j < G; ++j)
+      if (g0 + j < K) x1[j] = lg2v(x1[j]);
+#pragma unroll
+    for (int j = 0; j < G; ++j)
+      if (g0 + j < K) out[g0 + j] = (m[j] + x1[j]) + e[g0 + j];
+  }
+}
+
 // The per-head descriptors travel BY VALUE in the kernel parameters (<= 4 KB): no device copy of the array, hence
 // no synchronous pageable-memory transfer between the forward pass and the loss.
 constexpr int kCtcMaxHeads = 48;
@@ -110,7 +170,7 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_alpha_kernel(const __grid_
   load_pair(heads, h, n, n_utt, T, input_lengths, alpha_ws, p);
   const int S2 = 2 * p.S + 1;
   float* out = nll_out + static_cast<long long>(h) * n_utt + n;
-  if (S2 > 32 * K || p.S > heads.h[h].label_stride) {  // host guarantees this never happens
+  if (S2 > 32 * K || p.S > heads.h[h].label_stride || (p.alpha != nullptr && p.s_pad != 32 * K)) {  // host guarantees this never happens
     if (lane == 0) *out = NAN;
     return;
   }
@@ -188,25 +248,23 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_alpha_kernel(const __grid_
         }
       } else {
         const float left1 = __shfl_up_sync(0xffffffffu, a[K - 1], 1);
-        const float left2 = __shfl_up_sync(0xffffffffu, a[K - 2], 1);
-        float prev1 = lane == 0 ? -INFINITY : left1;
-        float prev2 = lane == 0 ? -INFINITY : left2;
+        const float prev1 = lane == 0 ? -INFINITY : left1;  // state lane*K - 1: the only neighbour outside this lane's states
+        float n1[K], n2[K], v[K];
 #pragma unroll
         for (int i = 0; i < K; ++i) {
-          const float cur = a[i];
-          // blank states (even s; K is even, so the parity of i is the parity of s) have no skip transition
-          const float v = ((i & 1) ? lse3(cur, prev1, skip[i] ? prev2 : -INFINITY) : lse2(cur, prev1)) + e[i];
-          prev2 = prev1;
-          prev1 = cur;
-          a[i] = (lane * K + i) < S2 ? v : -INFINITY;
+          n1[i] = i == 0 ? prev1 : a[i - 1];
+          // blank states (even s) have no skip transition
+          n2[i] = ((i & 1) && skip[i]) ? (i == 1 ? prev1 : a[i - 2]) : -INFINITY;
         }
+        lse_frame<K>(a, n1, n2, e, v);
+#pragma unroll
+        for (int i = 0; i < K; ++i) a[i] = (lane * K + i) < S2 ? v[i] : -INFINITY;
       }
       if (p.alpha) {
-        float* dst = p.alpha + static_cast<long long>(t) * p.s_pad + lane * K;
-        if (lane * K < p.s_pad) {
+        // state lane*K + i is kept at column i*32 + lane of the row: each of the K stores covers 128 contiguous bytes
+        float* dst = p.alpha + static_cast<long long>(t) * p.s_pad + lane;
 #pragma unroll
-          for (int i = 0; i < K; ++i) dst[i] = a[i];
-        }
+        for (int i = 0; i < K; ++i) dst[i * 32] = a[i];
       }
     }
   }
@@ -252,7 +310,7 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_beta_kernel(const __grid_c
   const float nll2 = nll * kLog2E;  // the recursions (and the alpha workspace) are in the log2 domain
   const float g = grad_scale ? grad_scale[h] : 1.f;
   const bool small_c = p.c <= kCtcSmallC;
-  const bool dead = !(nll < INFINITY) || S2 > 32 * K;  // inf / nan loss -> zero gradient
+  const bool dead = !(nll < INFINITY) || S2 > 32 * K || p.s_pad != 32 * K;  // inf / nan loss -> zero gradient
   // frames past the utterance's length (and every frame of a zeroed loss) get zero gradient
   if (small_c) {
     const int t_zero_from = dead ? 0 : p.T_in;
@@ -281,10 +339,10 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_beta_kernel(const __grid_c
   float al_next[K], e_next[K];
 #pragma unroll
   for (int i = 0; i < K; ++i) al_next[i] = e_next[i] = 0.f;
-  if (lane * K < p.s_pad) {
-    const float* nrow = p.alpha + static_cast<long long>(p.T_in - 1) * p.s_pad + lane * K;
+  {  // column i*32 + lane of an alpha row holds state lane*K + i (see the alpha kernel)
+    const float* nrow = p.alpha + static_cast<long long>(p.T_in - 1) * p.s_pad + lane;
 #pragma unroll
-    for (int i = 0; i < K; ++i) al_next[i] = nrow[i];
+    for (int i = 0; i < K; ++i) al_next[i] = nrow[i * 32];
   }
   if (!small_c) {
     const float* row = p.lp + static_cast<long long>(p.T_in - 1) * p.stride_t;
@@ -317,10 +375,10 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_beta_kernel(const __grid_c
       // alpha row of this frame was requested one iteration ago; request the one of frame t-1 now
 #pragma unroll
       for (int i = 0; i < K; ++i) al[i] = al_next[i];
-      if (t > 0 && lane * K < p.s_pad) {
-        const float* nrow = p.alpha + static_cast<long long>(t - 1) * p.s_pad + lane * K;
+      if (t > 0) {
+        const float* nrow = p.alpha + static_cast<long long>(t - 1) * p.s_pad + lane;
 #pragma unroll
-        for (int i = 0; i < K; ++i) al_next[i] = nrow[i];
+        for (int i = 0; i < K; ++i) al_next[i] = nrow[i * 32];
       }
       if (small_c) {
 #pragma unroll
@@ -344,16 +402,18 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_beta_kernel(const __grid_c
       } else {
         const float right1 = __shfl_down_sync(0xffffffffu, b[0], 1);
         const float right2 = __shfl_down_sync(0xffffffffu, b[1], 1);
-        float next1 = lane == 31 ? -INFINITY : right1;
-        float next2 = lane == 31 ? -INFINITY : right2;
+        const float next1 = lane == 31 ? -INFINITY : right1;  // states (lane+1)*K and (lane+1)*K + 1
+        const float next2 = lane == 31 ? -INFINITY : right2;
+        float n1[K], n2[K], v[K];
 #pragma unroll
-        for (int i = K - 1; i >= 0; --i) {
-          const float cur = b[i];
-          const float v = ((i & 1) ? lse3(cur, next1, skip[i] ? next2 : -INFINITY) : lse2(cur, next1)) + e[i];
-          next2 = next1;
-          next1 = cur;
-          b[i] = (lane * K + i) < S2 ? v : -INFINITY;
+        for (int i = 0; i < K; ++i) {
+          n1[i] = i == K - 1 ? next1 : b[i + 1];
+          n2[i] = ((i & 1) && skip[i]) ? (i == K - 1 ? next2 : b[i + 2]) : -INFINITY;  // odd i <= K - 3, or the last state of the lane
         }
+        lse_frame<K>(b, n1, n2, e, v);
+        // states past 2S+1 stay at -inf by themselves: probability flows from s+1, s+2 to s, never out of the valid range
+#pragma unroll
+        for (int i = 0; i < K; ++i) b[i] = v[i];
       }
       // occupation probabilities gamma_t(s)
       float gam[K];
@@ -362,7 +422,7 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_beta_kernel(const __grid_c
       for (int i = 0; i < K; ++i) {
         const int s = lane * K + i;
         float gm = 0.f;
-        if (s < S2) gm = ex2a(al[i] + b[i] - e[i] + nll2);  // ex2.approx.ftz: tiny occupancies flush to 0
+        if (s < S2) gm = ex2v(al[i] + b[i] - e[i] + nll2);  // ex2.approx.ftz: tiny occupancies flush to 0
         gam[i] = gm;
         if (!(s & 1)) blank_sum += gm;
       }
