@@ -11,6 +11,7 @@ KEYS = {
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed": "tensor_pct",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_pct",
     "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_pct",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active": "xu_pct",
     "sm__warps_active.avg.pct_of_peak_sustained_active": "occupancy_pct",
     "launch__registers_per_thread": "regs",
     "sm__cycles_elapsed.avg.per_second": "sm_ghz",
