@@ -492,6 +492,15 @@ class EncoderPlan:
             self.dqkv = z(M, 3 * H)
             self.delta = z(n_utt * heads * self.seq, dtype=f32)
             self.d_fp_in = z(M, 512, dtype=f32)
+            # Weight / bias gradients leave the critical path of the backward pass: they run on a second stream, one layer behind
+            # at most, and fill the SMs the data-gradient GEMMs leave idle in their last waves (80 tiles on 74 cluster slots at
+            # M = 4.9 k).  What they read is therefore double-buffered by layer parity.  APH_BWD_OVERLAP=0 keeps one stream.
+            self.bwd_overlap = os.environ.get("APH_BWD_OVERLAP", "1") != "0" and cfg.do_stable_layer_norm
+            if self.bwd_overlap:
+                self.dh16_ring = [self.dh_bf16, z(M, H), z(M, H), z(M, H)]  # [parity][feed-forward branch, attention branch]
+                self.d_ff_ring = [self.d_ff, z(M, FF)]
+                self.dqkv_ring = [self.dqkv, z(M, 3 * H)]
+                self._side_stream: Optional[torch.cuda.Stream] = None
             if not cfg.do_stable_layer_norm:
                 # post-LN ordering: hidden state i is the (normalised) input of layer i; per layer the pre-LayerNorm sums are kept
                 self.hs16 = [z(M, H) for _ in range(n_layers)]
@@ -1028,12 +1037,13 @@ class EncoderPlan:
         dh, dh16 = self.dh, self.dh_bf16
         st = self.stoch  # train()-mode regularisation of the forward pass this backward pass belongs to
 
-        def branch_gradient(drop: ops.Dropout) -> bool:
-            """dh16 <- bf16(dh o keep * scale): gradient of a residual branch behind the forward's epilogue dropout."""
+        def branch_gradient(drop: ops.Dropout, target: Optional[Tensor] = None) -> bool:
+            """target (dh16) <- bf16(dh o keep * scale): gradient of a residual branch behind the forward's epilogue dropout."""
+            target = dh16 if target is None else target
             if drop.threshold:
-                ops.dropout_2d(dh, H, M, H, drop, out_bf16=dh16, ld_bf16=H)
+                ops.dropout_2d(dh, H, M, H, drop, out_bf16=target, ld_bf16=H)
                 return True
-            ops.cast_bf16_2d(dh, H, dh16, H, M, H)
+            ops.cast_bf16_2d(dh, H, target, H, M, H)
             return False
 
         def group(shapes: Sequence[Tuple[str, Tuple[int, ...]]]) -> Tuple[Tensor, Dict[str, Tensor]]:
@@ -1065,6 +1075,24 @@ class EncoderPlan:
             if need_encoder:
                 done(flat, g, "encoder.layer_norm.")
 
+        # ---- the layers, last to first.  With `bwd_overlap` the weight and bias gradients of a layer are enqueued on a second
+        # stream behind two events of the main stream (d_ff ready; dqkv ready) and handed out (`done`) one layer later, when
+        # the main stream has waited for them — which is also what allows it to overwrite the buffers they read.
+        overlap = bool(getattr(self, "bwd_overlap", False)) and need_encoder and not post_ln
+        side: Optional[torch.cuda.Stream] = None
+        if overlap:
+            if self._side_stream is None or self._side_stream.device != dev:
+                self._side_stream = torch.cuda.Stream(device=dev)
+            side = self._side_stream
+        main = torch.cuda.current_stream(dev) if overlap else None
+        pending: List[Tuple[Any, Tensor, Dict[str, Tensor], str]] = []  # (side-stream event, flat, views, prefix) of layers not handed out yet
+
+        def hand_out(keep: int) -> None:
+            while len(pending) > keep:
+                event, flat_done, views_done, prefix_done = pending.pop(0)
+                main.wait_event(event)
+                done(flat_done, views_done, prefix_done)
+
         for index in (() if post_ln else reversed(range(n_layers))):
             lw, sv = p.layers[index], self.saved[index]
             if need_encoder:
@@ -1090,44 +1118,80 @@ class EncoderPlan:
                     for part, name in enumerate(("q_proj", "k_proj", "v_proj")):
                         g[f"attention.{name}.weight"] = wqkv[part * H : (part + 1) * H]
                         g[f"attention.{name}.bias"] = bqkv[part * H : (part + 1) * H]
-                    done(flat, g, f"encoder.layers.{index}.")
+                    if overlap:  # keep the hand-out order (the all-reduce of a data-parallel caller is issued per group, in this order)
+                        event = torch.cuda.Event()
+                        event.record(main)
+                        pending.append((event, flat, g, f"encoder.layers.{index}."))
+                    else:
+                        done(flat, g, f"encoder.layers.{index}.")
                 continue
+            parity = index & 1
+            dh16_ff = self.dh16_ring[2 * parity] if overlap else dh16
+            dh16_att = self.dh16_ring[2 * parity + 1] if overlap else dh16
+            d_ff = self.d_ff_ring[parity] if overlap else self.d_ff
+            dqkv = self.dqkv_ring[parity] if overlap else self.dqkv
+            if overlap:
+                hand_out(1)  # the layer of the same parity (two back) has been waited for: its operand buffers are free again
             # ---- feed forward: h_out = h_mid + dropout(W2 gelu(W1 LN2(h_mid) + b1) + b2)
-            dropped = branch_gradient(st.feed_forward_output(index) if st else ops.NO_DROPOUT)
-            args = ops.make_dgrad_args(dh16, lw["w2"], rows=M, ld_dy=H, k=H, n=FF, ld_w=FF, gelu_bwd=sv["pre"], ld_gelu_bwd=FF,
-                                       out_bf16=self.d_ff, ld_bf16=FF)  # fmt: skip
+            dropped_ff = branch_gradient(st.feed_forward_output(index) if st else ops.NO_DROPOUT, dh16_ff)
+            if need_encoder and not dropped_ff:  # (reads the fp32 stream the LayerNorm backward below rewrites: stays on this stream)
+                ops.colsum_f32(dh, M, H, H, out=g["feed_forward.output_dense.bias"])
+            args = ops.make_dgrad_args(dh16_ff, lw["w2"], rows=M, ld_dy=H, k=H, n=FF, ld_w=FF, gelu_bwd=sv["pre"], ld_gelu_bwd=FF,
+                                       out_bf16=d_ff, ld_bf16=FF)  # fmt: skip
             inner = st.activation(index) if st else ops.NO_DROPOUT  # the mask of the dropout behind the activation
             args.drop_threshold, args.drop_seed, args.drop_scale = inner.threshold, inner.seed, inner.scale
             ops.run_gemm(args)
+
+            def feed_forward_parameters() -> None:
+                wgrad(g["feed_forward.output_dense.weight"], dh16_ff, H, H, sv["act"], FF, FF)
+                if dropped_ff:
+                    ops.colsum_bf16(dh16_ff, M, H, H, out=g["feed_forward.output_dense.bias"])
+                wgrad(g["feed_forward.intermediate_dense.weight"], d_ff, FF, FF, sv["ln2"], H, H)
+                ops.colsum_bf16(d_ff, M, FF, FF, out=g["feed_forward.intermediate_dense.bias"])
+
             if need_encoder:
-                wgrad(g["feed_forward.output_dense.weight"], dh16, H, H, sv["act"], FF, FF)
-                if dropped:
-                    ops.colsum_bf16(dh16, M, H, H, out=g["feed_forward.output_dense.bias"])
+                if overlap:
+                    ready = torch.cuda.Event()
+                    ready.record(main)
+                    with torch.cuda.stream(side):
+                        side.wait_event(ready)
+                        feed_forward_parameters()
                 else:
-                    ops.colsum_f32(dh, M, H, H, out=g["feed_forward.output_dense.bias"])
-                wgrad(g["feed_forward.intermediate_dense.weight"], self.d_ff, FF, FF, sv["ln2"], H, H)
-                ops.colsum_bf16(self.d_ff, M, FF, FF, out=g["feed_forward.intermediate_dense.bias"])
-            ops.run_gemm(ops.make_dgrad_args(self.d_ff, lw["w1"], rows=M, ld_dy=FF, k=FF, n=H, ld_w=H, out_f32=self.d_ln, ld_f32=H))
+                    feed_forward_parameters()
+            ops.run_gemm(ops.make_dgrad_args(d_ff, lw["w1"], rows=M, ld_dy=FF, k=FF, n=H, ld_w=H, out_f32=self.d_ln, ld_f32=H))
             g2, _ = lw["ln2"]
             ops.layernorm_backward(self.mids[index], H, self.d_ln, H, M, H, g2, eps, dh, H, dh, H,
                                    g.get("final_layer_norm.weight"), g.get("final_layer_norm.bias"))  # fmt: skip
             # ---- attention block: h_mid = h_in + dropout(Wo attention(Wqkv LN1(h_in)) + bo)
-            dropped = branch_gradient(st.attention_output(index) if st else ops.NO_DROPOUT)
-            ops.run_gemm(ops.make_dgrad_args(dh16, lw["wo"], rows=M, ld_dy=H, k=H, n=H, ld_w=H, out_bf16=self.d_ctx, ld_bf16=H))
-            if need_encoder:
-                wgrad(g["attention.out_proj.weight"], dh16, H, H, sv["ctx"], H, H)
-                if dropped:
-                    ops.colsum_bf16(dh16, M, H, H, out=g["attention.out_proj.bias"])
-                else:
-                    ops.colsum_f32(dh, M, H, H, out=g["attention.out_proj.bias"])
+            dropped_att = branch_gradient(st.attention_output(index) if st else ops.NO_DROPOUT, dh16_att)
+            if need_encoder and not dropped_att:
+                ops.colsum_f32(dh, M, H, H, out=g["attention.out_proj.bias"])
+            ops.run_gemm(ops.make_dgrad_args(dh16_att, lw["wo"], rows=M, ld_dy=H, k=H, n=H, ld_w=H, out_bf16=self.d_ctx, ld_bf16=H))
             ops.attention_backward(
-                sv["q"], sv["k"], sv["v"], sv["ctx"], self.d_ctx, sv["lse"], self.delta, self.dqkv, self.att_lengths, N, heads, seq,
+                sv["q"], sv["k"], sv["v"], sv["ctx"], self.d_ctx, sv["lse"], self.delta, dqkv, self.att_lengths, N, heads, seq,
                 st.attention(index) if st else ops.NO_DROPOUT,
             )  # fmt: skip
+
+            def attention_parameters() -> None:
+                wgrad(g["attention.out_proj.weight"], dh16_att, H, H, sv["ctx"], H, H)
+                if dropped_att:
+                    ops.colsum_bf16(dh16_att, M, H, H, out=g["attention.out_proj.bias"])
+                wgrad(g["attention.qkv.weight"], dqkv, 3 * H, 3 * H, sv["ln1"], H, H)
+                ops.colsum_bf16(dqkv, M, 3 * H, 3 * H, out=g["attention.qkv.bias"])
+
+            finished = None
             if need_encoder:
-                wgrad(g["attention.qkv.weight"], self.dqkv, 3 * H, 3 * H, sv["ln1"], H, H)
-                ops.colsum_bf16(self.dqkv, M, 3 * H, 3 * H, out=g["attention.qkv.bias"])
-            ops.run_gemm(ops.make_dgrad_args(self.dqkv, lw["wqkv"], rows=M, ld_dy=3 * H, k=3 * H, n=H, ld_w=H, out_f32=self.d_ln, ld_f32=H))
+                if overlap:
+                    ready = torch.cuda.Event()
+                    ready.record(main)
+                    with torch.cuda.stream(side):
+                        side.wait_event(ready)
+                        attention_parameters()
+                        finished = torch.cuda.Event()
+                        finished.record(side)
+                else:
+                    attention_parameters()
+            ops.run_gemm(ops.make_dgrad_args(dqkv, lw["wqkv"], rows=M, ld_dy=3 * H, k=3 * H, n=H, ld_w=H, out_f32=self.d_ln, ld_f32=H))
             g1, _ = lw["ln1"]
             ops.layernorm_backward(self.hs[index], H, self.d_ln, H, M, H, g1, eps, dh, H, dh, H, g.get("layer_norm.weight"), g.get("layer_norm.bias"))
             if need_encoder:
@@ -1136,7 +1200,13 @@ class EncoderPlan:
                 for name, weight_part, bias_part in zip(("q_proj", "k_proj", "v_proj"), wqkv.split(H), bqkv.split(H)):
                     g[f"attention.{name}.weight"] = weight_part
                     g[f"attention.{name}.bias"] = bias_part
-                done(flat, g, f"encoder.layers.{index}.")
+                if overlap:
+                    # the LayerNorm gradients of this group are written by the main stream: the hand-out also follows this point
+                    pending.append((finished, flat, g, f"encoder.layers.{index}."))
+                else:
+                    done(flat, g, f"encoder.layers.{index}.")
+        if overlap:
+            hand_out(0)
 
         column = self.hidden_blocks.get(0)
         if column is not None and n_layers > 0:
