@@ -32,6 +32,18 @@ from .network.wav2vec2 import Wav2Vec2EncoderConfig, Wav2Vec2Weights
 _WEIGHT_GENERATION = 0
 
 
+_BACKWARD_OVERLAP = True
+
+
+def set_backward_overlap(enabled: bool) -> bool:
+    """Process-wide switch of the second stream of ``EncoderPlan.backward`` (weight / bias gradients off the data-gradient
+    path; on by default, ``APH_BWD_OVERLAP=0`` disables it when a plan is built).  Returns the previous setting.  Measurement
+    code turns it off to time kernels one at a time: records of overlapping kernels include the time they share the SMs."""
+    global _BACKWARD_OVERLAP
+    before, _BACKWARD_OVERLAP = _BACKWARD_OVERLAP, bool(enabled)
+    return before
+
+
 def bump_weight_generation() -> None:
     global _WEIGHT_GENERATION
     _WEIGHT_GENERATION += 1
@@ -1078,7 +1090,7 @@ class EncoderPlan:
         # ---- the layers, last to first.  With `bwd_overlap` the weight and bias gradients of a layer are enqueued on a second
         # stream behind two events of the main stream (d_ff ready; dqkv ready) and handed out (`done`) one layer later, when
         # the main stream has waited for them — which is also what allows it to overwrite the buffers they read.
-        overlap = bool(getattr(self, "bwd_overlap", False)) and need_encoder and not post_ln
+        overlap = bool(getattr(self, "bwd_overlap", False)) and _BACKWARD_OVERLAP and need_encoder and not post_ln
         side: Optional[torch.cuda.Stream] = None
         if overlap:
             if self._side_stream is None or self._side_stream.device != dev:

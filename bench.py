@@ -1008,6 +1008,11 @@ def measure_training(process, steps: int, warmup: int, eval_arithmetic: bool, de
     # ---- roofline of the dominant kernel: every rank runs one more step (it contains collectives), rank 0 times its GEMMs
     roofline = None
     if detail:
+        # kernels are timed one at a time: the weight-gradient stream is off for these two extra steps (records of overlapping
+        # kernels include the time they share the SMs, so their sum would exceed the step)
+        from allophant_b200 import engine as _engine
+
+        overlap_before = _engine.set_backward_overlap(False)
         gemm_events: List[Any] = []
         original = ops.run_gemm
         sizes = (1024, 3072, 4096)
@@ -1065,6 +1070,12 @@ def measure_training(process, steps: int, warmup: int, eval_arithmetic: bool, de
         else:
             device_step()
             torch.cuda.synchronize()
+        _engine.set_backward_overlap(overlap_before)
+        if roofline is not None:
+            roofline["note"] = (
+                "GEMM launches timed with the weight-gradient stream off (APH_BWD_OVERLAP): one kernel at a time; `share_of_step` relates "
+                "their sum to the timed step, which runs with the stream on"
+            )
     attach_gradient_reducer(model, None)
     del optimizer, estimator, model
     torch.cuda.empty_cache()
