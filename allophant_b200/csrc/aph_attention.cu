@@ -271,15 +271,24 @@ __global__ void __launch_bounds__(kAttThreads, 2)
         l_run *= alpha;
         m_ref = m_new;
       }
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+      // score - reference and the row sum as packed fp32 pairs (add.f32x2): half the issue slots of the two most frequent
+      // instructions of this loop next to the exponential itself
+      const float2 neg_ref = f2_splat(-m_ref);
+      float2 lsa = make_float2(0.f, 0.f), lsb = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        va[i] = ex2_approx(va[i] - m_ref);
-        vb[i] = ex2_approx(vb[i] - m_ref);
-        ls[i & 1] += va[i];
-        ls[2 + (i & 1)] += vb[i];
+      for (int i = 0; i < 16; ++i) {
+        const float2 da = f2_add(make_float2(va[2 * i], va[2 * i + 1]), neg_ref);
+        const float2 db = f2_add(make_float2(vb[2 * i], vb[2 * i + 1]), neg_ref);
+        const float2 pa = make_float2(ex2_approx(da.x), ex2_approx(da.y));
+        const float2 pb = make_float2(ex2_approx(db.x), ex2_approx(db.y));
+        va[2 * i] = pa.x;
+        va[2 * i + 1] = pa.y;
+        vb[2 * i] = pb.x;
+        vb[2 * i + 1] = pb.y;
+        lsa = f2_add(lsa, pa);
+        lsb = f2_add(lsb, pb);
       }
-      l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      l_run += (lsa.x + lsa.y) + (lsb.x + lsb.y);
       if constexpr (kDrop) {
         // dropout of the (still unnormalised) probabilities: the row sum above is taken before it, the 1/(1-p) scale is
         // folded into the final normalisation

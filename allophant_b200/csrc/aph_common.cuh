@@ -481,6 +481,13 @@ __device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
   return *reinterpret_cast<float2*>(&rd);
 }
+__device__ __forceinline__ float2 f2_add(float2 a, float2 b) {
+  uint64_t ra, rb, rd;
+  ra = *reinterpret_cast<uint64_t*>(&a);
+  rb = *reinterpret_cast<uint64_t*>(&b);
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
 __device__ __forceinline__ float2 f2_splat(float v) { return make_float2(v, v); }
 __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
