@@ -628,3 +628,31 @@ def test_custom_ops_run_the_library_kernels():
     nll = torch.ops.allophant_b200.ctc_nll(out.detach(), labels, lengths, label_lengths)
     reference = F.ctc_loss(out.detach().cpu(), labels.cpu(), lengths.cpu(), label_lengths.cpu(), reduction="none")
     assert range_err(nll, reference) < 1e-4
+    # CTC loss on the logits, differentiable (CTCWrapper.forward on one head)
+    from allophant_b200.custom_ops import ctc_loss
+
+    logits = x.detach().clone().requires_grad_(True)
+    loss = ctc_loss(logits, labels, lengths, label_lengths)
+    loss.backward()
+    leaf = x.detach().clone().requires_grad_(True)
+    expected = F.ctc_loss(F.log_softmax(leaf, -1), labels, lengths, label_lengths, reduction="sum", zero_infinity=True)
+    expected.backward()
+    assert abs(float(loss) - float(expected)) < 1e-3 * abs(float(expected))
+    assert range_err(logits.grad, leaf.grad) < 1e-4
+    # greedy decode = collapse of the frame-wise argmax
+    tokens, counts, _ = torch.ops.allophant_b200.ctc_greedy_decode(out.detach(), lengths)
+    best = out.detach().argmax(-1).transpose(0, 1).cpu()
+    for row in range(3):
+        frames = best[row, : int(lengths[row])].tolist()
+        collapsed = [c for i, c in enumerate(frames) if c != 0 and (i == 0 or c != frames[i - 1])]
+        assert tokens[row, : int(counts[row])].tolist() == collapsed
+    # attention against SDPA with the key-padding mask
+    heads, seq = 2, 200
+    q, k, v = (torch.randn(3 * heads, seq, 64, device=DEV).bfloat16() for _ in range(3))
+    frame_lengths = torch.tensor([200, 130, 1], device=DEV, dtype=torch.int32)
+    ctx = torch.ops.allophant_b200.attention(q, k, v, frame_lengths, heads)
+    mask = (torch.arange(seq, device=DEV)[None, :] < frame_lengths[:, None])[:, None, None, :]
+    expected_ctx = F.scaled_dot_product_attention(q.float().view(3, heads, seq, 64), k.float().view(3, heads, seq, 64), v.float().view(3, heads, seq, 64), attn_mask=mask)
+    expected_ctx = expected_ctx.transpose(1, 2).reshape(3 * seq, heads * 64)
+    valid = (torch.arange(seq, device=DEV)[None, :] < frame_lengths[:, None]).reshape(-1)
+    assert range_err(ctx.float()[valid], expected_ctx[valid]) < 2e-2

@@ -93,5 +93,12 @@ def test_custom_ops_are_registered_with_fake_kernels():
         assert torch.ops.allophant_b200.linear_bf16(x, torch.empty(16, 40, device="cuda"), None, True).shape == (7, 3, 16)
         assert torch.ops.allophant_b200.ctc_nll(x, torch.empty(3, 5, dtype=torch.long, device="cuda"), torch.empty(3, dtype=torch.long, device="cuda"),
                                                  torch.empty(3, dtype=torch.long, device="cuda")).shape == (3,)  # fmt: skip
+        q = torch.empty(6, 200, 64, device="cuda", dtype=torch.bfloat16)
+        assert torch.ops.allophant_b200.attention(q, q, q, torch.empty(3, dtype=torch.int32, device="cuda"), 2).shape == (600, 128)
+        loss, gradient = torch.ops.allophant_b200.ctc_loss_with_gradient(
+            x, torch.empty(3, 5, dtype=torch.long, device="cuda"), torch.empty(3, dtype=torch.long, device="cuda"), torch.empty(3, dtype=torch.long, device="cuda"))  # fmt: skip
+        assert loss.shape == (1,) and gradient.shape == x.shape
+        tokens, counts, scores = torch.ops.allophant_b200.ctc_greedy_decode(x, torch.empty(3, dtype=torch.int32, device="cuda"))
+        assert tokens.shape == (3, 7) and counts.shape == (3,) and scores.shape == (3,)
     with pytest.raises(NotImplementedError):
         torch.ops.allophant_b200.log_softmax(torch.zeros(2, 3))
