@@ -78,6 +78,60 @@ class FusedAdam(torch.optim.Optimizer):
             return
         self.shadow.update(packed.shadow_map())
         self.post_step_hooks.append(packed.after_fused_step)
+        self.__dict__["_tables"] = {}  # the prefilled tables hold the shadow pointers
+
+    # ---- host side of a step.  The arithmetic is three launches per 48 tensors; what used to cost more than those launches run
+    # (3.7 ms of Python for ~430 parameters, exposed: the GPU has finished the backward pass by then) is rebuilt only when the
+    # set of parameters with a gradient changes: parameter / moment pointers, sizes and bf16 shadows sit in prefilled ctypes
+    # tables, a step writes the gradient pointers into them, and the per-parameter `step` tensors torch.optim.Adam keeps are
+    # brought up to date lazily (`state_dict()`), from one Python counter per table.
+    def _table_for(self, group_index: int, live: List[Tensor]):
+        cache = self.__dict__.setdefault("_tables", {})
+        key = (group_index, tuple(id(p) for p in live))
+        entry = cache.get(group_index)
+        if entry is not None and entry["key"] == key and all(p.data_ptr() == ptr for p, ptr in zip(live[:4], entry["first_ptrs"])):
+            return entry
+        if entry is not None:
+            self._flush_steps()
+        _checked(live)
+        steps = set()
+        for p in live:
+            state = self.state[p]
+            if len(state) == 0:
+                state["step"] = torch.tensor(0.0)  # torch.optim.Adam keeps the step as a (host) tensor
+                state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            steps.add(int(state["step"]))
+        if len(steps) != 1:
+            return None  # parameters at different step counts (a freshly unfrozen layer): the general path below
+        n = len(live)
+        table = (ctypes.c_void_p * (4 * n))()
+        for i, p in enumerate(live):
+            state = self.state[p]
+            table[4 * i + 0] = p.data_ptr()
+            table[4 * i + 2] = state["exp_avg"].data_ptr()
+            table[4 * i + 3] = state["exp_avg_sq"].data_ptr()
+        entry = dict(
+            key=key, first_ptrs=[p.data_ptr() for p in live[:4]], params=live, table=table, grads=(ctypes.c_void_p * n)(), sizes=_sizes(live),
+            shadows=_pointer_table([[self.shadow.get(p)] for p in live]), step=steps.pop(), flushed=True,
+        )  # fmt: skip
+        cache[group_index] = entry
+        return entry
+
+    def _flush_steps(self) -> None:
+        for entry in self.__dict__.get("_tables", {}).values():
+            if entry is not None and not entry["flushed"]:
+                for p in entry["params"]:
+                    self.state[p]["step"].fill_(float(entry["step"]))
+                entry["flushed"] = True
+
+    def state_dict(self):
+        self._flush_steps()
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict) -> None:
+        self.__dict__["_tables"] = {}
+        super().load_state_dict(state_dict)
 
     @torch.no_grad()
     def step(self, closure=None, clip_norm: Optional[float] = None):
@@ -85,23 +139,46 @@ class FusedAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        sumsq = None
-        if clip_norm is not None:
-            grads = [p.grad for group in self.param_groups for p in group["params"] if p.grad is not None]
-            if grads:
-                sumsq = sum_of_squares(_checked(grads))
-        for group in self.param_groups:
-            beta1, beta2 = group["betas"]
+        stream = ops._stream()
+        plans = []
+        for group_index, group in enumerate(self.param_groups):
             live = [p for p in group["params"] if p.grad is not None]
             if not live:
                 continue
-            for p in live:
-                state = self.state[p]
-                if len(state) == 0:
-                    state["step"] = torch.tensor(0.0)  # torch.optim.Adam keeps the step as a (host) tensor
-                    state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                    state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-            # one host call advances every step counter and one reads them back (the loop over ~430 host tensors was 1 ms per step)
+            entry = self._table_for(group_index, live)
+            if entry is not None:
+                table, grad_table = entry["table"], entry["grads"]
+                for i, p in enumerate(live):
+                    g = p.grad
+                    if g.dtype is not torch.float32 or not g.is_cuda or not g.is_contiguous():
+                        raise ValueError("allophant_b200.optim expects contiguous fp32 CUDA gradients")
+                    pointer = g.data_ptr()
+                    table[4 * i + 1] = pointer
+                    grad_table[i] = pointer
+            plans.append((group, live, entry))
+        if not plans:
+            return loss
+        sumsq = None
+        if clip_norm is not None:
+            sumsq = torch.empty(1, device=plans[0][1][0].device, dtype=torch.float64)
+            if all(entry is not None for _, _, entry in plans) and len(plans) == 1:
+                entry = plans[0][2]
+                check(lib.aph_multi_tensor_sumsq(entry["grads"], entry["sizes"], len(entry["params"]), sumsq.data_ptr(), stream), "aph_multi_tensor_sumsq")
+            else:
+                sumsq = sum_of_squares(_checked([p.grad for _, live, _ in plans for p in live]))
+        for group, live, entry in plans:
+            beta1, beta2 = group["betas"]
+            hyper = (float(group["lr"]), float(beta1), float(beta2), float(group["eps"]), float(group["weight_decay"]))
+            clip = (None if sumsq is None else sumsq.data_ptr(), 0.0 if clip_norm is None else float(clip_norm))
+            if entry is not None:
+                entry["step"] += 1
+                entry["flushed"] = False
+                check(
+                    lib.aph_multi_tensor_adam(entry["table"], entry["shadows"], entry["sizes"], len(live), *hyper, entry["step"], *clip, stream),
+                    "aph_multi_tensor_adam",
+                )
+                continue
+            # general path: parameters of one group at different step counts
             counters = [self.state[p]["step"] for p in live]
             torch._foreach_add_(counters, 1.0)
             by_step: Dict[int, List[Tensor]] = {}
@@ -113,11 +190,7 @@ class FusedAdam(torch.optim.Optimizer):
                 rows = [[p, p.grad, self.state[p]["exp_avg"], self.state[p]["exp_avg_sq"]] for p in params]
                 shadows = [self.shadow.get(p) for p in params]
                 check(
-                    lib.aph_multi_tensor_adam(
-                        _pointer_table(rows), _pointer_table([[s] for s in shadows]), _sizes(params), len(params), float(group["lr"]), float(beta1),
-                        float(beta2), float(group["eps"]), float(group["weight_decay"]), step, None if sumsq is None else sumsq.data_ptr(),
-                        0.0 if clip_norm is None else float(clip_norm), ops._stream(),
-                    ),  # fmt: skip
+                    lib.aph_multi_tensor_adam(_pointer_table(rows), _pointer_table([[s] for s in shadows]), _sizes(params), len(params), *hyper, step, *clip, stream),
                     "aph_multi_tensor_adam",
                 )
         engine.bump_weight_generation()  # parameters changed behind torch's version counters: packed operands are stale
