@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_alpha_kernel(const __grid_
   // per-lane state metadata
   int lab[K];
   bool skip[K];
+  bool bad_label = false;
 #pragma unroll
   for (int i = 0; i < K; ++i) {
     const int s = lane * K + i;
@@ -189,19 +190,31 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_alpha_kernel(const __grid_
     if (s < S2 && (s & 1)) {
       l = static_cast<int>(p.labels[s >> 1]);
       if (s >= 3) sk = l != static_cast<int>(p.labels[(s >> 1) - 1]);
+      if (l < 0 || l >= p.c) {  // a label outside the head's classes would index the staged log-probs out of bounds
+        bad_label = true;
+        l = 0;
+      }
     }
     lab[i] = l;
     skip[i] = sk;
+  }
+  if (__any_sync(0xffffffffu, bad_label)) {  // nn.CTCLoss raises on such targets; here the loss (and its gradient) is NaN
+    if (lane == 0) *out = NAN;
+    return;
   }
   const bool small_c = p.c <= kCtcSmallC;
   float* st = stage[warp];
   float a[K];
   float nll = 0.f;
+  bool poisoned = false;
   float e_next[K];
 #pragma unroll
   for (int i = 0; i < K; ++i) e_next[i] = 0.f;
+  // fmaxf / fminf treat a NaN as missing data, so a NaN frame (diverged logits: the whole log_softmax row is NaN) would be washed
+  // out of the recursion from state 0 onwards: what is read from the log-probabilities is checked where it is loaded
   if (!small_c) {
     const float eb = __ldg(p.lp);
+    poisoned = poisoned || (eb != eb);
 #pragma unroll
     for (int i = 0; i < K; ++i) e_next[i] = (((lane * K + i) & 1) ? __ldg(p.lp + lab[i]) : eb) * kLog2E;
   }
@@ -213,11 +226,17 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_alpha_kernel(const __grid_
       const int total = nt * p.c;
       if (p.stride_t == p.c) {
         const float* src = p.lp + static_cast<long long>(t0) * p.stride_t;
-        for (int i = lane; i < total; i += 32) st[i] = __ldg(src + i) * kLog2E;
+        for (int i = lane; i < total; i += 32) {
+          const float x = __ldg(src + i) * kLog2E;
+          poisoned = poisoned || (x != x);
+          st[i] = x;
+        }
       } else {
         for (int i = lane; i < total; i += 32) {
           const int tt = i / p.c, k = i - tt * p.c;
-          st[i] = __ldg(p.lp + static_cast<long long>(t0 + tt) * p.stride_t + k) * kLog2E;
+          const float x = __ldg(p.lp + static_cast<long long>(t0 + tt) * p.stride_t + k) * kLog2E;
+          poisoned = poisoned || (x != x);
+          st[i] = x;
         }
       }
       __syncwarp();
@@ -236,6 +255,7 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_alpha_kernel(const __grid_
         if (t + 1 < p.T_in) {
           const float* row = p.lp + static_cast<long long>(t + 1) * p.stride_t;
           const float eb = __ldg(row);
+          poisoned = poisoned || (eb != eb);
 #pragma unroll
           for (int i = 0; i < K; ++i) e_next[i] = (((lane * K + i) & 1) ? __ldg(row + lab[i]) : eb) * kLog2E;
         }
@@ -276,9 +296,11 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_alpha_kernel(const __grid_
     if (s == S2 - 1) last1 = a[i];
     if (s == S2 - 2) last2 = a[i];
   }
-  last1 = warp_max(last1);
-  last2 = warp_max(last2);
-  nll = -lse2(last1, last2) * kLn2;  // back to natural units
+  // fetched from the lanes that own the two states (a maximum over the warp would drop a NaN: fmaxf(-inf, NaN) = -inf, and the
+  // diverged loss would come out as +inf and be zeroed)
+  last1 = __shfl_sync(0xffffffffu, last1, (S2 - 1) / K);
+  last2 = S2 >= 2 ? __shfl_sync(0xffffffffu, last2, (S2 - 2) / K) : -INFINITY;
+  nll = (__any_sync(0xffffffffu, poisoned) || last1 != last1 || last2 != last2) ? NAN : -lse2(last1, last2) * kLn2;  // natural units
   if (lane == 0) *out = nll;
 }
 
@@ -310,12 +332,15 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_beta_kernel(const __grid_c
   const float nll2 = nll * kLog2E;  // the recursions (and the alpha workspace) are in the log2 domain
   const float g = grad_scale ? grad_scale[h] : 1.f;
   const bool small_c = p.c <= kCtcSmallC;
-  const bool dead = !(nll < INFINITY) || S2 > 32 * K || p.s_pad != 32 * K;  // inf / nan loss -> zero gradient
+  // zero_infinity zeroes the gradient of an INFINITE loss only; a NaN loss (diverged logits, a label outside the classes)
+  // poisons the gradient of its valid frames, as it does in torch
+  const bool poisoned = nll != nll;
+  const bool dead = nll == INFINITY || poisoned || S2 > 32 * K || p.s_pad != 32 * K;
   // frames past the utterance's length (and every frame of a zeroed loss) get zero gradient
   if (small_c) {
     const int t_zero_from = dead ? 0 : p.T_in;
     for (int t = t_zero_from; t < T; ++t)
-      for (int k = lane; k < p.c; k += 32) p.grad[static_cast<long long>(t) * p.stride_t + k] = 0.f;
+      for (int k = lane; k < p.c; k += 32) p.grad[static_cast<long long>(t) * p.stride_t + k] = (poisoned && t < p.T_in) ? NAN : 0.f;
   }
   if (dead || p.T_in == 0) return;
 
@@ -484,14 +509,16 @@ __global__ void __launch_bounds__(256) ctc_grad_init_kernel(const aph_ctc_head h
   const float nll = nll_in[static_cast<long long>(h) * n_utt + n];
   const float g = grad_scale ? grad_scale[h] : 1.f;
   long long tl = input_lengths[n];
-  const int t_in = (nll < INFINITY) ? static_cast<int>(tl < 0 ? 0 : (tl > T ? T : tl)) : 0;
+  const bool poisoned = nll != nll;  // NaN loss: NaN gradient on the valid frames (the beta kernel leaves such pairs alone)
+  const int t_valid = static_cast<int>(tl < 0 ? 0 : (tl > T ? T : tl));
+  const int t_in = (nll < INFINITY) ? t_valid : 0;
   const long long total = static_cast<long long>(T) * hd.n_classes;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int t = static_cast<int>(i / hd.n_classes);
     const int k = static_cast<int>(i - static_cast<long long>(t) * hd.n_classes);
     const long long off = static_cast<long long>(n) * hd.stride_n + static_cast<long long>(t) * hd.stride_t + k;
-    hd.grad[off] = t < t_in ? g * expf(hd.log_probs[off]) : 0.f;
+    hd.grad[off] = t < t_in ? g * expf(hd.log_probs[off]) : ((poisoned && t < t_valid) ? NAN : 0.f);
   }
 }
 

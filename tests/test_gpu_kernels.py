@@ -566,6 +566,28 @@ def test_ctc_long_labels_and_empty_targets():
         assert float(row_sums.abs().max()) < 5e-3  # |nll| ~ 1e3 in fp32: 1e-6 relative on nll = 1e-3 on sum(gamma)
 
 
+def test_ctc_nan_losses_stay_visible_and_bad_labels_poison_the_loss():
+    """zero_infinity zeroes INFINITE losses only (loss_functions.py:24): a NaN loss (diverged logits) stays NaN in the per-head sum and
+    in the gradient of its utterance, as in torch; a label outside the head's classes (nn.CTCLoss raises) gives a NaN loss instead of
+    indexing the staged log-probabilities out of bounds."""
+    from allophant_b200.loss_functions import multi_head_ctc_loss
+
+    logits, labels, input_lengths, label_lengths = _ctc_case(5, 3, 120, [6, 40], 0.3)
+    logits[0][10, 1, 2] = float("nan")  # utterance 1 of the narrow head diverged
+    labels[1][2, 0] = 40  # utterance 2 of the wide head: label == number of classes
+    leaves = [t.cuda().requires_grad_(True) for t in logits]
+    losses = multi_head_ctc_loss(leaves, [l.cuda() for l in labels], input_lengths.cuda(), [l.cuda() for l in label_lengths])
+    assert torch.isnan(losses).all()
+    losses.sum().backward()
+    for head, poisoned in ((0, 1), (1, 2)):
+        grad = leaves[head].grad.cpu()
+        frames = int(input_lengths[poisoned])
+        assert torch.isnan(grad[:frames, poisoned]).all()
+        assert float(grad[frames:, poisoned].abs().max()) == 0.0 if frames < grad.shape[0] else True
+        clean = [n for n in range(3) if n != poisoned]
+        assert torch.isfinite(grad[:, clean]).all()  # the other utterances of the head are untouched
+
+
 def test_ctc_label_sequences_beyond_511():
     """More than 511 labels (2S+1 states no longer fit a warp's registers): the block-per-pair path, against the fp64 recursion.
     nn.CTCLoss has no cap (loss_functions.py:24); contour attributes and 30 s utterances can exceed 511 labels."""
