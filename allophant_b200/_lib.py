@@ -154,6 +154,7 @@ _SIGNATURES = {
     "aph_gelu_backward_bf16": [_P, _I64, _P, _I64, _I64, _I32, _P, _I64, _P],
     "aph_pack_posconv_weight_dgrad": [_P, _P, _P, _P, _I32, _I32, _I32, _P],
     "aph_posconv_weight_backward": [_P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P],
+    "aph_posconv_weight_backward_blocks": [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P],
     "aph_embedding_bag_backward": [_P, _I64, _I32, _I32, _I32, _P, _P, _P, _P],
     "aph_softmax_backward_cols": [_P, _I64, _P, _I64, _I64, _P, _P, _P, _I32, _I32, _P, _I64, _P],
     "aph_multi_tensor_sumsq": [_P, _P, _I32, _P, _P],

@@ -414,14 +414,14 @@ __global__ void __launch_bounds__(256) posconv_tap_norm_kernel(const float* __re
 
 // raw[tap][o][256] (output of the DIAG_TAPS GEMM) -> dot[tap] = sum_{o,ci} dW[o][ci][tap] * v[o][ci][tap]
 __global__ void __launch_bounds__(256) posconv_wgrad_dot_kernel(const float* __restrict__ raw, const float* __restrict__ v, int O,
-                                                                int Cg, int K, float* __restrict__ dot) {
+                                                                int Cg, int K, int W, float* __restrict__ dot) {
   __shared__ float red[256];
   const int tap = blockIdx.x;
-  const int blocks = 256 / Cg;  // channel groups per 256-wide diagonal block
+  const int blocks = W / Cg;  // channel groups per W-wide diagonal block (256: DIAG_TAPS GEMM; O: one full matrix per tap)
   float s = 0.f;
   for (int i = threadIdx.x; i < O * Cg; i += 256) {
     const int o = i / Cg, ci = i - o * Cg;
-    const float dw = raw[(static_cast<long long>(tap) * O + o) * 256 + ((o / Cg) % blocks) * Cg + ci];
+    const float dw = raw[(static_cast<long long>(tap) * O + o) * W + ((o / Cg) % blocks) * Cg + ci];
     s = fmaf(dw, v[static_cast<long long>(i) * K + tap], s);
   }
   red[threadIdx.x] = s;
@@ -436,9 +436,9 @@ __global__ void __launch_bounds__(256) posconv_wgrad_dot_kernel(const float* __r
 // dv = g/norm * (dW - v * dot / norm^2);  dg[tap] = dot / norm
 __global__ void __launch_bounds__(256) posconv_wgrad_finish_kernel(const float* __restrict__ raw, const float* __restrict__ v,
                                                                    const float* __restrict__ weight_g, const float* __restrict__ dot,
-                                                                   const float* __restrict__ tap_norm2, int O, int Cg, int K,
+                                                                   const float* __restrict__ tap_norm2, int O, int Cg, int K, int W,
                                                                    float* __restrict__ grad_v, float* __restrict__ grad_g) {
-  const int blocks = 256 / Cg;
+  const int blocks = W / Cg;
   const long long total = static_cast<long long>(O) * Cg * K;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(256) posconv_wgrad_finish_kernel(const float* 
     const int o = static_cast<int>(oc / Cg), ci = static_cast<int>(oc - static_cast<long long>(o) * Cg);
     const float n2 = tap_norm2[tap];
     const float inv = rsqrtf(n2);
-    const float dw = raw[(static_cast<long long>(tap) * O + o) * 256 + ((o / Cg) % blocks) * Cg + ci];
+    const float dw = raw[(static_cast<long long>(tap) * O + o) * W + ((o / Cg) % blocks) * Cg + ci];
     grad_v[i] = weight_g[tap] * inv * (dw - v[i] * dot[tap] / n2);
     if (oc == 0) grad_g[tap] = dot[tap] * inv;
   }
@@ -640,22 +640,31 @@ extern "C" int aph_pack_posconv_weight_dgrad(const float* weight_g, const float*
   return APH_OK;
 }
 
-extern "C" int aph_posconv_weight_backward(const float* raw, const float* weight_g, const float* weight_v, float* tap_scratch,
-                                           int32_t out_channels, int32_t group_channels, int32_t kernel, float* grad_g,
-                                           float* grad_v, void* stream_) {
+extern "C" int aph_posconv_weight_backward_blocks(const float* raw, const float* weight_g, const float* weight_v, float* tap_scratch,
+                                                  int32_t out_channels, int32_t group_channels, int32_t kernel, int32_t block_width,
+                                                  float* grad_g, float* grad_v, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   APH_REQUIRE(raw && weight_g && weight_v && tap_scratch && grad_g && grad_v, "null pointer");
-  APH_REQUIRE(out_channels > 0 && group_channels > 0 && kernel > 0 && 256 % group_channels == 0 && out_channels % 256 == 0, "bad shape");
+  APH_REQUIRE(out_channels > 0 && group_channels > 0 && kernel > 0 && block_width > 0 && block_width % group_channels == 0 &&
+                  out_channels % block_width == 0,
+              "bad shape: the diagonal blocks must hold whole channel groups and tile the channels");
   float* scale = tap_scratch;
   float* norm2 = tap_scratch + kernel;
   float* dot = tap_scratch + 2 * kernel;
   posconv_tap_norm_kernel<<<kernel, 256, 0, stream>>>(weight_g, weight_v, out_channels, group_channels, kernel, scale, norm2);
-  posconv_wgrad_dot_kernel<<<kernel, 256, 0, stream>>>(raw, weight_v, out_channels, group_channels, kernel, dot);
+  posconv_wgrad_dot_kernel<<<kernel, 256, 0, stream>>>(raw, weight_v, out_channels, group_channels, kernel, block_width, dot);
   const long long total = static_cast<long long>(out_channels) * group_channels * kernel;
   posconv_wgrad_finish_kernel<<<blocks_for(total, 256, 16LL * sm_count()), 256, 0, stream>>>(
-      raw, weight_v, weight_g, dot, norm2, out_channels, group_channels, kernel, grad_v, grad_g);
+      raw, weight_v, weight_g, dot, norm2, out_channels, group_channels, kernel, block_width, grad_v, grad_g);
   APH_POST_LAUNCH(3);
   return APH_OK;
+}
+
+extern "C" int aph_posconv_weight_backward(const float* raw, const float* weight_g, const float* weight_v, float* tap_scratch,
+                                           int32_t out_channels, int32_t group_channels, int32_t kernel, float* grad_g,
+                                           float* grad_v, void* stream_) {
+  return aph_posconv_weight_backward_blocks(raw, weight_g, weight_v, tap_scratch, out_channels, group_channels, kernel, 256, grad_g, grad_v,
+                                            stream_);
 }
 
 extern "C" int aph_add_f32_2d(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, int64_t rows, int32_t cols,

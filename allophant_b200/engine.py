@@ -331,9 +331,22 @@ class PackedEncoder:
         """B operand of the positional conv's data-gradient GEMM, packed on first use (training only)."""
         pc = self.weights.encoder.pos_conv_embed.conv
         if self._pos_w_dgrad is None or not self._pos_w_dgrad_valid:
-            self._pos_w_dgrad = ops.pack_posconv_weight_dgrad(
-                pc.parametrizations.weight.original0, pc.parametrizations.weight.original1, dst=self._pos_w_dgrad
-            )
+            weight_g, weight_v = pc.parametrizations.weight.original0, pc.parametrizations.weight.original1
+            group, span = weight_v.shape[1], self.pos_span
+            if span == 64:
+                self._pos_w_dgrad = ops.pack_posconv_weight_dgrad(weight_g, weight_v, dst=self._pos_w_dgrad)
+            else:
+                # [input channel][tap][group-local output channel] -> [input channel][tap][span]: block-diagonal over the super
+                # group, exactly as the forward operand (`_fill_derived`)
+                grouped = ops.pack_posconv_weight_dgrad(weight_g, weight_v)
+                channels, taps = grouped.shape[0], grouped.shape[1] // group
+                if self._pos_w_dgrad is None:
+                    self._pos_w_dgrad = torch.empty(channels, taps * span, device=grouped.device, dtype=torch.bfloat16)
+                wide = self._pos_w_dgrad.view(channels, taps, span)
+                wide.zero_()
+                offsets = (torch.arange(channels, device=wide.device) % span) // group * group
+                columns = offsets[:, None] + torch.arange(group, device=wide.device)[None, :]
+                wide.scatter_(2, columns[:, None, :].expand(channels, taps, group), grouped.view(channels, taps, group))
             self._pos_w_dgrad_valid = True
         return self._pos_w_dgrad
 
@@ -615,8 +628,6 @@ class EncoderPlan:
             steps.append(self._regularise_projection)
         # positional conv embedding: hidden += gelu(grouped_conv(hidden)) (HF:764-765, 353-368)
         taps = cfg.num_conv_pos_embeddings
-        if p.pos_span != 64 and self.training:
-            raise NotImplementedError("training through positional conv groups that are not 64 channels wide (wav2vec2-base) is not built")
         pos_args = ops.make_gemm_args(
             self.hidden_bf16,
             p.pos_w,
@@ -760,8 +771,6 @@ class EncoderPlan:
         """Post-LN ordering with everything the backward pass reads kept per layer (``_backward_post_ln_layers``)."""
         p, cfg = self.packed, self.cfg
         N, M, H, eps = self.n_utt, self.rows, cfg.hidden_size, cfg.layer_norm_eps
-        if H not in (512, 1024):
-            raise NotImplementedError("training of post-LN encoders is built for hidden sizes 512 and 1024")
         n_layers = len(p.layers)
         hs, hs16 = self.hs, self.hs16
         ge, be = p.final_ln  # encoder.layer_norm
@@ -1240,13 +1249,27 @@ class EncoderPlan:
                 [("bias", (H,)), ("parametrizations.weight.original0", tuple(weight_g.shape)), ("parametrizations.weight.original1", tuple(weight_v.shape))]
             )
             ops.colsum_bf16(dh16, M, H, H, out=g["bias"])
-            raw = torch.empty(taps, H, 256, device=dev, dtype=torch.float32)
-            args = ops.make_wgrad_args(dh16, self.hidden_bf16, raw, rows=seq, m=H, ld_dy=H, n=H, ld_x=H, ld_out=256)
-            args.mode, args.n_taps, args.tap_pad = _lib.APH_GEMM_DIAG_TAPS, taps, taps // 2
-            args.k_batch, args.a_batch_stride, args.b_seg_stride = N, seq * H, seq * H
-            args.out_batch_rows = H
-            ops.run_gemm(args)
-            ops.posconv_weight_backward(raw, weight_g, weight_v, g["parametrizations.weight.original0"], g["parametrizations.weight.original1"])
+            if p.pos_span == 64:
+                raw = torch.empty(taps, H, 256, device=dev, dtype=torch.float32)
+                args = ops.make_wgrad_args(dh16, self.hidden_bf16, raw, rows=seq, m=H, ld_dy=H, n=H, ld_x=H, ld_out=256)
+                args.mode, args.n_taps, args.tap_pad = _lib.APH_GEMM_DIAG_TAPS, taps, taps // 2
+                args.k_batch, args.a_batch_stride, args.b_seg_stride = N, seq * H, seq * H
+                args.out_batch_rows = H
+                ops.run_gemm(args)
+                block_width = 256
+            else:
+                # groups that do not tile 256 channels (wav2vec2-base: 16 x 48): one full [H][H] weight-gradient GEMM per tap, the
+                # input shifted by tap - taps/2 frames inside each utterance (zero fill outside); the group-diagonal entries are
+                # read out below.  ~H/group times the necessary FLOPs — a coverage path, not a tuned one
+                raw = torch.empty(taps, H, H, device=dev, dtype=torch.float32)
+                for tap in range(taps):
+                    args = ops.make_wgrad_args(dh16, self.hidden_bf16, raw[tap], rows=seq, m=H, ld_dy=H, n=H, ld_x=H, ld_out=H)
+                    args.k_batch, args.a_batch_stride, args.b_seg_stride = N, seq * H, seq * H
+                    args.b_k_shift = tap - taps // 2
+                    ops.run_gemm(args)
+                block_width = H
+            ops.posconv_weight_backward(raw, weight_g, weight_v, g["parametrizations.weight.original0"], g["parametrizations.weight.original1"],
+                                        block_width=block_width)  # fmt: skip
             done(flat, g, "encoder.pos_conv_embed.conv.")
         embed = getattr(w, "masked_spec_embed", None)
         need_embed = st is not None and self.spec_active and embed is not None and embed.requires_grad
@@ -1254,12 +1277,12 @@ class EncoderPlan:
             raise RuntimeError("this EncoderPlan did not keep the feature extractor's activations (train_extractor=False)")
         if need_projection or need_embed or need_extractor:
             # data gradient of the grouped conv: the same sliding-tap GEMM with flipped taps, accumulated onto dh
-            ops.run_gemm(
-                ops.make_gemm_args(
-                    dh16, p.pos_w_dgrad, a_rows=seq, a_inner=H, a_row_stride=H, batch=N, a_batch_stride=seq * H, mode=_lib.APH_GEMM_TAPS,
-                    tap_pad=taps // 2 - 1, n=H, k=taps * 64, resid=dh, ld_resid=H, out_f32=dh, ld_f32=H, out_batch_rows=seq,
-                )
+            dgrad_args = ops.make_gemm_args(
+                dh16, p.pos_w_dgrad, a_rows=seq, a_inner=H, a_row_stride=H, batch=N, a_batch_stride=seq * H, mode=_lib.APH_GEMM_TAPS,
+                tap_pad=taps // 2 - 1, n=H, k=taps * p.pos_span, resid=dh, ld_resid=H, out_f32=dh, ld_f32=H, out_batch_rows=seq,
             )  # fmt: skip
+            dgrad_args.taps_span = p.pos_span
+            ops.run_gemm(dgrad_args)
             if st is not None:
                 # SpecAugment: masked frames were replaced by masked_spec_embed (its gradient: their sum), then the
                 # feature projection dropout; both are functions of (seed, row, column) only

@@ -464,6 +464,13 @@ def layernorm_rows(
     ld_f32: int = 0,
 ) -> None:
     _require_cuda(x, gamma, beta, out_bf16, out_f32)
+    if cols not in (512, 1024):
+        # the row kernels are specialised for the two widths of the XLS-R path; every other width (wav2vec2-base: 768) takes the
+        # general kernel of the from-scratch transformer encoder
+        if x.dtype != torch.float32 or gelu:
+            raise NotImplementedError(f"layernorm_rows over {cols} columns takes fp32 rows and no fused GELU")
+        layernorm_any(x, ld_in, rows, cols, gamma, beta, eps, out_f32=out_f32, ld_f32=ld_f32, out_bf16=out_bf16, ld_bf16=ld_bf16)
+        return
     check(
         lib.aph_layernorm_rows(
             x.data_ptr(),
@@ -841,6 +848,14 @@ def layernorm_backward(
     dx_resid: Optional[Tensor], ld_resid: int, dx: Tensor, ld_dx: int, dgamma: Optional[Tensor], dbeta: Optional[Tensor],
 ) -> None:  # fmt: skip
     _require_cuda(x, dy, gamma, dx_resid, dx, dgamma, dbeta)
+    if cols not in (512, 1024):
+        if x.dtype != torch.float32 or dy.dtype != torch.float32:
+            raise NotImplementedError(f"layernorm_backward over {cols} columns takes fp32 rows")
+        if dgamma is not None:  # the general kernel accumulates into them
+            dgamma.zero_()
+            dbeta.zero_()
+        layernorm_any_backward(x, ld_x, dy, ld_dy, rows, cols, gamma, eps, dx_resid, ld_resid, dx, ld_dx, dgamma, dbeta)
+        return
     check(
         lib.aph_layernorm_backward(
             x.data_ptr(), int(x.dtype == torch.float32), ld_x, dy.data_ptr(), int(dy.dtype == torch.float32), ld_dy, rows, cols,
@@ -879,9 +894,10 @@ def pack_posconv_weight_dgrad(weight_g: Tensor, weight_v: Tensor, dst: Optional[
 
 
 def posconv_weight_backward(
-    raw: Tensor, weight_g: Tensor, weight_v: Tensor, grad_g: Optional[Tensor] = None, grad_v: Optional[Tensor] = None
+    raw: Tensor, weight_g: Tensor, weight_v: Tensor, grad_g: Optional[Tensor] = None, grad_v: Optional[Tensor] = None, block_width: int = 256
 ) -> Tuple[Tensor, Tensor]:
-    """``raw`` fp32 [k, O, 256] from the DIAG_TAPS GEMM -> (grad of original0 [1,1,k], grad of original1 [O,Cg,k])."""
+    """``raw`` fp32 [k, O, block_width] (256: from the DIAG_TAPS GEMM; O: one full weight-gradient GEMM per tap) -> (grad of
+    original0 [1,1,k], grad of original1 [O,Cg,k])."""
     _require_cuda(raw, weight_g, weight_v, grad_g, grad_v)
     g = weight_g.detach().float().contiguous()
     v = weight_v.detach().float().contiguous()
@@ -891,7 +907,10 @@ def posconv_weight_backward(
     if grad_v is None:
         grad_v = torch.empty(v.shape, device=v.device, dtype=torch.float32)
     scratch = torch.empty(3 * k, device=v.device, dtype=torch.float32)
-    check(lib.aph_posconv_weight_backward(raw.data_ptr(), g.data_ptr(), v.data_ptr(), scratch.data_ptr(), o, cg, k, grad_g.data_ptr(), grad_v.data_ptr(), _stream()), "aph_posconv_weight_backward")
+    check(
+        lib.aph_posconv_weight_backward_blocks(raw.data_ptr(), g.data_ptr(), v.data_ptr(), scratch.data_ptr(), o, cg, k, block_width, grad_g.data_ptr(), grad_v.data_ptr(), _stream()),
+        "aph_posconv_weight_backward_blocks",
+    )
     return grad_g, grad_v
 
 

@@ -29,7 +29,7 @@ extern "C" {
 #define APH_ERR_CUDA (-2)        /* CUDA runtime / driver error                    */
 #define APH_ERR_UNSUPPORTED (-3) /* valid request outside the implemented envelope */
 
-#define APH_ABI_VERSION 6
+#define APH_ABI_VERSION 7
 
 /* ---- library ------------------------------------------------------------ */
 int aph_abi_version(void);
@@ -423,6 +423,13 @@ int aph_pack_posconv_weight_dgrad(const float* weight_g, const float* weight_v, 
 int aph_posconv_weight_backward(const float* raw, const float* weight_g, const float* weight_v,
                                 float* tap_scratch, int32_t out_channels, int32_t group_channels,
                                 int32_t kernel, float* grad_g, float* grad_v, void* stream);
+/* The same with raw = fp32 [k][O][block_width]: row o holds the products of output channel o with the block_width input channels of
+ * its diagonal block (block_width a multiple of the group width that divides O).  256 = what APH_GEMM_DIAG_TAPS writes; O = one full
+ * [O][O] weight-gradient GEMM per tap (b_k_shift = tap - k/2), used where the groups do not tile 256 channels (wav2vec2-base:
+ * 16 groups of 48). */
+int aph_posconv_weight_backward_blocks(const float* raw, const float* weight_g, const float* weight_v,
+                                       float* tap_scratch, int32_t out_channels, int32_t group_channels,
+                                       int32_t kernel, int32_t block_width, float* grad_g, float* grad_v, void* stream);
 /* Backward of EmbeddingCompositionLayer's EmbeddingBag("sum") (acoustic_model.py:208, 225-232):
  * grad_rows[0] -> category 0 (blank), grad_rows[1+v] -> every category tfi[v][f] + offsets[f]. */
 int aph_embedding_bag_backward(const float* grad_rows, int64_t ld, int32_t n_phonemes,

@@ -309,6 +309,33 @@ def test_wav2vec2_base_shape_matches_oracle():
     for name, reference in outputs.items():
         error = _range_error(predictions.outputs[name].float().cpu(), reference, frames_ref.tolist())
         assert error < RANGE_TOL, f"{name}: {error:.3e} of range"
+    # training with the feature extractor frozen (the reference's default): loss and every gradient — the positional conv in 48-channel
+    # groups included — against autograd through the Hugging Face model
+    from allophant_b200.loss_functions import multi_head_ctc_loss
+
+    head_classes = {c.name: c.size + 1 for c in spec.classes}
+    labels, label_lengths = restatement.training_labels(spec, head_classes, frames_ref, None, seed=10)
+    model.eval()
+    for parameter in model.parameters():
+        parameter.grad = None
+    outputs = model(batch)
+    outputs.outputs.pop("phone", None)
+    order = list(outputs.outputs)
+    losses = multi_head_ctc_loss([outputs.outputs[n] for n in order], [labels[n].cuda() for n in order], outputs.lengths, [label_lengths[n].cuda() for n in order])
+    loss = losses.sum() / sum(int(label_lengths[n].sum()) for n in order)
+    loss.backward()
+    reference_loss, _, reference = oracle.training_step(audio, lengths, labels, label_lengths, torch.zeros(3, dtype=torch.long))
+    assert abs(float(loss) - float(reference_loss)) <= 2e-2 * abs(float(reference_loss))
+    worst = {}
+    for name, parameter in model.named_parameters():
+        if name not in reference or float(reference[name].norm()) < 1e-7:
+            continue
+        assert parameter.grad is not None, name
+        worst[name] = float((parameter.grad.double().cpu() - reference[name].double()).norm() / reference[name].double().norm())
+    ranked = sorted(worst.items(), key=lambda item: -item[1])
+    print("wav2vec2-base shape training: worst " + ", ".join(f"{k.split('._model.')[-1]}={v:.3e}" for k, v in ranked[:4]))
+    assert any("pos_conv_embed" in name for name in worst)
+    assert len(worst) > 40 and ranked[0][1] < 1e-1, ranked[:8]  # the post-LN noise band, see test_post_ln_group_norm_encoder_matches_oracle
 
 
 def test_time_layer_heads_match_the_reference():

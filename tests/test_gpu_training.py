@@ -218,13 +218,16 @@ def test_attention_backward(seq, lengths):
 
 
 # ------------------------------------------------------------------------------------------ positional conv
-def test_posconv_backward():
-    """Data and weight gradients of the weight-normed grouped positional conv (HF:326-368) + GELU + residual."""
+@pytest.mark.parametrize("hidden", [1024, 768])
+def test_posconv_backward(hidden):
+    """Data and weight gradients of the weight-normed grouped positional conv (HF:326-368) + GELU + residual: 16 groups of 64
+    channels (XLS-R) through the diagonal-block GEMM, 16 groups of 48 (wav2vec2-base) through block-diagonal super groups of 192
+    channels (data gradient) and one full weight-gradient GEMM per tap."""
     ops = _ops()
     from allophant_b200 import _lib
 
     torch.manual_seed(17)
-    n_utt, seq, hidden, groups, taps = 2, 200, 1024, 16, 128
+    n_utt, seq, groups, taps = 2, 200, 16, 128
     cg = hidden // groups
     weight_v = torch.randn(hidden, cg, taps, device=DEV) * 0.02
     weight_g = weight_v.pow(2).sum(dim=(0, 1), keepdim=True).sqrt() * (1 + 0.1 * torch.randn(1, 1, taps, device=DEV))
@@ -241,23 +244,42 @@ def test_posconv_backward():
 
     # data gradient
     packed = ops.pack_posconv_weight_dgrad(weight_g, weight_v)
+    span = 64
+    if cg != 64:  # block-diagonal super groups, as PackedEncoder.pos_w_dgrad builds them
+        import math
+
+        span = cg * 64 // math.gcd(cg, 64)
+        wide = torch.zeros(hidden, taps, span, device=DEV, dtype=torch.bfloat16)
+        offsets = (torch.arange(hidden, device=DEV) % span) // cg * cg
+        columns = offsets[:, None] + torch.arange(cg, device=DEV)[None, :]
+        wide.scatter_(2, columns[:, None, :].expand(hidden, taps, cg), packed.view(hidden, taps, cg))
+        packed = wide.view(hidden, taps * span)
     dx = torch.zeros(n_utt * seq, hidden, device=DEV)
-    ops.run_gemm(
-        ops.make_gemm_args(
-            dy16, packed, a_rows=seq, a_inner=hidden, a_row_stride=hidden, batch=n_utt, a_batch_stride=seq * hidden, mode=_lib.APH_GEMM_TAPS,
-            tap_pad=taps // 2 - 1, n=hidden, k=taps * cg, resid=dx, ld_resid=hidden, out_f32=dx, ld_f32=hidden, out_batch_rows=seq,
-        )
+    dgrad = ops.make_gemm_args(
+        dy16, packed, a_rows=seq, a_inner=hidden, a_row_stride=hidden, batch=n_utt, a_batch_stride=seq * hidden, mode=_lib.APH_GEMM_TAPS,
+        tap_pad=taps // 2 - 1, n=hidden, k=taps * span, resid=dx, ld_resid=hidden, out_f32=dx, ld_f32=hidden, out_batch_rows=seq,
     )  # fmt: skip
+    dgrad.taps_span = span
+    ops.run_gemm(dgrad)
     assert range_err(dx.view(n_utt, seq, hidden), xr.grad) < 2e-2
 
     # weight gradient
-    raw = torch.empty(taps, hidden, 256, device=DEV)
-    args = ops.make_wgrad_args(dy16, x16, raw, rows=seq, m=hidden, ld_dy=hidden, n=hidden, ld_x=hidden, ld_out=256)
-    args.mode, args.n_taps, args.tap_pad = _lib.APH_GEMM_DIAG_TAPS, taps, taps // 2
-    args.k_batch, args.a_batch_stride, args.b_seg_stride = n_utt, seq * hidden, seq * hidden
-    args.out_batch_rows = hidden
-    ops.run_gemm(args)
-    grad_g, grad_v = ops.posconv_weight_backward(raw, weight_g, weight_v)
+    if cg == 64:
+        raw = torch.empty(taps, hidden, 256, device=DEV)
+        args = ops.make_wgrad_args(dy16, x16, raw, rows=seq, m=hidden, ld_dy=hidden, n=hidden, ld_x=hidden, ld_out=256)
+        args.mode, args.n_taps, args.tap_pad = _lib.APH_GEMM_DIAG_TAPS, taps, taps // 2
+        args.k_batch, args.a_batch_stride, args.b_seg_stride = n_utt, seq * hidden, seq * hidden
+        args.out_batch_rows = hidden
+        ops.run_gemm(args)
+        grad_g, grad_v = ops.posconv_weight_backward(raw, weight_g, weight_v)
+    else:
+        raw = torch.empty(taps, hidden, hidden, device=DEV)
+        for tap in range(taps):
+            args = ops.make_wgrad_args(dy16, x16, raw[tap], rows=seq, m=hidden, ld_dy=hidden, n=hidden, ld_x=hidden, ld_out=hidden)
+            args.k_batch, args.a_batch_stride, args.b_seg_stride = n_utt, seq * hidden, seq * hidden
+            args.b_k_shift = tap - taps // 2
+            ops.run_gemm(args)
+        grad_g, grad_v = ops.posconv_weight_backward(raw, weight_g, weight_v, block_width=hidden)
     assert range_err(grad_v, vr.grad) < 2e-2
     assert range_err(grad_g, gr.grad) < 2e-2
 

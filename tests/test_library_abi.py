@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for symbol in declared_symbols():
         assert hasattr(_lib.lib, symbol), f"{symbol} is declared in the header but not exported"
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared_symbols(), "ctypes signatures and header disagree"
-    assert _lib.lib.aph_abi_version() == 6
+    assert _lib.lib.aph_abi_version() == 7
 
 
 def test_integration_guide_indexes_every_entry_point():
