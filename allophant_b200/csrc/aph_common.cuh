@@ -442,26 +442,29 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
 }
 
 // ---- math ------------------------------------------------------------------
-// Exact-form GELU 0.5 x (1 + erf(x / sqrt 2)) (torch's default, HF "gelu").  erf is evaluated with
-// Abramowitz-Stegun 7.1.28, erf(u) = 1 - (1 + a1 u + ... + a6 u^6)^-16 (|error| <= 3e-7, i.e. fp32
-// round-off of the GELU): 15 FMA-pipe instructions and ONE MUFU op per element.  erff() costs ~25
-// instructions and two MUFU ops, which made the FFN1 epilogue longer than its mainloop.
+// Exact-form GELU 0.5 x (1 + erf(x / sqrt 2)) (torch's default, HF "gelu") as
+//   y = h + a (1 - e),  h = x / 2,  a = |h|,  e = erfc(|x| / sqrt 2) = 2^R(s),  s = -|x|,
+//   R(s) = s (k1 + s (-k2 + s (k3 + s (-k4 + s k5))))
+// R is a degree-5 fit of log2 erfc (no constant term: erf(0) = 0 exactly; |erf error| <= 6.4e-7 in fp32 Horner form, the fp32
+// round-off class of the GELU; `tests/test_gpu_kernels.py::test_gelu_matches_erf`).  11 FMA-pipe instructions + one MUFU.EX2 per
+// element, 6.5 issue slots per element in the packed form below.  Round 1 used Abramowitz-Stegun 7.1.28,
+// 1 - (1 + a1 u + ... + a6 u^6)^-16: six Horner steps, four squarings and a reciprocal — 10 issue slots per element packed, and
+// the LayerNorm + GELU rows of the feature extractor, the first convolution and the FFN1 epilogue are bound by exactly this
+// arithmetic (profiles/r02_gelu.md).  erff() costs ~25 instructions and two MUFU ops.
+constexpr float kGeluK1 = 1.15109136f, kGeluK2 = -0.459254674f, kGeluK3 = 0.052561252f, kGeluK4 = 0.00739752032f, kGeluK5 = 0.000520460532f;
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float u = fabsf(x) * 0.70710678118654752440f;
-  float d = fmaf(0.0000430638f, u, 0.0002765672f);
-  d = fmaf(d, u, 0.0001520143f);
-  d = fmaf(d, u, 0.0092705272f);
-  d = fmaf(d, u, 0.0422820123f);
-  d = fmaf(d, u, 0.0705230784f);
-  d = fmaf(d, u, 1.0f);
-  d *= d;
-  d *= d;
-  d *= d;
-  d *= d;  // ^16 (overflows to +inf for |x| > ~25, where the reciprocal below is exactly 0)
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
-  const float hx = 0.5f * x;
-  return fmaf(fabsf(hx), 1.0f - r, hx);  // 0.5 x + 0.5 |x| erf(|x|/sqrt2) = 0.5 x (1 + erf(x/sqrt2))
+  const float s = -fabsf(x);
+  float p = fmaf(kGeluK5, s, kGeluK4);
+  p = fmaf(p, s, kGeluK3);
+  p = fmaf(p, s, kGeluK2);
+  p = fmaf(p, s, kGeluK1);
+  p *= s;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p));
+  const float h = 0.5f * x;
+  const float ms = 0.5f * s;           // -a
+  const float w = fmaf(s, -0.5f, h);   // h + a
+  return fmaf(ms, e, w);               // h + a - a e
 }
 // Two GELUs at once on the packed fp32 pipe (FFMA2 / FMUL2, sm_100): the same operations in the same order as
 // gelu_erf, so each half is bit-identical to the scalar function, at ~10 instead of ~18 issue slots per element.  The
@@ -490,25 +493,19 @@ __device__ __forceinline__ float2 f2_add(float2 a, float2 b) {
 }
 __device__ __forceinline__ float2 f2_splat(float v) { return make_float2(v, v); }
 __device__ __forceinline__ float2 gelu_erf2(float2 x) {
-  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
-  const float2 u = f2_mul(ax, f2_splat(0.70710678118654752440f));
-  float2 d = f2_fma(f2_splat(0.0000430638f), u, f2_splat(0.0002765672f));
-  d = f2_fma(d, u, f2_splat(0.0001520143f));
-  d = f2_fma(d, u, f2_splat(0.0092705272f));
-  d = f2_fma(d, u, f2_splat(0.0422820123f));
-  d = f2_fma(d, u, f2_splat(0.0705230784f));
-  d = f2_fma(d, u, f2_splat(1.0f));
-  d = f2_mul(d, d);
-  d = f2_mul(d, d);
-  d = f2_mul(d, d);
-  d = f2_mul(d, d);
-  float2 r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(d.x));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(d.y));
-  const float2 hx = f2_mul(x, f2_splat(0.5f));
-  const float2 ahx = make_float2(fabsf(hx.x), fabsf(hx.y));
-  const float2 e = f2_fma(r, f2_splat(-1.0f), f2_splat(1.0f));  // 1 - r, one rounding like the scalar subtraction
-  return f2_fma(ahx, e, hx);
+  const float2 s = make_float2(-fabsf(x.x), -fabsf(x.y));
+  float2 p = f2_fma(f2_splat(kGeluK5), s, f2_splat(kGeluK4));
+  p = f2_fma(p, s, f2_splat(kGeluK3));
+  p = f2_fma(p, s, f2_splat(kGeluK2));
+  p = f2_fma(p, s, f2_splat(kGeluK1));
+  p = f2_mul(p, s);
+  float2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(p.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(p.y));
+  const float2 h = f2_mul(x, f2_splat(0.5f));
+  const float2 ms = f2_mul(s, f2_splat(0.5f));
+  const float2 w = f2_fma(s, f2_splat(-0.5f), h);
+  return f2_fma(ms, e, w);
 }
 // Eight pairs at once with the order of operations pinned (volatile asm): Horner step by Horner step ACROSS the pairs, so that
 // eight independent dependency chains are in flight.  Left to itself the compiler interleaves only two or three of the sixteen
@@ -526,41 +523,34 @@ __device__ __forceinline__ void f2v_mul(float2& d, const float2& a, const float2
                : "l"(*reinterpret_cast<const uint64_t*>(&a)), "l"(*reinterpret_cast<const uint64_t*>(&b)));
 }
 __device__ __forceinline__ void gelu_erf2_x8(float2 (&x)[8]) {
-  float2 u[8], d[8];
-  const float2 c0 = f2_splat(0.70710678118654752440f);
+  float2 s[8], p[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) f2v_mul(u[i], make_float2(fabsf(x[i].x), fabsf(x[i].y)), c0);
-  const float2 k6 = f2_splat(0.0000430638f), k5 = f2_splat(0.0002765672f), k4 = f2_splat(0.0001520143f), k3 = f2_splat(0.0092705272f),
-               k2 = f2_splat(0.0422820123f), k1 = f2_splat(0.0705230784f), one = f2_splat(1.0f);
+  for (int i = 0; i < 8; ++i) s[i] = make_float2(-fabsf(x[i].x), -fabsf(x[i].y));
+  const float2 k5 = f2_splat(kGeluK5), k4 = f2_splat(kGeluK4), k3 = f2_splat(kGeluK3), k2 = f2_splat(kGeluK2), k1 = f2_splat(kGeluK1);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) f2v_fma(d[i], k6, u[i], k5);
+  for (int i = 0; i < 8; ++i) f2v_fma(p[i], k5, s[i], k4);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) f2v_fma(d[i], d[i], u[i], k4);
+  for (int i = 0; i < 8; ++i) f2v_fma(p[i], p[i], s[i], k3);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) f2v_fma(d[i], d[i], u[i], k3);
+  for (int i = 0; i < 8; ++i) f2v_fma(p[i], p[i], s[i], k2);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) f2v_fma(d[i], d[i], u[i], k2);
+  for (int i = 0; i < 8; ++i) f2v_fma(p[i], p[i], s[i], k1);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) f2v_fma(d[i], d[i], u[i], k1);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) f2v_fma(d[i], d[i], u[i], one);
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) f2v_mul(d[i], d[i], d[i]);
-  }
+  for (int i = 0; i < 8; ++i) f2v_mul(p[i], p[i], s[i]);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(d[i].x) : "f"(d[i].x));
-    asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(d[i].y) : "f"(d[i].y));
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p[i].x) : "f"(p[i].x));
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p[i].y) : "f"(p[i].y));
   }
-  const float2 half = f2_splat(0.5f), minus_one = f2_splat(-1.0f);
+  const float2 half = f2_splat(0.5f), minus_half = f2_splat(-0.5f);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) f2v_mul(u[i], x[i], half);                  // hx
+  for (int i = 0; i < 8; ++i) f2v_mul(x[i], x[i], half);              // h
 #pragma unroll
-  for (int i = 0; i < 8; ++i) f2v_fma(d[i], d[i], minus_one, one);        // 1 - r
+  for (int i = 0; i < 8; ++i) f2v_fma(x[i], s[i], minus_half, x[i]);  // w = h + a
 #pragma unroll
-  for (int i = 0; i < 8; ++i) f2v_fma(x[i], make_float2(fabsf(u[i].x), fabsf(u[i].y)), d[i], u[i]);
+  for (int i = 0; i < 8; ++i) f2v_mul(s[i], s[i], half);              // ms = -a
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f2v_fma(x[i], s[i], p[i], x[i]);        // h + a - a e
 }
 // d/dx of the GELU above: Phi(x) + x phi(x), Phi from the same erf approximation
 // ---- counter-based keep masks for train-mode dropout ----------------------------------------------------------------

@@ -62,6 +62,23 @@ def test_gemm_residual_mask_and_scale():
     assert range_err(out, reference) < 1e-4
 
 
+def test_gelu_matches_erf():
+    """The GELU of every epilogue / row kernel (aph_common.cuh:gelu_erf*: erfc as 2^R(-|x|) with a degree-5 fit of log2 erfc)
+    against the exact erf form in fp64, through a GEMM with an identity weight (its product reproduces the bf16 input exactly)."""
+    ops = _ops()
+    values = torch.linspace(-9.0, 9.0, 64 * 4096, device=DEV).bfloat16()
+    x = values.view(4096, 64)
+    identity = torch.eye(64, device=DEV).bfloat16()
+    out = torch.empty(4096, 64, device=DEV)
+    ops.run_gemm(ops.make_gemm_args(x, identity, a_rows=4096, a_inner=64, a_row_stride=64, gelu=True, out_f32=out, ld_f32=64))
+    exact = F.gelu(x.double())
+    error = (out.double() - exact).abs()
+    assert float(error.max()) < 2.5e-6, float(error.max())
+    # the negative tail keeps its relative accuracy well inside bf16 resolution (3.9e-3)
+    tail = exact.abs() > 1e-3
+    assert float((error[tail] / exact[tail].abs()).max()) < 1.5e-3
+
+
 @pytest.mark.parametrize(
     "m,n,k,form",
     [
