@@ -134,8 +134,8 @@ __global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ x,
                                                     int skip_padded) {
   pdl_trigger();
   pdl_wait();
-  __shared__ float w_s[kK0][kC0];
-  __shared__ float b_s[kC0], g_s[kC0], be_s[kC0];
+  __shared__ __align__(16) float w_s[kK0][kC0];
+  __shared__ __align__(16) float b_s[kC0], g_s[kC0], be_s[kC0];
   for (int i = threadIdx.x; i < kC0 * kK0; i += blockDim.x) w_s[i % kK0][i / kK0] = w[i];
   for (int i = threadIdx.x; i < kC0; i += blockDim.x) {
     b_s[i] = bias ? bias[i] : 0.f;
@@ -166,25 +166,23 @@ __global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ x,
     const int xi = t0 * kS0 + lane;
     float xv = 0.f;
     if (xi < T && xi < len) xv = (row[xi] - mr.x) * mr.y;
-    float acc[kTT][16];
+    // channel pairs (2 lane + 64 i, + 1) as packed fp32: the 10 x 16 multiply-adds of a frame, the statistics and the
+    // normalisation are one f32x2 instruction per pair (this kernel is bound by issue slots: profiles/r02_gelu.md)
+    float2 acc[kTT][8];
 #pragma unroll
     for (int tt = 0; tt < kTT; ++tt)
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[tt][i] = b_s[2 * lane + 64 * (i >> 1) + (i & 1)];
+      for (int i = 0; i < 8; ++i) acc[tt][i] = *reinterpret_cast<const float2*>(&b_s[2 * lane + 64 * i]);
 #pragma unroll
     for (int j = 0; j < kK0; ++j) {
-      float wv[16];
+      float2 wv[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float2 w2 = *reinterpret_cast<const float2*>(&w_s[j][2 * lane + 64 * i]);
-        wv[2 * i] = w2.x;
-        wv[2 * i + 1] = w2.y;
-      }
+      for (int i = 0; i < 8; ++i) wv[i] = *reinterpret_cast<const float2*>(&w_s[j][2 * lane + 64 * i]);
 #pragma unroll
       for (int tt = 0; tt < kTT; ++tt) {
-        const float xs = __shfl_sync(0xffffffffu, xv, tt * kS0 + j);
+        const float2 xs = f2_splat(__shfl_sync(0xffffffffu, xv, tt * kS0 + j));
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[tt][i] = fmaf(wv[i], xs, acc[tt][i]);
+        for (int i = 0; i < 8; ++i) acc[tt][i] = f2_fma(wv[i], xs, acc[tt][i]);
       }
     }
 #pragma unroll
@@ -192,23 +190,25 @@ __global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ x,
       const int t = t0 + tt;
       if (t >= L0) break;  // warp-uniform
       if (kLayerNorm) {
-        float s = 0.f;
+        float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) s += acc[tt][i];
-        const float mean = warp_sum(s) * (1.0f / kC0);
-        float q = 0.f;
+        for (int i = 0; i < 8; ++i) s2 = f2_add(s2, acc[tt][i]);
+        const float mean = warp_sum(s2.x + s2.y) * (1.0f / kC0);
+        const float2 neg_mean = f2_splat(-mean);
+        float2 q2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float d = acc[tt][i] - mean;
-          q = fmaf(d, d, q);
+        for (int i = 0; i < 8; ++i) {
+          acc[tt][i] = f2_add(acc[tt][i], neg_mean);
+          q2 = f2_fma(acc[tt][i], acc[tt][i], q2);
         }
-        const float rstd = rsqrtf(warp_sum(q) * (1.0f / kC0) + eps);
+        const float2 rstd = f2_splat(rsqrtf(warp_sum(q2.x + q2.y) * (1.0f / kC0) + eps));
         __nv_bfloat16* dst = out + (static_cast<long long>(b) * L0 + t) * kC0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int c = 2 * lane + 64 * i;
-          const float2 v = gelu_erf2(make_float2((acc[tt][2 * i] - mean) * rstd * g_s[c] + be_s[c],
-                                                 (acc[tt][2 * i + 1] - mean) * rstd * g_s[c + 1] + be_s[c + 1]));
+          const float2 g2 = *reinterpret_cast<const float2*>(&g_s[c]);
+          const float2 be2 = *reinterpret_cast<const float2*>(&be_s[c]);
+          const float2 v = gelu_erf2(f2_fma(acc[tt][i], f2_mul(g2, rstd), be2));
           *reinterpret_cast<uint32_t*>(dst + c) = pack_bf16x2(v.x, v.y);
         }
       } else {
@@ -217,11 +217,11 @@ __global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ x,
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int c = 2 * lane + 64 * i;
-          *reinterpret_cast<float2*>(dst + c) = make_float2(acc[tt][2 * i], acc[tt][2 * i + 1]);
-          gsum[2 * i] += acc[tt][2 * i];
-          gsum[2 * i + 1] += acc[tt][2 * i + 1];
-          gsq[2 * i] += static_cast<double>(acc[tt][2 * i]) * acc[tt][2 * i];
-          gsq[2 * i + 1] += static_cast<double>(acc[tt][2 * i + 1]) * acc[tt][2 * i + 1];
+          *reinterpret_cast<float2*>(dst + c) = acc[tt][i];
+          gsum[2 * i] += acc[tt][i].x;
+          gsum[2 * i + 1] += acc[tt][i].y;
+          gsq[2 * i] += static_cast<double>(acc[tt][i].x) * acc[tt][i].x;
+          gsq[2 * i + 1] += static_cast<double>(acc[tt][i].y) * acc[tt][i].y;
         }
       }
     }
@@ -287,7 +287,10 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const TIn* __restri
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  float v[kPer];
+  // The row lives in registers as fp32 PAIRS and every per-element step is one packed instruction per pair (add / fma / mul
+  // .f32x2): with the GELU these rows are bound by issue slots, not by HBM (profiles/r02_gelu.md), and statistics +
+  // normalisation were 6 scalar instructions per element against 2.5 this way.
+  float2 v[kPer / 2];
 #pragma unroll
   for (int c = 0; c < kChunks; ++c) {
     const int col = c * 256 + lane * kVec;
@@ -295,35 +298,28 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const TIn* __restri
       const uint4 u = *reinterpret_cast<const uint4*>(in + row * ld_in + col);
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __bfloat1622float2(h[i]);
-        v[c * kVec + 2 * i] = f.x;
-        v[c * kVec + 2 * i + 1] = f.y;
-      }
+      for (int i = 0; i < 4; ++i) v[c * 4 + i] = __bfloat1622float2(h[i]);
     } else {
       const float4 a = *reinterpret_cast<const float4*>(in + row * ld_in + col);
       const float4 b2 = *reinterpret_cast<const float4*>(in + row * ld_in + col + 4);
-      v[c * kVec + 0] = a.x;
-      v[c * kVec + 1] = a.y;
-      v[c * kVec + 2] = a.z;
-      v[c * kVec + 3] = a.w;
-      v[c * kVec + 4] = b2.x;
-      v[c * kVec + 5] = b2.y;
-      v[c * kVec + 6] = b2.z;
-      v[c * kVec + 7] = b2.w;
+      v[c * 4 + 0] = make_float2(a.x, a.y);
+      v[c * 4 + 1] = make_float2(a.z, a.w);
+      v[c * 4 + 2] = make_float2(b2.x, b2.y);
+      v[c * 4 + 3] = make_float2(b2.z, b2.w);
     }
   }
-  float s = 0.f;
+  float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int i = 0; i < kPer; ++i) s += v[i];
-  const float mean = warp_sum(s) * (1.0f / kCols);
-  float q = 0.f;
+  for (int i = 0; i < kPer / 2; ++i) s2 = f2_add(s2, v[i]);
+  const float mean = warp_sum(s2.x + s2.y) * (1.0f / kCols);
+  const float2 neg_mean = f2_splat(-mean);
+  float2 q2 = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int i = 0; i < kPer; ++i) {
-    const float d = v[i] - mean;
-    q = fmaf(d, d, q);
+  for (int i = 0; i < kPer / 2; ++i) {
+    v[i] = f2_add(v[i], neg_mean);  // centred from here on
+    q2 = f2_fma(v[i], v[i], q2);
   }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / kCols) + eps);
+  const float2 rstd = f2_splat(rsqrtf(warp_sum(q2.x + q2.y) * (1.0f / kCols) + eps));
 #pragma unroll
   for (int c = 0; c < kChunks; ++c) {
     const int col = c * 256 + lane * kVec;
@@ -331,30 +327,26 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const TIn* __restri
     const float4 g1 = *reinterpret_cast<const float4*>(gamma + col + 4);
     const float4 b0 = *reinterpret_cast<const float4*>(beta + col);
     const float4 b1 = *reinterpret_cast<const float4*>(beta + col + 4);
-    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    float o[8];
+    const float2 g[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
+    const float2 be[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+    float2 o[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = (v[c * kVec + i] - mean) * rstd * g[i] + be[i];
+    for (int i = 0; i < 4; ++i) o[i] = f2_fma(v[c * 4 + i], f2_mul(g[i], rstd), be[i]);
     if (gelu) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 a = gelu_erf2(make_float2(o[2 * i], o[2 * i + 1]));
-        o[2 * i] = a.x;
-        o[2 * i + 1] = a.y;
-      }
+      for (int i = 0; i < 4; ++i) o[i] = gelu_erf2(o[i]);
     }
     if (out_bf16) {
       uint4 u;
-      u.x = pack_bf16x2(o[0], o[1]);
-      u.y = pack_bf16x2(o[2], o[3]);
-      u.z = pack_bf16x2(o[4], o[5]);
-      u.w = pack_bf16x2(o[6], o[7]);
+      u.x = pack_bf16x2(o[0].x, o[0].y);
+      u.y = pack_bf16x2(o[1].x, o[1].y);
+      u.z = pack_bf16x2(o[2].x, o[2].y);
+      u.w = pack_bf16x2(o[3].x, o[3].y);
       *reinterpret_cast<uint4*>(out_bf16 + row * ld_bf16 + col) = u;
     }
     if (out_f32) {
-      *reinterpret_cast<float4*>(out_f32 + row * ld_f32 + col) = make_float4(o[0], o[1], o[2], o[3]);
-      *reinterpret_cast<float4*>(out_f32 + row * ld_f32 + col + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      *reinterpret_cast<float4*>(out_f32 + row * ld_f32 + col) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+      *reinterpret_cast<float4*>(out_f32 + row * ld_f32 + col + 4) = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
     }
   }
 }

@@ -269,7 +269,7 @@ def test_cuda_graph_predict_equals_eager(case):
     original = parameter.detach().clone()
     try:
         with torch.no_grad():
-            parameter.add_(0.5)
+            parameter[::2].add_(0.5)  # (not a constant over the channels: the final LayerNorm removes a uniform shift exactly)
         eager = estimator.predict(batch, tfi)
         graphed = estimator.predict(batch, tfi, cuda_graph=True)
         assert not torch.equal(eager.outputs["phoneme"], kept)
