@@ -185,32 +185,60 @@ __global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ x,
         for (int i = 0; i < 8; ++i) acc[tt][i] = f2_fma(wv[i], xs, acc[tt][i]);
       }
     }
+    if (kLayerNorm) {
+      // statistics of the kTT frames side by side: the 2 x kTT warp reductions are independent dependency chains (five
+      // shuffle + add steps each), kept apart by a per-frame early exit they ran one after the other
+      float mean[kTT], rstd[kTT];
 #pragma unroll
-    for (int tt = 0; tt < kTT; ++tt) {
-      const int t = t0 + tt;
-      if (t >= L0) break;  // warp-uniform
-      if (kLayerNorm) {
+      for (int tt = 0; tt < kTT; ++tt) {
         float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) s2 = f2_add(s2, acc[tt][i]);
-        const float mean = warp_sum(s2.x + s2.y) * (1.0f / kC0);
-        const float2 neg_mean = f2_splat(-mean);
+        mean[tt] = s2.x + s2.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int tt = 0; tt < kTT; ++tt) mean[tt] += __shfl_xor_sync(0xffffffffu, mean[tt], o);
+      }
+#pragma unroll
+      for (int tt = 0; tt < kTT; ++tt) {
+        const float2 neg_mean = f2_splat(-mean[tt] * (1.0f / kC0));
         float2 q2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           acc[tt][i] = f2_add(acc[tt][i], neg_mean);
           q2 = f2_fma(acc[tt][i], acc[tt][i], q2);
         }
-        const float2 rstd = f2_splat(rsqrtf(warp_sum(q2.x + q2.y) * (1.0f / kC0) + eps));
+        rstd[tt] = q2.x + q2.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int tt = 0; tt < kTT; ++tt) rstd[tt] += __shfl_xor_sync(0xffffffffu, rstd[tt], o);
+      }
+#pragma unroll
+      for (int tt = 0; tt < kTT; ++tt) {
+        const int t = t0 + tt;
+        if (t >= L0) break;  // warp-uniform
+        const float2 r2 = f2_splat(rsqrtf(rstd[tt] * (1.0f / kC0) + eps));
         __nv_bfloat16* dst = out + (static_cast<long long>(b) * L0 + t) * kC0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int c = 2 * lane + 64 * i;
           const float2 g2 = *reinterpret_cast<const float2*>(&g_s[c]);
           const float2 be2 = *reinterpret_cast<const float2*>(&be_s[c]);
-          const float2 v = gelu_erf2(f2_fma(acc[tt][i], f2_mul(g2, rstd), be2));
+          const float2 v = gelu_erf2(f2_fma(acc[tt][i], f2_mul(g2, r2), be2));
           *reinterpret_cast<uint32_t*>(dst + c) = pack_bf16x2(v.x, v.y);
         }
+      }
+    }
+#pragma unroll
+    for (int tt = 0; tt < kTT; ++tt) {
+      const int t = t0 + tt;
+      if (t >= L0) break;  // warp-uniform
+      if (kLayerNorm) {
+        break;
       } else {
         // GroupNorm(512 groups): statistics run over the whole (padded) time axis per channel
         float* dst = raw_out + (static_cast<long long>(b) * L0 + t) * kC0;
