@@ -45,6 +45,8 @@ namespace aph {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
+constexpr int kTapsPerStage = 4;  // sliding-window TAPS mode: B tiles (taps) per ring stage
+constexpr int kWinStages = 6;     // ... and ring stages (two 24 KB windows + 6 x 16 KB fit the 160 KB of the 64-column configuration)
 constexpr int kGemmThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kSmemBudget = 200 * 1024;
 
@@ -107,6 +109,9 @@ struct GemmParams {
   int total_work;           // work items of the launch (tiles x split_k, or full-wave tiles + 2 x tail tiles)
   int tail_first;           // first work item of the tail (== total_work: no tail split)
   uint32_t idesc_narrow;    // instruction descriptor of the half-width UMMA (N = BN / 2)
+  // ---- TAPS with a sliding A window (positional conv): see the producer
+  int taps_window;          // taps served by one A window (0: one A tile per tap)
+  int win_bytes;            // (taps_window + 128) rows x 128 B
 };
 
 // Work item -> (n block, m pair, output batch, k-block range, B row shift)
@@ -194,7 +199,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                      const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_resid,
                      const __grid_constant__ CUtensorMap tm_copy, const __grid_constant__ CUtensorMap tm_b_narrow,
-                     const GemmParams p) {
+                     const __grid_constant__ CUtensorMap tm_a_win, const GemmParams p) {
   using Cfg = GemmCfg<BN, EPI>;
   constexpr int kStages = Cfg::kStages;
 
@@ -211,7 +216,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* resid_bar = tempty_bar + 2;  // [8] one per epilogue warp (TMA-residual variant)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resid_bar + 8);
+  uint64_t* awin_full = resid_bar + 8;   // [2] A windows of the sliding-window TAPS mode
+  uint64_t* awin_empty = awin_full + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(awin_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -237,6 +244,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
       mbar_init(&tempty_bar[s], 16);  // leader's copy: one arrival per epilogue warp of both CTAs
     }
     for (int s = 0; s < 8; ++s) mbar_init(&resid_bar[s], 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&awin_full[s], 2);
+      mbar_init(&awin_empty[s], 1);
+    }
+    if (p.taps_window > 0) tma_prefetch_desc(&tm_a_win);
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
@@ -262,6 +274,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     {
       int stage = 0;
       uint32_t phase = 0;
+      int wbuf = 0;
+      uint32_t wphase = 0;
       for (int work = cluster_id; work < total_work; work += n_clusters) {
         const WorkItem w = decode_work(p, work, m_pairs);
         const int n_blk = w.n_blk;
@@ -269,6 +283,51 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
         if (mt >= tiles_m) mt = tiles_m - 1;  // odd tile count: the idle CTA still feeds the shared B half
         const int b = mt / p.m_tiles_per_batch;
         const int t0 = (mt % p.m_tiles_per_batch) * kBM;
+        if (p.taps_window > 0) {
+          // Sliding A window (grouped positional conv, one 64-channel group per N tile): tap j reads rows t0 - pad + j .. + 127 of
+          // the group's channels, so consecutive taps overlap in 127 of 128 rows.  ONE window of W + 127 rows serves W taps — the
+          // MMA issuer moves the A descriptor's start address down one 128-byte row per tap (the 128B swizzle is a function of
+          // the absolute shared-memory address, so a row-shifted descriptor reads what TMA wrote: tools/micro/umma_rowshift.cu) —
+          // and only the B tile (4 KB per CTA) still moves per tap.  One 16 KB A tile per tap was 160 B/clk/SM of L2 traffic for
+          // 128 cycles of tensor work: the kernel ran at 0.3 of the tensor peak (profiles/r02_posconv_window.md).
+          const int W = p.taps_window;
+          uint8_t* b_ring = smem + 2 * p.win_bytes;
+          for (int c = 0; c * W < p.k_blocks; ++c) {
+            mbar_wait(&awin_empty[wbuf], wphase ^ 1);
+            if (elect_one()) {
+              if (cta_rank == 0) {
+                mbar_arrive_expect_tx(&awin_full[wbuf], static_cast<uint32_t>(p.win_bytes));
+              } else {
+                mbar_arrive_expect_tx_remote(&awin_full[wbuf], 0, static_cast<uint32_t>(p.win_bytes));
+              }
+              tma_load_3d_pair(smem + wbuf * p.win_bytes, &tm_a_win, &awin_full[wbuf], n_blk * kBK, t0 - p.tap_pad + c * W, b);
+            }
+            __syncwarp();
+            wbuf ^= 1;
+            if (wbuf == 0) wphase ^= 1;
+            for (int jl = 0; jl < W; jl += kTapsPerStage) {  // a ring stage holds the B tiles of kTapsPerStage taps
+              const int kb = c * W + jl;
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              if (elect_one()) {
+                if (cta_rank == 0) {
+                  mbar_arrive_expect_tx(&full_bar[stage], kTapsPerStage * Cfg::kBBytes);
+                } else {
+                  mbar_arrive_expect_tx_remote(&full_bar[stage], 0, kTapsPerStage * Cfg::kBBytes);
+                }
+#pragma unroll
+                for (int g = 0; g < kTapsPerStage; ++g)
+                  tma_load_2d_pair(b_ring + (stage * kTapsPerStage + g) * Cfg::kBBytes, &tm_b, &full_bar[stage], (kb + g) * kBK,
+                                   n_blk * BN + cta_rank * (BN / 2));
+              }
+              __syncwarp();
+              if (++stage == kWinStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+          continue;
+        }
         for (int kb = w.kb_lo; kb < w.kb_hi; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
@@ -337,12 +396,52 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int wbuf = 0;
+      uint32_t wphase = 0;
       for (int work = cluster_id; work < total_work; work += n_clusters) {
         const WorkItem w = decode_work(p, work, m_pairs);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
         const uint32_t item_idesc = w.narrow != 0 ? p.idesc_narrow : idesc;
+        if (p.taps_window > 0) {  // sliding A window: see the producer
+          const int W = p.taps_window;
+          const uint32_t b_ring = smem_u32(smem + 2 * p.win_bytes);
+          for (int c = 0; c * W < p.k_blocks; ++c) {
+            mbar_wait(&awin_full[wbuf], wphase);
+            tc_fence_after();
+            const uint32_t win = smem_u32(smem + wbuf * p.win_bytes);
+            for (int jl = 0; jl < W; jl += kTapsPerStage) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint64_t da = umma_desc_sw128(win + static_cast<uint32_t>(jl) * 128u);
+              const uint64_t db = umma_desc_sw128(b_ring + static_cast<uint32_t>(stage * kTapsPerStage) * Cfg::kBBytes);
+              if (elect_one()) {
+#pragma unroll
+                for (int g = 0; g < kTapsPerStage; ++g) {  // next tap: A one row (8 x 16 B) down, B one tile on
+#pragma unroll
+                  for (int k = 0; k < kBK / 16; ++k)
+                    umma_bf16_pair(tmem_d, da + static_cast<uint64_t>(8 * g + 2 * k), db + static_cast<uint64_t>(g * (Cfg::kBBytes >> 4) + 2 * k), idesc,
+                                   (c | jl | g | k) != 0 ? 1u : 0u);
+                }
+                umma_commit_pair(&empty_bar[stage], static_cast<uint16_t>(3));
+                if (jl + kTapsPerStage >= W) umma_commit_pair(&awin_empty[wbuf], static_cast<uint16_t>(3));  // the window is free in both CTAs
+              }
+              __syncwarp();
+              if (++stage == kWinStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+            wbuf ^= 1;
+            if (wbuf == 0) wphase ^= 1;
+          }
+          if (elect_one()) umma_commit_pair(&tfull_bar[acc], static_cast<uint16_t>(3));
+          __syncwarp();
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+          continue;
+        }
         for (int kb = w.kb_lo; kb < w.kb_hi; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -825,6 +924,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
   }
 }
 
+static bool taps_window_enabled() {
+  static const bool enabled = [] {
+    const char* e = getenv("APH_TAPS_WINDOW");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return enabled;
+}
+
 template <int BN, int EPI>
 static int launch_gemm(const aph_gemm_args* a, GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, EPI>;
@@ -976,9 +1083,30 @@ static int launch_gemm(const aph_gemm_args* a, GemmParams& p, cudaStream_t strea
       total_work = full + 2 * rest;
     }
   }
+  // sliding A window for the tap GEMM over 64-channel groups (see the producer)
+  CUtensorMap tm_a_win;
+  memset(&tm_a_win, 0, sizeof(tm_a_win));
+  p.taps_window = 0;
+  p.win_bytes = 0;
+  if (BN == 64 && a->mode == APH_GEMM_TAPS && p.taps_span == 64 && !p.a_mn && !p.b_mn && p.split_k == 1 && taps_window_enabled()) {
+    const int window = p.k_blocks % 64 == 0 ? 64 : (p.k_blocks % 32 == 0 ? 32 : 0);
+    if (window > 0 && kWinStages <= Cfg::kStages && window % kTapsPerStage == 0 &&
+        2 * (window + 128) * 128 + kWinStages * kTapsPerStage * Cfg::kBBytes <= Cfg::kStages * Cfg::kStageBytes) {
+      const uint64_t inner = static_cast<uint64_t>(a->a_inner);
+      const uint64_t dims[3] = {inner, static_cast<uint64_t>(a->a_rows), static_cast<uint64_t>(a->batch)};
+      uint64_t batch_stride = static_cast<uint64_t>(a->a_batch_stride) * 2;
+      if (a->batch == 1 && batch_stride == 0) batch_stride = static_cast<uint64_t>(a->a_row_stride) * 2;
+      const uint64_t strides[2] = {static_cast<uint64_t>(a->a_row_stride) * 2, batch_stride};
+      const uint32_t box[3] = {kBK, static_cast<uint32_t>(window + 128), 1};
+      int rc = encode_tmap(&tm_a_win, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->a, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc != APH_OK) return rc;
+      p.taps_window = window;
+      p.win_bytes = (window + 128) * 128;
+    }
+  }
   p.total_work = total_work;
   const int grid = 2 * (total_work < max_clusters ? total_work : max_clusters);
-  APH_CUDA_CHECK(launch_pdl(gemm_bf16_kernel<BN, EPI>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tm_a, tm_b, tm_out, tm_resid, tm_copy, tm_b_narrow, p));
+  APH_CUDA_CHECK(launch_pdl(gemm_bf16_kernel<BN, EPI>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tm_a, tm_b, tm_out, tm_resid, tm_copy, tm_b_narrow, tm_a_win, p));
   APH_POST_LAUNCH(1);
   return APH_OK;
 }
