@@ -540,11 +540,12 @@ def run_gpu_arm(args) -> None:
             "unit": "TFLOP/s",
             "frac": achieved / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over one layer's QKV / out-proj / FFN1 /
-            # FFN2 launches of the `ncu --set full` capture in profiles/r01_ncu_summary.md (83.4 / 110.8 / 117.3 / 249.7 MB):
-            # equal to the algorithmic operand + residual bytes, i.e. no re-reads
-            "traffic": 140.3e6,
+            # FFN2 launches of the `ncu --set full` capture in profiles/r02_ncu_summary.md (89.9 / 118.1 / 124.3 / 263.5 MB: the
+            # plan now pads the batch to a 512-frame length bucket, round 1: 83.4 / 110.8 / 117.3 / 249.7): equal to the algorithmic
+            # operand + residual bytes, i.e. no re-reads
+            "traffic": 148.9e6,
             "traffic_unit": "bytes per launch",
-            "traffic_source": "constant from profiles/r01_ncu_summary.md (one `ncu --set full` capture of this step; not re-measured per run)",
+            "traffic_source": "constant from profiles/r02_ncu_summary.md (one `ncu --set full` capture of this step; not re-measured per run)",
             "peak_source": f"bf16_tflops_sustained, {peaks['source']}",
             "launches": len(encoder_gemms),
             "avg_launch_ms": gemm_ms / max(1, len(encoder_gemms)),
