@@ -212,6 +212,13 @@ __device__ __forceinline__ void bulk_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
 }
 
+// waits until this thread's bulk stores have completed (written, not only read)
+__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// named barrier among `threads` threads of the CTA (id 0 is __syncthreads)
+__device__ __forceinline__ void named_barrier_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 // ---- thread-block clusters -------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -492,6 +499,12 @@ __device__ __forceinline__ float2 f2_add(float2 a, float2 b) {
   return *reinterpret_cast<float2*>(&rd);
 }
 __device__ __forceinline__ float2 f2_splat(float v) { return make_float2(v, v); }
+// three-input maximum (one FMNMX3 on sm_100)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   const float2 s = make_float2(-fabsf(x.x), -fabsf(x.y));
   float2 p = f2_fma(f2_splat(kGeluK5), s, f2_splat(kGeluK4));
