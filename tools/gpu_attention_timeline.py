@@ -27,7 +27,18 @@ torch.cuda.synchronize()
 print(f"attention kernel: {start.elapsed_time(end) / 20 * 1000:.1f} us per launch")
 timeline = torch.zeros(192, device=DEV, dtype=torch.int64)
 _lib.check(_lib.lib.aph_debug_set_timeline(timeline.data_ptr()), "timeline")
-ops.attention(q, k, v, ctx, frames, n_utt, heads, seq)
+EXPERIMENT = int(os.environ.get("APH_ATT_EXPERIMENT", "0"))  # timeline builds: bit 0 PV cut, 1 scores cut, 2 no exponentials
+if EXPERIMENT:
+    import ctypes
+
+    _lib.check(
+        _lib.lib.aph_attention_bf16_dropout(
+            q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), None, frames.data_ptr(), n_utt, heads, seq, 0, EXPERIMENT, ctypes.c_float(1.0), None
+        ),
+        "attention",
+    )
+else:
+    ops.attention(q, k, v, ctx, frames, n_utt, heads, seq)
 torch.cuda.synchronize()
 stamps = timeline.tolist()
 base = stamps[0]
