@@ -630,10 +630,12 @@ __global__ void __launch_bounds__(kPairThreads, 1)
         tc_fence_after();
         APH_DSTAMP(items == 2 && (threadIdx.x & 127) == 0, 32 + t * 32 + j * 8 + 0);
         // The row's 128 scores pass through the registers 64 at a time (registers are allocated in units of four warps: the
-        // 11 warps of this CTA get 168 each, not enough for 128 scores next to the rest).  First the block maximum (keys
-        // 0-63, then 64-127), then the exponentials of keys 64-127, which are still there, then keys 0-63 again — TMEM reads are
-        // cheap, and the score buffer is released as soon as that last read has landed.
+        // 11 warps of this CTA get 168 each, not enough for 128 scores next to the rest): two online-softmax steps per block,
+        // keys 0-63 and keys 64-127, each with its own lazy-rescaling decision.  The probabilities of the first half wait in
+        // registers (32 of them, bf16 pairs); both halves go to the P columns at the end of the block, because the columns are
+        // still being read by the previous block's PV product, which then has the whole block to finish.
         float xa[32], xb[32];
+        uint32_t p_lo[32], p_hi[32];
         auto load_half = [&](int half) {
           tmem_ld32(tmem_s + static_cast<uint32_t>(64 * half), xa);
           tmem_ld32(tmem_s + static_cast<uint32_t>(64 * half + 32), xb);
@@ -647,48 +649,6 @@ __global__ void __launch_bounds__(kPairThreads, 1)
             }
           }
         };
-        auto half_max = [&]() -> float {
-          float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            mx0 = fmax3(mx0, xa[2 * i], xa[2 * i + 1]);
-            mx1 = fmax3(mx1, xb[2 * i], xb[2 * i + 1]);
-          }
-          return fmaxf(mx0, mx1);
-        };
-        load_half(0);
-        APH_DSTAMP(items == 2 && (threadIdx.x & 127) == 0, 32 + t * 32 + j * 8 + 5);
-        float m_blk = half_max();
-        if (two) {
-          load_half(1);
-          m_blk = fmaxf(m_blk, half_max());
-        }
-        APH_DSTAMP(items == 2 && (threadIdx.x & 127) == 0, 32 + t * 32 + j * 8 + 6);
-        // lazy rescaling: only when this row's maximum outgrows the reference by more than 2^8
-        const bool grow = m_blk > m_ref + kAttRescaleThreshold;  // always true for the first block (m_ref = -inf)
-        if (__any_sync(0xffffffffu, grow)) {
-          const float m_new = grow ? m_blk : m_ref;
-          const float alpha = ex2_approx(m_ref - m_new);  // 1 for rows that keep their reference, 0 for the first block
-          l_run *= alpha;
-          m_ref = m_new;
-          if (j > 0) {
-            // O_t <- O_t * alpha in TMEM; the previous PV product must have landed first (warp-collective ld/st).  The scores
-            // are read again afterwards instead of staying live across this.
-            mbar_wait(&pv_done[t], (blocks - 1u) & 1u);
-            tc_fence_after();
-#pragma unroll
-            for (int c0 = 0; c0 < kAttD; c0 += 32) {
-              float o[32];
-              tmem_ld32(tmem_o + static_cast<uint32_t>(c0), o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] *= alpha;
-              tmem_st32(tmem_o + static_cast<uint32_t>(c0), o);
-            }
-            tmem_st_wait();
-            load_half(two ? 1 : 0);
-          }
-        }
         // p = 2^(score - reference) in place; subtract and row sum as packed fp32 pairs (add.f32x2)
         auto exp_half = [&]() -> float {
           const float2 neg_ref = f2_splat(-m_ref);
@@ -715,11 +675,56 @@ __global__ void __launch_bounds__(kPairThreads, 1)
           }
           return (lsa.x + lsa.y) + (lsb.x + lsb.y);
         };
-        // exponentials, dropout of the (still unnormalised) probabilities — the row sum is taken before it, the 1/(1-p) scale
-        // is folded into the final normalisation — and the bf16 pairs into the tile's P columns (the A operand layout of the
-        // TS form)
-        auto finish_half = [&](int half, uint32_t* packed) -> float {
-          const float l_half = exp_half();
+        // One online-softmax step over the 64 scores in xa / xb.  `release`: these are the block's last scores, the score buffer
+        // is handed back once the (rare) re-read below can no longer happen.
+        auto softmax_half = [&](int half, uint32_t* packed, bool release) {
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            mx0 = fmax3(mx0, xa[2 * i], xa[2 * i + 1]);
+            mx1 = fmax3(mx1, xb[2 * i], xb[2 * i + 1]);
+          }
+          const float m_half = fmaxf(mx0, mx1);
+          // lazy rescaling: only when this row's maximum outgrows the reference by more than 2^8
+          const bool grow = m_half > m_ref + kAttRescaleThreshold;  // always true for an item's first scores (m_ref = -inf)
+          if (__any_sync(0xffffffffu, grow)) {
+            const float m_new = grow ? m_half : m_ref;
+            const float alpha = ex2_approx(m_ref - m_new);  // 1 for rows that keep their reference, 0 for the first scores
+            l_run *= alpha;
+            m_ref = m_new;
+            if (half == 1) {  // the first half's probabilities of this block are relative to the old reference
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float2 v = unpack_bf16x2(p_lo[i]);
+                p_lo[i] = pack_bf16x2(v.x * alpha, v.y * alpha);
+              }
+            }
+            if (j > 0) {
+              // O_t <- O_t * alpha in TMEM; the previous PV product must have landed first (warp-collective ld/st).  The scores
+              // are read again afterwards instead of staying live across this.
+              mbar_wait(&pv_done[t], (blocks - 1u) & 1u);
+              tc_fence_after();
+#pragma unroll
+              for (int c0 = 0; c0 < kAttD; c0 += 32) {
+                float o[32];
+                tmem_ld32(tmem_o + static_cast<uint32_t>(c0), o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] *= alpha;
+                tmem_st32(tmem_o + static_cast<uint32_t>(c0), o);
+              }
+              tmem_st_wait();
+              load_half(half);
+            }
+          }
+          if (release) {
+            tc_fence_before();
+            mbar_arrive(&s_read[t]);  // every score of the block has been read: the buffer may take the next block
+            APH_DSTAMP(items == 2 && (threadIdx.x & 127) == 0, 32 + t * 32 + j * 8 + 1);
+          }
+          // exponentials, dropout of the (still unnormalised) probabilities — the row sum is taken before it, the 1/(1-p) scale
+          // is folded into the final normalisation — and the bf16 pairs (the A operand layout of the TS form)
+          l_run += exp_half();
           if constexpr (kDrop) {
             const uint32_t key = drop_row_key(p.drop_seed, static_cast<uint32_t>(bh) * static_cast<uint32_t>(p.T) + static_cast<uint32_t>(q0 + r));
             const uint32_t pair0 = static_cast<uint32_t>((key0 >> 1) + 32 * half);
@@ -738,23 +743,15 @@ __global__ void __launch_bounds__(kPairThreads, 1)
             packed[i] = pack_bf16x2(xa[2 * i], xa[2 * i + 1]);
             packed[16 + i] = pack_bf16x2(xb[2 * i], xb[2 * i + 1]);
           }
-          return l_half;
         };
-        // The probabilities of keys 64-127 wait in registers (32 of them) while keys 0-63 are redone, and both halves go to the
-        // P columns at the end of the block: the columns are still being read by the previous block's PV product, which has
-        // the whole block to finish.
-        uint32_t p_hi[32], p_lo[32];
-        float l_blk = 0.f;
+        load_half(0);
+        APH_DSTAMP(items == 2 && (threadIdx.x & 127) == 0, 32 + t * 32 + j * 8 + 5);
+        softmax_half(0, p_lo, !two);
+        APH_DSTAMP(items == 2 && (threadIdx.x & 127) == 0, 32 + t * 32 + j * 8 + 2);
         if (two) {
-          l_blk = finish_half(1, p_hi);
-          APH_DSTAMP(items == 2 && (threadIdx.x & 127) == 0, 32 + t * 32 + j * 8 + 2);
-          load_half(0);
+          load_half(1);
+          softmax_half(1, p_hi, true);
         }
-        tc_fence_before();
-        mbar_arrive(&s_read[t]);  // every score of the block has been read: the buffer may take the next block
-        APH_DSTAMP(items == 2 && (threadIdx.x & 127) == 0, 32 + t * 32 + j * 8 + 1);
-        l_blk += finish_half(0, p_lo);
-        l_run += l_blk;
         // (within an item; the item's first block follows the epilogue's wait for the previous item's last product)
         if (j > 0) mbar_wait(&pv_done[t], (blocks - 1u) & 1u);
         APH_DSTAMP(items == 2 && (threadIdx.x & 127) == 0, 32 + t * 32 + j * 8 + 7);
