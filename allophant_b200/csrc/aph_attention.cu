@@ -396,6 +396,29 @@ constexpr int kPairQBytes = 2 * kAttQ * kAttD * 2;  // 32 KB: both query tiles, 
 constexpr int kPairKVBytes = kPairKV * kAttD * 2;   // 16 KB
 constexpr int kPairSmemBytes = 2 * kPairQBytes + 2 * kPairStages * kPairKVBytes + 2 * kAttQ * kAttD * 2 /*output staging*/ + 256;
 constexpr uint32_t kPairTmemCols = 512;
+#ifndef APH_ATT_POLY_EVERY
+#define APH_ATT_POLY_EVERY 0
+#endif
+constexpr int kPolyEvery = APH_ATT_POLY_EVERY;  // one exponential pair in this many on the FMA pipe; 0 = none (4: 63.8 -> 67.3 us, profiles/r02_attention_experiments.md)
+
+// 2^x for a pair of scores on the FMA / ALU pipes instead of the MUFU pipe (Cody-Waite: x = n + f with |f| <= 1/2 through the
+// 1.5 * 2^23 rounding constant, a degree-3 fit of 2^f with 7.5e-5 relative error — P is rounded to bf16 afterwards — and n added
+// into the exponent field).  Valid for -125 <= x < 128; anything below gives exactly 0 (masked keys are -inf).
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  const float2 xc = make_float2(fmaxf(x.x, -125.f), fmaxf(x.y, -125.f));
+  const float2 t = f2_add(xc, f2_splat(12582912.f));
+  const float2 n = f2_add(t, f2_splat(-12582912.f));
+  const float2 f = f2_fma(n, f2_splat(-1.f), xc);
+  float2 q = f2_fma(f2_splat(0.05517165f), f, f2_splat(0.24261113f));
+  q = f2_fma(q, f, f2_splat(0.69326097f));
+  q = f2_fma(q, f, f2_splat(0.99992806f));
+  float2 y;
+  y.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
+  y.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
+  y.x = x.x < -125.f ? 0.f : y.x;
+  y.y = x.y < -125.f ? 0.f : y.y;
+  return y;
+}
 
 template <bool kDrop>
 __global__ void __launch_bounds__(kPairThreads, 1)
@@ -664,8 +687,10 @@ __global__ void __launch_bounds__(kPairThreads, 1)
               continue;
             }
 #endif
-            const float2 pa = make_float2(ex2_approx(da.x), ex2_approx(da.y));
-            const float2 pb = make_float2(ex2_approx(db.x), ex2_approx(db.y));
+            // one pair in kPolyEvery leaves the MUFU pipe (the exponentials are MUFU-bound while both tiles' warps are in them)
+            const bool poly = kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == (kPolyEvery - 1);
+            const float2 pa = poly ? ex2_poly2(da) : make_float2(ex2_approx(da.x), ex2_approx(da.y));
+            const float2 pb = poly ? ex2_poly2(db) : make_float2(ex2_approx(db.x), ex2_approx(db.y));
             xa[2 * i] = pa.x;
             xa[2 * i + 1] = pa.y;
             xb[2 * i] = pb.x;
