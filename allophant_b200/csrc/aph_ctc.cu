@@ -6,6 +6,9 @@
 //   (loss_functions.py:19-27, called per head at estimator.py:721-734 / 645-650)
 // and its autograd backward (estimator.py:738).
 //
+// Two sets of recursion kernels.  While all (utterance, head) pairs fit the GPU at two blocks per SM (a training step:
+// 37 heads x 8 utterances) a BLOCK owns a pair, one state per thread (ctc_pair_* further down); beyond that — and with
+// APH_CTC_V1=1 — the warp kernels below:
 // One warp owns one (utterance, head) pair and walks time sequentially in log
 // space.  The 2S+1 CTC states are distributed over the lanes in contiguous
 // chunks of K states (K = 2..32 by template), so only two values cross lanes
@@ -680,6 +683,305 @@ __global__ void __launch_bounds__(kCtcLongThreads) ctc_long_beta_kernel(const __
   }
 }
 
+// ---------------------------------------------------------------------------
+// Block-per-pair recursions (the default for label sequences up to 511): one block per (utterance, head), ONE STATE PER
+// THREAD, two rows in shared memory, one block barrier per frame.  The warp-per-pair kernels above walk K = 10 states per
+// lane in series on a warp that is alone on its scheduler (~1 000 cycles per frame, profiles/r02_ctc_recursion.md); here a
+// frame is one log-sum-exp of three values per thread, ~10 warps per block and two to three blocks per SM.
+//   alpha kernel: alpha rows [t][s] (log2 domain, natural state order) into the workspace, nll per pair;
+//   beta kernel:  beta recursion; OVERWRITES alpha_t(s) with the state occupancy exp(alpha + beta - lp + nll);
+//   grad kernel:  parallel over (pair, 48-frame chunk): the occupancies of a frame are summed per class (the states are
+//                 visited in class order: a warp-segmented shuffle scan plus one shared-memory atomic per class and warp)
+//                 and the gradient row g * (softmax - occupancy sums) is written (narrow heads: the whole row; wide heads:
+//                 the label columns of the row ctc_grad_init_kernel wrote).
+// Nothing in the time loop of the two recursions depends on the number of classes.
+// ---------------------------------------------------------------------------
+constexpr int kCtcGradChunk = 48;    // frames per block of the gradient kernel (the class-order setup is O(states^2) per block)
+constexpr int kCtcAhead = 8;  // frames per group of emission / alpha loads (even)
+
+__device__ __forceinline__ int pair_symbol(const PairInfo& p, int s, int S2, bool& bad) {
+  if (s >= S2 || !(s & 1)) return 0;
+  int l = static_cast<int>(p.labels[s >> 1]);
+  if (l < 0 || l >= p.c) {  // a label outside the head's classes: the loss is NaN (see the warp kernels)
+    bad = true;
+    l = 0;
+  }
+  return l;
+}
+
+// Emissions (and, backwards, alpha values) reach a thread kCtcAhead frames at a time: the loads of the NEXT group are issued
+// at the top of a group and consumed a whole group (~2 800 cycles) later.  A rolling one-load-per-frame prefetch does not work:
+// the wait on the oldest load is a wait on a scoreboard the newer loads share (ncu: a third of all warp samples on the first
+// use of a value requested four frames earlier).
+__global__ void __launch_bounds__(1024) ctc_pair_alpha_kernel(const __grid_constant__ CtcHeadPack heads, int n_heads, int n_utt, int T,
+                                                              const long long* __restrict__ input_lengths,
+                                                              float* __restrict__ alpha_ws, float* __restrict__ nll_out) {
+  extern __shared__ float pair_smem[];  // two rows of blockDim.x + 2 floats (two -inf guards in front of state 0)
+  __shared__ int any_bad;
+  const int pair = blockIdx.x;
+  const int h = pair / n_utt, n = pair - h * n_utt;
+  const int s = threadIdx.x;
+  const int threads = static_cast<int>(blockDim.x);
+  PairInfo p;
+  load_pair(heads, h, n, n_utt, T, input_lengths, alpha_ws, p);
+  const int S2 = 2 * p.S + 1;
+  float* out = nll_out + static_cast<long long>(h) * n_utt + n;
+  if (S2 > threads || p.S > heads.h[h].label_stride || (p.alpha != nullptr && p.s_pad != threads)) {
+    if (s == 0) *out = NAN;  // the host guarantees this never happens
+    return;
+  }
+  if (p.T_in == 0) {
+    if (s == 0) *out = p.S == 0 ? 0.f : INFINITY;
+    return;
+  }
+  if (s == 0) any_bad = 0;
+  __syncthreads();
+  bool bad = false;
+  const int sym = pair_symbol(p, s, S2, bad);
+  const bool live = s < S2;
+  const bool skip = (s & 1) && s >= 3 && live && sym != static_cast<int>(p.labels[(s >> 1) - 1]);  // transition s-2 -> s
+  const int row_len = threads + 2;
+  float* const row_even = pair_smem + 2;  // frame parity 0 / 1 (no pointer array: it would live in local memory)
+  float* const row_odd = pair_smem + row_len + 2;
+  if (s < 2) {
+    pair_smem[s] = -INFINITY;
+    pair_smem[row_len + s] = -INFINITY;
+  }
+  const long long stride_t = p.stride_t;
+  const int T_in = p.T_in;
+  const float* lp = p.lp + sym;
+  float* alpha_out = (p.alpha != nullptr && live) ? p.alpha + s : nullptr;
+  float a = (live && s < 2) ? __ldg(lp) * kLog2E : -INFINITY;
+  bad = bad || a != a;
+  row_even[s] = a;
+  if (alpha_out != nullptr) *alpha_out = a;
+  float e_next[kCtcAhead];
+#pragma unroll
+  for (int j = 0; j < kCtcAhead; ++j) e_next[j] = (live && 1 + j < T_in) ? __ldg(lp + static_cast<long long>(1 + j) * stride_t) : 0.f;
+  __syncthreads();
+  for (int tb = 1; tb < T_in; tb += kCtcAhead) {  // kCtcAhead is even: frame tb + j has the parity of 1 + j
+    float e_cur[kCtcAhead];
+#pragma unroll
+    for (int j = 0; j < kCtcAhead; ++j) e_cur[j] = e_next[j] * kLog2E;
+#pragma unroll
+    for (int j = 0; j < kCtcAhead; ++j) {
+      const int t = tb + kCtcAhead + j;
+      e_next[j] = (live && t < T_in) ? __ldg(lp + static_cast<long long>(t) * stride_t) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < kCtcAhead; ++j) {
+      const int t = tb + j;
+      if (t < T_in) {  // block-uniform
+        const float e = e_cur[j];
+        bad = bad || (live && e != e);  // fmaxf drops NaNs: a diverged frame is remembered where its log-probabilities are used
+        const float* prev = (j & 1) ? row_odd : row_even;  // frame t - 1
+        float* cur = (j & 1) ? row_even : row_odd;
+        const float a1 = prev[s - 1];
+        const float a2 = skip ? prev[s - 2] : -INFINITY;
+        a = live ? lse3(a, a1, a2) + e : -INFINITY;
+        cur[s] = a;
+        if (alpha_out != nullptr) alpha_out[static_cast<long long>(t) * threads] = a;
+        __syncthreads();
+      }
+    }
+  }
+  if (bad) any_bad = 1;
+  __syncthreads();
+  if (s == 0) {
+    const float* last = ((T_in - 1) & 1) ? row_odd : row_even;
+    const float last1 = last[S2 - 1];
+    const float last2 = S2 >= 2 ? last[S2 - 2] : -INFINITY;
+    // (fmaxf would drop a NaN: the diverged loss must stay NaN, not become +inf and be zeroed)
+    *out = (any_bad || last1 != last1 || last2 != last2) ? NAN : -lse2(last1, last2) * kLn2;  // natural units
+  }
+}
+
+__global__ void __launch_bounds__(1024) ctc_pair_beta_kernel(const __grid_constant__ CtcHeadPack heads, int n_heads, int n_utt, int T,
+                                                             const long long* __restrict__ input_lengths, float* __restrict__ alpha_ws,
+                                                             const float* __restrict__ nll_in) {
+  extern __shared__ float pair_smem[];  // two rows of blockDim.x + 2 floats (two -inf guards behind the last state)
+  const int pair = blockIdx.x;
+  const int h = pair / n_utt, n = pair - h * n_utt;
+  const int s = threadIdx.x;
+  const int threads = static_cast<int>(blockDim.x);
+  PairInfo p;
+  load_pair(heads, h, n, n_utt, T, input_lengths, alpha_ws, p);
+  if (p.grad == nullptr) return;
+  const int S2 = 2 * p.S + 1;
+  const float nll = nll_in[static_cast<long long>(h) * n_utt + n];
+  // an infinite loss has zero gradient (zero_infinity), a NaN loss a NaN gradient: the gradient kernel writes both
+  if (!(nll < INFINITY) || S2 > threads || p.s_pad != threads || p.T_in == 0) return;
+  const float nll2 = nll * kLog2E;
+  bool bad = false;
+  const int sym = pair_symbol(p, s, S2, bad);
+  const bool live = s < S2;
+  const bool skip = (s & 1) && s + 2 < S2 && sym != static_cast<int>(p.labels[(s >> 1) + 1]);  // transition s -> s+2
+  const int row_len = threads + 2;
+  if (s < 2) {
+    pair_smem[threads + s] = -INFINITY;
+    pair_smem[row_len + threads + s] = -INFINITY;
+  }
+  const long long stride_t = p.stride_t;
+  const int t_last = p.T_in - 1;
+  const float* lp = p.lp + sym;
+  float* const alpha_io = p.alpha + s;
+  float e_next[kCtcAhead], a_next[kCtcAhead];
+#pragma unroll
+  for (int j = 0; j < kCtcAhead; ++j) {
+    const int t = t_last - j;
+    e_next[j] = (live && t >= 0) ? __ldg(lp + static_cast<long long>(t) * stride_t) : 0.f;
+    a_next[j] = (live && t >= 0) ? alpha_io[static_cast<long long>(t) * threads] : -INFINITY;
+  }
+  float b = -INFINITY;
+  for (int tb = t_last; tb >= 0; tb -= kCtcAhead) {
+    float e_cur[kCtcAhead], a_cur[kCtcAhead];
+#pragma unroll
+    for (int j = 0; j < kCtcAhead; ++j) {
+      e_cur[j] = e_next[j] * kLog2E;
+      a_cur[j] = a_next[j];
+    }
+#pragma unroll
+    for (int j = 0; j < kCtcAhead; ++j) {
+      const int t = tb - kCtcAhead - j;
+      e_next[j] = (live && t >= 0) ? __ldg(lp + static_cast<long long>(t) * stride_t) : 0.f;
+      a_next[j] = (live && t >= 0) ? alpha_io[static_cast<long long>(t) * threads] : -INFINITY;
+    }
+#pragma unroll
+    for (int j = 0; j < kCtcAhead; ++j) {
+      const int t = tb - j;
+      if (t >= 0) {  // block-uniform
+        const float e = e_cur[j];
+        float* cur = pair_smem + (t & 1) * row_len;
+        if (t == t_last) {
+          b = (live && s >= S2 - 2) ? e : -INFINITY;
+        } else {
+          const float* next = pair_smem + ((t + 1) & 1) * row_len;
+          const float b1 = next[s + 1];
+          const float b2 = skip ? next[s + 2] : -INFINITY;
+          b = live ? lse3(b, b1, b2) + e : -INFINITY;
+        }
+        cur[s] = b;
+        // the occupancy of state s at frame t replaces alpha_t(s): exp(alpha + beta - lp + nll), 0 for unreachable states
+        if (live) alpha_io[static_cast<long long>(t) * threads] = ex2a(a_cur[j] + b - e + nll2);
+        __syncthreads();
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024) ctc_pair_grad_kernel(const __grid_constant__ CtcHeadPack heads, int n_heads, int n_utt, int T,
+                                                             const long long* __restrict__ input_lengths, const float* __restrict__ occ_ws,
+                                                             const float* __restrict__ nll_in, const float* __restrict__ grad_scale) {
+  extern __shared__ float pair_smem[];  // occupancies in class order [blockDim.x] | keys in class order [blockDim.x] | class sums [c]
+  const int pair = blockIdx.y;
+  const int h = pair / n_utt, n = pair - h * n_utt;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int threads = static_cast<int>(blockDim.x);
+  PairInfo p;
+  load_pair(heads, h, n, n_utt, T, input_lengths, const_cast<float*>(occ_ws), p);
+  if (p.grad == nullptr) return;
+  const int S2 = 2 * p.S + 1;
+  const float nll = nll_in[static_cast<long long>(h) * n_utt + n];
+  const float g = grad_scale ? grad_scale[h] : 1.f;
+  const bool narrow = p.c <= kCtcSmallC;  // the whole gradient row is written here; wide rows start from ctc_grad_init_kernel
+  const bool poisoned = nll != nll;
+  const bool dead = !(nll < INFINITY) || S2 > threads || p.s_pad != threads;
+  const int t0 = blockIdx.x * kCtcGradChunk;
+  const int t1 = min(T, t0 + kCtcGradChunk);
+  const int t_live = dead ? 0 : p.T_in;
+  if (narrow) {  // frames past the utterance and every frame of a zeroed loss: zero gradient; NaN loss: NaN on its valid frames
+    for (int t = max(t0, t_live); t < t1; ++t)
+      if (tid < p.c) p.grad[static_cast<long long>(t) * p.stride_t + tid] = (poisoned && t < p.T_in) ? NAN : 0.f;
+  }
+  if (t0 >= t_live) return;
+  float* occ_sm = pair_smem;
+  int* key_sm = reinterpret_cast<int*>(pair_smem + threads);
+  float* class_sum = pair_smem + 2 * threads;
+  // states in class order: position = number of states with a smaller (class, state) key; padding threads sort last
+  bool bad = false;
+  const int key = tid < S2 ? pair_symbol(p, tid, S2, bad) : 0x7fffffff;
+  key_sm[tid] = key;
+  for (int k = tid; k < p.c; k += threads) class_sum[k] = 0.f;
+  __syncthreads();
+  int pos = 0;
+  for (int j = 0; j < threads; j += 4) {  // threads is a multiple of 32
+    const int4 other = *reinterpret_cast<const int4*>(key_sm + j);
+    pos += (other.x < key || (other.x == key && j + 0 < tid)) ? 1 : 0;
+    pos += (other.y < key || (other.y == key && j + 1 < tid)) ? 1 : 0;
+    pos += (other.z < key || (other.z == key && j + 2 < tid)) ? 1 : 0;
+    pos += (other.w < key || (other.w == key && j + 3 < tid)) ? 1 : 0;
+  }
+  __syncthreads();
+  key_sm[pos] = key;
+  __syncthreads();
+  const int my_key = key_sm[tid];  // from here on the thread owns POSITION tid of the class order
+  const bool valid = my_key != 0x7fffffff;
+  unsigned same = 0;  // bit d: the position 2^d to the left belongs to the same class and the same warp
+#pragma unroll
+  for (int d = 0; d < 5; ++d)
+    if (lane >= (1 << d) && key_sm[tid - (1 << d)] == my_key) same |= 1u << d;
+  const bool warp_tail = lane == 31 || tid + 1 >= threads || key_sm[tid + 1] != my_key;
+  const bool class_head = tid == 0 || key_sm[tid - 1] != my_key;
+  const int t_end = min(t1, t_live);
+  const float* occ_row = p.alpha + static_cast<long long>(t0) * p.s_pad + tid;
+  float occ_next = tid < S2 ? *occ_row : 0.f;
+  for (int t = t0; t < t_end; ++t) {
+    const float occ = occ_next;
+    if (t + 1 < t_end && tid < S2) occ_next = occ_row[static_cast<long long>(t + 1 - t0) * p.s_pad];
+    occ_sm[pos] = occ;
+    __syncthreads();
+    float v = occ_sm[tid];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) {
+      const float u = __shfl_up_sync(0xffffffffu, v, 1 << d);
+      if (same & (1u << d)) v += u;
+    }
+    if (valid && warp_tail) atomicAdd(&class_sum[my_key], v);
+    __syncthreads();
+    float* grad_t = p.grad + static_cast<long long>(t) * p.stride_t;
+    if (narrow) {
+      if (tid < p.c) {
+        grad_t[tid] = g * (ex2a(__ldg(p.lp + static_cast<long long>(t) * p.stride_t + tid) * kLog2E) - class_sum[tid]);
+        class_sum[tid] = 0.f;
+      }
+    } else if (valid && class_head) {
+      grad_t[my_key] -= g * class_sum[my_key];
+      class_sum[my_key] = 0.f;
+    }
+    // (the next frame's first barrier orders these resets before its atomics, and this frame's reads of occ_sm before its writes)
+  }
+}
+
+// Which recursion kernels a problem takes (the forward and the backward call must agree: the workspace layouts differ).  A
+// block per pair cuts the latency of a frame in half, but spends ten times the instructions of the warp kernels on it: it is
+// used while all pairs fit the GPU at two blocks per SM (the 37 heads x 8 utterances of a training step), the warp kernels
+// beyond (64 utterances: 2 368 pairs are throughput-bound either way).  APH_CTC_V1=1 forces the warp kernels.
+static int ctc_sm_count() {
+  static int count = 0;
+  if (count == 0) {
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess || cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) count = 1;
+  }
+  return count;
+}
+static bool ctc_use_warp_kernels(int pairs) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* v = getenv("APH_CTC_V1");
+    forced = (v != nullptr && v[0] == '1') ? 1 : 0;
+  }
+  return forced == 1 || pairs > 2 * ctc_sm_count();
+}
+// Dynamic shared memory of a recursion block: what it needs, padded so that no more than ceil(pairs / SMs) blocks fit one SM —
+// otherwise the block scheduler stacks several blocks on some SMs while others stay empty, and a launch takes as long as
+// its most crowded SM (measured: 296 pairs 880 cycles per frame unpadded against 350 for a single pair).
+static size_t ctc_pair_smem(int pairs, size_t needed) {
+  const int per_sm = (pairs + ctc_sm_count() - 1) / ctc_sm_count();
+  const size_t share = static_cast<size_t>(220) * 1024 / static_cast<size_t>(per_sm < 1 ? 1 : per_sm);
+  const size_t padded = share > 2048 ? share - 1024 : share;  // 1 KB per block is reserved by the driver
+  return padded > needed ? padded : needed;
+}
+
 static size_t long_smem_bytes(int s_pad) { return static_cast<size_t>(s_pad) * 12; }
 
 static int pick_k(int max_label_len) {
@@ -729,6 +1031,14 @@ extern "C" int aph_ctc_forward(const aph_ctc_head* heads_host, int32_t n_heads, 
     if (k == 0) {
       ctc_long_alpha_kernel<<<nh * n_utt, kCtcLongThreads, long_smem_bytes(aph_ctc_states_pad(max_label_len)), stream>>>(
           pack, nh, n_utt, T, reinterpret_cast<const long long*>(input_lengths), alpha_ws, nll);
+      ++launched;
+      continue;
+    }
+    if (!ctc_use_warp_kernels(n_heads * n_utt)) {
+      const int s_pad = 32 * k;
+      const size_t smem = ctc_pair_smem(nh * n_utt, 2 * (static_cast<size_t>(s_pad) + 2) * sizeof(float));
+      APH_CUDA_CHECK(cudaFuncSetAttribute(ctc_pair_alpha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      ctc_pair_alpha_kernel<<<nh * n_utt, s_pad, smem, stream>>>(pack, nh, n_utt, T, reinterpret_cast<const long long*>(input_lengths), alpha_ws, nll);
       ++launched;
       continue;
     }
@@ -796,6 +1106,22 @@ extern "C" int aph_ctc_backward(const aph_ctc_head* heads_host, int32_t n_heads,
     memcpy(pack.h, heads_host + h0, sizeof(aph_ctc_head) * nh);
     const float* nll_h = nll + static_cast<long long>(h0) * n_utt;
     const float* scale_h = grad_scale ? grad_scale + h0 : nullptr;
+    if (!ctc_use_warp_kernels(n_heads * n_utt)) {
+      const int s_pad = 32 * k;
+      const size_t smem = ctc_pair_smem(nh * n_utt, 2 * (static_cast<size_t>(s_pad) + 2) * sizeof(float));
+      APH_CUDA_CHECK(cudaFuncSetAttribute(ctc_pair_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      int max_classes = 0;
+      for (int i = 0; i < nh; ++i) max_classes = pack.h[i].n_classes > max_classes ? pack.h[i].n_classes : max_classes;
+      const size_t grad_smem = (2 * static_cast<size_t>(s_pad) + max_classes) * sizeof(float);
+      if (grad_smem > 48 * 1024)
+        APH_CUDA_CHECK(cudaFuncSetAttribute(ctc_pair_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(grad_smem)));
+      ctc_pair_beta_kernel<<<nh * n_utt, s_pad, smem, stream>>>(pack, nh, n_utt, T, reinterpret_cast<const long long*>(input_lengths),
+                                                                const_cast<float*>(alpha_ws), nll_h);
+      ctc_pair_grad_kernel<<<dim3(ceil_div(T, kCtcGradChunk), nh * n_utt), s_pad, grad_smem, stream>>>(
+          pack, nh, n_utt, T, reinterpret_cast<const long long*>(input_lengths), alpha_ws, nll_h, scale_h);
+      launched += 2;
+      continue;
+    }
     switch (k) {
       case 2: launch_beta<2>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll_h, scale_h, stream); break;
       case 4: launch_beta<4>(pack, nh, n_utt, T, input_lengths, alpha_ws, nll_h, scale_h, stream); break;

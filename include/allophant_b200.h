@@ -366,7 +366,9 @@ int aph_ctc_forward(const aph_ctc_head* heads_host, int32_t n_heads, int32_t n_u
                     float* nll_out, float* loss_out, void* stream);
 /* Backward: writes grad (w.r.t. the logits that produced log_probs) for every head with a
  * non-NULL grad pointer: grad_scale[h] * (softmax - state occupancies), zero for padded
- * frames and for pairs whose loss was infinite. */
+ * frames and for pairs whose loss was infinite. alpha_ws is CONSUMED: the block-per-pair
+ * recursions overwrite the forward variables with the state occupancies (one backward call per
+ * forward call, with the same n_heads / n_utt / max_label_len: they select the kernels). */
 int aph_ctc_backward(const aph_ctc_head* heads_host, int32_t n_heads, int32_t n_utt, int32_t T, int32_t max_label_len,
                      const int64_t* input_lengths, const float* alpha_ws, const float* nll,
                      const float* grad_scale, void* stream);
