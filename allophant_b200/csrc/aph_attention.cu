@@ -399,6 +399,11 @@ constexpr uint32_t kPairTmemCols = 512;
 #ifndef APH_ATT_POLY_EVERY
 #define APH_ATT_POLY_EVERY 0
 #endif
+// Lazy rescaling threshold of the pair kernel (log2 units).  P is bf16 and O / the row sums are fp32, so probabilities up to 2^32
+// relative to a stale reference are as exact as those below 1 (the 2^8 of the 64-key kernel is the fp16 bound of the published
+// kernels); the rescale itself is expensive here — it has to wait for the previous block's PV product, which is issued at the
+// end of that block — and with unit-variance q and k (score deviation 8) it fired in most blocks: 90.6 us against 63.8 us.
+constexpr float kPairRescaleThreshold = 32.0f;
 constexpr int kPolyEvery = APH_ATT_POLY_EVERY;  // one exponential pair in this many on the FMA pipe; 0 = none (4: 63.8 -> 67.3 us, profiles/r02_attention_experiments.md)
 
 // 2^x for a pair of scores on the FMA / ALU pipes instead of the MUFU pipe (Cody-Waite: x = n + f with |f| <= 1/2 through the
@@ -538,9 +543,26 @@ __global__ void __launch_bounds__(kPairThreads, 1)
       len = len < p.T ? len : p.T;
       if (q0 >= len) continue;
       const int n_kv = (len + kPairKV - 1) / kPairKV;
-      const bool both = q0 + kAttQ < len;  // false: tile B is padding only; tile A's issuer releases the tiles for both
+      const bool both = q0 + kAttQ < len;  // false: tile B is padding only
       const uint32_t buf = it & 1u;
       if (t == 1 && !both) {
+        // Tile B has nothing to compute, but its issuer still WALKS the item's barriers and gives its share of every release:
+        // skipping ahead would let it wait for a phase two ring revolutions away, which an mbarrier parity cannot tell from
+        // the phase that has already completed (it would pass the wait and issue MMAs on stale tiles).
+        mbar_wait(&q_full[buf], (it >> 1) & 1u);
+        for (int j = 0; j < n_kv; ++j) {
+          const uint32_t gj = g + static_cast<uint32_t>(j);
+          const uint32_t st = gj % kPairStages;
+          mbar_wait(&k_full[st], (gj / kPairStages) & 1u);
+          if (elect_one()) {
+            umma_commit(&k_empty[st]);
+            if (j == n_kv - 1) umma_commit(&q_empty[buf]);
+          }
+          __syncwarp();
+          mbar_wait(&v_full[st], (gj / kPairStages) & 1u);
+          if (elect_one()) umma_commit(&v_empty[st]);
+          __syncwarp();
+        }
         g += static_cast<uint32_t>(n_kv);
         ++it;
         continue;
@@ -566,11 +588,7 @@ __global__ void __launch_bounds__(kPairThreads, 1)
             if (k < s_steps) umma_bf16(tmem_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc_s, k != 0 ? 1u : 0u);
           umma_commit(&s_full[t]);
           umma_commit(&k_empty[st]);
-          if (!both) umma_commit(&k_empty[st]);
-          if (j == n_kv - 1) {
-            umma_commit(&q_empty[buf]);
-            if (!both) umma_commit(&q_empty[buf]);
-          }
+          if (j == n_kv - 1) umma_commit(&q_empty[buf]);
         }
         __syncwarp();
       };
@@ -608,7 +626,6 @@ __global__ void __launch_bounds__(kPairThreads, 1)
           }
           umma_commit(&pv_done[t]);
           umma_commit(&v_empty[st]);
-          if (!both) umma_commit(&v_empty[st]);
         }
         __syncwarp();
         APH_DSTAMP(it == 2 && lane == 0, 96 + j * 8 + t * 4 + 2);
@@ -710,8 +727,8 @@ __global__ void __launch_bounds__(kPairThreads, 1)
             mx1 = fmax3(mx1, xb[2 * i], xb[2 * i + 1]);
           }
           const float m_half = fmaxf(mx0, mx1);
-          // lazy rescaling: only when this row's maximum outgrows the reference by more than 2^8
-          const bool grow = m_half > m_ref + kAttRescaleThreshold;  // always true for an item's first scores (m_ref = -inf)
+          // lazy rescaling: only when this row's maximum outgrows the reference by more than 2^32
+          const bool grow = m_half > m_ref + kPairRescaleThreshold;  // always true for an item's first scores (m_ref = -inf)
           if (__any_sync(0xffffffffu, grow)) {
             const float m_new = grow ? m_half : m_ref;
             const float alpha = ex2_approx(m_ref - m_new);  // 1 for rows that keep their reference, 0 for the first scores

@@ -275,6 +275,37 @@ def test_attention(n, heads, frames, lengths):
         assert range_err(ours[index, :length], reference[index, :length]) < 2e-2
 
 
+def test_attention_ragged_batches_on_the_persistent_schedule():
+    """Batches as a MaxFrameBatchSampler stream produces them (many utterances of very different lengths, frames padded to a
+    multiple of 64): every persistent CTA works through a long list of items that mixes full query-tile pairs, pairs whose second
+    tile is padding only (its MMA issuer still walks the ring barriers: skipping ahead aliases mbarrier parities and once hung the
+    kernel) and pairs that are skipped altogether."""
+    ops = _ops()
+    generator = torch.Generator().manual_seed(5)
+    heads = 4
+    for _ in range(3):
+        n = int(torch.randint(20, 60, (1,), generator=generator))
+        seconds = torch.rand(n, generator=generator) * 12 + 3
+        lengths = (((seconds * 16000 - 400) / 320).floor().int() + 1).tolist()
+        lengths[0] = 1
+        lengths[1] = 129
+        frames = (max(lengths) + 63) // 64 * 64
+        q = torch.randn(n, heads, frames, 64, device=DEV, generator=None).bfloat16()
+        k = torch.randn(n, heads, frames, 64, device=DEV).bfloat16()
+        v = torch.randn(n, heads, frames, 64, device=DEV).bfloat16()
+        q_scaled = (q.float() * 0.125 * math.log2(math.e)).bfloat16()
+        ctx = torch.full((n * frames, heads * 64), float("nan"), device=DEV, dtype=torch.bfloat16)
+        frame_lengths = torch.tensor(lengths, device=DEV, dtype=torch.int32)
+        ops.attention(q_scaled, k, v, ctx, frame_lengths, n, heads, frames)
+        mask = torch.arange(frames, device=DEV)[None, :] < frame_lengths[:, None]
+        scores = (q_scaled.float() / math.log2(math.e) @ k.float().transpose(2, 3)).masked_fill(~mask[:, None, None, :], float("-inf"))
+        reference = (torch.softmax(scores, -1) @ v.float()).permute(0, 2, 1, 3).reshape(n, frames, heads * 64)
+        ours = ctx.float().view(n, frames, heads * 64)
+        assert torch.isfinite(ours).all()  # rows of padded queries are written too (zeros or values computed from real keys)
+        for index, length in enumerate(lengths):
+            assert range_err(ours[index, :length], reference[index, :length]) < 2e-2
+
+
 @pytest.mark.parametrize("sharpness", [8.0, 40.0])
 def test_attention_large_scores_exercise_lazy_rescaling(sharpness):
     """Peaked score distributions (row maxima that keep growing by more than 2^8 from block to block) exercise the

@@ -74,7 +74,8 @@ with open(os.path.join(PROFILES, "r02_ncu_summary.md"), "w") as handle:
     )
     for name, title in (
         ("r02_gemm_final.ncu-rep", "encoder GEMMs of one layer (FFN1 `<256,0>`, FFN2 `<256,2>`, QKV `<256,1>`, out-proj `<256,2>`)"),
-        ("r02_attention_final.ncu-rep", "attention forward, 32 x 16 heads x 499 frames x 64"),
+        ("r02_attention_final.ncu-rep", "attention forward (query-tile-pair kernel), 32 x 16 heads x 499 frames x 64"),
+        ("r02_ctc_pair_final.ncu-rep", "block-per-pair CTC recursions + gradient kernel of the training step (37 heads x 8 utterances)"),
         ("r02_ctc.ncu-rep", "CTC alpha / beta of the training step (before the staged log-sum-exp, see r02_ctc_recursion.md)"),
     ):
         rep = os.path.join(OUT, name)

@@ -11,3 +11,4 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:atte
 timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench_reference.json 2> gpurun_out/r02_bench_reference.err; tail -c 400 gpurun_out/r02_bench_reference.json
 timeout 600 python tools/gpu_library_bar.py > gpurun_out/r02_library_bar.md 2> gpurun_out/r02_library_bar.err; echo "library bar rc=$?"; tail -12 gpurun_out/r02_library_bar.md
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 1800 --csv --log-file gpurun_out/r02_launches_train_step.csv python bench.py --workload train --steps 2 --warmup 3 --skip-cpu-baseline > gpurun_out/r02_launches_train.log 2>&1; echo "train launch list rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:ctc_pair -s 6 -c 3 -f -o gpurun_out/r02_ctc_pair_final python bench.py --workload train --steps 1 --warmup 2 --skip-cpu-baseline > gpurun_out/r02_ncu_ctc.log 2>&1; echo "ncu ctc rc=$?"
