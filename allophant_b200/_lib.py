@@ -88,6 +88,12 @@ class GemmArgs(Structure):
     ]
 
 
+class HeadBlock(Structure):
+    """Mirror of ``aph_head_block``."""
+
+    _fields_ = [("ptr", c_void_p), ("ld", c_int64), ("width", c_int32), ("reserved", c_int32)]
+
+
 class CtcHead(Structure):
     """Mirror of ``aph_ctc_head``."""
 
@@ -179,6 +185,8 @@ _SIGNATURES = {
     "aph_edit_statistics_batch": [_P, _P, _P, _P, _I64, _P, _P, _I32],
     "aph_fold_layernorm_linear": [_P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P],
     "aph_attention_small": [_P, _I64, _P, _I64, _P, _I32, _I32, _I32, _I32, _P],
+    "aph_copy_head_blocks": [POINTER(HeadBlock), POINTER(HeadBlock), _I32, _I64, _I32, _P],
+    "aph_log_softmax_head_blocks": [POINTER(HeadBlock), POINTER(HeadBlock), _I32, _I64, _P],
     "aph_ctc_states_pad": [_I32],
     "aph_ctc_forward": [POINTER(CtcHead), _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
     "aph_ctc_backward": [POINTER(CtcHead), _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],

@@ -513,6 +513,110 @@ extern "C" int aph_log_softmax_wide(const float* logits, int64_t ld, int64_t row
   return APH_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Multi-head block kernels of the training step: every classifier head is a [rows][width] fp32 block inside some row-major
+// matrix (its logits inside the level's output matrix, its gradient inside the level's gradient matrix, or a matrix of its
+// own).  One launch walks all heads; the block descriptors travel by value in the kernel parameters.  They replace one torch
+// launch PER HEAD each: the copies that hand the logits to autograd, the per-head log_softmax in front of the CTC loss and the
+// strided adds that collect the logits gradients (3 x 37 launches of a few microseconds on the step's critical path).
+// ---------------------------------------------------------------------------
+constexpr int kMaxHeadBlocks = 48;
+struct HeadBlockPack {
+  aph_head_block src[kMaxHeadBlocks];
+  aph_head_block dst[kMaxHeadBlocks];
+};
+
+__global__ void __launch_bounds__(256) copy_head_blocks_kernel(const __grid_constant__ HeadBlockPack pack, long long rows, int accumulate) {
+  const aph_head_block src = pack.src[blockIdx.y];
+  const aph_head_block dst = pack.dst[blockIdx.y];
+  const float* in = static_cast<const float*>(src.ptr);
+  float* out = static_cast<float*>(dst.ptr);
+  const int width = src.width;
+  const long long total = rows * width;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / width;
+    const int c = static_cast<int>(i - r * width);
+    const float v = in[r * src.ld + c];
+    float* o = out + r * dst.ld + c;
+    *o = accumulate ? *o + v : v;
+  }
+}
+
+// one warp per row: functional.log_softmax(x, -1) with the arithmetic of log_softmax_wide_kernel (expf / logf, fp32)
+__global__ void __launch_bounds__(256) log_softmax_head_blocks_kernel(const __grid_constant__ HeadBlockPack pack, long long rows) {
+  const aph_head_block src = pack.src[blockIdx.y];
+  const aph_head_block dst = pack.dst[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const int width = src.width;
+  const long long warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  for (long long r = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
+    const float* in = static_cast<const float*>(src.ptr) + r * src.ld;
+    float* out = static_cast<float*>(dst.ptr) + r * dst.ld;
+    float m = -INFINITY;
+    for (int c = lane; c < width; c += 32) m = fmaxf(m, in[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+    for (int c = lane; c < width; c += 32) sum += expf(in[c] - m);
+    sum = warp_sum(sum);
+    const float lse = m + logf(sum);
+    for (int c = lane; c < width; c += 32) out[c] = in[c] - lse;
+  }
+}
+
+static int pack_head_blocks(const aph_head_block* src, const aph_head_block* dst, int first, int count, HeadBlockPack& pack) {
+  for (int i = 0; i < count; ++i) {
+    pack.src[i] = src[first + i];
+    pack.dst[i] = dst[first + i];
+    APH_REQUIRE(pack.src[i].ptr && pack.dst[i].ptr, "null block pointer");
+    APH_REQUIRE(pack.src[i].width > 0 && pack.src[i].width == pack.dst[i].width, "source and destination blocks must have the same positive width");
+    APH_REQUIRE(pack.src[i].ld >= pack.src[i].width && pack.dst[i].ld >= pack.dst[i].width, "row stride smaller than the block width");
+  }
+  return APH_OK;
+}
+
+extern "C" int aph_copy_head_blocks(const aph_head_block* src_host, const aph_head_block* dst_host, int32_t n_blocks, int64_t rows,
+                                    int32_t accumulate, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  APH_REQUIRE(src_host && dst_host, "null pointer");
+  if (rows <= 0 || n_blocks <= 0) return APH_OK;
+  int launched = 0;
+  for (int first = 0; first < n_blocks; first += kMaxHeadBlocks) {
+    const int count = n_blocks - first < kMaxHeadBlocks ? n_blocks - first : kMaxHeadBlocks;
+    HeadBlockPack pack;
+    const int rc = pack_head_blocks(src_host, dst_host, first, count, pack);
+    if (rc != APH_OK) return rc;
+    int widest = 0;
+    for (int i = 0; i < count; ++i) widest = pack.src[i].width > widest ? pack.src[i].width : widest;
+    long long blocks = (rows * widest + 1023) / 1024;
+    if (blocks > 64) blocks = 64;
+    copy_head_blocks_kernel<<<dim3(static_cast<unsigned>(blocks), count), 256, 0, stream>>>(pack, rows, accumulate);
+    ++launched;
+  }
+  APH_POST_LAUNCH(launched);
+  return APH_OK;
+}
+
+extern "C" int aph_log_softmax_head_blocks(const aph_head_block* src_host, const aph_head_block* dst_host, int32_t n_blocks, int64_t rows,
+                                           void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  APH_REQUIRE(src_host && dst_host, "null pointer");
+  if (rows <= 0 || n_blocks <= 0) return APH_OK;
+  int launched = 0;
+  for (int first = 0; first < n_blocks; first += kMaxHeadBlocks) {
+    const int count = n_blocks - first < kMaxHeadBlocks ? n_blocks - first : kMaxHeadBlocks;
+    HeadBlockPack pack;
+    const int rc = pack_head_blocks(src_host, dst_host, first, count, pack);
+    if (rc != APH_OK) return rc;
+    long long blocks = (rows + 7) / 8;
+    if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
+    log_softmax_head_blocks_kernel<<<dim3(static_cast<unsigned>(blocks), count), 256, 0, stream>>>(pack, rows);
+    ++launched;
+  }
+  APH_POST_LAUNCH(launched);
+  return APH_OK;
+}
+
 extern "C" int aph_dependency_softmax(const float* logits, int64_t ld, int64_t rows, const int32_t* col_off, const int32_t* width,
                                       const int32_t* dst_col, int32_t n_deps, int32_t skip, void* dst_bf16, int64_t ld_dst,
                                       void* stream_) {

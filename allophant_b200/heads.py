@@ -554,7 +554,17 @@ class HeadsRuntime:
         state["heads"] = heads
         state["head_names"] = [name for name, *_ in heads]
         state["dims"] = (rows, n_utt, seq)
-        return tuple(buffer[:, column : column + width].reshape(n_utt, seq, width).contiguous() for _, buffer, _, column, width in heads)
+        # every classifier's logits as a tensor of its own (autograd hands each to the caller's loss): one flat buffer, one launch
+        flat = torch.empty(sum(width for *_, width in heads) * rows, device=plan.x.device, dtype=torch.float32)
+        outputs, src, dst, position = [], [], [], 0
+        for _, buffer, ld, column, width in heads:
+            block = flat[position : position + rows * width]
+            position += rows * width
+            src.append((buffer, ld, column, width))
+            dst.append((block, width, 0, width))
+            outputs.append(block.view(n_utt, seq, width))
+        ops.copy_head_blocks(src, dst, rows)
+        return tuple(outputs)
 
     @torch.no_grad()
     def _differentiable_backward_impl(self, state: Dict[str, Any], grads: Tuple[Optional[Tensor], ...]) -> List[Optional[Tensor]]:
@@ -615,6 +625,20 @@ class HeadsRuntime:
                 widths = self._int_tensor(("bwd_w", level_index, skip), [self.dep_cols[name][1] + skip for name in feeders], device, torch.int32)
                 dst_col = self._int_tensor(("bwd_dst", level_index), [layout.offsets[name] for name in feeders], device, torch.int32)
                 ops.softmax_backward_cols(d_x, self.ldx, x, self.ldx, rows, x_col, widths, dst_col, len(feeders), skip, grad_level, n_pad)
+            # plain linear heads: their logits gradients join the level's gradient matrix in ONE launch (not one strided add each)
+            plain_src, plain_dst = [], []
+            for spec in layout.specs:
+                if projection._layers[spec.name]._composition_layer is not None:
+                    continue
+                grad = head_grads.get(spec.name)
+                if grad is None:
+                    grad = head_grads.get("__phone__" + spec.name)
+                if grad is None:
+                    continue
+                grad = grad if grad.is_contiguous() else grad.contiguous()
+                plain_src.append((grad, spec.out_features, 0, spec.out_features))
+                plain_dst.append((grad_level, n_pad, layout.offsets[spec.name], spec.out_features))
+            ops.copy_head_blocks(plain_src, plain_dst, rows, accumulate=True)
             for spec in layout.specs:
                 classifier = projection._layers[spec.name]
                 offset = layout.offsets[spec.name]
@@ -624,7 +648,6 @@ class HeadsRuntime:
                 if grad is None:
                     continue
                 if classifier._composition_layer is None:
-                    grad_level[:, offset : offset + spec.out_features] += grad
                     continue
                 # composed phoneme logits = (projection @ table^T) / sqrt(E)   (acoustic_model.py:219-234)
                 info = state["composed"][spec.name]

@@ -22,7 +22,7 @@ class _MultiHeadCtc(torch.autograd.Function):
     @staticmethod
     def forward(ctx, labels, label_lengths, input_lengths, *logits):
         need_grad = any(t.requires_grad for t in logits)
-        log_probs = [ops.log_softmax(t.detach()) for t in logits]
+        log_probs = ops.log_softmax_many([t.detach() for t in logits])  # one launch for all heads
         problem = ops.CtcProblem(log_probs, labels, label_lengths, input_lengths, batch_first=False, need_grad=need_grad)
         loss = problem.forward()
         ctx.problem = problem

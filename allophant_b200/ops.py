@@ -14,7 +14,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import CtcHead, GemmArgs, check, lib
+from ._lib import CtcHead, GemmArgs, HeadBlock, check, lib
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
@@ -553,6 +553,68 @@ def log_softmax(x: Tensor) -> Tensor:
     out = torch.empty_like(flat)
     log_softmax_wide(flat, width, flat.shape[0], width, out, width, None, None)
     return out.view(x.shape)
+
+
+def _head_blocks(blocks: Sequence[Tuple[Tensor, int, int, int]]):
+    """``(matrix, ld, column, width)`` per head -> ctypes array of ``aph_head_block`` (fp32 matrices, the block starts at
+    element ``column`` of row 0)."""
+    array = (HeadBlock * len(blocks))()
+    for slot, (matrix, ld, column, width) in zip(array, blocks):
+        if matrix.dtype != torch.float32:
+            raise ValueError("head blocks are fp32")
+        slot.ptr = matrix.data_ptr() + 4 * column
+        slot.ld = ld
+        slot.width = width
+    return array
+
+
+def copy_head_blocks(src: Sequence[Tuple[Tensor, int, int, int]], dst: Sequence[Tuple[Tensor, int, int, int]], rows: int, accumulate: bool = False) -> None:
+    """``dst_b (+)= src_b`` for every ``[rows, width]`` block ``(matrix, ld, column, width)`` in one launch."""
+    _require_cuda(*[b[0] for b in src], *[b[0] for b in dst])
+    if not src:
+        return
+    check(lib.aph_copy_head_blocks(_head_blocks(src), _head_blocks(dst), len(src), rows, int(accumulate), _stream()), "aph_copy_head_blocks")
+
+
+def log_softmax_head_blocks(src: Sequence[Tuple[Tensor, int, int, int]], dst: Sequence[Tuple[Tensor, int, int, int]], rows: int) -> None:
+    """Row-wise ``log_softmax`` of every ``[rows, width]`` block in one launch."""
+    _require_cuda(*[b[0] for b in src], *[b[0] for b in dst])
+    if not src:
+        return
+    check(lib.aph_log_softmax_head_blocks(_head_blocks(src), _head_blocks(dst), len(src), rows, _stream()), "aph_log_softmax_head_blocks")
+
+
+def log_softmax_many(tensors: Sequence[Tensor]) -> List[Tensor]:
+    """``[log_softmax(t, -1) for t in tensors]`` in ONE launch when every tensor is an fp32 ``[A, B, C]`` block that is contiguous
+    either as it is or transposed (the time-first views ``Allophant.forward`` returns) and all share ``A * B``; each result has
+    the strides of its input.  Anything else goes through :func:`log_softmax` one by one."""
+    bases = []
+    for t in tensors:
+        if t.dim() != 3 or t.dtype != torch.float32 or not t.is_cuda:
+            bases = None
+            break
+        if t.is_contiguous():
+            bases.append((t, False))
+        elif t.transpose(0, 1).is_contiguous():
+            bases.append((t.transpose(0, 1), True))
+        else:
+            bases = None
+            break
+    if not bases or len({b.shape[0] * b.shape[1] for b, _ in bases}) != 1:
+        return [log_softmax(t) for t in tensors]
+    rows = bases[0][0].shape[0] * bases[0][0].shape[1]
+    flat = torch.empty(sum(b.numel() for b, _ in bases), device=bases[0][0].device, dtype=torch.float32)
+    outputs, src, dst, position = [], [], [], 0
+    for base, transposed in bases:
+        width = base.shape[2]
+        block = flat[position : position + rows * width]
+        position += rows * width
+        src.append((base, width, 0, width))
+        dst.append((block, width, 0, width))
+        view = block.view(base.shape)
+        outputs.append(view.transpose(0, 1) if transposed else view)
+    log_softmax_head_blocks(src, dst, rows)
+    return outputs
 
 
 def dependency_softmax(logits: Tensor, ld: int, rows: int, col_off: Tensor, width: Tensor, dst_col: Tensor, n_deps: int, skip: int, dst: Tensor, ld_dst: int) -> None:

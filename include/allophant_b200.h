@@ -437,6 +437,21 @@ int aph_posconv_weight_backward_blocks(const float* raw, const float* weight_g, 
 int aph_embedding_bag_backward(const float* grad_rows, int64_t ld, int32_t n_phonemes,
                                int32_t n_features, int32_t embedding_size, const int64_t* tfi,
                                const int64_t* category_offsets, float* grad_weight, void* stream);
+/* One classifier head's [rows][width] fp32 block inside a row-major matrix (ptr = its first element). */
+typedef struct aph_head_block {
+  void* ptr;
+  int64_t ld; /* row stride in elements */
+  int32_t width;
+  int32_t reserved;
+} aph_head_block;
+/* dst_b = src_b (accumulate == 0) or dst_b += src_b for every block b in ONE launch: the per-head logits handed to autograd
+ * (acoustic_model.py:395-416 returns one tensor per classifier) and the logits gradients collected into the level's gradient
+ * matrix on the way back. src_host / dst_host are HOST arrays (descriptors travel in the kernel parameters). */
+int aph_copy_head_blocks(const aph_head_block* src_host, const aph_head_block* dst_host, int32_t n_blocks, int64_t rows,
+                         int32_t accumulate, void* stream);
+/* functional.log_softmax(x, -1) of every block in ONE launch (loss_functions.py:26: CTCWrapper applies it per head). */
+int aph_log_softmax_head_blocks(const aph_head_block* src_host, const aph_head_block* dst_host, int32_t n_blocks, int64_t rows,
+                                void* stream);
 /* Backward of the dependency softmax (acoustic_model.py:497-514): for dependency d,
  * grad_logits[:, dst_col[d]+skip : ...] += p * (dp - sum(p*dp)) with p the bf16 probabilities stored
  * in x[:, x_col[d] : ...] and dp = grad_x[:, x_col[d] : ...]. */

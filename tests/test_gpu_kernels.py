@@ -275,6 +275,35 @@ def test_attention(n, heads, frames, lengths):
         assert range_err(ours[index, :length], reference[index, :length]) < 2e-2
 
 
+def test_multi_head_block_kernels_match_torch():
+    """One launch for all heads: column blocks of a level matrix copied out / accumulated back, and the per-head log_softmax in front
+    of the CTC loss (time-first views keep their strides)."""
+    ops = _ops()
+    torch.manual_seed(3)
+    rows, ld = 1237, 96
+    level = torch.randn(rows, ld, device=DEV)
+    layout = [(0, 5), (5, 31), (36, 2), (40, 47)]  # (column, width)
+    outs = [torch.full((rows, width), float("nan"), device=DEV) for _, width in layout]
+    ops.copy_head_blocks([(level, ld, column, width) for column, width in layout], [(out, width, 0, width) for out, (_, width) in zip(outs, layout)], rows)
+    for out, (column, width) in zip(outs, layout):
+        assert torch.equal(out, level[:, column : column + width])
+    target = torch.randn(rows, ld, device=DEV)
+    expected = target.clone()
+    for out, (column, width) in zip(outs, layout):
+        expected[:, column : column + width] += out
+    ops.copy_head_blocks([(out, width, 0, width) for out, (_, width) in zip(outs, layout)], [(target, ld, column, width) for column, width in layout], rows, accumulate=True)
+    assert torch.equal(target, expected)
+    n_utt, seq = 7, 53
+    logits = [torch.randn(n_utt, seq, width, device=DEV).transpose(0, 1) * 3 for width in (4, 33, 501, 2)]  # time-first views
+    logits.append(torch.randn(seq, n_utt, 9, device=DEV).transpose(0, 1).contiguous().transpose(0, 1))
+    results = ops.log_softmax_many(logits)
+    for ours, x in zip(results, logits):
+        assert ours.shape == x.shape and ours.stride() == x.stride()
+        assert float((ours - torch.log_softmax(x, -1)).abs().max()) < 2e-6
+    mixed = ops.log_softmax_many([logits[0], torch.randn(3, 4, 5, device=DEV)])  # different row counts: one by one
+    assert float((mixed[1] - torch.log_softmax(torch.randn(3, 4, 5, device=DEV) * 0 + mixed[1].exp().log(), -1)).abs().max()) < 1e-5
+
+
 def test_attention_ragged_batches_on_the_persistent_schedule():
     """Batches as a MaxFrameBatchSampler stream produces them (many utterances of very different lengths, frames padded to a
     multiple of 64): every persistent CTA works through a long list of items that mixes full query-tile pairs, pairs whose second
