@@ -91,7 +91,7 @@ class GemmArgs(Structure):
 class HeadBlock(Structure):
     """Mirror of ``aph_head_block``."""
 
-    _fields_ = [("ptr", c_void_p), ("ld", c_int64), ("width", c_int32), ("reserved", c_int32)]
+    _fields_ = [("ptr", c_void_p), ("ld", c_int64), ("width", c_int32), ("rows", c_int32)]
 
 
 class CtcHead(Structure):

@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(256) copy_head_blocks_kernel(const __grid_cons
   const float* in = static_cast<const float*>(src.ptr);
   float* out = static_cast<float*>(dst.ptr);
   const int width = src.width;
-  const long long total = rows * width;
+  const long long total = (src.rows > 0 ? src.rows : rows) * width;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long r = i / width;
     const int c = static_cast<int>(i - r * width);
@@ -549,6 +549,7 @@ __global__ void __launch_bounds__(256) log_softmax_head_blocks_kernel(const __gr
   const int lane = threadIdx.x & 31;
   const int width = src.width;
   const long long warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  if (src.rows > 0) rows = src.rows;
   for (long long r = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
     const float* in = static_cast<const float*>(src.ptr) + r * src.ld;
     float* out = static_cast<float*>(dst.ptr) + r * dst.ld;
@@ -571,6 +572,7 @@ static int pack_head_blocks(const aph_head_block* src, const aph_head_block* dst
     APH_REQUIRE(pack.src[i].ptr && pack.dst[i].ptr, "null block pointer");
     APH_REQUIRE(pack.src[i].width > 0 && pack.src[i].width == pack.dst[i].width, "source and destination blocks must have the same positive width");
     APH_REQUIRE(pack.src[i].ld >= pack.src[i].width && pack.dst[i].ld >= pack.dst[i].width, "row stride smaller than the block width");
+    APH_REQUIRE(pack.src[i].rows >= 0 && pack.src[i].rows == pack.dst[i].rows, "source and destination blocks must have the same row count");
   }
   return APH_OK;
 }
@@ -579,16 +581,20 @@ extern "C" int aph_copy_head_blocks(const aph_head_block* src_host, const aph_he
                                     int32_t accumulate, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   APH_REQUIRE(src_host && dst_host, "null pointer");
-  if (rows <= 0 || n_blocks <= 0) return APH_OK;
+  if (rows < 0 || n_blocks <= 0) return APH_OK;
   int launched = 0;
   for (int first = 0; first < n_blocks; first += kMaxHeadBlocks) {
     const int count = n_blocks - first < kMaxHeadBlocks ? n_blocks - first : kMaxHeadBlocks;
     HeadBlockPack pack;
     const int rc = pack_head_blocks(src_host, dst_host, first, count, pack);
     if (rc != APH_OK) return rc;
-    int widest = 0;
-    for (int i = 0; i < count; ++i) widest = pack.src[i].width > widest ? pack.src[i].width : widest;
-    long long blocks = (rows * widest + 1023) / 1024;
+    long long largest = 0;
+    for (int i = 0; i < count; ++i) {
+      const long long elements = (pack.src[i].rows > 0 ? pack.src[i].rows : rows) * pack.src[i].width;
+      largest = elements > largest ? elements : largest;
+    }
+    long long blocks = (largest + 1023) / 1024;
+    if (blocks < 1) blocks = 1;
     if (blocks > 64) blocks = 64;
     copy_head_blocks_kernel<<<dim3(static_cast<unsigned>(blocks), count), 256, 0, stream>>>(pack, rows, accumulate);
     ++launched;

@@ -152,6 +152,11 @@ class HeadsRuntime:
         for layout in self.levels:
             weight = torch.zeros(layout.n_pad, self.ldx, device=device, dtype=torch.float32)
             bias = torch.zeros(layout.n_pad, device=device, dtype=torch.float32)
+            # the classifiers' weight / bias blocks join the level matrices in two launches (a training step rebuilds them after
+            # every optimizer step: one strided add and one copy per classifier were 74 launches on its critical path)
+            w_src, w_dst, b_src, b_dst = [], [], [], []
+            seen_targets: set = set()
+            late_adds: List[Tuple[Tensor, Tensor]] = []
             for spec in layout.specs:
                 linear = projection._layers[spec.name]._time_distributed_layer
                 if not isinstance(linear, torch.nn.Linear):
@@ -168,11 +173,27 @@ class HeadsRuntime:
                         target = self.x_cols[dependency.name]
                     else:
                         target = self.dep_cols[dependency.name][0]
-                    weight[row : row + spec.out_features, target : target + dependency.size] += linear.weight.detach()[
-                        :, source_column : source_column + dependency.size
-                    ].float()
+                    source = linear.weight.detach()
+                    # (two dependencies on the same columns, e.g. the output and the last hidden state, must not race in one launch)
+                    first_use = (row, target) not in seen_targets
+                    seen_targets.add((row, target))
+                    if first_use and source.dtype == torch.float32 and source.is_contiguous():
+                        w_src.append((source, source.shape[1], source_column, dependency.size, spec.out_features))
+                        w_dst.append((weight, self.ldx, row * self.ldx + target, dependency.size, spec.out_features))
+                    else:
+                        late_adds.append((weight[row : row + spec.out_features, target : target + dependency.size],
+                                          source[:, source_column : source_column + dependency.size].float()))  # fmt: skip
                     source_column += dependency.size
-                bias[row : row + spec.out_features] = linear.bias.detach().float()
+                source_bias = linear.bias.detach()
+                if source_bias.dtype == torch.float32 and source_bias.is_contiguous():
+                    b_src.append((source_bias, spec.out_features, 0, spec.out_features, 1))
+                    b_dst.append((bias, layout.n_pad, row, spec.out_features, 1))
+                else:
+                    bias[row : row + spec.out_features] = source_bias.float()
+            ops.copy_head_blocks(w_src, w_dst, 0, accumulate=True)
+            ops.copy_head_blocks(b_src, b_dst, 0)
+            for destination, addend in late_adds:
+                destination += addend
             self.level_w.append(ops.cast_bf16(weight))
             self.level_b.append(bias)
         self._composed_cache.clear()

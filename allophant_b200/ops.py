@@ -555,20 +555,22 @@ def log_softmax(x: Tensor) -> Tensor:
     return out.view(x.shape)
 
 
-def _head_blocks(blocks: Sequence[Tuple[Tensor, int, int, int]]):
-    """``(matrix, ld, column, width)`` per head -> ctypes array of ``aph_head_block`` (fp32 matrices, the block starts at
-    element ``column`` of row 0)."""
+def _head_blocks(blocks: Sequence[Tuple]):
+    """``(matrix, ld, offset, width[, rows])`` per block -> ctypes array of ``aph_head_block`` (fp32 matrices, the block starts
+    ``offset`` elements behind the matrix's first one; ``rows`` = the block's own row count, absent or 0 = the call's)."""
     array = (HeadBlock * len(blocks))()
-    for slot, (matrix, ld, column, width) in zip(array, blocks):
+    for slot, block in zip(array, blocks):
+        matrix, ld, offset, width = block[:4]
         if matrix.dtype != torch.float32:
             raise ValueError("head blocks are fp32")
-        slot.ptr = matrix.data_ptr() + 4 * column
+        slot.ptr = matrix.data_ptr() + 4 * offset
         slot.ld = ld
         slot.width = width
+        slot.rows = block[4] if len(block) > 4 else 0
     return array
 
 
-def copy_head_blocks(src: Sequence[Tuple[Tensor, int, int, int]], dst: Sequence[Tuple[Tensor, int, int, int]], rows: int, accumulate: bool = False) -> None:
+def copy_head_blocks(src: Sequence[Tuple], dst: Sequence[Tuple], rows: int, accumulate: bool = False) -> None:
     """``dst_b (+)= src_b`` for every ``[rows, width]`` block ``(matrix, ld, column, width)`` in one launch."""
     _require_cuda(*[b[0] for b in src], *[b[0] for b in dst])
     if not src:

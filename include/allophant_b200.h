@@ -442,11 +442,12 @@ typedef struct aph_head_block {
   void* ptr;
   int64_t ld; /* row stride in elements */
   int32_t width;
-  int32_t reserved;
+  int32_t rows; /* 0 = the row count of the call; > 0 = this block's own (the weight blocks of the level matrices) */
 } aph_head_block;
 /* dst_b = src_b (accumulate == 0) or dst_b += src_b for every block b in ONE launch: the per-head logits handed to autograd
  * (acoustic_model.py:395-416 returns one tensor per classifier) and the logits gradients collected into the level's gradient
- * matrix on the way back. src_host / dst_host are HOST arrays (descriptors travel in the kernel parameters). */
+ * matrix on the way back; also the per-step assembly of a level's weight / bias matrix from the classifiers' nn.Linear parameters
+ * (blocks with their own row counts). src_host / dst_host are HOST arrays (descriptors travel in the kernel parameters). */
 int aph_copy_head_blocks(const aph_head_block* src_host, const aph_head_block* dst_host, int32_t n_blocks, int64_t rows,
                          int32_t accumulate, void* stream);
 /* functional.log_softmax(x, -1) of every block in ONE launch (loss_functions.py:26: CTCWrapper applies it per head). */

@@ -160,13 +160,17 @@ def test_full_size_gradients_of_shards_sum_to_the_full_batch_gradient():
     second_loss, second = gradients(range(1, count, 2))
     assert abs(first_loss + second_loss - full_loss) <= 2e-3 * abs(full_loss)
     assert len(full) > 400  # every trainable tensor of the 24-layer model got a gradient
-    worst = 0.0
+    worst, worst_name = 0.0, ""
     for name, gradient in full.items():
         combined = first[name].double() + second[name].double()
         size = float(gradient.double().norm())
-        if size < 1e-6:
+        if size < 1e-6 or name.endswith("attention.k_proj.bias"):
+            # the key bias shifts every score of a row by the same amount and softmax does not see it: its gradient is analytically
+            # zero, what the kernels produce is rounding noise (norm ~1e-6, sometimes just above the floor) with no additivity
             continue
-        worst = max(worst, float((combined - gradient.double()).norm()) / size)
+        deviation = float((combined - gradient.double()).norm()) / size
+        if deviation > worst:
+            worst, worst_name = deviation, name
         assert torch.isfinite(gradient).all(), name
-    print(f"full-size shard additivity: loss {full_loss:.2f} = {first_loss:.2f} + {second_loss:.2f}; worst gradient deviation {worst:.3e}")
-    assert worst < 2e-2, worst
+    print(f"full-size shard additivity: loss {full_loss:.2f} = {first_loss:.2f} + {second_loss:.2f}; worst gradient deviation {worst:.3e} ({worst_name})")
+    assert worst < 2e-2, (worst, worst_name)

@@ -293,6 +293,18 @@ def test_multi_head_block_kernels_match_torch():
         expected[:, column : column + width] += out
     ops.copy_head_blocks([(out, width, 0, width) for out, (_, width) in zip(outs, layout)], [(target, ld, column, width) for column, width in layout], rows, accumulate=True)
     assert torch.equal(target, expected)
+    # blocks with their own row counts (weight blocks of different classifiers into one level matrix)
+    big = torch.zeros(40, 64, device=DEV)
+    parts = [torch.randn(3, 64, device=DEV), torch.randn(17, 20, device=DEV), torch.randn(1, 9, device=DEV)]
+    ops.copy_head_blocks(
+        [(parts[0], 64, 0, 64, 3), (parts[1], 20, 0, 20, 17), (parts[2], 9, 0, 9, 1)],
+        [(big, 64, 0, 64, 3), (big, 64, 5 * 64 + 8, 20, 17), (big, 64, 30 * 64 + 50, 9, 1)], 0, accumulate=True,
+    )  # fmt: skip
+    reference = torch.zeros(40, 64, device=DEV)
+    reference[:3] += parts[0]
+    reference[5:22, 8:28] += parts[1]
+    reference[30:31, 50:59] += parts[2]
+    assert torch.equal(big, reference)
     n_utt, seq = 7, 53
     logits = [torch.randn(n_utt, seq, width, device=DEV).transpose(0, 1) * 3 for width in (4, 33, 501, 2)]  # time-first views
     logits.append(torch.randn(seq, n_utt, 9, device=DEV).transpose(0, 1).contiguous().transpose(0, 1))
