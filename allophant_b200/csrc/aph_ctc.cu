@@ -691,7 +691,7 @@ __global__ void __launch_bounds__(kCtcLongThreads) ctc_long_beta_kernel(const __
 //   alpha kernel: alpha rows [t][s] (log2 domain, natural state order) into the workspace, nll per pair;
 //   beta kernel:  beta recursion; OVERWRITES alpha_t(s) with the state occupancy exp(alpha + beta - lp + nll);
 //   grad kernel:  parallel over (pair, 48-frame chunk): the occupancies of a frame are summed per class (the states are
-//                 visited in class order: a warp-segmented shuffle scan plus one shared-memory atomic per class and warp)
+//                 visited in class order: a warp-segmented shuffle scan, the segment sums of a class added up by the thread at its first position)
 //                 and the gradient row g * (softmax - occupancy sums) is written (narrow heads: the whole row; wide heads:
 //                 the label columns of the row ctc_grad_init_kernel wrote).
 // Nothing in the time loop of the two recursions depends on the number of classes.
@@ -872,7 +872,7 @@ __global__ void __launch_bounds__(1024) ctc_pair_beta_kernel(const __grid_consta
 __global__ void __launch_bounds__(1024) ctc_pair_grad_kernel(const __grid_constant__ CtcHeadPack heads, int n_heads, int n_utt, int T,
                                                              const long long* __restrict__ input_lengths, const float* __restrict__ occ_ws,
                                                              const float* __restrict__ nll_in, const float* __restrict__ grad_scale) {
-  extern __shared__ float pair_smem[];  // occupancies in class order [blockDim.x] | keys in class order [blockDim.x] | class sums [c]
+  extern __shared__ float pair_smem[];  // occupancies in class order [blockDim.x] | keys in class order [blockDim.x] | segment sums [32][32] | present [32]
   const int pair = blockIdx.y;
   const int h = pair / n_utt, n = pair - h * n_utt;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -896,32 +896,46 @@ __global__ void __launch_bounds__(1024) ctc_pair_grad_kernel(const __grid_consta
   if (t0 >= t_live) return;
   float* occ_sm = pair_smem;
   int* key_sm = reinterpret_cast<int*>(pair_smem + threads);
-  float* class_sum = pair_smem + 2 * threads;
+  float* partial = pair_smem + 2 * threads;  // [warps][32]: the sum of every warp's i-th class segment
+  int* present = reinterpret_cast<int*>(pair_smem + 2 * threads + 32 * 32);  // [32] narrow heads: class occurs among the states
   // states in class order: position = number of states with a smaller (class, state) key; padding threads sort last
   bool bad = false;
   const int key = tid < S2 ? pair_symbol(p, tid, S2, bad) : 0x7fffffff;
   key_sm[tid] = key;
-  for (int k = tid; k < p.c; k += threads) class_sum[k] = 0.f;
+  if (tid < 32) present[tid] = 0;
   __syncthreads();
-  int pos = 0;
+  int pos = 0, same_key = 0;
   for (int j = 0; j < threads; j += 4) {  // threads is a multiple of 32
     const int4 other = *reinterpret_cast<const int4*>(key_sm + j);
     pos += (other.x < key || (other.x == key && j + 0 < tid)) ? 1 : 0;
     pos += (other.y < key || (other.y == key && j + 1 < tid)) ? 1 : 0;
     pos += (other.z < key || (other.z == key && j + 2 < tid)) ? 1 : 0;
     pos += (other.w < key || (other.w == key && j + 3 < tid)) ? 1 : 0;
+    same_key += (other.x == key) + (other.y == key) + (other.z == key) + (other.w == key);
   }
   __syncthreads();
   key_sm[pos] = key;
+  reinterpret_cast<int*>(occ_sm)[pos] = same_key;  // (scratch until the frame loop starts)
   __syncthreads();
   const int my_key = key_sm[tid];  // from here on the thread owns POSITION tid of the class order
+  const int my_count = reinterpret_cast<int*>(occ_sm)[tid];
   const bool valid = my_key != 0x7fffffff;
   unsigned same = 0;  // bit d: the position 2^d to the left belongs to the same class and the same warp
 #pragma unroll
   for (int d = 0; d < 5; ++d)
     if (lane >= (1 << d) && key_sm[tid - (1 << d)] == my_key) same |= 1u << d;
   const bool warp_tail = lane == 31 || tid + 1 >= threads || key_sm[tid + 1] != my_key;
-  const bool class_head = tid == 0 || key_sm[tid - 1] != my_key;
+  const bool class_head = valid && (tid == 0 || key_sm[tid - 1] != my_key);
+  // No atomics: the tail of every class segment of a warp writes the segment's sum to partial[warp][segment index], and the
+  // thread at a class's first position adds up the class's segments (its own warp's, then segment 0 of the warps the class
+  // continues into).  All of this indexing is static over the frames.
+  const unsigned tails = __ballot_sync(0xffffffffu, warp_tail);
+  const int segment = __popc(tails & ((1u << lane) - 1u));
+  const int first_warp = tid >> 5;
+  const int last_warp = class_head ? (tid + my_count - 1) >> 5 : first_warp;
+  if (narrow && class_head) present[my_key] = 1;
+  __syncthreads();
+  const bool absent_class = narrow && tid < p.c && present[tid] == 0;  // its gradient is g * softmax
   const int t_end = min(t1, t_live);
   const float* occ_row = p.alpha + static_cast<long long>(t0) * p.s_pad + tid;
   float occ_next = tid < S2 ? *occ_row : 0.f;
@@ -936,19 +950,20 @@ __global__ void __launch_bounds__(1024) ctc_pair_grad_kernel(const __grid_consta
       const float u = __shfl_up_sync(0xffffffffu, v, 1 << d);
       if (same & (1u << d)) v += u;
     }
-    if (valid && warp_tail) atomicAdd(&class_sum[my_key], v);
+    if (warp_tail) partial[first_warp * 32 + segment] = v;
     __syncthreads();
     float* grad_t = p.grad + static_cast<long long>(t) * p.stride_t;
-    if (narrow) {
-      if (tid < p.c) {
-        grad_t[tid] = g * (ex2a(__ldg(p.lp + static_cast<long long>(t) * p.stride_t + tid) * kLog2E) - class_sum[tid]);
-        class_sum[tid] = 0.f;
-      }
-    } else if (valid && class_head) {
-      grad_t[my_key] -= g * class_sum[my_key];
-      class_sum[my_key] = 0.f;
+    if (class_head) {
+      float sum = partial[first_warp * 32 + segment];
+      for (int w = first_warp + 1; w <= last_warp; ++w) sum += partial[w * 32];
+      if (narrow)
+        grad_t[my_key] = g * (ex2a(__ldg(p.lp + static_cast<long long>(t) * p.stride_t + my_key) * kLog2E) - sum);
+      else
+        grad_t[my_key] -= g * sum;
     }
-    // (the next frame's first barrier orders these resets before its atomics, and this frame's reads of occ_sm before its writes)
+    if (absent_class) grad_t[tid] = g * ex2a(__ldg(p.lp + static_cast<long long>(t) * p.stride_t + tid) * kLog2E);
+    // (the next frame's first barrier orders these reads before the next writes of `partial`, and this frame's reads of occ_sm
+    // before its writes)
   }
 }
 
@@ -1110,9 +1125,7 @@ extern "C" int aph_ctc_backward(const aph_ctc_head* heads_host, int32_t n_heads,
       const int s_pad = 32 * k;
       const size_t smem = ctc_pair_smem(nh * n_utt, 2 * (static_cast<size_t>(s_pad) + 2) * sizeof(float));
       APH_CUDA_CHECK(cudaFuncSetAttribute(ctc_pair_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      int max_classes = 0;
-      for (int i = 0; i < nh; ++i) max_classes = pack.h[i].n_classes > max_classes ? pack.h[i].n_classes : max_classes;
-      const size_t grad_smem = (2 * static_cast<size_t>(s_pad) + max_classes) * sizeof(float);
+      const size_t grad_smem = (2 * static_cast<size_t>(s_pad) + 32 * 32 + 32) * sizeof(float);
       if (grad_smem > 48 * 1024)
         APH_CUDA_CHECK(cudaFuncSetAttribute(ctc_pair_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(grad_smem)));
       ctc_pair_beta_kernel<<<nh * n_utt, s_pad, smem, stream>>>(pack, nh, n_utt, T, reinterpret_cast<const long long*>(input_lengths),
