@@ -404,6 +404,7 @@ constexpr uint32_t kPairTmemCols = 512;
 // kernels); the rescale itself is expensive here — it has to wait for the previous block's PV product, which is issued at the
 // end of that block — and with unit-variance q and k (score deviation 8) it fired in most blocks: 90.6 us against 63.8 us.
 constexpr float kPairRescaleThreshold = 32.0f;
+constexpr int kPairSkewCycles = 3000;  // head start of tile A over tile B at the first item of a CTA (APH_ATT_SKEW overrides)
 constexpr int kPolyEvery = APH_ATT_POLY_EVERY;  // one exponential pair in this many on the FMA pipe; 0 = none (4: 63.8 -> 67.3 us, profiles/r02_attention_experiments.md)
 
 // 2^x for a pair of scores on the FMA / ALU pipes instead of the MUFU pipe (Cody-Waite: x = n + f with |f| <= 1/2 through the
@@ -429,7 +430,7 @@ template <bool kDrop>
 __global__ void __launch_bounds__(kPairThreads, 1)
     attention_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                           const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, const AttParams p,
-                          const int n_pairs, const int n_items) {
+                          const int n_pairs, const int n_items, const int skew_cycles) {
   pdl_trigger();
   if (threadIdx.x == 0) APH_STAMP(0);
 #ifdef APH_ATT_TIMELINE
@@ -592,6 +593,14 @@ __global__ void __launch_bounds__(kPairThreads, 1)
         }
         __syncwarp();
       };
+      if (skew_cycles > 0 && t == 1 && it == 0) {
+        // Tile B starts about one key block behind tile A and stays there (both advance at the same rate): the two tiles'
+        // item tails — last PV product, output — no longer coincide, and the tile that is busy has the MUFU pipe to itself
+        // while the other one is in its tail.
+        const long long start = clock64();
+        while (clock64() - start < skew_cycles) {
+        }
+      }
       issue_s(0);
       for (int j = 0; j < n_kv; ++j) {
         const uint32_t gj = g + static_cast<uint32_t>(j);
@@ -923,6 +932,7 @@ extern "C" int aph_attention_bf16_dropout(const void* q, const void* k, const vo
     if (rc != APH_OK) return rc;
   }
   static int sm_count = 0;
+  static int pair_skew = kPairSkewCycles;
   static bool use_blocks_of_64 = false;  // APH_ATT_V1=1: the 64-key, two-CTAs-per-SM kernel (kept for same-box comparisons)
   if (sm_count == 0) {
     int device = 0;
@@ -935,6 +945,8 @@ extern "C" int aph_attention_bf16_dropout(const void* q, const void* k, const vo
     APH_CUDA_CHECK(cudaFuncSetAttribute(attention_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
     const char* v1 = getenv("APH_ATT_V1");
     use_blocks_of_64 = v1 != nullptr && v1[0] == '1';
+    const char* skew = getenv("APH_ATT_SKEW");
+    if (skew != nullptr) pair_skew = atoi(skew);
     sm_count = count;
   }
   AttParams p;
@@ -958,9 +970,9 @@ extern "C" int aph_attention_bf16_dropout(const void* q, const void* k, const vo
     const int n_items = static_cast<int>(nh) * n_pairs;
     dim3 grid(static_cast<unsigned>(n_items < sm_count ? n_items : sm_count));
     if (drop_threshold != 0)
-      APH_CUDA_CHECK(launch_pdl(attention_pair_kernel<true>, grid, dim3(kPairThreads), kPairSmemBytes, stream, tm_q2, tm_k2, tm_v2, tm_o, p, n_pairs, n_items));
+      APH_CUDA_CHECK(launch_pdl(attention_pair_kernel<true>, grid, dim3(kPairThreads), kPairSmemBytes, stream, tm_q2, tm_k2, tm_v2, tm_o, p, n_pairs, n_items, pair_skew));
     else
-      APH_CUDA_CHECK(launch_pdl(attention_pair_kernel<false>, grid, dim3(kPairThreads), kPairSmemBytes, stream, tm_q2, tm_k2, tm_v2, tm_o, p, n_pairs, n_items));
+      APH_CUDA_CHECK(launch_pdl(attention_pair_kernel<false>, grid, dim3(kPairThreads), kPairSmemBytes, stream, tm_q2, tm_k2, tm_v2, tm_o, p, n_pairs, n_items, pair_skew));
   }
   APH_POST_LAUNCH(1);
   return APH_OK;
