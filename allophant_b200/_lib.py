@@ -194,7 +194,7 @@ _SIGNATURES = {
 
 EXPORTED_SYMBOLS = sorted(
     list(_SIGNATURES)
-    + ["aph_abi_version", "aph_last_error", "aph_launch_count", "aph_reset_launch_count", "aph_set_pdl", "aph_set_gemm_tail_split", "aph_word_error_rate"]
+    + ["aph_abi_version", "aph_last_error", "aph_launch_count", "aph_reset_launch_count", "aph_set_pdl", "aph_set_gemm_tail_split", "aph_set_attention_kernel", "aph_word_error_rate"]
     + ["aph_edit_operations", "aph_edit_weighted", "aph_segmenter_create", "aph_segmenter_free", "aph_segmenter_find"]
 )
 
@@ -215,6 +215,8 @@ def _load() -> ctypes.CDLL:
     lib.aph_set_pdl.restype = c_int
     lib.aph_set_gemm_tail_split.argtypes = [c_int]
     lib.aph_set_gemm_tail_split.restype = c_int
+    lib.aph_set_attention_kernel.argtypes = [c_int]
+    lib.aph_set_attention_kernel.restype = c_int
     lib.aph_word_error_rate.argtypes = [ctypes.c_uint64] * 4
     lib.aph_word_error_rate.restype = c_float
     lib.aph_edit_operations.argtypes = [_P, _I64, _P, _I64, _P, _P]

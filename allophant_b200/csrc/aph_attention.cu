@@ -52,6 +52,9 @@ struct AttParams {
   float drop_scale;
 };
 
+// 0 = by problem size, 1 = the 64-key kernel, 2 = the persistent pair kernel (aph_set_attention_kernel, APH_ATT_V1=1 / 0)
+static std::atomic<int> g_attention_mode{0};
+
 // Debug timeline (device buffer set through aph_debug_set_timeline; NULL in production): clock64 stamps of CTA (0,0)
 __device__ long long* g_timeline = nullptr;
 #define APH_STAMP(slot)                                                                       \
@@ -878,6 +881,12 @@ __global__ void __launch_bounds__(kPairThreads, 1)
 
 }  // namespace aph
 
+extern "C" int aph_set_attention_kernel(int mode) {
+  const int before = aph::g_attention_mode.load();
+  if (mode >= 0 && mode <= 2) aph::g_attention_mode.store(mode);
+  return before;
+}
+
 extern "C" int aph_debug_set_timeline(int64_t* device_buffer) {
   long long* ptr = reinterpret_cast<long long*>(device_buffer);
   APH_CUDA_CHECK(cudaMemcpyToSymbol(aph::g_timeline, &ptr, sizeof(ptr)));
@@ -932,8 +941,7 @@ extern "C" int aph_attention_bf16_dropout(const void* q, const void* k, const vo
     if (rc != APH_OK) return rc;
   }
   static int sm_count = 0;
-  static int pair_skew = kPairSkewCycles;
-  static bool use_blocks_of_64 = false;  // APH_ATT_V1=1: the 64-key, two-CTAs-per-SM kernel (kept for same-box comparisons)
+  static int pair_skew = kPairSkewCycles;  // APH_ATT_V1=1: the 64-key, two-CTAs-per-SM kernel (kept for same-box comparisons)
   if (sm_count == 0) {
     int device = 0;
     APH_CUDA_CHECK(cudaGetDevice(&device));
@@ -944,7 +952,7 @@ extern "C" int aph_attention_bf16_dropout(const void* q, const void* k, const vo
     APH_CUDA_CHECK(cudaFuncSetAttribute(attention_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
     APH_CUDA_CHECK(cudaFuncSetAttribute(attention_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
     const char* v1 = getenv("APH_ATT_V1");
-    use_blocks_of_64 = v1 != nullptr && v1[0] == '1';
+    if (v1 != nullptr && (v1[0] == '0' || v1[0] == '1') && g_attention_mode.load() == 0) g_attention_mode.store(v1[0] == '1' ? 1 : 2);
     const char* skew = getenv("APH_ATT_SKEW");
     if (skew != nullptr) pair_skew = atoi(skew);
     sm_count = count;
@@ -958,6 +966,11 @@ extern "C" int aph_attention_bf16_dropout(const void* q, const void* k, const vo
   p.drop_threshold = drop_threshold;
   p.drop_seed = drop_seed;
   p.drop_scale = drop_scale;
+  // 64-key blocks with two CTAs per SM while every persistent CTA would get at most one item (a single utterance: 8.4 us against
+  // 11.8), the persistent pair kernel beyond; aph_set_attention_kernel / APH_ATT_V1 force one of them
+  const int mode = g_attention_mode.load();
+  const uint64_t pair_items = nh * static_cast<uint64_t>(ceil_div(T, 2 * kAttQ));
+  const bool use_blocks_of_64 = mode == 1 || (mode == 0 && pair_items <= static_cast<uint64_t>(sm_count));
   if (use_blocks_of_64) {
     dim3 grid(ceil_div(T, kAttQ), static_cast<unsigned>(nh));
     if (drop_threshold != 0)

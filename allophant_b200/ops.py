@@ -61,6 +61,12 @@ def set_gemm_tail_split(enabled: bool) -> bool:
     return bool(lib.aph_set_gemm_tail_split(1 if enabled else 0))
 
 
+def set_attention_kernel(mode: int) -> int:
+    """Which attention forward kernel runs: 0 = chosen by problem size (default), 1 = 64-key blocks with two CTAs per SM, 2 = the
+    persistent query-tile-pair kernel (``aph_set_attention_kernel``).  Returns the previous setting."""
+    return int(lib.aph_set_attention_kernel(int(mode)))
+
+
 # --------------------------------------------------------------------------------------
 # GEMM
 # --------------------------------------------------------------------------------------

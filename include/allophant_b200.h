@@ -47,6 +47,11 @@ int aph_set_pdl(int enabled);
  * element accumulates the same products in the same order).  On by default, APH_GEMM_TAIL_SPLIT=0 or this call turn it
  * off; returns the previous setting.  No reference counterpart. */
 int aph_set_gemm_tail_split(int enabled);
+/* Which kernel aph_attention_bf16* launches: 0 = by problem size (the default: 64-key blocks with two CTAs per SM while a
+ * persistent CTA would get at most one (utterance, head, query-tile pair) item, the persistent query-tile-pair kernel beyond),
+ * 1 = always the 64-key kernel, 2 = always the pair kernel (APH_ATT_V1=1 / APH_ATT_V1=0 in the environment).  Returns the
+ * previous setting; results agree within the tolerances of the tests.  No reference counterpart. */
+int aph_set_attention_kernel(int mode);
 
 /* ---- tensor-core GEMM (tcgen05 + TMEM accumulators, TMA-fed) ------------- */
 /* One kernel serves every dense contraction of the path:

@@ -256,8 +256,17 @@ def test_gemm_qkv_scatter_epilogue():
 
 
 # ------------------------------------------------------------------------------------------ attention
+@pytest.fixture(params=[1, 2], ids=["blocks_of_64", "tile_pairs"])
+def attention_kernel(request):
+    """Both forward kernels on every shape (by default the library picks by problem size: ops.set_attention_kernel)."""
+    ops = _ops()
+    before = ops.set_attention_kernel(request.param)
+    yield request.param
+    ops.set_attention_kernel(before)
+
+
 @pytest.mark.parametrize("n,heads,frames,lengths", [(1, 1, 128, [128]), (2, 16, 499, [499, 300]), (3, 4, 749, [749, 1, 130]), (1, 2, 1499, [1000])])
-def test_attention(n, heads, frames, lengths):
+def test_attention(n, heads, frames, lengths, attention_kernel):
     ops = _ops()
     torch.manual_seed(frames)
     q = torch.randn(n, heads, frames, 64, device=DEV).bfloat16()
@@ -316,7 +325,7 @@ def test_multi_head_block_kernels_match_torch():
     assert float((mixed[1] - torch.log_softmax(torch.randn(3, 4, 5, device=DEV) * 0 + mixed[1].exp().log(), -1)).abs().max()) < 1e-5
 
 
-def test_attention_ragged_batches_on_the_persistent_schedule():
+def test_attention_ragged_batches_on_the_persistent_schedule(attention_kernel):
     """Batches as a MaxFrameBatchSampler stream produces them (many utterances of very different lengths, frames padded to a
     multiple of 64): every persistent CTA works through a long list of items that mixes full query-tile pairs, pairs whose second
     tile is padding only (its MMA issuer still walks the ring barriers: skipping ahead aliases mbarrier parities and once hung the
@@ -348,7 +357,7 @@ def test_attention_ragged_batches_on_the_persistent_schedule():
 
 
 @pytest.mark.parametrize("sharpness", [8.0, 40.0])
-def test_attention_large_scores_exercise_lazy_rescaling(sharpness):
+def test_attention_large_scores_exercise_lazy_rescaling(sharpness, attention_kernel):
     """Peaked score distributions (row maxima that keep growing by more than 2^8 from block to block) exercise the
     in-TMEM rescaling of the running output and its barrier protocol; many CTAs run concurrently (warps of one CTA
     drift apart by a block), repeated launches must agree bit for bit."""

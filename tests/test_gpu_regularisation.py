@@ -70,6 +70,15 @@ def test_dropout_kernels_use_the_restated_hash():
     assert ops.Dropout.site(0.0, 1, 1) == ops.NO_DROPOUT
 
 
+@pytest.fixture(params=[1, 2], ids=["blocks_of_64", "tile_pairs"])
+def attention_kernel(request):
+    from allophant_b200 import ops
+
+    before = ops.set_attention_kernel(request.param)
+    yield request.param
+    ops.set_attention_kernel(before)
+
+
 @pytest.mark.parametrize("rows,n,k", [(300, 1024, 1024), (517, 320, 4096)])
 def test_gemm_epilogue_dropout(rows, n, k):
     """out = dropout(A W^T + b) + resid with the mask of (seed, row, col): both fp32-output epilogues."""
@@ -92,7 +101,7 @@ def test_gemm_epilogue_dropout(rows, n, k):
 
 
 @pytest.mark.parametrize("seq,lengths", [(200, [200, 77]), (131, [131, 1, 64])])
-def test_attention_dropout_forward_and_backward(seq, lengths):
+def test_attention_dropout_forward_and_backward(seq, lengths, attention_kernel):
     ops = _ops()
     torch.manual_seed(seq)
     n_utt, heads, d = len(lengths), 4, 64
