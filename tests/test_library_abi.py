@@ -102,3 +102,32 @@ def test_custom_ops_are_registered_with_fake_kernels():
         assert tokens.shape == (3, 7) and counts.shape == (3,) and scores.shape == (3,)
     with pytest.raises(NotImplementedError):
         torch.ops.allophant_b200.log_softmax(torch.zeros(2, 3))
+
+
+def test_ctypes_mirrors_match_the_header_structs(tmp_path):
+    """The by-value descriptor structs (`aph_ctc_head`, `aph_head_block`, `aph_gemm_args`) are mirrored as ctypes Structures in
+    `_lib.py`: sizes and field offsets are compared with what gcc computes from `include/allophant_b200.h` itself."""
+    import ctypes
+    import re
+    import subprocess
+
+    from allophant_b200 import _lib
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mirrors = {"aph_ctc_head": _lib.CtcHead, "aph_head_block": _lib.HeadBlock, "aph_gemm_args": _lib.GemmArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "allophant_b200.h"', "int main(void) {"]
+    for c_name, mirror in mirrors.items():
+        lines.append(f'  printf("{c_name} size %zu\\n", sizeof({c_name}));')
+        for field, _ in mirror._fields_:
+            lines.append(f'  printf("{c_name} {field} %zu\\n", offsetof({c_name}, {field}));')
+    lines += ["  return 0;", "}"]
+    source = tmp_path / "layout.c"
+    source.write_text("\n".join(lines))
+    binary = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(source), "-o", str(binary)], check=True)
+    output = subprocess.run([str(binary)], check=True, capture_output=True, text=True).stdout
+    for line in output.splitlines():
+        c_name, field, value = re.match(r"(\w+) (\w+) (\d+)", line).groups()
+        mirror = mirrors[c_name]
+        expected = ctypes.sizeof(mirror) if field == "size" else getattr(mirror, field).offset
+        assert int(value) == expected, (c_name, field, value, expected)
